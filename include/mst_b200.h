@@ -1,0 +1,133 @@
+/* mst_b200 -- C ABI of the B200-native Master stylization hot path.
+ *
+ * Plain pointers, sizes and a cudaStream_t (passed as void*); no torch types.  Every function
+ * enqueues work on the given stream, never synchronises the host, never allocates persistent
+ * memory, keeps no global mutable state, and returns
+ *      0  = OK,   <0 = bad argument / unsupported shape,   >0 = a cudaError_t value.
+ *
+ * The reference (uozyurt/MasterMetaStyleTransfer) has no FFI: its boundary is the Python
+ * nn.Module API.  Each entry point therefore cites the reference
+ * function whose arithmetic it replaces; INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add.
+ *
+ * Layout conventions: activations are token-major [B,H,W,C] ("BHWC", exactly the layout
+ * codes/style_transformer.py works in); bf16 = IEEE bfloat16 stored as uint16_t.
+ */
+#ifndef MST_B200_H
+#define MST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t mst_bf16;
+
+#define MST_OK 0
+#define MST_ERR_BAD_ARG (-1)
+#define MST_ERR_UNSUPPORTED (-2)
+
+/* library version (major*10000 + minor*100 + patch) and the SM architecture it was compiled for */
+int mst_version(void);
+int mst_sm_arch(void);
+const char* mst_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing.  nn.Linear weight [N,K] fp32 (codes/style_transformer.py:206-213) and
+ * nn.Conv2d weight [N,Cin,3,3] fp32 (codes/decoder.py:23-55, torchvision vgg19) are converted
+ * to the bf16 [n_pad, k_pad] K-contiguous operand the tensor-core GEMM streams; conv k index is
+ * (ky*3+kx)*Cin + ci.  Rows >= N and columns >= K are zero.
+ * ------------------------------------------------------------------------------------------ */
+int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* dst, int n_pad, int k_pad, void* stream);
+int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n_pad, int k_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core GEMM with gathered A operand and fused epilogue (tcgen05.mma, fp32 accum in TMEM).
+ *     acc[m,n] = sum_k A(m,k) * Wt[n,k]
+ *     x = act(acc + bias[n]);  x = mul ? res*mul + x : (res ? res + x : x);  store fp32 / bf16
+ * a_mode MST_A_PLAIN:   A(m,k) = A[m*lda + k]                       (F.linear, style_transformer.py:114-116,156)
+ * a_mode MST_A_CONV3X3: A(m,k) = in[b, pad(y+ky-1), pad(x+kx-1), ci] (Conv2d 3x3 stride 1;
+ *                       pad_mode 0 = zeros (vgg19), 1 = reflect (codes/decoder.py:24);
+ *                       upsample=1 folds nn.Upsample(2,'nearest') (decoder.py:27) into the read:
+ *                       the stored input is [B,H/2,W/2,Cin]).  m = (b*H + y)*W + x.
+ * ------------------------------------------------------------------------------------------ */
+enum { MST_A_PLAIN = 0, MST_A_CONV3X3 = 1 };
+enum { MST_ACT_NONE = 0, MST_ACT_RELU = 1, MST_ACT_GELU = 2 };
+
+typedef struct MstGemm {
+  const mst_bf16* A; /* bf16 activations */
+  const mst_bf16* Wt; /* packed weights [n_pad, k_pad] */
+  const float* bias;  /* [N] or NULL */
+  const float* res;   /* fp32 [M, ld_res] or NULL (may alias out_f32) */
+  const float* mul;   /* fp32 [M, ld_res] or NULL: out = res*mul + x (Query*sigma+mu, style_transformer.py:1123) */
+  float* out_f32;     /* fp32 [M, ld_out32] or NULL */
+  mst_bf16* out_bf16; /* bf16 [M, ld_out16] or NULL */
+  int M, N, K;        /* logical sizes; N % 16 == 0 after packing; K is the un-padded reduction length */
+  int k_pad;          /* row stride of Wt, multiple of 64 */
+  int lda, ld_res, ld_out32, ld_out16;
+  int a_mode, act;
+  int H, W, Cin, pad_mode, upsample; /* MST_A_CONV3X3 geometry (H,W = output = padded-input size) */
+  int out_nchw;       /* 1: out_f32 is [B, n_real, H, W] (final decoder conv, decoder.py:54) */
+  int n_real;         /* channels actually stored when out_nchw (<= N) */
+} MstGemm;
+
+int mst_gemm(const MstGemm* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused shifted-window attention core: roll + window partition folded into the loads, QK^T,
+ * relative-position bias, 9-region shift mask, softmax, PV, window reverse + roll back folded into
+ * the store (codes/style_transformer.py:83-111,127-168; with v2/out2 set it is the shared-softmax
+ * sigma/mu core of :544-607).  q,k,v are the already projected bf16 token-major tensors (row
+ * strides ldq/ldk/ldv elements, so slices of a fused qkv buffer work); q is scaled by
+ * head_dim^-0.5 inside.  pad_q/pad_k/pad_v ([C] fp32 or NULL) are the values a zero-padded
+ * token takes after its projection (= the bias, :83-85,114-116); needed when H or W is not a
+ * multiple of ws.  head_dim must be 32; ws in {7, 8}.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MstWindowAttn {
+  const mst_bf16 *q, *k, *v, *v2;
+  mst_bf16 *out, *out2;
+  const float* bias_table; /* [(2ws-1)^2, heads] fp32 */
+  const float *pad_q, *pad_k, *pad_v, *pad_v2;
+  int B, H, W, heads, ws, shift;
+  int ldq, ldk, ldv, ldo;
+} MstWindowAttn;
+
+int mst_window_attention(const MstWindowAttn* a, void* stream);
+
+/* integer maps the attention kernel uses, exported for the bit-exact parity tests
+ * (gather: [nW, ws*ws] int32 = y*W+x or -1 for padding; labels: [nW, ws*ws] int32;
+ *  relidx: [ws^4] int32).  Device pointers. */
+int mst_window_maps(int H, int W, int ws, int shift, int32_t* gather, int32_t* labels, int32_t* relidx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalisations.
+ * mst_layernorm: nn.LayerNorm(C) eps 1e-5 over the last dim, fp32 in -> bf16 out
+ *   (style_transformer.py:340-343,390-392; tv swin blocks).  C in {128,256,512}.
+ * mst_patch_merge_layernorm: tv _patch_merging_pad + LayerNorm(4C): x [B,H,W,C] fp32 ->
+ *   [B,H/2,W/2,4C] bf16 (H, W even).
+ * mst_instnorm_stats: nn.InstanceNorm2d(C, affine=False) statistics of x [B,T,C] fp32 over T
+ *   (style_transformer.py:468,526,1056-1057): mean[B,C], rstd[B,C].  twice=1 returns the
+ *   combined scale of IN(IN(x)) (the reference normalises the query twice, :1056 then :468).
+ * mst_instnorm_apply: y = (x-mean)*rstd -> bf16 and/or fp32.
+ * ------------------------------------------------------------------------------------------ */
+int mst_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int rows, int C, void* stream);
+int mst_patch_merge_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int B, int H, int W,
+                              int C, void* stream);
+int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream);
+int mst_instnorm_apply(const float* x, const float* mean, const float* rstd, mst_bf16* y16, float* y32, int B, int T,
+                       int C, void* stream);
+
+/* Swin patch embedding: Conv2d(3,128,4,stride 4) + permute + LayerNorm(128) (tv swin features[0]):
+ * img [B,3,S,S] fp32 NCHW -> x [B,S/4,S/4,128] fp32. */
+int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x,
+                    int B, int S, void* stream);
+
+/* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
+int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MST_B200_H */

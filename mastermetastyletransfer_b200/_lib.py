@@ -1,0 +1,84 @@
+"""ctypes binding of libmst_b200.so (the C ABI declared in include/mst_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, this
+raises.  The library is built in-tree by ``__graft_entry__.build()`` / ``csrc/build.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmst_b200.so")
+
+c_bf16_p = C.c_void_p
+c_f32_p = C.c_void_p
+
+
+class MstGemm(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("Wt", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("mul", C.c_void_p),
+        ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("k_pad", C.c_int),
+        ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int),
+        ("a_mode", C.c_int), ("act", C.c_int),
+        ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("pad_mode", C.c_int), ("upsample", C.c_int),
+        ("out_nchw", C.c_int), ("n_real", C.c_int),
+    ]
+
+
+class MstWindowAttn(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("v2", C.c_void_p),
+        ("out", C.c_void_p), ("out2", C.c_void_p), ("bias_table", C.c_void_p),
+        ("pad_q", C.c_void_p), ("pad_k", C.c_void_p), ("pad_v", C.c_void_p), ("pad_v2", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("heads", C.c_int), ("ws", C.c_int), ("shift", C.c_int),
+        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
+    ]
+
+
+# every symbol include/mst_b200.h declares: name -> (restype, argtypes)
+_I, _P, _Z = C.c_int, C.c_void_p, C.c_size_t
+SYMBOLS = {
+    "mst_version": (_I, []),
+    "mst_sm_arch": (_I, []),
+    "mst_error_string": (C.c_char_p, [_I]),
+    "mst_pack_linear_weight": (_I, [_P, _I, _I, _P, _I, _I, _P]),
+    "mst_pack_conv3x3_weight": (_I, [_P, _I, _I, _P, _I, _I, _P]),
+    "mst_gemm": (_I, [C.POINTER(MstGemm), _P]),
+    "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
+    "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "mst_patch_merge_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mst_instnorm_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mst_instnorm_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the hot path).")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError here = header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    msg = lib().mst_error_string(code).decode()
+    if code < 0:
+        raise ValueError(f"{what}: {msg} ({code})")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")

@@ -1,0 +1,177 @@
+// Shared device helpers for the sm_100a kernels: mbarrier / cp.async / tcgen05 / TMEM PTX wrappers
+// and the window-index arithmetic that every kernel (and the map-export test hook) uses.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mst {
+
+typedef __nv_bfloat16 bf16;
+
+#define MST_DEVINL __device__ __forceinline__
+
+MST_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- mbarrier
+MST_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+MST_DEVINL void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MST_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+MST_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a launch failure) instead of a hung GPU.
+MST_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mst: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- cp.async (LDGSTS) with zero fill
+MST_DEVINL void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+MST_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+MST_DEVINL void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+MST_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+MST_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+MST_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+MST_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+MST_DEVINL void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+MST_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, issued by ONE thread
+MST_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all tcgen05 ops previously issued by this thread have completed
+MST_DEVINL void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+MST_DEVINL void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i)
+MST_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024 B between
+// 8-row groups, [46,48) version=1 (sm_100), [61,64) layout type 2 = SWIZZLE_128B.
+MST_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (bit 4), a=b=bf16 (bits 7,10),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SW128 K-major tile
+MST_DEVINL uint32_t sw128_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// ---------------------------------------------------------------- window index arithmetic (integer, bit-exact)
+// Follows codes/style_transformer.py:77-111 (pad -> clamp shift -> roll(-s) -> partition) and :134-147 (mask labels).
+struct WinGeom {
+  int H, W;      // un-padded feature map
+  int Hp, Wp;    // padded to a multiple of ws
+  int ws;        // window side
+  int sy, sx;    // effective shift (0 when the window covers the padded axis)
+  int nwx, nW;   // windows per row / per image
+};
+__host__ __device__ inline WinGeom make_geom(int H, int W, int ws, int shift) {
+  WinGeom g;
+  g.H = H; g.W = W; g.ws = ws;
+  g.Hp = H + (ws - H % ws) % ws;
+  g.Wp = W + (ws - W % ws) % ws;
+  g.sy = ws >= g.Hp ? 0 : shift;
+  g.sx = ws >= g.Wp ? 0 : shift;
+  g.nwx = g.Wp / ws;
+  g.nW = (g.Hp / ws) * g.nwx;
+  return g;
+}
+// slot (win, tok) -> source (y, x) on the padded un-rolled grid; y >= H or x >= W means zero padding
+__host__ __device__ inline void win_source(const WinGeom& g, int win, int tok, int& y, int& x) {
+  const int wy = win / g.nwx, wx = win - wy * g.nwx;
+  const int iy = tok / g.ws, ix = tok - iy * g.ws;
+  y = wy * g.ws + iy + g.sy; if (y >= g.Hp) y -= g.Hp;
+  x = wx * g.ws + ix + g.sx; if (x >= g.Wp) x -= g.Wp;
+}
+__host__ __device__ inline int win_band(int p, int size, int ws, int s) {
+  if (s == 0) return 2;
+  if (p >= size - s) return 2;
+  return p >= size - ws ? 1 : 0;
+}
+// region label of slot (win, tok) on the rolled grid; only differences of labels are ever used
+__host__ __device__ inline int win_label(const WinGeom& g, int win, int tok) {
+  const int wy = win / g.nwx, wx = win - wy * g.nwx;
+  const int iy = tok / g.ws, ix = tok - iy * g.ws;
+  return 3 * win_band(wy * g.ws + iy, g.Hp, g.ws, g.sy) + win_band(wx * g.ws + ix, g.Wp, g.ws, g.sx);
+}
+__host__ __device__ inline int rel_pos_index(int i, int j, int ws) {
+  const int yi = i / ws, xi = i - yi * ws, yj = j / ws, xj = j - yj * ws;
+  return (yi - yj + ws - 1) * (2 * ws - 1) + (xi - xj + ws - 1);
+}
+
+MST_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+MST_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+MST_DEVINL float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace mst

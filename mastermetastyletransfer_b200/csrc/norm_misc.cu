@@ -1,0 +1,280 @@
+// HBM-streaming kernels around the tensor-core path: LayerNorm (+ the Swin patch-merging gather),
+// InstanceNorm statistics / apply, Swin patch embedding, weight packing, fp32 -> bf16 casts.
+#include "../../include/mst_b200.h"
+#include "common.cuh"
+
+namespace mst {
+
+// ---------------------------------------------------------------- LayerNorm: one warp per row
+// PER = C / 32 values per lane, lane-strided by float4 so global reads are 512 B coalesced per warp.
+template <int C, bool MERGE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ y, int rows,
+                                                        int H, int W) {
+  constexpr int V4 = C / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float4 v[V4];
+  if (!MERGE) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)warp * C);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) v[i] = xr[lane + 32 * i];
+  } else {
+    // tv _patch_merging_pad: out[b,y2,x2,:] = cat(x[2y2,2x2], x[2y2+1,2x2], x[2y2,2x2+1], x[2y2+1,2x2+1])
+    constexpr int Cs = C / 4;  // source channels
+    const int W2 = W >> 1, H2 = H >> 1;
+    const int b = warp / (H2 * W2);
+    const int rem = warp - b * (H2 * W2);
+    const int y2 = rem / W2, x2 = rem - y2 * W2;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      const int e = (lane + 32 * i) * 4;  // element index in the 4C row
+      const int part = e / Cs, ch = e - part * Cs;
+      const int dy = part & 1, dx = part >> 1;
+      v[i] = *reinterpret_cast<const float4*>(x + (((long long)b * H + 2 * y2 + dy) * W + 2 * x2 + dx) * Cs + ch);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b2 * b2 + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  uint2* yr = reinterpret_cast<uint2*>(y + (long long)warp * C);
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const float4 g = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+    const float4 bt = reinterpret_cast<const float4*>(beta)[lane + 32 * i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w);
+    yr[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+// ---------------------------------------------------------------- InstanceNorm statistics
+// x [B,T,C] fp32.  CTA = (b, 32-channel group); 8 warps stride over T, lane = channel (128 B rows).
+// Two passes (mean, then centred second moment) as torch's InstanceNorm2d does (biased variance).
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
+                                                             float* __restrict__ rstd, int T, int C, int twice) {
+  __shared__ float red[8][33];
+  const int groups = C / 32;
+  const int b = blockIdx.x / groups;
+  const int c = (blockIdx.x - b * groups) * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (long long)b * T * C + c;
+  float s = 0.f;
+  for (int t = warp; t < T; t += 8) s += xb[(long long)t * C];
+  red[warp][lane] = s;
+  __syncthreads();
+  float m = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) m += red[w][lane];
+  m /= (float)T;
+  __syncthreads();
+  float q = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    const float d = xb[(long long)t * C] - m;
+    q += d * d;
+  }
+  red[warp][lane] = q;
+  __syncthreads();
+  if (warp == 0) {
+    float var = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) var += red[w][lane];
+    var /= (float)T;
+    float r = 1.0f / sqrtf(var + 1e-5f);
+    if (twice) {
+      // IN(IN(x)): the once-normalised tensor has mean 0 and variance var*r^2, so the second pass
+      // multiplies by 1/sqrt(var*r^2 + eps) (codes/style_transformer.py:1056 then :468)
+      r *= 1.0f / sqrtf(var * r * r + 1e-5f);
+    }
+    mean[(long long)b * C + c] = m;
+    rstd[(long long)b * C + c] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, bf16* __restrict__ y16,
+                                                             float* __restrict__ y32, long long n4, int TC4, int C4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int b = (int)(i / TC4);
+  const int c4 = (int)(i % C4);
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  const float4 m = reinterpret_cast<const float4*>(mean)[(long long)b * C4 + c4];
+  const float4 r = reinterpret_cast<const float4*>(rstd)[(long long)b * C4 + c4];
+  const float4 o = make_float4((v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w);
+  if (y32) reinterpret_cast<float4*>(y32)[i] = o;
+  if (y16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+    reinterpret_cast<uint2*>(y16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+// ---------------------------------------------------------------- Swin patch embedding + LayerNorm(128)
+// One warp per output token; lane owns output channels lane, lane+32, lane+64, lane+96.
+// Weights [128][48] sit in shared memory transposed to [48][128] so lanes read consecutive words.
+__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ out, int B,
+                                                          int S, int tokens_per_cta) {
+  __shared__ float ws[48 * 128];
+  for (int i = threadIdx.x; i < 48 * 128; i += blockDim.x) {
+    const int k = i / 128, n = i - k * 128;
+    ws[i] = w[n * 48 + k];  // conv weight [128][3][4][4] -> k = ci*16 + ky*4 + kx
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = S / 4;
+  const long long total = (long long)B * P * P;
+  const long long first = (long long)blockIdx.x * tokens_per_cta;
+  for (long long tok = first + warp; tok < first + tokens_per_cta && tok < total; tok += 8) {
+    const int b = (int)(tok / (P * P));
+    const int rem = (int)(tok - (long long)b * P * P);
+    const int py = rem / P, px = rem - py * P;
+    // 48 inputs: lanes 0..11 each load one float4 (ci, ky) row of 4 pixels
+    float4 in4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < 12) {
+      const int ci = lane >> 2, ky = lane & 3;
+      in4 = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + ci) * S + py * 4 + ky) * S + px * 4);
+    }
+    float acc[4] = {bias[lane], bias[lane + 32], bias[lane + 64], bias[lane + 96]};
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      const float i0 = __shfl_sync(0xffffffffu, in4.x, r), i1 = __shfl_sync(0xffffffffu, in4.y, r);
+      const float i2 = __shfl_sync(0xffffffffu, in4.z, r), i3 = __shfl_sync(0xffffffffu, in4.w, r);
+      const float* wr = ws + (r * 4) * 128 + lane;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        acc[o] = fmaf(i0, wr[o * 32], acc[o]);
+        acc[o] = fmaf(i1, wr[128 + o * 32], acc[o]);
+        acc[o] = fmaf(i2, wr[256 + o * 32], acc[o]);
+        acc[o] = fmaf(i3, wr[384 + o * 32], acc[o]);
+      }
+    }
+    const float mean = warp_sum(acc[0] + acc[1] + acc[2] + acc[3]) * (1.0f / 128.f);
+    float q = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) q += (acc[o] - mean) * (acc[o] - mean);
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 128.f) + 1e-5f);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int n = lane + 32 * o;
+      out[tok * 128 + n] = (acc[o] - mean) * rstd * gamma[n] + beta[n];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- packing / casts
+__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, bf16* __restrict__ dst, int n_pad, int k_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pad * k_pad) return;
+  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
+  dst[i] = __float2bfloat16((n < N && k < K) ? w[(long long)n * K + k] : 0.f);
+}
+__global__ void pack_conv_kernel(const float* __restrict__ w, int N, int Cin, bf16* __restrict__ dst, int n_pad, int k_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pad * k_pad) return;
+  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
+  float v = 0.f;
+  if (n < N && k < 9 * Cin) {
+    const int tap = k / Cin, ci = k - tap * Cin;
+    v = w[((long long)n * Cin + ci) * 9 + tap];  // [N][Cin][3][3] -> tap = ky*3+kx
+  }
+  dst[i] = __float2bfloat16(v);
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  reinterpret_cast<uint2*>(y)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" int mst_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int rows, int C, void* stream) {
+  if (!x || !gamma || !beta || !y || rows <= 0) return MST_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (rows + 7) / 8;
+  bf16* yy = reinterpret_cast<bf16*>(y);
+  if (C == 128) layernorm_kernel<128, false><<<blocks, 256, 0, st>>>(x, gamma, beta, yy, rows, 0, 0);
+  else if (C == 256) layernorm_kernel<256, false><<<blocks, 256, 0, st>>>(x, gamma, beta, yy, rows, 0, 0);
+  else if (C == 512) layernorm_kernel<512, false><<<blocks, 256, 0, st>>>(x, gamma, beta, yy, rows, 0, 0);
+  else return MST_ERR_UNSUPPORTED;
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_patch_merge_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int B, int H,
+                                         int W, int C, void* stream) {
+  if (!x || !gamma || !beta || !y || B <= 0 || H <= 0 || W <= 0) return MST_ERR_BAD_ARG;
+  if ((H | W) & 1) return MST_ERR_UNSUPPORTED;
+  if (C != 128) return MST_ERR_UNSUPPORTED;
+  const int rows = B * (H / 2) * (W / 2);
+  layernorm_kernel<512, true><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, reinterpret_cast<bf16*>(y), rows, H, W);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream) {
+  if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0) return MST_ERR_BAD_ARG;
+  instnorm_stats_kernel<<<B * (C / 32), 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_instnorm_apply(const float* x, const float* mean, const float* rstd, mst_bf16* y16, float* y32, int B,
+                                  int T, int C, void* stream) {
+  if (!x || !mean || !rstd || (!y16 && !y32) || B <= 0 || T <= 0 || C <= 0 || C % 4 != 0) return MST_ERR_BAD_ARG;
+  const long long n4 = (long long)B * T * C / 4;
+  instnorm_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, mean, rstd, reinterpret_cast<bf16*>(y16), y32, n4, T * C / 4, C / 4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta,
+                               float* x, int B, int S, void* stream) {
+  if (!img || !w || !b || !gamma || !beta || !x || B <= 0 || S <= 0 || S % 4 != 0) return MST_ERR_BAD_ARG;
+  const long long total = (long long)B * (S / 4) * (S / 4);
+  const int per = 64;
+  patch_embed_kernel<<<(unsigned)((total + per - 1) / per), 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, B, S, per);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
+  if (!w || !dst || N <= 0 || K <= 0 || n_pad < N || k_pad < K) return MST_ERR_BAD_ARG;
+  const long long n = (long long)n_pad * k_pad;
+  pack_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, reinterpret_cast<bf16*>(dst), n_pad, k_pad);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
+  if (!w || !dst || N <= 0 || Cin <= 0 || n_pad < N || k_pad < 9 * Cin) return MST_ERR_BAD_ARG;
+  const long long n = (long long)n_pad * k_pad;
+  pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, Cin, reinterpret_cast<bf16*>(dst), n_pad, k_pad);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream) {
+  if (!x || !y || n == 0 || n % 4 != 0) return MST_ERR_BAD_ARG;
+  const size_t n4 = n / 4;
+  cast_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<bf16*>(y), n4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_version(void) { return 100; }
+extern "C" int mst_sm_arch(void) { return 100; }
+extern "C" const char* mst_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == MST_ERR_BAD_ARG) return "bad argument";
+  if (code == MST_ERR_UNSUPPORTED) return "unsupported shape";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}

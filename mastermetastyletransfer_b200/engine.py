@@ -1,0 +1,276 @@
+"""Forward engine of the stylization hot path: sequences the C-ABI kernels over pre-allocated
+HBM buffers.  The nn.Module mirrors in this package (full_model.py, style_transformer.py,
+decoder.py) own the parameters; this file only reads them (packed once per parameter version).
+
+Data layout in HBM: every activation is token-major [B*H*W, C]; the residual
+stream of each sub-network is fp32, every tensor-core A operand is a bf16 copy written by the
+producing kernel's epilogue.  Window partition / cyclic shift are never materialised: they are
+address arithmetic inside the attention kernel.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, PAD_REFLECT, PackedMatrix
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class Workspace:
+    """Named, lazily created, shape-checked device buffers (PyTorch's caching allocator owns the memory)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype) -> torch.Tensor:
+        t = self.bufs.get(name)
+        n = 1
+        for s in shape:
+            n *= s
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t[:n].view(*shape)
+
+    def bf16(self, name, *shape):
+        return self.get(name, shape, torch.bfloat16)
+
+    def f32(self, name, *shape):
+        return self.get(name, shape, torch.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# Swin-B first two stages (reference: codes/utils.py:59-102 slice of torchvision swin_b;
+# arithmetic tv swin_transformer.py:116-220,35-87,401-456)
+# --------------------------------------------------------------------------------------------
+
+
+class SwinEncoderWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
+        g = lambda k: _f32(sd[prefix + k])
+        self.pe_w, self.pe_b = g("0.0.weight"), g("0.0.bias")
+        self.pe_g, self.pe_beta = g("0.2.weight"), g("0.2.bias")
+        self.blocks = {}
+        for name, heads in (("1.0", 4), ("1.1", 4), ("3.0", 8), ("3.1", 8)):
+            p = name + "."
+            qkv_b = g(p + "attn.qkv.bias")
+            C = qkv_b.numel() // 3
+            self.blocks[name] = dict(
+                heads=heads, C=C,
+                n1w=g(p + "norm1.weight"), n1b=g(p + "norm1.bias"), n2w=g(p + "norm2.weight"), n2b=g(p + "norm2.bias"),
+                qkv=ops.pack_linear(g(p + "attn.qkv.weight"), qkv_b),
+                pad_q=qkv_b[:C].contiguous(), pad_k=qkv_b[C:2 * C].contiguous(), pad_v=qkv_b[2 * C:].contiguous(),
+                proj=ops.pack_linear(g(p + "attn.proj.weight"), g(p + "attn.proj.bias")),
+                table=g(p + "attn.relative_position_bias_table"),
+                fc1=ops.pack_linear(g(p + "mlp.0.weight"), g(p + "mlp.0.bias")),
+                fc2=ops.pack_linear(g(p + "mlp.3.weight"), g(p + "mlp.3.bias")),
+            )
+        self.pm_g, self.pm_b = g("2.norm.weight"), g("2.norm.bias")
+        self.pm_red = ops.pack_linear(g("2.reduction.weight"), None)
+
+
+def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W: int, shift: int, tag: str):
+    """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place)."""
+    C, heads = bw["C"], bw["heads"]
+    T = Bt * H * W
+    ln = ws_.bf16(tag + "ln", T, C)
+    qkv = ws_.bf16(tag + "qkv", T, 3 * C)
+    o = ws_.bf16(tag + "o", T, C)
+    h = ws_.bf16(tag + "h", T, 4 * C)
+    ops.layernorm(x32, bw["n1w"], bw["n1b"], ln, T, C)
+    ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
+    ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
+                         3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
+    ops.gemm(o, bw["proj"], T, res=x32, out_f32=x32)
+    ops.layernorm(x32, bw["n2w"], bw["n2b"], ln, T, C)
+    ops.gemm(ln, bw["fc1"], T, act=ACT_GELU, out_bf16=h)
+    ops.gemm(h, bw["fc2"], T, res=x32, out_f32=x32)
+
+
+def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor]):
+    """imgs: list of [B,3,S,S] fp32 NCHW tensors (content, style) encoded as one batch.
+    out32: fp32 [sum(B), S/8, S/8, 256]; out16: optional bf16 copy."""
+    Bt = sum(int(i.shape[0]) for i in imgs)
+    P = S // 4
+    x1 = ws_.f32("sw_x1", Bt * P * P, 128)
+    off = 0
+    for img in imgs:
+        b = int(img.shape[0])
+        ops.patch_embed(img, w.pe_w, w.pe_b, w.pe_g, w.pe_beta, x1[off * P * P:], b, S)
+        off += b
+    _swin_block(w.blocks["1.0"], x1, ws_, Bt, P, P, 0, "sw1_")
+    _swin_block(w.blocks["1.1"], x1, ws_, Bt, P, P, 3, "sw1_")
+    P2 = P // 2
+    T2 = Bt * P2 * P2
+    pm = ws_.bf16("sw_pm", T2, 512)
+    ops.patch_merge_layernorm(x1, w.pm_g, w.pm_b, pm, Bt, P, P, 128)
+    x2 = out32.view(T2, 256)
+    ops.gemm(pm, w.pm_red, T2, out_f32=x2)
+    _swin_block(w.blocks["3.0"], x2, ws_, Bt, P2, P2, 0, "sw2_")
+    _swin_block(w.blocks["3.1"], x2, ws_, Bt, P2, P2, 3, "sw2_")
+    if out16 is not None:
+        ops.cast_bf16(x2, out16.view(T2, 256))
+
+
+# --------------------------------------------------------------------------------------------
+# Style transformer (codes/style_transformer.py:777-1245, default flags)
+# --------------------------------------------------------------------------------------------
+
+
+class StyleTransformerWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
+        g = lambda k: _f32(sd[prefix + k])
+
+        def mlp(p):
+            return (ops.pack_linear(g(p + "0.weight"), g(p + "0.bias")), ops.pack_linear(g(p + "3.weight"), g(p + "3.bias")))
+
+        e = "encoder.shared_MHA_without_MLP.attn."
+        wq, wk, wv = g(e + "Wq.weight"), g(e + "Wk.weight"), g(e + "Wv.weight")
+        bq, bk, bv = g(e + "Wq.bias"), g(e + "Wk.bias"), g(e + "Wv.bias")
+        self.C = wq.shape[0]
+        self.enc_qkv = ops.pack_linear(torch.cat([wq, wk, wv], 0), torch.cat([bq, bk, bv], 0))
+        self.enc_qk = ops.pack_linear(torch.cat([wq, wk], 0), torch.cat([bq, bk], 0))
+        self.enc_v = ops.pack_linear(wv, bv)
+        self.enc_pad = (bq, bk, bv)
+        self.enc_proj = ops.pack_linear(g(e + "proj.weight"), g(e + "proj.bias"))
+        self.enc_table = g(e + "relative_position_bias_table")
+        self.mlp_key = mlp("encoder.encoder_MLP_Key.")
+        self.mlp_scale = mlp("encoder.encoder_MLP_Scale.")
+        self.mlp_shift = mlp("encoder.encoder_MLP_Shift.")
+        d = "decoder.MHA_self_attn."
+        self.n1 = (g(d + "norm1.weight"), g(d + "norm1.bias"))
+        self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias"))
+        a = d + "attn."
+        dbq, dbk, dbv = g(a + "Wq.bias"), g(a + "Wk.bias"), g(a + "Wv.bias")
+        self.dec_qkv = ops.pack_linear(torch.cat([g(a + "Wq.weight"), g(a + "Wk.weight"), g(a + "Wv.weight")], 0),
+                                       torch.cat([dbq, dbk, dbv], 0))
+        self.dec_pad = (dbq, dbk, dbv)
+        self.dec_proj = ops.pack_linear(g(a + "proj.weight"), g(a + "proj.bias"))
+        self.dec_table = g(a + "relative_position_bias_table")
+        self.dec_mlp = mlp(d + "mlp.")
+        m = "decoder.decoder_MHA_for_sigma_and_mu."
+        self.sm_k = ops.pack_linear(g(m + "Wk.weight"), g(m + "Wk.bias"))
+        self.sm_vs = ops.pack_linear(g(m + "Wv_scale.weight"), g(m + "Wv_scale.bias"))
+        self.sm_vh = ops.pack_linear(g(m + "Wv_shift.weight"), g(m + "Wv_shift.bias"))
+        self.sm_proj = ops.pack_linear(g(m + "proj.weight"), g(m + "proj.bias"))
+        self.sm_table = g(m + "relative_position_bias_table")
+        self.last_mlp = mlp("decoder.last_MLP.")
+
+
+def _mlp_residual(x16, x32, fc, T, ws_: Workspace, out16):
+    """x32 += fc2(gelu(fc1(x16))) ; optionally refresh the bf16 copy."""
+    h = ws_.bf16("st_h", T, fc[0].n_pad)
+    ops.gemm(x16, fc[0], T, act=ACT_GELU, out_bf16=h)
+    ops.gemm(h, fc[1], T, res=x32, out_f32=x32, out_bf16=out16)
+
+
+def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs32: torch.Tensor, k: int, ws_: Workspace,
+                              B: int, H: int, W: int, win: int, shift: int, heads: int,
+                              out32: torch.Tensor, out16: Optional[torch.Tensor] = None):
+    """Fc, Fs fp32 [B,H,W,C] -> out32 fp32 [B,H,W,C] (+ bf16 copy for the CNN decoder).
+    Follows StyleTransformer.forward (:1229-1245) -> StyleEncoder.forward (:855-882) ->
+    StyleDecoder.forward (:1045-1059,1123-1128)."""
+    if H % win or W % win:
+        raise ValueError("style transformer feature map must be a multiple of the window (7x7 padded path: see DESIGN.md)")
+    C = w.C
+    T = B * H * W
+    key32, scale32, shift32 = ws_.f32("st_key32", T, C), ws_.f32("st_scale32", T, C), ws_.f32("st_shift32", T, C)
+    key16, scale16, shift16 = ws_.bf16("st_key16", T, C), ws_.bf16("st_scale16", T, C), ws_.bf16("st_shift16", T, C)
+    x32 = out32.view(T, C)
+    x16 = out16.view(T, C) if out16 is not None else ws_.bf16("st_x16", T, C)
+    qkv = ws_.bf16("st_qkv", T, 3 * C)
+    vs16, vh16 = ws_.bf16("st_vs", T, C), ws_.bf16("st_vh", T, C)
+    o16, o2_16 = ws_.bf16("st_o", T, C), ws_.bf16("st_o2", T, C)
+    ln16 = ws_.bf16("st_ln", T, C)
+    qhat16, khat16 = ws_.bf16("st_qhat", T, C), ws_.bf16("st_khat", T, C)
+    kk32, sigma32 = ws_.f32("st_kk32", T, C), ws_.f32("st_sigma32", T, C)
+    mean, rstd = ws_.f32("st_mean", B, C), ws_.f32("st_rstd", B, C)
+
+    x32.copy_(fc32.reshape(T, C))
+    key32.copy_(fs32.reshape(T, C))
+    scale32.copy_(key32)
+    shift32.copy_(key32)
+    ops.cast_bf16(key32, key16)
+    scale16.copy_(key16)
+    shift16.copy_(key16)
+
+    for _ in range(k):
+        # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
+        ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
+        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
+        ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
+        _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
+        # Scale / Shift passes: q = k = processed Key (one softmax), v = Scale | Shift, residual from v
+        ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
+        ops.gemm(scale16, w.enc_v, T, out_bf16=vs16)
+        ops.gemm(shift16, w.enc_v, T, out_bf16=vh16)
+        ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
+                             v2=vh16, out2=o2_16)
+        ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
+        _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
+        ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
+        _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
+
+        # ---------------- StyleDecoder ----------------
+        ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
+        ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
+        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
+        ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
+        ops.layernorm(x32, w.n2[0], w.n2[1], ln16, T, C)
+        _mlp_residual(ln16, x32, w.dec_mlp, T, ws_, None)  # x32 = Query
+        # Query is instance-normalised twice (:1056 then :468); Key once before Wk and once after (:1057, :520-530)
+        ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True)
+        ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16)
+        ops.instnorm_stats(key32, mean, rstd, B, H * W, C)
+        ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16)
+        ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
+        ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
+        ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16)
+        ops.gemm(scale16, w.sm_vs, T, out_bf16=vs16)
+        ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
+        ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16)
+        ops.gemm(o16, w.sm_proj, T, out_f32=sigma32)
+        ops.gemm(o2_16, w.sm_proj, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16)  # Query*sigma + mu (:1123)
+        _mlp_residual(x16, x32, w.last_mlp, T, ws_, x16)
+
+
+# --------------------------------------------------------------------------------------------
+# CNN decoder (codes/decoder.py:23-55)
+# --------------------------------------------------------------------------------------------
+
+CNN_LAYOUT = [  # (sequential index, upsample folded into this conv's read, relu)
+    (0, False, True), (3, True, True), (5, False, True), (7, False, True), (9, False, True),
+    (12, True, True), (14, False, True), (17, True, True), (19, False, False)]
+
+
+class CnnDecoderWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = "decoder."):
+        self.convs = []
+        for idx, up, relu in CNN_LAYOUT:
+            wt = _f32(sd[f"{prefix}{idx}.weight"])
+            self.convs.append((ops.pack_conv3x3(wt, _f32(sd[f"{prefix}{idx}.bias"])), int(wt.shape[1]), up, relu))
+
+
+def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace, B: int, H: int, W: int, out: torch.Tensor):
+    """x16 bf16 [B,H,W,256] token-major -> out fp32 [B,3,8H,8W] NCHW."""
+    cur = x16
+    h, wd = H, W
+    last = len(w.convs) - 1
+    for i, (pm, cin, up, relu) in enumerate(w.convs):
+        if up:
+            h, wd = 2 * h, 2 * wd
+        M = B * h * wd
+        conv = dict(H=h, W=wd, Cin=cin, pad_mode=PAD_REFLECT, upsample=up)
+        if i == last:
+            conv.update(out_nchw=True, n_real=pm.N)
+            ops.gemm(cur, pm, M, act=ACT_NONE, out_f32=out, conv=conv)
+        else:
+            nxt = ws_.bf16(f"cnn_{i % 2}", M, pm.n_pad)
+            ops.gemm(cur, pm, M, act=ACT_RELU if relu else ACT_NONE, out_bf16=nxt, conv=conv)
+            cur = nxt

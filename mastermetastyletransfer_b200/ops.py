@@ -1,0 +1,197 @@
+"""Thin torch-tensor wrappers over the C ABI (raw device pointers + the current CUDA stream).
+
+PyTorch is used here only for device memory and streams.  Every wrapper checks dtype, device
+and contiguity and raises instead of falling back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MstGemm, MstWindowAttn, check
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+A_PLAIN, A_CONV3X3 = 0, 1
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+# number of kernels this process has enqueued through the C ABI (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def n_pad_of(n: int) -> int:
+    return round_up(n, 16)
+
+
+class PackedMatrix:
+    """bf16 [n_pad, k_pad] tensor-core operand plus the fp32 bias padded to n_pad."""
+
+    __slots__ = ("w", "bias", "N", "K", "n_pad", "k_pad")
+
+    def __init__(self, w, bias, N, K, n_pad, k_pad):
+        self.w, self.bias, self.N, self.K, self.n_pad, self.k_pad = w, bias, N, K, n_pad, k_pad
+
+
+def _pad_bias(bias: Optional[torch.Tensor], n_pad: int, device) -> Optional[torch.Tensor]:
+    if bias is None:
+        return None
+    out = torch.zeros(n_pad, dtype=torch.float32, device=device)
+    out[: bias.numel()].copy_(bias.detach().reshape(-1))
+    return out
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedMatrix:
+    """nn.Linear weight [N,K] fp32 -> PackedMatrix (several weights may be concatenated along N first)."""
+    global launch_count
+    w = weight.detach().contiguous()
+    N, K = w.shape
+    n_pad, k_pad = n_pad_of(N), round_up(K, 64)
+    dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
+    check(_lib.lib().mst_pack_linear_weight(_ptr(w, torch.float32, "weight"), N, K, dst.data_ptr(), n_pad, k_pad, _stream()),
+          "mst_pack_linear_weight")
+    launch_count += 1
+    return PackedMatrix(dst, _pad_bias(bias, n_pad, w.device), N, K, n_pad, k_pad)
+
+
+def pack_conv3x3(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedMatrix:
+    """nn.Conv2d weight [N,Cin,3,3] fp32 -> PackedMatrix with k = (ky*3+kx)*Cin + ci."""
+    global launch_count
+    w = weight.detach().contiguous()
+    N, Cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError("pack_conv3x3: expected a 3x3 kernel")
+    n_pad, k_pad = n_pad_of(N), round_up(9 * Cin, 64)
+    dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
+    check(_lib.lib().mst_pack_conv3x3_weight(_ptr(w, torch.float32, "weight"), N, Cin, dst.data_ptr(), n_pad, k_pad, _stream()),
+          "mst_pack_conv3x3_weight")
+    launch_count += 1
+    return PackedMatrix(dst, _pad_bias(bias, n_pad, w.device), N, 9 * Cin, n_pad, k_pad)
+
+
+def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None, act: int = ACT_NONE,
+         res: Optional[torch.Tensor] = None, mul: Optional[torch.Tensor] = None,
+         out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
+         ld_out32: Optional[int] = None, ld_out16: Optional[int] = None, ld_res: Optional[int] = None,
+         conv: Optional[dict] = None, n_rows: Optional[int] = None) -> None:
+    """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h)."""
+    global launch_count
+    g = MstGemm()
+    g.A = _ptr(A, torch.bfloat16, "A")
+    g.Wt = pm.w.data_ptr()
+    g.bias = _ptr(pm.bias, torch.float32, "bias")
+    g.res = _ptr(res, torch.float32, "res")
+    g.mul = _ptr(mul, torch.float32, "mul")
+    g.out_f32 = _ptr(out_f32, torch.float32, "out_f32")
+    g.out_bf16 = _ptr(out_bf16, torch.bfloat16, "out_bf16")
+    N = pm.n_pad if n_rows is None else n_rows
+    g.M, g.N, g.K, g.k_pad = M, N, pm.K, pm.k_pad
+    g.lda = pm.K if lda is None else lda
+    g.ld_res = N if ld_res is None else ld_res
+    g.ld_out32 = N if ld_out32 is None else ld_out32
+    g.ld_out16 = N if ld_out16 is None else ld_out16
+    g.act = act
+    if conv is None:
+        g.a_mode = A_PLAIN
+    else:
+        g.a_mode = A_CONV3X3
+        g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
+        g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
+        g.out_nchw, g.n_real = int(conv.get("out_nchw", False)), conv.get("n_real", pm.N)
+    check(_lib.lib().mst_gemm(C.byref(g), _stream()), "mst_gemm")
+    launch_count += 1
+
+
+def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
+                     v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None) -> None:
+    global launch_count
+    a = MstWindowAttn()
+    a.q, a.k, a.v = _ptr(q, torch.bfloat16, "q"), _ptr(k, torch.bfloat16, "k"), _ptr(v, torch.bfloat16, "v")
+    a.v2, a.out, a.out2 = _ptr(v2, torch.bfloat16, "v2"), _ptr(out, torch.bfloat16, "out"), _ptr(out2, torch.bfloat16, "out2")
+    a.bias_table = _ptr(bias_table, torch.float32, "bias_table")
+    a.pad_q, a.pad_k = _ptr(pad_q, torch.float32, "pad_q"), _ptr(pad_k, torch.float32, "pad_k")
+    a.pad_v, a.pad_v2 = _ptr(pad_v, torch.float32, "pad_v"), _ptr(pad_v2, torch.float32, "pad_v2")
+    a.B, a.H, a.W, a.heads, a.ws, a.shift = B, H, W, heads, ws, shift
+    a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+    check(_lib.lib().mst_window_attention(C.byref(a), _stream()), "mst_window_attention")
+    launch_count += 1
+
+
+def window_maps(H: int, W: int, ws: int, shift: int, device="cuda"):
+    """(gather [nW,N] int32, labels [nW,N] int32, relidx [N*N] int32) as the attention kernel computes them."""
+    global launch_count
+    Hp, Wp = H + (ws - H % ws) % ws, W + (ws - W % ws) % ws
+    nW, N = (Hp // ws) * (Wp // ws), ws * ws
+    gather = torch.empty(nW, N, dtype=torch.int32, device=device)
+    labels = torch.empty(nW, N, dtype=torch.int32, device=device)
+    relidx = torch.empty(N * N, dtype=torch.int32, device=device)
+    check(_lib.lib().mst_window_maps(H, W, ws, shift, gather.data_ptr(), labels.data_ptr(), relidx.data_ptr(), _stream()),
+          "mst_window_maps")
+    launch_count += 1
+    return gather, labels, relidx
+
+
+def layernorm(x, gamma, beta, y, rows, Cdim) -> None:
+    global launch_count
+    check(_lib.lib().mst_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                   _ptr(beta, torch.float32, "beta"), _ptr(y, torch.bfloat16, "y"), rows, Cdim, _stream()),
+          "mst_layernorm")
+    launch_count += 1
+
+
+def patch_merge_layernorm(x, gamma, beta, y, B, H, W, Cdim) -> None:
+    global launch_count
+    check(_lib.lib().mst_patch_merge_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                               _ptr(beta, torch.float32, "beta"), _ptr(y, torch.bfloat16, "y"), B, H, W, Cdim,
+                                               _stream()), "mst_patch_merge_layernorm")
+    launch_count += 1
+
+
+def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False) -> None:
+    global launch_count
+    check(_lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                        _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), _stream()),
+          "mst_instnorm_stats")
+    launch_count += 1
+
+
+def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None) -> None:
+    global launch_count
+    check(_lib.lib().mst_instnorm_apply(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                        _ptr(rstd, torch.float32, "rstd"), _ptr(y16, torch.bfloat16, "y16"),
+                                        _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream()), "mst_instnorm_apply")
+    launch_count += 1
+
+
+def patch_embed(img, w, b, gamma, beta, x, B, S) -> None:
+    global launch_count
+    check(_lib.lib().mst_patch_embed(_ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
+                                     _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
+                                     _ptr(x, torch.float32, "x"), B, S, _stream()), "mst_patch_embed")
+    launch_count += 1
+
+
+def cast_bf16(x, y) -> None:
+    global launch_count
+    check(_lib.lib().mst_cast_bf16(_ptr(x, torch.float32, "x"), _ptr(y, torch.bfloat16, "y"), x.numel(), _stream()),
+          "mst_cast_bf16")
+    launch_count += 1

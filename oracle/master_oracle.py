@@ -1,0 +1,385 @@
+"""CPU oracle for the Master stylization hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch fp32 restatement (torch CPU tensors, explicit gather maps) of
+the reference algorithm.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import it; the product package never does.
+
+Pinned: oracle/make_golden.py imports the real reference from /root/reference in the build
+container, runs both on the same seeded weights/inputs, asserts agreement (<= 2e-5 max-abs on
+O(1) activations, bit-exact on integer maps) and writes tests/golden/*.npz, which
+tests/test_oracle_golden.py re-checks wherever the repo travels.  The reference itself has
+no tests or golden vectors, so this pinning against the reference's own
+outputs is the only anchor there is.
+
+Every function cites the reference file:line it follows (paths relative to the reference root;
+"tv:" = torchvision 0.26 models/swin_transformer.py, the reference's un-vendored dependency).
+All tensors are token-major BHWC unless noted.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+# ----------------------------------------------------------------------------------------------
+# integer maps (bit-exact contract)
+# ----------------------------------------------------------------------------------------------
+
+
+def relative_position_index(ws: int) -> Tensor:
+    """codes/style_transformer.py:227-239: idx[i,j]=(yi-yj+ws-1)*(2ws-1)+(xi-xj+ws-1), flat [ws^4] int64."""
+    n = ws * ws
+    out = torch.empty(n * n, dtype=torch.int64)
+    for i in range(n):
+        yi, xi = divmod(i, ws)
+        for j in range(n):
+            yj, xj = divmod(j, ws)
+            out[i * n + j] = (yi - yj + ws - 1) * (2 * ws - 1) + (xi - xj + ws - 1)
+    return out
+
+
+def padded_dims(H: int, W: int, ws: int) -> Tuple[int, int]:
+    """codes/style_transformer.py:77-87: pad bottom/right up to a multiple of the window."""
+    return H + (ws - H % ws) % ws, W + (ws - W % ws) % ws
+
+
+def effective_shift(Hp: int, Wp: int, ws: int, shift: int) -> Tuple[int, int]:
+    """codes/style_transformer.py:89-94: no shift along an axis the window already covers."""
+    return (0 if ws >= Hp else shift), (0 if ws >= Wp else shift)
+
+
+def window_gather_map(H: int, W: int, ws: int, shift: int) -> Tensor:
+    """Source position of every window slot.
+
+    Returns int64 [nW, ws*ws]: flat index y*Wp+x into the *padded, un-rolled* grid (values
+    with y>=H or x>=W are zero padding), following pad -> roll(-s) -> partition
+    (codes/style_transformer.py:83-111).  rolled[y,x] = padded[(y+sy)%Hp,(x+sx)%Wp].
+    """
+    Hp, Wp = padded_dims(H, W, ws)
+    sy, sx = effective_shift(Hp, Wp, ws, shift)
+    nwx = Wp // ws
+    out = torch.empty((Hp // ws) * nwx, ws * ws, dtype=torch.int64)
+    for wy in range(Hp // ws):
+        for wx in range(nwx):
+            for iy in range(ws):
+                for ix in range(ws):
+                    y = (wy * ws + iy + sy) % Hp
+                    x = (wx * ws + ix + sx) % Wp
+                    out[wy * nwx + wx, iy * ws + ix] = y * Wp + x
+    return out
+
+
+def region_labels(H: int, W: int, ws: int, shift: int) -> Optional[Tensor]:
+    """9-region labels of each window slot on the rolled grid (codes/style_transformer.py:134-145).
+
+    Returns int64 [nW, ws*ws] or None when no shift is active (then no mask is added, :134).
+    """
+    Hp, Wp = padded_dims(H, W, ws)
+    sy, sx = effective_shift(Hp, Wp, ws, shift)
+    if sy + sx == 0:
+        return None
+
+    def band(p: int, size: int, s: int) -> int:
+        # slices (0,-ws), (-ws,-s), (-s,None); with s == 0 the last two are empty / whole-tail
+        # exactly as python slicing makes them in the reference loop (later writes win).
+        if s == 0:
+            return 2  # slice(-ws, -0) is empty and slice(-0, None) is the whole axis: written last
+        if p >= size - s:
+            return 2
+        return 1 if p >= size - ws else 0
+
+    nwx = Wp // ws
+    out = torch.empty((Hp // ws) * nwx, ws * ws, dtype=torch.int64)
+    for wy in range(Hp // ws):
+        for wx in range(nwx):
+            for iy in range(ws):
+                for ix in range(ws):
+                    out[wy * nwx + wx, iy * ws + ix] = 3 * band(wy * ws + iy, Hp, sy) + band(wx * ws + ix, Wp, sx)
+    return out
+
+
+def shift_mask(H: int, W: int, ws: int, shift: int) -> Optional[Tensor]:
+    """float32 [nW, N, N] in {0,-100}: label[j]-label[i] != 0 -> -100 (codes/style_transformer.py:146-147)."""
+    lab = region_labels(H, W, ws, shift)
+    if lab is None:
+        return None
+    diff = lab.unsqueeze(1) - lab.unsqueeze(2)
+    return torch.where(diff != 0, torch.tensor(-100.0), torch.tensor(0.0))
+
+
+# ----------------------------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------------------------
+
+
+def _to_windows(x: Tensor, ws: int, shift: int) -> Tensor:
+    """[B,H,W,C] -> [B*nW, N, C] via the gather map (zeros where the map points at padding)."""
+    B, H, W, C = x.shape
+    Hp, Wp = padded_dims(H, W, ws)
+    gm = window_gather_map(H, W, ws, shift)
+    xp = torch.zeros(B, Hp, Wp, C, dtype=x.dtype)
+    xp[:, :H, :W] = x
+    return xp.reshape(B, Hp * Wp, C)[:, gm.reshape(-1)].reshape(B * gm.shape[0], gm.shape[1], C)
+
+
+def _from_windows(xw: Tensor, B: int, H: int, W: int, ws: int, shift: int) -> Tensor:
+    """Inverse of _to_windows followed by the un-pad (codes/style_transformer.py:160-168)."""
+    Hp, Wp = padded_dims(H, W, ws)
+    gm = window_gather_map(H, W, ws, shift).reshape(-1)
+    C = xw.shape[-1]
+    out = torch.empty(B, Hp * Wp, C, dtype=xw.dtype)
+    out[:, gm] = xw.reshape(B, -1, C)
+    return out.reshape(B, Hp, Wp, C)[:, :H, :W].contiguous()
+
+
+def _bias_from_table(table: Tensor, ws: int) -> Tensor:
+    """codes/style_transformer.py:21-28: [heads, N, N]."""
+    n = ws * ws
+    return table[relative_position_index(ws)].reshape(n, n, -1).permute(2, 0, 1)
+
+
+def _softmax_probs(q: Tensor, k: Tensor, heads: int, bias: Tensor, mask: Optional[Tensor], B: int) -> Tensor:
+    """q,k [B*nW,N,C] -> P [B*nW, heads, N, N] (codes/style_transformer.py:120-152)."""
+    bw, n, C = q.shape
+    d = C // heads
+    qh = q.reshape(bw, n, heads, d).permute(0, 2, 1, 3) * (d ** -0.5)
+    kh = k.reshape(bw, n, heads, d).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-2, -1) + bias.unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        s = (s.reshape(B, nW, heads, n, n) + mask.reshape(1, nW, 1, n, n)).reshape(bw, heads, n, n)
+    return torch.softmax(s, dim=-1)
+
+
+def _apply_probs(p: Tensor, v: Tensor, heads: int) -> Tensor:
+    bw, n, C = v.shape
+    vh = v.reshape(bw, n, heads, C // heads).permute(0, 2, 1, 3)
+    return (p @ vh).transpose(1, 2).reshape(bw, n, C)
+
+
+def window_attention(xq: Tensor, xk: Tensor, xv: Tensor, wq, bq, wk, bk, wv, bv, wp, bp,
+                     table: Tensor, ws: int, shift: int, heads: int) -> Tensor:
+    """codes/style_transformer.py:37-169 (a3): three possibly different inputs, split Q/K/V weights."""
+    B, H, W, C = xq.shape
+    q = F.linear(_to_windows(xq, ws, shift), wq, bq)
+    k = F.linear(_to_windows(xk, ws, shift), wk, bk)
+    v = F.linear(_to_windows(xv, ws, shift), wv, bv)
+    p = _softmax_probs(q, k, heads, _bias_from_table(table, ws), shift_mask(H, W, ws, shift), B)
+    o = F.linear(_apply_probs(p, v, heads), wp, bp)
+    return _from_windows(o, B, H, W, ws, shift)
+
+
+def instance_norm_bhwc(x: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.InstanceNorm2d(C, affine=False) on a BHWC tensor (codes/style_transformer.py:986,1056-1057)."""
+    mean = x.mean(dim=(1, 2), keepdim=True)
+    var = x.var(dim=(1, 2), unbiased=False, keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps)
+
+
+def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk, wvs, bvs, wvh, bvh, wp, bp,
+                       table: Tensor, ws: int, shift: int, heads: int) -> Tuple[Tensor, Tensor]:
+    """codes/style_transformer.py:414-611 (a8), default flags: IN(q) again (:468), no Q projection
+    (:511-514), IN over the whole (padded) map of Wk*K (:520-530), one softmax for both values,
+    the same proj for sigma and mu (:575-607)."""
+    B, H, W, C = xq.shape
+    Hp, Wp = padded_dims(H, W, ws)
+    q = _to_windows(instance_norm_bhwc(xq), ws, shift)
+    k = F.linear(_to_windows(xk, ws, shift), wk, bk)
+    vs = F.linear(_to_windows(xvs, ws, shift), wvs, bvs)
+    vh = F.linear(_to_windows(xvh, ws, shift), wvh, bvh)
+    # un-window k (still rolled, still padded), normalise per (b,c) over Hp*Wp, re-window
+    gm = window_gather_map(H, W, ws, shift).reshape(-1)
+    kmap = torch.empty(B, Hp * Wp, C)
+    kmap[:, gm] = k.reshape(B, -1, C)
+    kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C)).reshape(B, Hp * Wp, C)
+    k = kmap[:, gm].reshape(k.shape)
+    p = _softmax_probs(q, k, heads, _bias_from_table(table, ws), shift_mask(H, W, ws, shift), B)
+    sig = F.linear(_apply_probs(p, vs, heads), wp, bp)
+    mu = F.linear(_apply_probs(p, vh, heads), wp, bp)
+    return _from_windows(sig, B, H, W, ws, shift), _from_windows(mu, B, H, W, ws, shift)
+
+
+def mlp(x: Tensor, sd: SD, pre: str) -> Tensor:
+    """torchvision ops/misc.py:264-306 MLP: Linear - GELU(erf) - Linear (dropout p=0)."""
+    h = F.gelu(F.linear(x, sd[pre + "0.weight"], sd[pre + "0.bias"]))
+    return F.linear(h, sd[pre + "3.weight"], sd[pre + "3.bias"])
+
+
+def _attn_weights(sd: SD, pre: str):
+    return [sd[pre + n] for n in ("Wq.weight", "Wq.bias", "Wk.weight", "Wk.bias", "Wv.weight", "Wv.bias",
+                                  "proj.weight", "proj.bias", "relative_position_bias_table")]
+
+
+# ----------------------------------------------------------------------------------------------
+# style transformer (a5, a7, a9, a11)
+# ----------------------------------------------------------------------------------------------
+
+
+def style_encoder(sd: SD, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
+                  pre: str = "encoder."):
+    """codes/style_transformer.py:855-882 default branch: one shared MHA (no norm, residual from
+    input_q for the Key pass and from input_v for Scale/Shift, :383-386), three private MLPs."""
+    aw = _attn_weights(sd, pre + "shared_MHA_without_MLP.attn.")
+    key = key + window_attention(key, key, key, *aw, ws, sh, heads)
+    key = key + mlp(key, sd, pre + "encoder_MLP_Key.")
+    scale = scale + window_attention(key, key, scale, *aw, ws, sh, heads)
+    scale = scale + mlp(scale, sd, pre + "encoder_MLP_Scale.")
+    shift_t = shift_t + window_attention(key, key, shift_t, *aw, ws, sh, heads)
+    shift_t = shift_t + mlp(shift_t, sd, pre + "encoder_MLP_Shift.")
+    return key, scale, shift_t
+
+
+def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
+                  pre: str = "decoder."):
+    """codes/style_transformer.py:1045-1059,1123-1128 default branch."""
+    b = pre + "MHA_self_attn."
+    C = fcs.shape[-1]
+    n1 = F.layer_norm(fcs, (C,), sd[b + "norm1.weight"], sd[b + "norm1.bias"])
+    x = fcs + window_attention(n1, n1, n1, *_attn_weights(sd, b + "attn."), ws, sh, heads)
+    x = x + mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp.")
+    query_in = instance_norm_bhwc(x)
+    key_in = instance_norm_bhwc(key)
+    m = pre + "decoder_MHA_for_sigma_and_mu."
+    sigma, mu = sigma_mu_attention(query_in, key_in, scale, shift_t,
+                                   sd[m + "Wk.weight"], sd[m + "Wk.bias"],
+                                   sd[m + "Wv_scale.weight"], sd[m + "Wv_scale.bias"],
+                                   sd[m + "Wv_shift.weight"], sd[m + "Wv_shift.bias"],
+                                   sd[m + "proj.weight"], sd[m + "proj.bias"],
+                                   sd[m + "relative_position_bias_table"], ws, sh, heads)
+    x = x * sigma + mu
+    return x + mlp(x, sd, pre + "last_MLP.")
+
+
+def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8) -> Tensor:
+    """codes/style_transformer.py:1229-1245: Scale=Shift=Fs, k times the same weights."""
+    scale, shift_t = fs, fs
+    for _ in range(k):
+        fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads)
+        fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads)
+    return fc
+
+
+# ----------------------------------------------------------------------------------------------
+# Swin-B first two stages (a12) -- torchvision arithmetic
+# ----------------------------------------------------------------------------------------------
+
+
+def _tv_block(sd: SD, pre: str, x: Tensor, heads: int, shift: int, ws: int = 7) -> Tensor:
+    """tv:401-456 block, tv:116-220 attention with fused qkv weight [3C,C]."""
+    C = x.shape[-1]
+    n1 = F.layer_norm(x, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
+    w, b = sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"]
+    a = window_attention(n1, n1, n1, w[:C], b[:C], w[C:2 * C], b[C:2 * C], w[2 * C:], b[2 * C:],
+                         sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"],
+                         sd[pre + "attn.relative_position_bias_table"], ws, shift, heads)
+    x = x + a
+    n2 = F.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
+    h = F.gelu(F.linear(n2, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"]))
+    return x + F.linear(h, sd[pre + "mlp.3.weight"], sd[pre + "mlp.3.bias"])
+
+
+def swin_encoder(sd: SD, img: Tensor, pre: str = "") -> Tensor:
+    """codes/utils.py:59-102 slice of tv swin_b: [B,3,S,S] NCHW -> [B,S/8,S/8,256] BHWC."""
+    x = F.conv2d(img, sd[pre + "0.0.weight"], sd[pre + "0.0.bias"], stride=4).permute(0, 2, 3, 1)
+    x = F.layer_norm(x, (128,), sd[pre + "0.2.weight"], sd[pre + "0.2.bias"])
+    x = _tv_block(sd, pre + "1.0.", x, 4, 0)
+    x = _tv_block(sd, pre + "1.1.", x, 4, 3)
+    # patch merging tv:35-87 (H, W even here; odd sizes pad one row/col of zeros)
+    B, H, W, C = x.shape
+    x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+    x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    x = F.layer_norm(x, (4 * C,), sd[pre + "2.norm.weight"], sd[pre + "2.norm.bias"])
+    x = F.linear(x, sd[pre + "2.reduction.weight"])
+    x = _tv_block(sd, pre + "3.0.", x, 8, 0)
+    x = _tv_block(sd, pre + "3.1.", x, 8, 3)
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
+# CNN decoder (a13), full model (a14)
+# ----------------------------------------------------------------------------------------------
+
+CNN_DECODER_LAYOUT = [  # (sequential index, upsample before this conv, relu after)
+    (0, False, True), (3, True, True), (5, False, True), (7, False, True), (9, False, True),
+    (12, True, True), (14, False, True), (17, True, True), (19, False, False)]
+
+
+def cnn_decoder(sd: SD, x: Tensor, pre: str = "decoder.") -> Tensor:
+    """codes/decoder.py:23-55: NCHW in, reflect-padded 3x3 convs, nearest x2 upsamples."""
+    for idx, up, relu in CNN_DECODER_LAYOUT:
+        if up:
+            x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        x = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), sd[f"{pre}{idx}.weight"], sd[f"{pre}{idx}.bias"])
+        if relu:
+            x = torch.relu(x)
+    return x
+
+
+def full_forward(sd: SD, content: Tensor, style: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8) -> Tensor:
+    """codes/full_model.py:214-226."""
+    fc = swin_encoder(sd, content, "swin_encoder.")
+    fs = swin_encoder(sd, style, "swin_encoder.")
+    st = {n[len("style_transformer."):]: t for n, t in sd.items() if n.startswith("style_transformer.")}
+    fcs = style_transformer(st, fc, fs, k, ws, sh, heads).permute(0, 3, 1, 2)
+    return cnn_decoder(sd, fcs, "decoder.decoder.")
+
+
+# ----------------------------------------------------------------------------------------------
+# VGG-19 taps and loss (a15-a18)
+# ----------------------------------------------------------------------------------------------
+
+VGG_CONVS = [0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28]  # conv indices in features[:30]
+VGG_POOL_BEFORE = {5, 10, 19, 28}                              # a 2x2 max-pool precedes these convs
+VGG_TAPS = {5: 0, 10: 1, 19: 2, 28: 3}                         # relu after conv idx -> tap slot (relu2_1..5_1)
+
+
+def vgg_taps(sd: SD, x: Tensor, pre: str = "") -> List[Tensor]:
+    """codes/loss.py:23-37: relu2_1, relu3_1, relu4_1, relu5_1 of vgg19.features[:30]."""
+    taps: List[Optional[Tensor]] = [None] * 4
+    for idx in VGG_CONVS:
+        if idx in VGG_POOL_BEFORE:
+            x = F.max_pool2d(x, 2)
+        x = torch.relu(F.conv2d(x, sd[f"{pre}{idx}.weight"], sd[f"{pre}{idx}.bias"], padding=1))
+        if idx in VGG_TAPS:
+            taps[VGG_TAPS[idx]] = x
+    return taps  # type: ignore[return-value]
+
+
+def _in_nchw(x: Tensor, eps: float = 1e-5) -> Tensor:
+    m = x.mean(dim=(2, 3), keepdim=True)
+    v = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    return (x - m) / torch.sqrt(v + eps)
+
+
+def content_loss(taps_c: List[Tensor], taps_o: List[Tensor], squared: bool = False) -> Tensor:
+    """codes/loss.py:110-116,267-289: sum over taps of mean|IN(Fc)-IN(Fcs)| (or squared)."""
+    tot = torch.zeros(())
+    for a, b in zip(taps_c, taps_o):
+        d = _in_nchw(a) - _in_nchw(b)
+        tot = tot + (d.square().mean() if squared else d.abs().mean())
+    return tot
+
+
+def style_loss(taps_s: List[Tensor], taps_o: List[Tensor], squared: bool = False) -> Tensor:
+    """codes/loss.py:122-130,293-315: mean|mu-mu'| + mean|std-std'| with torch's unbiased std."""
+    tot = torch.zeros(())
+    for a, b in zip(taps_s, taps_o):
+        dm = a.mean(dim=(2, 3)) - b.mean(dim=(2, 3))
+        ds = a.std(dim=(2, 3)) - b.std(dim=(2, 3))
+        tot = tot + ((dm.square().mean() + ds.square().mean()) if squared else (dm.abs().mean() + ds.abs().mean()))
+    return tot
+
+
+def overall_loss(vgg_sd: SD, content: Tensor, style: Tensor, output: Tensor, lam: float = 10.0,
+                 squared_content: bool = False, squared_style: bool = False):
+    """codes/loss.py:201-262: total = content + lambda*style; returns (total, content, style)."""
+    assert content.shape == style.shape == output.shape, "All images should be in the exact same shape"
+    tc, ts, to = vgg_taps(vgg_sd, content), vgg_taps(vgg_sd, style), vgg_taps(vgg_sd, output)
+    lc = content_loss(tc, to, squared_content)
+    ls = style_loss(ts, to, squared_style)
+    return lc + lam * ls, lc, ls
