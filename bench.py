@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""Headline benchmark: stylised images/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 256|512] [--layers k]
+
+N=1 workload = BASELINE configs[1]: zero-shot stylization, batch 32 at 256x256, synthetic tensors,
+forward only, one transformer layer.  For N>1 (torchrun, one rank per GPU) every rank stylises its own
+batch of 32 (images are independent: no data-path collective, weak scaling).
+
+`value`  : whole-job images/s with inputs resident in HBM, one CUDA-graph launch per step, timed with
+           CUDA events between barrier+synchronize pairs, max over ranks.
+`e2e`    : same metric through the public host API (GraphedStylizer.stylize_host): pinned host images
+           in -> H2D -> graph -> D2H of the stylised images, every step, host-synchronised per step.
+`roofline`: the dominant kernel (gemm_tc_kernel: every projection / MLP / convolution) -- algorithmic
+           FLOPs of its launches / their summed CUDA-event durations, against the measured bf16 peak.
+`cpu_baseline`: the CPU oracle port of the reference timed on this box's host cores (bounded sample).
+`--impl reference`: the reference's CPU implementation of the path (its oracle port: the reference is
+           Python and /root/reference does not exist on the GPU box), all host threads, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+GF_PER_IMAGE = {256: {"swin": 7.552, "st": 8.556, "cnn": 7.965}, 512: {"swin": 29.609, "st": 34.226, "cnn": 31.860}}
+
+
+def flops_per_image(size: int, layers: int) -> float:
+    g = GF_PER_IMAGE[size]
+    return (2 * g["swin"] + layers * g["st"] + g["cnn"]) * 1e9  # BASELINE.md section 2 (reference-algorithm FLOPs)
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d["bf16_tflops_sustained"], d["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        busy = [s for s in sm if s > 0.5 * (mx[0] if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(size: int, layers: int, batch: int, iters: int, threads: int):
+    """images/s of the CPU oracle port (full forward, fp32) on a bounded sample."""
+    from mastermetastyletransfer_b200 import synthetic
+    from mastermetastyletransfer_b200.full_model import MasterStyleTransferModel
+    from oracle import master_oracle as O
+    torch.set_num_threads(threads)
+    m = MasterStyleTransferModel()
+    synthetic.fill_state_dict_(m, 0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    content, style = synthetic.synthetic_images(batch, size, seed=0)
+    with torch.no_grad():
+        O.full_forward(sd, content, style, layers)  # warm-up
+        times = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            O.full_forward(sd, content, style, layers)
+            times.append(time.perf_counter() - t0)
+    return batch / min(times), times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=256, choices=[256, 512])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 32 @256, 16 @512)")
+    ap.add_argument("--layers", type=int, default=1)
+    ap.add_argument("--cpu-baseline", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    batch = args.batch or (32 if args.size == 256 else 16)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = f"zero-shot stylization, batch {batch}/GPU at {args.size}x{args.size}, forward only, {args.layers} transformer layer(s), window 8/shift 4"
+    config = {"workload": workload, "batch_per_gpu": batch, "size": args.size, "layers": args.layers,
+              "weights": "seeded random init (reference checkpoints unavailable offline)"}
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        cpu_batch = 4 if args.size == 256 else 1
+        steps = min(args.steps, 10)
+        _, times = cpu_oracle_rate(args.size, args.layers, cpu_batch, steps, threads)  # 1 warm-up + `steps` timed forwards
+        ms = 1e3 * sum(times) / len(times)
+        value = cpu_batch / (ms / 1e3)
+        sample = f"{steps} steps of batch {cpu_batch} at {args.size}x{args.size} (CPU oracle port of the reference, fp32, {threads} threads)"
+        print(json.dumps({
+            "impl": "reference", "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}))
+        return
+
+    import torch.distributed as dist
+    from mastermetastyletransfer_b200 import ops, synthetic
+    from mastermetastyletransfer_b200.full_model import MasterStyleTransferModel
+    from mastermetastyletransfer_b200.runtime import GraphedStylizer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    model = MasterStyleTransferModel()
+    synthetic.fill_state_dict_(model, 0)
+    model = model.eval().to(dev)
+    content, style = synthetic.synthetic_images(batch, args.size, seed=rank)
+    runner = GraphedStylizer(model, batch, args.size, args.layers, dev)
+    runner.load(content.to(dev), style.to(dev))
+    torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput ----------------
+    for _ in range(args.warmup):
+        runner.replay()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        runner.replay()
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total.item() / args.steps
+    value = world * batch / (ms_step / 1e3)
+
+    # ---------------- end to end through the host API ----------------
+    c_pin, s_pin = content.pin_memory(), style.pin_memory()
+    o_pin = torch.empty(batch, 3, args.size, args.size).pin_memory()
+    for _ in range(args.warmup):
+        runner.stylize_host(c_pin, s_pin, o_pin)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        runner.stylize_host(c_pin, s_pin, o_pin)
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch / (ms_e2e.item() / args.steps / 1e3)
+    h2d = c_pin.numel() * 4 + s_pin.numel() * 4
+    d2h = o_pin.numel() * 4
+
+    # ---------------- per-kernel-family timing (eager pass with CUDA events around every launch) ----------------
+    burst, sustained, hbm, peak_src = peaks()
+    roofline, families = None, None
+    if rank == 0:
+        with ops.timing() as rec:
+            with torch.no_grad():
+                model(runner.content, runner.style, args.layers)
+        torch.cuda.synchronize(dev)
+        fam = {}
+        for name, flops, nbytes, a, b in rec:
+            f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            f["launches"] += 1
+            f["ms"] += a.elapsed_time(b)
+            f["flops"] += flops
+            f["bytes"] += nbytes
+        tot_ms = sum(f["ms"] for f in fam.values())
+        families = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4),
+                        "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["flops"] else None,
+                        "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["bytes"] else None} for k, v in fam.items()}
+        g = fam["gemm_tc_kernel"]
+        achieved = g["flops"] / (g["ms"] * 1e9)
+        roofline = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                    "frac": achieved / sustained, "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                    "launches_per_step": g["launches"], "share_of_step": g["ms"] / tot_ms,
+                    "step": {"achieved": flops_per_image(args.size, args.layers) * batch / (ms_step * 1e9), "unit": "TFLOP/s",
+                             "frac": flops_per_image(args.size, args.layers) * batch / (ms_step * 1e9) / sustained}}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        cpu_batch = 4 if args.size == 256 else 1
+        rate, times = cpu_oracle_rate(args.size, args.layers, cpu_batch, 3, threads)
+        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"best of 3 full forwards of batch {cpu_batch} at {args.size}x{args.size}, fp32 CPU oracle port of the reference"}
+
+    if rank == 0:
+        act_mb = batch * (args.size // 8) ** 2 * 256 * 4 / 1e6
+        config["l2"] = f"no explicit flush: a step streams >1 GB of activations (feature map alone {act_mb:.0f} MB fp32 x dozens of tensors) through a 126 MB L2"
+        config["timed"] = "one CUDA-graph replay per step"
+        print(json.dumps({
+            "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e.item() / args.steps},
+            "gpu_launches": runner.launches_per_step * args.steps, "launches_per_step": runner.launches_per_step,
+            "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

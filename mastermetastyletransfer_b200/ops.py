@@ -19,6 +19,42 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 
 # number of kernels this process has enqueued through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0
+_records = None  # list of (kernel family, algorithmic flops, algorithmic bytes, start event, end event) while timing()
+
+
+class timing:
+    """Context manager: CUDA-event bracket around every kernel launched through this module (bench.py roofline pass)."""
+
+    def __enter__(self):
+        global _records
+        _records = []
+        return _records
+
+    def __exit__(self, *exc):
+        global _records
+        _records = None
+        return False
+
+
+def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Run one C-ABI call (= one kernel launch), count it, and time it when a timing() context is active."""
+    global launch_count
+    if _records is None:
+        check(fn(), name)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(fn(), name)
+        b.record()
+        _records.append((KERNEL_OF.get(name, name), flops, nbytes, a, b))
+    launch_count += 1
+
+
+KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
+             "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
+             "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
+             "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
+             "mst_window_maps": "window_maps_kernel"}
 
 
 def _stream() -> int:
@@ -62,29 +98,23 @@ def _pad_bias(bias: Optional[torch.Tensor], n_pad: int, device) -> Optional[torc
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedMatrix:
     """nn.Linear weight [N,K] fp32 -> PackedMatrix (several weights may be concatenated along N first)."""
-    global launch_count
     w = weight.detach().contiguous()
     N, K = w.shape
     n_pad, k_pad = n_pad_of(N), round_up(K, 64)
     dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
-    check(_lib.lib().mst_pack_linear_weight(_ptr(w, torch.float32, "weight"), N, K, dst.data_ptr(), n_pad, k_pad, _stream()),
-          "mst_pack_linear_weight")
-    launch_count += 1
+    _launch("mst_pack_linear_weight", lambda: _lib.lib().mst_pack_linear_weight(_ptr(w, torch.float32, "weight"), N, K, dst.data_ptr(), n_pad, k_pad, _stream()))
     return PackedMatrix(dst, _pad_bias(bias, n_pad, w.device), N, K, n_pad, k_pad)
 
 
 def pack_conv3x3(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedMatrix:
     """nn.Conv2d weight [N,Cin,3,3] fp32 -> PackedMatrix with k = (ky*3+kx)*Cin + ci."""
-    global launch_count
     w = weight.detach().contiguous()
     N, Cin, kh, kw = w.shape
     if (kh, kw) != (3, 3):
         raise ValueError("pack_conv3x3: expected a 3x3 kernel")
     n_pad, k_pad = n_pad_of(N), round_up(9 * Cin, 64)
     dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
-    check(_lib.lib().mst_pack_conv3x3_weight(_ptr(w, torch.float32, "weight"), N, Cin, dst.data_ptr(), n_pad, k_pad, _stream()),
-          "mst_pack_conv3x3_weight")
-    launch_count += 1
+    _launch("mst_pack_conv3x3_weight", lambda: _lib.lib().mst_pack_conv3x3_weight(_ptr(w, torch.float32, "weight"), N, Cin, dst.data_ptr(), n_pad, k_pad, _stream()))
     return PackedMatrix(dst, _pad_bias(bias, n_pad, w.device), N, 9 * Cin, n_pad, k_pad)
 
 
@@ -94,7 +124,6 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
          ld_out32: Optional[int] = None, ld_out16: Optional[int] = None, ld_res: Optional[int] = None,
          conv: Optional[dict] = None, n_rows: Optional[int] = None) -> None:
     """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h)."""
-    global launch_count
     g = MstGemm()
     g.A = _ptr(A, torch.bfloat16, "A")
     g.Wt = pm.w.data_ptr()
@@ -117,13 +146,11 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
         g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
         g.out_nchw, g.n_real = int(conv.get("out_nchw", False)), conv.get("n_real", pm.N)
-    check(_lib.lib().mst_gemm(C.byref(g), _stream()), "mst_gemm")
-    launch_count += 1
+    _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=2.0 * M * min(N, pm.N) * pm.K)
 
 
 def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
                      v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None) -> None:
-    global launch_count
     a = MstWindowAttn()
     a.q, a.k, a.v = _ptr(q, torch.bfloat16, "q"), _ptr(k, torch.bfloat16, "k"), _ptr(v, torch.bfloat16, "v")
     a.v2, a.out, a.out2 = _ptr(v2, torch.bfloat16, "v2"), _ptr(out, torch.bfloat16, "out"), _ptr(out2, torch.bfloat16, "out2")
@@ -132,66 +159,55 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
     a.pad_v, a.pad_v2 = _ptr(pad_v, torch.float32, "pad_v"), _ptr(pad_v2, torch.float32, "pad_v2")
     a.B, a.H, a.W, a.heads, a.ws, a.shift = B, H, W, heads, ws, shift
     a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
-    check(_lib.lib().mst_window_attention(C.byref(a), _stream()), "mst_window_attention")
-    launch_count += 1
+    n_tok = ws * ws
+    n_win = B * (-(-H // ws)) * (-(-W // ws))
+    _launch("mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
+            flops=2.0 * n_win * heads * n_tok * n_tok * 32 * (3 if v2 is not None else 2))
 
 
 def window_maps(H: int, W: int, ws: int, shift: int, device="cuda"):
     """(gather [nW,N] int32, labels [nW,N] int32, relidx [N*N] int32) as the attention kernel computes them."""
-    global launch_count
     Hp, Wp = H + (ws - H % ws) % ws, W + (ws - W % ws) % ws
     nW, N = (Hp // ws) * (Wp // ws), ws * ws
     gather = torch.empty(nW, N, dtype=torch.int32, device=device)
     labels = torch.empty(nW, N, dtype=torch.int32, device=device)
     relidx = torch.empty(N * N, dtype=torch.int32, device=device)
-    check(_lib.lib().mst_window_maps(H, W, ws, shift, gather.data_ptr(), labels.data_ptr(), relidx.data_ptr(), _stream()),
-          "mst_window_maps")
-    launch_count += 1
+    _launch("mst_window_maps", lambda: _lib.lib().mst_window_maps(H, W, ws, shift, gather.data_ptr(), labels.data_ptr(), relidx.data_ptr(), _stream()))
     return gather, labels, relidx
 
 
 def layernorm(x, gamma, beta, y, rows, Cdim) -> None:
-    global launch_count
-    check(_lib.lib().mst_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+    _launch("mst_layernorm", lambda: _lib.lib().mst_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
                                    _ptr(beta, torch.float32, "beta"), _ptr(y, torch.bfloat16, "y"), rows, Cdim, _stream()),
-          "mst_layernorm")
-    launch_count += 1
+            nbytes=6.0 * rows * Cdim)
 
 
 def patch_merge_layernorm(x, gamma, beta, y, B, H, W, Cdim) -> None:
-    global launch_count
-    check(_lib.lib().mst_patch_merge_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+    _launch("mst_patch_merge_layernorm", lambda: _lib.lib().mst_patch_merge_layernorm(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
                                                _ptr(beta, torch.float32, "beta"), _ptr(y, torch.bfloat16, "y"), B, H, W, Cdim,
-                                               _stream()), "mst_patch_merge_layernorm")
-    launch_count += 1
+                                               _stream()), nbytes=6.0 * B * H * W * Cdim)
 
 
 def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False) -> None:
-    global launch_count
-    check(_lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+    _launch("mst_instnorm_stats", lambda: _lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
                                         _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), _stream()),
-          "mst_instnorm_stats")
-    launch_count += 1
+            nbytes=4.0 * B * T * Cdim)
 
 
 def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None) -> None:
-    global launch_count
-    check(_lib.lib().mst_instnorm_apply(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+    _launch("mst_instnorm_apply", lambda: _lib.lib().mst_instnorm_apply(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
                                         _ptr(rstd, torch.float32, "rstd"), _ptr(y16, torch.bfloat16, "y16"),
-                                        _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream()), "mst_instnorm_apply")
-    launch_count += 1
+                                        _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream()),
+            nbytes=B * T * Cdim * (4.0 + (2.0 if y16 is not None else 0.0) + (4.0 if y32 is not None else 0.0)))
 
 
 def patch_embed(img, w, b, gamma, beta, x, B, S) -> None:
-    global launch_count
-    check(_lib.lib().mst_patch_embed(_ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
+    _launch("mst_patch_embed", lambda: _lib.lib().mst_patch_embed(_ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
                                      _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
-                                     _ptr(x, torch.float32, "x"), B, S, _stream()), "mst_patch_embed")
-    launch_count += 1
+                                     _ptr(x, torch.float32, "x"), B, S, _stream()),
+            nbytes=4.0 * B * S * S * 3 + 4.0 * B * (S // 4) ** 2 * 128)
 
 
 def cast_bf16(x, y) -> None:
-    global launch_count
-    check(_lib.lib().mst_cast_bf16(_ptr(x, torch.float32, "x"), _ptr(y, torch.bfloat16, "y"), x.numel(), _stream()),
-          "mst_cast_bf16")
-    launch_count += 1
+    _launch("mst_cast_bf16", lambda: _lib.lib().mst_cast_bf16(_ptr(x, torch.float32, "x"), _ptr(y, torch.bfloat16, "y"), x.numel(), _stream()),
+            nbytes=6.0 * x.numel())

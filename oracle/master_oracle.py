@@ -17,6 +17,7 @@ All tensors are token-major BHWC unless noted.
 """
 from __future__ import annotations
 
+import functools
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -31,6 +32,7 @@ SD = Dict[str, Tensor]
 # ----------------------------------------------------------------------------------------------
 
 
+@functools.lru_cache(maxsize=None)
 def relative_position_index(ws: int) -> Tensor:
     """codes/style_transformer.py:227-239: idx[i,j]=(yi-yj+ws-1)*(2ws-1)+(xi-xj+ws-1), flat [ws^4] int64."""
     n = ws * ws
@@ -53,6 +55,7 @@ def effective_shift(Hp: int, Wp: int, ws: int, shift: int) -> Tuple[int, int]:
     return (0 if ws >= Hp else shift), (0 if ws >= Wp else shift)
 
 
+@functools.lru_cache(maxsize=None)
 def window_gather_map(H: int, W: int, ws: int, shift: int) -> Tensor:
     """Source position of every window slot.
 
@@ -74,6 +77,7 @@ def window_gather_map(H: int, W: int, ws: int, shift: int) -> Tensor:
     return out
 
 
+@functools.lru_cache(maxsize=None)
 def region_labels(H: int, W: int, ws: int, shift: int) -> Optional[Tensor]:
     """9-region labels of each window slot on the rolled grid (codes/style_transformer.py:134-145).
 
@@ -103,6 +107,7 @@ def region_labels(H: int, W: int, ws: int, shift: int) -> Optional[Tensor]:
     return out
 
 
+@functools.lru_cache(maxsize=None)
 def shift_mask(H: int, W: int, ws: int, shift: int) -> Optional[Tensor]:
     """float32 [nW, N, N] in {0,-100}: label[j]-label[i] != 0 -> -100 (codes/style_transformer.py:146-147)."""
     lab = region_labels(H, W, ws, shift)
