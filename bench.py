@@ -209,7 +209,12 @@ def main():
                 model(runner.content, runner.style, args.layers)
         torch.cuda.synchronize(dev)
         fam = {}
-        for name, flops, nbytes, a, b in rec:
+        if os.environ.get("MST_BENCH_DETAIL"):
+            with open(os.environ["MST_BENCH_DETAIL"], "w") as fh:
+                for name, flops, nbytes, a, b, desc in rec:
+                    ms = a.elapsed_time(b)
+                    fh.write(f"{name:24s} {ms*1e3:9.1f} us  {flops/(ms*1e9) if flops else 0:8.1f} TF/s  {nbytes/(ms*1e6) if nbytes else 0:8.1f} GB/s  {desc}\n")
+        for name, flops, nbytes, a, b, _desc in rec:
             f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             f["launches"] += 1
             f["ms"] += a.elapsed_time(b)

@@ -38,8 +38,12 @@ const char* mst_error_string(int code);
  * Weight packing.  nn.Linear weight [N,K] fp32 (codes/style_transformer.py:206-213) and
  * nn.Conv2d weight [N,Cin,3,3] fp32 (codes/decoder.py:23-55, torchvision vgg19) are converted
  * to the bf16 [n_pad, k_pad] K-contiguous operand the tensor-core GEMM streams; conv k index is
- * (ky*3+kx)*Cin + ci.  Rows >= N and columns >= K are zero.
+ * (ky*3+kx)*Cin + ci.  Rows >= N and columns >= K are zero.  The operand is stored tile-blocked and
+ * pre-swizzled: block (n_tile, k_block) is the exact 128B-swizzled shared-memory image of a
+ * [tile_n x 64] K-major UMMA operand, tile_n = mst_gemm_tile_n(n_pad), so the GEMM fetches it with one
+ * bulk copy.  n_pad % 16 == 0, k_pad % 64 == 0.
  * ------------------------------------------------------------------------------------------ */
+int mst_gemm_tile_n(int n_pad);
 int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* dst, int n_pad, int k_pad, void* stream);
 int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n_pad, int k_pad, void* stream);
 
@@ -64,7 +68,7 @@ typedef struct MstGemm {
   const float* mul;   /* fp32 [M, ld_res] or NULL: out = res*mul + x (Query*sigma+mu, style_transformer.py:1123) */
   float* out_f32;     /* fp32 [M, ld_out32] or NULL */
   mst_bf16* out_bf16; /* bf16 [M, ld_out16] or NULL */
-  int M, N, K;        /* logical sizes; N % 16 == 0 after packing; K is the un-padded reduction length */
+  int M, N, K;        /* N = the n_pad the weight was packed with (<= 1024); K = un-padded reduction length */
   int k_pad;          /* row stride of Wt, multiple of 64 */
   int lda, ld_res, ld_out32, ld_out16;
   int a_mode, act;

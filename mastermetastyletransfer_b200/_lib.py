@@ -45,6 +45,7 @@ SYMBOLS = {
     "mst_error_string": (C.c_char_p, [_I]),
     "mst_pack_linear_weight": (_I, [_P, _I, _I, _P, _I, _I, _P]),
     "mst_pack_conv3x3_weight": (_I, [_P, _I, _I, _P, _I, _I, _P]),
+    "mst_gemm_tile_n": (_I, [_I]),
     "mst_gemm": (_I, [C.POINTER(MstGemm), _P]),
     "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
     "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

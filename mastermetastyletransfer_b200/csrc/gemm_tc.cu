@@ -1,12 +1,15 @@
-// Tensor-core GEMM for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) with a gathering A-operand
-// producer and a fused epilogue.  One CTA computes a 128 x BN output tile.
+// Tensor-core GEMM for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), persistent and warp-specialised.
 //
-//   warps 0-3 : producer (cp.async 16-byte gathers into 128B-swizzled K-major smem stages), then epilogue
-//               (tcgen05.ld of their 32-lane TMEM quadrant -> bias/activation/residual/blend -> global)
-//   warp  4   : TMEM allocation, then one elected lane issues tcgen05.mma and commits to mbarriers
+//   warps 0-7  : epilogue.  warp w reads TMEM lane quadrant w%4 (rows) and column half w/4 of the finished
+//                accumulator, applies bias / activation / residual / blend and stores fp32 and/or bf16.
+//   warps 8-11 : A-operand producers.  128 threads gather 16-byte chunks with cp.async into 128B-swizzled
+//                K-major stages (F.linear rows, or 3x3-conv taps with zero / reflect padding and an optional
+//                nearest x2 upsample folded into the address).  Thread 0 of warp 8 also issues ONE bulk copy
+//                (cp.async.bulk, UBLKCP) per stage for the weight tile, which is stored pre-swizzled in HBM.
+//   warp 12    : TMEM allocation; one elected lane issues tcgen05.mma and commits to mbarriers.
 //
-// The gather makes the same kernel serve F.linear on token-major activations and 3x3 convolutions as
-// implicit GEMM (zero or reflect padding, optional nearest x2 upsample folded into the read).
+// Each CTA loops over output tiles (128 x BN) with a static stride schedule; the accumulator is double
+// buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
 
@@ -15,48 +18,65 @@ namespace mst {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_PROD_WARPS = 4;
+constexpr int GEMM_THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 1) * 32;
+constexpr int MAX_BIAS = 1024;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 5 : 6);
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for manual 1024 B alignment
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators
+  static constexpr int EPI_SPLIT = BN >= 64 ? 2 : 1;               // column halves handled by warps 0-3 / 4-7
+  static constexpr int COLS_PER_WARP = BN / EPI_SPLIT;
 };
 
+MST_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+MST_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
 template <int BN>
-__global__ void __launch_bounds__(160) gemm_tc_kernel(const MstGemm p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm p, const int num_tiles) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int LAG = STAGES - 1;  // cp.async groups kept in flight per producer thread
+  constexpr int LAG = 2;  // cp.async groups kept in flight per producer thread before the stage is published
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t accum_bar;
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[MAX_BIAS];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   const int n_tiles = p.N / BN;
-  const int n_tile = blockIdx.x % n_tiles;
-  const int m_tile = blockIdx.x / n_tiles;
-  const int m0 = m_tile * BM;
-  const int n0 = n_tile * BN;
   const int nkb = p.k_pad / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 128);
+      mbar_init(smem_u32(&full_bar[s]), NUM_PROD_WARPS * 32 + 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[b]), NUM_EPI_WARPS);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) {
+  for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == NUM_EPI_WARPS + NUM_PROD_WARPS) {
     tmem_alloc(smem_u32(&tmem_base_slot), Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -65,192 +85,222 @@ __global__ void __launch_bounds__(160) gemm_tc_kernel(const MstGemm p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp < 4) {
-    // =========================== producer ===========================
-    const int t = threadIdx.x;
+  if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int t = threadIdx.x - NUM_EPI_WARPS * 32;
     const int c = t & 7;    // 16-byte chunk column inside the 128-byte k-slab
     const int r0 = t >> 3;  // first of this thread's rows; rows r0 + 16*i
-    // per-row source bookkeeping
-    long long row_base[8];  // PLAIN: element offset of the row; CONV: image base offset (b*Hs*Ws*Cin)
-    int row_yx[8];          // CONV: y | x << 16 ; -1 if row >= M
     const int Hs = p.upsample ? (p.H >> 1) : p.H;
     const int Ws = p.upsample ? (p.W >> 1) : p.W;
+    const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*2048 for row r0+16i
+    const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
+    const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
+    int it = 0;  // running k-block counter across tiles (pipeline position)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % n_tiles;
+      const int m0 = (tile / n_tiles) * BM;
+      long long row_base[8];  // PLAIN: element offset of the row; CONV: image base offset
+      int row_yx[8];          // CONV: y | x << 16 ; -1 if row >= M
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + r0 + 16 * i;
-      if (m >= p.M) {
-        row_base[i] = 0;
-        row_yx[i] = -1;
-      } else if (p.a_mode == MST_A_PLAIN) {
-        row_base[i] = (long long)m * p.lda;
-        row_yx[i] = 0;
-      } else {
-        const int hw = p.H * p.W;
-        const int b = m / hw;
-        const int rem = m - b * hw;
-        const int y = rem / p.W;
-        const int x = rem - y * p.W;
-        row_base[i] = (long long)b * Hs * Ws * p.Cin;
-        row_yx[i] = y | (x << 16);
-      }
-    }
-    const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*2048 for row r0+16i (two 8-row groups further)
-
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      if (kb >= STAGES) mbar_wait(smem_u32(&empty_bar[s]), ((kb / STAGES) - 1) & 1);
-      const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
-      const uint32_t b_stage = a_stage + A_STAGE_BYTES;
-      const int k0 = kb * BK + c * 8;
-      // ---- A tile: 128 rows x 64 k ----
-      if (p.a_mode == MST_A_PLAIN) {
-        const bool kvalid = k0 < p.K;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool valid = kvalid && row_yx[i] >= 0;
-          const bf16* src = reinterpret_cast<const bf16*>(p.A) + (valid ? row_base[i] + k0 : 0);
-          cp_async16(a_stage + a_dst0 + i * 2048, src, valid);
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + r0 + 16 * i;
+        if (m >= p.M) {
+          row_base[i] = 0;
+          row_yx[i] = -1;
+        } else if (p.a_mode == MST_A_PLAIN) {
+          row_base[i] = (long long)m * p.lda;
+          row_yx[i] = 0;
+        } else {
+          const int hw = p.H * p.W;
+          const int b = m / hw;
+          const int rem = m - b * hw;
+          const int y = rem / p.W;
+          const int x = rem - y * p.W;
+          row_base[i] = (long long)b * Hs * Ws * p.Cin;
+          row_yx[i] = y | (x << 16);
         }
-      } else {
-        const int tap = k0 / p.Cin;
-        const int ch = k0 - tap * p.Cin;
-        const int ky = tap / 3, kx = tap - ky * 3;
-        const bool kvalid = tap < 9;
+      }
+      const uint8_t* wtile = Wbase + (size_t)n_tile * nkb * Cfg::B_STAGE_BYTES;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) - 1) & 1);
+        const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
+        if (t == 0) {  // weight tile: one bulk copy of the pre-swizzled [BN x 64] block
+          mbar_arrive_expect_tx(smem_u32(&full_bar[s]), Cfg::B_STAGE_BYTES);
+          bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
+        }
+        const int k0 = kb * BK + c * 8;
+        if (p.a_mode == MST_A_PLAIN) {
+          const bool kvalid = k0 < p.K;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          bool valid = kvalid && row_yx[i] >= 0;
-          int yy = (row_yx[i] & 0xFFFF) + ky - 1;
-          int xx = (row_yx[i] >> 16) + kx - 1;
-          if (p.pad_mode == 1) {  // reflect (no edge repeat): -1 -> 1, H -> H-2
-            yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
-            xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
-          } else {
-            valid = valid && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+          for (int i = 0; i < 8; ++i) {
+            const bool valid = kvalid && row_yx[i] >= 0;
+            cp_async16(a_stage + a_dst0 + i * 2048, Abase + (valid ? row_base[i] + k0 : 0), valid);
           }
-          if (p.upsample) { yy >>= 1; xx >>= 1; }
-          const long long off = valid ? row_base[i] + ((long long)(yy * Ws + xx)) * p.Cin + ch : 0;
-          cp_async16(a_stage + a_dst0 + i * 2048, reinterpret_cast<const bf16*>(p.A) + off, valid);
-        }
-      }
-      // ---- B tile: BN rows (output channels) x 64 k, always in range (weights are padded) ----
-      {
-        const bf16* wsrc = reinterpret_cast<const bf16*>(p.Wt) + (long long)(n0 + r0) * p.k_pad + kb * BK + c * 8;
+        } else {
+          const int tap = k0 / p.Cin;
+          const int ch = k0 - tap * p.Cin;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const bool kvalid = tap < 9;
 #pragma unroll
-        for (int i = 0; i < (BN + 15) / 16; ++i) {
-          if (BN >= 16 || r0 + 16 * i < BN)
-            cp_async16(b_stage + a_dst0 + i * 2048, wsrc + (long long)i * 16 * p.k_pad, true);
+          for (int i = 0; i < 8; ++i) {
+            bool valid = kvalid && row_yx[i] >= 0;
+            int yy = (row_yx[i] & 0xFFFF) + ky - 1;
+            int xx = (row_yx[i] >> 16) + kx - 1;
+            if (p.pad_mode == 1) {  // reflect (no edge repeat): -1 -> 1, H -> H-2
+              yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+              xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+            } else {
+              valid = valid && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+            }
+            if (p.upsample) { yy >>= 1; xx >>= 1; }
+            const long long off = valid ? row_base[i] + ((long long)(yy * Ws + xx)) * p.Cin + ch : 0;
+            cp_async16(a_stage + a_dst0 + i * 2048, Abase + off, valid);
+          }
         }
-      }
-      cp_async_commit();
-      if (kb >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&full_bar[(kb - LAG) % STAGES]));
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(smem_u32(&full_bar[(it - LAG) % STAGES]));
+        }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    for (int kb = (nkb > LAG ? nkb - LAG : 0); kb < nkb; ++kb) mbar_arrive(smem_u32(&full_bar[kb % STAGES]));
-
-    // =========================== epilogue ===========================
-    mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < p.M;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    long long nchw_base = 0;
-    int hw = 0;
-    if (p.out_nchw && row_ok) {
-      hw = p.H * p.W;
-      const int b = row / hw;
-      nchw_base = (long long)b * p.n_real * hw + (row - b * hw);
-    }
-#pragma unroll 1
-    for (int col0 = 0; col0 < BN; col0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_row + col0, v);
-      tmem_wait_ld();
-      if (!row_ok) continue;
-      const int n = n0 + col0;
-      float x[16];
+    for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) mbar_arrive(smem_u32(&full_bar[j % STAGES]));
+  } else if (warp == NUM_EPI_WARPS + NUM_PROD_WARPS) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(smem_u32(&full_bar[s]), (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t b_stage = a_stage + A_STAGE_BYTES;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        x[j] = __uint_as_float(v[j]);
-        if (p.bias) x[j] += __ldg(p.bias + n + j);
-        if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
-        else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
-      }
-      if (p.res) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.res + (long long)row * p.ld_res + n);
-        if (p.mul) {
-          const float4* m4 = reinterpret_cast<const float4*>(p.mul + (long long)row * p.ld_res + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 r = r4[j], m = m4[j];
-            x[4 * j + 0] += r.x * m.x; x[4 * j + 1] += r.y * m.y; x[4 * j + 2] += r.z * m.z; x[4 * j + 3] += r.w * m.w;
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, umma_desc_sw128(a_stage + k * 32), umma_desc_sw128(b_stage + k * 32), idesc, (kb | k) != 0);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 r = r4[j];
-            x[4 * j + 0] += r.x; x[4 * j + 1] += r.y; x[4 * j + 2] += r.z; x[4 * j + 3] += r.w;
-          }
+          umma_commit(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
+          if (kb == nkb - 1) umma_commit(smem_u32(&tmem_full_bar[buf]));  // accumulator complete
         }
-      }
-      if (p.out_nchw) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n + j < p.n_real) p.out_f32[nchw_base + (long long)(n + j) * hw] = x[j];
-      } else {
-        if (p.out_f32) {
-          float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ld_out32 + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        }
-        if (p.out_bf16) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n);
-          o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        __syncwarp();
       }
     }
     tc_fence_before();
   } else {
-    // =========================== MMA issuer (warp 4) ===========================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      mbar_wait(smem_u32(&full_bar[s]), (kb / STAGES) & 1);
+    // =========================== epilogue (warps 0-7) ===========================
+    constexpr int CPW = Cfg::COLS_PER_WARP;
+    constexpr int CH = CPW >= 32 ? 32 : 16;  // columns per tcgen05.ld
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    const bool active = half < Cfg::EPI_SPLIT;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      const int n_tile = tile % n_tiles;
+      const int m0 = (tile / n_tiles) * BM;
+      mbar_wait(smem_u32(&tmem_full_bar[buf]), (tcount >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
-        const uint32_t b_stage = a_stage + A_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-          const uint64_t ad = umma_desc_sw128(a_stage + k * 32);
-          const uint64_t bd = umma_desc_sw128(b_stage + k * 32);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0);
+      if (active) {
+        const int row = m0 + quad * 32 + lane;
+        const bool row_ok = row < p.M;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + half * CPW;
+        const int nbase = n_tile * BN + half * CPW;
+        long long nchw_base = 0;
+        int hw = 0;
+        if (p.out_nchw && row_ok) {
+          hw = p.H * p.W;
+          const int b = row / hw;
+          nchw_base = (long long)b * p.n_real * hw + (row - b * hw);
         }
-        umma_commit(smem_u32(&empty_bar[s]));                  // smem stage reusable once these MMAs retire
-        if (kb == nkb - 1) umma_commit(smem_u32(&accum_bar));  // accumulator complete
+#pragma unroll 1
+        for (int col0 = 0; col0 < CPW; col0 += CH) {
+          uint32_t v[CH];
+          if constexpr (CH == 32) tmem_ld32(t_row + col0, v);
+          else tmem_ld16(t_row + col0, v);
+          tmem_wait_ld();
+          if (col0 + CH >= CPW) {  // last read of this accumulator: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+          }
+          if (!row_ok) continue;
+          const int n = nbase + col0;
+          float x[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            x[j] = __uint_as_float(v[j]) + bias_s[n + j];
+            if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
+            else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
+          }
+          if (p.res) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.res + (long long)row * p.ld_res + n);
+            if (p.mul) {
+              const float4* m4 = reinterpret_cast<const float4*>(p.mul + (long long)row * p.ld_res + n);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 r = r4[j], m = m4[j];
+                x[4 * j + 0] += r.x * m.x; x[4 * j + 1] += r.y * m.y; x[4 * j + 2] += r.z * m.z; x[4 * j + 3] += r.w * m.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 r = r4[j];
+                x[4 * j + 0] += r.x; x[4 * j + 1] += r.y; x[4 * j + 2] += r.z; x[4 * j + 3] += r.w;
+              }
+            }
+          }
+          if (p.out_nchw) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.n_real) p.out_f32[nchw_base + (long long)(n + j) * hw] = x[j];
+          } else {
+            if (p.out_f32) {
+              float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ld_out32 + n);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
+            if (p.out_bf16) {
+              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
-      __syncwarp();
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NUM_EPI_WARPS + NUM_PROD_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
+
+static int g_num_sms = 0;
 
 template <int BN>
 static int launch_gemm(const MstGemm& g, cudaStream_t st) {
@@ -261,19 +311,81 @@ static int launch_gemm(const MstGemm& g, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
   const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN);
   if (tiles <= 0 || tiles > 0x7fffffffLL) return MST_ERR_BAD_ARG;
-  gemm_tc_kernel<BN><<<(unsigned)tiles, 160, Cfg::SMEM_BYTES, st>>>(g);
+  const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(g, (int)tiles);
   return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- weight packing (tile-blocked, pre-swizzled)
+// dst is the exact shared-memory image of every [bn x 64] weight tile: block (n_tile, kb) is contiguous
+// (bn*128 bytes) and inside it row r, 16-byte chunk c sits at sw128_offset(r, c) -- so one cp.async.bulk
+// lands a ready-to-use SWIZZLE_128B K-major UMMA operand.
+template <bool CONV>
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, int Cin, bf16* __restrict__ dst, int n_pad,
+                                   int k_pad, int bn) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pad * k_pad) return;
+  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
+  float v = 0.f;
+  if (n < N && k < K) {
+    if (CONV) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      v = w[((long long)n * Cin + ci) * 9 + tap];  // [N][Cin][3][3] -> k = (ky*3+kx)*Cin + ci
+    } else {
+      v = w[(long long)n * K + k];
+    }
+  }
+  const int nkb = k_pad / 64;
+  const int n_tile = n / bn, r = n - n_tile * bn;
+  const int kb = k / 64, kk = k - kb * 64;
+  const int c = kk >> 3, e = kk & 7;
+  const long long block = ((long long)n_tile * nkb + kb) * bn * 64;  // elements
+  const long long off = block + ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) / 2 + e;
+  dst[off] = __float2bfloat16(v);
+}
+
+static int tile_n_for(int n_pad) {
+  if (n_pad % 256 == 0) return 256;
+  if (n_pad % 128 == 0) return 128;
+  if (n_pad % 64 == 0) return 64;
+  if (n_pad % 32 == 0) return 32;
+  return 16;
 }
 
 }  // namespace mst
 
+using namespace mst;
+
+extern "C" int mst_gemm_tile_n(int n_pad) { return n_pad > 0 && n_pad % 16 == 0 ? tile_n_for(n_pad) : MST_ERR_BAD_ARG; }
+
+extern "C" int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
+  if (!w || !dst || N <= 0 || K <= 0 || n_pad < N || k_pad < K || n_pad % 16 || k_pad % 64) return MST_ERR_BAD_ARG;
+  const long long n = (long long)n_pad * k_pad;
+  pack_weight_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, 0, reinterpret_cast<bf16*>(dst),
+                                                                                         n_pad, k_pad, tile_n_for(n_pad));
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
+  if (!w || !dst || N <= 0 || Cin <= 0 || n_pad < N || k_pad < 9 * Cin || n_pad % 16 || k_pad % 64) return MST_ERR_BAD_ARG;
+  const long long n = (long long)n_pad * k_pad;
+  pack_weight_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, 9 * Cin, Cin, reinterpret_cast<bf16*>(dst),
+                                                                                        n_pad, k_pad, tile_n_for(n_pad));
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mst_gemm(const MstGemm* g, void* stream) {
-  using namespace mst;
   if (!g || !g->A || !g->Wt) return MST_ERR_BAD_ARG;
   if (g->M <= 0 || g->N <= 0 || g->K <= 0 || g->k_pad % BK != 0 || g->k_pad < g->K) return MST_ERR_BAD_ARG;
-  if (g->N % 16 != 0 || g->K % 8 != 0) return MST_ERR_UNSUPPORTED;
+  if (g->N % 16 != 0 || g->K % 8 != 0 || g->N > MAX_BIAS) return MST_ERR_UNSUPPORTED;
   if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
   if (g->mul && !g->res) return MST_ERR_BAD_ARG;
   if (g->a_mode == MST_A_PLAIN) {
@@ -293,9 +405,12 @@ extern "C" int mst_gemm(const MstGemm* g, void* stream) {
     if (g->res && g->ld_res % 4 != 0) return MST_ERR_BAD_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int N = g->N;
-  if (N % 128 == 0) return launch_gemm<128>(*g, st);
-  if (N % 64 == 0) return launch_gemm<64>(*g, st);
-  if (N % 32 == 0) return launch_gemm<32>(*g, st);
-  return launch_gemm<16>(*g, st);
+  // the tile width is a property of the packed weight (N here must be the n_pad it was packed with)
+  switch (tile_n_for(g->N)) {
+    case 256: return launch_gemm<256>(*g, st);
+    case 128: return launch_gemm<128>(*g, st);
+    case 64: return launch_gemm<64>(*g, st);
+    case 32: return launch_gemm<32>(*g, st);
+    default: return launch_gemm<16>(*g, st);
+  }
 }

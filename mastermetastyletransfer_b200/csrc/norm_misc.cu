@@ -173,23 +173,6 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------- packing / casts
-__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, bf16* __restrict__ dst, int n_pad, int k_pad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_pad * k_pad) return;
-  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
-  dst[i] = __float2bfloat16((n < N && k < K) ? w[(long long)n * K + k] : 0.f);
-}
-__global__ void pack_conv_kernel(const float* __restrict__ w, int N, int Cin, bf16* __restrict__ dst, int n_pad, int k_pad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_pad * k_pad) return;
-  const int n = (int)(i / k_pad), k = (int)(i % k_pad);
-  float v = 0.f;
-  if (n < N && k < 9 * Cin) {
-    const int tap = k / Cin, ci = k - tap * Cin;
-    v = w[((long long)n * Cin + ci) * 9 + tap];  // [N][Cin][3][3] -> tap = ky*3+kx
-  }
-  dst[i] = __float2bfloat16(v);
-}
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -245,20 +228,6 @@ extern "C" int mst_patch_embed(const float* img, const float* w, const float* b,
   const long long total = (long long)B * (S / 4) * (S / 4);
   const int per = 64;
   patch_embed_kernel<<<(unsigned)((total + per - 1) / per), 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, B, S, per);
-  return (int)cudaGetLastError();
-}
-
-extern "C" int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
-  if (!w || !dst || N <= 0 || K <= 0 || n_pad < N || k_pad < K) return MST_ERR_BAD_ARG;
-  const long long n = (long long)n_pad * k_pad;
-  pack_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, reinterpret_cast<bf16*>(dst), n_pad, k_pad);
-  return (int)cudaGetLastError();
-}
-
-extern "C" int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
-  if (!w || !dst || N <= 0 || Cin <= 0 || n_pad < N || k_pad < 9 * Cin) return MST_ERR_BAD_ARG;
-  const long long n = (long long)n_pad * k_pad;
-  pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, Cin, reinterpret_cast<bf16*>(dst), n_pad, k_pad);
   return (int)cudaGetLastError();
 }
 

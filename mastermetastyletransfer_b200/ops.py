@@ -36,7 +36,7 @@ class timing:
         return False
 
 
-def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
+def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = "") -> None:
     """Run one C-ABI call (= one kernel launch), count it, and time it when a timing() context is active."""
     global launch_count
     if _records is None:
@@ -46,7 +46,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
         a.record()
         check(fn(), name)
         b.record()
-        _records.append((KERNEL_OF.get(name, name), flops, nbytes, a, b))
+        _records.append((KERNEL_OF.get(name, name), flops, nbytes, a, b, desc))
     launch_count += 1
 
 
@@ -122,7 +122,7 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
          res: Optional[torch.Tensor] = None, mul: Optional[torch.Tensor] = None,
          out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
          ld_out32: Optional[int] = None, ld_out16: Optional[int] = None, ld_res: Optional[int] = None,
-         conv: Optional[dict] = None, n_rows: Optional[int] = None) -> None:
+         conv: Optional[dict] = None) -> None:
     """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h)."""
     g = MstGemm()
     g.A = _ptr(A, torch.bfloat16, "A")
@@ -132,7 +132,7 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
     g.mul = _ptr(mul, torch.float32, "mul")
     g.out_f32 = _ptr(out_f32, torch.float32, "out_f32")
     g.out_bf16 = _ptr(out_bf16, torch.bfloat16, "out_bf16")
-    N = pm.n_pad if n_rows is None else n_rows
+    N = pm.n_pad
     g.M, g.N, g.K, g.k_pad = M, N, pm.K, pm.k_pad
     g.lda = pm.K if lda is None else lda
     g.ld_res = N if ld_res is None else ld_res
@@ -146,7 +146,8 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
         g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
         g.out_nchw, g.n_real = int(conv.get("out_nchw", False)), conv.get("n_real", pm.N)
-    _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=2.0 * M * min(N, pm.N) * pm.K)
+    _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=2.0 * M * min(N, pm.N) * pm.K,
+            desc=f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}")
 
 
 def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
@@ -162,7 +163,8 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
     n_tok = ws * ws
     n_win = B * (-(-H // ws)) * (-(-W // ws))
     _launch("mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
-            flops=2.0 * n_win * heads * n_tok * n_tok * 32 * (3 if v2 is not None else 2))
+            flops=2.0 * n_win * heads * n_tok * n_tok * 32 * (3 if v2 is not None else 2),
+            desc=f"B={B} H={H} heads={heads} ws={ws} shift={shift} dual={v2 is not None}")
 
 
 def window_maps(H: int, W: int, ws: int, shift: int, device="cuda"):
