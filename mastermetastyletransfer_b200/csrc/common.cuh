@@ -57,6 +57,11 @@ template <int N>
 MST_DEVINL void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// mbarrier arrival that fires when all cp.async previously issued by this thread have completed
+MST_DEVINL void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+MST_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 MST_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -47,7 +47,6 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm p, const int num_tiles) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int LAG = 2;  // cp.async groups kept in flight per producer thread before the stage is published
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
@@ -158,17 +157,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
             cp_async16(a_stage + a_dst0 + i * 2048, Abase + off, valid);
           }
         }
-        cp_async_commit();
-        if (it >= LAG) {
-          cp_async_wait<LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(smem_u32(&full_bar[(it - LAG) % STAGES]));
-        }
+        // asynchronous arrival: counts as this thread's arrival once all of its cp.async above have landed,
+        // so the thread never blocks and every stage of the ring can be in flight
+        cp_async_mbar_arrive_noinc(smem_u32(&full_bar[s]));
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) mbar_arrive(smem_u32(&full_bar[j % STAGES]));
+    cp_async_wait_all();  // nothing may still be writing shared memory when the CTA exits
   } else if (warp == NUM_EPI_WARPS + NUM_PROD_WARPS) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);

@@ -124,6 +124,11 @@ def main():
 
         model = make_model(8)
         sd = {k: v.clone() for k, v in model.state_dict().items()}
+        import json
+        layout = {k: [list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()}
+        layout_vgg = {k: [list(v.shape), str(v.dtype)] for k, v in loss.feature_extractor_model.state_dict().items()}
+        with open(os.path.join(GOLD, "state_dict_layout.json"), "w") as fh:
+            json.dump({"model": layout, "loss.feature_extractor_model": layout_vgg}, fh, indent=0, sort_keys=True)
         vgg_sd = {k: v.clone() for k, v in loss.feature_extractor_model.features.state_dict().items()}
         st_sd = {k[len("style_transformer."):]: v for k, v in sd.items() if k.startswith("style_transformer.")}
         worst = {}

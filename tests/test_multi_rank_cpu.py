@@ -1,0 +1,53 @@
+"""CPU suite: the N>1 plumbing under gloo, world_size 2 (image sharding, max-over-ranks timing)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mastermetastyletransfer_b200 import parallel
+
+
+def test_shard_range_covers_everything_once():
+    for total in (1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            spans = [parallel.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = parallel.shard_range(33, rank, world)
+        images = torch.arange(33.0)[lo:hi]
+        mx = parallel.max_over_ranks(10.0 + rank)
+        total = parallel.sum_over_ranks(float(images.sum()))
+        count = parallel.sum_over_ranks(float(hi - lo))
+        dist.barrier()
+        q.put((rank, mx, total, count))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_timing_reduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, mx, total, count in out:
+        assert mx == 11.0            # max over ranks, as bench.py reduces its device timings
+        assert total == sum(range(33))  # every image processed exactly once
+        assert count == 33

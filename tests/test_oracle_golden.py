@@ -1,0 +1,119 @@
+"""CPU suite: the oracle restatement against the golden vectors minted from the real reference
+(oracle/make_golden.py).  Integer maps bit-exact, fp32 tensors to 1e-4 of their magnitude."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mastermetastyletransfer_b200 import synthetic
+from oracle import master_oracle as O
+
+
+@pytest.fixture(scope="module")
+def model_sd():
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel
+    m = MasterStyleTransferModel()
+    synthetic.fill_state_dict_(m, 0)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+@pytest.fixture(scope="module")
+def vgg_sd():
+    vgg = synthetic.build_vgg19_to_relu5_1()
+    synthetic.fill_state_dict_(vgg, 0, prefix="vgg.")
+    return {k: v.detach().clone() for k, v in vgg.state_dict().items()}
+
+
+def close(a, gold, tol=1e-4):
+    gold = torch.from_numpy(np.asarray(gold)).float()
+    return (a.float() - gold).abs().max().item() <= tol * max(1.0, gold.abs().max().item())
+
+
+@pytest.mark.parametrize("H,ws,s", [(32, 8, 4), (64, 8, 4), (16, 8, 4), (8, 8, 4), (32, 7, 4), (64, 7, 4), (32, 7, 3), (64, 7, 3), (16, 7, 3)])
+def test_integer_maps_bit_exact(golden_dir, H, ws, s):
+    gold = np.load(os.path.join(golden_dir, "maps.npz"))
+    Hp, Wp = O.padded_dims(H, H, ws)
+    g = O.window_gather_map(H, H, ws, s)
+    y, x = g // Wp, g % Wp
+    mine = torch.where((y < H) & (x < H), y * H + x, torch.full_like(g, -1))
+    assert np.array_equal(mine.numpy(), gold[f"gather_{H}_{ws}_{s}"])
+    m = O.shift_mask(H, H, ws, s)
+    key = f"mask_{H}_{ws}_{s}"
+    assert (m is None) == (key not in gold)
+    if m is not None:
+        assert np.array_equal((m != 0).numpy().astype(np.uint8), gold[key])
+        assert set(m.unique().tolist()) <= {0.0, -100.0}
+    assert np.array_equal(O.relative_position_index(ws).numpy(), gold[f"relidx_{ws}"].astype(np.int64))
+
+
+def test_gather_map_is_a_permutation_of_the_padded_grid():
+    for H, ws, s in [(32, 8, 4), (32, 7, 3), (20, 7, 3), (24, 8, 4)]:
+        Hp, Wp = O.padded_dims(H, H, ws)
+        g = O.window_gather_map(H, H, ws, s).reshape(-1)
+        assert sorted(g.tolist()) == list(range(Hp * Wp))
+
+
+@pytest.mark.parametrize("ws,s", [(8, 4), (7, 4), (7, 3)])
+def test_window_attention_component(golden_dir, ws, s):
+    gold = np.load(os.path.join(golden_dir, "path_128.npz"))
+    from mastermetastyletransfer_b200 import ShiftedWindowAttention
+    mod = ShiftedWindowAttention(256, 8, [ws, ws], [s, s])
+    synthetic.fill_state_dict_(mod, 0, prefix=f"unit{ws}.")
+    g = torch.Generator().manual_seed(77 + ws + s)
+    xq, xk, xv = (torch.randn(2, 16, 16, 256, generator=g) for _ in range(3))
+    out = O.window_attention(xq, xk, xv, *O._attn_weights(mod.state_dict(), ""), ws, s, 8)
+    assert close(out[:, ::2, ::2, ::4], gold[f"wattn_{ws}_{s}"])
+
+
+def test_path_128_against_reference_goldens(golden_dir, model_sd):
+    gold = np.load(os.path.join(golden_dir, "path_128.npz"))
+    content, style = synthetic.synthetic_images(2, 128, seed=0)
+    st = {n[len("style_transformer."):]: t for n, t in model_sd.items() if n.startswith("style_transformer.")}
+    with torch.no_grad():
+        fc = O.swin_encoder(model_sd, content, "swin_encoder.")
+        fs = O.swin_encoder(model_sd, style, "swin_encoder.")
+        assert close(fc[:, ::2, ::2, ::4], gold["fc"])
+        key, scale, shift = O.style_encoder(st, fs, fs, fs, 8, 4, 8)
+        assert close(key[:, ::2, ::2, ::4], gold["enc_key"]) and close(scale[:, ::2, ::2, ::4], gold["enc_scale"])
+        assert close(shift[:, ::2, ::2, ::4], gold["enc_shift"])
+        out1 = O.style_transformer(st, fc, fs, 1)
+        assert close(out1[:, ::2, ::2, ::4], gold["st_k1"])
+        assert close(O.style_transformer(st, fc, fs, 2)[:, ::2, ::2, ::4], gold["st_k2"])
+        img = O.cnn_decoder(model_sd, out1.permute(0, 3, 1, 2), "decoder.decoder.")
+        assert close(img, gold["img_k1"])
+        assert close(O.cnn_decoder(model_sd, fc.permute(0, 3, 1, 2), "decoder.decoder.")[:, :, ::2, ::2], gold["cnn_dec"])
+
+
+def test_config1_256_against_reference_goldens(golden_dir, model_sd):
+    gold = np.load(os.path.join(golden_dir, "path_256.npz"))
+    content, style = synthetic.synthetic_images(1, 256, seed=1)
+    with torch.no_grad():
+        img = O.full_forward(model_sd, content, style, 1)
+    assert close(img[:, :, ::4, ::4], gold["img_k1"])
+    stats = gold["img_k1_stats"]
+    assert abs(img.mean().item() - stats[0]) < 1e-5 and abs(img.std().item() - stats[1]) < 1e-5
+
+
+def test_loss_against_reference_goldens(golden_dir, model_sd, vgg_sd):
+    gold = np.load(os.path.join(golden_dir, "path_128.npz"))
+    content, style = synthetic.synthetic_images(2, 128, seed=0)
+    img = torch.from_numpy(gold["img_k1"])
+    with torch.no_grad():
+        taps = O.vgg_taps(vgg_sd, img)
+        for i, t in enumerate(taps):
+            assert close(t.mean(dim=(2, 3)), gold[f"tap{i}_mean"]) and close(t.std(dim=(2, 3)), gold[f"tap{i}_std"])
+        tot, lc, ls = O.overall_loss(vgg_sd, content, style, img, lam=10.0)
+        np.testing.assert_allclose([tot.item(), lc.item(), ls.item()], gold["loss"], rtol=1e-5)
+        tot2, lc2, ls2 = O.overall_loss(vgg_sd, content, style, img, 10.0, True, True)
+        np.testing.assert_allclose([tot2.item(), lc2.item(), ls2.item()], gold["loss_squared"], rtol=1e-5)
+    with pytest.raises(AssertionError):
+        O.overall_loss(vgg_sd, content, style[:1], img)  # codes/loss.py:212 shape assertion
+
+
+def test_instance_norm_twice_is_not_idempotent():
+    """IN(IN(x)) != IN(x) at eps=1e-5 -- the reference applies both, so does the oracle."""
+    x = torch.randn(1, 8, 8, 4, generator=torch.Generator().manual_seed(0)) * 0.01
+    once = O.instance_norm_bhwc(x)
+    assert (O.instance_norm_bhwc(once) - once).abs().max() > 1e-4
