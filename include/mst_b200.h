@@ -131,6 +131,38 @@ int mst_patch_embed(const float* img, const float* w, const float* b, const floa
 /* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
 int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * VGG-19 perceptual loss (codes/loss.py).  Activations are bf16 NHWC; the twelve 64..512-channel
+ * convolutions go through mst_gemm (MST_A_CONV3X3, zero padding, ReLU epilogue).
+ * mst_conv3x3_first: features[0] Conv2d(3,64,3,pad 1) (+ReLU features[1]) on fp32 NCHW images
+ *   (loss.py:23-25) -> bf16 [B,H,W,64].
+ * mst_maxpool2x2: nn.MaxPool2d(2) on bf16 [B,H,W,C] (features[4,9,18,27]).
+ * mst_tap_stats: per (image, channel) mean and biased variance over T=H*W of a tap [B,T,C]
+ *   (the statistics both loss terms need: loss.py:102-105 InstanceNorm2d, :122-130 mean/std).
+ * mst_content_term: sum over all elements of |IN(Fc)-IN(Fcs)| (squared=0, "euclidian", loss.py:114-116)
+ *   or its square (loss.py:110-112) as n_partials deterministic per-CTA partial sums.
+ * mst_loss_finalize: content = sum_taps partial_sum/(B*T*C); style = sum_taps mean|mu_s-mu_o| +
+ *   mean|std_s-std_o| with the unbiased std torch.std uses (loss.py:122-130,293-315);
+ *   out3 = {content + lambda*style, content, style} (loss.py:243).
+ * ------------------------------------------------------------------------------------------ */
+int mst_conv3x3_first(const float* img, const float* w, const float* b, mst_bf16* out, int B, int H, int W, int relu,
+                      void* stream);
+int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream);
+int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, void* stream);
+int mst_content_term(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
+                     const float* var_o, int B, int T, int C, int squared, float* partials, int n_partials, void* stream);
+
+typedef struct MstLossTap {
+  const float* partials; /* content-term partial sums of this tap */
+  const float *mean_s, *var_s, *mean_o, *var_o; /* [B,C] statistics of the style / output taps */
+  int n_partials, B, T, C;
+} MstLossTap;
+typedef struct MstLossTaps {
+  MstLossTap tap[4];
+  int n_taps;
+} MstLossTaps;
+int mst_loss_finalize(const MstLossTaps* taps, float lambda, int squared_style, float* out3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ Drop-in mirrors of the reference's codes/{full_model,style_transformer,decoder,l
 forward passes run hand-written CUDA kernels behind the C ABI in include/mst_b200.h.
 """
 from .decoder import Decoder  # noqa: F401
+from .loss import VGG19_custom, custom_loss  # noqa: F401
 from .full_model import MasterStyleTransferModel, SwinEncoderB200  # noqa: F401
 from .style_transformer import (ShiftedWindowAttention, ShiftedWindowAttention_for_decoder_last_MHA,  # noqa: F401
                                 StyleDecoder, StyleEncoder, StyleSwinTransformerBlock, StyleTransformer)

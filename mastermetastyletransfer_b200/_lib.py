@@ -37,6 +37,15 @@ class MstWindowAttn(C.Structure):
     ]
 
 
+class MstLossTap(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("mean_s", C.c_void_p), ("var_s", C.c_void_p), ("mean_o", C.c_void_p),
+                ("var_o", C.c_void_p), ("n_partials", C.c_int), ("B", C.c_int), ("T", C.c_int), ("C", C.c_int)]
+
+
+class MstLossTaps(C.Structure):
+    _fields_ = [("tap", MstLossTap * 4), ("n_taps", C.c_int)]
+
+
 # every symbol include/mst_b200.h declares: name -> (restype, argtypes)
 _I, _P, _Z = C.c_int, C.c_void_p, C.c_size_t
 SYMBOLS = {
@@ -55,6 +64,11 @@ SYMBOLS = {
     "mst_instnorm_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
+    "mst_conv3x3_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mst_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "mst_content_term": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "mst_loss_finalize": (_I, [C.POINTER(MstLossTaps), C.c_float, _I, _P, _P]),
 }
 
 _lib = None

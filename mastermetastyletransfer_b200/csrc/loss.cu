@@ -1,0 +1,251 @@
+// VGG-19 perceptual-loss side kernels (codes/loss.py): the Cin=3 first convolution, 2x2 max-pool, and the
+// HBM-streaming reductions of the content / style loss.  The other twelve VGG convolutions run through the
+// tensor-core implicit GEMM (gemm_tc.cu, zero padding + ReLU epilogue).  Activations are bf16 NHWC.
+#include "../../include/mst_b200.h"
+#include "common.cuh"
+
+namespace mst {
+
+// ---------------------------------------------------------------- conv1_1: 3 -> 64, K = 27 (HBM-bound)
+// One thread per output pixel, 64 accumulators in registers, weights [27][64] in shared memory.
+__global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, bf16* __restrict__ out, int B,
+                                                            int H, int W, int relu) {
+  __shared__ float ws[27 * 64];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int k = i / 64, n = i - k * 64;  // k = ci*9 + ky*3 + kx
+    ws[i] = w[n * 27 + k];
+  }
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W;
+  if (pix >= total) return;
+  const int b = (int)(pix / ((long long)H * W));
+  const int rem = (int)(pix - (long long)b * H * W);
+  const int y = rem / W, x = rem - y * W;
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        const bool ok = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
+        in[ci * 9 + ky * 3 + kx] = ok ? img[(((long long)b * 3 + ci) * H + yy) * W + xx] : 0.f;
+      }
+  uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+  for (int n0 = 0; n0 < 64; n0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[n0 + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + k * 64 + n0);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + k * 64 + n0 + 4);
+      acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+      acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+      acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+      acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[2 * j], c = acc[2 * j + 1];
+      if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, c);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    o4[n0 / 8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// ---------------------------------------------------------------- 2x2 max-pool, bf16 NHWC, 8 channels per thread
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8, int Ho,
+                                                         int Wo, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int c8 = (int)(i % C8);
+  long long p = i / C8;
+  const int xo = (int)(p % Wo); p /= Wo;
+  const int yo = (int)(p % Ho);
+  const long long b = p / Ho;
+  const int W = 2 * Wo;
+  const uint4* src = reinterpret_cast<const uint4*>(x);
+  const long long base = ((b * 2 * Ho + 2 * yo) * W + 2 * xo) * C8 + c8;
+  const uint4 v[4] = {src[base], src[base + C8], src[base + (long long)W * C8], src[base + (long long)W * C8 + C8]};
+  uint4 r;
+  uint32_t* rp = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 m = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[0]) + j);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const uint32_t*>(&v[q]) + j));
+    rp[j] = *reinterpret_cast<uint32_t*>(&m);
+  }
+  reinterpret_cast<uint4*>(y)[i] = r;
+}
+
+// ---------------------------------------------------------------- per-(image, channel) mean / biased variance of a bf16 tap
+// x [B,T,C] bf16.  CTA = (b, 64-channel group): lane owns 2 channels (one 32-bit load), 8 warps stride over T.
+// Single pass with a per-thread shift (first value) to keep the sum of squares well conditioned.
+__global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ mean,
+                                                        float* __restrict__ var, int T, int C) {
+  __shared__ float red[3][8][65];
+  const int groups = C / 64;
+  const int b = blockIdx.x / groups;
+  const int c = (blockIdx.x - b * groups) * 64 + 2 * (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C + c);
+  const int stride = C / 2;
+  // shift = the channel's first element (same for all warps of the CTA)
+  const uint32_t f = xb[0];
+  const float k0 = __uint_as_float(f << 16), k1 = __uint_as_float(f & 0xFFFF0000u);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    const uint32_t u = xb[(long long)t * stride];
+    const float a = __uint_as_float(u << 16) - k0, d = __uint_as_float(u & 0xFFFF0000u) - k1;
+    s0 += a; q0 = fmaf(a, a, q0);
+    s1 += d; q1 = fmaf(d, d, q1);
+  }
+  red[0][warp][2 * lane] = s0; red[0][warp][2 * lane + 1] = s1;
+  red[1][warp][2 * lane] = q0; red[1][warp][2 * lane + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s += red[0][w][threadIdx.x]; q += red[1][w][threadIdx.x]; }
+    const int cc = (blockIdx.x - b * groups) * 64 + threadIdx.x;
+    const uint32_t fu = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C + (cc & ~1))[0];
+    const float k = (cc & 1) ? __uint_as_float(fu & 0xFFFF0000u) : __uint_as_float(fu << 16);
+    const float m = s / (float)T;
+    mean[(long long)b * C + cc] = m + k;
+    var[(long long)b * C + cc] = fmaxf(q / (float)T - m * m, 0.f);
+  }
+}
+
+// ---------------------------------------------------------------- content term: sum |IN(Fc) - IN(Fcs)| (or squared)
+// fc, fo [B,T,C] bf16; stats [B,C].  Grid-stride over 8-channel vectors; deterministic per-CTA partial sums.
+__global__ void __launch_bounds__(256) content_term_kernel(const bf16* __restrict__ fc, const bf16* __restrict__ fo,
+                                                           const float* __restrict__ mean_c, const float* __restrict__ var_c,
+                                                           const float* __restrict__ mean_o, const float* __restrict__ var_o,
+                                                           long long n8, int TC8, int C8, int squared, float* __restrict__ partials) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / TC8);
+    const int c = (int)(i % C8) * 8;
+    const uint4 a = reinterpret_cast<const uint4*>(fc)[i];
+    const uint4 o = reinterpret_cast<const uint4*>(fo)[i];
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* op = reinterpret_cast<const uint32_t*>(&o);
+    const long long sb = (long long)b * C8 * 8 + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float av = h ? __uint_as_float(ap[j] & 0xFFFF0000u) : __uint_as_float(ap[j] << 16);
+        const float ov = h ? __uint_as_float(op[j] & 0xFFFF0000u) : __uint_as_float(op[j] << 16);
+        const int cc = 2 * j + h;
+        const float d = (av - mean_c[sb + cc]) * rsqrtf(var_c[sb + cc] + 1e-5f) - (ov - mean_o[sb + cc]) * rsqrtf(var_o[sb + cc] + 1e-5f);
+        acc += squared ? d * d : fabsf(d);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// ---------------------------------------------------------------- finalize: content + lambda * style
+// One CTA.  content = sum_taps partial_sum / (B*T*C);  style = sum_taps [mean|mu_s-mu_o| + mean|std_s-std_o|]
+// with torch's unbiased std (codes/loss.py:122-130).  out = {total, content, style}.
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const MstLossTaps taps, float lambda, int squared_style, float* __restrict__ out) {
+  __shared__ double red[2][8];
+  double content = 0.0, style = 0.0;
+  for (int t = 0; t < taps.n_taps; ++t) {
+    const MstLossTap& tp = taps.tap[t];
+    double cs = 0.0;
+    for (int i = threadIdx.x; i < tp.n_partials; i += blockDim.x) cs += (double)tp.partials[i];
+    content += cs / ((double)tp.B * tp.T * tp.C);
+    const float ub = tp.T > 1 ? (float)tp.T / (float)(tp.T - 1) : 1.f;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < tp.B * tp.C; i += blockDim.x) {
+      const float dm = tp.mean_s[i] - tp.mean_o[i];
+      const float ds = sqrtf(tp.var_s[i] * ub) - sqrtf(tp.var_o[i] * ub);
+      ss += squared_style ? (double)(dm * dm + ds * ds) : (double)(fabsf(dm) + fabsf(ds));
+    }
+    style += ss / ((double)tp.B * tp.C);
+  }
+  // block reduce (fixed order -> deterministic)
+  for (int o = 16; o > 0; o >>= 1) {
+    content += __shfl_xor_sync(0xffffffffu, content, o);
+    style += __shfl_xor_sync(0xffffffffu, style, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = content; red[1][threadIdx.x >> 5] = style; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0.0, s = 0.0;
+    for (int w = 0; w < 8; ++w) { c += red[0][w]; s += red[1][w]; }
+    out[0] = (float)(c + (double)lambda * s);
+    out[1] = (float)c;
+    out[2] = (float)s;
+  }
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" int mst_conv3x3_first(const float* img, const float* w, const float* b, mst_bf16* out, int B, int H, int W, int relu,
+                                 void* stream) {
+  if (!img || !w || !b || !out || B <= 0 || H <= 0 || W <= 0) return MST_ERR_BAD_ARG;
+  const long long total = (long long)B * H * W;
+  conv3x3_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(img, w, b, reinterpret_cast<bf16*>(out), B, H, W, relu);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return MST_ERR_BAD_ARG;
+  if ((H | W) & 1 || C % 8) return MST_ERR_UNSUPPORTED;
+  const long long n8 = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  maxpool2x2_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
+                                                                                 n8, H / 2, W / 2, C / 8);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, void* stream) {
+  if (!x || !mean || !var || B <= 0 || T <= 0 || C <= 0) return MST_ERR_BAD_ARG;
+  if (C % 64) return MST_ERR_UNSUPPORTED;
+  tap_stats_kernel<<<B * (C / 64), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), mean, var, T, C);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_content_term(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
+                                const float* var_o, int B, int T, int C, int squared, float* partials, int n_partials, void* stream) {
+  if (!fc || !fo || !mean_c || !var_c || !mean_o || !var_o || !partials || B <= 0 || T <= 0 || C <= 0 || n_partials <= 0) return MST_ERR_BAD_ARG;
+  if (C % 8) return MST_ERR_UNSUPPORTED;
+  const long long n8 = (long long)B * T * C / 8;
+  content_term_kernel<<<n_partials, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(fc), reinterpret_cast<const bf16*>(fo), mean_c, var_c,
+                                                                    mean_o, var_o, n8, T * C / 8, C / 8, squared, partials);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_loss_finalize(const MstLossTaps* taps, float lambda, int squared_style, float* out3, void* stream) {
+  if (!taps || !out3 || taps->n_taps <= 0 || taps->n_taps > 4) return MST_ERR_BAD_ARG;
+  for (int t = 0; t < taps->n_taps; ++t) {
+    const MstLossTap& tp = taps->tap[t];
+    if (!tp.partials || !tp.mean_s || !tp.var_s || !tp.mean_o || !tp.var_o || tp.B <= 0 || tp.T <= 0 || tp.C <= 0) return MST_ERR_BAD_ARG;
+  }
+  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*taps, lambda, squared_style, out3);
+  return (int)cudaGetLastError();
+}

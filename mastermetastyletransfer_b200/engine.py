@@ -274,3 +274,71 @@ def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace,
             nxt = ws_.bf16(f"cnn_{i % 2}", M, pm.n_pad)
             ops.gemm(cur, pm, M, act=ACT_RELU if relu else ACT_NONE, out_bf16=nxt, conv=conv)
             cur = nxt
+
+
+# --------------------------------------------------------------------------------------------
+# VGG-19 taps + content/style loss (codes/loss.py:15-37,71-336)
+# --------------------------------------------------------------------------------------------
+
+VGG_CONVS = [0, 2, 5, 7, 10, 12, 14, 16, 19, 21, 23, 25, 28]  # Conv2d indices inside features[:30]
+VGG_POOL_BEFORE = {5, 10, 19, 28}                              # MaxPool2d(2) sits right before these convs
+VGG_TAP_AFTER = {5: 0, 10: 1, 19: 2, 28: 3}                    # relu2_1, relu3_1, relu4_1, relu5_1
+
+
+class VggWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = "features."):
+        self.first_w = _f32(sd[prefix + "0.weight"])
+        self.first_b = _f32(sd[prefix + "0.bias"])
+        self.convs = {}
+        for idx in VGG_CONVS[1:]:
+            wt = _f32(sd[f"{prefix}{idx}.weight"])
+            self.convs[idx] = (ops.pack_conv3x3(wt, _f32(sd[f"{prefix}{idx}.bias"])), int(wt.shape[1]))
+
+
+def vgg_taps_forward(w: VggWeights, imgs: torch.Tensor, ws_: Workspace, tag: str):
+    """imgs fp32 [N,3,H,W] NCHW -> four bf16 NHWC taps [N,h,w,C] (views into the workspace, valid until the next call
+    with the same tag)."""
+    N, _, H, W = imgs.shape
+    cur = ws_.bf16(tag + "a0", N * H * W, 64)
+    ops.conv3x3_first(imgs, w.first_w, w.first_b, cur, N, H, W, relu=True)
+    h, wd, c = H, W, 64
+    taps = [None] * 4
+    flip = 1
+    for idx in VGG_CONVS[1:]:
+        pm, cin = w.convs[idx]
+        if idx in VGG_POOL_BEFORE:
+            pooled = ws_.bf16(tag + f"p{idx}", N * (h // 2) * (wd // 2), c)
+            ops.maxpool2x2(cur, pooled, N, h, wd, c)
+            cur, h, wd = pooled, h // 2, wd // 2
+        name = tag + (f"tap{VGG_TAP_AFTER[idx]}" if idx in VGG_TAP_AFTER else f"a{flip}")
+        out = ws_.bf16(name, N * h * wd, pm.n_pad)
+        ops.gemm(cur, pm, N * h * wd, act=ACT_RELU, out_bf16=out, conv=dict(H=h, W=wd, Cin=cin, pad_mode=0, upsample=False))
+        cur, c = out, pm.n_pad
+        if idx in VGG_TAP_AFTER:
+            taps[VGG_TAP_AFTER[idx]] = (out, h, wd, c)
+        else:
+            flip ^= 1
+    return taps
+
+
+def perceptual_loss_forward(w: VggWeights, content: torch.Tensor, style: torch.Tensor, output: torch.Tensor, lam: float,
+                            squared_content: bool, squared_style: bool, ws_: Workspace) -> torch.Tensor:
+    """Returns a device fp32 tensor [3] = (total, content, style) following get_overall_loss (loss.py:201-262)."""
+    B = int(content.shape[0])
+    imgs = ws_.f32("loss_imgs", 3 * B, 3, content.shape[2], content.shape[3])
+    imgs[:B].copy_(content)
+    imgs[B:2 * B].copy_(style)
+    imgs[2 * B:].copy_(output)
+    taps = vgg_taps_forward(w, imgs, ws_, "vgg_")
+    descs = []
+    for i, (t, h, wd, c) in enumerate(taps):
+        T = h * wd
+        mean, var = ws_.f32(f"loss_mean{i}", 3 * B, c), ws_.f32(f"loss_var{i}", 3 * B, c)
+        ops.tap_stats(t, mean, var, 3 * B, T, c)
+        partials = ws_.f32(f"loss_part{i}", 592)
+        tv = t.view(3 * B, T * c)
+        ops.content_term(tv[:B], tv[2 * B:], mean[:B], var[:B], mean[2 * B:], var[2 * B:], B, T, c, squared_content, partials)
+        descs.append(dict(partials=partials, mean_s=mean[B:2 * B], var_s=var[B:2 * B], mean_o=mean[2 * B:], var_o=var[2 * B:], B=B, T=T, C=c))
+    out3 = torch.empty(3, dtype=torch.float32, device=content.device)
+    ops.loss_finalize(descs, lam, squared_style, out3)
+    return out3

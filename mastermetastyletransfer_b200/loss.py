@@ -1,0 +1,97 @@
+"""Host-side mirror of the reference's codes/loss.py (VGG-19 content + style loss).
+
+Same class names, constructor arguments, forward signature, return tuples and state_dict layout
+(feature_extractor_model.features.{idx}.{weight,bias}); the VGG convolutions and the loss reductions
+run in the sm_100a kernels behind the C ABI.  Forward only this round (no backward kernels yet).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import engine
+from .style_transformer import packed_weights, workspace_of
+
+
+class VGG19_custom(nn.Module):
+    """Mirror of loss.py:15-37: holds vgg19.features[:30]; forward returns [relu2_1, relu3_1, relu4_1, relu5_1]
+    as NCHW fp32 tensors (converted from the kernels' bf16 NHWC taps)."""
+
+    def __init__(self, features: nn.Module):
+        super().__init__()
+        self.features = features
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, scope)")
+        with torch.no_grad():
+            w = packed_weights(self, engine.VggWeights)
+            ws = workspace_of(self, x.device)
+            taps = engine.vgg_taps_forward(w, x.float().contiguous(), ws, "vggmod_")
+            N = x.shape[0]
+            return [t.view(N, h, wd, c).permute(0, 3, 1, 2).float() for (t, h, wd, c) in taps]
+
+
+class custom_loss(nn.Module):
+    """Mirror of loss.py:71-336.  total = content + lambda * style (:243)."""
+
+    def __init__(self, project_absolute_path, feature_extractor_model_relative_path=None, use_vgg19_with_batchnorm=False,
+                 default_lambda_value=10, distance_content="euclidian", distance_style="euclidian"):
+        super().__init__()
+        assert distance_content in ["euclidian", "euclidian_squared"], "distance should be either 'euclidian' or 'euclidian_squared'"
+        assert distance_style in ["euclidian", "euclidian_squared"], "distance should be either 'euclidian' or 'euclidian_squared'"
+        if use_vgg19_with_batchnorm:
+            raise NotImplementedError("the VGG-19-BN variant has no sm_100a kernels (SURVEY.md 8f-4)")
+        if feature_extractor_model_relative_path is None:
+            feature_extractor_model_relative_path = os.path.join("weights", "vgg_19_last_layer_is_relu_5_1_output.pt")
+        self.lambda_value = default_lambda_value
+        self.distance_content, self.distance_style = distance_content, distance_style
+        # parameter-free, kept for attribute compatibility with the reference (loss.py:102-105)
+        self.IN_0, self.IN_1 = nn.InstanceNorm2d(128), nn.InstanceNorm2d(256)
+        self.IN_2, self.IN_3 = nn.InstanceNorm2d(512), nn.InstanceNorm2d(512)
+        path = os.path.join(project_absolute_path, feature_extractor_model_relative_path)
+        if os.path.exists(path):
+            features = torch.load(path, weights_only=False)
+        else:  # offline: same architecture, random init (the reference would download IMAGENET1K_V1 here)
+            from .synthetic import build_vgg19_to_relu5_1
+            features = build_vgg19_to_relu5_1()
+        self.feature_extractor_model = VGG19_custom(features)
+        for p in self.feature_extractor_model.parameters():
+            p.requires_grad = False
+
+    def forward(self, content_image, style_image, output_image, distance="euclidian", lambda_value=None,
+                output_content_and_style_loss=False, output_similarity_loss=False):
+        # the reference overwrites an explicitly passed lambda with the default (loss.py:189-190): reproduced
+        if lambda_value is not None:
+            lambda_value = self.lambda_value
+        return self.get_overall_loss(content_image=content_image, style_image=style_image, output_image=output_image,
+                                     loss_weight=lambda_value, output_content_and_style_loss=output_content_and_style_loss,
+                                     output_similarity_loss=output_similarity_loss)
+
+    def get_overall_loss(self, content_image, style_image, output_image, loss_weight=None, output_content_and_style_loss=False,
+                         output_similarity_loss=False):
+        assert content_image.shape == style_image.shape == output_image.shape, "All images should be in the exact same shape"
+        assert content_image.requires_grad == False, "Content image should not require gradient"  # noqa: E712
+        assert style_image.requires_grad == False, "Style image should not require gradient"  # noqa: E712
+        if output_similarity_loss:
+            raise NotImplementedError("similarity loss is out of scope (off by default and always 0 in the reference, SURVEY.md 0.2-4)")
+        if not output_image.is_cuda:
+            raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
+        if torch.is_grad_enabled() and output_image.requires_grad:
+            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, scope): call under torch.no_grad()")
+        if loss_weight is None:
+            loss_weight = self.lambda_value
+        with torch.no_grad():
+            w = packed_weights(self.feature_extractor_model, engine.VggWeights)
+            ws = workspace_of(self, output_image.device)
+            out3 = engine.perceptual_loss_forward(w, content_image.float(), style_image.float(), output_image.float(), float(loss_weight),
+                                                  self.distance_content == "euclidian_squared",
+                                                  self.distance_style == "euclidian_squared", ws)
+        total, content, style = out3[0], out3[1], out3[2]
+        if output_content_and_style_loss:
+            return total, content, style
+        return total

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MstGemm, MstWindowAttn, check
+from ._lib import MstGemm, MstLossTap, MstLossTaps, MstWindowAttn, check
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 A_PLAIN, A_CONV3X3 = 0, 1
@@ -54,7 +54,9 @@ KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_window_attention": "window_attn_
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
-             "mst_window_maps": "window_maps_kernel"}
+             "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
+             "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
+             "mst_loss_finalize": "loss_finalize_kernel"}
 
 
 def _stream() -> int:
@@ -213,3 +215,43 @@ def patch_embed(img, w, b, gamma, beta, x, B, S) -> None:
 def cast_bf16(x, y) -> None:
     _launch("mst_cast_bf16", lambda: _lib.lib().mst_cast_bf16(_ptr(x, torch.float32, "x"), _ptr(y, torch.bfloat16, "y"), x.numel(), _stream()),
             nbytes=6.0 * x.numel())
+
+
+def conv3x3_first(img, w, b, out, B, H, W, relu=True) -> None:
+    _launch("mst_conv3x3_first", lambda: _lib.lib().mst_conv3x3_first(_ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"),
+                                                                       _ptr(b, torch.float32, "b"), _ptr(out, torch.bfloat16, "out"),
+                                                                       B, H, W, int(relu), _stream()),
+            flops=2.0 * B * H * W * 27 * 64, nbytes=B * H * W * (12.0 + 128.0))
+
+
+def maxpool2x2(x, y, B, H, W, Cdim) -> None:
+    _launch("mst_maxpool2x2", lambda: _lib.lib().mst_maxpool2x2(_ptr(x, torch.bfloat16, "x"), _ptr(y, torch.bfloat16, "y"), B, H, W, Cdim, _stream()),
+            nbytes=2.5 * B * H * W * Cdim)
+
+
+def tap_stats(x, mean, var, B, T, Cdim) -> None:
+    _launch("mst_tap_stats", lambda: _lib.lib().mst_tap_stats(_ptr(x, torch.bfloat16, "x"), _ptr(mean, torch.float32, "mean"),
+                                                               _ptr(var, torch.float32, "var"), B, T, Cdim, _stream()),
+            nbytes=2.0 * B * T * Cdim)
+
+
+def content_term(fc, fo, mean_c, var_c, mean_o, var_o, B, T, Cdim, squared, partials) -> None:
+    _launch("mst_content_term", lambda: _lib.lib().mst_content_term(
+        _ptr(fc, torch.bfloat16, "fc"), _ptr(fo, torch.bfloat16, "fo"), _ptr(mean_c, torch.float32, "mean_c"),
+        _ptr(var_c, torch.float32, "var_c"), _ptr(mean_o, torch.float32, "mean_o"), _ptr(var_o, torch.float32, "var_o"),
+        B, T, Cdim, int(squared), _ptr(partials, torch.float32, "partials"), partials.numel(), _stream()),
+        nbytes=4.0 * B * T * Cdim)
+
+
+def loss_finalize(taps, lam: float, squared_style: bool, out3) -> None:
+    """taps: list of dicts(partials, mean_s, var_s, mean_o, var_o, B, T, C) for relu2_1..relu5_1."""
+    pack = MstLossTaps()
+    pack.n_taps = len(taps)
+    for i, t in enumerate(taps):
+        e = pack.tap[i]
+        e.partials = _ptr(t["partials"], torch.float32, "partials")
+        e.mean_s, e.var_s = _ptr(t["mean_s"], torch.float32, "mean_s"), _ptr(t["var_s"], torch.float32, "var_s")
+        e.mean_o, e.var_o = _ptr(t["mean_o"], torch.float32, "mean_o"), _ptr(t["var_o"], torch.float32, "var_o")
+        e.n_partials, e.B, e.T, e.C = t["partials"].numel(), t["B"], t["T"], t["C"]
+    _launch("mst_loss_finalize", lambda: _lib.lib().mst_loss_finalize(C.byref(pack), float(lam), int(squared_style),
+                                                                       _ptr(out3, torch.float32, "out3"), _stream()))

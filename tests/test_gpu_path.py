@@ -122,3 +122,78 @@ def test_no_cpu_fallback(model):
     content, style = synthetic.synthetic_images(1, 64, seed=0)
     with pytest.raises(RuntimeError):
         model(content, style, 1)  # CPU tensors: the product path refuses instead of falling back
+
+
+# ------------------------------------------------------------------------------------------------
+# VGG-19 perceptual loss (rows a15-a18).  Tolerance: relative <= 1e-3 on the loss scalars (north_star).
+# ------------------------------------------------------------------------------------------------
+LOSS_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def loss_module():
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    m = custom_loss(project_absolute_path="/nonexistent")
+    synthetic.fill_state_dict_(m.feature_extractor_model.features, 0, prefix="vgg.")
+    return m.eval().cuda()
+
+
+def test_vgg_taps_vs_oracle(loss_module):
+    from oracle import master_oracle as O
+    from mastermetastyletransfer_b200 import synthetic
+    content, _ = synthetic.synthetic_images(2, 128, seed=0)
+    vsd = {k: v.detach().cpu() for k, v in loss_module.feature_extractor_model.features.state_dict().items()}
+    with torch.no_grad():
+        taps = loss_module.feature_extractor_model(content.cuda())
+        ref = O.vgg_taps(vsd, content)
+    for t, r in zip(taps, ref):
+        assert t.shape == r.shape
+        assert rel_err(t, r) <= FEAT_TOL, rel_err(t, r)
+
+
+@pytest.mark.parametrize("squared", [False, True])
+def test_loss_vs_oracle_and_golden(loss_module, squared, golden_dir):
+    from oracle import master_oracle as O
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    content, style = synthetic.synthetic_images(2, 128, seed=0)
+    gold = np.load(os.path.join(golden_dir, "path_128.npz"))
+    img = torch.from_numpy(gold["img_k1"])
+    vsd = {k: v.detach().cpu() for k, v in loss_module.feature_extractor_model.features.state_dict().items()}
+    mod = loss_module
+    if squared:
+        mod = custom_loss(project_absolute_path="/nonexistent", distance_content="euclidian_squared", distance_style="euclidian_squared")
+        mod.feature_extractor_model.load_state_dict(loss_module.feature_extractor_model.state_dict())
+        mod = mod.eval().cuda()
+    with torch.no_grad():
+        tot, lc, ls = mod(content.cuda(), style.cuda(), img.cuda(), output_content_and_style_loss=True)
+        ref = O.overall_loss(vsd, content, style, img, 10.0, squared, squared)
+    got = [tot.item(), lc.item(), ls.item()]
+    np.testing.assert_allclose(got, [r.item() for r in ref], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(got, gold["loss_squared" if squared else "loss"], rtol=LOSS_RTOL)
+    # lambda handling: forward() ignores an explicit lambda (reference bug loss.py:189-190), get_overall_loss honours it
+    with torch.no_grad():
+        t2 = mod(content.cuda(), style.cuda(), img.cuda(), lambda_value=1.0)
+        t3 = mod.get_overall_loss(content.cuda(), style.cuda(), img.cuda(), loss_weight=1.0)
+    assert abs(t2.item() - got[0]) <= 1e-6 * abs(got[0])
+    np.testing.assert_allclose(t3.item(), got[1] + 1.0 * got[2], rtol=1e-5)
+
+
+def test_loss_input_assertions(loss_module):
+    x = torch.zeros(1, 3, 64, 64, device="cuda")
+    with pytest.raises(AssertionError):
+        loss_module(x, x[:, :, :32], x)
+
+
+def test_loss_properties_at_bench_shape(loss_module):
+    """Size-independent checks at 256^2: identical content/output gives zero content loss, identical style/output
+    gives zero style loss, and the result is deterministic."""
+    from mastermetastyletransfer_b200 import synthetic
+    content, style = synthetic.synthetic_images(4, 256, seed=2)
+    c, s = content.cuda(), style.cuda()
+    with torch.no_grad():
+        t, lc, ls = loss_module(c, s, c, output_content_and_style_loss=True)
+        assert lc.item() < 1e-6 and ls.item() > 0  # (fma contraction leaves ~1e-8)
+        t2, lc2, ls2 = loss_module(c, s, s, output_content_and_style_loss=True)
+        assert ls2.item() < 1e-6 and lc2.item() > 0
+        again = loss_module(c, s, s, output_content_and_style_loss=True)
+        assert again[0].item() == t2.item()
