@@ -19,7 +19,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_PROD_WARPS = 4;
+constexpr int NUM_PROD_WARPS = 8;
 constexpr int GEMM_THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 1) * 32;
 constexpr int MAX_BIAS = 1024;
 
@@ -86,40 +86,68 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
 
   if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
     // =========================== producers ===========================
+    constexpr int RPT = BM * 8 / (NUM_PROD_WARPS * 32);  // rows per thread (4 with 8 producer warps)
+    constexpr int RSTEP = NUM_PROD_WARPS * 4;            // row distance between a thread's rows (32)
     const int t = threadIdx.x - NUM_EPI_WARPS * 32;
     const int c = t & 7;    // 16-byte chunk column inside the 128-byte k-slab
-    const int r0 = t >> 3;  // first of this thread's rows; rows r0 + 16*i
+    const int r0 = t >> 3;  // first of this thread's rows; rows r0 + RSTEP*i
     const int Hs = p.upsample ? (p.H >> 1) : p.H;
     const int Ws = p.upsample ? (p.W >> 1) : p.W;
-    const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*2048 for row r0+16i
+    const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*RSTEP*128 for row r0+RSTEP*i (whole 8-row groups further)
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
+    const bool conv = p.a_mode != MST_A_PLAIN;
     int it = 0;  // running k-block counter across tiles (pipeline position)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % n_tiles;
       const int m0 = (tile / n_tiles) * BM;
-      long long row_base[8];  // PLAIN: element offset of the row; CONV: image base offset
-      int row_yx[8];          // CONV: y | x << 16 ; -1 if row >= M
+      // Per-row source bookkeeping, computed once per tile.
+      //   PLAIN: rowp = &A[m*lda].   CONV: rowp = image base; yo/xo = element offsets of the three source rows /
+      //   columns a 3x3 tap can touch (reflect or zero padding and the nearest-x2 upsample already applied),
+      //   vmask bit ky / bit 3+kx = that source row / column exists.
+      const bf16* rowp[RPT];
+      int yo[RPT][3], xo[RPT][3];
+      uint32_t vmask[RPT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + r0 + 16 * i;
-        if (m >= p.M) {
-          row_base[i] = 0;
-          row_yx[i] = -1;
-        } else if (p.a_mode == MST_A_PLAIN) {
-          row_base[i] = (long long)m * p.lda;
-          row_yx[i] = 0;
-        } else {
-          const int hw = p.H * p.W;
-          const int b = m / hw;
-          const int rem = m - b * hw;
-          const int y = rem / p.W;
-          const int x = rem - y * p.W;
-          row_base[i] = (long long)b * Hs * Ws * p.Cin;
-          row_yx[i] = y | (x << 16);
+      for (int i = 0; i < RPT; ++i) {
+        const int m = m0 + r0 + RSTEP * i;
+        vmask[i] = 0;
+        rowp[i] = Abase;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { yo[i][j] = 0; xo[i][j] = 0; }
+        if (m < p.M) {
+          if (!conv) {
+            rowp[i] = Abase + (long long)m * p.lda;
+            vmask[i] = 0x3F;
+          } else {
+            const int hw = p.H * p.W;
+            const int b = m / hw;
+            const int rem = m - b * hw;
+            const int y = rem / p.W;
+            const int x = rem - y * p.W;
+            rowp[i] = Abase + (long long)b * Hs * Ws * p.Cin;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              int yy = y + j - 1, xx = x + j - 1;
+              bool vy = true, vx = true;
+              if (p.pad_mode == 1) {  // reflect (no edge repeat): -1 -> 1, H -> H-2
+                yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+                xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+              } else {
+                vy = (unsigned)yy < (unsigned)p.H;
+                vx = (unsigned)xx < (unsigned)p.W;
+              }
+              if (p.upsample) { yy >>= 1; xx >>= 1; }
+              yo[i][j] = vy ? yy * Ws * p.Cin : 0;
+              xo[i][j] = vx ? xx * p.Cin : 0;
+              vmask[i] |= (vy ? 1u : 0u) << j | (vx ? 1u : 0u) << (3 + j);
+            }
+          }
         }
       }
       const uint8_t* wtile = Wbase + (size_t)n_tile * nkb * Cfg::B_STAGE_BYTES;
+      int tap = 0, ch = c * 8;  // conv: this thread's (tap, channel) for k0 = kb*64 + c*8, advanced without divisions
+      while (conv && ch >= p.Cin) { ch -= p.Cin; ++tap; }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES;
         if (it >= STAGES) mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) - 1) & 1);
@@ -128,34 +156,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
           mbar_arrive_expect_tx(smem_u32(&full_bar[s]), Cfg::B_STAGE_BYTES);
           bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
         }
-        const int k0 = kb * BK + c * 8;
-        if (p.a_mode == MST_A_PLAIN) {
+        if (!conv) {
+          const int k0 = kb * BK + c * 8;
           const bool kvalid = k0 < p.K;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool valid = kvalid && row_yx[i] >= 0;
-            cp_async16(a_stage + a_dst0 + i * 2048, Abase + (valid ? row_base[i] + k0 : 0), valid);
+          for (int i = 0; i < RPT; ++i) {
+            const bool valid = kvalid && vmask[i] != 0;
+            cp_async16(a_stage + a_dst0 + i * (RSTEP * 128), valid ? rowp[i] + k0 : Abase, valid);
           }
         } else {
-          const int tap = k0 / p.Cin;
-          const int ch = k0 - tap * p.Cin;
-          const int ky = tap / 3, kx = tap - ky * 3;
+          const int ky = tap / 3, kx = tap - ky * 3;  // tap < 16: cheap constant division
           const bool kvalid = tap < 9;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            bool valid = kvalid && row_yx[i] >= 0;
-            int yy = (row_yx[i] & 0xFFFF) + ky - 1;
-            int xx = (row_yx[i] >> 16) + kx - 1;
-            if (p.pad_mode == 1) {  // reflect (no edge repeat): -1 -> 1, H -> H-2
-              yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
-              xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
-            } else {
-              valid = valid && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
-            }
-            if (p.upsample) { yy >>= 1; xx >>= 1; }
-            const long long off = valid ? row_base[i] + ((long long)(yy * Ws + xx)) * p.Cin + ch : 0;
-            cp_async16(a_stage + a_dst0 + i * 2048, Abase + off, valid);
+          for (int i = 0; i < RPT; ++i) {
+            const int yoff = ky == 0 ? yo[i][0] : (ky == 1 ? yo[i][1] : yo[i][2]);
+            const int xoff = kx == 0 ? xo[i][0] : (kx == 1 ? xo[i][1] : xo[i][2]);
+            const bool valid = kvalid && ((vmask[i] >> ky) & (vmask[i] >> (3 + kx)) & 1u);
+            cp_async16(a_stage + a_dst0 + i * (RSTEP * 128), valid ? rowp[i] + (yoff + xoff + ch) : Abase, valid);
           }
+          ch += BK;
+          while (ch >= p.Cin) { ch -= p.Cin; ++tap; }
         }
         // asynchronous arrival: counts as this thread's arrival once all of its cp.async above have landed,
         // so the thread never blocks and every stage of the ring can be in flight
@@ -203,7 +223,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
       const int buf = tcount & 1;
       const int n_tile = tile % n_tiles;
       const int m0 = (tile / n_tiles) * BM;
-      mbar_wait(smem_u32(&tmem_full_bar[buf]), (tcount >> 1) & 1);
+      if (lane == 0) mbar_wait(smem_u32(&tmem_full_bar[buf]), (tcount >> 1) & 1);  // one poller per warp
+      __syncwarp();
       tc_fence_after();
       if (active) {
         const int row = m0 + quad * 32 + lane;

@@ -1,170 +1,228 @@
 // Fused shifted-window attention core (codes/style_transformer.py:83-111,127-168 and :544-607).
-// One CTA per window, one warp per head (head_dim 32).  Roll + partition live in the load addresses,
-// window reverse + roll back in the store addresses; scores, relative-position bias, 9-region mask,
-// softmax and PV stay in registers / shared memory in fp32.  With v2/out2 set the softmax is shared by
-// two value tensors (the sigma/mu attention of the style decoder).
+//
+// One warp per (window, head), four warps per CTA.  Roll + partition live in the load addresses, window
+// reverse + roll back in the store addresses.  Q, K, V head slices ([64 x 32] bf16, 7x7 windows padded to
+// 64 rows) are staged in shared memory; S = QK^T and O = PV run on the tensor cores (mma.sync m16n8k16,
+// bf16 in, fp32 accumulate) 16 query rows at a time, with scale, relative-position bias, the 9-region shift
+// mask and the softmax applied to the fp32 accumulator fragments in registers (quad shuffles for the row
+// max / sum).  With v2/out2 the same probabilities multiply a second value tensor (sigma/mu attention).
 #include "../../include/mst_b200.h"
 #include "common.cuh"
 
 namespace mst {
 
+constexpr int AT_WARPS = 4;
+constexpr int AT_LD = 40;  // bf16 row stride of the staged tiles: 80 B keeps ldmatrix bank-conflict free
+
+MST_DEVINL void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+MST_DEVINL void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+MST_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+MST_DEVINL uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 template <int WS>
-__global__ void __launch_bounds__(256) window_attn_kernel(const MstWindowAttn a, const WinGeom g) {
-  constexpr int N = WS * WS;
-  constexpr int D = 32;
+__global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWindowAttn a, const WinGeom g) {
+  constexpr int N = WS * WS;   // real tokens per window
+  constexpr int NP = 64;       // rows of the staged tiles (N padded to a multiple of 16)
   constexpr int NT = (2 * WS - 1) * (2 * WS - 1);
-  extern __shared__ float smem[];
-  // per warp: K [N][D], V [N][D], (V2 [N][D]); per CTA: bias table [NT*heads], labels [N], src [N]
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int heads = a.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dual = a.v2 != nullptr;
-  const int per_warp = N * D * (dual ? 3 : 2);
-  float* table_s = smem + heads * per_warp;
+  const int tiles_per_warp = dual ? 4 : 3;
+  bf16* tile0 = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * tiles_per_warp * NP * AT_LD;
+  bf16* Qs = tile0;
+  bf16* Ks = Qs + NP * AT_LD;
+  bf16* Vs = Ks + NP * AT_LD;
+  bf16* V2s = Vs + NP * AT_LD;
+  float* table_s = reinterpret_cast<float*>(reinterpret_cast<bf16*>(smem_raw) + (size_t)AT_WARPS * tiles_per_warp * NP * AT_LD);
   int* src_s = reinterpret_cast<int*>(table_s + NT * heads);
-  int* lab_s = src_s + N;
-  float* Ks = smem + warp * per_warp;
-  float* Vs = Ks + N * D;
-  float* V2s = Vs + N * D;
+  int* lab_s = src_s + NP;
 
-  const int win_global = blockIdx.x;
+  // the CTA's four tasks share one window (AT_WARPS divides heads)
+  const int task0 = blockIdx.x * AT_WARPS;
+  const int win_global = task0 / heads;
+  const int h = task0 - win_global * heads + warp;
   const int b = win_global / g.nW;
   const int win = win_global - b * g.nW;
   const bool masked = (g.sy + g.sx) > 0;
 
-  for (int i = threadIdx.x; i < NT * heads; i += blockDim.x) table_s[i] = a.bias_table[i];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    int y, x;
-    win_source(g, win, i, y, x);
-    src_s[i] = (y < g.H && x < g.W) ? (b * g.H + y) * g.W + x : -1;  // token row in the [B*H*W, C] tensors
-    lab_s[i] = win_label(g, win, i);
+  // bias table transposed to [heads][NT] so a head's lookups are contiguous
+  for (int i = threadIdx.x; i < NT * heads; i += blockDim.x) {
+    const int idx = i / heads, hh = i - idx * heads;
+    table_s[hh * NT + idx] = a.bias_table[i];
+  }
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+    int s = -2, l = 0;  // -2: row beyond the window (7x7 padded to 64 rows)
+    if (i < N) {
+      int y, x;
+      win_source(g, win, i, y, x);
+      s = (y < g.H && x < g.W) ? (b * g.H + y) * g.W + x : -1;  // -1: zero-padded token (takes the projection bias)
+      l = win_label(g, win, i);
+    }
+    src_s[i] = s;
+    lab_s[i] = l;
   }
   __syncthreads();
 
-  const int h = warp;
-  const int c0 = h * D;
-  // ---- stage K, V (and V2) of this head: lane = channel, loop over tokens (64-byte coalesced rows) ----
-  for (int j = 0; j < N; ++j) {
-    const int s = src_s[j];
-    float kv, vv, v2v = 0.f;
-    if (s >= 0) {
-      kv = __bfloat162float(reinterpret_cast<const bf16*>(a.k)[(long long)s * a.ldk + c0 + lane]);
-      vv = __bfloat162float(reinterpret_cast<const bf16*>(a.v)[(long long)s * a.ldv + c0 + lane]);
-      if (dual) v2v = __bfloat162float(reinterpret_cast<const bf16*>(a.v2)[(long long)s * a.ldv + c0 + lane]);
-    } else {
-      kv = a.pad_k ? a.pad_k[c0 + lane] : 0.f;
-      vv = a.pad_v ? a.pad_v[c0 + lane] : 0.f;
-      if (dual) v2v = a.pad_v2 ? a.pad_v2[c0 + lane] : 0.f;
+  const int c0 = h * 32;
+  // ---- stage Q, K, V (V2): 4 lanes x 16 B per token row, 8 rows per pass ----
+  {
+    const int chunk = lane & 3, rsub = lane >> 2;
+#pragma unroll 2
+    for (int r = rsub; r < NP; r += 8) {
+      const int s = src_s[r];
+      uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv, v2v = qv;
+      if (s >= 0) {
+        qv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.q) + (long long)s * a.ldq + c0 + chunk * 8);
+        kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.k) + (long long)s * a.ldk + c0 + chunk * 8);
+        vv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.v) + (long long)s * a.ldv + c0 + chunk * 8);
+        if (dual) v2v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.v2) + (long long)s * a.ldv + c0 + chunk * 8);
+      } else if (s == -1) {
+        const int cc = c0 + chunk * 8;
+        uint32_t* qp = reinterpret_cast<uint32_t*>(&qv); uint32_t* kp = reinterpret_cast<uint32_t*>(&kv);
+        uint32_t* vp = reinterpret_cast<uint32_t*>(&vv); uint32_t* wp = reinterpret_cast<uint32_t*>(&v2v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (a.pad_q) qp[e] = pack_bf16(a.pad_q[cc + 2 * e], a.pad_q[cc + 2 * e + 1]);
+          if (a.pad_k) kp[e] = pack_bf16(a.pad_k[cc + 2 * e], a.pad_k[cc + 2 * e + 1]);
+          if (a.pad_v) vp[e] = pack_bf16(a.pad_v[cc + 2 * e], a.pad_v[cc + 2 * e + 1]);
+          if (dual && a.pad_v2) wp[e] = pack_bf16(a.pad_v2[cc + 2 * e], a.pad_v2[cc + 2 * e + 1]);
+        }
+      }
+      *reinterpret_cast<uint4*>(Qs + r * AT_LD + chunk * 8) = qv;
+      *reinterpret_cast<uint4*>(Ks + r * AT_LD + chunk * 8) = kv;
+      *reinterpret_cast<uint4*>(Vs + r * AT_LD + chunk * 8) = vv;
+      if (dual) *reinterpret_cast<uint4*>(V2s + r * AT_LD + chunk * 8) = v2v;
     }
-    Ks[j * D + lane] = kv;
-    Vs[j * D + lane] = vv;
-    if (dual) V2s[j * D + lane] = v2v;
   }
   __syncwarp();
 
-  const float scale = 0.17677669529663687f;  // 32^-0.5
-  for (int i = lane; i < N; i += 32) {
-    // ---- q row (scaled as the reference does before the matmul) ----
-    float q[D];
-    const int si = src_s[i];
-    if (si >= 0) {
-      const uint4* q4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.q) + (long long)si * a.ldq + c0);
+  const float scale = 0.17677669529663687f;  // 32^-0.5 (the reference scales q before the matmul)
+  const float* tab = table_s + h * NT;
+  const int gq = lane >> 2;        // fragment row within the 16-row tile (and +8)
+  const int cq = (lane & 3) * 2;   // fragment column pair within an 8-column tile
+  const uint32_t q_base = smem_u32(Qs), k_base = smem_u32(Ks), v_base = smem_u32(Vs), v2_base = smem_u32(V2s);
+  constexpr int MT = (N + 15) / 16;
+
+#pragma unroll 1
+  for (int mt = 0; mt < MT; ++mt) {
+    // ---- Q fragments: 16 rows x 32 dims = two k-steps ----
+    uint32_t qa[2][4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint4 u = q4[t];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int ks = 0; ks < 2; ++ks) {
+      const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int col = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(q_base + (row * AT_LD + col) * 2, qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    // ---- S = Q K^T : 8 key tiles of 8 ----
+    float sc[8][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          q[t * 8 + 2 * e] = __uint_as_float(w[e] << 16) * scale;
-          q[t * 8 + 2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u) * scale;
+    for (int nt = 0; nt < 8; ++nt) { sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f; }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int krow = np * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int kcol = ks * 16 + ((lane >> 3) & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(k_base + (krow * AT_LD + kcol) * 2, b0, b1, b2, b3);
+        mma_bf16_16816(sc[2 * np], qa[ks], b0, b1);
+        mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
+      }
+    }
+    // ---- scale + relative-position bias + shift mask, row max ----
+    const int i0 = mt * 16 + gq, i1 = i0 + 8;
+    const int yi0 = i0 / WS, xi0 = i0 - yi0 * WS, yi1 = i1 / WS, xi1 = i1 - yi1 * WS;
+    const int li0 = lab_s[i0], li1 = lab_s[i1];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = nt * 8 + cq + e;
+        float s0 = -INFINITY, s1 = -INFINITY;
+        if (j < N) {
+          const int yj = j / WS, xj = j - yj * WS;
+          const int lj = lab_s[j];
+          s0 = sc[nt][e] * scale + ((i0 < N) ? tab[(yi0 - yj + WS - 1) * (2 * WS - 1) + (xi0 - xj + WS - 1)] : 0.f);
+          s1 = sc[nt][2 + e] * scale + ((i1 < N) ? tab[(yi1 - yj + WS - 1) * (2 * WS - 1) + (xi1 - xj + WS - 1)] : 0.f);
+          if (masked) {
+            if (lj != li0) s0 += -100.0f;
+            if (lj != li1) s1 += -100.0f;
+          }
+        }
+        sc[nt][e] = s0;
+        sc[nt][2 + e] = s1;
+        mx0 = fmaxf(mx0, s0);
+        mx1 = fmaxf(mx1, s1);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[4][4];  // P as bf16 A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p00 = __expf(sc[nt][0] - mx0), p01 = __expf(sc[nt][1] - mx0);
+      const float p10 = __expf(sc[nt][2] - mx1), p11 = __expf(sc[nt][3] - mx1);
+      sum0 += p00 + p01;
+      sum1 += p10 + p11;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p00, p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p10, p11);
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+    // ---- O = P V (and P V2): 4 dim tiles of 8, 4 k-steps of 16 keys ----
+#pragma unroll 1
+    for (int which = 0; which < (dual ? 2 : 1); ++which) {
+      const uint32_t vb = which ? v2_base : v_base;
+      float o[4][4];
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < 2; ++dp) {
+          const int vrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int vcol = dp * 16 + (lane >> 4) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(vb + (vrow * AT_LD + vcol) * 2, b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * dp], pa[kk], b0, b1);
+          mma_bf16_16816(o[2 * dp + 1], pa[kk], b2, b3);
         }
       }
-    } else {
+      // ---- stage the 16 x 32 output tile in this m-tile's (already consumed) Q rows, then 16-byte stores ----
+      __syncwarp();
 #pragma unroll
-      for (int d = 0; d < D; ++d) q[d] = (a.pad_q ? a.pad_q[c0 + d] : 0.f) * scale;
-    }
-    const int li = lab_s[i];
-    // ---- scores ----
-    float sc[N];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * D);
-      float acc = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float4 kk = k4[t];
-        acc = fmaf(q[4 * t], kk.x, acc);
-        acc = fmaf(q[4 * t + 1], kk.y, acc);
-        acc = fmaf(q[4 * t + 2], kk.z, acc);
-        acc = fmaf(q[4 * t + 3], kk.w, acc);
+      for (int dt = 0; dt < 4; ++dt) {
+        *reinterpret_cast<uint32_t*>(Qs + (mt * 16 + gq) * AT_LD + dt * 8 + cq) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+        *reinterpret_cast<uint32_t*>(Qs + (mt * 16 + gq + 8) * AT_LD + dt * 8 + cq) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
       }
-      acc += table_s[rel_pos_index(i, j, WS) * heads + h];
-      if (masked && lab_s[j] != li) acc += -100.0f;
-      sc[j] = acc;
-      mx = fmaxf(mx, acc);
-    }
-    float sum = 0.f;
+      __syncwarp();
+      bf16* outp = reinterpret_cast<bf16*>(which ? a.out2 : a.out);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      sc[j] = __expf(sc[j] - mx);
-      sum += sc[j];
-    }
-    const float inv = 1.0f / sum;
-    // ---- PV ----
-    float o[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float4* v4 = reinterpret_cast<const float4*>(Vs + j * D);
-      const float pj = sc[j];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float4 vv = v4[t];
-        o[4 * t] = fmaf(pj, vv.x, o[4 * t]);
-        o[4 * t + 1] = fmaf(pj, vv.y, o[4 * t + 1]);
-        o[4 * t + 2] = fmaf(pj, vv.z, o[4 * t + 2]);
-        o[4 * t + 3] = fmaf(pj, vv.w, o[4 * t + 3]);
-      }
-    }
-    if (si >= 0) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        __nv_bfloat162 hh = __floats2bfloat162_rn(o[2 * d] * inv, o[2 * d + 1] * inv);
-        pk[d] = *reinterpret_cast<uint32_t*>(&hh);
-      }
-      uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (long long)si * a.ldo + c0);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) o4[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-    }
-    if (dual) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const float4* v4 = reinterpret_cast<const float4*>(V2s + j * D);
-        const float pj = sc[j];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float4 vv = v4[t];
-          o[4 * t] = fmaf(pj, vv.x, o[4 * t]);
-          o[4 * t + 1] = fmaf(pj, vv.y, o[4 * t + 1]);
-          o[4 * t + 2] = fmaf(pj, vv.z, o[4 * t + 2]);
-          o[4 * t + 3] = fmaf(pj, vv.w, o[4 * t + 3]);
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = mt * 16 + rr * 8 + (lane >> 2);
+        const int s = src_s[r];
+        if (s >= 0) {
+          const uint4 val = *reinterpret_cast<const uint4*>(Qs + r * AT_LD + (lane & 3) * 8);
+          *reinterpret_cast<uint4*>(outp + (long long)s * a.ldo + c0 + (lane & 3) * 8) = val;
         }
       }
-      if (si >= 0) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int d = 0; d < 16; ++d) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(o[2 * d] * inv, o[2 * d + 1] * inv);
-          pk[d] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out2) + (long long)si * a.ldo + c0);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) o4[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-      }
+      __syncwarp();
     }
   }
 }
@@ -184,12 +242,16 @@ __global__ void window_maps_kernel(WinGeom g, int32_t* gather, int32_t* labels, 
 
 template <int WS>
 static int launch_attn(const MstWindowAttn& a, const WinGeom& g, cudaStream_t st) {
-  constexpr int N = WS * WS, NT = (2 * WS - 1) * (2 * WS - 1);
-  const size_t smem = sizeof(float) * ((size_t)a.heads * N * 32 * (a.v2 ? 3 : 2) + (size_t)NT * a.heads) + sizeof(int) * 2 * N;
-  cudaError_t e = cudaFuncSetAttribute(window_attn_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  if (e != cudaSuccess) return (int)e;
-  if (smem > 200 * 1024) return MST_ERR_UNSUPPORTED;
-  window_attn_kernel<WS><<<a.B * g.nW, a.heads * 32, smem, st>>>(a, g);
+  constexpr int NT = (2 * WS - 1) * (2 * WS - 1);
+  const size_t smem = (size_t)AT_WARPS * (a.v2 ? 4 : 3) * 64 * AT_LD * sizeof(bf16) + sizeof(float) * NT * a.heads + sizeof(int) * 2 * 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long long tasks = (long long)a.B * g.nW * a.heads;
+  window_attn_kernel<WS><<<(unsigned)(tasks / AT_WARPS), AT_WARPS * 32, smem, st>>>(a, g);
   return (int)cudaGetLastError();
 }
 
@@ -199,7 +261,8 @@ extern "C" int mst_window_attention(const MstWindowAttn* a, void* stream) {
   using namespace mst;
   if (!a || !a->q || !a->k || !a->v || !a->out || !a->bias_table) return MST_ERR_BAD_ARG;
   if ((a->v2 == nullptr) != (a->out2 == nullptr)) return MST_ERR_BAD_ARG;
-  if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->heads <= 0 || a->heads > 8) return MST_ERR_BAD_ARG;
+  if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->heads <= 0 || a->heads > 32) return MST_ERR_BAD_ARG;
+  if (a->heads % AT_WARPS != 0) return MST_ERR_UNSUPPORTED;
   if ((a->ldq | a->ldk | a->ldv | a->ldo) % 8 != 0) return MST_ERR_BAD_ARG;
   if (a->shift < 0 || a->shift >= a->ws) return MST_ERR_BAD_ARG;
   const WinGeom g = make_geom(a->H, a->W, a->ws, a->shift);
