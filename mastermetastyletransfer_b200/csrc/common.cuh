@@ -52,6 +52,11 @@ MST_DEVINL void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int n = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
+// L1-allocating variant: 3x3-conv taps re-read each input pixel up to nine times, mostly from the same SM
+MST_DEVINL void cp_async16_ca(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
 MST_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 MST_DEVINL void cp_async_wait() {

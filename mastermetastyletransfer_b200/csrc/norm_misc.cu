@@ -119,55 +119,79 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------- Swin patch embedding + LayerNorm(128)
-// One warp per output token; lane owns output channels lane, lane+32, lane+64, lane+96.
-// Weights [128][48] sit in shared memory transposed to [48][128] so lanes read consecutive words.
-__global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float* __restrict__ out, int B,
-                                                          int S, int tokens_per_cta) {
-  __shared__ float ws[48 * 128];
-  for (int i = threadIdx.x; i < 48 * 128; i += blockDim.x) {
-    const int k = i / 128, n = i - k * 128;
-    ws[i] = w[n * 48 + k];  // conv weight [128][3][4][4] -> k = ci*16 + ky*4 + kx
-  }
-  __syncthreads();
+// Persistent CTAs; each loops over groups of 64 consecutive tokens (flattened b, py, px).  The 12 (channel, row)
+// image segments of a group are loaded coalesced into shared memory; then one warp per token.  Lane owns output
+// channels lane + 32*o and keeps its 48 x 4 weights in REGISTERS (the kernel is otherwise bound by shared-memory
+// weight reads: one LDS per FMA), so a token costs 12 broadcast LDS.128 + 192 FMA per lane.
+constexpr int PE_TOK = 64;
+__global__ void __launch_bounds__(256, 1) patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ out, int B,
+                                                             int S, int groups) {
+  __shared__ float4 in_s[PE_TOK][13];  // [token][ci*4+ky] = 4 pixels of one patch row (+1 pad)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float wr[48][4];
+#pragma unroll
+  for (int k = 0; k < 48; ++k)
+#pragma unroll
+    for (int o = 0; o < 4; ++o) wr[k][o] = w[(lane + 32 * o) * 48 + k];  // conv weight [128][3][4][4] -> k = ci*16 + ky*4 + kx
+  float bs[4], gm[4], bt[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) { bs[o] = bias[lane + 32 * o]; gm[o] = gamma[lane + 32 * o]; bt[o] = beta[lane + 32 * o]; }
   const int P = S / 4;
   const long long total = (long long)B * P * P;
-  const long long first = (long long)blockIdx.x * tokens_per_cta;
-  for (long long tok = first + warp; tok < first + tokens_per_cta && tok < total; tok += 8) {
-    const int b = (int)(tok / (P * P));
-    const int rem = (int)(tok - (long long)b * P * P);
-    const int py = rem / P, px = rem - py * P;
-    // 48 inputs: lanes 0..11 each load one float4 (ci, ky) row of 4 pixels
-    float4 in4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < 12) {
-      const int ci = lane >> 2, ky = lane & 3;
-      in4 = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + ci) * S + py * 4 + ky) * S + px * 4);
-    }
-    float acc[4] = {bias[lane], bias[lane + 32], bias[lane + 64], bias[lane + 96]};
+  // software pipeline: the next group's 3 float4 per thread are fetched into registers while this group computes
+  auto fetch = [&](int grp, float4 (&v)[3]) {
+    const long long first = (long long)grp * PE_TOK;
 #pragma unroll
-    for (int r = 0; r < 12; ++r) {
-      const float i0 = __shfl_sync(0xffffffffu, in4.x, r), i1 = __shfl_sync(0xffffffffu, in4.y, r);
-      const float i2 = __shfl_sync(0xffffffffu, in4.z, r), i3 = __shfl_sync(0xffffffffu, in4.w, r);
-      const float* wr = ws + (r * 4) * 128 + lane;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        acc[o] = fmaf(i0, wr[o * 32], acc[o]);
-        acc[o] = fmaf(i1, wr[128 + o * 32], acc[o]);
-        acc[o] = fmaf(i2, wr[256 + o * 32], acc[o]);
-        acc[o] = fmaf(i3, wr[384 + o * 32], acc[o]);
+    for (int j = 0; j < 3; ++j) {
+      const int i = threadIdx.x + j * 256;
+      const int r = i / PE_TOK, tk = i - r * PE_TOK;  // consecutive threads -> consecutive tokens -> contiguous 16 B
+      const long long tok = first + tk;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grp < groups && tok < total) {
+        const int b = (int)(tok / (P * P));
+        const int rem = (int)(tok - (long long)b * P * P);
+        const int py = rem / P, px = rem - py * P;
+        const int ci = r >> 2, ky = r & 3;
+        v[j] = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + ci) * S + py * 4 + ky) * S + px * 4);
       }
     }
-    const float mean = warp_sum(acc[0] + acc[1] + acc[2] + acc[3]) * (1.0f / 128.f);
-    float q = 0.f;
+  };
+  float4 nxt[3];
+  fetch(blockIdx.x, nxt);
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const long long first = (long long)grp * PE_TOK;
+    __syncthreads();  // previous group's readers are done with in_s
 #pragma unroll
-    for (int o = 0; o < 4; ++o) q += (acc[o] - mean) * (acc[o] - mean);
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 128.f) + 1e-5f);
+    for (int j = 0; j < 3; ++j) {
+      const int i = threadIdx.x + j * 256;
+      in_s[i % PE_TOK][i / PE_TOK] = nxt[j];
+    }
+    __syncthreads();
+    fetch(grp + gridDim.x, nxt);
+    for (int tk = warp; tk < PE_TOK; tk += 8) {
+      const long long tok = first + tk;
+      if (tok >= total) break;
+      float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const int n = lane + 32 * o;
-      out[tok * 128 + n] = (acc[o] - mean) * rstd * gamma[n] + beta[n];
+      for (int r = 0; r < 12; ++r) {
+        const float4 iv = in_s[tk][r];  // broadcast read
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          acc[o] = fmaf(iv.x, wr[4 * r + 0][o], acc[o]);
+          acc[o] = fmaf(iv.y, wr[4 * r + 1][o], acc[o]);
+          acc[o] = fmaf(iv.z, wr[4 * r + 2][o], acc[o]);
+          acc[o] = fmaf(iv.w, wr[4 * r + 3][o], acc[o]);
+        }
+      }
+      const float mean = warp_sum(acc[0] + acc[1] + acc[2] + acc[3]) * (1.0f / 128.f);
+      float q = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) q += (acc[o] - mean) * (acc[o] - mean);
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / 128.f) + 1e-5f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) out[tok * 128 + lane + 32 * o] = (acc[o] - mean) * rstd * gm[o] + bt[o];
     }
   }
 }
@@ -226,8 +250,12 @@ extern "C" int mst_patch_embed(const float* img, const float* w, const float* b,
                                float* x, int B, int S, void* stream) {
   if (!img || !w || !b || !gamma || !beta || !x || B <= 0 || S <= 0 || S % 4 != 0) return MST_ERR_BAD_ARG;
   const long long total = (long long)B * (S / 4) * (S / 4);
-  const int per = 64;
-  patch_embed_kernel<<<(unsigned)((total + per - 1) / per), 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, B, S, per);
+  const long long groups = (total + PE_TOK - 1) / PE_TOK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(groups < 2LL * sms ? groups : 2LL * sms);
+  patch_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, B, S, (int)groups);
   return (int)cudaGetLastError();
 }
 
