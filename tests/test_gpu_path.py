@@ -197,3 +197,19 @@ def test_loss_properties_at_bench_shape(loss_module):
         assert ls2.item() < 1e-6 and lc2.item() > 0
         again = loss_module(c, s, s, output_content_and_style_loss=True)
         assert again[0].item() == t2.item()
+
+
+def test_pipelined_host_api_matches_direct_call(model):
+    """GraphedStylizer.stylize_many (overlapped H2D / graph / D2H) returns exactly what model(...) returns."""
+    from mastermetastyletransfer_b200 import synthetic
+    from mastermetastyletransfer_b200.runtime import GraphedStylizer
+    runner = GraphedStylizer(model, 2, 128, 1)
+    batches, expect = [], []
+    for i in range(5):
+        c, s = synthetic.synthetic_images(2, 128, seed=10 + i)
+        with torch.no_grad():
+            expect.append(model(c.cuda(), s.cuda(), 1).cpu())
+        batches.append((c.pin_memory(), s.pin_memory(), torch.empty(2, 3, 128, 128).pin_memory()))
+    runner.stylize_many(batches)
+    for (_, _, out), ref in zip(batches, expect):
+        assert torch.equal(out, ref)
