@@ -79,6 +79,12 @@ typedef struct MstGemm {
 
 int mst_gemm(const MstGemm* g, void* stream);
 
+/* Same operation for a_mode == MST_A_CONV3X3 (no res/mul), im2col-free: a CTA stages R+2 input rows of a band
+ * once in shared memory and the tensor core reads all nine taps from it through shifted SWIZZLE_NONE descriptors
+ * (conv_band.cu).  Cin % 16 == 0.  mst_conv3x3_band_supported() says whether a band plan exists for a shape. */
+int mst_conv3x3_band(const MstGemm* g, void* stream);
+int mst_conv3x3_band_supported(int N, int Cin, int H, int W);
+
 /* ------------------------------------------------------------------------------------------
  * Fused shifted-window attention core: roll + window partition folded into the loads, QK^T,
  * relative-position bias, 9-region shift mask, softmax, PV, window reverse + roll back folded into

@@ -56,6 +56,8 @@ SYMBOLS = {
     "mst_pack_conv3x3_weight": (_I, [_P, _I, _I, _P, _I, _I, _P]),
     "mst_gemm_tile_n": (_I, [_I]),
     "mst_gemm": (_I, [C.POINTER(MstGemm), _P]),
+    "mst_conv3x3_band": (_I, [C.POINTER(MstGemm), _P]),
+    "mst_conv3x3_band_supported": (_I, [_I, _I, _I, _I]),
     "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
     "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),

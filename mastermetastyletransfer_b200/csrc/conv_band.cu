@@ -1,0 +1,372 @@
+// 3x3 convolution as an im2col-free implicit GEMM on tcgen05 (sm_100a).
+//
+// A CTA takes a "band": R output rows of one image, full width.  The R+2 input rows it needs (zero / reflect
+// padding and an optional nearest x2 upsample applied while loading) are staged ONCE in shared memory as
+//     halo[channel chunk of 8][padded pixel]   (16 bytes per entry, pitch Wp = W + 2 pixels per row)
+// which is exactly the SWIZZLE_NONE K-major UMMA layout: for one 16-byte channel chunk, 8 consecutive pixels
+// are a contiguous 128-byte core matrix, the next 8 pixels are SBO = 128 B further, the next channel chunk is
+// LBO = NPX*16 B further.  Output positions are enumerated over the PADDED raster (Wp per row, 2 of Wp are
+// discarded), so tap (ky,kx) of 128 consecutive positions is the same operand shifted by ky*Wp + kx pixels:
+// nine taps = nine descriptor start addresses, no data movement.  Each input pixel is read from L2/HBM
+// (R+2)/R times instead of nine.  Weight tiles stream through a small ring with one bulk copy per k-block
+// (same pre-swizzled packing as gemm_tc.cu).  All NS = ceil(R*Wp/128) strips of the band accumulate in TMEM
+// (NS*BN <= 512 columns) while the k-blocks stream once.
+#include "../../include/mst_b200.h"
+#include "common.cuh"
+
+namespace mst {
+
+constexpr int CB_THREADS = 256;
+constexpr int CB_MAX_BIAS = 1024;
+
+struct BandGeom {
+  int R;          // output rows per band
+  int NS;         // 128-position strips per band
+  int npx;        // allocated halo pixels per channel chunk
+  int Wp;         // padded row pitch (W + 2)
+  int bands_per_img;
+  int n_tiles;    // N / BN
+  int wst;        // weight ring stages
+  int tmem_cols;  // TMEM columns allocated by the CTA (256 when two CTAs share an SM, else 512)
+};
+
+MST_DEVINL void cb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+MST_DEVINL void cb_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// K-major SWIZZLE_NONE descriptor: 8-row x 16-byte core matrices, LBO between the two K chunks of a K=16 step,
+// SBO between consecutive 8-row groups (cute::UMMA::SmemDescriptor, layout type 0).
+MST_DEVINL uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const MstGemm p, const BandGeom g, const int total_units) {
+  constexpr int MAXST = 4;
+  constexpr int B_STAGE_BYTES = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[MAXST];
+  __shared__ uint64_t empty_bar[MAXST];
+  __shared__ uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[CB_MAX_BIAS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t halo_base = ring_base + g.wst * B_STAGE_BYTES;
+  const int cpp = p.Cin >> 3;            // 16-byte chunks per pixel
+  const int kpt = p.Cin >> 4;            // K=16 steps per tap
+  const int total_ks = 9 * kpt;
+  const int nkb = p.k_pad / 64;
+  const int Hs = p.upsample ? (p.H >> 1) : p.H;
+  const int Ws = p.upsample ? (p.W >> 1) : p.W;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.wst; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < p.N; i += CB_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_slot), g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
+  const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
+  constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+#ifdef MST_BAND_PROF
+  long long t_fill = 0, t_mma = 0, t_epi = 0, t_mark = clock64();
+#endif
+  int wit = 0;  // running weight k-block counter (ring position), identical in producer and MMA warps
+  int ucount = 0;
+
+  // Issue (do not wait for) the cp.async gathers that stage the (R+2)-row halo of `unit`, with zero / reflect
+  // padding and the nearest-x2 upsample applied on the fly.
+  auto issue_halo = [&](int unit) {
+    const int band = unit / g.n_tiles;
+    const int b = band / g.bands_per_img;
+    const int y0 = (band - b * g.bands_per_img) * g.R;
+    const bf16* img = Abase + (long long)b * Hs * Ws * p.Cin;
+    const int row_chunks = g.Wp * cpp;
+    for (int hr = 0; hr < g.R + 2; ++hr) {
+      int yy = y0 + hr - 1;
+      bool vrow = true;
+      if (p.pad_mode == 1) {  // reflect (no edge repeat)
+        yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+        yy = min(max(yy, 0), p.H - 1);  // rows past the image in a partial last band (their outputs are discarded)
+      } else {
+        vrow = (unsigned)yy < (unsigned)p.H;
+      }
+      if (p.upsample) yy >>= 1;
+      const bf16* rowsrc = img + (long long)yy * Ws * p.Cin;
+      const uint32_t rowdst = halo_base + (uint32_t)(hr * g.Wp + 1) * 16u;
+      for (int idx = threadIdx.x; idx < row_chunks; idx += CB_THREADS) {
+        const int col = idx / cpp;
+        const int c = idx - col * cpp;
+        int xx = col - 1;
+        bool valid = vrow;
+        if (p.pad_mode == 1) xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        else valid = valid && (unsigned)xx < (unsigned)p.W;
+        if (p.upsample) xx >>= 1;
+        cp_async16(rowdst + (uint32_t)(c * g.npx + col) * 16u, valid ? rowsrc + (xx * p.Cin + c * 8) : Abase, valid);
+      }
+    }
+  };
+  if ((int)blockIdx.x < total_units) issue_halo(blockIdx.x);
+
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++ucount) {
+    const int n_tile = unit % g.n_tiles;
+    const int band = unit / g.n_tiles;
+    const int b = band / g.bands_per_img;
+    const int y0 = (band - b * g.bands_per_img) * g.R;
+
+    // ---------------- phase 1: the halo of this band was issued ahead (before the previous epilogue); land it ----------------
+    cp_async_wait_all();
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    __syncthreads();
+#ifdef MST_BAND_PROF
+    { long long n = clock64(); t_fill += n - t_mark; t_mark = n; }
+#endif
+
+    // ---------------- phase 2: stream weight k-blocks, accumulate every strip of the band in TMEM ----------------
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint8_t* wtile = Wbase + (size_t)n_tile * nkb * B_STAGE_BYTES;
+        int it = wit;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % g.wst;
+          if (it >= g.wst) mbar_wait(smem_u32(&empty_bar[s]), ((it / g.wst) - 1) & 1);
+          cb_arrive_expect_tx(smem_u32(&full_bar[s]), B_STAGE_BYTES);
+          cb_bulk_g2s(ring_base + s * B_STAGE_BYTES, wtile + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&full_bar[s]));
+        }
+      }
+    } else if (warp == 1) {
+      int it = wit;
+      const uint32_t lbo = (uint32_t)g.npx * 16u;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % g.wst;
+        mbar_wait(smem_u32(&full_bar[s]), (it / g.wst) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t b_stage = ring_base + s * B_STAGE_BYTES;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int ks = kb * 4 + j;
+            if (ks >= total_ks) break;
+            const int tap = ks / kpt;
+            const int chunk0 = (ks - tap * kpt) * 2;  // first of the two 16-byte channel chunks of this K=16 step
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint64_t bd = umma_desc_sw128(b_stage + j * 32);
+            const uint32_t a0 = halo_base + (uint32_t)(chunk0 * g.npx + ky * g.Wp + kx) * 16u;
+            for (int st = 0; st < g.NS; ++st)
+              umma_bf16(tmem_base + st * BN, umma_desc_none(a0 + (uint32_t)st * 2048u, lbo, 128u), bd, idesc, ks != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (kb == nkb - 1) umma_commit(smem_u32(&accum_bar));
+        }
+        __syncwarp();
+      }
+    }
+    wit += nkb;
+
+    // ---------------- phase 3: epilogue (all 8 warps) ----------------
+    if (lane == 0) mbar_wait(smem_u32(&accum_bar), ucount & 1);
+    __syncwarp();
+    tc_fence_after();
+#ifdef MST_BAND_PROF
+    { long long n = clock64(); t_mma += n - t_mark; t_mark = n; }
+#endif
+    // every MMA of this band has retired, so the halo buffer is free: start fetching the next band's halo now and
+    // let it land while the epilogue drains TMEM
+    __syncthreads();
+    if (unit + (int)gridDim.x < total_units) issue_halo(unit + gridDim.x);
+    {
+      constexpr int CH = 16;
+      constexpr int NCC = BN / CH;
+      const int quad = warp & 3, half = warp >> 2;
+      const int nbase = n_tile * BN;
+      const long long hw = (long long)p.H * p.W;
+#pragma unroll 1
+      for (int item = half; item < g.NS * NCC; item += 2) {
+        const int st = item / NCC, cc = item - st * NCC;
+        uint32_t v[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + st * BN + cc * CH;
+        tmem_ld16(taddr, v);
+        tmem_wait_ld();
+        const int q = st * 128 + quad * 32 + lane;
+        const int r = q / g.Wp;
+        const int pxl = q - r * g.Wp;
+        const int y = y0 + r, x = pxl - 1;
+        if (r >= g.R || y >= p.H || x < 0 || x >= p.W) continue;
+        const int n = nbase + cc * CH;
+        float xv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          xv[j] = __uint_as_float(v[j]) + bias_s[n + j];
+          if (p.act == MST_ACT_RELU) xv[j] = fmaxf(xv[j], 0.0f);
+          else if (p.act == MST_ACT_GELU) xv[j] = gelu_erf(xv[j]);
+        }
+        const long long pix = (long long)b * hw + (long long)y * p.W + x;
+        if (p.out_nchw) {
+          const long long base = (long long)b * p.n_real * hw + (long long)y * p.W + x;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.n_real) p.out_f32[base + (long long)(n + j) * hw] = xv[j];
+        } else {
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out32 + n);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]);
+          }
+          if (p.out_bf16) {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + pix * p.ld_out16 + n);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(xv[8 * j + 2 * e], xv[8 * j + 2 * e + 1]);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and the halo are free for the next band
+    tc_fence_after();
+#ifdef MST_BAND_PROF
+    { long long n = clock64(); t_epi += n - t_mark; t_mark = n; }
+#endif
+  }
+#ifdef MST_BAND_PROF
+  if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 64)) printf("band prof thread %d units %d: fill %lld mma %lld epi %lld cycles (R=%d NS=%d npx=%d)\n", threadIdx.x, ucount, t_fill, t_mma, t_epi, g.R, g.NS, g.npx);
+#endif
+  if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+static int cb_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// Choose rows per band: the halo must fit beside the weight ring, all strips must fit in TMEM; maximise
+// (useful MMA rows / issued MMA rows) * (halo reuse R/(R+2)).
+static bool plan_band_with(const MstGemm& g, int BN, long long smem_total, int tmem_cols, BandGeom& out, double& best) {
+  const int Wp = g.W + 2;
+  const int wst = BN >= 256 ? 2 : 4;
+  const long long budget = smem_total - 1024 /*align*/ - (long long)wst * BN * 128;
+  best = 0.0;
+  bool ok = false;
+  for (int R = 1; R <= g.H && R <= 32; ++R) {
+    const int NS = (R * Wp + 127) / 128;
+    if (NS * BN > tmem_cols) break;
+    const int npx = NS * 128 + 2 * Wp + 8;
+    const long long halo = (long long)g.Cin * 2 * npx;
+    if (halo > budget) break;
+    if (npx > 0x3FFF) break;  // LBO field
+    const int bands = (g.H + R - 1) / R;
+    const double util = (double)g.H * g.W / ((double)bands * NS * 128.0);
+    const double score = util * R / (R + 2.0);
+    if (score > best) {
+      best = score;
+      ok = true;
+      out.R = R; out.NS = NS; out.npx = npx; out.Wp = Wp; out.bands_per_img = bands; out.n_tiles = g.N / BN; out.wst = wst;
+      out.tmem_cols = tmem_cols;
+    }
+  }
+  return ok;
+}
+
+// Prefer a plan that lets two CTAs share an SM (half the shared memory and TMEM each): their load / MMA / epilogue
+// phases then overlap.  Fall back to one big CTA per SM when that would cost too much halo re-reading.
+static bool plan_band(const MstGemm& g, int BN, BandGeom& out) {
+  BandGeom two, one;
+  double s2 = 0.0, s1 = 0.0;
+  const bool ok2 = plan_band_with(g, BN, 110 * 1024, 256, two, s2);
+  const bool ok1 = plan_band_with(g, BN, 220 * 1024, 512, one, s1);
+  // measured (tools/gemm_bench.py band): the extra halo re-reads of the small plan cost more than the overlap gains
+  if (ok1) { out = one; return true; }
+  if (ok2) { out = two; return true; }
+  return false;
+}
+
+template <int BN>
+static int launch_band(const MstGemm& g, cudaStream_t st) {
+  BandGeom geo;
+  if (!plan_band(g, BN, geo)) return MST_ERR_UNSUPPORTED;
+  const size_t smem = 1024 + (size_t)geo.wst * BN * 128 + (size_t)g.Cin * 2 * geo.npx;
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_band_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = 227 * 1024;
+  }
+  const int B = g.M / (g.H * g.W);
+  const long long units = (long long)B * geo.bands_per_img * geo.n_tiles;
+  const unsigned grid = (unsigned)(units < cb_num_sms() ? units : cb_num_sms());
+  conv_band_kernel<BN><<<grid, CB_THREADS, smem, st>>>(g, geo, (int)units);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" int mst_conv3x3_band_supported(int N, int Cin, int H, int W) {
+  if (N <= 0 || N % 16 || N > CB_MAX_BIAS || Cin % 16 || Cin <= 0 || H < 2 || W < 2) return 0;
+  MstGemm g{};
+  g.N = N; g.Cin = Cin; g.H = H; g.W = W;
+  BandGeom geo;
+  const int bn = mst_gemm_tile_n(N);
+  return plan_band(g, bn, geo) ? 1 : 0;
+}
+
+extern "C" int mst_conv3x3_band(const MstGemm* g, void* stream) {
+  if (!g || !g->A || !g->Wt) return MST_ERR_BAD_ARG;
+  if (g->a_mode != MST_A_CONV3X3 || g->M <= 0 || g->N <= 0 || g->K != 9 * g->Cin || g->k_pad % 64 || g->k_pad < g->K) return MST_ERR_BAD_ARG;
+  if (g->N % 16 || g->N > CB_MAX_BIAS || g->Cin % 16) return MST_ERR_UNSUPPORTED;
+  if (g->H < 2 || g->W < 2 || g->M % (g->H * g->W) != 0) return MST_ERR_BAD_ARG;
+  if (g->upsample && ((g->H | g->W) & 1)) return MST_ERR_BAD_ARG;
+  if (g->res || g->mul) return MST_ERR_UNSUPPORTED;
+  if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
+  if (g->out_nchw) {
+    if (!g->out_f32 || g->n_real <= 0 || g->n_real > g->N) return MST_ERR_BAD_ARG;
+  } else {
+    if (g->out_f32 && g->ld_out32 % 4) return MST_ERR_BAD_ARG;
+    if (g->out_bf16 && g->ld_out16 % 8) return MST_ERR_BAD_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mst_gemm_tile_n(g->N)) {
+    case 256: return launch_band<256>(*g, st);
+    case 128: return launch_band<128>(*g, st);
+    case 64: return launch_band<64>(*g, st);
+    case 32: return launch_band<32>(*g, st);
+    default: return launch_band<16>(*g, st);
+  }
+}

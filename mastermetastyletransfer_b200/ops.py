@@ -50,7 +50,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
     launch_count += 1
 
 
-KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
+KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -148,8 +148,31 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
         g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
         g.out_nchw, g.n_real = int(conv.get("out_nchw", False)), conv.get("n_real", pm.N)
-    _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=2.0 * M * min(N, pm.N) * pm.K,
-            desc=f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}")
+    desc = f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}"
+    flops = 2.0 * M * min(N, pm.N) * pm.K
+    if conv is not None and _use_band(conv, N):
+        _launch("mst_conv3x3_band", lambda: _lib.lib().mst_conv3x3_band(C.byref(g), _stream()), flops=flops, desc=desc + " band")
+    else:
+        _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=flops, desc=desc)
+
+
+BAND_MAX_CIN = 64  # measured: from Cin = 128 up the gathered implicit GEMM is faster (tools/gemm_bench.py band)
+
+
+def band_supported(n: int, cin: int, H: int, W: int) -> bool:
+    return cin % 16 == 0 and bool(_lib.lib().mst_conv3x3_band_supported(n_pad_of(n), cin, H, W))
+
+
+def _use_band(conv: dict, n_pad: int) -> bool:
+    impl = conv.get("impl", "auto")
+    if impl == "gather":
+        return False
+    ok = conv["Cin"] % 16 == 0 and bool(_lib.lib().mst_conv3x3_band_supported(n_pad, conv["Cin"], conv["H"], conv["W"]))
+    if impl == "band":
+        if not ok:
+            raise ValueError("conv3x3 band kernel does not support this shape")
+        return True
+    return ok and conv["Cin"] <= BAND_MAX_CIN
 
 
 def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,

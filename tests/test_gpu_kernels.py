@@ -68,10 +68,15 @@ def test_gemm_epilogues():
     (2, 16, 16, 64, 64, "reflect", False, True), (1, 32, 32, 256, 128, "reflect", False, True),
     (2, 16, 16, 128, 128, "reflect", True, True), (1, 32, 32, 32, 32, "reflect", True, True),
     (2, 16, 16, 64, 128, "zeros", False, True), (1, 8, 8, 512, 512, "zeros", False, True),
-    (3, 12, 20, 32, 64, "zeros", False, False)])
-def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu):
-    """H, W are the conv's output size; with up=True the stored input is [B,H/2,W/2,Cin]."""
+    (3, 12, 20, 32, 64, "zeros", False, False), (1, 128, 128, 64, 64, "reflect", True, True),
+    (1, 256, 256, 32, 32, "reflect", False, True), (2, 30, 34, 64, 256, "zeros", False, True)])
+@pytest.mark.parametrize("impl", ["gather", "band"])
+def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
+    """H, W are the conv's output size; with up=True the stored input is [B,H/2,W/2,Cin].
+    impl: gathered implicit GEMM (gemm_tc.cu) or the halo-band kernel (conv_band.cu)."""
     ops = _ops()
+    if impl == "band" and not ops.band_supported(Cout, Cin, H, W):
+        pytest.skip("no band plan for this shape (halo + weight ring exceed shared memory)")
     hs, ws = (H // 2, W // 2) if up else (H, W)
     x = _rand(B, hs, ws, Cin, seed=10).bfloat16()
     wt = _rand(Cout, Cin, 3, 3, seed=11, scale=(9 * Cin) ** -0.5)
@@ -79,7 +84,7 @@ def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu):
     pm = ops.pack_conv3x3(wt.cuda(), bias.cuda())
     out = torch.empty(B * H * W, Cout, device="cuda")
     ops.gemm(x.cuda(), pm, B * H * W, act=ops.ACT_RELU if relu else ops.ACT_NONE, out_f32=out,
-             conv=dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT if pad == "reflect" else ops.PAD_ZERO, upsample=up))
+             conv=dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT if pad == "reflect" else ops.PAD_ZERO, upsample=up, impl=impl))
     xi = x.float().permute(0, 3, 1, 2)
     if up:
         xi = xi.repeat_interleave(2, 2).repeat_interleave(2, 3)
@@ -91,7 +96,8 @@ def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu):
     assert torch.allclose(out.cpu(), ref, atol=3e-3, rtol=3e-3), (out.cpu() - ref).abs().max()
 
 
-def test_conv3x3_nchw_out():
+@pytest.mark.parametrize("impl", ["gather", "band"])
+def test_conv3x3_nchw_out(impl):
     ops = _ops()
     B, H, W, Cin = 2, 32, 32, 32
     x = _rand(B, H, W, Cin, seed=13).bfloat16()
@@ -100,7 +106,7 @@ def test_conv3x3_nchw_out():
     pm = ops.pack_conv3x3(wt.cuda(), bias.cuda())
     out = torch.empty(B, 3, H, W, device="cuda")
     ops.gemm(x.cuda(), pm, B * H * W, out_f32=out,
-             conv=dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT, upsample=False, out_nchw=True, n_real=3))
+             conv=dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT, upsample=False, out_nchw=True, n_real=3, impl=impl))
     ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect"), wt.bfloat16().float(), bias)
     assert torch.allclose(out.cpu(), ref, atol=3e-3, rtol=3e-3)
 
