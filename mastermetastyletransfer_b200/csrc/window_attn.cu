@@ -76,35 +76,41 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
   __syncthreads();
 
   const int c0 = h * 32;
-  // ---- stage Q, K, V (V2): 4 lanes x 16 B per token row, 8 rows per pass ----
+  // ---- stage Q, K, V (V2): 4 lanes x 16 B per token row, 8 rows per pass; real tokens go global -> shared with
+  //      cp.async (all 24-32 copies of a lane in flight at once, no register staging) ----
   {
     const int chunk = lane & 3, rsub = lane >> 2;
-#pragma unroll 2
+    const uint32_t qs = smem_u32(Qs), ks_ = smem_u32(Ks), vs = smem_u32(Vs), v2s = smem_u32(V2s);
+#pragma unroll
     for (int r = rsub; r < NP; r += 8) {
       const int s = src_s[r];
-      uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv, v2v = qv;
+      const uint32_t off = (uint32_t)(r * AT_LD + chunk * 8) * 2u;
       if (s >= 0) {
-        qv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.q) + (long long)s * a.ldq + c0 + chunk * 8);
-        kv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.k) + (long long)s * a.ldk + c0 + chunk * 8);
-        vv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.v) + (long long)s * a.ldv + c0 + chunk * 8);
-        if (dual) v2v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.v2) + (long long)s * a.ldv + c0 + chunk * 8);
-      } else if (s == -1) {
-        const int cc = c0 + chunk * 8;
-        uint32_t* qp = reinterpret_cast<uint32_t*>(&qv); uint32_t* kp = reinterpret_cast<uint32_t*>(&kv);
-        uint32_t* vp = reinterpret_cast<uint32_t*>(&vv); uint32_t* wp = reinterpret_cast<uint32_t*>(&v2v);
+        cp_async16(qs + off, reinterpret_cast<const bf16*>(a.q) + (long long)s * a.ldq + c0 + chunk * 8, true);
+        cp_async16(ks_ + off, reinterpret_cast<const bf16*>(a.k) + (long long)s * a.ldk + c0 + chunk * 8, true);
+        cp_async16(vs + off, reinterpret_cast<const bf16*>(a.v) + (long long)s * a.ldv + c0 + chunk * 8, true);
+        if (dual) cp_async16(v2s + off, reinterpret_cast<const bf16*>(a.v2) + (long long)s * a.ldv + c0 + chunk * 8, true);
+      } else {
+        uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv, v2v = qv;
+        if (s == -1) {  // zero-padded token: its projections are the biases
+          const int cc = c0 + chunk * 8;
+          uint32_t* qp = reinterpret_cast<uint32_t*>(&qv); uint32_t* kp = reinterpret_cast<uint32_t*>(&kv);
+          uint32_t* vp = reinterpret_cast<uint32_t*>(&vv); uint32_t* wp = reinterpret_cast<uint32_t*>(&v2v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (a.pad_q) qp[e] = pack_bf16(a.pad_q[cc + 2 * e], a.pad_q[cc + 2 * e + 1]);
-          if (a.pad_k) kp[e] = pack_bf16(a.pad_k[cc + 2 * e], a.pad_k[cc + 2 * e + 1]);
-          if (a.pad_v) vp[e] = pack_bf16(a.pad_v[cc + 2 * e], a.pad_v[cc + 2 * e + 1]);
-          if (dual && a.pad_v2) wp[e] = pack_bf16(a.pad_v2[cc + 2 * e], a.pad_v2[cc + 2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            if (a.pad_q) qp[e] = pack_bf16(a.pad_q[cc + 2 * e], a.pad_q[cc + 2 * e + 1]);
+            if (a.pad_k) kp[e] = pack_bf16(a.pad_k[cc + 2 * e], a.pad_k[cc + 2 * e + 1]);
+            if (a.pad_v) vp[e] = pack_bf16(a.pad_v[cc + 2 * e], a.pad_v[cc + 2 * e + 1]);
+            if (dual && a.pad_v2) wp[e] = pack_bf16(a.pad_v2[cc + 2 * e], a.pad_v2[cc + 2 * e + 1]);
+          }
         }
+        *reinterpret_cast<uint4*>(Qs + r * AT_LD + chunk * 8) = qv;
+        *reinterpret_cast<uint4*>(Ks + r * AT_LD + chunk * 8) = kv;
+        *reinterpret_cast<uint4*>(Vs + r * AT_LD + chunk * 8) = vv;
+        if (dual) *reinterpret_cast<uint4*>(V2s + r * AT_LD + chunk * 8) = v2v;
       }
-      *reinterpret_cast<uint4*>(Qs + r * AT_LD + chunk * 8) = qv;
-      *reinterpret_cast<uint4*>(Ks + r * AT_LD + chunk * 8) = kv;
-      *reinterpret_cast<uint4*>(Vs + r * AT_LD + chunk * 8) = vv;
-      if (dual) *reinterpret_cast<uint4*>(V2s + r * AT_LD + chunk * 8) = v2v;
     }
+    cp_async_wait_all();
   }
   __syncwarp();
 
@@ -114,6 +120,17 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
   const int cq = (lane & 3) * 2;   // fragment column pair within an 8-column tile
   const uint32_t q_base = smem_u32(Qs), k_base = smem_u32(Ks), v_base = smem_u32(Vs), v2_base = smem_u32(V2s);
   constexpr int MT = (N + 15) / 16;
+  // this lane's 16 score columns j = nt*8 + cq + e: relative-position part yj*(2WS-1)+xj and region label, once per task
+  int colpart[8][2], collab[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + cq + e;
+      const int yj = j / WS, xj = j - yj * WS;
+      colpart[nt][e] = yj * (2 * WS - 1) + xj;
+      collab[nt][e] = j < N ? lab_s[j] : -1;
+    }
 
 #pragma unroll 1
   for (int mt = 0; mt < MT; ++mt) {
@@ -144,22 +161,23 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
     // ---- scale + relative-position bias + shift mask, row max ----
     const int i0 = mt * 16 + gq, i1 = i0 + 8;
     const int yi0 = i0 / WS, xi0 = i0 - yi0 * WS, yi1 = i1 / WS, xi1 = i1 - yi1 * WS;
+    // bias index = (yi-yj+WS-1)*(2WS-1) + (xi-xj+WS-1) = rowpart - colpart; rows past the window read entry 0 (discarded)
+    const int rp0 = i0 < N ? (yi0 + WS - 1) * (2 * WS - 1) + xi0 + WS - 1 : 0;
+    const int rp1 = i1 < N ? (yi1 + WS - 1) * (2 * WS - 1) + xi1 + WS - 1 : 0;
     const int li0 = lab_s[i0], li1 = lab_s[i1];
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + cq + e;
         float s0 = -INFINITY, s1 = -INFINITY;
-        if (j < N) {
-          const int yj = j / WS, xj = j - yj * WS;
-          const int lj = lab_s[j];
-          s0 = sc[nt][e] * scale + ((i0 < N) ? tab[(yi0 - yj + WS - 1) * (2 * WS - 1) + (xi0 - xj + WS - 1)] : 0.f);
-          s1 = sc[nt][2 + e] * scale + ((i1 < N) ? tab[(yi1 - yj + WS - 1) * (2 * WS - 1) + (xi1 - xj + WS - 1)] : 0.f);
+        if (nt * 8 + cq + e < N) {  // (always true for 8x8 windows; folds away)
+          const int cp = colpart[nt][e];
+          s0 = fmaf(sc[nt][e], scale, tab[i0 < N ? rp0 - cp : 0]);
+          s1 = fmaf(sc[nt][2 + e], scale, tab[i1 < N ? rp1 - cp : 0]);
           if (masked) {
-            if (lj != li0) s0 += -100.0f;
-            if (lj != li1) s1 += -100.0f;
+            if (collab[nt][e] != li0) s0 += -100.0f;
+            if (collab[nt][e] != li1) s1 += -100.0f;
           }
         }
         sc[nt][e] = s0;
