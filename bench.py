@@ -233,9 +233,10 @@ def main():
         families = {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "share": round(v["ms"] / tot_ms, 4),
                         "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["flops"] else None,
                         "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["bytes"] else None} for k, v in fam.items()}
-        g = fam["gemm_tc_kernel"]
+        dom = max((k for k in fam if fam[k]["flops"]), key=lambda k: fam[k]["ms"])  # dominant tensor-core kernel family
+        g = fam[dom]
         achieved = g["flops"] / (g["ms"] * 1e9)
-        roofline = {"kernel": "gemm_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                     "frac": achieved / sustained, "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
                     "launches_per_step": g["launches"], "share_of_step": g["ms"] / tot_ms,
                     "step": {"achieved": flops_per_image(args.size, args.layers) * batch / (ms_step * 1e9), "unit": "TFLOP/s",

@@ -86,6 +86,26 @@ int mst_conv3x3_band(const MstGemm* g, void* stream);
 int mst_conv3x3_band_supported(int N, int Cin, int H, int W);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused transformer MLP (torchvision ops/misc.py:264-306 MLP as used at style_transformer.py:366,839-841,991
+ * and in the tv Swin blocks):  out = res + fc2(GELU_erf(fc1(A) + b1)) + b2  with the [M x 4C] hidden activation
+ * kept on chip (TMEM -> GELU -> swizzled shared memory -> second tcgen05 GEMM).  C in {128, 256}.
+ * Both weight matrices are packed once into one linear stream of 32 KB stages in consumption order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MstMlp {
+  const mst_bf16* A;       /* bf16 [M, lda] */
+  const mst_bf16* Wstream; /* mst_pack_mlp_weights() output, mst_mlp_stream_bytes(C) bytes */
+  const float* b1;         /* [4C] */
+  const float* b2;         /* [C] */
+  const float* res;        /* fp32 [M, ld_res] or NULL (may alias out_f32) */
+  float* out_f32;          /* fp32 [M, ld_out32] or NULL */
+  mst_bf16* out_bf16;      /* bf16 [M, ld_out16] or NULL */
+  int M, C, lda, ld_res, ld_out32, ld_out16;
+} MstMlp;
+size_t mst_mlp_stream_bytes(int C);
+int mst_pack_mlp_weights(const float* w1 /*[4C,C]*/, const float* w2 /*[C,4C]*/, mst_bf16* dst, int C, void* stream);
+int mst_mlp_fused(const MstMlp* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused shifted-window attention core: roll + window partition folded into the loads, QK^T,
  * relative-position bias, 9-region shift mask, softmax, PV, window reverse + roll back folded into
  * the store (codes/style_transformer.py:83-111,127-168; with v2/out2 set it is the shared-softmax

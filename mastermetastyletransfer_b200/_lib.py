@@ -37,6 +37,12 @@ class MstWindowAttn(C.Structure):
     ]
 
 
+class MstMlp(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("Wstream", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("res", C.c_void_p),
+                ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
+                ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int)]
+
+
 class MstLossTap(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("mean_s", C.c_void_p), ("var_s", C.c_void_p), ("mean_o", C.c_void_p),
                 ("var_o", C.c_void_p), ("n_partials", C.c_int), ("B", C.c_int), ("T", C.c_int), ("C", C.c_int)]
@@ -58,6 +64,9 @@ SYMBOLS = {
     "mst_gemm": (_I, [C.POINTER(MstGemm), _P]),
     "mst_conv3x3_band": (_I, [C.POINTER(MstGemm), _P]),
     "mst_conv3x3_band_supported": (_I, [_I, _I, _I, _I]),
+    "mst_mlp_stream_bytes": (_Z, [_I]),
+    "mst_pack_mlp_weights": (_I, [_P, _P, _P, _I, _P]),
+    "mst_mlp_fused": (_I, [C.POINTER(MstMlp), _P]),
     "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
     "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),

@@ -68,8 +68,7 @@ class SwinEncoderWeights:
                 pad_q=qkv_b[:C].contiguous(), pad_k=qkv_b[C:2 * C].contiguous(), pad_v=qkv_b[2 * C:].contiguous(),
                 proj=ops.pack_linear(g(p + "attn.proj.weight"), g(p + "attn.proj.bias")),
                 table=g(p + "attn.relative_position_bias_table"),
-                fc1=ops.pack_linear(g(p + "mlp.0.weight"), g(p + "mlp.0.bias")),
-                fc2=ops.pack_linear(g(p + "mlp.3.weight"), g(p + "mlp.3.bias")),
+                mlp=ops.pack_mlp(g(p + "mlp.0.weight"), g(p + "mlp.0.bias"), g(p + "mlp.3.weight"), g(p + "mlp.3.bias")),
             )
         self.pm_g, self.pm_b = g("2.norm.weight"), g("2.norm.bias")
         self.pm_red = ops.pack_linear(g("2.reduction.weight"), None)
@@ -82,15 +81,13 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
     ln = ws_.bf16(tag + "ln", T, C)
     qkv = ws_.bf16(tag + "qkv", T, 3 * C)
     o = ws_.bf16(tag + "o", T, C)
-    h = ws_.bf16(tag + "h", T, 4 * C)
     ops.layernorm(x32, bw["n1w"], bw["n1b"], ln, T, C)
     ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
     ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
                          3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
     ops.gemm(o, bw["proj"], T, res=x32, out_f32=x32)
     ops.layernorm(x32, bw["n2w"], bw["n2b"], ln, T, C)
-    ops.gemm(ln, bw["fc1"], T, act=ACT_GELU, out_bf16=h)
-    ops.gemm(h, bw["fc2"], T, res=x32, out_f32=x32)
+    ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32)  # fc1 + GELU + fc2 + residual, hidden kept on chip
 
 
 def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor]):
@@ -128,7 +125,7 @@ class StyleTransformerWeights:
         g = lambda k: _f32(sd[prefix + k])
 
         def mlp(p):
-            return (ops.pack_linear(g(p + "0.weight"), g(p + "0.bias")), ops.pack_linear(g(p + "3.weight"), g(p + "3.bias")))
+            return ops.pack_mlp(g(p + "0.weight"), g(p + "0.bias"), g(p + "3.weight"), g(p + "3.bias"))
 
         e = "encoder.shared_MHA_without_MLP.attn."
         wq, wk, wv = g(e + "Wq.weight"), g(e + "Wk.weight"), g(e + "Wv.weight")
@@ -164,10 +161,8 @@ class StyleTransformerWeights:
 
 
 def _mlp_residual(x16, x32, fc, T, ws_: Workspace, out16):
-    """x32 += fc2(gelu(fc1(x16))) ; optionally refresh the bf16 copy."""
-    h = ws_.bf16("st_h", T, fc[0].n_pad)
-    ops.gemm(x16, fc[0], T, act=ACT_GELU, out_bf16=h)
-    ops.gemm(h, fc[1], T, res=x32, out_f32=x32, out_bf16=out16)
+    """x32 += fc2(gelu(fc1(x16))) in one fused kernel; optionally refresh the bf16 copy."""
+    ops.mlp_fused(x16, fc, T, res=x32, out_f32=x32, out_bf16=out16)
 
 
 def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs32: torch.Tensor, k: int, ws_: Workspace,

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MstGemm, MstLossTap, MstLossTaps, MstWindowAttn, check
+from ._lib import MstGemm, MstLossTap, MstLossTaps, MstMlp, MstWindowAttn, check
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 A_PLAIN, A_CONV3X3 = 0, 1
@@ -50,7 +50,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
     launch_count += 1
 
 
-KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
+KERNEL_OF = {"mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -278,3 +278,38 @@ def loss_finalize(taps, lam: float, squared_style: bool, out3) -> None:
         e.n_partials, e.B, e.T, e.C = t["partials"].numel(), t["B"], t["T"], t["C"]
     _launch("mst_loss_finalize", lambda: _lib.lib().mst_loss_finalize(C.byref(pack), float(lam), int(squared_style),
                                                                        _ptr(out3, torch.float32, "out3"), _stream()))
+
+
+class PackedMlp:
+    """fc1/fc2 of one MLP packed as the fused kernel's weight stream, plus the fp32 biases."""
+
+    __slots__ = ("stream", "b1", "b2", "C")
+
+    def __init__(self, stream, b1, b2, Cdim):
+        self.stream, self.b1, self.b2, self.C = stream, b1, b2, Cdim
+
+
+def pack_mlp(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> PackedMlp:
+    """nn.Linear weights fc1 [4C,C], fc2 [C,4C] (fp32) -> PackedMlp.  C must be 128 or 256."""
+    w1, w2 = w1.detach().contiguous(), w2.detach().contiguous()
+    hidden, Cdim = w1.shape
+    if hidden != 4 * Cdim or tuple(w2.shape) != (Cdim, hidden) or Cdim not in (128, 256):
+        raise ValueError("pack_mlp: expected fc1 [4C,C], fc2 [C,4C] with C in {128, 256}")
+    nbytes = _lib.lib().mst_mlp_stream_bytes(Cdim)
+    stream = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w1.device)
+    _launch("mst_pack_mlp_weights", lambda: _lib.lib().mst_pack_mlp_weights(_ptr(w1, torch.float32, "w1"), _ptr(w2, torch.float32, "w2"),
+                                                                            stream.data_ptr(), Cdim, _stream()))
+    return PackedMlp(stream, b1.detach().float().contiguous(), b2.detach().float().contiguous(), Cdim)
+
+
+def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out_bf16=None) -> None:
+    """out = res + fc2(gelu(fc1(A) + b1)) + b2, hidden activation kept on chip."""
+    g = MstMlp()
+    g.A, g.Wstream = _ptr(A, torch.bfloat16, "A"), pm.stream.data_ptr()
+    g.b1, g.b2 = _ptr(pm.b1, torch.float32, "b1"), _ptr(pm.b2, torch.float32, "b2")
+    g.res, g.out_f32, g.out_bf16 = _ptr(res, torch.float32, "res"), _ptr(out_f32, torch.float32, "out_f32"), _ptr(out_bf16, torch.bfloat16, "out_bf16")
+    g.M, g.C = M, pm.C
+    g.lda = pm.C if lda is None else lda
+    g.ld_res = g.ld_out32 = g.ld_out16 = pm.C
+    _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=16.0 * M * pm.C * pm.C,
+            desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}")

@@ -228,3 +228,26 @@ def test_bad_arguments_raise():
         ops.gemm(A.float(), pm, 128, out_f32=torch.empty(128, 16, device="cuda"))
     with pytest.raises(RuntimeError):
         ops.gemm(A.cpu(), pm, 128, out_f32=torch.empty(128, 16, device="cuda"))
+
+
+@pytest.mark.parametrize("M,C", [(128, 256), (1000, 256), (4096, 128), (333, 128), (40000, 256)])
+def test_mlp_fused(M, C):
+    """fc1 + GELU(erf) + fc2 + residual in one kernel, against fp32 torch on bf16-rounded operands
+    (the hidden activation is rounded to bf16 between the two GEMMs, as in the unfused path)."""
+    ops = _ops()
+    A = _rand(M, C, seed=70).bfloat16()
+    w1, b1 = _rand(4 * C, C, seed=71, scale=C ** -0.5), 0.1 * _rand(4 * C, seed=72)
+    w2, b2 = _rand(C, 4 * C, seed=73, scale=(4 * C) ** -0.5), 0.1 * _rand(C, seed=74)
+    res = _rand(M, C, seed=75)
+    pm = ops.pack_mlp(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    out32 = torch.empty(M, C, device="cuda")
+    out16 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    ops.mlp_fused(A.cuda(), pm, M, res=res.cuda(), out_f32=out32, out_bf16=out16)
+    h = F.gelu(A.float() @ w1.bfloat16().float().T + b1).bfloat16().float()
+    ref = res + h @ w2.bfloat16().float().T + b2
+    torch.cuda.synchronize()
+    assert torch.allclose(out32.cpu(), ref, atol=4e-3, rtol=4e-3), (out32.cpu() - ref).abs().max()
+    assert torch.allclose(out16.float().cpu(), ref, atol=3e-2, rtol=1e-2)
+    r = res.cuda()
+    ops.mlp_fused(A.cuda(), pm, M, res=r, out_f32=r)  # in-place residual stream
+    assert torch.allclose(r.cpu(), ref, atol=4e-3, rtol=4e-3)
