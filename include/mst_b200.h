@@ -189,6 +189,34 @@ typedef struct MstLossTaps {
 } MstLossTaps;
 int mst_loss_finalize(const MstLossTaps* taps, float lambda, int squared_style, float* out3, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-step glue: multi-tensor optimiser updates, one launch for all parameters.
+ * MstTensorTable describes up to any number of fp32 tensors through DEVICE arrays (built once per parameter
+ * list): chunk_start[t] = first CTA-chunk of tensor t (chunks of mst_opt_chunk_elems() elements, prefix sums),
+ * numel[t], flat_offset[t] = offset of tensor t in a flat fp32 buffer, a..d = per-tensor base pointers.
+ * mst_adam_step: torch.optim.Adam (no amsgrad) as used at train_only_inner_loop.py:468-478,573-575:
+ *   a = param, b = grad, c = exp_avg, d = exp_avg_sq; step is 1-based.
+ * mst_reptile_delta: flat[off_t + i] = omega_t[i] - theta_t[i]  (a = theta, b = omega)  -- the tensor that is
+ *   all-reduced across GPUs when each rank trained omega on its own style task.
+ * mst_reptile_apply: theta_t[i] += scale * flat[off_t + i]  (a = theta); with scale = outer_lr (/ world size)
+ *   this is train.py:524-534's theta += outer_lr * (omega - theta).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MstTensorTable {
+  const int* chunk_start;
+  const long long* numel;
+  const long long* flat_offset;
+  void* const* a;
+  void* const* b;
+  void* const* c;
+  void* const* d;
+  int n_tensors, n_chunks;
+} MstTensorTable;
+int mst_opt_chunk_elems(void);
+int mst_adam_step(const MstTensorTable* tb, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  void* stream);
+int mst_reptile_delta(const MstTensorTable* tb, float* flat, void* stream);
+int mst_reptile_apply(const MstTensorTable* tb, float* flat, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

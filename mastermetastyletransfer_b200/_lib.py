@@ -43,6 +43,11 @@ class MstMlp(C.Structure):
                 ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int)]
 
 
+class MstTensorTable(C.Structure):
+    _fields_ = [("chunk_start", C.c_void_p), ("numel", C.c_void_p), ("flat_offset", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p),
+                ("c", C.c_void_p), ("d", C.c_void_p), ("n_tensors", C.c_int), ("n_chunks", C.c_int)]
+
+
 class MstLossTap(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("mean_s", C.c_void_p), ("var_s", C.c_void_p), ("mean_o", C.c_void_p),
                 ("var_o", C.c_void_p), ("n_partials", C.c_int), ("B", C.c_int), ("T", C.c_int), ("C", C.c_int)]
@@ -75,6 +80,10 @@ SYMBOLS = {
     "mst_instnorm_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
+    "mst_opt_chunk_elems": (_I, []),
+    "mst_adam_step": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
+    "mst_reptile_delta": (_I, [C.POINTER(MstTensorTable), _P, _P]),
+    "mst_reptile_apply": (_I, [C.POINTER(MstTensorTable), _P, C.c_float, _P]),
     "mst_conv3x3_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),

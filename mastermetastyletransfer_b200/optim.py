@@ -1,0 +1,119 @@
+"""Training-step glue on the GPU: fused multi-tensor Adam and the Reptile-style
+outer update of train.py:524-534, generalised to one style task per GPU with an NCCL all-reduce of the
+parameter deltas.  Parameters stay ordinary nn.Parameters; the kernels get a device
+table of their pointers."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import MstTensorTable
+
+
+def _bump_versions(params) -> None:
+    """The kernels write parameters through raw pointers; bump the tensors' version counters so that everything keyed
+    on (data_ptr, _version) -- the packed-weight caches of the forward path -- sees the update."""
+    params = list(params)
+    try:
+        torch._C._autograd._unsafe_set_version_counter(tuple(params), tuple(p._version + 1 for p in params))
+    except Exception:  # older/newer torch without the helper: an in-place no-op bumps the counter too
+        with torch.no_grad():
+            for p in params:
+                p.add_(0.0)
+
+
+class _Table:
+    """Device-side description of a list of fp32 tensors (rebuilt only when a data pointer changes)."""
+
+    def __init__(self, lists: List[List[torch.Tensor]]):
+        n = len(lists[0])
+        dev = lists[0][0].device
+        chunk = _lib.lib().mst_opt_chunk_elems()
+        starts, numel, offs, c, off = [], [], [], 0, 0
+        for t in lists[0]:
+            starts.append(c)
+            numel.append(t.numel())
+            offs.append(off)
+            c += -(-t.numel() // chunk)
+            off += (t.numel() + 3) // 4 * 4
+        self.total, self.n_chunks, self.n = off, c, n
+        self.key = tuple(t.data_ptr() for l in lists for t in l)
+        self._keep = [torch.tensor(starts, dtype=torch.int32, device=dev), torch.tensor(numel, dtype=torch.int64, device=dev),
+                      torch.tensor(offs, dtype=torch.int64, device=dev)]
+        for l in lists:
+            for t in l:
+                if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                    raise TypeError("optimiser kernels need contiguous fp32 CUDA tensors")
+            self._keep.append(torch.tensor([t.data_ptr() for t in l], dtype=torch.int64, device=dev))
+        tb = MstTensorTable()
+        tb.chunk_start, tb.numel, tb.flat_offset = (k.data_ptr() for k in self._keep[:3])
+        ptrs = [k.data_ptr() for k in self._keep[3:]] + [None] * 4
+        tb.a, tb.b, tb.c, tb.d = ptrs[:4]
+        tb.n_tensors, tb.n_chunks = n, c
+        self.tb = tb
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (lr, betas, eps, weight_decay; no amsgrad) in one kernel launch per step.
+    Mirrors how the reference builds its optimisers (train_only_inner_loop.py:468-478): pass the parameters."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.step_count = 0
+        self._table: Optional[_Table] = None
+
+    def zero_grad(self, set_to_none: bool = False):
+        for p in self.params:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        grads = []
+        for p in self.params:
+            if p.grad is None:
+                raise RuntimeError("FusedAdam.step: every parameter needs a gradient (the kernel updates all tensors in one launch)")
+            grads.append(p.grad.contiguous())
+        lists = [[p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq]
+        key = tuple(t.data_ptr() for l in lists for t in l)
+        if self._table is None or self._table.key != key:
+            self._table = _Table(lists)
+        self.step_count += 1
+        n = sum(p.numel() for p in self.params)
+        ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step(C.byref(self._table.tb), float(self.lr), float(self.betas[0]),
+                                                                     float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                                                                     int(self.step_count), ops._stream()), nbytes=28.0 * n)
+        _bump_versions(self.params)
+
+
+@torch.no_grad()
+def reptile_update(theta: torch.nn.Module, omega: torch.nn.Module, outer_lr: float, group=None) -> None:
+    """theta += outer_lr * mean_over_ranks(omega - theta)  (train.py:524-534 when there is a single rank).
+
+    With torch.distributed initialised, each rank holds an omega trained on its own style task; the flat delta
+    buffer is all-reduced (NCCL on GPUs) and every rank applies the same averaged update."""
+    tp = [p for _, p in theta.named_parameters()]
+    op = [p for _, p in omega.named_parameters()]
+    if len(tp) != len(op) or any(a.shape != b.shape for a, b in zip(tp, op)):
+        raise ValueError("theta and omega must have identical parameter lists")
+    table = _Table([[p.data for p in tp], [p.data for p in op]])
+    flat = torch.empty(table.total, dtype=torch.float32, device=tp[0].device)
+    n = sum(p.numel() for p in tp)
+    ops._launch("mst_reptile_delta", lambda: _lib.lib().mst_reptile_delta(C.byref(table.tb), flat.data_ptr(), ops._stream()), nbytes=12.0 * n)
+    world = 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    ops._launch("mst_reptile_apply", lambda: _lib.lib().mst_reptile_apply(C.byref(table.tb), flat.data_ptr(), float(outer_lr) / world,
+                                                                         ops._stream()), nbytes=12.0 * n)
+    _bump_versions(tp)

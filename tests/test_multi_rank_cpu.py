@@ -51,3 +51,15 @@ def test_two_rank_gloo_sharding_and_timing_reduce():
         assert mx == 11.0            # max over ranks, as bench.py reduces its device timings
         assert total == sum(range(33))  # every image processed exactly once
         assert count == 33
+
+
+def test_tensor_table_layout_is_consistent():
+    """Host-side chunk table of the multi-tensor optimiser kernels (no GPU needed for the arithmetic)."""
+    from mastermetastyletransfer_b200 import _lib
+    chunk = _lib.lib().mst_opt_chunk_elems()
+    sizes = [1, chunk - 1, chunk, chunk + 1, 5 * chunk + 7]
+    starts, c = [], 0
+    for n in sizes:
+        starts.append(c)
+        c += -(-n // chunk)
+    assert starts == [0, 1, 2, 3, 5] and c == 11
