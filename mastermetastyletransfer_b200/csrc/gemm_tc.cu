@@ -43,14 +43,22 @@ MST_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+// res_stages == 0: streaming mode -- every stage carries an A k-block and the matching weight k-block.
+// res_stages  > 0: weight-resident mode (the CTA's [BN x k_pad] weight slab fits in shared memory): the slab is
+//                  fetched once, the CTA keeps one n-tile and walks m-tiles, and the ring (res_stages deep) carries only
+//                  A k-blocks.  Cuts the L2 traffic of the K<=256 projections by the weight re-reads, which
+//                  otherwise exceed the activation traffic (ncu: lts__t_bytes ~3.6x the algorithmic bytes).
+constexpr int MAX_STAGES = 8;
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm p, const int num_tiles) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm p, const int num_tiles, const int res_stages) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const bool resident = res_stages > 0;
+  const int STAGES = resident ? res_stages : Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[STAGES];
-  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t full_bar[MAX_STAGES];
+  __shared__ uint64_t empty_bar[MAX_STAGES];
+  __shared__ uint64_t b_full_bar;
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -62,12 +70,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
 
   const int n_tiles = p.N / BN;
   const int nkb = p.k_pad / BK;
+  // tile schedule (identical in every role), advanced without divisions inside the loops
+  const int m_tiles = num_tiles / n_tiles;
+  const int g_q = gridDim.x / n_tiles, g_r = gridDim.x % n_tiles;
+  struct TileIter {
+    int n_tile, m_tile;
+  };
+  auto tile_begin = [&]() { return TileIter{(int)(blockIdx.x % n_tiles), (int)(blockIdx.x / n_tiles)}; };
+  auto tile_next = [&](TileIter& t) {  // streaming: tile index += gridDim.x ; resident: same n-tile, m += gridDim.x / n_tiles
+    t.m_tile += g_q;
+    if (!resident) {
+      t.n_tile += g_r;
+      if (t.n_tile >= n_tiles) { t.n_tile -= n_tiles; ++t.m_tile; }
+    }
+  };
+  const int res_nt = blockIdx.x % n_tiles;
+  // shared-memory carve-up: [resident weight slab (nkb k-blocks)] [ring of stages]
+  const uint32_t ring_base = smem_base + (resident ? nkb * Cfg::B_STAGE_BYTES : 0);
+  const uint32_t stage_bytes = resident ? A_STAGE_BYTES : Cfg::STAGE_BYTES;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), NUM_PROD_WARPS * 32 + 1);
+      mbar_init(smem_u32(&full_bar[s]), NUM_PROD_WARPS * 32 + (resident ? 0 : 1));
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
+    mbar_init(smem_u32(&b_full_bar), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full_bar[b]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[b]), NUM_EPI_WARPS);
@@ -97,10 +124,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
     const bool conv = p.a_mode != MST_A_PLAIN;
-    int it = 0;  // running k-block counter across tiles (pipeline position)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % n_tiles;
-      const int m0 = (tile / n_tiles) * BM;
+    if (resident && t == 0) {  // the CTA's whole weight slab, once
+      mbar_arrive_expect_tx(smem_u32(&b_full_bar), nkb * Cfg::B_STAGE_BYTES);
+      const uint8_t* wslab = Wbase + (size_t)res_nt * nkb * Cfg::B_STAGE_BYTES;
+      for (int kb = 0; kb < nkb; ++kb)
+        bulk_g2s(smem_base + kb * Cfg::B_STAGE_BYTES, wslab + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&b_full_bar));
+    }
+    int stage = 0;
+    uint32_t pphase = 1;  // producer's view of empty_bar: a fresh barrier passes a wait on parity 1
+    for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt)) {
+      const int n_tile = tt.n_tile, m0 = tt.m_tile * BM;
       // Per-row source bookkeeping, computed once per tile.
       //   PLAIN: rowp = &A[m*lda].   CONV: rowp = image base; yo/xo = element offsets of the three source rows /
       //   columns a 3x3 tap can touch (reflect or zero padding and the nearest-x2 upsample already applied),
@@ -148,11 +181,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
       const uint8_t* wtile = Wbase + (size_t)n_tile * nkb * Cfg::B_STAGE_BYTES;
       int tap = 0, ch = c * 8;  // conv: this thread's (tap, channel) for k0 = kb*64 + c*8, advanced without divisions
       while (conv && ch >= p.Cin) { ch -= p.Cin; ++tap; }
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        if (it >= STAGES) mbar_wait(smem_u32(&empty_bar[s]), ((it / STAGES) - 1) & 1);
-        const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
-        if (t == 0) {  // weight tile: one bulk copy of the pre-swizzled [BN x 64] block
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = stage;
+        mbar_wait(smem_u32(&empty_bar[s]), pphase);
+        if (++stage == STAGES) { stage = 0; pphase ^= 1; }
+        const uint32_t a_stage = ring_base + s * stage_bytes;
+        if (!resident && t == 0) {  // weight tile: one bulk copy of the pre-swizzled [BN x 64] block
           mbar_arrive_expect_tx(smem_u32(&full_bar[s]), Cfg::B_STAGE_BYTES);
           bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
         }
@@ -186,19 +220,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
   } else if (warp == NUM_EPI_WARPS + NUM_PROD_WARPS) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-    int it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    int tcount = 0, stage = 0;
+    uint32_t cphase = 0;
+    if (resident) mbar_wait(smem_u32(&b_full_bar), 0);
+    for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt), ++tcount) {
       const int buf = tcount & 1;
       mbar_wait(smem_u32(&tmem_empty_bar[buf]), ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(smem_u32(&full_bar[s]), (it / STAGES) & 1);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = stage;
+        mbar_wait(smem_u32(&full_bar[s]), cphase);
+        if (++stage == STAGES) { stage = 0; cphase ^= 1; }
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
-          const uint32_t b_stage = a_stage + A_STAGE_BYTES;
+          const uint32_t a_stage = ring_base + s * stage_bytes;
+          const uint32_t b_stage = resident ? smem_base + kb * Cfg::B_STAGE_BYTES : a_stage + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
@@ -219,10 +256,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
     const int half = warp >> 2;
     const bool active = half < Cfg::EPI_SPLIT;
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt), ++tcount) {
+      const int n_tile = tt.n_tile, m0 = tt.m_tile * BM;
       const int buf = tcount & 1;
-      const int n_tile = tile % n_tiles;
-      const int m0 = (tile / n_tiles) * BM;
       if (lane == 0) mbar_wait(smem_u32(&tmem_full_bar[buf]), (tcount >> 1) & 1);  // one poller per warp
       __syncwarp();
       tc_fence_after();
@@ -320,9 +356,10 @@ static int g_num_sms = 0;
 template <int BN>
 static int launch_gemm(const MstGemm& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
+  constexpr int MAX_SMEM = 222 * 1024;  // + ~4.3 KB static (bias, barriers) <= 227 KB
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -332,10 +369,29 @@ static int launch_gemm(const MstGemm& g, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  const long long tiles = (long long)((g.M + BM - 1) / BM) * (g.N / BN);
+  const int n_tiles = g.N / BN;
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const long long tiles = (long long)m_tiles * n_tiles;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return MST_ERR_BAD_ARG;
-  const unsigned grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(g, (int)tiles);
+  // weight-resident mode when the [BN x k_pad] slab leaves room for >= 3 A stages and there are enough m-tiles to amortise it
+  const long long slab = (long long)(g.k_pad / BK) * Cfg::B_STAGE_BYTES;
+  int res_stages = 0;
+  if (slab + 3 * A_STAGE_BYTES + 1024 <= MAX_SMEM && n_tiles <= g_num_sms && m_tiles >= 2 * (g_num_sms / n_tiles)) {
+    res_stages = (int)((MAX_SMEM - 1024 - slab) / A_STAGE_BYTES);
+    if (res_stages > MAX_STAGES) res_stages = MAX_STAGES;
+  }
+  unsigned grid;
+  size_t smem;
+  if (res_stages > 0) {
+    long long gsz = (long long)(g_num_sms / n_tiles) * n_tiles;
+    if (gsz > tiles) gsz = tiles;
+    grid = (unsigned)gsz;
+    smem = 1024 + (size_t)slab + (size_t)res_stages * A_STAGE_BYTES;
+  } else {
+    grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
+    smem = Cfg::SMEM_BYTES;
+  }
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(g, (int)tiles, res_stages);
   return (int)cudaGetLastError();
 }
 
