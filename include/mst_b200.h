@@ -59,6 +59,7 @@ int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n
  * ------------------------------------------------------------------------------------------ */
 enum { MST_A_PLAIN = 0, MST_A_CONV3X3 = 1 };
 enum { MST_ACT_NONE = 0, MST_ACT_RELU = 1, MST_ACT_GELU = 2 };
+enum { MST_GATE_NONE = 0, MST_GATE_RELU = 1, MST_GATE_GELU = 2 };
 
 typedef struct MstGemm {
   const mst_bf16* A; /* bf16 activations */
@@ -75,6 +76,18 @@ typedef struct MstGemm {
   int H, W, Cin, pad_mode, upsample; /* MST_A_CONV3X3 geometry (H,W = output = padded-input size) */
   int out_nchw;       /* 1: out_f32 is [B, n_real, H, W] (final decoder conv, decoder.py:54) */
   int n_real;         /* channels actually stored when out_nchw (<= N) */
+  /* ---- training-step extensions (all optional; zero = the inference behaviour above) ----
+   * epilogue order:  x = acc + bias;  out_pre16 <- x;  x = act(x);  gate;  x += add16;  x *= row_scale[m / rows_per_scale];
+   *                  res / mul;  stores.
+   * gate_mode MST_GATE_RELU: x = gate[m,n] > 0 ? x : 0      (ReLU backward: gate = the forward output)
+   *           MST_GATE_GELU: x *= GELU'(gate[m,n])          (GELU backward: gate = the forward pre-activation)
+   * conv_full = 1 (MST_A_CONV3X3, zero padding): "full" correlation used for the data gradient of a reflect-padded conv:
+   *   H, W are the OUTPUT grid, the stored input is [B, H-2, W-2, Cin] and tap (ky,kx) reads in[y+ky-2, x+kx-2]. */
+  const mst_bf16* gate;  /* bf16 [M, ld_gate] or NULL */
+  const mst_bf16* add16; /* bf16 [M, ld_gate] or NULL */
+  mst_bf16* out_pre16;   /* bf16 [M, ld_out16] or NULL: pre-activation copy kept for the backward pass */
+  const float* row_scale; /* fp32 [ceil(M / rows_per_scale)] or NULL: per-sample stochastic-depth factor (tv StochasticDepth "row") */
+  int gate_mode, ld_gate, rows_per_scale, conv_full;
 } MstGemm;
 
 int mst_gemm(const MstGemm* g, void* stream);
@@ -216,6 +229,81 @@ int mst_adam_step(const MstTensorTable* tb, float lr, float beta1, float beta2, 
                   void* stream);
 int mst_reptile_delta(const MstTensorTable* tb, float* flat, void* stream);
 int mst_reptile_apply(const MstTensorTable* tb, float* flat, float scale, void* stream);
+
+/* ==========================================================================================
+ * Backward kernels of the training step (train.py:515-517 loss.backward()).
+ * The reference differentiates with autograd; each entry point cites the forward it is the adjoint of.
+ * Data gradients of nn.Linear / Conv2d reuse mst_gemm with transposed (flipped) packed weights.
+ * ========================================================================================== */
+
+/* Weight gradient:  dW[n,k'] += sum_m dY[m,n] * X(m,k')  (fp32 atomics: shared weights accumulate over their uses).
+ * x_mode MST_A_PLAIN: nn.Linear, dW is [N,K] row-major.  MST_A_CONV3X3: Conv2d 3x3, dW is [N,Cin,3,3], X is the
+ * conv INPUT image [B,Hs,Ws,Cin] with the same pad_mode / upsample meaning as MstGemm.  n_real (0 = N) limits the
+ * dW rows written (a 3-channel dY is stored padded to 8 channels). */
+typedef struct MstWgrad {
+  const mst_bf16* dY; /* bf16 [M, ld_dy] */
+  const mst_bf16* X;  /* bf16 [M, ld_x] or conv input image */
+  float* dW;
+  int M, N, K;        /* K = X channels (linear) or 9*Cin (conv) */
+  int ld_dy, ld_x, x_mode;
+  int H, W, Cin, pad_mode, upsample;
+  int n_real;
+} MstWgrad;
+int mst_wgrad(const MstWgrad* g, void* stream);
+/* bias gradient: out[n] += sum_m dY[m,n] */
+int mst_colsum(const mst_bf16* dY, int M, int N, int ld, float* out, void* stream);
+
+/* Adjoint of mst_window_attention (8x8 windows, no padding): recomputes the probabilities from q,k and returns
+ * dq (already multiplied by head_dim^-0.5), dk, dv (dv2) in the token-major layout of their forward tensors, and
+ * accumulates the relative-position-bias-table gradient (+=).  dout2/v2/dv2 set = the shared-softmax sigma/mu core. */
+typedef struct MstWindowAttnBwd {
+  const mst_bf16 *q, *k, *v, *v2;
+  const mst_bf16 *dout, *dout2;
+  mst_bf16 *dq, *dk, *dv, *dv2;
+  const float* bias_table;
+  float* dbias_table; /* [(2ws-1)^2, heads] fp32, += */
+  int B, H, W, heads, ws, shift;
+  int ldq, ldk, ldv, ldo, lddq, lddk, lddv;
+} MstWindowAttnBwd;
+int mst_window_attention_bwd(const MstWindowAttnBwd* a, void* stream);
+
+/* LayerNorm backward: dx_accum[r,:] += d/dx of LN(x)[r,:] . dy[r,:];  dgamma += sum_r dy*xhat;  dbeta += sum_r dy.
+ * x fp32 (the forward input; statistics are recomputed), dy bf16. */
+int mst_layernorm_bwd(const float* x, const float* gamma, const mst_bf16* dy, float* dx_accum, float* dgamma, float* dbeta,
+                      int rows, int C, void* stream);
+/* InstanceNorm2d(affine=False) backward over T for x [B,T,C] fp32 (twice=1: adjoint of IN(IN(x)), the double
+ * normalisation of the decoder query).  Step 1 reduces per (b,c): coef[b,c,0..2] such that
+ * dx = coef0*(dy - coef1) + coef2*(x - mean); step 2 applies it: dx_accum += dx (fp32) and/or dx16 = dx. */
+int mst_instnorm_bwd_stats(const float* x, const void* dy, int dy_is_f32, float* coef /* [B,C,4] */, int B, int T, int C, int twice,
+                           void* stream);
+int mst_instnorm_bwd_apply(const float* x, const void* dy, int dy_is_f32, const float* coef, float* dx_accum, mst_bf16* dx16,
+                           int B, int T, int C, void* stream);
+/* y = query*sigma + mu (style_transformer.py:1123):  gquery = gy*sigma (fp32), gsigma16 = gy*query, gmu16 = gy (bf16) */
+int mst_blend_bwd(const float* gy, const float* sigma, const float* query, float* gquery, mst_bf16* gsigma16, mst_bf16* gmu16,
+                  size_t n, void* stream);
+/* out[i] = a[i] (+ b[i]) -> fp32 and/or bf16 (gradient-stream bookkeeping) */
+int mst_add_cast(const float* a, const float* b, float* out32, mst_bf16* out16, size_t n, void* stream);
+
+/* Reflect-pad fold (adjoint of F.pad(mode='reflect') + optional nn.Upsample(2,'nearest'), decoder.py:24-27):
+ * dxp bf16 [B,H+2,W+2,C] (the conv_full data gradient on the padded grid) -> dx bf16 [B,H,W,C], or [B,H/2,W/2,C]
+ * summing 2x2 blocks when upsample=1; gate (bf16, shape of dx) applies the previous ReLU's mask (gate > 0). */
+int mst_reflect_fold(const mst_bf16* dxp, const mst_bf16* gate, mst_bf16* dx, int B, int H, int W, int C, int upsample, void* stream);
+/* MaxPool2d(2) backward fused with the preceding ReLU's mask: dx[b,y,x,c] = dy[b,y/2,x/2,c] if x is the (first) maximum
+ * of its 2x2 block and > 0, else 0.  x bf16 [B,H,W,C] = pool input. */
+int mst_maxpool2x2_bwd(const mst_bf16* x, const mst_bf16* dy, mst_bf16* dx, int B, int H, int W, int C, void* stream);
+/* fp32 NCHW [B,3,H,W] gradient image -> bf16 NHWC [B,H,W,8] (channels 3..7 zero) */
+int mst_nchw3_to_nhwc8(const float* g, mst_bf16* out, int B, int H, int W, void* stream);
+
+/* Loss backward (adjoint of mst_content_term + mst_loss_finalize for the OUTPUT image's taps, loss.py:110-130).
+ * mst_loss_bwd_stats: per (b,c) sums s[b,c,0] = sum_t g, s[b,c,1] = sum_t g*n_o with g = -phi'(IN(Fc)-IN(Fo)).
+ * mst_loss_bwd_apply: dFo = w_c/(B*T*C) * rstd_o*(g - s0/T - n_o*s1/T) + w_s/(B*C) * (-psi'(dmu)/T - psi'(dstd)*(Fo-mu_o)/((T-1)*std_o)),
+ *   masked by Fo > 0 (the tap is a ReLU output), bf16.  w = {w_content, w_style} is a DEVICE float[2]
+ *   (= {g_total + g_content, lambda*g_total + g_style} of the incoming gradient). */
+int mst_loss_bwd_stats(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
+                       const float* var_o, int B, int T, int C, int squared, float* s, void* stream);
+int mst_loss_bwd_apply(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
+                       const float* var_o, const float* mean_s, const float* var_s, const float* s, const float* w, int B, int T,
+                       int C, int squared_content, int squared_style, mst_bf16* dfo, void* stream);
 
 #ifdef __cplusplus
 }

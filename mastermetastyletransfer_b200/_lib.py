@@ -24,6 +24,30 @@ class MstGemm(C.Structure):
         ("a_mode", C.c_int), ("act", C.c_int),
         ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("pad_mode", C.c_int), ("upsample", C.c_int),
         ("out_nchw", C.c_int), ("n_real", C.c_int),
+        ("gate", C.c_void_p), ("add16", C.c_void_p), ("out_pre16", C.c_void_p), ("row_scale", C.c_void_p),
+        ("gate_mode", C.c_int), ("ld_gate", C.c_int), ("rows_per_scale", C.c_int), ("conv_full", C.c_int),
+    ]
+
+
+class MstWgrad(C.Structure):
+    _fields_ = [
+        ("dY", C.c_void_p), ("X", C.c_void_p), ("dW", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("ld_dy", C.c_int), ("ld_x", C.c_int), ("x_mode", C.c_int),
+        ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("pad_mode", C.c_int), ("upsample", C.c_int),
+        ("n_real", C.c_int),
+    ]
+
+
+class MstWindowAttnBwd(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("v2", C.c_void_p),
+        ("dout", C.c_void_p), ("dout2", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("dv2", C.c_void_p),
+        ("bias_table", C.c_void_p), ("dbias_table", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("heads", C.c_int), ("ws", C.c_int), ("shift", C.c_int),
+        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
+        ("lddq", C.c_int), ("lddk", C.c_int), ("lddv", C.c_int),
     ]
 
 
@@ -89,6 +113,19 @@ SYMBOLS = {
     "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mst_content_term": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "mst_loss_finalize": (_I, [C.POINTER(MstLossTaps), C.c_float, _I, _P, _P]),
+    "mst_wgrad": (_I, [C.POINTER(MstWgrad), _P]),
+    "mst_colsum": (_I, [_P, _I, _I, _I, _P, _P]),
+    "mst_window_attention_bwd": (_I, [C.POINTER(MstWindowAttnBwd), _P]),
+    "mst_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mst_instnorm_bwd_stats": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "mst_instnorm_bwd_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
+    "mst_blend_bwd": (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
+    "mst_add_cast": (_I, [_P, _P, _P, _P, _Z, _P]),
+    "mst_reflect_fold": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mst_maxpool2x2_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mst_nchw3_to_nhwc8": (_I, [_P, _P, _I, _I, _I, _P]),
+    "mst_loss_bwd_stats": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "mst_loss_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

@@ -199,6 +199,20 @@ MST_DEVINL float gelu_erf(float x) {
   return 0.5f * x * (1.0f + er);
 }
 
+// d/dx of the exact GELU: Phi(x) + x*phi(x), same erf approximation (e = exp(-x^2/2) is shared by both terms)
+MST_DEVINL float gelu_erf_grad(float x) {
+  const float z = x * 0.70710678118654752440f, az = fabsf(z);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-az * az * 1.4426950408889634f));
+  const float er = copysignf(fmaf(-p * t, e, 1.0f), z);
+  return fmaf(x * 0.3989422804014327f, e, 0.5f * (1.0f + er));
+}
+
 MST_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
     const int t = threadIdx.x - NUM_EPI_WARPS * 32;
     const int c = t & 7;    // 16-byte chunk column inside the 128-byte k-slab
     const int r0 = t >> 3;  // first of this thread's rows; rows r0 + RSTEP*i
-    const int Hs = p.upsample ? (p.H >> 1) : p.H;
-    const int Ws = p.upsample ? (p.W >> 1) : p.W;
+    const int Hs = p.conv_full ? p.H - 2 : (p.upsample ? (p.H >> 1) : p.H);  // stored input grid
+    const int Ws = p.conv_full ? p.W - 2 : (p.upsample ? (p.W >> 1) : p.W);
+    const int tap_off = p.conv_full ? 2 : 1;
     const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*RSTEP*128 for row r0+RSTEP*i (whole 8-row groups further)
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
@@ -161,14 +162,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
             rowp[i] = Abase + (long long)b * Hs * Ws * p.Cin;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              int yy = y + j - 1, xx = x + j - 1;
+              int yy = y + j - tap_off, xx = x + j - tap_off;
               bool vy = true, vx = true;
               if (p.pad_mode == 1) {  // reflect (no edge repeat): -1 -> 1, H -> H-2
                 yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
                 xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
-              } else {
-                vy = (unsigned)yy < (unsigned)p.H;
-                vx = (unsigned)xx < (unsigned)p.W;
+              } else {  // zeros; conv_full: the input grid is (H-2) x (W-2)
+                vy = (unsigned)yy < (unsigned)(p.conv_full ? Hs : p.H);
+                vx = (unsigned)xx < (unsigned)(p.conv_full ? Ws : p.W);
               }
               if (p.upsample) { yy >>= 1; xx >>= 1; }
               yo[i][j] = vy ? yy * Ws * p.Cin : 0;
@@ -289,10 +290,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
           const int n = nbase + col0;
           float x[CH];
 #pragma unroll
+          for (int j = 0; j < CH; ++j) x[j] = __uint_as_float(v[j]) + bias_s[n + j];
+          if (p.out_pre16) {  // pre-activation copy for the backward pass
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_pre16) + (long long)row * p.ld_out16 + n);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+#pragma unroll
           for (int j = 0; j < CH; ++j) {
-            x[j] = __uint_as_float(v[j]) + bias_s[n + j];
             if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
             else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
+          }
+          if (p.gate_mode != MST_GATE_NONE) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + (long long)row * p.ld_gate + n);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              const uint4 gv = g4[j];
+              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float g0 = __uint_as_float(gw[e] << 16), g1 = __uint_as_float(gw[e] & 0xffff0000u);
+                if (p.gate_mode == MST_GATE_RELU) {
+                  x[8 * j + 2 * e] = g0 > 0.f ? x[8 * j + 2 * e] : 0.f;
+                  x[8 * j + 2 * e + 1] = g1 > 0.f ? x[8 * j + 2 * e + 1] : 0.f;
+                } else {
+                  x[8 * j + 2 * e] *= gelu_erf_grad(g0);
+                  x[8 * j + 2 * e + 1] *= gelu_erf_grad(g1);
+                }
+              }
+            }
+          }
+          if (p.add16) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.add16) + (long long)row * p.ld_gate + n);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              const uint4 av = a4[j];
+              const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[8 * j + 2 * e] += __uint_as_float(aw[e] << 16);
+                x[8 * j + 2 * e + 1] += __uint_as_float(aw[e] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.row_scale) {
+            const float rs = p.row_scale[row / p.rows_per_scale];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) x[j] *= rs;
           }
           if (p.res) {
             const float4* r4 = reinterpret_cast<const float4*>(p.res + (long long)row * p.ld_res + n);
@@ -457,8 +509,14 @@ extern "C" int mst_gemm(const MstGemm* g, void* stream) {
   if (!g || !g->A || !g->Wt) return MST_ERR_BAD_ARG;
   if (g->M <= 0 || g->N <= 0 || g->K <= 0 || g->k_pad % BK != 0 || g->k_pad < g->K) return MST_ERR_BAD_ARG;
   if (g->N % 16 != 0 || g->K % 8 != 0 || g->N > MAX_BIAS) return MST_ERR_UNSUPPORTED;
-  if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
+  if (!g->out_f32 && !g->out_bf16 && !g->out_pre16) return MST_ERR_BAD_ARG;
   if (g->mul && !g->res) return MST_ERR_BAD_ARG;
+  if ((g->gate_mode != MST_GATE_NONE) != (g->gate != nullptr) || g->gate_mode < 0 || g->gate_mode > MST_GATE_GELU) return MST_ERR_BAD_ARG;
+  if ((g->gate || g->add16) && g->ld_gate % 8 != 0) return MST_ERR_BAD_ARG;
+  if (g->row_scale && g->rows_per_scale <= 0) return MST_ERR_BAD_ARG;
+  if (g->out_pre16 && (g->ld_out16 % 8 != 0 || g->out_nchw)) return MST_ERR_BAD_ARG;
+  if (g->out_nchw && (g->gate || g->add16 || g->row_scale)) return MST_ERR_BAD_ARG;
+  if (g->conv_full && (g->a_mode != MST_A_CONV3X3 || g->pad_mode != 0 || g->upsample || g->H < 3 || g->W < 3)) return MST_ERR_BAD_ARG;
   if (g->a_mode == MST_A_PLAIN) {
     if (g->lda % 8 != 0 || g->lda < g->K) return MST_ERR_BAD_ARG;
   } else if (g->a_mode == MST_A_CONV3X3) {

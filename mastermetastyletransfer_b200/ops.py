@@ -11,9 +11,10 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MstGemm, MstLossTap, MstLossTaps, MstMlp, MstWindowAttn, check
+from ._lib import MstGemm, MstLossTap, MstLossTaps, MstMlp, MstWgrad, MstWindowAttn, MstWindowAttnBwd, check
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+GATE_NONE, GATE_RELU, GATE_GELU = 0, 1, 2
 A_PLAIN, A_CONV3X3 = 0, 1
 PAD_ZERO, PAD_REFLECT = 0, 1
 
@@ -57,7 +58,12 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
-             "mst_loss_finalize": "loss_finalize_kernel"}
+             "mst_loss_finalize": "loss_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
+             "mst_window_attention_bwd": "window_attn_bwd_kernel", "mst_layernorm_bwd": "layernorm_bwd_kernel",
+             "mst_instnorm_bwd_stats": "instnorm_bwd_stats_kernel", "mst_instnorm_bwd_apply": "instnorm_bwd_apply_kernel",
+             "mst_blend_bwd": "blend_bwd_kernel", "mst_add_cast": "add_cast_kernel", "mst_reflect_fold": "reflect_fold_kernel",
+             "mst_maxpool2x2_bwd": "maxpool2x2_bwd_kernel", "mst_nchw3_to_nhwc8": "nchw3_to_nhwc8_kernel",
+             "mst_loss_bwd_stats": "loss_bwd_stats_kernel", "mst_loss_bwd_apply": "loss_bwd_apply_kernel"}
 
 
 def _stream() -> int:
@@ -125,7 +131,9 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
          res: Optional[torch.Tensor] = None, mul: Optional[torch.Tensor] = None,
          out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
          ld_out32: Optional[int] = None, ld_out16: Optional[int] = None, ld_res: Optional[int] = None,
-         conv: Optional[dict] = None) -> None:
+         conv: Optional[dict] = None, gate: Optional[torch.Tensor] = None, gate_mode: int = GATE_NONE,
+         add16: Optional[torch.Tensor] = None, ld_gate: Optional[int] = None, out_pre16: Optional[torch.Tensor] = None,
+         row_scale: Optional[torch.Tensor] = None, rows_per_scale: int = 0) -> None:
     """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h)."""
     g = MstGemm()
     g.A = _ptr(A, torch.bfloat16, "A")
@@ -142,6 +150,11 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
     g.ld_out32 = N if ld_out32 is None else ld_out32
     g.ld_out16 = N if ld_out16 is None else ld_out16
     g.act = act
+    g.gate, g.add16 = _ptr(gate, torch.bfloat16, "gate"), _ptr(add16, torch.bfloat16, "add16")
+    g.out_pre16 = _ptr(out_pre16, torch.bfloat16, "out_pre16")
+    g.row_scale, g.rows_per_scale = _ptr(row_scale, torch.float32, "row_scale"), rows_per_scale
+    g.gate_mode, g.ld_gate = gate_mode, (N if ld_gate is None else ld_gate)
+    training_ext = gate is not None or add16 is not None or out_pre16 is not None or row_scale is not None
     if conv is None:
         g.a_mode = A_PLAIN
     else:
@@ -149,9 +162,11 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
         g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
         g.out_nchw, g.n_real = int(conv.get("out_nchw", False)), conv.get("n_real", pm.N)
+        g.conv_full = int(conv.get("full", False))
+        training_ext = training_ext or bool(g.conv_full)
     desc = f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}"
     flops = 2.0 * M * min(N, pm.N) * pm.K
-    if conv is not None and _use_band(conv, N):
+    if conv is not None and not training_ext and _use_band(conv, N):
         _launch("mst_conv3x3_band", lambda: _lib.lib().mst_conv3x3_band(C.byref(g), _stream()), flops=flops, desc=desc + " band")
     else:
         _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=flops, desc=desc)
@@ -314,3 +329,107 @@ def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out
     g.ld_res = g.ld_out32 = g.ld_out16 = pm.C
     _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=16.0 * M * pm.C * pm.C,
             desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}")
+
+
+# --------------------------------------------------------------------------------------------
+# training step: backward kernels (include/mst_b200.h, "Backward kernels of the training step")
+# --------------------------------------------------------------------------------------------
+
+
+def wgrad(dY, X, dW, M, N, K, *, ld_dy=None, ld_x=None, conv: Optional[dict] = None, n_real: int = 0) -> None:
+    """dW[n,k'] += sum_m dY[m,n] * X(m,k'); conv = dict(H, W, Cin, pad_mode, upsample) for a 3x3 Conv2d weight."""
+    g = MstWgrad()
+    g.dY, g.X, g.dW = _ptr(dY, torch.bfloat16, "dY"), _ptr(X, torch.bfloat16, "X"), _ptr(dW, torch.float32, "dW")
+    g.M, g.N, g.K = M, N, K
+    g.ld_dy = N if ld_dy is None else ld_dy
+    g.n_real = n_real
+    if conv is None:
+        g.x_mode, g.ld_x = A_PLAIN, (K if ld_x is None else ld_x)
+    else:
+        g.x_mode, g.ld_x = A_CONV3X3, 0
+        g.H, g.W, g.Cin = conv["H"], conv["W"], conv["Cin"]
+        g.pad_mode, g.upsample = conv.get("pad_mode", PAD_ZERO), int(conv.get("upsample", False))
+    _launch("mst_wgrad", lambda: _lib.lib().mst_wgrad(C.byref(g), _stream()), flops=2.0 * M * (n_real or N) * K,
+            desc=f"wgrad M={M} N={N} K={K} conv={conv is not None}")
+
+
+def colsum(dY, M, N, out, ld=None) -> None:
+    _launch("mst_colsum", lambda: _lib.lib().mst_colsum(_ptr(dY, torch.bfloat16, "dY"), M, N, N if ld is None else ld,
+                                                        _ptr(out, torch.float32, "out"), _stream()), nbytes=2.0 * M * N)
+
+
+def window_attention_bwd(q, k, v, dout, dq, dk, dv, bias_table, dbias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
+                         lddq, lddk, lddv, v2=None, dout2=None, dv2=None) -> None:
+    a = MstWindowAttnBwd()
+    a.q, a.k, a.v, a.v2 = _ptr(q, torch.bfloat16, "q"), _ptr(k, torch.bfloat16, "k"), _ptr(v, torch.bfloat16, "v"), _ptr(v2, torch.bfloat16, "v2")
+    a.dout, a.dout2 = _ptr(dout, torch.bfloat16, "dout"), _ptr(dout2, torch.bfloat16, "dout2")
+    a.dq, a.dk, a.dv, a.dv2 = _ptr(dq, torch.bfloat16, "dq"), _ptr(dk, torch.bfloat16, "dk"), _ptr(dv, torch.bfloat16, "dv"), _ptr(dv2, torch.bfloat16, "dv2")
+    a.bias_table, a.dbias_table = _ptr(bias_table, torch.float32, "bias_table"), _ptr(dbias_table, torch.float32, "dbias_table")
+    a.B, a.H, a.W, a.heads, a.ws, a.shift = B, H, W, heads, ws, shift
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddq, a.lddk, a.lddv = ldq, ldk, ldv, ldo, lddq, lddk, lddv
+    n_win = B * (H // ws) * (W // ws)
+    _launch("mst_window_attention_bwd", lambda: _lib.lib().mst_window_attention_bwd(C.byref(a), _stream()),
+            flops=2.0 * n_win * heads * 64 * 64 * 32 * (9 if v2 is not None else 7), desc=f"B={B} H={H} dual={v2 is not None}")
+
+
+def layernorm_bwd(x, gamma, dy, dx_accum, dgamma, dbeta, rows, Cdim) -> None:
+    _launch("mst_layernorm_bwd", lambda: _lib.lib().mst_layernorm_bwd(
+        _ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"), _ptr(dy, torch.bfloat16, "dy"), _ptr(dx_accum, torch.float32, "dx_accum"),
+        _ptr(dgamma, torch.float32, "dgamma"), _ptr(dbeta, torch.float32, "dbeta"), rows, Cdim, _stream()), nbytes=14.0 * rows * Cdim)
+
+
+def instnorm_bwd(x, dy, coef, B, T, Cdim, *, twice=False, dx_accum=None, dx16=None) -> None:
+    """InstanceNorm2d(affine=False) adjoint (two launches: per-(b,c) coefficients, then the elementwise apply)."""
+    f32 = dy.dtype == torch.float32
+    if not f32 and dy.dtype != torch.bfloat16:
+        raise TypeError("instnorm_bwd: dy must be fp32 or bf16")
+    _launch("mst_instnorm_bwd_stats", lambda: _lib.lib().mst_instnorm_bwd_stats(
+        _ptr(x, torch.float32, "x"), _ptr(dy), int(f32), _ptr(coef, torch.float32, "coef"), B, T, Cdim, int(twice), _stream()),
+        nbytes=(8.0 if f32 else 6.0) * B * T * Cdim + 4.0 * B * T * Cdim)
+    _launch("mst_instnorm_bwd_apply", lambda: _lib.lib().mst_instnorm_bwd_apply(
+        _ptr(x, torch.float32, "x"), _ptr(dy), int(f32), _ptr(coef, torch.float32, "coef"), _ptr(dx_accum, torch.float32, "dx_accum"),
+        _ptr(dx16, torch.bfloat16, "dx16"), B, T, Cdim, _stream()), nbytes=12.0 * B * T * Cdim)
+
+
+def blend_bwd(gy, sigma, query, gquery, gsigma16, gmu16) -> None:
+    n = gy.numel()
+    _launch("mst_blend_bwd", lambda: _lib.lib().mst_blend_bwd(
+        _ptr(gy, torch.float32, "gy"), _ptr(sigma, torch.float32, "sigma"), _ptr(query, torch.float32, "query"), _ptr(gquery, torch.float32, "gquery"),
+        _ptr(gsigma16, torch.bfloat16, "gsigma16"), _ptr(gmu16, torch.bfloat16, "gmu16"), n, _stream()), nbytes=20.0 * n)
+
+
+def add_cast(a, b=None, out32=None, out16=None) -> None:
+    n = a.numel()
+    _launch("mst_add_cast", lambda: _lib.lib().mst_add_cast(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), _ptr(out32, torch.float32, "out32"),
+                                                            _ptr(out16, torch.bfloat16, "out16"), n, _stream()), nbytes=8.0 * n)
+
+
+def reflect_fold(dxp, gate, dx, B, H, W, Cdim, upsample=False) -> None:
+    _launch("mst_reflect_fold", lambda: _lib.lib().mst_reflect_fold(_ptr(dxp, torch.bfloat16, "dxp"), _ptr(gate, torch.bfloat16, "gate"),
+                                                                    _ptr(dx, torch.bfloat16, "dx"), B, H, W, Cdim, int(upsample), _stream()),
+            nbytes=4.0 * B * H * W * Cdim)
+
+
+def maxpool2x2_bwd(x, dy, dx, B, H, W, Cdim) -> None:
+    _launch("mst_maxpool2x2_bwd", lambda: _lib.lib().mst_maxpool2x2_bwd(_ptr(x, torch.bfloat16, "x"), _ptr(dy, torch.bfloat16, "dy"),
+                                                                        _ptr(dx, torch.bfloat16, "dx"), B, H, W, Cdim, _stream()),
+            nbytes=4.5 * B * H * W * Cdim)
+
+
+def nchw3_to_nhwc8(g, out, B, H, W) -> None:
+    _launch("mst_nchw3_to_nhwc8", lambda: _lib.lib().mst_nchw3_to_nhwc8(_ptr(g, torch.float32, "g"), _ptr(out, torch.bfloat16, "out"), B, H, W, _stream()),
+            nbytes=28.0 * B * H * W)
+
+
+def loss_bwd(fc, fo, mean_c, var_c, mean_o, var_o, mean_s, var_s, s, w, B, T, Cdim, squared_content, squared_style, dfo) -> None:
+    """Gradient of content + style terms w.r.t. one tap of the stylised image (two launches); s [B,C,2] scratch is zeroed here."""
+    s.zero_()
+    _launch("mst_loss_bwd_stats", lambda: _lib.lib().mst_loss_bwd_stats(
+        _ptr(fc, torch.bfloat16, "fc"), _ptr(fo, torch.bfloat16, "fo"), _ptr(mean_c, torch.float32), _ptr(var_c, torch.float32),
+        _ptr(mean_o, torch.float32), _ptr(var_o, torch.float32), B, T, Cdim, int(squared_content), _ptr(s, torch.float32, "s"), _stream()),
+        nbytes=4.0 * B * T * Cdim)
+    _launch("mst_loss_bwd_apply", lambda: _lib.lib().mst_loss_bwd_apply(
+        _ptr(fc, torch.bfloat16, "fc"), _ptr(fo, torch.bfloat16, "fo"), _ptr(mean_c, torch.float32), _ptr(var_c, torch.float32),
+        _ptr(mean_o, torch.float32), _ptr(var_o, torch.float32), _ptr(mean_s, torch.float32), _ptr(var_s, torch.float32),
+        _ptr(s, torch.float32, "s"), _ptr(w, torch.float32, "w"), B, T, Cdim, int(squared_content), int(squared_style),
+        _ptr(dfo, torch.bfloat16, "dfo"), _stream()), nbytes=6.0 * B * T * Cdim)
