@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import engine
-from .style_transformer import packed_weights, require_inference, workspace_of
+from .style_transformer import packed_weights, require_cuda, wants_grad, workspace_of
 
 _INITS = ("default", "kaiming_normal_", "kaiming_uniform_", "xavier_normal_", "xavier_uniform_", "orthogonal_")
 
@@ -50,10 +50,13 @@ class Decoder(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: [B,C,H,W] (the reference passes the BHWC transformer output permuted, full_model.py:222)."""
-        require_inference(self, x)
+        require_cuda(x)
         if x.dim() != 4 or x.shape[1] != self.decoder[0].in_channels:
             raise ValueError("Decoder expects [B, channel_dim, H, W]")
         B, C, H, W = x.shape
+        if wants_grad(self, x):
+            from .autograd_fns import cnn_decoder_apply
+            return cnn_decoder_apply(self, x)
         with torch.no_grad():
             w = packed_weights(self, engine.CnnDecoderWeights)
             ws = workspace_of(self, x.device)

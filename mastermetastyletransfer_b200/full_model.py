@@ -14,7 +14,7 @@ from torch import Tensor, nn
 
 from . import engine
 from .decoder import Decoder
-from .style_transformer import StyleTransformer, packed_weights, require_inference, workspace_of
+from .style_transformer import StyleTransformer, packed_weights, require_cuda, require_inference, wants_grad, workspace_of
 
 
 class SwinEncoderB200(nn.Sequential):
@@ -110,9 +110,17 @@ class MasterStyleTransferModel(nn.Module):
 
     def forward(self, content_image: Tensor, style_image: Tensor, transformer_layer_count: int = 1) -> Tensor:
         """[B,3,S,S] x2 -> stylised [B,3,S,S] (reference :214-226), one fused pass over shared buffers."""
-        require_inference(self, content_image, style_image)
+        require_cuda(content_image, style_image)
         if content_image.shape != style_image.shape or content_image.dim() != 4 or content_image.shape[1] != 3:
             raise ValueError("content and style must both be [B,3,S,S]")
+        st_sd = self.style_transformer.training and (self.style_transformer.encoder.encoder_stochastic_depth_prob > 0
+                                                     or self.style_transformer.decoder.stochastic_depth.p > 0)
+        if wants_grad(self, content_image, style_image) or st_sd:
+            # training: module by module as the reference composes them (full_model.py:219-226); each module records its own tape
+            fc = self.swin_encoder(content_image)
+            fs = self.swin_encoder(style_image)
+            fcs = self.style_transformer(fc, fs, transformer_layer_count)
+            return self.decoder(fcs.permute(0, 3, 1, 2))
         B, _, S, S2 = content_image.shape
         if S != S2 or S % 8:
             raise ValueError("square inputs with S a multiple of 8 only")

@@ -2,7 +2,8 @@
 
 Same class names, constructor arguments, forward signature, return tuples and state_dict layout
 (feature_extractor_model.features.{idx}.{weight,bias}); the VGG convolutions and the loss reductions
-run in the sm_100a kernels behind the C ABI.  Forward only this round (no backward kernels yet).
+run in the sm_100a kernels behind the C ABI; with a grad-requiring output image the call records the VGG
+activations and its backward runs the hand-written adjoint kernels (train_engine.py).
 """
 from __future__ import annotations
 
@@ -81,10 +82,14 @@ class custom_loss(nn.Module):
             raise NotImplementedError("similarity loss is out of scope (off by default and always 0 in the reference, SURVEY.md 0.2-4)")
         if not output_image.is_cuda:
             raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
-        if torch.is_grad_enabled() and output_image.requires_grad:
-            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, scope): call under torch.no_grad()")
         if loss_weight is None:
             loss_weight = self.lambda_value
+        if torch.is_grad_enabled() and output_image.requires_grad:
+            from .autograd_fns import perceptual_loss_apply
+            out3 = perceptual_loss_apply(self, content_image, style_image, output_image, float(loss_weight))
+            if output_content_and_style_loss:
+                return out3[0], out3[1], out3[2]
+            return out3[0]
         with torch.no_grad():
             w = packed_weights(self.feature_extractor_model, engine.VggWeights)
             ws = workspace_of(self, output_image.device)

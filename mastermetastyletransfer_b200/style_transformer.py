@@ -30,12 +30,18 @@ def params_key(module: nn.Module):
 
 
 def packed_weights(module: nn.Module, builder):
-    """Pack the module's parameters for the kernels once per parameter version."""
+    """Pack the module's parameters for the kernels once per parameter version (one cache slot per builder:
+    the inference and the training engines keep different packings of the same module)."""
     key = params_key(module)
-    hit = _cache.get(module)
+    slots = _cache.get(module)
+    if slots is None:
+        slots = {}
+        _cache[module] = slots
+    hit = slots.get(builder)
     if hit is None or hit[0] != key:
-        hit = (key, builder({k: v for k, v in module.state_dict().items()}))
-        _cache[module] = hit
+        with torch.no_grad():
+            hit = (key, builder({k: v for k, v in module.state_dict().items()}))
+        slots[builder] = hit
     return hit[1]
 
 
@@ -47,13 +53,26 @@ def workspace_of(module: nn.Module, device) -> engine.Workspace:
     return ws
 
 
-def require_inference(module: nn.Module, *tensors: Tensor) -> None:
+def require_cuda(*tensors: Tensor) -> None:
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+
+
+def wants_grad(module: nn.Module, *tensors: Tensor) -> bool:
+    """True when this call must go through the training engine (autograd is recording and something upstream or a
+    parameter of this module requires a gradient)."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(p.requires_grad for p in module.parameters()) or any(t.requires_grad for t in tensors)
+
+
+def require_inference(module: nn.Module, *tensors: Tensor) -> None:
+    require_cuda(*tensors)
+    if wants_grad(module, *tensors):
         raise NotImplementedError(
-            "backward kernels are not built yet (DESIGN.md, scope): call under torch.no_grad() for stylization")
+            "this module has no backward kernels (the Swin encoder is frozen in the reference's training setup, train.py:216-218): "
+            "freeze its parameters or call under torch.no_grad()")
 
 
 def _relative_position_index(ws: List[int]) -> Tensor:
@@ -289,15 +308,17 @@ class StyleTransformer(nn.Module):
             raise NotImplementedError("only the reference's default StyleTransformer configuration has sm_100a kernels (SURVEY.md 8f-4)")
         if c["window"][0] != c["window"][1] or c["shift"][0] != c["shift"][1] or c["dim"] // c["heads"] != 32:
             raise NotImplementedError("square windows and head_dim 32 only")
-        if self.training and (self.encoder.encoder_stochastic_depth_prob > 0):
-            raise NotImplementedError("train-mode StochasticDepth is not reproduced: call .eval() (SURVEY.md 0.2-8)")
 
     def forward(self, Fc: Tensor, Fs: Tensor, k: int = 1) -> Tensor:
         self._check_config()
-        require_inference(self, Fc, Fs)
+        require_cuda(Fc, Fs)
         if Fc.shape != Fs.shape or Fc.dim() != 4 or Fc.shape[-1] != self._cfg["dim"]:
             raise ValueError("Fc and Fs must both be [B,H,W,C] with identical shapes")
         B, H, W, C = Fc.shape
+        sd_active = self.training and (self.encoder.encoder_stochastic_depth_prob > 0 or self.decoder.stochastic_depth.p > 0)
+        if wants_grad(self, Fc, Fs) or sd_active:
+            from .autograd_fns import style_transformer_apply
+            return style_transformer_apply(self, Fc, Fs, int(k))
         with torch.no_grad():
             w = packed_weights(self, engine.StyleTransformerWeights)
             ws = workspace_of(self, Fc.device)

@@ -225,28 +225,37 @@ def _attn_weights(sd: SD, pre: str):
 # ----------------------------------------------------------------------------------------------
 
 
+def _sd(x: Tensor, scales, i: int) -> Tensor:
+    """torchvision StochasticDepth(p, "row") (ops/stochastic_depth.py) with the per-sample factors given explicitly:
+    scales[i] is [B] = bernoulli(1-p)/(1-p); None = eval mode (identity)."""
+    if scales is None:
+        return x
+    return x * scales[i].reshape(-1, *([1] * (x.dim() - 1)))
+
+
 def style_encoder(sd: SD, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
-                  pre: str = "encoder."):
+                  pre: str = "encoder.", sd_scales=None):
     """codes/style_transformer.py:855-882 default branch: one shared MHA (no norm, residual from
-    input_q for the Key pass and from input_v for Scale/Shift, :383-386), three private MLPs."""
+    input_q for the Key pass and from input_v for Scale/Shift, :383-386), three private MLPs.
+    sd_scales: optional 9 per-sample stochastic-depth factor vectors in call order (:395,865,873,882)."""
     aw = _attn_weights(sd, pre + "shared_MHA_without_MLP.attn.")
-    key = key + window_attention(key, key, key, *aw, ws, sh, heads)
-    key = key + mlp(key, sd, pre + "encoder_MLP_Key.")
-    scale = scale + window_attention(key, key, scale, *aw, ws, sh, heads)
-    scale = scale + mlp(scale, sd, pre + "encoder_MLP_Scale.")
-    shift_t = shift_t + window_attention(key, key, shift_t, *aw, ws, sh, heads)
-    shift_t = shift_t + mlp(shift_t, sd, pre + "encoder_MLP_Shift.")
+    key = key + _sd(window_attention(key, key, key, *aw, ws, sh, heads), sd_scales, 0)
+    key = key + _sd(mlp(key, sd, pre + "encoder_MLP_Key."), sd_scales, 1)
+    scale = scale + _sd(window_attention(key, key, scale, *aw, ws, sh, heads), sd_scales, 2)
+    scale = scale + _sd(mlp(scale, sd, pre + "encoder_MLP_Scale."), sd_scales, 3)
+    shift_t = shift_t + _sd(window_attention(key, key, shift_t, *aw, ws, sh, heads), sd_scales, 4)
+    shift_t = shift_t + _sd(mlp(shift_t, sd, pre + "encoder_MLP_Shift."), sd_scales, 5)
     return key, scale, shift_t
 
 
 def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
-                  pre: str = "decoder."):
-    """codes/style_transformer.py:1045-1059,1123-1128 default branch."""
+                  pre: str = "decoder.", sd_scales=None):
+    """codes/style_transformer.py:1045-1059,1123-1128 default branch (stochastic depth at :390,392,1125)."""
     b = pre + "MHA_self_attn."
     C = fcs.shape[-1]
     n1 = F.layer_norm(fcs, (C,), sd[b + "norm1.weight"], sd[b + "norm1.bias"])
-    x = fcs + window_attention(n1, n1, n1, *_attn_weights(sd, b + "attn."), ws, sh, heads)
-    x = x + mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp.")
+    x = fcs + _sd(window_attention(n1, n1, n1, *_attn_weights(sd, b + "attn."), ws, sh, heads), sd_scales, 6)
+    x = x + _sd(mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp."), sd_scales, 7)
     query_in = instance_norm_bhwc(x)
     key_in = instance_norm_bhwc(key)
     m = pre + "decoder_MHA_for_sigma_and_mu."
@@ -257,15 +266,18 @@ def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tens
                                    sd[m + "proj.weight"], sd[m + "proj.bias"],
                                    sd[m + "relative_position_bias_table"], ws, sh, heads)
     x = x * sigma + mu
-    return x + mlp(x, sd, pre + "last_MLP.")
+    return x + _sd(mlp(x, sd, pre + "last_MLP."), sd_scales, 8)
 
 
-def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8) -> Tensor:
-    """codes/style_transformer.py:1229-1245: Scale=Shift=Fs, k times the same weights."""
+def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8,
+                      sd_scales=None) -> Tensor:
+    """codes/style_transformer.py:1229-1245: Scale=Shift=Fs, k times the same weights.
+    sd_scales: optional [k, 9, B] train-mode stochastic-depth factors (None = eval)."""
     scale, shift_t = fs, fs
-    for _ in range(k):
-        fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads)
-        fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads)
+    for l in range(k):
+        sc = None if sd_scales is None else sd_scales[l]
+        fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads, sd_scales=sc)
+        fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads, sd_scales=sc)
     return fc
 
 
