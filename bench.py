@@ -101,6 +101,66 @@ def cpu_oracle_rate(size: int, layers: int, batch: int, iters: int, threads: int
     return batch / min(times), times
 
 
+TRAIN_GF_PER_SAMPLE = {1: 253.34, 4: 330.35}  # fwd+bwd, 256^2, reference-algorithm FLOPs
+
+
+def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: int = 8, size: int = 256, layers: int = 1):
+    """BASELINE configs[2] / [3]: the reference's inner-loop step (frozen encoder, style transformer + decoder trained with the
+    VGG-19 loss, Adam) at batch 8/GPU, data-parallel across ranks with one gradient all-reduce; and one meta iteration
+    (omega <- theta, one inner step on this rank's style task, all-reduced Reptile update).  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    from mastermetastyletransfer_b200 import ops, synthetic
+    from mastermetastyletransfer_b200.full_model import MasterStyleTransferModel
+    from mastermetastyletransfer_b200.loss import custom_loss
+    from mastermetastyletransfer_b200.training import InnerLoopTrainer, meta_iteration
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    model = MasterStyleTransferModel()
+    synthetic.fill_state_dict_(model, 0)
+    model = model.to(dev)
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.to(dev)
+    for m in (model.style_transformer.encoder, model.style_transformer.decoder):  # fixed-work steps: stochastic depth off (SURVEY 8d)
+        m.stochastic_depth.p = 0.0
+    model.style_transformer.encoder.encoder_stochastic_depth_prob = 0.0
+    content, style = synthetic.synthetic_images(batch, size, seed=rank)
+    style = style[:1].repeat(batch, 1, 1, 1)  # one style image repeated (train_only_inner_loop.py:491-496)
+    content, style = content.to(dev), style.to(dev)
+    out = {}
+    for name, dp in (("train_step", True), ("meta_step", False)):
+        trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1)
+        run = (lambda: trainer.step(content, style, layers)) if name == "train_step" else \
+              (lambda: meta_iteration(trainer, style, [content], 1e-4, layers))
+        for _ in range(warmup):
+            last = run()
+        n0 = ops.launch_count
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = run()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+        gf = TRAIN_GF_PER_SAMPLE.get(layers)
+        out[name] = {"ms_per_step": ms, "samples_per_s": world * batch / (ms / 1e3), "batch_per_gpu": batch, "size": size,
+                     "layers": layers, "n_gpus": world, "launches_per_step": (ops.launch_count - n0) // steps,
+                     "tflops": (gf * 1e9 * batch / (ms * 1e9)) if gf and size == 256 else None,
+                     "loss": [round(v, 5) for v in last.tolist()],
+                     "collective": ("all-reduce of the 4.30 M fp32 gradient per step" if name == "train_step" else
+                                    "all-reduce of the 4.30 M fp32 (omega - theta) delta per outer iteration") if world > 1 else "none (1 rank)",
+                     "timed": "eager launches through the C ABI (no CUDA graph), CUDA events, max over ranks"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -111,6 +171,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 32 @256, 16 @512)")
     ap.add_argument("--layers", type=int, default=1)
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the secondary training-step measurement (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     batch = args.batch or (32 if args.size == 256 else 16)
@@ -209,6 +270,7 @@ def main():
     barrier()
     ms_single = e0.elapsed_time(e1) / args.steps
 
+    launches_per_step = runner.launches_per_step
     # ---------------- per-kernel-family timing (eager pass with CUDA events around every launch) ----------------
     burst, sustained, hbm, peak_src = peaks()
     roofline, families = None, None
@@ -250,6 +312,13 @@ def main():
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"best of 3 full forwards of batch {cpu_batch} at {args.size}x{args.size}, fp32 CPU oracle port of the reference"}
 
+    # ---------------- secondary: training-step workloads (BASELINE configs[2], [3]) ----------------
+    training = None
+    if args.train_steps > 0 and args.size == 256:
+        del runner
+        torch.cuda.empty_cache()
+        training = bench_training(dev, rank, world, args.train_steps, 3)
+
     if rank == 0:
         act_mb = batch * (args.size // 8) ** 2 * 256 * 4 / 1e6
         config["l2"] = f"no explicit flush: a step streams >1 GB of activations (feature map alone {act_mb:.0f} MB fp32 x dozens of tensors) through a 126 MB L2"
@@ -261,8 +330,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e.item() / args.steps,
                     "api": "GraphedStylizer.stylize_many (pipelined); single blocking stylize_host call: %.3f ms" % ms_single},
-            "gpu_launches": runner.launches_per_step * args.steps, "launches_per_step": runner.launches_per_step,
-            "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu}))
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu, "training": training}))
     if world > 1:
         dist.destroy_process_group()
 

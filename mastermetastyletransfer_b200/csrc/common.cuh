@@ -140,6 +140,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SW128 K-major tile
 MST_DEVINL uint32_t sw128_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
+// ---------------------------------------------------------------- kernel-side views of MstGemm
+// The C-ABI struct is passed to kernels BY VALUE in two pieces: GemmCore is the inference part (layout-identical to the
+// leading fields of MstGemm), GemmExt the training-step extensions.  The split matters: the tensor-core kernels run at
+// their register cap, and growing the by-value parameter of the inference instantiation by 48 bytes was measured to push
+// ptxas into spilling in the producer / epilogue loops (16.3 -> 25.9 us on the 32768x256x256 projection).
+struct GemmCore {
+  const void* A; const void* Wt; const float* bias; const float* res; const float* mul;
+  float* out_f32; void* out_bf16;
+  int M, N, K, k_pad, lda, ld_res, ld_out32, ld_out16, a_mode, act, H, W, Cin, pad_mode, upsample, out_nchw, n_real;
+};
+struct GemmExt {
+  const void* gate; const void* add16; void* out_pre16; const float* row_scale;
+  int gate_mode, ld_gate, rows_per_scale, conv_full;
+};
+struct GemmNoExt {};
+
 // ---------------------------------------------------------------- window index arithmetic (integer, bit-exact)
 // Follows codes/style_transformer.py:77-111 (pad -> clamp shift -> roll(-s) -> partition) and :134-147 (mask labels).
 struct WinGeom {

@@ -13,6 +13,7 @@
 // (NS*BN <= 512 columns) while the k-blocks stream once.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <string.h>
 
 namespace mst {
 
@@ -50,7 +51,7 @@ MST_DEVINL uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint3
 }
 
 template <int BN>
-__global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const MstGemm p, const BandGeom g, const int total_units) {
+__global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore p, const BandGeom g, const int total_units) {
   constexpr int MAXST = 4;
   constexpr int B_STAGE_BYTES = BN * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -330,7 +331,9 @@ static int launch_band(const MstGemm& g, cudaStream_t st) {
   const int B = g.M / (g.H * g.W);
   const long long units = (long long)B * geo.bands_per_img * geo.n_tiles;
   const unsigned grid = (unsigned)(units < cb_num_sms() ? units : cb_num_sms());
-  conv_band_kernel<BN><<<grid, CB_THREADS, smem, st>>>(g, geo, (int)units);
+  GemmCore core;
+  memcpy(&core, &g, sizeof(GemmCore));
+  conv_band_kernel<BN><<<grid, CB_THREADS, smem, st>>>(core, geo, (int)units);
   return (int)cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 // buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <string.h>
 
 namespace mst {
 
@@ -49,8 +50,15 @@ MST_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 //                  A k-blocks.  Cuts the L2 traffic of the K<=256 projections by the weight re-reads, which
 //                  otherwise exceed the activation traffic (ncu: lts__t_bytes ~3.6x the algorithmic bytes).
 constexpr int MAX_STAGES = 8;
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm p, const int num_tiles, const int res_stages) {
+// EXT = false: the inference epilogue (bias / activation / residual / blend).  EXT = true additionally compiles the
+// training-step epilogue (pre-activation copy, ReLU / GELU' gates, bf16 addend, per-sample row scale) and the
+// conv_full gather; kept out of the inference instantiation so its register allocation and code size are untouched.
+template <bool EXT> struct ExtSel { typedef GemmNoExt type; };
+template <> struct ExtSel<true> { typedef GemmExt type; };
+
+template <int BN, bool EXT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore p, const typename ExtSel<EXT>::type x_, const int num_tiles,
+                                                                  const int res_stages) {
   using Cfg = GemmCfg<BN>;
   const bool resident = res_stages > 0;
   const int STAGES = resident ? res_stages : Cfg::STAGES;
@@ -118,9 +126,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
     const int t = threadIdx.x - NUM_EPI_WARPS * 32;
     const int c = t & 7;    // 16-byte chunk column inside the 128-byte k-slab
     const int r0 = t >> 3;  // first of this thread's rows; rows r0 + RSTEP*i
-    const int Hs = p.conv_full ? p.H - 2 : (p.upsample ? (p.H >> 1) : p.H);  // stored input grid
-    const int Ws = p.conv_full ? p.W - 2 : (p.upsample ? (p.W >> 1) : p.W);
-    const int tap_off = p.conv_full ? 2 : 1;
+    bool full = false;
+    if constexpr (EXT) full = x_.conv_full != 0;
+    const int Hs = full ? p.H - 2 : (p.upsample ? (p.H >> 1) : p.H);  // stored input grid
+    const int Ws = full ? p.W - 2 : (p.upsample ? (p.W >> 1) : p.W);
+    const int tap_off = full ? 2 : 1;
     const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*RSTEP*128 for row r0+RSTEP*i (whole 8-row groups further)
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
@@ -168,8 +178,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
                 yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
                 xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
               } else {  // zeros; conv_full: the input grid is (H-2) x (W-2)
-                vy = (unsigned)yy < (unsigned)(p.conv_full ? Hs : p.H);
-                vx = (unsigned)xx < (unsigned)(p.conv_full ? Ws : p.W);
+                vy = (unsigned)yy < (unsigned)(full ? Hs : p.H);
+                vx = (unsigned)xx < (unsigned)(full ? Ws : p.W);
               }
               if (p.upsample) { yy >>= 1; xx >>= 1; }
               yo[i][j] = vy ? yy * Ws * p.Cin : 0;
@@ -290,9 +300,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
           const int n = nbase + col0;
           float x[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) x[j] = __uint_as_float(v[j]) + bias_s[n + j];
-          if (p.out_pre16) {  // pre-activation copy for the backward pass
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_pre16) + (long long)row * p.ld_out16 + n);
+          for (int j = 0; j < CH; ++j) {
+            x[j] = __uint_as_float(v[j]) + bias_s[n + j];
+            if constexpr (!EXT) {
+              if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
+              else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
+            }
+          }
+          if constexpr (EXT) if (x_.out_pre16) {  // pre-activation copy for the backward pass
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(x_.out_pre16) + (long long)row * p.ld_out16 + n);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {
               uint32_t pk[4];
@@ -304,13 +320,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
               o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
+          if constexpr (EXT) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
-            else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < CH; ++j) {
+              if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
+              else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
+            }
           }
-          if (p.gate_mode != MST_GATE_NONE) {
-            const uint4* g4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gate) + (long long)row * p.ld_gate + n);
+          if constexpr (EXT) if (x_.gate_mode != MST_GATE_NONE) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x_.gate) + (long long)row * x_.ld_gate + n);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {
               const uint4 gv = g4[j];
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float g0 = __uint_as_float(gw[e] << 16), g1 = __uint_as_float(gw[e] & 0xffff0000u);
-                if (p.gate_mode == MST_GATE_RELU) {
+                if (x_.gate_mode == MST_GATE_RELU) {
                   x[8 * j + 2 * e] = g0 > 0.f ? x[8 * j + 2 * e] : 0.f;
                   x[8 * j + 2 * e + 1] = g1 > 0.f ? x[8 * j + 2 * e + 1] : 0.f;
                 } else {
@@ -328,8 +346,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
               }
             }
           }
-          if (p.add16) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.add16) + (long long)row * p.ld_gate + n);
+          if constexpr (EXT) if (x_.add16) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x_.add16) + (long long)row * x_.ld_gate + n);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {
               const uint4 av = a4[j];
@@ -341,8 +359,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
               }
             }
           }
-          if (p.row_scale) {
-            const float rs = p.row_scale[row / p.rows_per_scale];
+          if constexpr (EXT) if (x_.row_scale) {
+            const float rs = x_.row_scale[row / x_.rows_per_scale];
 #pragma unroll
             for (int j = 0; j < CH; ++j) x[j] *= rs;
           }
@@ -405,13 +423,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const MstGemm 
 
 static int g_num_sms = 0;
 
-template <int BN>
-static int launch_gemm(const MstGemm& g, cudaStream_t st) {
+template <int BN, bool EXT>
+static int launch_gemm_ext(const MstGemm& g, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   constexpr int MAX_SMEM = 222 * 1024;  // + ~4.3 KB static (bias, barriers) <= 227 KB
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -443,8 +461,22 @@ static int launch_gemm(const MstGemm& g, cudaStream_t st) {
     grid = (unsigned)(tiles < g_num_sms ? tiles : g_num_sms);
     smem = Cfg::SMEM_BYTES;
   }
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(g, (int)tiles, res_stages);
+  GemmCore core;
+  static_assert(sizeof(GemmCore) <= sizeof(MstGemm), "GemmCore must be a prefix of MstGemm");
+  memcpy(&core, &g, sizeof(GemmCore));
+  typename ExtSel<EXT>::type ext;
+  if constexpr (EXT) {
+    ext.gate = g.gate; ext.add16 = g.add16; ext.out_pre16 = g.out_pre16; ext.row_scale = g.row_scale;
+    ext.gate_mode = g.gate_mode; ext.ld_gate = g.ld_gate; ext.rows_per_scale = g.rows_per_scale; ext.conv_full = g.conv_full;
+  }
+  gemm_tc_kernel<BN, EXT><<<grid, GEMM_THREADS, smem, st>>>(core, ext, (int)tiles, res_stages);
   return (int)cudaGetLastError();
+}
+
+template <int BN>
+static int launch_gemm(const MstGemm& g, cudaStream_t st) {
+  const bool ext = g.out_pre16 || g.gate || g.add16 || g.row_scale || g.conv_full;
+  return ext ? launch_gemm_ext<BN, true>(g, st) : launch_gemm_ext<BN, false>(g, st);
 }
 
 // ---------------------------------------------------------------- weight packing (tile-blocked, pre-swizzled)

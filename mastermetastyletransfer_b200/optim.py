@@ -58,16 +58,33 @@ class _Table:
 
 
 class FusedAdam:
-    """torch.optim.Adam semantics (lr, betas, eps, weight_decay; no amsgrad) in one kernel launch per step.
-    Mirrors how the reference builds its optimisers (train_only_inner_loop.py:468-478): pass the parameters."""
+    """torch.optim.Adam semantics (lr, betas, eps, weight_decay; no amsgrad) with one kernel launch per parameter group.
+    Built the way the reference builds its optimisers: from a parameter iterable (train.py:398) or from a list of
+    {'params': ...} groups (train_only_inner_loop.py:468-478); `param_groups[i]['lr']` can be rescheduled between steps
+    (train_only_inner_loop.py:321-340)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
-        self.params = [p for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+    def __init__(self, params: Iterable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(params)
+        groups = params if params and isinstance(params[0], dict) else [{"params": params}]
+        self.param_groups = []
+        for g in groups:
+            ps = [p for p in g["params"] if p.requires_grad]
+            self.param_groups.append({"params": ps, "lr": g.get("lr", lr), "betas": g.get("betas", betas), "eps": g.get("eps", eps),
+                                      "weight_decay": g.get("weight_decay", weight_decay)})
+        self.params = [p for g in self.param_groups for p in g["params"]]
+        self.state = [{"exp_avg": [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in g["params"]],
+                       "exp_avg_sq": [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in g["params"]],
+                       "table": None} for g in self.param_groups]
         self.step_count = 0
-        self._table: Optional[_Table] = None
+
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        for g in self.param_groups:
+            g["lr"] = value
 
     def zero_grad(self, set_to_none: bool = False):
         for p in self.params:
@@ -79,20 +96,24 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
-        grads = []
-        for p in self.params:
-            if p.grad is None:
-                raise RuntimeError("FusedAdam.step: every parameter needs a gradient (the kernel updates all tensors in one launch)")
-            grads.append(p.grad.contiguous())
-        lists = [[p.data for p in self.params], grads, self.exp_avg, self.exp_avg_sq]
-        key = tuple(t.data_ptr() for l in lists for t in l)
-        if self._table is None or self._table.key != key:
-            self._table = _Table(lists)
         self.step_count += 1
-        n = sum(p.numel() for p in self.params)
-        ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step(C.byref(self._table.tb), float(self.lr), float(self.betas[0]),
-                                                                     float(self.betas[1]), float(self.eps), float(self.weight_decay),
-                                                                     int(self.step_count), ops._stream()), nbytes=28.0 * n)
+        for g, st in zip(self.param_groups, self.state):
+            if not g["params"]:
+                continue
+            grads = []
+            for p in g["params"]:
+                if p.grad is None:
+                    raise RuntimeError("FusedAdam.step: every parameter needs a gradient (the kernel updates all tensors in one launch)")
+                grads.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
+            lists = [[p.data for p in g["params"]], grads, st["exp_avg"], st["exp_avg_sq"]]
+            key = tuple(t.data_ptr() for l in lists for t in l)
+            if st["table"] is None or st["table"].key != key:
+                st["table"] = _Table(lists)
+            n = sum(p.numel() for p in g["params"])
+            tb = st["table"].tb
+            ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step(C.byref(tb), float(g["lr"]), float(g["betas"][0]),
+                                                                         float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                                                         int(self.step_count), ops._stream()), nbytes=28.0 * n)
         _bump_versions(self.params)
 
 

@@ -16,15 +16,16 @@ def timeit(fn, iters=20):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / iters * 1e3  # us
 
-def plain(M, N, K, o32=False, o16=True, res=False, act=0):
+def plain(M, N, K, o32=False, o16=True, res=False, act=0, ext=False):
     A = torch.randn(M, K, device=dev).bfloat16()
     pm = ops.pack_linear(torch.randn(N, K, device=dev) / K ** 0.5, torch.randn(N, device=dev))
     out16 = torch.empty(M, pm.n_pad, device=dev, dtype=torch.bfloat16) if o16 else None
     out32 = torch.empty(M, pm.n_pad, device=dev) if o32 else None
     r = torch.randn(M, pm.n_pad, device=dev) if res else None
-    us = timeit(lambda: ops.gemm(A, pm, M, act=act, res=r, out_f32=out32, out_bf16=out16))
+    rs = torch.ones(M // 128 + 1, device=dev) if ext else None
+    us = timeit(lambda: ops.gemm(A, pm, M, act=act, res=r, out_f32=out32, out_bf16=out16, row_scale=rs, rows_per_scale=128))
     by = M * K * 2 + (M * N * 2 if o16 else 0) + (M * N * 4 if o32 else 0) + (M * N * 4 if res else 0)
-    print(f"plain M={M:8d} N={N:4d} K={K:4d} o32={int(o32)} o16={int(o16)} res={int(res)} act={act}: {us:8.1f} us  {2*M*N*K/us/1e6:7.1f} TF/s  {by/us/1e3:7.1f} GB/s(alg)")
+    print(f"plain ext={int(ext)} M={M:8d} N={N:4d} K={K:4d} o32={int(o32)} o16={int(o16)} res={int(res)} act={act}: {us:8.1f} us  {2*M*N*K/us/1e6:7.1f} TF/s  {by/us/1e3:7.1f} GB/s(alg)")
 
 def conv(B, H, Cin, Cout, up=False, reflect=True, impl='auto'):
     hs = H // 2 if up else H
@@ -42,6 +43,8 @@ def conv(B, H, Cin, Cout, up=False, reflect=True, impl='auto'):
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("plain", "all"):
     plain(32768, 256, 256)
+    plain(32768, 256, 256, ext=True)
+    plain(262144, 384, 128, ext=True)
     plain(32768, 1024, 256, act=2)
     plain(32768, 256, 1024, o32=True, res=True)
     plain(262144, 384, 128)
