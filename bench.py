@@ -112,7 +112,7 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
     from mastermetastyletransfer_b200 import ops, synthetic
     from mastermetastyletransfer_b200.full_model import MasterStyleTransferModel
     from mastermetastyletransfer_b200.loss import custom_loss
-    from mastermetastyletransfer_b200.training import InnerLoopTrainer, meta_iteration
+    from mastermetastyletransfer_b200.training import GraphedTrainStep, InnerLoopTrainer, meta_iteration
 
     def barrier():
         if world > 1:
@@ -132,10 +132,15 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
     style = style[:1].repeat(batch, 1, 1, 1)  # one style image repeated (train_only_inner_loop.py:491-496)
     content, style = content.to(dev), style.to(dev)
     out = {}
-    for name, dp in (("train_step", True), ("meta_step", False)):
-        trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1)
-        run = (lambda: trainer.step(content, style, layers)) if name == "train_step" else \
-              (lambda: meta_iteration(trainer, style, [content], 1e-4, layers))
+    for name, dp in (("train_step", True), ("train_step_eager", True), ("meta_step", False)):
+        trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1, capturable=(name == "train_step"))
+        if name == "train_step":
+            graphed = GraphedTrainStep(trainer, batch, size, layers)
+            run = lambda: graphed.step(content, style)
+        elif name == "train_step_eager":
+            run = lambda: trainer.step(content, style, layers)
+        else:
+            run = lambda: meta_iteration(trainer, style, [content], 1e-4, layers)
         for _ in range(warmup):
             last = run()
         n0 = ops.launch_count
@@ -155,9 +160,10 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
                      "layers": layers, "n_gpus": world, "launches_per_step": (ops.launch_count - n0) // steps,
                      "tflops": (gf * 1e9 * batch / (ms * 1e9)) if gf and size == 256 else None,
                      "loss": [round(v, 5) for v in last.tolist()],
-                     "collective": ("all-reduce of the 4.30 M fp32 gradient per step" if name == "train_step" else
+                     "collective": ("all-reduce of the 4.30 M fp32 gradient per step" if name.startswith("train_step") else
                                     "all-reduce of the 4.30 M fp32 (omega - theta) delta per outer iteration") if world > 1 else "none (1 rank)",
-                     "timed": "eager launches through the C ABI (no CUDA graph), CUDA events, max over ranks"}
+                     "timed": ("one CUDA-graph replay per step (training.GraphedTrainStep)" if name == "train_step" else
+                               "eager launches through the C ABI (no CUDA graph)") + ", CUDA events, max over ranks"}
     return out
 
 

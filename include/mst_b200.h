@@ -176,7 +176,9 @@ int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
  * mst_conv3x3_first: features[0] Conv2d(3,64,3,pad 1) (+ReLU features[1]) on fp32 NCHW images
  *   (loss.py:23-25) -> bf16 [B,H,W,64].
  * mst_maxpool2x2: nn.MaxPool2d(2) on bf16 [B,H,W,C] (features[4,9,18,27]).
- * mst_tap_stats: per (image, channel) mean and biased variance over T=H*W of a tap [B,T,C]
+ * mst_tap_stats: per (image, channel) mean and biased variance over T=H*W of a tap [B,T,C]; T is split over CTAs and
+ *   the per-slab partial sums go through caller-provided scratch (mst_tap_stats_scratch_floats floats), combined in a
+ *   fixed order so the result is deterministic
  *   (the statistics both loss terms need: loss.py:102-105 InstanceNorm2d, :122-130 mean/std).
  * mst_content_term: sum over all elements of |IN(Fc)-IN(Fcs)| (squared=0, "euclidian", loss.py:114-116)
  *   or its square (loss.py:110-112) as n_partials deterministic per-CTA partial sums.
@@ -187,7 +189,9 @@ int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
 int mst_conv3x3_first(const float* img, const float* w, const float* b, mst_bf16* out, int B, int H, int W, int relu,
                       void* stream);
 int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream);
-int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, void* stream);
+size_t mst_tap_stats_scratch_floats(int B, int T, int C);
+int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, float* scratch, size_t scratch_floats,
+                  void* stream);
 int mst_content_term(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
                      const float* var_o, int B, int T, int C, int squared, float* partials, int n_partials, void* stream);
 
@@ -227,6 +231,11 @@ typedef struct MstTensorTable {
 int mst_opt_chunk_elems(void);
 int mst_adam_step(const MstTensorTable* tb, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                   void* stream);
+/* CUDA-graph-capturable Adam: learning rate and step count live on the device (dev_state = {float lr; int step}), so a captured
+ * training step replays with the right bias correction; advance=1 increments the step first (once per optimiser step, i.e. on
+ * the first parameter group). */
+int mst_adam_step_dev(const MstTensorTable* tb, float beta1, float beta2, float eps, float weight_decay, void* dev_state, int advance,
+                      void* stream);
 int mst_reptile_delta(const MstTensorTable* tb, float* flat, void* stream);
 int mst_reptile_apply(const MstTensorTable* tb, float* flat, float scale, void* stream);
 

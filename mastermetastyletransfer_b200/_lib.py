@@ -106,11 +106,13 @@ SYMBOLS = {
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
     "mst_opt_chunk_elems": (_I, []),
     "mst_adam_step": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
+    "mst_adam_step_dev": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, _P, _I, _P]),
     "mst_reptile_delta": (_I, [C.POINTER(MstTensorTable), _P, _P]),
     "mst_reptile_apply": (_I, [C.POINTER(MstTensorTable), _P, C.c_float, _P]),
     "mst_conv3x3_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
-    "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "mst_tap_stats_scratch_floats": (_Z, [_I, _I, _I]),
+    "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "mst_content_term": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "mst_loss_finalize": (_I, [C.POINTER(MstLossTaps), C.c_float, _I, _P, _P]),
     "mst_wgrad": (_I, [C.POINTER(MstWgrad), _P]),

@@ -90,41 +90,72 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const bf16* __restrict_
 }
 
 // ---------------------------------------------------------------- per-(image, channel) mean / biased variance of a bf16 tap
-// x [B,T,C] bf16.  CTA = (b, 64-channel group): lane owns 2 channels (one 32-bit load), 8 warps stride over T.
-// Single pass with a per-thread shift (first value) to keep the sum of squares well conditioned.
-__global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ mean,
-                                                        float* __restrict__ var, int T, int C) {
-  __shared__ float red[3][8][65];
-  const int groups = C / 64;
-  const int b = blockIdx.x / groups;
-  const int c = (blockIdx.x - b * groups) * 64 + 2 * (threadIdx.x & 31);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C + c);
-  const int stride = C / 2;
-  // shift = the channel's first element (same for all warps of the CTA)
-  const uint32_t f = xb[0];
-  const float k0 = __uint_as_float(f << 16), k1 = __uint_as_float(f & 0xFFFF0000u);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  for (int t = warp; t < T; t += 8) {
-    const uint32_t u = xb[(long long)t * stride];
-    const float a = __uint_as_float(u << 16) - k0, d = __uint_as_float(u & 0xFFFF0000u) - k1;
-    s0 += a; q0 = fmaf(a, a, q0);
-    s1 += d; q1 = fmaf(d, d, q1);
-  }
-  red[0][warp][2 * lane] = s0; red[0][warp][2 * lane + 1] = s1;
-  red[1][warp][2 * lane] = q0; red[1][warp][2 * lane + 1] = q1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f, q = 0.f;
+// x [B,T,C] bf16.  CTA = (T slab, b, 64-channel group); thread = (8-channel chunk, row lane): 16-byte loads, 128-byte rows.
+// Sums are taken relative to a per-channel shift (the channel's first element) so the sum of squares stays well
+// conditioned; every slab writes its partial (sum, sum of squares) to the caller's scratch [slabs][B*C][2] and
+// tap_stats_finalize adds the slabs in a fixed order (deterministic) into mean and biased variance.  The T split is what
+// fills the GPU: the taps are [B, 16384..256, 128..512].
+__global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ part, int T, int C,
+                                                        int rows_per_cta, int BC) {
+  __shared__ float red[2][32][65];
+  const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int b = blockIdx.y;
+  const int col = blockIdx.z * 64 + c8 * 8;
+  const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  const bf16* xb = x + (long long)b * T * C + col;
+  float k[8], s[8], q[8];
+  {
+    const uint4 f = *reinterpret_cast<const uint4*>(xb);
+    const uint32_t w[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { s += red[0][w][threadIdx.x]; q += red[1][w][threadIdx.x]; }
-    const int cc = (blockIdx.x - b * groups) * 64 + threadIdx.x;
-    const uint32_t fu = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C + (cc & ~1))[0];
-    const float k = (cc & 1) ? __uint_as_float(fu & 0xFFFF0000u) : __uint_as_float(fu << 16);
-    const float m = s / (float)T;
-    mean[(long long)b * C + cc] = m + k;
-    var[(long long)b * C + cc] = fmaxf(q / (float)T - m * m, 0.f);
+    for (int e = 0; e < 4; ++e) { k[2 * e] = __uint_as_float(w[e] << 16); k[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u); }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  for (int t = t0 + rl; t < t1; t += 32) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xb + (long long)t * C);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(w[e] << 16) - k[2 * e], d = __uint_as_float(w[e] & 0xFFFF0000u) - k[2 * e + 1];
+      s[2 * e] += a; q[2 * e] = fmaf(a, a, q[2 * e]);
+      s[2 * e + 1] += d; q[2 * e + 1] = fmaf(d, d, q[2 * e + 1]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[0][rl][c8 * 8 + e] = s[e]; red[1][rl][c8 * 8 + e] = q[e]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a += red[which][i][cc];
+    part[((long long)blockIdx.x * BC + (long long)b * C + blockIdx.z * 64 + cc) * 2 + which] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) tap_stats_finalize_kernel(const bf16* __restrict__ x, const float* __restrict__ part,
+                                                                 float* __restrict__ mean, float* __restrict__ var, int B, int T,
+                                                                 int C, int slabs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  float s = 0.f, q = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) {
+    const float2 v = reinterpret_cast<const float2*>(part)[(long long)sl * B * C + i];
+    s += v.x;
+    q += v.y;
+  }
+  const float k = __bfloat162float(x[(long long)b * T * C + c]);
+  const float m = s / (float)T;
+  mean[i] = m + k;
+  var[i] = fmaxf(q / (float)T - m * m, 0.f);
+}
+
+static int tap_stats_rows(int B, int T, int C) {  // slab size: enough CTAs to cover the GPU a few times over, >= 64 rows each
+  int rows = 64;
+  while ((long long)((T + rows - 1) / rows) * B * (C / 64) > 148 * 8 && rows < T) rows *= 2;
+  return rows;
 }
 
 // ---------------------------------------------------------------- content term: sum |IN(Fc) - IN(Fcs)| (or squared)
@@ -223,10 +254,23 @@ extern "C" int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int 
   return (int)cudaGetLastError();
 }
 
-extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, void* stream) {
-  if (!x || !mean || !var || B <= 0 || T <= 0 || C <= 0) return MST_ERR_BAD_ARG;
+extern "C" size_t mst_tap_stats_scratch_floats(int B, int T, int C) {
+  if (B <= 0 || T <= 0 || C <= 0) return 0;
+  const int rows = tap_stats_rows(B, T, C);
+  return (size_t)((T + rows - 1) / rows) * B * C * 2;
+}
+
+extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, float* scratch, size_t scratch_floats,
+                             void* stream) {
+  if (!x || !mean || !var || !scratch || B <= 0 || T <= 0 || C <= 0) return MST_ERR_BAD_ARG;
   if (C % 64) return MST_ERR_UNSUPPORTED;
-  tap_stats_kernel<<<B * (C / 64), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), mean, var, T, C);
+  if (scratch_floats < mst_tap_stats_scratch_floats(B, T, C)) return MST_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = tap_stats_rows(B, T, C);
+  const int slabs = (T + rows - 1) / rows;
+  dim3 grid((unsigned)slabs, (unsigned)B, (unsigned)(C / 64));
+  tap_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, T, C, rows, B * C);
+  tap_stats_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, mean, var, B, T, C, slabs);
   return (int)cudaGetLastError();
 }
 

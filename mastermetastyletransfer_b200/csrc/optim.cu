@@ -20,8 +20,21 @@ MST_DEVINL int find_tensor(const int* __restrict__ chunk_start, int n_tensors, i
   return lo;
 }
 
+// dev_state (optional, CUDA-graph-capturable mode): {float lr, int step}; step has already been incremented for this update
+struct AdamDevState {
+  float lr;
+  int step;
+};
+__global__ void adam_advance_kernel(AdamDevState* st) { st->step += 1; }
+
 __global__ void __launch_bounds__(256) adam_kernel(const MstTensorTable tb, float lr, float beta1, float beta2, float eps,
-                                                   float weight_decay, float bc1, float bc2_sqrt) {
+                                                   float weight_decay, float bc1, float bc2_sqrt, const AdamDevState* dev_state) {
+  if (dev_state) {  // the captured graph must not bake the step count or the learning rate into its launch arguments
+    lr = dev_state->lr;
+    const double t = (double)dev_state->step;
+    bc1 = (float)(1.0 - pow((double)beta1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
   const int t = find_tensor(tb.chunk_start, tb.n_tensors, blockIdx.x);
   const long long base = (long long)(blockIdx.x - tb.chunk_start[t]) * OPT_CHUNK;
   const long long n = tb.numel[t];
@@ -85,7 +98,17 @@ extern "C" int mst_adam_step(const MstTensorTable* tb, float lr, float beta1, fl
     return MST_ERR_BAD_ARG;
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  adam_kernel<<<tb->n_chunks, 256, 0, (cudaStream_t)stream>>>(*tb, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt);
+  adam_kernel<<<tb->n_chunks, 256, 0, (cudaStream_t)stream>>>(*tb, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_adam_step_dev(const MstTensorTable* tb, float beta1, float beta2, float eps, float weight_decay, void* dev_state,
+                                 int advance, void* stream) {
+  if (!tb || tb->n_tensors <= 0 || tb->n_chunks <= 0 || !tb->chunk_start || !tb->numel || !tb->a || !tb->b || !tb->c || !tb->d || !dev_state)
+    return MST_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (advance) adam_advance_kernel<<<1, 1, 0, st>>>(reinterpret_cast<AdamDevState*>(dev_state));
+  adam_kernel<<<tb->n_chunks, 256, 0, st>>>(*tb, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, reinterpret_cast<const AdamDevState*>(dev_state));
   return (int)cudaGetLastError();
 }
 

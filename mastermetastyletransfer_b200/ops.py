@@ -268,9 +268,20 @@ def maxpool2x2(x, y, B, H, W, Cdim) -> None:
             nbytes=2.5 * B * H * W * Cdim)
 
 
-def tap_stats(x, mean, var, B, T, Cdim) -> None:
+_tap_scratch = {}
+
+
+def tap_stats(x, mean, var, B, T, Cdim, scratch=None) -> None:
+    """scratch: optional fp32 workspace of mst_tap_stats_scratch_floats(B,T,C) floats; a per-device one is kept otherwise."""
+    need = _lib.lib().mst_tap_stats_scratch_floats(B, T, Cdim)
+    if scratch is None:
+        scratch = _tap_scratch.get(x.device)
+        if scratch is None or scratch.numel() < need:
+            scratch = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=x.device)
+            _tap_scratch[x.device] = scratch
     _launch("mst_tap_stats", lambda: _lib.lib().mst_tap_stats(_ptr(x, torch.bfloat16, "x"), _ptr(mean, torch.float32, "mean"),
-                                                               _ptr(var, torch.float32, "var"), B, T, Cdim, _stream()),
+                                                               _ptr(var, torch.float32, "var"), B, T, Cdim,
+                                                               _ptr(scratch, torch.float32, "scratch"), scratch.numel(), _stream()),
             nbytes=2.0 * B * T * Cdim)
 
 

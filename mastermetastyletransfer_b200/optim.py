@@ -42,13 +42,19 @@ class _Table:
             off += (t.numel() + 3) // 4 * 4
         self.total, self.n_chunks, self.n = off, c, n
         self.key = tuple(t.data_ptr() for l in lists for t in l)
-        self._keep = [torch.tensor(starts, dtype=torch.int32, device=dev), torch.tensor(numel, dtype=torch.int64, device=dev),
-                      torch.tensor(offs, dtype=torch.int64, device=dev)]
+        self._host = []  # pinned staging: the uploads are async copies, legal inside a CUDA-graph capture and replayable
+
+        def upload(values, dtype):
+            h = torch.tensor(values, dtype=dtype).pin_memory()
+            self._host.append(h)
+            return h.to(dev, non_blocking=True)
+
+        self._keep = [upload(starts, torch.int32), upload(numel, torch.int64), upload(offs, torch.int64)]
         for l in lists:
             for t in l:
                 if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
                     raise TypeError("optimiser kernels need contiguous fp32 CUDA tensors")
-            self._keep.append(torch.tensor([t.data_ptr() for t in l], dtype=torch.int64, device=dev))
+            self._keep.append(upload([t.data_ptr() for t in l], torch.int64))
         tb = MstTensorTable()
         tb.chunk_start, tb.numel, tb.flat_offset = (k.data_ptr() for k in self._keep[:3])
         ptrs = [k.data_ptr() for k in self._keep[3:]] + [None] * 4
@@ -63,7 +69,9 @@ class FusedAdam:
     {'params': ...} groups (train_only_inner_loop.py:468-478); `param_groups[i]['lr']` can be rescheduled between steps
     (train_only_inner_loop.py:321-340)."""
 
-    def __init__(self, params: Iterable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params: Iterable, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, capturable: bool = False):
+        """capturable=True keeps {lr, step} on the device so that step() can be captured in a CUDA graph and replayed
+        (training.GraphedTrainStep); change the learning rate with set_lr() between replays."""
         params = list(params)
         groups = params if params and isinstance(params[0], dict) else [{"params": params}]
         self.param_groups = []
@@ -76,6 +84,21 @@ class FusedAdam:
                        "exp_avg_sq": [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in g["params"]],
                        "table": None} for g in self.param_groups]
         self.step_count = 0
+        self.capturable = capturable
+        self._dev_state = None
+        if capturable:
+            dev = self.params[0].device
+            self._dev_state = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in self.param_groups]  # {float lr, int step}
+            for g, st in zip(self.param_groups, self._dev_state):
+                st.view(torch.float32)[0] = float(g["lr"])
+
+    def set_lr(self, lr: float, group: Optional[int] = None) -> None:
+        """Learning-rate change that a captured graph sees (device-side state); eager mode just updates param_groups."""
+        for i, g in enumerate(self.param_groups):
+            if group is None or group == i:
+                g["lr"] = lr
+                if self._dev_state is not None:
+                    self._dev_state[i].view(torch.float32)[0] = float(lr)
 
     @property
     def lr(self):
@@ -111,9 +134,15 @@ class FusedAdam:
                 st["table"] = _Table(lists)
             n = sum(p.numel() for p in g["params"])
             tb = st["table"].tb
-            ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step(C.byref(tb), float(g["lr"]), float(g["betas"][0]),
-                                                                         float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                                                                         int(self.step_count), ops._stream()), nbytes=28.0 * n)
+            if self.capturable:
+                ds = self._dev_state[self.param_groups.index(g)]
+                ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step_dev(C.byref(tb), float(g["betas"][0]), float(g["betas"][1]),
+                                                                                 float(g["eps"]), float(g["weight_decay"]), ds.data_ptr(), 1,
+                                                                                 ops._stream()), nbytes=28.0 * n)
+            else:
+                ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step(C.byref(tb), float(g["lr"]), float(g["betas"][0]),
+                                                                             float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                                                             int(self.step_count), ops._stream()), nbytes=28.0 * n)
         _bump_versions(self.params)
 
 

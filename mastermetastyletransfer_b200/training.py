@@ -35,7 +35,11 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], group=None, flat: 
     total = sum(p.numel() for p in params)
     if flat is None or flat.numel() != total or flat.device != params[0].device:
         flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
-    torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+    lo, hi = flat.data_ptr(), flat.data_ptr() + 4 * total
+    if any(lo <= p.grad.data_ptr() < hi for p in params):  # gradients accumulated into last step's views: pack out of place
+        flat.copy_(torch.cat([p.grad.reshape(-1) for p in params]))
+    else:
+        torch.cat([p.grad.reshape(-1) for p in params], out=flat)
     if _dist_on(group):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.mul_(1.0 / dist.get_world_size(group))
@@ -52,14 +56,14 @@ class InnerLoopTrainer:
     frozen (train.py:216-218,306-309,436-517).  `model` is a MasterStyleTransferModel, `loss_fn` a custom_loss."""
 
     def __init__(self, model, loss_fn, inner_lr: float = 1e-4, max_layers: int = 4, data_parallel: bool = False, group=None,
-                 seed: int = 0):
+                 seed: int = 0, capturable: bool = False):
         self.model, self.loss_fn = model, loss_fn
         for p in model.swin_encoder.parameters():
             p.requires_grad = False
         self.omega_st = copy.deepcopy(model.style_transformer).train()
         self.omega_dec = copy.deepcopy(model.decoder).train()
         self.params: List[torch.nn.Parameter] = list(self.omega_st.parameters()) + list(self.omega_dec.parameters())
-        self.opt = FusedAdam(self.params, lr=inner_lr)
+        self.opt = FusedAdam(self.params, lr=inner_lr, capturable=capturable)
         self.max_layers, self.data_parallel, self.group = max_layers, data_parallel, group
         self._rng = random.Random(seed)  # shared seed: every rank samples the same layer count (SURVEY 8e)
         self._flat = None
@@ -101,3 +105,57 @@ def meta_iteration(trainer: InnerLoopTrainer, style: torch.Tensor, content_batch
         last = trainer.step(content, style, num_layers)
     trainer.outer_update(outer_lr)
     return last
+
+
+class GraphedTrainStep:
+    """One inner-loop step (forward, loss, backward, optional gradient all-reduce, Adam) captured in a CUDA graph: the ~360
+    kernel launches of a step cost ~15 ms of host time when issued one by one through ctypes, more than the GPU work itself;
+    a replay costs one launch.  The layer count is a host-side choice (train.py:449), so there is one graph per value.
+    `trainer` must have been built with capturable=True (device-side Adam step / learning rate)."""
+
+    def __init__(self, trainer: InnerLoopTrainer, batch: int, size: int, num_layers: int = 1, warmup: int = 3):
+        if not trainer.opt.capturable:
+            raise ValueError("GraphedTrainStep needs InnerLoopTrainer(..., capturable=True)")
+        self.trainer, self.num_layers = trainer, num_layers
+        dev = trainer.params[0].device
+        self.content = torch.zeros(batch, 3, size, size, device=dev)
+        self.style = torch.zeros(batch, 3, size, size, device=dev)
+        self._rand_fill()
+        # the warm-up steps really train (on noise): snapshot parameters and optimiser state, restore after the capture
+        opt = trainer.opt
+        snap = [[p.detach().clone() for p in trainer.params], [[t.clone() for t in st["exp_avg"]] for st in opt.state],
+                [[t.clone() for t in st["exp_avg_sq"]] for st in opt.state], [d.clone() for d in opt._dev_state], opt.step_count]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # sizes every workspace, packs weights, sets kernel attributes
+                trainer.step(self.content, self.style, num_layers)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = trainer.step(self.content, self.style, num_layers)
+        torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for p, v in zip(trainer.params, snap[0]):
+                p.copy_(v)
+            for st, ea, es in zip(opt.state, snap[1], snap[2]):
+                for t, v in zip(st["exp_avg"], ea):
+                    t.copy_(v)
+                for t, v in zip(st["exp_avg_sq"], es):
+                    t.copy_(v)
+            for d, v in zip(opt._dev_state, snap[3]):
+                d.copy_(v)
+        opt.step_count = snap[4]
+
+    def _rand_fill(self):
+        g = torch.Generator(device=self.content.device).manual_seed(0)
+        self.content.copy_(torch.rand(self.content.shape, generator=g, device=self.content.device))
+        self.style.copy_(torch.rand(self.style.shape, generator=g, device=self.style.device))
+
+    def step(self, content: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+        self.content.copy_(content, non_blocking=True)
+        self.style.copy_(style, non_blocking=True)
+        self.graph.replay()
+        return self.losses

@@ -18,3 +18,14 @@ def test_reptile_update_two_ranks_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "identical_across_ranks=True" in out.stdout
+
+
+def test_data_parallel_training_two_ranks_nccl():
+    """DP inner-loop steps + meta iteration across two ranks: one gradient / delta all-reduce, replicas identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(REPO, "tools", "train_2gpu.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "dp_identical=True" in out.stdout and "meta_identical=True" in out.stdout

@@ -373,3 +373,32 @@ def test_model_forward_train_mode_matches_modules(model):
     assert all(p.grad is not None for p in model.style_transformer.parameters())
     assert all(p.grad is not None for p in model.decoder.parameters())
     model.zero_grad(set_to_none=True)
+
+
+def test_graphed_train_step_matches_eager(model):
+    """GraphedTrainStep (one CUDA-graph replay per inner-loop step, device-side Adam step count) follows the eager trainer."""
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    from mastermetastyletransfer_b200.training import GraphedTrainStep, InnerLoopTrainer
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.cuda()
+    m = copy.deepcopy(model)
+    for mod in (m.style_transformer.encoder, m.style_transformer.decoder):
+        mod.stochastic_depth.p = 0.0
+    m.style_transformer.encoder.encoder_stochastic_depth_prob = 0.0
+    content, style = synthetic.synthetic_images(2, 64, seed=9)
+    content, style = content.cuda(), style.cuda()
+    eager = InnerLoopTrainer(m, loss_fn, inner_lr=1e-3)
+    graphed = InnerLoopTrainer(m, loss_fn, inner_lr=1e-3, capturable=True)
+    g = GraphedTrainStep(graphed, 2, 64, num_layers=1)
+    for a, b in zip(eager.params, graphed.params):  # the capture's warm-up steps left no trace
+        assert torch.equal(a, b)
+    le, lg = [], []
+    for _ in range(4):
+        le.append(eager.step(content, style, 1).clone())
+        lg.append(g.step(content, style).clone())
+    le, lg = torch.stack(le).cpu(), torch.stack(lg).cpu()
+    assert torch.allclose(le, lg, rtol=2e-3), (le, lg)
+    assert le[-1, 0] != le[0, 0]  # the parameters really moved
+    worst = max(((a - b).norm() / (a.norm() + 1e-12)).item() for a, b in zip(eager.params, graphed.params))
+    assert worst < 2e-3, worst  # (Adam's sign-like first steps amplify the fp32-atomics ordering noise of the gradients)
