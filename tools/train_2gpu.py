@@ -52,7 +52,9 @@ def same_everywhere(params):
     v = torch.cat([p.detach().reshape(-1) for p in params])
     ref = v.clone()
     dist.broadcast(ref, 0)
-    return torch.equal(v, ref)
+    same = torch.tensor([1.0 if torch.equal(v, ref) else 0.0], device=v.device)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)  # rank 0 always equals itself: the verdict is the minimum over ranks
+    return bool(same.item())
 dp_same = same_everywhere(tr.params)
 tm = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=False)
 theta0 = torch.cat([p.detach().reshape(-1) for p in model.style_transformer.parameters()]).clone()
