@@ -140,6 +140,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows x 128 B] SW128 K-major tile
 MST_DEVINL uint32_t sw128_offset(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
 
+// ---------------------------------------------------------------- 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256)
+// One lane moves a whole 32-byte sector, so a row-per-lane epilogue issues half as many L1 requests as with 128-bit
+// accesses.  Addresses must be 32-byte aligned.
+MST_DEVINL void st_global_256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+MST_DEVINL void st_global_256f(void* p, const float* r) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]),
+               "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
+MST_DEVINL void ld_global_256(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+MST_DEVINL void ld_global_256f(const void* p, float* r) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+
 // ---------------------------------------------------------------- kernel-side views of MstGemm
 // The C-ABI struct is passed to kernels BY VALUE in two pieces: GemmCore is the inference part (layout-identical to the
 // leading fields of MstGemm), GemmExt the training-step extensions.  The split matters: the tensor-core kernels run at

@@ -236,7 +236,19 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
 #pragma unroll
             for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]);
           }
-          if (p.out_bf16) {
+          if (p.out_bf16 && CH >= 16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0) {
+            bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + pix * p.ld_out16 + n;  // one 32-byte sector per lane and store
+#pragma unroll
+            for (int j = 0; j < CH / 16; ++j) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(xv[16 * j + 2 * e], xv[16 * j + 2 * e + 1]);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              st_global_256(op + 16 * j, pk);
+            }
+          } else if (p.out_bf16) {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + pix * p.ld_out16 + n);
 #pragma unroll
             for (int j = 0; j < CH / 8; ++j) {

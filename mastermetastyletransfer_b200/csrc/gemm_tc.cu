@@ -20,7 +20,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_PROD_WARPS = 7;  // 8 + 7 + 1 = 16 warps: register files are allotted per 4 warps, a 17th warp costs 32 regs/thread
 constexpr int GEMM_THREADS = (NUM_EPI_WARPS + NUM_PROD_WARPS + 1) * 32;
 constexpr int MAX_BIAS = 1024;
 
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
 
   if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_PROD_WARPS) {
     // =========================== producers ===========================
-    constexpr int RPT = BM * 8 / (NUM_PROD_WARPS * 32);  // rows per thread (4 with 8 producer warps)
-    constexpr int RSTEP = NUM_PROD_WARPS * 4;            // row distance between a thread's rows (32)
+    constexpr int RSTEP = NUM_PROD_WARPS * 4;            // row distance between a thread's rows (28)
+    constexpr int RPT = (BM + RSTEP - 1) / RSTEP;        // rows per thread (5; the fifth only for r0 < BM - 4*RSTEP)
     const int t = threadIdx.x - NUM_EPI_WARPS * 32;
     const int c = t & 7;    // 16-byte chunk column inside the 128-byte k-slab
     const int r0 = t >> 3;  // first of this thread's rows; rows r0 + RSTEP*i
@@ -131,7 +131,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
     const int Hs = full ? p.H - 2 : (p.upsample ? (p.H >> 1) : p.H);  // stored input grid
     const int Ws = full ? p.W - 2 : (p.upsample ? (p.W >> 1) : p.W);
     const int tap_off = full ? 2 : 1;
-    const uint32_t a_dst0 = sw128_offset(r0, c);  // + i*RSTEP*128 for row r0+RSTEP*i (whole 8-row groups further)
+    uint32_t a_dst[RPT];  // swizzled byte offset of (row r0 + RSTEP*i, chunk c) inside a stage
+    bool row_in[RPT];     // the row exists in the 128-row tile (false only for the last i of the higher producer warps)
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      row_in[i] = r0 + RSTEP * i < BM;
+      a_dst[i] = sw128_offset(r0 + RSTEP * i, c);
+    }
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
     const bool conv = p.a_mode != MST_A_PLAIN;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
         rowp[i] = Abase;
 #pragma unroll
         for (int j = 0; j < 3; ++j) { yo[i][j] = 0; xo[i][j] = 0; }
-        if (m < p.M) {
+        if (row_in[i] && m < p.M) {
           if (!conv) {
             rowp[i] = Abase + (long long)m * p.lda;
             vmask[i] = 0x3F;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const bool valid = kvalid && vmask[i] != 0;
-            cp_async16(a_stage + a_dst0 + i * (RSTEP * 128), valid ? rowp[i] + k0 : Abase, valid);
+            if (row_in[i]) cp_async16(a_stage + a_dst[i], valid ? rowp[i] + k0 : Abase, valid);
           }
         } else {
           const int ky = tap / 3, kx = tap - ky * 3;  // tap < 16: cheap constant division
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
             const int yoff = ky == 0 ? yo[i][0] : (ky == 1 ? yo[i][1] : yo[i][2]);
             const int xoff = kx == 0 ? xo[i][0] : (kx == 1 ? xo[i][1] : xo[i][2]);
             const bool valid = kvalid && ((vmask[i] >> ky) & (vmask[i] >> (3 + kx)) & 1u);
-            cp_async16(a_stage + a_dst0 + i * (RSTEP * 128), valid ? rowp[i] + (yoff + xoff + ch) : Abase, valid);
+            if (row_in[i]) cp_async16(a_stage + a_dst[i], valid ? rowp[i] + (yoff + xoff + ch) : Abase, valid);
           }
           ch += BK;
           while (ch >= p.Cin) { ch -= p.Cin; ++tap; }
@@ -266,6 +272,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
     const int quad = warp & 3;
     const int half = warp >> 2;
     const bool active = half < Cfg::EPI_SPLIT;
+    // 256-bit accesses when every row segment starts on a 32-byte boundary (CH >= 16 columns per chunk)
+    const bool wide16 = CH >= 16 && p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
+    const bool wide32 = p.out_f32 && !p.out_nchw && ((reinterpret_cast<uintptr_t>(p.out_f32) | (uintptr_t)(p.ld_out32 * 4)) & 31) == 0;
+    const bool wideres = p.res && ((reinterpret_cast<uintptr_t>(p.res) | (uintptr_t)(p.ld_res * 4) |
+                                    (p.mul ? reinterpret_cast<uintptr_t>(p.mul) : 0)) & 31) == 0;
     int tcount = 0;
     for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt), ++tcount) {
       const int n_tile = tt.n_tile, m0 = tt.m_tile * BM;
@@ -308,16 +319,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
             }
           }
           if constexpr (EXT) if (x_.out_pre16) {  // pre-activation copy for the backward pass
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(x_.out_pre16) + (long long)row * p.ld_out16 + n);
+            bf16* op = reinterpret_cast<bf16*>(x_.out_pre16) + (long long)row * p.ld_out16 + n;
+            if (CH >= 16 && ((reinterpret_cast<uintptr_t>(x_.out_pre16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint32_t pk[4];
+              for (int j = 0; j < CH / 16; ++j) {
+                uint32_t pk[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(x[16 * j + 2 * e], x[16 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                st_global_256(op + 16 * j, pk);
               }
-              o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            } else {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
             }
           }
           if constexpr (EXT) {
@@ -327,35 +352,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
               else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);
             }
           }
-          if constexpr (EXT) if (x_.gate_mode != MST_GATE_NONE) {
-            const uint4* g4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x_.gate) + (long long)row * x_.ld_gate + n);
+          if constexpr (EXT) {
+            const bool wide_g = CH >= 16 && ((uintptr_t)(x_.ld_gate * 2) & 31) == 0;
+            auto load_row = [&](const void* base, uint32_t (&w)[CH / 2]) {  // CH bf16 of this row, as packed pairs
+              const bf16* gp = reinterpret_cast<const bf16*>(base) + (long long)row * x_.ld_gate + n;
+              if (wide_g && (reinterpret_cast<uintptr_t>(base) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              const uint4 gv = g4[j];
-              const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                for (int j = 0; j < CH / 16; ++j) {
+                  uint32_t t8[8];
+                  ld_global_256(gp + 16 * j, t8);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+                  for (int e = 0; e < 8; ++e) w[8 * j + e] = t8[e];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) {
+                  const uint4 t4 = reinterpret_cast<const uint4*>(gp)[j];
+                  w[4 * j] = t4.x; w[4 * j + 1] = t4.y; w[4 * j + 2] = t4.z; w[4 * j + 3] = t4.w;
+                }
+              }
+            };
+            if (x_.gate_mode != MST_GATE_NONE) {
+              uint32_t gw[CH / 2];
+              load_row(x_.gate, gw);
+#pragma unroll
+              for (int e = 0; e < CH / 2; ++e) {
                 const float g0 = __uint_as_float(gw[e] << 16), g1 = __uint_as_float(gw[e] & 0xffff0000u);
                 if (x_.gate_mode == MST_GATE_RELU) {
-                  x[8 * j + 2 * e] = g0 > 0.f ? x[8 * j + 2 * e] : 0.f;
-                  x[8 * j + 2 * e + 1] = g1 > 0.f ? x[8 * j + 2 * e + 1] : 0.f;
+                  x[2 * e] = g0 > 0.f ? x[2 * e] : 0.f;
+                  x[2 * e + 1] = g1 > 0.f ? x[2 * e + 1] : 0.f;
                 } else {
-                  x[8 * j + 2 * e] *= gelu_erf_grad(g0);
-                  x[8 * j + 2 * e + 1] *= gelu_erf_grad(g1);
+                  x[2 * e] *= gelu_erf_grad(g0);
+                  x[2 * e + 1] *= gelu_erf_grad(g1);
                 }
               }
             }
-          }
-          if constexpr (EXT) if (x_.add16) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x_.add16) + (long long)row * x_.ld_gate + n);
+            if (x_.add16) {
+              uint32_t aw[CH / 2];
+              load_row(x_.add16, aw);
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              const uint4 av = a4[j];
-              const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                x[8 * j + 2 * e] += __uint_as_float(aw[e] << 16);
-                x[8 * j + 2 * e + 1] += __uint_as_float(aw[e] & 0xffff0000u);
+              for (int e = 0; e < CH / 2; ++e) {
+                x[2 * e] += __uint_as_float(aw[e] << 16);
+                x[2 * e + 1] += __uint_as_float(aw[e] & 0xffff0000u);
               }
             }
           }
@@ -364,7 +402,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
 #pragma unroll
             for (int j = 0; j < CH; ++j) x[j] *= rs;
           }
-          if (p.res) {
+          if (p.res && wideres) {
+            const float* rp = p.res + (long long)row * p.ld_res + n;
+            const float* mp = p.mul ? p.mul + (long long)row * p.ld_res + n : nullptr;
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              float r[8];
+              ld_global_256f(rp + 8 * j, r);
+              if (mp) {
+                float m[8];
+                ld_global_256f(mp + 8 * j, m);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[8 * j + e] += r[e] * m[e];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[8 * j + e] += r[e];
+              }
+            }
+          } else if (p.res) {
             const float4* r4 = reinterpret_cast<const float4*>(p.res + (long long)row * p.ld_res + n);
             if (p.mul) {
               const float4* m4 = reinterpret_cast<const float4*>(p.mul + (long long)row * p.ld_res + n);
@@ -386,12 +441,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
             for (int j = 0; j < CH; ++j)
               if (n + j < p.n_real) p.out_f32[nchw_base + (long long)(n + j) * hw] = x[j];
           } else {
-            if (p.out_f32) {
+            if (p.out_f32 && wide32) {
+              float* op = p.out_f32 + (long long)row * p.ld_out32 + n;
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) st_global_256f(op + 8 * j, x + 8 * j);
+            } else if (p.out_f32) {
               float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ld_out32 + n);
 #pragma unroll
               for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             }
-            if (p.out_bf16) {
+            if (p.out_bf16 && wide16) {
+              bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n;
+#pragma unroll
+              for (int j = 0; j < CH / 16; ++j) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(x[16 * j + 2 * e], x[16 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                st_global_256(op + 16 * j, pk);
+              }
+            } else if (p.out_bf16) {
               uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n);
 #pragma unroll
               for (int j = 0; j < CH / 8; ++j) {

@@ -259,6 +259,9 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       __syncwarp();
       tc_fence_after();
       constexpr int CPW = C / 2;
+      const bool wide_res = p.res && ((reinterpret_cast<uintptr_t>(p.res) | (uintptr_t)(p.ld_res * 4)) & 31) == 0;
+      const bool wide_o32 = p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) | (uintptr_t)(p.ld_out32 * 4)) & 31) == 0;
+      const bool wide_o16 = p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
       const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + half * CPW;
 #pragma unroll 1
       for (int col0 = 0; col0 < CPW; col0 += 32) {
@@ -275,30 +278,62 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         float x[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) x[e] = __uint_as_float(v[e]) + b2_s[n + e];
+        // 256-bit accesses (one 32-byte sector per lane and instruction) when the row segments are 32-byte aligned
         if (p.res) {
-          const float4* r4 = reinterpret_cast<const float4*>(p.res + (long long)row * p.ld_res + n);
+          const float* rp = p.res + (long long)row * p.ld_res + n;
+          if (wide_res) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 r = r4[e];
-            x[4 * e] += r.x; x[4 * e + 1] += r.y; x[4 * e + 2] += r.z; x[4 * e + 3] += r.w;
+            for (int e = 0; e < 4; ++e) {
+              float r[8];
+              ld_global_256f(rp + 8 * e, r);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) x[8 * e + q] += r[q];
+            }
+          } else {
+            const float4* r4 = reinterpret_cast<const float4*>(rp);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 r = r4[e];
+              x[4 * e] += r.x; x[4 * e + 1] += r.y; x[4 * e + 2] += r.z; x[4 * e + 3] += r.w;
+            }
           }
         }
         if (p.out_f32) {
-          float4* o4 = reinterpret_cast<float4*>(p.out_f32 + (long long)row * p.ld_out32 + n);
+          float* op = p.out_f32 + (long long)row * p.ld_out32 + n;
+          if (wide_o32) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o4[e] = make_float4(x[4 * e], x[4 * e + 1], x[4 * e + 2], x[4 * e + 3]);
+            for (int e = 0; e < 4; ++e) st_global_256f(op + 8 * e, x + 8 * e);
+          } else {
+            float4* o4 = reinterpret_cast<float4*>(op);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o4[e] = make_float4(x[4 * e], x[4 * e + 1], x[4 * e + 2], x[4 * e + 3]);
+          }
         }
         if (p.out_bf16) {
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n);
+          bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n;
+          if (wide_o16) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint32_t pk[4];
+            for (int e = 0; e < 2; ++e) {
+              uint32_t pk[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * e + 2 * q], x[8 * e + 2 * q + 1]);
-              pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int q = 0; q < 8; ++q) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[16 * e + 2 * q], x[16 * e + 2 * q + 1]);
+                pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              st_global_256(op + 16 * e, pk);
             }
-            o4[e] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * e + 2 * q], x[8 * e + 2 * q + 1]);
+                pk[q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              o4[e] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
         }
       }
