@@ -98,6 +98,12 @@ int mst_gemm(const MstGemm* g, void* stream);
 int mst_conv3x3_band(const MstGemm* g, void* stream);
 int mst_conv3x3_band_supported(int N, int Cin, int H, int W);
 
+/* Row-streaming variant for the thin layers (Cin in {32,64}, N <= 64 in one tile, W % 128 == 0; decoder.py:39-54 and
+ * VGG conv1_2): the padded input rows stream through a shared-memory ring while producers, the MMA issuer and the
+ * epilogue run concurrently (warp-specialised), the [N x 9 Cin] weights stay resident in shared memory. */
+int mst_conv3x3_rows(const MstGemm* g, void* stream);
+int mst_conv3x3_rows_supported(int N, int Cin, int H, int W);
+
 /* ------------------------------------------------------------------------------------------
  * Fused transformer MLP (torchvision ops/misc.py:264-306 MLP as used at style_transformer.py:366,839-841,991
  * and in the tv Swin blocks):  out = res + fc2(GELU_erf(fc1(A) + b1)) + b2  with the [M x 4C] hidden activation

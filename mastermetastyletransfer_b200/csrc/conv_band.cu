@@ -14,6 +14,7 @@
 #include "../../include/mst_b200.h"
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace mst {
 
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[CB_MAX_BIAS];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
   const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t halo_base = ring_base + g.wst * B_STAGE_BYTES;
   const int cpp = p.Cin >> 3;            // 16-byte chunks per pixel
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
         const int s = it % g.wst;
         mbar_wait(smem_u32(&full_bar[s]), (it / g.wst) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        {  // whole warp, warp-uniform values, one lane elected inside the asm (uniform-register issue loop)
           const uint32_t b_stage = ring_base + s * B_STAGE_BYTES;
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
@@ -177,12 +178,11 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
             const uint64_t bd = umma_desc_sw128(b_stage + j * 32);
             const uint32_t a0 = halo_base + (uint32_t)(chunk0 * g.npx + ky * g.Wp + kx) * 16u;
             for (int st = 0; st < g.NS; ++st)
-              umma_bf16(tmem_base + st * BN, umma_desc_none(a0 + (uint32_t)st * 2048u, lbo, 128u), bd, idesc, ks != 0);
+              umma_bf16_pred(tmem_base + st * BN, umma_desc_none(a0 + (uint32_t)st * 2048u, lbo, 128u), bd, idesc, ks != 0);
           }
-          umma_commit(smem_u32(&empty_bar[s]));
-          if (kb == nkb - 1) umma_commit(smem_u32(&accum_bar));
+          umma_commit_pred(smem_u32(&empty_bar[s]));
+          if (kb == nkb - 1) umma_commit_pred(smem_u32(&accum_bar));
         }
-        __syncwarp();
       }
     }
     wit += nkb;
@@ -349,6 +349,376 @@ static int launch_band(const MstGemm& g, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+
+// =====================================================================================================
+// Row-streaming variant for the thin layers (Cin <= 64, one n-tile, W a multiple of 128).
+//
+// The band kernel above runs load -> MMA -> epilogue one after the other per band; for the thin layers of the
+// CNN decoder (64->64, 64->32 at 128^2; 32->32, 32->3 at 256^2) and VGG conv1_2 that serial chain, not HBM or
+// the tensor pipe, set the time (ncu: tensor pipe 9 %, dram 6 %).  Here the image is a STREAM of padded input
+// rows through a shared-memory ring and the three phases run concurrently, warp-specialised:
+//
+//   warps 0-7   epilogue   : TMEM -> bias / activation -> global, one finished output row at a time
+//   warps 8-14  producers  : one padded input row per ring slot with cp.async (reflect / zero padding and the
+//                            nearest-x2 upsample folded into the source address), asynchronous mbarrier arrival
+//   warp  15    MMA issuer : output row y = 9 taps x Cin/16 k-steps x W/128 strips of tcgen05.mma reading ring
+//                            rows y-1, y, y+1 through shifted SWIZZLE_NONE descriptors; accumulators rotate
+//                            through NACC TMEM buffers
+//
+// The whole [N x 9 Cin] weight matrix stays resident in shared memory (fetched once per CTA).  Each CTA owns a
+// contiguous run of output rows (over all images), so every input row is fetched from L2/HBM once per CTA that
+// needs it (3 extra rows per run) and each strip is exactly one 128-pixel half/whole row: no padded-raster waste.
+// Ring layout: plane c (16-byte channel chunk) x [slot][padded pixel] x 16 B -- for one chunk, 8 consecutive
+// pixels are one 128-byte core matrix (SBO = 128 B), the next chunk is LBO = plane bytes further.
+constexpr int RS_EPI_WARPS = 8;
+constexpr int RS_PROD_WARPS = 7;
+constexpr int RS_MMA_WARPS = 1;
+constexpr int RS_THREADS = (RS_EPI_WARPS + RS_PROD_WARPS + RS_MMA_WARPS) * 32;
+constexpr int RS_MAX_RING = 16;
+
+struct RowsGeom {
+  int ring;         // ring slots (padded input rows resident)
+  int spr;          // 128-pixel strips per output row (W / 128)
+  int nacc;         // TMEM accumulator buffers
+  int tmem_cols;    // allocated TMEM columns (power of two >= nacc * spr * BN)
+  int rows_total;   // B * H output rows
+  int rows_per_cta;
+  int plane_bytes;  // ring * (W + 2) * 16
+  int mode;         // experiment switch (MST_ROWS_MODE)
+};
+
+template <int BN, int CIN>
+__global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore p, const RowsGeom g) {
+  constexpr int CPP = CIN / 8;    // 16-byte chunks per pixel
+  constexpr int KPT = CIN / 16;   // K=16 steps per tap
+  constexpr int TOTAL_KS = 9 * KPT;
+  constexpr int NKB = (9 * CIN + 63) / 64;
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
+  constexpr int NCC = BN / CH;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[RS_MAX_RING];
+  __shared__ uint64_t free_bar[RS_MAX_RING];
+  __shared__ uint64_t acc_full[4];
+  __shared__ uint64_t acc_empty[4];
+  __shared__ uint64_t w_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[BN];
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
+  const uint32_t w_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_base = w_base + NKB * B_STAGE_BYTES;
+  const int Wp = p.W + 2;
+  const int r_begin = blockIdx.x * g.rows_per_cta;
+  const int r_end = min(r_begin + g.rows_per_cta, g.rows_total);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.ring; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), RS_PROD_WARPS * 32);
+      mbar_init(smem_u32(&free_bar[s]), RS_MMA_WARPS);
+    }
+    for (int b = 0; b < g.nacc; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), RS_MMA_WARPS);
+      mbar_init(smem_u32(&acc_empty[b]), RS_EPI_WARPS);
+    }
+    mbar_init(smem_u32(&w_bar), 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
+  if (warp == RS_EPI_WARPS + RS_PROD_WARPS) {
+    tmem_alloc(smem_u32(&tmem_base_slot), g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int acc_cols = g.spr * BN;
+
+  if (warp >= RS_EPI_WARPS && warp < RS_EPI_WARPS + RS_PROD_WARPS) {
+    // =========================== producers ===========================
+    const int t = threadIdx.x - RS_EPI_WARPS * 32;
+    if (t == 0) {  // resident weights, once
+      cb_arrive_expect_tx(smem_u32(&w_bar), NKB * B_STAGE_BYTES);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wt);
+      for (int kb = 0; kb < NKB; ++kb)
+        cb_bulk_g2s(w_base + kb * B_STAGE_BYTES, wsrc + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&w_bar));
+    }
+    const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
+    const int Hs = p.upsample ? (p.H >> 1) : p.H;
+    const int Ws = p.upsample ? (p.W >> 1) : p.W;
+    const int row_chunks = Wp * CPP;
+    // this thread's copies are the same for every row: chunk idx = t + k * NPROD -> (padded column, channel chunk);
+    // source element offset inside the source row (-1 = zero fill) and destination byte offset inside the ring row
+    constexpr int NPROD = RS_PROD_WARPS * 32;
+    constexpr int MAXK = (514 * CPP + NPROD - 1) / NPROD;  // W <= 512
+    int src_off[MAXK];
+    uint32_t dst_off[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+      const int idx = t + k * NPROD;
+      const int col = idx / CPP;
+      const int c = idx - col * CPP;
+      int xx = col - 1;
+      bool valid = idx < row_chunks;
+      if (p.pad_mode == 1) xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+      else valid = valid && (unsigned)xx < (unsigned)p.W;
+      if (p.upsample) xx >>= 1;
+      src_off[k] = valid ? xx * CIN + c * 8 : -1;
+      dst_off[k] = (uint32_t)c * (uint32_t)g.plane_bytes + (uint32_t)col * 16u;
+    }
+    const int nk = (row_chunks - t + NPROD - 1) / NPROD;  // copies this thread makes per row
+    int slot = 0;
+    const bool prof = (g.mode & 8) != 0;
+    long long t_wait = 0, t_all = prof ? clock64() : 0;
+    uint32_t fphase = 1;  // a fresh free_bar passes a wait on parity 1
+    int b = r_begin / p.H;
+    int y = r_begin - b * p.H;
+    for (int r = r_begin; r < r_end; ++r) {
+      const int nload = (r == r_begin || y == 0) ? 3 : 1;
+      for (int j = 3 - nload; j < 3; ++j) {
+        int yy = y + j - 1;  // padded row -1 .. H
+        bool vrow = true;
+        if (p.pad_mode == 1) yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+        else vrow = (unsigned)yy < (unsigned)p.H;
+        if (p.upsample) yy >>= 1;
+        const bf16* rowsrc = Abase + ((long long)b * Hs + (vrow ? yy : 0)) * Ws * CIN;
+        long long tp0 = prof ? clock64() : 0;
+        mbar_wait(smem_u32(&free_bar[slot]), fphase);
+        if (prof) t_wait += clock64() - tp0;
+        const uint32_t rowdst = ring_base + (uint32_t)(slot * Wp) * 16u;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+          if (k < nk) {
+            const bool valid = vrow && src_off[k] >= 0;
+            cp_async16(rowdst + dst_off[k], valid ? rowsrc + src_off[k] : Abase, valid);
+          }
+        }
+        cp_async_mbar_arrive_noinc(smem_u32(&full_bar[slot]));
+        if (++slot == g.ring) { slot = 0; fphase ^= 1; }
+      }
+      if (++y == p.H) { y = 0; ++b; }
+    }
+    cp_async_wait_all();
+    if (prof && blockIdx.x == 1 && t == 0) printf("rows prof producer: total %lld wait_free %lld rows %d\n", clock64() - t_all, t_wait, r_end - r_begin);
+  } else if (warp == RS_EPI_WARPS + RS_PROD_WARPS) {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs this loop convergently on warp-uniform values (kernel parameters, blockIdx, loop counters);
+    // umma_bf16_pred / umma_commit_pred elect one lane inside the asm.  ptxas then keeps the descriptors in uniform
+    // registers and emits back-to-back UTCHMMA with one uniform add in between -- issuing from inside an
+    // `if (lane == 0)` branch instead costs ~15 instructions (register -> uniform-register broadcasts in an elect
+    // loop) per MMA, more than these small (N <= 64) MMAs take to execute.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    const uint32_t lbo16 = (uint32_t)g.plane_bytes >> 4;
+    constexpr uint32_t a_hi = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
+    constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t row16 = (uint32_t)Wp;                               // one ring row in address-field units (16 B)
+    const uint32_t a_lo_base = ((ring_base & 0x3FFFFu) >> 4) | (lbo16 << 16);
+    mbar_wait(smem_u32(&w_bar), 0);
+    int rcount = 0;                 // output rows issued
+    int y = r_begin % p.H;
+    int s_new = 0;                  // ring slot of the next padded row to arrive
+    uint32_t full_phase = 0;
+    int s0 = 0, s1 = 0, s2 = 0;     // ring slots of padded rows y-1, y, y+1
+    int buf = 0;
+    uint32_t acc_phase = 1;         // a fresh acc_empty passes a wait on parity 1
+    for (int r = r_begin; r < r_end; ++r, ++rcount) {
+      const int nload = (r == r_begin || y == 0) ? 3 : 1;
+      for (int j = 0; j < nload; ++j) {
+        mbar_wait(smem_u32(&full_bar[s_new]), full_phase);
+        s0 = s1; s1 = s2; s2 = s_new;
+        if (++s_new == g.ring) { s_new = 0; full_phase ^= 1; }
+      }
+      mbar_wait(smem_u32(&acc_empty[buf]), acc_phase);
+      fence_proxy_async_smem();
+      tc_fence_after();
+      if (++y == p.H) y = 0;
+      const bool last_of_run = (r + 1 == r_end || y == 0);
+      const uint32_t a_row0 = a_lo_base + (uint32_t)s0 * row16, a_row1 = a_lo_base + (uint32_t)s1 * row16,
+                     a_row2 = a_lo_base + (uint32_t)s2 * row16;
+      for (int st = 0; st < g.spr; ++st) {
+        const uint32_t d_tmem = tmem_base + buf * acc_cols + st * BN;
+#pragma unroll
+        for (int ks = 0; ks < TOTAL_KS; ++ks) {
+          const int tap = ks / KPT, kk = ks - tap * KPT;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          // +1 in the address field = 16 bytes = one pixel; a K=16 step further = two channel-chunk planes
+          const uint32_t a_lo = (ky == 0 ? a_row0 : (ky == 1 ? a_row1 : a_row2)) + (uint32_t)(st * 128 + kx) + (uint32_t)(kk * 2) * lbo16;
+          const uint32_t b_lo = b_lo0 + (uint32_t)(((ks >> 2) * B_STAGE_BYTES + (ks & 3) * 32) >> 4);
+          umma_bf16_pred(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, ks != 0);
+        }
+      }
+      umma_commit_pred(smem_u32(&acc_full[buf]));
+      umma_commit_pred(smem_u32(&free_bar[s0]));  // padded row y-1 is not needed again
+      if (last_of_run) {                           // last row of an image / of this CTA's run: rows y and y+1 die too
+        umma_commit_pred(smem_u32(&free_bar[s1]));
+        umma_commit_pred(smem_u32(&free_bar[s2]));
+      }
+      if (++buf == g.nacc) { buf = 0; acc_phase ^= 1; }
+    }
+    tc_fence_before();
+  } else {
+    // =========================== epilogue (warps 0-7) ===========================
+    const int quad = warp & 3, half = warp >> 2;
+    const bool prof = (g.mode & 8) != 0;
+    long long t_wait = 0, t_all = prof ? clock64() : 0;
+    const int items = g.spr * NCC;
+    const long long hw = (long long)p.H * p.W;
+    const bool wide16 = p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
+    int rcount = 0;
+    for (int r = r_begin; r < r_end; ++r, ++rcount) {
+      const int buf = rcount % g.nacc;
+      long long te0 = prof ? clock64() : 0;
+      if (lane == 0) mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)(rcount / g.nacc)) & 1u);
+      __syncwarp();
+      if (prof) t_wait += clock64() - te0;
+      tc_fence_after();
+      const int last_item = half + ((items - 1 - half) / 2) * 2;  // this warp's last item (< half: none)
+      if (half >= items) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        continue;
+      }
+#pragma unroll 1
+      for (int item = half; item < items; item += 2) {
+        const int st = item / NCC, cc = item - st * NCC;
+        uint32_t v[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * acc_cols + st * BN + cc * CH;
+        if constexpr (CH == 32) tmem_ld32(taddr, v);
+        else tmem_ld16(taddr, v);
+        tmem_wait_ld();
+        if (item == last_item) {  // accumulator drained by this warp: hand it back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+        const int x = st * 128 + quad * 32 + lane;
+        const int n = cc * CH;
+        float xv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          xv[j] = __uint_as_float(v[j]) + bias_s[n + j];
+          if (p.act == MST_ACT_RELU) xv[j] = fmaxf(xv[j], 0.0f);
+          else if (p.act == MST_ACT_GELU) xv[j] = gelu_erf(xv[j]);
+        }
+        const long long pix = (long long)r * p.W + x;
+        if (p.out_nchw) {
+          const int b = r / p.H;
+          const long long base = (long long)b * p.n_real * hw + (pix - (long long)b * hw);
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.n_real) p.out_f32[base + (long long)(n + j) * hw] = xv[j];
+        } else {
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out32 + n);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]);
+          }
+          if (p.out_bf16) {
+            bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + pix * p.ld_out16 + n;
+            if (wide16) {
+#pragma unroll
+              for (int j = 0; j < CH / 16; ++j) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(xv[16 * j + 2 * e], xv[16 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                st_global_256(op + 16 * j, pk);
+              }
+            } else {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(xv[8 * j + 2 * e], xv[8 * j + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                o4[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (prof && blockIdx.x == 1 && lane == 0 && (warp == 0 || warp == 7)) printf("rows prof epilogue warp %d: total %lld wait_acc_full %lld\n", warp, clock64() - t_all, t_wait);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == RS_EPI_WARPS + RS_PROD_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, g.tmem_cols);
+  }
+}
+
+static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
+  if (g.W % 128 != 0 || g.W > 512 || g.N != BN || BN > 64) return false;
+  if (g.Cin != 32 && g.Cin != 64) return false;
+  const int nkb = (9 * g.Cin + 63) / 64;
+  if (g.k_pad != nkb * 64) return false;
+  const long long budget = 220LL * 1024 - 1024 - (long long)nkb * BN * 128;
+  const long long row_bytes = (long long)(g.W + 2) * g.Cin * 2;
+  long long ring = budget / row_bytes;
+  if (ring > 12) ring = 12;
+  if (ring < 4) return false;
+  out.ring = (int)ring;
+  out.spr = g.W / 128;
+  const int acc_cols = out.spr * BN;
+  if (acc_cols > 256) return false;
+  int nacc = 256 / acc_cols;
+  if (nacc > 4) nacc = 4;
+  if (nacc < 2) nacc = 2;
+  out.nacc = nacc;
+  int cols = 32;
+  while (cols < nacc * acc_cols) cols <<= 1;
+  out.tmem_cols = cols;
+  out.plane_bytes = out.ring * (g.W + 2) * 16;
+  { const char* e = getenv("MST_ROWS_MODE"); out.mode = e ? atoi(e) : 0; }
+  if (out.plane_bytes >= (1 << 18)) return false;
+  const int B = g.M / (g.H * g.W);
+  out.rows_total = B * g.H;
+  const int sms = cb_num_sms();
+  out.rows_per_cta = (out.rows_total + sms - 1) / sms;
+  const int min_rows = out.rows_total < 4 ? out.rows_total : 4;  // a run re-fetches 2 extra input rows: keep runs >= 4 rows
+  if (out.rows_per_cta < min_rows) out.rows_per_cta = min_rows;
+  return true;
+}
+
+template <int BN, int CIN>
+static int launch_rows(const MstGemm& g, const RowsGeom& geo, cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)((9 * CIN + 63) / 64) * BN * 128 + (size_t)geo.ring * (g.W + 2) * CIN * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((geo.rows_total + geo.rows_per_cta - 1) / geo.rows_per_cta);
+  GemmCore core;
+  memcpy(&core, &g, sizeof(GemmCore));
+  conv_rows_kernel<BN, CIN><<<grid, RS_THREADS, smem, st>>>(core, geo);
+  return (int)cudaGetLastError();
+}
+
+// Row-streaming kernel when the shape allows it, else the band kernel.
+static int try_launch_rows(const MstGemm& g, cudaStream_t st, bool& handled) {
+  RowsGeom geo;
+  handled = true;
+  const int bn = mst_gemm_tile_n(g.N);
+  if (!plan_rows(g, bn, geo)) { handled = false; return 0; }
+  if (bn == 64 && g.Cin == 64) return launch_rows<64, 64>(g, geo, st);
+  if (bn == 32 && g.Cin == 64) return launch_rows<32, 64>(g, geo, st);
+  if (bn == 32 && g.Cin == 32) return launch_rows<32, 32>(g, geo, st);
+  if (bn == 16 && g.Cin == 32) return launch_rows<16, 32>(g, geo, st);
+  handled = false;
+  return 0;
+}
+
 }  // namespace mst
 
 using namespace mst;
@@ -384,4 +754,36 @@ extern "C" int mst_conv3x3_band(const MstGemm* g, void* stream) {
     case 32: return launch_band<32>(*g, st);
     default: return launch_band<16>(*g, st);
   }
+}
+
+static bool rows_instantiated(int bn, int Cin) {
+  return (bn == 64 && Cin == 64) || (bn == 32 && Cin == 64) || (bn == 32 && Cin == 32) || (bn == 16 && Cin == 32);
+}
+
+extern "C" int mst_conv3x3_rows_supported(int N, int Cin, int H, int W) {
+  if (N <= 0 || N % 16 || Cin <= 0 || H < 2 || W < 2) return 0;
+  MstGemm g{};
+  g.N = N; g.Cin = Cin; g.H = H; g.W = W; g.M = H * W;
+  g.k_pad = (9 * Cin + 63) / 64 * 64;
+  RowsGeom geo;
+  const int bn = mst_gemm_tile_n(N);
+  return plan_rows(g, bn, geo) && rows_instantiated(bn, Cin) ? 1 : 0;
+}
+
+extern "C" int mst_conv3x3_rows(const MstGemm* g, void* stream) {
+  if (!g || !g->A || !g->Wt) return MST_ERR_BAD_ARG;
+  if (g->a_mode != MST_A_CONV3X3 || g->M <= 0 || g->N <= 0 || g->K != 9 * g->Cin || g->k_pad % 64 || g->k_pad < g->K) return MST_ERR_BAD_ARG;
+  if (g->H < 2 || g->W < 2 || g->M % (g->H * g->W) != 0) return MST_ERR_BAD_ARG;
+  if (g->upsample && ((g->H | g->W) & 1)) return MST_ERR_BAD_ARG;
+  if (g->res || g->mul || g->gate || g->add16 || g->out_pre16 || g->row_scale || g->conv_full) return MST_ERR_UNSUPPORTED;
+  if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
+  if (g->out_nchw) {
+    if (!g->out_f32 || g->n_real <= 0 || g->n_real > g->N) return MST_ERR_BAD_ARG;
+  } else {
+    if (g->out_f32 && g->ld_out32 % 4) return MST_ERR_BAD_ARG;
+    if (g->out_bf16 && g->ld_out16 % 8) return MST_ERR_BAD_ARG;
+  }
+  bool handled = false;
+  const int rc = try_launch_rows(*g, (cudaStream_t)stream, handled);
+  return handled ? rc : MST_ERR_UNSUPPORTED;
 }

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[MAX_BIAS];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for ptxas (uniform-register MMA issue loop)
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
@@ -250,18 +250,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
         mbar_wait(smem_u32(&full_bar[s]), cphase);
         if (++stage == STAGES) { stage = 0; cphase ^= 1; }
         tc_fence_after();
-        if (lane == 0) {
+        {
+          // The whole warp runs this convergently on warp-uniform values; one lane is elected inside the asm.  ptxas
+          // then forms the descriptors in uniform registers and emits back-to-back UTCHMMA (issuing from an
+          // `if (lane == 0)` branch costs ~15 instructions of register -> uniform-register broadcasts per MMA).
           const uint32_t a_stage = ring_base + s * stage_bytes;
           const uint32_t b_stage = resident ? smem_base + kb * Cfg::B_STAGE_BYTES : a_stage + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, umma_desc_sw128(a_stage + k * 32), umma_desc_sw128(b_stage + k * 32), idesc, (kb | k) != 0);
+            umma_bf16_pred(d_tmem, umma_desc_sw128(a_stage + k * 32), umma_desc_sw128(b_stage + k * 32), idesc, (kb | k) != 0);
           }
-          umma_commit(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
-          if (kb == nkb - 1) umma_commit(smem_u32(&tmem_full_bar[buf]));  // accumulator complete
+          umma_commit_pred(smem_u32(&empty_bar[s]));                          // stage reusable once these MMAs retire
+          if (kb == nkb - 1) umma_commit_pred(smem_u32(&tmem_full_bar[buf]));  // accumulator complete
         }
-        __syncwarp();
       }
     }
     tc_fence_before();

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
   __shared__ float b1_s[1024];
   __shared__ float b2_s[256];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
   const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t hs_base = a_base + Cfg::A_BYTES;
   const uint32_t ring_base = hs_base + 2 * Cfg::HS_BYTES;
@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
     }
   } else if (warp == 12) {
     // =========================== MMA issuer ===========================
+    // whole warp, convergent, warp-uniform values; one lane elected inside umma_bf16_pred / umma_commit_pred so that
+    // ptxas keeps the descriptors in uniform registers (see gemm_tc.cu)
     constexpr uint32_t idesc1 = umma_idesc_bf16(128, ML_HC);
     constexpr uint32_t idesc2 = umma_idesc_bf16(128, C);
     int ws = 0, lt = 0;
@@ -146,27 +148,25 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       for (int s = 0; s < Cfg::S2; ++s, ++ws) {
         int slot;
         wait_stage(slot);
-        if (lane == 0) {
+        {
           const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
           if constexpr (C == 256) {  // stage = k-block s of the chunk: [256 x 64]
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + s * 16384 + k * 32), umma_desc_sw128(wb + k * 32), idesc2,
+              umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + s * 16384 + k * 32), umma_desc_sw128(wb + k * 32), idesc2,
                         (j | s | k) != 0);
           } else {  // stage = both k-blocks: 2 x [128 x 64]
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + kb * 16384 + k * 32), umma_desc_sw128(wb + kb * 16384 + k * 32),
+                umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + kb * 16384 + k * 32), umma_desc_sw128(wb + kb * 16384 + k * 32),
                           idesc2, (j | kb | k) != 0);
           }
-          umma_commit(smem_u32(&w_empty[slot]));
+          umma_commit_pred(smem_u32(&w_empty[slot]));
         }
-        __syncwarp();
       }
-      if (lane == 0) umma_commit(smem_u32(&hs_empty[buf]));
-      __syncwarp();
+      umma_commit_pred(smem_u32(&hs_empty[buf]));
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       mbar_wait(smem_u32(&a_full), lt & 1);
@@ -179,30 +179,25 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         for (int s = 0; s < Cfg::S1; ++s, ++ws) {
           int slot;
           wait_stage(slot);
-          if (lane == 0) {
+          {
             const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
 #pragma unroll
             for (int kb2 = 0; kb2 < 2; ++kb2) {
               const int kb = s * 2 + kb2;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + buf * ML_HC, umma_desc_sw128(a_base + kb * 16384 + k * 32),
+                umma_bf16_pred(tmem_base + buf * ML_HC, umma_desc_sw128(a_base + kb * 16384 + k * 32),
                           umma_desc_sw128(wb + kb2 * 16384 + k * 32), idesc1, (kb | k) != 0);
             }
-            umma_commit(smem_u32(&w_empty[slot]));
+            umma_commit_pred(smem_u32(&w_empty[slot]));
           }
-          __syncwarp();
         }
-        if (lane == 0) umma_commit(smem_u32(&acc1_full[buf]));
-        __syncwarp();
+        umma_commit_pred(smem_u32(&acc1_full[buf]));
         if (t >= 1) mma2(t - 1);
       }
       mma2(NCH - 1);
-      if (lane == 0) {
-        umma_commit(smem_u32(&acc2_full));
-        umma_commit(smem_u32(&a_empty));
-      }
-      __syncwarp();
+      umma_commit_pred(smem_u32(&acc2_full));
+      umma_commit_pred(smem_u32(&a_empty));
     }
     tc_fence_before();
   } else {

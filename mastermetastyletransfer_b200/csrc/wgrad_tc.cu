@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const MstWgrad 
   __shared__ uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   int bid = blockIdx.x;
@@ -201,18 +201,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const MstWgrad 
       mbar_wait(smem_u32(&full_bar[s]), cphase);
       if (++stage == STAGES) { stage = 0; cphase ^= 1; }
       tc_fence_after();
-      if (lane == 0) {
+      {  // whole warp, warp-uniform values, one lane elected inside the asm (uniform-register issue loop, see gemm_tc.cu)
         const uint32_t a_stage = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t b_stage = a_stage + WG_A_BYTES;
 #pragma unroll
         for (int k = 0; k < WG_TOK / 16; ++k) {  // 16 tokens = two 8-row groups = 2048 bytes
-          umma_bf16(tmem_base, umma_desc_mn_sw128(a_stage + k * 2048, WG_PANEL), umma_desc_mn_sw128(b_stage + k * 2048, WG_PANEL),
-                    idesc, (blk | k) != 0);
+          umma_bf16_pred(tmem_base, umma_desc_mn_sw128(a_stage + k * 2048, WG_PANEL), umma_desc_mn_sw128(b_stage + k * 2048, WG_PANEL),
+                         idesc, (blk | k) != 0);
         }
-        umma_commit(smem_u32(&empty_bar[s]));
-        if (blk == nblk - 1) umma_commit(smem_u32(&tmem_full_bar));
+        umma_commit_pred(smem_u32(&empty_bar[s]));
+        if (blk == nblk - 1) umma_commit_pred(smem_u32(&tmem_full_bar));
       }
-      __syncwarp();
     }
     tc_fence_before();
   } else {

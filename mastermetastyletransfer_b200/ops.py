@@ -52,7 +52,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 
 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
-             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
+             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -166,7 +166,9 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         training_ext = training_ext or bool(g.conv_full)
     desc = f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}"
     flops = 2.0 * M * min(N, pm.N) * pm.K
-    if conv is not None and not training_ext and _use_band(conv, N):
+    if conv is not None and not training_ext and _use_rows(conv, N):
+        _launch("mst_conv3x3_rows", lambda: _lib.lib().mst_conv3x3_rows(C.byref(g), _stream()), flops=flops, desc=desc + " rows")
+    elif conv is not None and not training_ext and _use_band(conv, N):
         _launch("mst_conv3x3_band", lambda: _lib.lib().mst_conv3x3_band(C.byref(g), _stream()), flops=flops, desc=desc + " band")
     else:
         _launch("mst_gemm", lambda: _lib.lib().mst_gemm(C.byref(g), _stream()), flops=flops, desc=desc)
@@ -177,6 +179,20 @@ BAND_MAX_CIN = 64  # measured: from Cin = 128 up the gathered implicit GEMM is f
 
 def band_supported(n: int, cin: int, H: int, W: int) -> bool:
     return cin % 16 == 0 and bool(_lib.lib().mst_conv3x3_band_supported(n_pad_of(n), cin, H, W))
+
+
+def rows_supported(n: int, cin: int, H: int, W: int) -> bool:
+    return bool(_lib.lib().mst_conv3x3_rows_supported(n_pad_of(n), cin, H, W))
+
+
+def _use_rows(conv: dict, n_pad: int) -> bool:
+    impl = conv.get("impl", "auto")
+    if impl not in ("auto", "rows"):
+        return False
+    ok = bool(_lib.lib().mst_conv3x3_rows_supported(n_pad, conv["Cin"], conv["H"], conv["W"]))
+    if impl == "rows" and not ok:
+        raise ValueError("conv3x3 row-streaming kernel does not support this shape")
+    return ok
 
 
 def _use_band(conv: dict, n_pad: int) -> bool:

@@ -69,14 +69,18 @@ def test_gemm_epilogues():
     (2, 16, 16, 128, 128, "reflect", True, True), (1, 32, 32, 32, 32, "reflect", True, True),
     (2, 16, 16, 64, 128, "zeros", False, True), (1, 8, 8, 512, 512, "zeros", False, True),
     (3, 12, 20, 32, 64, "zeros", False, False), (1, 128, 128, 64, 64, "reflect", True, True),
-    (1, 256, 256, 32, 32, "reflect", False, True), (2, 30, 34, 64, 256, "zeros", False, True)])
-@pytest.mark.parametrize("impl", ["gather", "band"])
+    (1, 256, 256, 32, 32, "reflect", False, True), (2, 30, 34, 64, 256, "zeros", False, True),
+    (3, 128, 128, 64, 32, "zeros", False, True), (2, 256, 256, 32, 32, "zeros", True, True), (2, 6, 128, 64, 64, "reflect", False, False),
+    (5, 3, 512, 32, 32, "reflect", False, True), (40, 8, 128, 32, 16, "zeros", False, False), (2, 64, 256, 64, 64, "reflect", True, True)])
+@pytest.mark.parametrize("impl", ["gather", "band", "rows"])
 def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
     """H, W are the conv's output size; with up=True the stored input is [B,H/2,W/2,Cin].
     impl: gathered implicit GEMM (gemm_tc.cu) or the halo-band kernel (conv_band.cu)."""
     ops = _ops()
     if impl == "band" and not ops.band_supported(Cout, Cin, H, W):
         pytest.skip("no band plan for this shape (halo + weight ring exceed shared memory)")
+    if impl == "rows" and not ops.rows_supported(Cout, Cin, H, W):
+        pytest.skip("row-streaming kernel: Cin in {32,64}, Cout <= 64, W % 128 == 0 only")
     hs, ws = (H // 2, W // 2) if up else (H, W)
     x = _rand(B, hs, ws, Cin, seed=10).bfloat16()
     wt = _rand(Cout, Cin, 3, 3, seed=11, scale=(9 * Cin) ** -0.5)
@@ -96,10 +100,10 @@ def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
     assert torch.allclose(out.cpu(), ref, atol=3e-3, rtol=3e-3), (out.cpu() - ref).abs().max()
 
 
-@pytest.mark.parametrize("impl", ["gather", "band"])
+@pytest.mark.parametrize("impl", ["gather", "band", "rows"])
 def test_conv3x3_nchw_out(impl):
     ops = _ops()
-    B, H, W, Cin = 2, 32, 32, 32
+    B, H, W, Cin = (3, 20, 256, 32) if impl == "rows" else (2, 32, 32, 32)
     x = _rand(B, H, W, Cin, seed=13).bfloat16()
     wt = _rand(3, Cin, 3, 3, seed=14, scale=(9 * Cin) ** -0.5)
     bias = _rand(3, seed=15)

@@ -60,6 +60,13 @@ if which in ("conv", "all"):
     conv(32, 64, 128, 128)
     conv(32, 32, 256, 128)
     conv(32, 64, 128, 128, reflect=False)
+if which == "rows":
+    for impl in ("rows", "band"):
+        conv(32, 256, 32, 32, up=True, impl=impl)
+        conv(32, 256, 32, 16, impl=impl)
+        conv(32, 128, 64, 64, up=True, impl=impl)
+        conv(32, 128, 64, 32, impl=impl)
+        conv(96, 256, 64, 64, reflect=False, impl=impl)
 if which in ("band", "all"):
     for impl in ("band", "gather"):
         conv(32, 256, 32, 32, impl=impl)
