@@ -172,6 +172,12 @@ int mst_instnorm_apply(const float* x, const float* mean, const float* rstd, mst
  * img [B,3,S,S] fp32 NCHW -> x [B,S/4,S/4,128] fp32. */
 int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x,
                     int B, int S, void* stream);
+/* Same, with the first Swin block's norm1 (LayerNorm(128), gamma1/beta1) fused: y16 [B*(S/4)^2, 128] bf16 receives
+ * LN1(x) (NULL = not wanted).  S % 64 == 0 runs on the tensor cores (mma.sync bf16, image split hi+lo, bf16 weights)
+ * unless exact != 0; other sizes use the fp32 SIMT kernel followed by mst_layernorm. */
+int mst_patch_embed_ln(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x,
+                       const float* gamma1, const float* beta1, mst_bf16* y16, int B, int S, int exact, void* stream);
+
 
 /* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
 int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);

@@ -58,36 +58,51 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- InstanceNorm statistics
-// x [B,T,C] fp32.  CTA = (b, 32-channel group); 8 warps stride over T, lane = channel (128 B rows).
-// Two passes (mean, then centred second moment) as torch's InstanceNorm2d does (biased variance).
-__global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
-                                                             float* __restrict__ rstd, int T, int C, int twice) {
-  __shared__ float red[8][33];
+// x [B,T,C] fp32.  CTA = (b, 32-channel group); 16 warps stride over T, lane = channel (128 B rows), four rows in flight
+// per warp (the kernel is latency-bound: a CTA's slice is only T*128 B).  Two passes (mean, then centred second moment)
+// as torch's InstanceNorm2d does (biased variance); the second pass re-reads the slice from L1/L2.
+constexpr int IN_WARPS = 16;
+__global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
+                                                                        float* __restrict__ rstd, int T, int C, int twice) {
+  __shared__ float red[IN_WARPS][33];
   const int groups = C / 32;
   const int b = blockIdx.x / groups;
   const int c = (blockIdx.x - b * groups) * 32 + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* xb = x + (long long)b * T * C + c;
-  float s = 0.f;
-  for (int t = warp; t < T; t += 8) s += xb[(long long)t * C];
-  red[warp][lane] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int t = warp;
+  for (; t + 3 * IN_WARPS < T; t += 4 * IN_WARPS) {
+    s0 += xb[(long long)t * C];
+    s1 += xb[(long long)(t + IN_WARPS) * C];
+    s2 += xb[(long long)(t + 2 * IN_WARPS) * C];
+    s3 += xb[(long long)(t + 3 * IN_WARPS) * C];
+  }
+  for (; t < T; t += IN_WARPS) s0 += xb[(long long)t * C];
+  red[warp][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   float m = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) m += red[w][lane];
+  for (int w = 0; w < IN_WARPS; ++w) m += red[w][lane];
   m /= (float)T;
   __syncthreads();
-  float q = 0.f;
-  for (int t = warp; t < T; t += 8) {
-    const float d = xb[(long long)t * C] - m;
-    q += d * d;
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  t = warp;
+  for (; t + 3 * IN_WARPS < T; t += 4 * IN_WARPS) {
+    const float d0 = xb[(long long)t * C] - m, d1 = xb[(long long)(t + IN_WARPS) * C] - m;
+    const float d2 = xb[(long long)(t + 2 * IN_WARPS) * C] - m, d3 = xb[(long long)(t + 3 * IN_WARPS) * C] - m;
+    q0 += d0 * d0; q1 += d1 * d1; q2 += d2 * d2; q3 += d3 * d3;
   }
-  red[warp][lane] = q;
+  for (; t < T; t += IN_WARPS) {
+    const float d = xb[(long long)t * C] - m;
+    q0 += d * d;
+  }
+  red[warp][lane] = (q0 + q1) + (q2 + q3);
   __syncthreads();
   if (warp == 0) {
     float var = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) var += red[w][lane];
+    for (int w = 0; w < IN_WARPS; ++w) var += red[w][lane];
     var /= (float)T;
     float r = 1.0f / sqrtf(var + 1e-5f);
     if (twice) {
@@ -196,6 +211,145 @@ __global__ void __launch_bounds__(256, 1) patch_embed_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------- Swin patch embedding on the tensor cores
+// The 4x4/stride-4 conv is a [tokens x 48] . [48 x 128] GEMM: mma.sync m16n8k16 (bf16 in, fp32 accumulate), one warp per
+// 16 consecutive tokens of a patch row.  k = ci*16 + ky*4 + kx, so one k-step is one input channel and a thread's A
+// fragment is four float2 loads straight from the NCHW image (no staging).  The image is split hi + lo into two bf16
+// operands (16 mantissa bits), the weights are rounded to bf16 like every other layer's and live in registers as B
+// fragments.  LayerNorm(128) runs on the accumulator fragments (quad shuffles); with y16 != nullptr the first block's
+// norm1 is applied as well and written as the bf16 operand of its QKV projection (saves one full LayerNorm pass).
+MST_DEVINL uint32_t pe_pack(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+MST_DEVINL void pe_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ out,
+                                                                 const float* __restrict__ gamma1, const float* __restrict__ beta1,
+                                                                 bf16* __restrict__ y16, int S, int groups) {
+  __shared__ float2 prm[5][64];  // bias, gamma, beta, gamma1, beta1 as column pairs
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tg = lane & 3;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    prm[0][i] = make_float2(bias[2 * i], bias[2 * i + 1]);
+    prm[1][i] = make_float2(gamma[2 * i], gamma[2 * i + 1]);
+    prm[2][i] = make_float2(beta[2 * i], beta[2 * i + 1]);
+    prm[3][i] = y16 ? make_float2(gamma1[2 * i], gamma1[2 * i + 1]) : make_float2(0.f, 0.f);
+    prm[4][i] = y16 ? make_float2(beta1[2 * i], beta1[2 * i + 1]) : make_float2(0.f, 0.f);
+  }
+  uint32_t bw[3][16][2];  // B fragments: B[k][n] = W[n][ci*16 + k]
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float* wp = w + (nt * 8 + g) * 48 + ci * 16 + 2 * tg;
+      bw[ci][nt][0] = pe_pack(wp[0], wp[1]);
+      bw[ci][nt][1] = pe_pack(wp[8], wp[9]);
+    }
+  __syncthreads();
+  const int P = S >> 2;
+  const int gpr = P >> 4;  // 16-token groups per patch row
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // element offset (inside the image tensor) of this thread's first float2 of group gi: channel 0, patch row ky = tg>>1
+  auto src_of = [&](int gi) -> long long {
+    const int rowi = gi / gpr;          // b * P + py
+    const int px0 = (gi - rowi * gpr) << 4;
+    const int b = rowi / P, py = rowi - b * P;
+    return ((long long)b * 3 * S + py * 4 + (tg >> 1)) * S + (px0 + g) * 4 + (tg & 1) * 2;
+  };
+  const long long plane = (long long)S * S;
+  float2 nx[12];
+  auto fetch = [&](int gi) {
+    if (gi < groups) {
+      const float* p0 = img + src_of(gi);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* pc = p0 + ci * plane;
+        nx[ci * 4 + 0] = *reinterpret_cast<const float2*>(pc);                   // row g,   ky
+        nx[ci * 4 + 1] = *reinterpret_cast<const float2*>(pc + 32);              // row g+8 (8 tokens = 32 pixels further)
+        nx[ci * 4 + 2] = *reinterpret_cast<const float2*>(pc + 2 * S);           // row g,   ky + 2
+        nx[ci * 4 + 3] = *reinterpret_cast<const float2*>(pc + 2 * S + 32);      // row g+8, ky + 2
+      }
+    }
+  };
+  fetch(wid);
+  for (int gi = wid; gi < groups; gi += nwarps) {
+    float2 cur[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) cur[i] = nx[i];
+    fetch(gi + nwarps);
+    float acc[16][4];
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float2 bb = prm[0][nt * 4 + tg];
+      acc[nt][0] = bb.x; acc[nt][1] = bb.y; acc[nt][2] = bb.x; acc[nt][3] = bb.y;
+    }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = cur[ci * 4 + i];
+        const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y);
+        ah[i] = pe_pack(__bfloat162float(hx), __bfloat162float(hy));
+        al[i] = pe_pack(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        pe_mma(acc[nt], ah, bw[ci][nt][0], bw[ci][nt][1]);
+        pe_mma(acc[nt], al, bw[ci][nt][0], bw[ci][nt][1]);
+      }
+    }
+    const long long tok0 = (long long)gi * 16 + g;  // rows g and g+8 of the group
+    // ---- LayerNorm(128) of rows g / g+8 (fragment columns nt*8 + 2tg, +1; quad = the four tg lanes) ----
+    auto layer_norm = [&](int gsel, int bsel) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) { s0 += acc[nt][0] + acc[nt][1]; s1 += acc[nt][2] + acc[nt][3]; }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float m0 = s0 * (1.f / 128.f), m1 = s1 * (1.f / 128.f);
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const float a = acc[nt][0] - m0, b = acc[nt][1] - m0, c = acc[nt][2] - m1, d = acc[nt][3] - m1;
+        q0 += a * a + b * b; q1 += c * c + d * d;
+      }
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      const float r0 = rsqrtf(q0 * (1.f / 128.f) + 1e-5f), r1 = rsqrtf(q1 * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const float2 gm = prm[gsel][nt * 4 + tg], bt = prm[bsel][nt * 4 + tg];
+        acc[nt][0] = (acc[nt][0] - m0) * r0 * gm.x + bt.x; acc[nt][1] = (acc[nt][1] - m0) * r0 * gm.y + bt.y;
+        acc[nt][2] = (acc[nt][2] - m1) * r1 * gm.x + bt.x; acc[nt][3] = (acc[nt][3] - m1) * r1 * gm.y + bt.y;
+      }
+    };
+    layer_norm(1, 2);
+    float* o0 = out + tok0 * 128 + 2 * tg;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      *reinterpret_cast<float2*>(o0 + nt * 8) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(o0 + 8 * 128 + nt * 8) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    if (y16) {
+      layer_norm(3, 4);
+      bf16* y0 = y16 + tok0 * 128 + 2 * tg;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        *reinterpret_cast<uint32_t*>(y0 + nt * 8) = pe_pack(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(y0 + 8 * 128 + nt * 8) = pe_pack(acc[nt][2], acc[nt][3]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- packing / casts
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,7 +387,7 @@ extern "C" int mst_patch_merge_layernorm(const float* x, const float* gamma, con
 
 extern "C" int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream) {
   if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0) return MST_ERR_BAD_ARG;
-  instnorm_stats_kernel<<<B * (C / 32), 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice);
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice);
   return (int)cudaGetLastError();
 }
 
@@ -248,15 +402,35 @@ extern "C" int mst_instnorm_apply(const float* x, const float* mean, const float
 
 extern "C" int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta,
                                float* x, int B, int S, void* stream) {
+  return mst_patch_embed_ln(img, w, b, gamma, beta, x, nullptr, nullptr, nullptr, B, S, 0, stream);
+}
+
+extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float* b, const float* gamma, const float* beta,
+                                  float* x, const float* gamma1, const float* beta1, mst_bf16* y16, int B, int S, int exact,
+                                  void* stream) {
   if (!img || !w || !b || !gamma || !beta || !x || B <= 0 || S <= 0 || S % 4 != 0) return MST_ERR_BAD_ARG;
+  if (y16 && (!gamma1 || !beta1)) return MST_ERR_BAD_ARG;
   const long long total = (long long)B * (S / 4) * (S / 4);
-  const long long groups = (total + PE_TOK - 1) / PE_TOK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (S % 64 == 0 && !exact) {  // tensor-core path: 16-token groups inside a patch row
+    const long long groups = total / 16;
+    if (groups > 0x7fffffffLL) return MST_ERR_BAD_ARG;
+    const long long want = (groups + 7) / 8;
+    const unsigned grid = (unsigned)(want < sms ? want : sms);
+    patch_embed_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, gamma1, beta1,
+                                                                   reinterpret_cast<bf16*>(y16), S, (int)groups);
+    return (int)cudaGetLastError();
+  }
+  // fp32 SIMT kernel (any S % 4 == 0); a fused second LayerNorm is then a separate launch
+  const long long groups = (total + PE_TOK - 1) / PE_TOK;
   const unsigned grid = (unsigned)(groups < 2LL * sms ? groups : 2LL * sms);
   patch_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, B, S, (int)groups);
-  return (int)cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (y16) return mst_layernorm(x, gamma1, beta1, y16, (int)total, 128, stream);
+  return 0;
 }
 
 extern "C" int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream) {

@@ -74,14 +74,17 @@ class SwinEncoderWeights:
         self.pm_red = ops.pack_linear(g("2.reduction.weight"), None)
 
 
-def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W: int, shift: int, tag: str):
-    """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place)."""
+def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W: int, shift: int, tag: str,
+                ln1_done: bool = False):
+    """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place).
+    ln1_done: the producer of x32 already wrote LN1(x) into the block's `ln` buffer (patch embedding)."""
     C, heads = bw["C"], bw["heads"]
     T = Bt * H * W
     ln = ws_.bf16(tag + "ln", T, C)
     qkv = ws_.bf16(tag + "qkv", T, 3 * C)
     o = ws_.bf16(tag + "o", T, C)
-    ops.layernorm(x32, bw["n1w"], bw["n1b"], ln, T, C)
+    if not ln1_done:
+        ops.layernorm(x32, bw["n1w"], bw["n1b"], ln, T, C)
     ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
     ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
                          3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
@@ -96,12 +99,15 @@ def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torc
     Bt = sum(int(i.shape[0]) for i in imgs)
     P = S // 4
     x1 = ws_.f32("sw_x1", Bt * P * P, 128)
+    ln1 = ws_.bf16("sw1_ln", Bt * P * P, 128)  # the first block's LN1 output comes out of the patch-embedding kernel
+    b10 = w.blocks["1.0"]
     off = 0
     for img in imgs:
         b = int(img.shape[0])
-        ops.patch_embed(img, w.pe_w, w.pe_b, w.pe_g, w.pe_beta, x1[off * P * P:], b, S)
+        ops.patch_embed(img, w.pe_w, w.pe_b, w.pe_g, w.pe_beta, x1[off * P * P:], b, S,
+                        gamma1=b10["n1w"], beta1=b10["n1b"], y16=ln1[off * P * P:])
         off += b
-    _swin_block(w.blocks["1.0"], x1, ws_, Bt, P, P, 0, "sw1_")
+    _swin_block(b10, x1, ws_, Bt, P, P, 0, "sw1_", ln1_done=True)
     _swin_block(w.blocks["1.1"], x1, ws_, Bt, P, P, 3, "sw1_")
     P2 = P // 2
     T2 = Bt * P2 * P2

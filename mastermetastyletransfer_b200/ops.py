@@ -260,11 +260,15 @@ def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None) -> None:
             nbytes=B * T * Cdim * (4.0 + (2.0 if y16 is not None else 0.0) + (4.0 if y32 is not None else 0.0)))
 
 
-def patch_embed(img, w, b, gamma, beta, x, B, S) -> None:
-    _launch("mst_patch_embed", lambda: _lib.lib().mst_patch_embed(_ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
-                                     _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"),
-                                     _ptr(x, torch.float32, "x"), B, S, _stream()),
-            nbytes=4.0 * B * S * S * 3 + 4.0 * B * (S // 4) ** 2 * 128)
+def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact: bool = False) -> None:
+    """tv swin features[0] (conv 4x4/s4 + LayerNorm).  With y16 the first block's norm1 (gamma1/beta1) is fused and its bf16
+    output written to y16.  exact=True forces the fp32 SIMT kernel (the default tensor-core path rounds the weights to bf16)."""
+    _launch("mst_patch_embed", lambda: _lib.lib().mst_patch_embed_ln(
+        _ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
+        _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"), _ptr(x, torch.float32, "x"),
+        _ptr(gamma1, torch.float32, "gamma1"), _ptr(beta1, torch.float32, "beta1"), _ptr(y16, torch.bfloat16, "y16"),
+        B, S, int(exact), _stream()),
+            nbytes=4.0 * B * S * S * 3 + (4.0 + (2.0 if y16 is not None else 0.0)) * B * (S // 4) ** 2 * 128)
 
 
 def cast_bf16(x, y) -> None:

@@ -210,16 +210,30 @@ def test_instance_norm(twice):
     assert torch.allclose(y16.float().cpu(), ref, atol=2e-2, rtol=1e-2)
 
 
-def test_patch_embed():
+@pytest.mark.parametrize("S,exact", [(64, False), (128, False), (64, True), (40, False)])
+def test_patch_embed(S, exact):
+    """tv swin features[0] + (fused) norm1 of the first block.  The tensor-core path (S % 64 == 0) rounds the conv weights to
+    bf16 like every other layer; exact / other sizes run the fp32 kernel."""
     ops = _ops()
-    B, S = 2, 64
+    B = 3
     img = _rand(B, 3, S, S, seed=57)
     w, b = _rand(128, 3, 4, 4, seed=58, scale=48 ** -0.5), 0.05 * _rand(128, seed=59)
     g, beta = 1 + 0.1 * _rand(128, seed=60), 0.1 * _rand(128, seed=61)
+    g1, beta1 = 1 + 0.1 * _rand(128, seed=62), 0.1 * _rand(128, seed=63)
     out = torch.empty(B, S // 4, S // 4, 128, device="cuda")
-    ops.patch_embed(img.cuda(), w.cuda(), b.cuda(), g.cuda(), beta.cuda(), out, B, S)
-    ref = F.layer_norm(F.conv2d(img, w, b, stride=4).permute(0, 2, 3, 1), (128,), g, beta)
-    assert torch.allclose(out.cpu(), ref, atol=1e-4, rtol=1e-4), (out.cpu() - ref).abs().max()
+    y16 = torch.empty(B, S // 4, S // 4, 128, device="cuda", dtype=torch.bfloat16)
+    ops.patch_embed(img.cuda(), w.cuda(), b.cuda(), g.cuda(), beta.cuda(), out, B, S, gamma1=g1.cuda(), beta1=beta1.cuda(), y16=y16, exact=exact)
+    tc = S % 64 == 0 and not exact
+    ref = F.layer_norm(F.conv2d(img, w.bfloat16().float() if tc else w, b, stride=4).permute(0, 2, 3, 1), (128,), g, beta)
+    assert torch.allclose(out.cpu(), ref, atol=2e-4, rtol=1e-4), (out.cpu() - ref).abs().max()
+    ref1 = F.layer_norm(ref, (128,), g1, beta1)
+    assert torch.allclose(y16.float().cpu(), ref1, atol=2e-2, rtol=1e-2)
+    if tc:  # distance to the un-rounded fp32 layer: bf16 weight rounding only
+        full = F.layer_norm(F.conv2d(img, w, b, stride=4).permute(0, 2, 3, 1), (128,), g, beta)
+        assert (out.cpu() - full).abs().max() < 3e-2
+    out2 = torch.empty_like(out)
+    ops.patch_embed(img.cuda(), w.cuda(), b.cuda(), g.cuda(), beta.cuda(), out2, B, S, exact=exact)  # without the fused norm1
+    assert torch.equal(out2, out)
 
 
 def test_bad_arguments_raise():
