@@ -119,9 +119,23 @@ typedef struct MstMlp {
   float* out_f32;          /* fp32 [M, ld_out32] or NULL */
   mst_bf16* out_bf16;      /* bf16 [M, ld_out16] or NULL */
   int M, C, lda, ld_res, ld_out32, ld_out16;
+  /* ---- optional attention-output stage in front of the MLP (pre != 0; all zero = the plain MLP above) ----
+   *   x1  = res + A . Wpre^T + bpre            (attention projection + residual: style_transformer.py:156,383-386 / tv swin block)
+   *      or res * mul + A . Wpre^T + bpre      (mul != NULL: Query*sigma + mu, style_transformer.py:1123; A.Wpre^T+bpre is mu)
+   *   X   = LayerNorm(x1; ln_g, ln_b) eps 1e-5, or x1 when ln_g == NULL     (bf16, never leaves shared memory)
+   *   out = x1 + fc2(GELU(fc1(X) + b1)) + b2
+   * res is required (it may alias out_f32); x1 itself stays on chip (pre-loaded into the fc2 accumulator); Wstream must come from
+   * mst_pack_mlp_weights_pre (the [C, C] projection weight is prepended to every tile's weight stream). */
+  const float* bpre;       /* [C] projection bias */
+  const float* mul;        /* fp32 [M, ld_res] or NULL */
+  const float* ln_g;       /* [C] or NULL */
+  const float* ln_b;       /* [C] or NULL */
+  int pre;
 } MstMlp;
 size_t mst_mlp_stream_bytes(int C);
+size_t mst_mlp_stream_bytes_pre(int C);
 int mst_pack_mlp_weights(const float* w1 /*[4C,C]*/, const float* w2 /*[C,4C]*/, mst_bf16* dst, int C, void* stream);
+int mst_pack_mlp_weights_pre(const float* wpre /*[C,C]*/, const float* w1, const float* w2, mst_bf16* dst, int C, void* stream);
 int mst_mlp_fused(const MstMlp* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------

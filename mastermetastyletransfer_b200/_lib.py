@@ -64,7 +64,8 @@ class MstWindowAttn(C.Structure):
 class MstMlp(C.Structure):
     _fields_ = [("A", C.c_void_p), ("Wstream", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("res", C.c_void_p),
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
-                ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int)]
+                ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int),
+                ("bpre", C.c_void_p), ("mul", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("pre", C.c_int)]
 
 
 class MstTensorTable(C.Structure):
@@ -97,6 +98,8 @@ SYMBOLS = {
     "mst_conv3x3_rows_supported": (_I, [_I, _I, _I, _I]),
     "mst_mlp_stream_bytes": (_Z, [_I]),
     "mst_pack_mlp_weights": (_I, [_P, _P, _P, _I, _P]),
+    "mst_mlp_stream_bytes_pre": (_Z, [_I]),
+    "mst_pack_mlp_weights_pre": (_I, [_P, _P, _P, _P, _I, _P]),
     "mst_mlp_fused": (_I, [C.POINTER(MstMlp), _P]),
     "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
     "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

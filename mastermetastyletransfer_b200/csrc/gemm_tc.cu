@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float bias_s[MAX_BIAS];
+  __shared__ __align__(16) float bias_s[MAX_BIAS];
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for ptxas (uniform-register MMA issue loop)
   const int lane = threadIdx.x & 31;
@@ -312,9 +312,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
           if (!row_ok) continue;
           const int n = nbase + col0;
           float x[CH];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + n);  // n % 16 == 0: LDS.128 broadcasts (4x fewer LSU wavefronts)
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 bb = b4[j];
+            x[4 * j] = __uint_as_float(v[4 * j]) + bb.x; x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z; x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+          }
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
-            x[j] = __uint_as_float(v[j]) + bias_s[n + j];
             if constexpr (!EXT) {
               if (p.act == MST_ACT_RELU) x[j] = fmaxf(x[j], 0.0f);
               else if (p.act == MST_ACT_GELU) x[j] = gelu_erf(x[j]);

@@ -5,12 +5,14 @@
 // from there as the A operand of the second tcgen05 GEMM, which accumulates the [128 x C] output in TMEM
 // across all hidden chunks.
 //
-//   warps 0-7  : epilogue.  fc1 chunk: TMEM -> +b1 -> GELU -> bf16 -> swizzled smem (Hs, double buffered);
-//                tile end: TMEM -> +b2 -> +residual -> fp32 / bf16 global stores.
-//   warps 8-11 : A-tile producers (cp.async, [128 x C] bf16 stays resident for the whole tile).
-//   warp 12    : MMA issuer (one elected lane): MMA1(t) then MMA2(t-1), so the tensor core always has the next
-//                fc1 chunk to chew on while the epilogue warps run GELU on the previous one.
-//   warp 13    : weight streamer: both weight matrices are pre-packed as ONE linear stream of 32 KB stages in
+//   warps 0-15 : epilogue (four per TMEM lane quadrant: the erf-GELU is a ~100-cycle dependent chain with two MUFU
+//                ops per element, measured latency-bound with two warps per scheduler).  fc1 chunk: TMEM -> +b1 ->
+//                GELU -> bf16 -> swizzled smem (Hs, double buffered); tile end: TMEM -> +b2 -> +residual -> fp32 /
+//                bf16 global stores.
+//   warps 16-17: A-tile producers (cp.async, [128 x C] bf16 stays resident for the whole tile).
+//   warp 18    : MMA issuer (warp-uniform loop, one elected lane): MMA1(t) then MMA2(t-1), so the tensor core always
+//                has the next fc1 chunk to chew on while the epilogue warps run GELU on the previous one.
+//   warp 19    : weight streamer: both weight matrices are pre-packed as ONE linear stream of 32 KB stages in
 //                exactly the order the MMA warp consumes them (each stage is the swizzled smem image), so the
 //                producer is a loop of cp.async.bulk copies.
 // TMEM: fc1 accumulator double buffered (2 x 128 columns) + fc2 accumulator (C columns) <= 512 columns.
@@ -19,9 +21,11 @@
 
 namespace mst {
 
-constexpr int ML_EPI_WARPS = 8;
-constexpr int ML_PROD_WARPS = 4;
-constexpr int ML_THREADS = (ML_EPI_WARPS + ML_PROD_WARPS + 2) * 32;
+constexpr int ML_EPI_WARPS = 16;  // four per TMEM lane quadrant: the GELU epilogue is latency-bound, it needs the warps
+constexpr int ML_PROD_WARPS = 2;
+constexpr int ML_MMA_WARP = ML_EPI_WARPS + ML_PROD_WARPS;      // 18
+constexpr int ML_STREAM_WARP = ML_MMA_WARP + 1;                // 19
+constexpr int ML_THREADS = (ML_EPI_WARPS + ML_PROD_WARPS + 2) * 32;  // 640
 constexpr int ML_HC = 128;               // hidden units per chunk
 constexpr int ML_STAGE_BYTES = 32 * 1024;
 
@@ -39,37 +43,51 @@ struct MlpCfg {
   static constexpr int KB1 = C / 64;                 // k-blocks of fc1 (K = C)
   static constexpr int S1 = C / 128;                 // weight stages per fc1 chunk (two [128 x 64] k-blocks per stage)
   static constexpr int S2 = C == 256 ? 2 : 1;        // weight stages per fc2 chunk
-  static constexpr int NSTG = C == 256 ? 2 : 3;      // ring depth
+  static constexpr int NSTG = 3;                     // ring depth (C == 256 streams 1 MB of weights per tile: two stages starved the MMA)
+  static constexpr int ABUF = C == 256 ? 1 : 2;      // A tiles resident (C == 128: the next tile's A is prefetched during this tile)
   static constexpr int A_BYTES = KB1 * 128 * 128;    // resident A tile
   static constexpr int HS_BYTES = 2 * 128 * 128;     // one Hs buffer: [128 x 128] bf16 as two k-blocks
-  static constexpr int SMEM_BYTES = 1024 + A_BYTES + 2 * HS_BYTES + NSTG * ML_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + ABUF * A_BYTES + 2 * HS_BYTES + NSTG * ML_STAGE_BYTES;
   static constexpr int ACC2_COL = 256;
 };
 
-template <int C>
+// PRE = true puts the attention-output stage of a transformer block in front of the MLP (MstMlp::pre):
+//     x1 = res (* mul) + A . Wpre^T + bpre          (attention projection + residual, or the Query*sigma+mu blend)
+//     X  = LayerNorm(x1) (ln_g / ln_b) or x1          bf16, written by the epilogue warps straight into the swizzled
+//                                                     shared-memory A tile of fc1 -- it never exists in HBM
+//     out = x1 + fc2(GELU(fc1(X)))                    x1 is pre-loaded into the fc2 accumulator (TMEM): fc2 accumulates onto it
+// The projection runs as C/128 extra "chunks" of the fc1 machinery (same [128 x C] x [C x 128] shape, same weight-stage
+// format, accumulators = the two fc1 TMEM buffers).  Its A operand O (the attention output tile) is loaded by the
+// producer warps: C = 128 has a buffer of its own, C = 256 borrows the two Hs buffers (free until the first GELU).
+template <int C, bool PRE>
 __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles) {
   using Cfg = MlpCfg<C>;
   constexpr int NSTG = Cfg::NSTG;
+  constexpr int ABUF = PRE ? 1 : Cfg::ABUF;
+  constexpr int NPRE = PRE ? C / 128 : 0;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full, a_empty, acc2_full, acc2_empty;
+  __shared__ uint64_t a_full[2], a_empty[2], acc2_full, acc2_empty, x_full;
   __shared__ uint64_t w_full[NSTG], w_empty[NSTG];
   __shared__ uint64_t acc1_full[2], acc1_empty[2], hs_full[2], hs_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float b1_s[1024];
-  __shared__ float b2_s[256];
+  __shared__ __align__(16) float b2_s[256];
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
   const uint32_t a_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t hs_base = a_base + Cfg::A_BYTES;
+  const uint32_t hs_base = a_base + Cfg::ABUF * Cfg::A_BYTES;
   const uint32_t ring_base = hs_base + 2 * Cfg::HS_BYTES;
+  // PRE: O = projection input tile (producers), X = fc1 input tile (epilogue warps)
+  const uint32_t x_base = (PRE && C == 128) ? a_base + Cfg::A_BYTES : a_base;
+  const uint32_t o_base = C == 128 ? a_base : hs_base;
   const int hidden = 4 * C;
   const int NCH = hidden / ML_HC;
+  const int CPT = NPRE + NCH;  // fc1-type chunks per tile (the acc1 buffers alternate over this running count)
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&a_full), ML_PROD_WARPS * 32);
-    mbar_init(smem_u32(&a_empty), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&a_full[b]), ML_PROD_WARPS * 32); mbar_init(smem_u32(&a_empty[b]), 1); }
     mbar_init(smem_u32(&acc2_full), 1);
     mbar_init(smem_u32(&acc2_empty), ML_EPI_WARPS);
+    mbar_init(smem_u32(&x_full), ML_EPI_WARPS);
     for (int s = 0; s < NSTG; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&acc1_full[b]), 1);
@@ -79,9 +97,8 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < hidden; i += ML_THREADS) b1_s[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += ML_THREADS) b2_s[i] = p.b2[i];
-  if (warp == 12) {
+  if (warp == ML_MMA_WARP) {
     tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
@@ -92,30 +109,33 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
 
   if (warp >= ML_EPI_WARPS && warp < ML_EPI_WARPS + ML_PROD_WARPS) {
     // =========================== A-tile producers ===========================
+    // !PRE: the fc1 input tile (double buffered for C = 128).  PRE: the projection input tile O.
     const int t = threadIdx.x - ML_EPI_WARPS * 32;
-    const int c = t & 7, r0 = t >> 3;  // rows r0 + 16*i
+    const int c = t & 7, r0 = t >> 3;  // rows r0 + 8*i (64 threads: 8 chunk columns x 8 row phases)
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      if (lt >= 1) mbar_wait(smem_u32(&a_empty), (lt - 1) & 1);
+      const int ab = lt % ABUF, au = lt / ABUF;  // buffer and its use count
+      if (au >= 1) mbar_wait(smem_u32(&a_empty[ab]), (au - 1) & 1);
       const int m0 = tile * 128;
+      const uint32_t a_buf = PRE ? o_base : a_base + ab * Cfg::A_BYTES;
 #pragma unroll
       for (int kb = 0; kb < Cfg::KB1; ++kb) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
+        for (int i = 0; i < 16; ++i) {
+          const int r = r0 + 8 * i;
           const int m = m0 + r;
           const bool valid = m < p.M;
-          cp_async16(a_base + kb * 16384 + sw128_offset(r, c), valid ? Abase + (long long)m * p.lda + kb * 64 + c * 8 : Abase, valid);
+          cp_async16(a_buf + kb * 16384 + sw128_offset(r, c), valid ? Abase + (long long)m * p.lda + kb * 64 + c * 8 : Abase, valid);
         }
       }
-      cp_async_mbar_arrive_noinc(smem_u32(&a_full));
+      cp_async_mbar_arrive_noinc(smem_u32(&a_full[ab]));
     }
     cp_async_wait_all();
-  } else if (warp == 13) {
+  } else if (warp == ML_STREAM_WARP) {
     // =========================== weight streamer ===========================
     if (lane == 0) {
-      const int stages_per_tile = NCH * (Cfg::S1 + Cfg::S2);
+      const int stages_per_tile = NPRE * Cfg::S1 + NCH * (Cfg::S1 + Cfg::S2);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wstream);
       int ws = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -127,7 +147,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == ML_MMA_WARP) {
     // =========================== MMA issuer ===========================
     // whole warp, convergent, warp-uniform values; one lane elected inside umma_bf16_pred / umma_commit_pred so that
     // ptxas keeps the descriptors in uniform registers (see gemm_tc.cu)
@@ -139,6 +159,27 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       mbar_wait(smem_u32(&w_full[slot]), (ws / NSTG) & 1);
       tc_fence_after();
     };
+    // fc1-type chunk: acc1[a1 & 1] = Atile . W^T, W = the next S1 stages of the stream ([128 x C] as 64-wide k-blocks)
+    auto mma1 = [&](int a1, uint32_t a_tile) {
+      const int buf = a1 & 1, u = a1 >> 1;
+      mbar_wait(smem_u32(&acc1_empty[buf]), (u & 1) ^ 1);
+      tc_fence_after();
+      for (int s = 0; s < Cfg::S1; ++s, ++ws) {
+        int slot;
+        wait_stage(slot);
+        const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
+#pragma unroll
+        for (int kb2 = 0; kb2 < 2; ++kb2) {
+          const int kb = s * 2 + kb2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_pred(tmem_base + buf * ML_HC, umma_desc_sw128(a_tile + kb * 16384 + k * 32),
+                           umma_desc_sw128(wb + kb2 * 16384 + k * 32), idesc1, (kb | k) != 0);
+        }
+        umma_commit_pred(smem_u32(&w_empty[slot]));
+      }
+      umma_commit_pred(smem_u32(&acc1_full[buf]));
+    };
     auto mma2 = [&](int j) {  // acc2 += Hs(j) . W2_j^T
       const int gc = lt * NCH + j, buf = j & 1, u = gc >> 1;
       mbar_wait(smem_u32(&hs_full[buf]), u & 1);
@@ -148,103 +189,221 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       for (int s = 0; s < Cfg::S2; ++s, ++ws) {
         int slot;
         wait_stage(slot);
-        {
-          const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
-          if constexpr (C == 256) {  // stage = k-block s of the chunk: [256 x 64]
+        const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
+        if constexpr (C == 256) {  // stage = k-block s of the chunk: [256 x 64]
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + s * 16384 + k * 32), umma_desc_sw128(wb + k * 32), idesc2,
+                           PRE || (j | s | k) != 0);
+        } else {  // stage = both k-blocks: 2 x [128 x 64]
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + s * 16384 + k * 32), umma_desc_sw128(wb + k * 32), idesc2,
-                        (j | s | k) != 0);
-          } else {  // stage = both k-blocks: 2 x [128 x 64]
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + kb * 16384 + k * 32), umma_desc_sw128(wb + kb * 16384 + k * 32),
-                          idesc2, (j | kb | k) != 0);
-          }
-          umma_commit_pred(smem_u32(&w_empty[slot]));
+              umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + kb * 16384 + k * 32), umma_desc_sw128(wb + kb * 16384 + k * 32),
+                             idesc2, PRE || (j | kb | k) != 0);
         }
+        umma_commit_pred(smem_u32(&w_empty[slot]));
       }
       umma_commit_pred(smem_u32(&hs_empty[buf]));
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      mbar_wait(smem_u32(&a_full), lt & 1);
+      const int ab = lt % ABUF, au = lt / ABUF;
+      mbar_wait(smem_u32(&a_full[ab]), au & 1);
       tc_fence_after();
-      for (int t = 0; t < NCH; ++t) {
-        const int gc = lt * NCH + t, buf = t & 1, u = gc >> 1;
-        mbar_wait(smem_u32(&acc1_empty[buf]), (u & 1) ^ 1);
+      int a1 = lt * CPT;
+      uint32_t a_tile = a_base + ab * Cfg::A_BYTES;
+      if constexpr (PRE) {
+        for (int pc = 0; pc < NPRE; ++pc) mma1(a1++, o_base);   // projection: acc1[.] = O . Wpre[pc*128 .. +127]^T
+        if constexpr (C == 128) umma_commit_pred(smem_u32(&a_empty[0]));  // O consumed: the next tile's O may be loaded
+        a_tile = x_base;
+        mbar_wait(smem_u32(&x_full), lt & 1);  // the epilogue warps wrote X (generic proxy, fenced) into shared memory
         tc_fence_after();
-        // ---- MMA1(t): acc1[buf] = A . W1_t^T ----
-        for (int s = 0; s < Cfg::S1; ++s, ++ws) {
-          int slot;
-          wait_stage(slot);
-          {
-            const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
-#pragma unroll
-            for (int kb2 = 0; kb2 < 2; ++kb2) {
-              const int kb = s * 2 + kb2;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_pred(tmem_base + buf * ML_HC, umma_desc_sw128(a_base + kb * 16384 + k * 32),
-                          umma_desc_sw128(wb + kb2 * 16384 + k * 32), idesc1, (kb | k) != 0);
-            }
-            umma_commit_pred(smem_u32(&w_empty[slot]));
-          }
-        }
-        umma_commit_pred(smem_u32(&acc1_full[buf]));
+      }
+      for (int t = 0; t < NCH; ++t) {
+        mma1(a1++, a_tile);
         if (t >= 1) mma2(t - 1);
       }
       mma2(NCH - 1);
       umma_commit_pred(smem_u32(&acc2_full));
-      umma_commit_pred(smem_u32(&a_empty));
+      if constexpr (!(PRE && C == 128)) umma_commit_pred(smem_u32(&a_empty[ab]));  // PRE, C = 256: O aliases Hs -> free only now
     }
     tc_fence_before();
   } else {
-    // =========================== epilogue warps 0-7 ===========================
-    const int quad = warp & 3, half = warp >> 2;
+    // =========================== epilogue warps 0-15 ===========================
+    // warp = (TMEM lane quadrant `quad`, column part `part` of 4): rows quad*32 + lane, columns part*C/4 .. of every
+    // [128 x C] tile, columns part*32 .. of every 128-wide fc1 chunk.
+    const int quad = warp & 3, part = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
+    constexpr int CPW = C / 4;
+    const float* resp = PRE ? nullptr : p.res;  // PRE: x1 is pre-loaded into the fc2 accumulator
+    const int ld_resp = p.ld_res;
+    // byte offset of this row's 16-byte chunk 0 inside a [128 x 64] SW128 k-block
+    const uint32_t xrow = (uint32_t)((row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128);
+    // 32 consecutive columns starting at tile column n0 (a multiple of 32) -> bf16 -> [128 x 64] k-blocks at `base`
+    auto store_tile32 = [&](uint32_t base, int n0, const float* y) {
+      const uint32_t kbase = base + (n0 >> 6) * 16384 + xrow;
+      const int c0 = (n0 & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * q + 2 * e], y[8 * q + 2 * e + 1]);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        const uint32_t addr = kbase + ((uint32_t)((c0 + q) ^ (row_in_tile & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      }
+    };
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int row = tile * 128 + row_in_tile;
       const bool row_ok = row < p.M;
-      for (int j = 0; j < NCH; ++j) {
-        const int gc = lt * NCH + j, buf = j & 1, u = gc >> 1;
-        if (lane == 0) mbar_wait(smem_u32(&acc1_full[buf]), u & 1);
+      if constexpr (PRE) {
+        // ---------------- attention-output stage: x1 = res (*mul) + acc + bpre; X = [LN](x1) -> shared memory ----------------
+        // x1 never goes to HBM: it is written (tcgen05.st) into the fc2 accumulator's TMEM columns, which are idle until
+        // MMA2(0) of this tile; fc2 then ACCUMULATES onto it, so the block's second residual add is free, and the LayerNorm
+        // passes re-read x1 from TMEM.  The only global traffic of the stage is one read of res (and mul).
+        const int n_first = part * CPW;                           // this warp's first tile column
+        const int a1p = lt * CPT + (n_first >> 7);                // its projection chunk (C = 256: columns 128.. are chunk 1)
+        const int pbuf = a1p & 1;
+        const bool ln = p.ln_g != nullptr;
+        const float* rp = p.res + (long long)row * p.ld_res + n_first;
+        const float* mp = p.mul ? p.mul + (long long)row * p.ld_res + n_first : nullptr;
+        // the residual (and blend factor) of the first 32 columns: requested before the accumulator wait, latency hidden
+        float4 rr[8];
+        auto fetch_res = [&](int col0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            rr[e] = row_ok ? *reinterpret_cast<const float4*>(rp + col0 + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        fetch_res(0);
+        if (lane == 0) mbar_wait(smem_u32(&acc1_full[pbuf]), (a1p >> 1) & 1);
         __syncwarp();
         tc_fence_after();
-        // this warp's 64 hidden units = k-block `half` of the Hs tile
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * ML_HC + half * 64;
-        uint32_t packed[32];
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
+        const uint32_t tp = tmem_base + ((uint32_t)(quad * 32) << 16) + pbuf * ML_HC + (n_first & 127);
+        const uint32_t tx = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + n_first;  // x1 home: fc2 accumulator
+        float sum = 0.f;
+#pragma unroll 1
+        for (int col0 = 0; col0 < CPW; col0 += 32) {
           uint32_t v[32];
-          tmem_ld32(taddr + part * 32, v);
+          tmem_ld32(tp + col0, v);
           tmem_wait_ld();
-          if (part == 1) {  // both loads done: the fc1 accumulator can be overwritten by MMA1(j+2)
+          if (col0 + 32 >= CPW) {  // projection accumulator drained by this warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&acc1_empty[buf]));
+            if (lane == 0) {
+              mbar_arrive(smem_u32(&acc1_empty[pbuf]));
+              if (C == 256) mbar_arrive(smem_u32(&acc1_empty[pbuf ^ 1]));  // the other chunk: not read by this warp
+            }
           }
-          const float* bb = b1_s + j * ML_HC + half * 64 + part * 32;
+          float x[32];
+          const float4* bp4 = reinterpret_cast<const float4*>(p.bpre + n_first + col0);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float x0 = gelu_erf(__uint_as_float(v[2 * e]) + bb[2 * e]);
-            const float x1 = gelu_erf(__uint_as_float(v[2 * e + 1]) + bb[2 * e + 1]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-            packed[part * 16 + e] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int e = 0; e < 8; ++e) {
+            const float4 b4 = __ldg(bp4 + e);
+            const float4 r = rr[e];
+            float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (mp && row_ok) m = *reinterpret_cast<const float4*>(mp + col0 + 4 * e);
+            x[4 * e] = fmaf(r.x, m.x, __uint_as_float(v[4 * e]) + b4.x);
+            x[4 * e + 1] = fmaf(r.y, m.y, __uint_as_float(v[4 * e + 1]) + b4.y);
+            x[4 * e + 2] = fmaf(r.z, m.z, __uint_as_float(v[4 * e + 2]) + b4.z);
+            x[4 * e + 3] = fmaf(r.w, m.w, __uint_as_float(v[4 * e + 3]) + b4.w);
           }
+          if (col0 + 32 < CPW) fetch_res(col0 + 32);  // next chunk's residual while this one is stored / reduced
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(x[e]);
+          tmem_st32(tx + col0, v);
+          if (ln) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sum += x[e];
+          } else {
+            store_tile32(x_base, n_first + col0, x);
+          }
+        }
+        tmem_wait_st();
+        if (ln) {
+          // LayerNorm over the C columns of the row: this thread owns CPW of them, the three other warps of the TMEM
+          // quadrant the rest.  Local mean / centred M2 (x1 re-read from TMEM), one exchange through the quadrant's own rows
+          // of the X tile, pairwise-merge formula M2 = sum M2_i + CPW * sum (mean_i - mean)^2, then normalise into X.
+          const float ml = sum * (1.0f / CPW);
+          float q = 0.f;
+#pragma unroll 1
+          for (int col0 = 0; col0 < CPW; col0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tx + col0, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float d = __uint_as_float(v[e]) - ml;
+              q = fmaf(d, d, q);
+            }
+          }
+          const uint32_t ex = x_base + quad * 4096 + (uint32_t)lane * 32u;  // [lane][part] float2, inside this quadrant's rows
+          asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(ex + part * 8), "f"(ml), "f"(q) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+          float mi[4], qi[4];
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(mi[0]), "=f"(qi[0]), "=f"(mi[1]), "=f"(qi[1]) : "r"(ex) : "memory");
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(mi[2]), "=f"(qi[2]), "=f"(mi[3]), "=f"(qi[3]) : "r"(ex + 16) : "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");  // all four have read before X rows are overwritten
+          const float mean = 0.25f * ((mi[0] + mi[1]) + (mi[2] + mi[3]));
+          float m2 = (qi[0] + qi[1]) + (qi[2] + qi[3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m2 = fmaf((mi[i] - mean) * (mi[i] - mean), (float)CPW, m2);
+          const float rstd = rsqrtf(m2 * (1.0f / C) + 1e-5f);
+#pragma unroll 1
+          for (int col0 = 0; col0 < CPW; col0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tx + col0, v);
+            tmem_wait_ld();
+            float y[32];
+            const float4* g4 = reinterpret_cast<const float4*>(p.ln_g + n_first + col0);
+            const float4* be4 = reinterpret_cast<const float4*>(p.ln_b + n_first + col0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 g = __ldg(g4 + e), be = __ldg(be4 + e);
+              y[4 * e] = (__uint_as_float(v[4 * e]) - mean) * rstd * g.x + be.x;
+              y[4 * e + 1] = (__uint_as_float(v[4 * e + 1]) - mean) * rstd * g.y + be.y;
+              y[4 * e + 2] = (__uint_as_float(v[4 * e + 2]) - mean) * rstd * g.z + be.z;
+              y[4 * e + 3] = (__uint_as_float(v[4 * e + 3]) - mean) * rstd * g.w + be.w;
+            }
+            store_tile32(x_base, n_first + col0, y);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&x_full));
+      }
+      for (int j = 0; j < NCH; ++j) {
+        const int a1 = lt * CPT + NPRE + j;              // running fc1-chunk count -> acc1 buffer
+        const int abuf = a1 & 1, au = a1 >> 1;
+        const int gc = lt * NCH + j, buf = j & 1, u = gc >> 1;  // Hs buffer
+        if (lane == 0) mbar_wait(smem_u32(&acc1_full[abuf]), au & 1);
+        __syncwarp();
+        tc_fence_after();
+        // this warp's 32 hidden units of the chunk: columns part*32 .. of the [128 x 128] Hs tile
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + abuf * ML_HC + part * 32, v);
+        tmem_wait_ld();
+        tc_fence_before();  // the fc1 accumulator can be overwritten by MMA1(j+2) once all sixteen warps have read it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc1_empty[abuf]));
+        // fc1 bias straight from global (warp-uniform address, L1-resident): shared memory is fully committed to tiles
+        const float4* bb = reinterpret_cast<const float4*>(p.b1 + j * ML_HC + part * 32);
+        float h[32];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 b4 = __ldg(bb + e);
+          h[4 * e] = gelu_erf(__uint_as_float(v[4 * e]) + b4.x);
+          h[4 * e + 1] = gelu_erf(__uint_as_float(v[4 * e + 1]) + b4.y);
+          h[4 * e + 2] = gelu_erf(__uint_as_float(v[4 * e + 2]) + b4.z);
+          h[4 * e + 3] = gelu_erf(__uint_as_float(v[4 * e + 3]) + b4.w);
         }
         if (lane == 0) mbar_wait(smem_u32(&hs_empty[buf]), (u & 1) ^ 1);  // MMA2(j-2) has finished reading this buffer
         __syncwarp();
-        const uint32_t hrow = hs_base + buf * Cfg::HS_BYTES + half * 16384;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = hrow + sw128_offset(row_in_tile, c);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[4 * c]), "r"(packed[4 * c + 1]),
-                       "r"(packed[4 * c + 2]), "r"(packed[4 * c + 3])
-                       : "memory");
-        }
+        store_tile32(hs_base + buf * Cfg::HS_BYTES, part * 32, h);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hs_full[buf]));
@@ -253,11 +412,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       if (lane == 0) mbar_wait(smem_u32(&acc2_full), lt & 1);
       __syncwarp();
       tc_fence_after();
-      constexpr int CPW = C / 2;
-      const bool wide_res = p.res && ((reinterpret_cast<uintptr_t>(p.res) | (uintptr_t)(p.ld_res * 4)) & 31) == 0;
+      const bool wide_res = resp && ((reinterpret_cast<uintptr_t>(resp) | (uintptr_t)(ld_resp * 4)) & 31) == 0;
       const bool wide_o32 = p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) | (uintptr_t)(p.ld_out32 * 4)) & 31) == 0;
       const bool wide_o16 = p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
-      const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + half * CPW;
+      const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + part * CPW;
 #pragma unroll 1
       for (int col0 = 0; col0 < CPW; col0 += 32) {
         uint32_t v[32];
@@ -269,13 +427,13 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           if (lane == 0) mbar_arrive(smem_u32(&acc2_empty));
         }
         if (!row_ok) continue;
-        const int n = half * CPW + col0;
+        const int n = part * CPW + col0;
         float x[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) x[e] = __uint_as_float(v[e]) + b2_s[n + e];
         // 256-bit accesses (one 32-byte sector per lane and instruction) when the row segments are 32-byte aligned
-        if (p.res) {
-          const float* rp = p.res + (long long)row * p.ld_res + n;
+        if (resp) {
+          const float* rp = resp + (long long)row * ld_resp + n;
           if (wide_res) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -336,7 +494,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == ML_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -351,16 +509,18 @@ __device__ __forceinline__ int mlp_stage_of_w1(int t, int S1, int S2) { return t
 __device__ __forceinline__ int mlp_stage_of_w2(int j, int NCH, int S1, int S2) {
   return j == NCH - 1 ? NCH * S1 + (NCH - 1) * S2 : (j + 2) * S1 + j * S2;
 }
-__global__ void pack_mlp_kernel(const float* __restrict__ w1, const float* __restrict__ w2, bf16* __restrict__ dst, int C) {
+__global__ void pack_mlp_kernel(const float* __restrict__ wpre, const float* __restrict__ w1, const float* __restrict__ w2,
+                                bf16* __restrict__ dst, int C) {
   const int hidden = 4 * C, NCH = hidden / ML_HC;
   const int S1 = C / 128, S2 = C == 256 ? 2 : 1;
+  const int pre_stages = wpre ? (C / 128) * S1 : 0;  // projection chunks come first in every tile's stream
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n1 = (long long)hidden * C;
   if (i < n1) {  // W1[hid][k]
     const int hid = (int)(i / C), k = (int)(i % C);
     const int t = hid / ML_HC, r = hid % ML_HC;
     const int kb = k / 64, kk = k % 64, c = kk >> 3, e = kk & 7;
-    const long long stage = mlp_stage_of_w1(t, S1, S2) + kb / 2;
+    const long long stage = pre_stages + mlp_stage_of_w1(t, S1, S2) + kb / 2;
     const long long off = stage * (ML_STAGE_BYTES / 2) + (kb & 1) * 8192 + ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) / 2 + e;
     dst[off] = __float2bfloat16(w1[i]);
   } else if (i < 2 * n1) {  // W2[n][hid]
@@ -368,10 +528,18 @@ __global__ void pack_mlp_kernel(const float* __restrict__ w1, const float* __res
     const int n = (int)(q / hidden), hid = (int)(q % hidden);
     const int j = hid / ML_HC, hh = hid % ML_HC;
     const int kb = hh / 64, kk = hh % 64, c = kk >> 3, e = kk & 7;
-    long long stage = mlp_stage_of_w2(j, NCH, S1, S2);
+    long long stage = pre_stages + mlp_stage_of_w2(j, NCH, S1, S2);
     long long inner = ((n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4)) / 2 + e;
     if (C == 256) stage += kb; else inner += kb * 8192;
     dst[stage * (ML_STAGE_BYTES / 2) + inner] = __float2bfloat16(w2[q]);
+  } else if (wpre && i < 2 * n1 + (long long)C * C) {  // Wpre[n][k]: chunk pc = n / 128, same stage format as a W1 chunk
+    const long long q = i - 2 * n1;
+    const int n = (int)(q / C), k = (int)(q % C);
+    const int pc = n / 128, r = n % 128;
+    const int kb = k / 64, kk = k % 64, c = kk >> 3, e = kk & 7;
+    const long long stage = (long long)pc * S1 + kb / 2;
+    const long long off = stage * (ML_STAGE_BYTES / 2) + (kb & 1) * 8192 + ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) / 2 + e;
+    dst[off] = __float2bfloat16(wpre[q]);
   }
 }
 
@@ -386,18 +554,18 @@ static int ml_num_sms() {
   return sms;
 }
 
-template <int C>
+template <int C, bool PRE>
 static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   using Cfg = MlpCfg<C>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int tiles = (p.M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < ml_num_sms() ? tiles : ml_num_sms());
-  mlp_fused_kernel<C><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles);
+  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles);
   return (int)cudaGetLastError();
 }
 
@@ -406,21 +574,41 @@ static int launch_mlp(const MstMlp& p, cudaStream_t st) {
 using namespace mst;
 
 extern "C" size_t mst_mlp_stream_bytes(int C) { return (C == 128 || C == 256) ? (size_t)2 * 4 * C * C * 2 : 0; }
+extern "C" size_t mst_mlp_stream_bytes_pre(int C) { return (C == 128 || C == 256) ? (size_t)(2 * 4 + 1) * C * C * 2 : 0; }
 
 extern "C" int mst_pack_mlp_weights(const float* w1, const float* w2, mst_bf16* dst, int C, void* stream) {
   if (!w1 || !w2 || !dst || (C != 128 && C != 256)) return MST_ERR_BAD_ARG;
   const long long n = 2LL * 4 * C * C;
-  pack_mlp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w1, w2, reinterpret_cast<bf16*>(dst), C);
+  pack_mlp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nullptr, w1, w2, reinterpret_cast<bf16*>(dst), C);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_pack_mlp_weights_pre(const float* wpre, const float* w1, const float* w2, mst_bf16* dst, int C, void* stream) {
+  if (!wpre || !w1 || !w2 || !dst || (C != 128 && C != 256)) return MST_ERR_BAD_ARG;
+  const long long n = (2LL * 4 + 1) * C * C;
+  pack_mlp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wpre, w1, w2, reinterpret_cast<bf16*>(dst), C);
   return (int)cudaGetLastError();
 }
 
 extern "C" int mst_mlp_fused(const MstMlp* p, void* stream) {
   if (!p || !p->A || !p->Wstream || !p->b1 || !p->b2) return MST_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(p->b1) & 15) return MST_ERR_BAD_ARG;  // read as float4
   if (p->M <= 0 || p->lda % 8 || p->lda < p->C) return MST_ERR_BAD_ARG;
   if (!p->out_f32 && !p->out_bf16) return MST_ERR_BAD_ARG;
   if ((p->out_f32 && p->ld_out32 % 4) || (p->out_bf16 && p->ld_out16 % 8) || (p->res && p->ld_res % 4)) return MST_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->C == 256) return launch_mlp<256>(*p, st);
-  if (p->C == 128) return launch_mlp<128>(*p, st);
+  if (p->pre) {
+    // attention-output stage in front: needs the residual / blend operand, the x1 destination and 16-byte aligned vectors
+    if (!p->bpre || !p->res || (p->ln_g == nullptr) != (p->ln_b == nullptr)) return MST_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(p->bpre) | reinterpret_cast<uintptr_t>(p->ln_g) | reinterpret_cast<uintptr_t>(p->ln_b) |
+         reinterpret_cast<uintptr_t>(p->res) | reinterpret_cast<uintptr_t>(p->mul) | reinterpret_cast<uintptr_t>(p->out_f32)) & 15)
+      return MST_ERR_BAD_ARG;
+    if (p->C == 256) return launch_mlp<256, true>(*p, st);
+    if (p->C == 128) return launch_mlp<128, true>(*p, st);
+    return MST_ERR_UNSUPPORTED;
+  }
+  if (p->mul || p->ln_g || p->ln_b || p->bpre) return MST_ERR_BAD_ARG;
+  if (p->C == 256) return launch_mlp<256, false>(*p, st);
+  if (p->C == 128) return launch_mlp<128, false>(*p, st);
   return MST_ERR_UNSUPPORTED;
 }

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -51,6 +53,10 @@ class Workspace:
 # --------------------------------------------------------------------------------------------
 
 
+# MST_FUSE_PROJ_MLP=0 falls back to the separate projection GEMM / LayerNorm / MLP kernels (A/B measurements)
+FUSE_PROJ_MLP = os.environ.get("MST_FUSE_PROJ_MLP", "1") != "0"
+
+
 class SwinEncoderWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
         g = lambda k: _f32(sd[prefix + k])
@@ -69,6 +75,9 @@ class SwinEncoderWeights:
                 proj=ops.pack_linear(g(p + "attn.proj.weight"), g(p + "attn.proj.bias")),
                 table=g(p + "attn.relative_position_bias_table"),
                 mlp=ops.pack_mlp(g(p + "mlp.0.weight"), g(p + "mlp.0.bias"), g(p + "mlp.3.weight"), g(p + "mlp.3.bias")),
+                # attention projection + residual + norm2 + MLP + residual as ONE kernel (MstMlp::pre)
+                proj_mlp=ops.pack_mlp(g(p + "mlp.0.weight"), g(p + "mlp.0.bias"), g(p + "mlp.3.weight"), g(p + "mlp.3.bias"),
+                                      wpre=g(p + "attn.proj.weight"), bpre=g(p + "attn.proj.bias")),
             )
         self.pm_g, self.pm_b = g("2.norm.weight"), g("2.norm.bias")
         self.pm_red = ops.pack_linear(g("2.reduction.weight"), None)
@@ -88,6 +97,9 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
     ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
     ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
                          3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
+    if FUSE_PROJ_MLP:  # x1 = x + proj(o); x = x1 + mlp(LN2(x1)): one kernel, LN2(x1) and the hidden activation stay on chip
+        ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"])
+        return
     ops.gemm(o, bw["proj"], T, res=x32, out_f32=x32)
     ops.layernorm(x32, bw["n2w"], bw["n2b"], ln, T, C)
     ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32)  # fc1 + GELU + fc2 + residual, hidden kept on chip
@@ -130,8 +142,11 @@ class StyleTransformerWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
         g = lambda k: _f32(sd[prefix + k])
 
-        def mlp(p):
-            return ops.pack_mlp(g(p + "0.weight"), g(p + "0.bias"), g(p + "3.weight"), g(p + "3.bias"))
+        def mlp(p, proj=None):
+            if proj is None:
+                return ops.pack_mlp(g(p + "0.weight"), g(p + "0.bias"), g(p + "3.weight"), g(p + "3.bias"))
+            return ops.pack_mlp(g(p + "0.weight"), g(p + "0.bias"), g(p + "3.weight"), g(p + "3.bias"),
+                                wpre=g(proj + "weight"), bpre=g(proj + "bias"))
 
         e = "encoder.shared_MHA_without_MLP.attn."
         wq, wk, wv = g(e + "Wq.weight"), g(e + "Wk.weight"), g(e + "Wv.weight")
@@ -146,6 +161,10 @@ class StyleTransformerWeights:
         self.mlp_key = mlp("encoder.encoder_MLP_Key.")
         self.mlp_scale = mlp("encoder.encoder_MLP_Scale.")
         self.mlp_shift = mlp("encoder.encoder_MLP_Shift.")
+        # fused attention-output halves: shared projection + the private MLP that follows it
+        self.pm_key = mlp("encoder.encoder_MLP_Key.", e + "proj.")
+        self.pm_scale = mlp("encoder.encoder_MLP_Scale.", e + "proj.")
+        self.pm_shift = mlp("encoder.encoder_MLP_Shift.", e + "proj.")
         d = "decoder.MHA_self_attn."
         self.n1 = (g(d + "norm1.weight"), g(d + "norm1.bias"))
         self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias"))
@@ -157,6 +176,7 @@ class StyleTransformerWeights:
         self.dec_proj = ops.pack_linear(g(a + "proj.weight"), g(a + "proj.bias"))
         self.dec_table = g(a + "relative_position_bias_table")
         self.dec_mlp = mlp(d + "mlp.")
+        self.pm_dec = mlp(d + "mlp.", a + "proj.")
         m = "decoder.decoder_MHA_for_sigma_and_mu."
         self.sm_k = ops.pack_linear(g(m + "Wk.weight"), g(m + "Wk.bias"))
         self.sm_vs = ops.pack_linear(g(m + "Wv_scale.weight"), g(m + "Wv_scale.bias"))
@@ -164,6 +184,7 @@ class StyleTransformerWeights:
         self.sm_proj = ops.pack_linear(g(m + "proj.weight"), g(m + "proj.bias"))
         self.sm_table = g(m + "relative_position_bias_table")
         self.last_mlp = mlp("decoder.last_MLP.")
+        self.pm_last = mlp("decoder.last_MLP.", m + "proj.")
 
 
 def _mlp_residual(x16, x32, fc, T, ws_: Workspace, out16):
@@ -205,26 +226,36 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
         ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
         ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
-        ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
-        _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
+        if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
+            ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
+        else:
+            ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
+            _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
         # Scale / Shift passes: q = k = processed Key (one softmax), v = Scale | Shift, residual from v
         ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
         ops.gemm(scale16, w.enc_v, T, out_bf16=vs16)
         ops.gemm(shift16, w.enc_v, T, out_bf16=vh16)
         ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
                              v2=vh16, out2=o2_16)
-        ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
-        _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
-        ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
-        _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
+        if FUSE_PROJ_MLP:
+            ops.mlp_fused(o16, w.pm_scale, T, res=scale32, out_f32=scale32, out_bf16=scale16, pre=True)
+            ops.mlp_fused(o2_16, w.pm_shift, T, res=shift32, out_f32=shift32, out_bf16=shift16, pre=True)
+        else:
+            ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
+            _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
+            ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
+            _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
 
         # ---------------- StyleDecoder ----------------
         ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
         ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
         ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
-        ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
-        ops.layernorm(x32, w.n2[0], w.n2[1], ln16, T, C)
-        _mlp_residual(ln16, x32, w.dec_mlp, T, ws_, None)  # x32 = Query
+        if FUSE_PROJ_MLP:
+            ops.mlp_fused(o16, w.pm_dec, T, res=x32, out_f32=x32, pre=True, ln_g=w.n2[0], ln_b=w.n2[1])  # x32 = Query
+        else:
+            ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
+            ops.layernorm(x32, w.n2[0], w.n2[1], ln16, T, C)
+            _mlp_residual(ln16, x32, w.dec_mlp, T, ws_, None)  # x32 = Query
         # Query is instance-normalised twice (:1056 then :468); Key once before Wk and once after (:1057, :520-530)
         ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True)
         ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16)
@@ -237,8 +268,11 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
         ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16)
         ops.gemm(o16, w.sm_proj, T, out_f32=sigma32)
-        ops.gemm(o2_16, w.sm_proj, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16)  # Query*sigma + mu (:1123)
-        _mlp_residual(x16, x32, w.last_mlp, T, ws_, x16)
+        if FUSE_PROJ_MLP:  # Query = Query*sigma + mu (:1123); Query += last_MLP(Query)
+            ops.mlp_fused(o2_16, w.pm_last, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16, pre=True)
+        else:
+            ops.gemm(o2_16, w.sm_proj, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16)  # Query*sigma + mu (:1123)
+            _mlp_residual(x16, x32, w.last_mlp, T, ws_, x16)
 
 
 # --------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@ and contiguity and raises instead of falling back.
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from typing import Optional
 
@@ -328,29 +329,45 @@ def loss_finalize(taps, lam: float, squared_style: bool, out3) -> None:
 
 
 class PackedMlp:
-    """fc1/fc2 of one MLP packed as the fused kernel's weight stream, plus the fp32 biases."""
+    """fc1/fc2 of one MLP packed as the fused kernel's weight stream, plus the fp32 biases.  With bpre set the stream also
+    carries the [C, C] attention-output projection in front (MstMlp::pre)."""
 
-    __slots__ = ("stream", "b1", "b2", "C")
+    __slots__ = ("stream", "b1", "b2", "C", "bpre")
 
-    def __init__(self, stream, b1, b2, Cdim):
-        self.stream, self.b1, self.b2, self.C = stream, b1, b2, Cdim
+    def __init__(self, stream, b1, b2, Cdim, bpre=None):
+        self.stream, self.b1, self.b2, self.C, self.bpre = stream, b1, b2, Cdim, bpre
 
 
-def pack_mlp(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> PackedMlp:
-    """nn.Linear weights fc1 [4C,C], fc2 [C,4C] (fp32) -> PackedMlp.  C must be 128 or 256."""
+def pack_mlp(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+             wpre: Optional[torch.Tensor] = None, bpre: Optional[torch.Tensor] = None) -> PackedMlp:
+    """nn.Linear weights fc1 [4C,C], fc2 [C,4C] (fp32) -> PackedMlp.  C must be 128 or 256.
+    wpre [C,C] / bpre [C]: the attention projection fused in front of the MLP (mlp_fused(..., pre=True))."""
     w1, w2 = w1.detach().contiguous(), w2.detach().contiguous()
     hidden, Cdim = w1.shape
     if hidden != 4 * Cdim or tuple(w2.shape) != (Cdim, hidden) or Cdim not in (128, 256):
         raise ValueError("pack_mlp: expected fc1 [4C,C], fc2 [C,4C] with C in {128, 256}")
-    nbytes = _lib.lib().mst_mlp_stream_bytes(Cdim)
+    if wpre is None:
+        nbytes = _lib.lib().mst_mlp_stream_bytes(Cdim)
+        stream = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w1.device)
+        _launch("mst_pack_mlp_weights", lambda: _lib.lib().mst_pack_mlp_weights(_ptr(w1, torch.float32, "w1"), _ptr(w2, torch.float32, "w2"),
+                                                                                stream.data_ptr(), Cdim, _stream()))
+        return PackedMlp(stream, b1.detach().float().contiguous(), b2.detach().float().contiguous(), Cdim)
+    wpre = wpre.detach().contiguous()
+    if tuple(wpre.shape) != (Cdim, Cdim) or bpre is None:
+        raise ValueError("pack_mlp: wpre must be [C,C] with a bias")
+    nbytes = _lib.lib().mst_mlp_stream_bytes_pre(Cdim)
     stream = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w1.device)
-    _launch("mst_pack_mlp_weights", lambda: _lib.lib().mst_pack_mlp_weights(_ptr(w1, torch.float32, "w1"), _ptr(w2, torch.float32, "w2"),
-                                                                            stream.data_ptr(), Cdim, _stream()))
-    return PackedMlp(stream, b1.detach().float().contiguous(), b2.detach().float().contiguous(), Cdim)
+    _launch("mst_pack_mlp_weights", lambda: _lib.lib().mst_pack_mlp_weights_pre(
+        _ptr(wpre, torch.float32, "wpre"), _ptr(w1, torch.float32, "w1"), _ptr(w2, torch.float32, "w2"), stream.data_ptr(), Cdim, _stream()))
+    return PackedMlp(stream, b1.detach().float().contiguous(), b2.detach().float().contiguous(), Cdim,
+                     bpre.detach().float().contiguous())
 
 
-def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out_bf16=None) -> None:
-    """out = res + fc2(gelu(fc1(A) + b1)) + b2, hidden activation kept on chip."""
+def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out_bf16=None,
+              pre: bool = False, mul=None, ln_g=None, ln_b=None) -> None:
+    """out = res + fc2(gelu(fc1(A) + b1)) + b2, hidden activation kept on chip.
+    pre=True (pm packed with wpre): x1 = res (*mul) + A.Wpre^T + bpre; out = x1 + mlp([LayerNorm](x1)) -- the whole
+    attention-output half of a transformer block in one kernel (see include/mst_b200.h)."""
     g = MstMlp()
     g.A, g.Wstream = _ptr(A, torch.bfloat16, "A"), pm.stream.data_ptr()
     g.b1, g.b2 = _ptr(pm.b1, torch.float32, "b1"), _ptr(pm.b2, torch.float32, "b2")
@@ -358,8 +375,18 @@ def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out
     g.M, g.C = M, pm.C
     g.lda = pm.C if lda is None else lda
     g.ld_res = g.ld_out32 = g.ld_out16 = pm.C
-    _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=16.0 * M * pm.C * pm.C,
-            desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}")
+    flops = 16.0 * M * pm.C * pm.C
+    if pre:
+        if pm.bpre is None:
+            raise ValueError("mlp_fused(pre=True) needs a PackedMlp built with wpre/bpre")
+        g.pre = 1
+        g.bpre, g.mul = _ptr(pm.bpre, torch.float32, "bpre"), _ptr(mul, torch.float32, "mul")
+        g.ln_g, g.ln_b = _ptr(ln_g, torch.float32, "ln_g"), _ptr(ln_b, torch.float32, "ln_b")
+        flops += 2.0 * M * pm.C * pm.C
+    elif pm.bpre is not None or mul is not None or ln_g is not None:
+        raise ValueError("mlp_fused: mul / ln / a pre-packed stream need pre=True")
+    _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=flops,
+            desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None} pre={int(pre)} ln={ln_g is not None} mul={mul is not None}")
 
 
 # --------------------------------------------------------------------------------------------

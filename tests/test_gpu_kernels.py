@@ -269,3 +269,33 @@ def test_mlp_fused(M, C):
     r = res.cuda()
     ops.mlp_fused(A.cuda(), pm, M, res=r, out_f32=r)  # in-place residual stream
     assert torch.allclose(r.cpu(), ref, atol=4e-3, rtol=4e-3)
+
+
+@pytest.mark.parametrize("M,C,ln,mul", [(128, 256, True, False), (1000, 256, False, False), (4096, 128, True, False), (333, 128, False, True),
+                                       (40000, 256, True, False), (40000, 128, True, False), (20000, 256, False, True), (19201, 128, False, False)])
+def test_proj_mlp_fused(M, C, ln, mul):
+    """Attention-output half of a transformer block in one kernel (MstMlp::pre): x1 = res (*mul) + A.Wp^T + bp;
+    out = x1 + mlp([LN](x1)).  Reference: fp32 torch on bf16-rounded operands, with the MLP input and the hidden activation
+    rounded to bf16 where the kernel rounds them."""
+    ops = _ops()
+    A = _rand(M, C, seed=80).bfloat16()
+    wp, bp = _rand(C, C, seed=81, scale=C ** -0.5), 0.1 * _rand(C, seed=82)
+    w1, b1 = _rand(4 * C, C, seed=83, scale=C ** -0.5), 0.1 * _rand(4 * C, seed=84)
+    w2, b2 = _rand(C, 4 * C, seed=85, scale=(4 * C) ** -0.5), 0.1 * _rand(C, seed=86)
+    res = _rand(M, C, seed=87) + 0.5  # non-zero row means: exercises the pairwise mean/M2 merge of the fused LayerNorm
+    m = (1 + 0.3 * _rand(M, C, seed=88)) if mul else None
+    g, be = (1 + 0.1 * _rand(C, seed=89), 0.1 * _rand(C, seed=90)) if ln else (None, None)
+    pm = ops.pack_mlp(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), wpre=wp.cuda(), bpre=bp.cuda())
+    x = res.cuda()
+    out16 = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    ops.mlp_fused(A.cuda(), pm, M, res=x, out_f32=x, out_bf16=out16, pre=True, mul=m.cuda() if mul else None,
+                  ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None)  # in-place residual stream
+    v = A.float() @ wp.bfloat16().float().T + bp
+    x1 = res * m + v if mul else res + v
+    xin = F.layer_norm(x1, (C,), g, be) if ln else x1
+    h = F.gelu(xin.bfloat16().float() @ w1.bfloat16().float().T + b1).bfloat16().float()
+    ref = x1 + h @ w2.bfloat16().float().T + b2
+    torch.cuda.synchronize()
+    err = (x.cpu() - ref).abs().max()
+    assert torch.allclose(x.cpu(), ref, atol=6e-3, rtol=6e-3), err
+    assert torch.allclose(out16.float().cpu(), ref, atol=4e-2, rtol=1e-2)
