@@ -41,6 +41,18 @@ def flops_per_image(size: int, layers: int) -> float:
     return (2 * g["swin"] + layers * g["st"] + g["cnn"]) * 1e9  # BASELINE.md section 2 (reference-algorithm FLOPs)
 
 
+def ncu_traffic(kernel: str, size: int, batch: int):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the family's launches of
+    one forward) from the committed `ncu --set full` capture of this workload (tools/ncu_traffic.py), or None."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(f"b{batch}_{size}", {}).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,7 +317,7 @@ def main():
         g = fam[dom]
         achieved = g["flops"] / (g["ms"] * 1e9)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                    "frac": achieved / sustained, "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                    "frac": achieved / sustained, "traffic": ncu_traffic(dom, args.size, batch), "peak_source": f"bf16_tflops_sustained, {peak_src}",
                     "launches_per_step": g["launches"], "share_of_step": g["ms"] / tot_ms,
                     "step": {"achieved": flops_per_image(args.size, args.layers) * batch / (ms_step * 1e9), "unit": "TFLOP/s",
                              "frac": flops_per_image(args.size, args.layers) * batch / (ms_step * 1e9) / sustained}}
