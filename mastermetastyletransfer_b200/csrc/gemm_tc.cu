@@ -12,6 +12,8 @@
 // buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mst {
@@ -55,9 +57,27 @@ constexpr int MAX_STAGES = 8;
 // conv_full gather; kept out of the inference instantiation so its register allocation and code size are untouched.
 template <bool EXT> struct ExtSel { typedef GemmNoExt type; };
 template <> struct ExtSel<true> { typedef GemmExt type; };
+// TMA = true: the A operand of a plain (F.linear) GEMM is fetched with ONE cp.async.bulk.tensor per stage (2-D tensor map over
+// A[M, lda], box 64 x 128, SWIZZLE_128B -- the hardware writes exactly the swizzled K-major UMMA image, zero-fills the M / K
+// tails) instead of 1024 16-byte cp.async: ncu showed the LSU data pipe as the busiest unit of the K <= 256 projections
+// (l1tex__data_pipe_lsu_wavefronts 64 %), and the 16-byte LDGSTS path tops out near 11 B/clk/SM against L2.
+MST_DEVINL void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+               : "memory");
+}
+struct TmaNone {};
+template <bool TMA> struct TmaSel { typedef TmaNone type; };
+template <> struct TmaSel<true> { typedef CUtensorMap type; };
+MST_DEVINL void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
 
-template <int BN, bool EXT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore p, const typename ExtSel<EXT>::type x_, const int num_tiles,
+template <int BN, bool EXT, bool TMA>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore p, const typename ExtSel<EXT>::type x_,
+                                                                  const __grid_constant__ typename TmaSel<TMA>::type tm_, const int num_tiles,
                                                                   const int res_stages) {
   using Cfg = GemmCfg<BN>;
   const bool resident = res_stages > 0;
@@ -67,6 +87,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
   __shared__ uint64_t full_bar[MAX_STAGES];
   __shared__ uint64_t empty_bar[MAX_STAGES];
   __shared__ uint64_t b_full_bar;
+  __shared__ uint64_t tma_bar[MAX_STAGES];  // conv TMA mode: tensor copies land here, the producer warp patches reflect borders, then arrives on full_bar
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -99,8 +120,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), NUM_PROD_WARPS * 32 + (resident ? 0 : 1));
+      mbar_init(smem_u32(&full_bar[s]), TMA ? 1 : NUM_PROD_WARPS * 32 + (resident ? 0 : 1));
       mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&tma_bar[s]), 1);
     }
     mbar_init(smem_u32(&b_full_bar), 1);
     for (int b = 0; b < 2; ++b) {
@@ -149,6 +171,84 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
     }
     int stage = 0;
     uint32_t pphase = 1;  // producer's view of empty_bar: a fresh barrier passes a wait on parity 1
+    if constexpr (TMA) {
+      if (conv) {
+        // 3x3 conv as implicit GEMM fed by TMA: k-block kb = 64 channels (c0 ..) of tap (ky, kx); the 128 tile rows are
+        // 128 / W whole image rows (or a 128-pixel row segment), each fetched with one 4-D tensor copy at pixel offset
+        // (kx - 1, ky - 1): out-of-image coordinates are zero-filled by the hardware (= zero padding).  Reflect padding:
+        // the row coordinate is reflected before the copy, and the one border pixel per row a kx != 1 tap reads out of the
+        // image is patched (its 128 bytes are requested before the copy lands, written after) by the issuing warp.
+        // Each ring stage is owned by one producer warp, so several stages are being issued / patched at any time.
+        const int pw = warp - NUM_EPI_WARPS;
+        const int Wb = p.W < BM ? p.W : BM;         // pixels per tensor copy
+        const int nrow = BM / Wb;                    // image rows (or 1 segment) per tile
+        const int hw = p.H * p.W;
+        const int kb_per_tap = p.Cin >> 6;
+        const uint32_t row_bytes = (uint32_t)Wb * 128u;
+        const uint32_t stage_tx = A_STAGE_BYTES + (resident ? 0 : Cfg::B_STAGE_BYTES);
+        long long it = 0;  // running (tile, k-block) count: ring position and the warp that owns it
+        for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt)) {
+          const int m0 = tt.m_tile * BM;
+          const int b = m0 / hw;
+          const int rem = m0 - b * hw;
+          const int y0 = rem / p.W, x0 = rem - y0 * p.W;
+          const uint8_t* wtile = Wbase + (size_t)tt.n_tile * nkb * Cfg::B_STAGE_BYTES;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = (int)(it % STAGES);
+            // a ring stage is owned by ONE warp, which therefore sees its uses in order: a parity wait cannot tell "phase
+            // u-1 complete" from "phase u-3 complete", so the waiter must itself have produced use u-1
+            if (s % NUM_PROD_WARPS != pw) continue;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            const int tap = kb / kb_per_tap, c0c = (kb - tap * kb_per_tap) << 6;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            // reflect patch: lane = (image row j of the tile, 16-byte chunk); source pixel x = 1 (kx = 0) or W - 2 (kx = 2)
+            const int j = lane >> 3, chunk = lane & 7;
+            const bool left = kx == 0 && x0 == 0, right = kx == 2 && x0 + Wb == p.W;
+            const bool patch = p.pad_mode == 1 && (left || right) && j < nrow;
+            uint4 pv = make_uint4(0, 0, 0, 0);
+            if (patch) {
+              int yy = y0 + j + ky - 1;
+              yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+              const int xs = left ? 1 : p.W - 2;
+              pv = *reinterpret_cast<const uint4*>(Abase + ((long long)(b * p.H + yy) * p.W + xs) * p.Cin + c0c + chunk * 8);
+            }
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+            const uint32_t a_stage = ring_base + s * stage_bytes;
+            if (lane == 0) {
+              mbar_arrive_expect_tx(smem_u32(&tma_bar[s]), stage_tx);
+              for (int r = 0; r < nrow; ++r) {
+                int yy = y0 + r + ky - 1;
+                if (p.pad_mode == 1) yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+                tma_load_4d(a_stage + r * row_bytes, &tm_, c0c, x0 + kx - 1, yy, b, smem_u32(&tma_bar[s]));
+              }
+              if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&tma_bar[s]));
+            }
+            mbar_wait(smem_u32(&tma_bar[s]), ph);
+            if (patch) {
+              const int row = j * Wb + (left ? 0 : Wb - 1);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_stage + sw128_offset(row, chunk)), "r"(pv.x), "r"(pv.y), "r"(pv.z), "r"(pv.w) : "memory");
+              fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+          }
+        }
+      } else if (t == 0) {  // one thread feeds the whole ring: a tensor copy for A (+ a bulk copy for the weight tile) per stage
+        for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt)) {
+          const int m0 = tt.m_tile * BM;
+          const uint8_t* wtile = Wbase + (size_t)tt.n_tile * nkb * Cfg::B_STAGE_BYTES;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int s = stage;
+            mbar_wait(smem_u32(&empty_bar[s]), pphase);
+            if (++stage == STAGES) { stage = 0; pphase ^= 1; }
+            const uint32_t a_stage = ring_base + s * stage_bytes;
+            mbar_arrive_expect_tx(smem_u32(&full_bar[s]), A_STAGE_BYTES + (resident ? 0 : Cfg::B_STAGE_BYTES));
+            tma_load_2d(a_stage, &tm_, kb * BK, m0, smem_u32(&full_bar[s]));
+            if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
+          }
+        }
+      }
+    } else
     for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt)) {
       const int n_tile = tt.n_tile, m0 = tt.m_tile * BM;
       // Per-row source bookkeeping, computed once per tile.
@@ -502,13 +602,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
 
 static int g_num_sms = 0;
 
-template <int BN, bool EXT>
-static int launch_gemm_ext(const MstGemm& g, cudaStream_t st) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda); NULL = unavailable
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("MST_GEMM_TMA");
+    if (e && e[0] == '0') return nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <int BN, bool EXT, bool TMA>
+static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename TmaSel<TMA>::type& tmap) {
   using Cfg = GemmCfg<BN>;
   constexpr int MAX_SMEM = 222 * 1024;  // + ~4.3 KB static (bias, barriers) <= 227 KB
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EXT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -548,14 +666,45 @@ static int launch_gemm_ext(const MstGemm& g, cudaStream_t st) {
     ext.gate = g.gate; ext.add16 = g.add16; ext.out_pre16 = g.out_pre16; ext.row_scale = g.row_scale;
     ext.gate_mode = g.gate_mode; ext.ld_gate = g.ld_gate; ext.rows_per_scale = g.rows_per_scale; ext.conv_full = g.conv_full;
   }
-  gemm_tc_kernel<BN, EXT><<<grid, GEMM_THREADS, smem, st>>>(core, ext, (int)tiles, res_stages);
+  gemm_tc_kernel<BN, EXT, TMA><<<grid, GEMM_THREADS, smem, st>>>(core, ext, tmap, (int)tiles, res_stages);
   return (int)cudaGetLastError();
 }
 
 template <int BN>
 static int launch_gemm(const MstGemm& g, cudaStream_t st) {
   const bool ext = g.out_pre16 || g.gate || g.add16 || g.row_scale || g.conv_full;
-  return ext ? launch_gemm_ext<BN, true>(g, st) : launch_gemm_ext<BN, false>(g, st);
+  if (ext) return launch_gemm_ext<BN, true, false>(g, st, TmaNone{});
+  if (g.a_mode == MST_A_PLAIN && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (g.lda * 2) % 16 == 0) {
+    if (EncodeTiledFn enc = tma_encoder()) {
+      alignas(64) CUtensorMap tmap;
+      const cuuint64_t gdim[2] = {(cuuint64_t)g.K, (cuuint64_t)g.M};
+      const cuuint64_t gstride[1] = {(cuuint64_t)g.lda * 2};
+      const cuuint32_t box[2] = {BK, BM};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box,
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) return launch_gemm_ext<BN, false, true>(g, st, tmap);
+    }
+  }
+  // 3x3 conv through TMA: 64-channel k-blocks inside one tap, tiles = whole image rows (or 128-pixel row segments)
+  if (g.a_mode == MST_A_CONV3X3 && !g.upsample && g.Cin % 64 == 0 && g.k_pad == g.K && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
+      ((g.W <= BM && BM % g.W == 0 && g.H % (BM / g.W) == 0 && (g.pad_mode == 0 || BM / g.W <= 4)) || g.W % BM == 0) && g.W >= 8 &&
+      g.M % BM == 0) {
+    if (EncodeTiledFn enc = tma_encoder()) {
+      alignas(64) CUtensorMap tmap;
+      const int B = g.M / (g.H * g.W);
+      const cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B};
+      const cuuint64_t gstride[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
+      const cuuint32_t box[4] = {BK, (cuuint32_t)(g.W < BM ? g.W : BM), 1, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box,
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) return launch_gemm_ext<BN, false, true>(g, st, tmap);
+    }
+  }
+  return launch_gemm_ext<BN, false, false>(g, st, TmaNone{});
 }
 
 // ---------------------------------------------------------------- weight packing (tile-blocked, pre-swizzled)

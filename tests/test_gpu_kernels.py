@@ -71,7 +71,10 @@ def test_gemm_epilogues():
     (3, 12, 20, 32, 64, "zeros", False, False), (1, 128, 128, 64, 64, "reflect", True, True),
     (1, 256, 256, 32, 32, "reflect", False, True), (2, 30, 34, 64, 256, "zeros", False, True),
     (3, 128, 128, 64, 32, "zeros", False, True), (2, 256, 256, 32, 32, "zeros", True, True), (2, 6, 128, 64, 64, "reflect", False, False),
-    (5, 3, 512, 32, 32, "reflect", False, True), (40, 8, 128, 32, 16, "zeros", False, False), (2, 64, 256, 64, 64, "reflect", True, True)])
+    (5, 3, 512, 32, 32, "reflect", False, True), (40, 8, 128, 32, 16, "zeros", False, False), (2, 64, 256, 64, 64, "reflect", True, True),
+    # TMA-fed implicit GEMM (Cin % 64 == 0, whole image rows per tile): the CNN decoder's reflect layers and VGG's zero-padded ones
+    (2, 64, 64, 128, 128, "reflect", False, True), (3, 32, 32, 256, 128, "reflect", False, True), (1, 64, 64, 128, 64, "reflect", False, True),
+    (3, 32, 32, 512, 512, "zeros", False, True), (2, 16, 16, 512, 512, "zeros", False, True), (1, 256, 256, 64, 64, "zeros", False, True)])
 @pytest.mark.parametrize("impl", ["gather", "band", "rows"])
 def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
     """H, W are the conv's output size; with up=True the stored input is [B,H/2,W/2,Cin].

@@ -32,3 +32,11 @@ if which in ("attn", "all"):
         ops.window_attention(q, k, v, o, table, B, H, H, 8, 8, 4, C, C, C, C)
 torch.cuda.synchronize()
 print("ok")
+if which == "conv128":
+    x = torch.randn(32, 64, 64, 128, device=dev).bfloat16()
+    pc = ops.pack_conv3x3(torch.randn(128, 128, 3, 3, device=dev) / 34, torch.randn(128, device=dev))
+    oc = torch.empty(32 * 64 * 64, 128, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(x, pc, 32 * 64 * 64, act=ops.ACT_RELU, out_bf16=oc, conv=dict(H=64, W=64, Cin=128, pad_mode=1, upsample=False, impl="gather"))
+    torch.cuda.synchronize()
+    print("ok")
