@@ -15,7 +15,7 @@ PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libmst_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + os.environ.get("MST_NVCC_EXTRA", "").split()
 
 
 def sources():

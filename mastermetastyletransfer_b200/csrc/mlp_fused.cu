@@ -58,7 +58,9 @@ struct MlpCfg {
 //     out = x1 + fc2(GELU(fc1(X)))                    x1 is pre-loaded into the fc2 accumulator (TMEM): fc2 accumulates onto it
 // The projection runs as C/128 extra "chunks" of the fc1 machinery (same [128 x C] x [C x 128] shape, same weight-stage
 // format, accumulators = the two fc1 TMEM buffers).  Its A operand O (the attention output tile) is loaded by the
-// producer warps: C = 128 has a buffer of its own, C = 256 borrows the two Hs buffers (free until the first GELU).
+// producer warps: C = 128 has a buffer of its own; C = 256 time-shares the X tile -- O(next tile) is loaded as soon as this
+// tile's last fc1 MMA has retired (so it arrives during the GELU / fc2 / output tail), and the projection epilogue overwrites it
+// with X only after BOTH projection chunks have finished reading it.
 template <int C, bool PRE>
 __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles) {
   using Cfg = MlpCfg<C>;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
   const uint32_t ring_base = hs_base + 2 * Cfg::HS_BYTES;
   // PRE: O = projection input tile (producers), X = fc1 input tile (epilogue warps)
   const uint32_t x_base = (PRE && C == 128) ? a_base + Cfg::A_BYTES : a_base;
-  const uint32_t o_base = C == 128 ? a_base : hs_base;
+  const uint32_t o_base = a_base;  // C = 256: O shares the X tile (free from the tile's last fc1 MMA until its projection epilogue)
   const int hidden = 4 * C;
   const int NCH = hidden / ML_HC;
   const int CPT = NPRE + NCH;  // fc1-type chunks per tile (the acc1 buffers alternate over this running count)
@@ -130,6 +132,17 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         }
       }
       cp_async_mbar_arrive_noinc(smem_u32(&a_full[ab]));
+      if constexpr (PRE) {
+        // The projection epilogue reads this tile's residual rows (and blend factors) row-per-lane; all SMs reach that phase
+        // at about the same time, which makes it HBM-bound while the bus idles during the GELU phases.  Pull the rows
+        // into L2 now (one bulk prefetch: a tile's rows are contiguous when ld_res == C), a tile ahead of their use.
+        if (t == 0 && p.ld_res == C) {
+          const int rows = min(128, p.M - m0);
+          const uint32_t bytes = (uint32_t)rows * C * 4u;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.res + (long long)m0 * C), "r"(bytes) : "memory");
+          if (p.mul) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.mul + (long long)m0 * C), "r"(bytes) : "memory");
+        }
+      }
     }
     cp_async_wait_all();
   } else if (warp == ML_STREAM_WARP) {
@@ -222,11 +235,13 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       }
       for (int t = 0; t < NCH; ++t) {
         mma1(a1++, a_tile);
+        if constexpr (PRE && C == 256)
+          if (t == NCH - 1) umma_commit_pred(smem_u32(&a_empty[0]));  // last reader of the X tile: the next tile's O may be loaded into it
         if (t >= 1) mma2(t - 1);
       }
       mma2(NCH - 1);
       umma_commit_pred(smem_u32(&acc2_full));
-      if constexpr (!(PRE && C == 128)) umma_commit_pred(smem_u32(&a_empty[ab]));  // PRE, C = 256: O aliases Hs -> free only now
+      if constexpr (!PRE) umma_commit_pred(smem_u32(&a_empty[ab]));
     }
     tc_fence_before();
   } else {
@@ -257,9 +272,20 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       }
     };
     int lt = 0;
+#ifdef MST_MLP_PROF
+    long long tA = 0, tGw = 0, tG = 0, tHw = 0, tFw = 0, tF = 0, t_all = clock64(), tm = 0, tAw = 0, tAld = 0, tAres = 0, tAst = 0, tm2 = 0;
+#define PROF_MARK2(acc) { long long n_ = clock64(); acc += n_ - tm2; tm2 = n_; }
+#define PROF_MARK(acc) { long long n_ = clock64(); acc += n_ - tm; tm = n_; }
+#else
+#define PROF_MARK(acc)
+#define PROF_MARK2(acc)
+#endif
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int row = tile * 128 + row_in_tile;
       const bool row_ok = row < p.M;
+#ifdef MST_MLP_PROF
+      tm = clock64();
+#endif
       if constexpr (PRE) {
         // ---------------- attention-output stage: x1 = res (*mul) + acc + bpre; X = [LN](x1) -> shared memory ----------------
         // x1 never goes to HBM: it is written (tcgen05.st) into the fc2 accumulator's TMEM columns, which are idle until
@@ -272,15 +298,36 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         const float* rp = p.res + (long long)row * p.ld_res + n_first;
         const float* mp = p.mul ? p.mul + (long long)row * p.ld_res + n_first : nullptr;
         // the residual (and blend factor) of the first 32 columns: requested before the accumulator wait, latency hidden
-        float4 rr[8];
-        auto fetch_res = [&](int col0) {
+        float rr[32];
+        const bool wide_rp = ((reinterpret_cast<uintptr_t>(p.res) | (uintptr_t)(p.ld_res * 4)) & 31) == 0;
+        auto fetch_res = [&](int col0) {  // 256-bit loads: one 32-byte sector per lane and instruction
+          if (!row_ok) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            rr[e] = row_ok ? *reinterpret_cast<const float4*>(rp + col0 + 4 * e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = 0; e < 32; ++e) rr[e] = 0.f;
+          } else if (wide_rp) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ld_global_256f(rp + col0 + 8 * e, rr + 8 * e);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 t4 = *reinterpret_cast<const float4*>(rp + col0 + 4 * e);
+              rr[4 * e] = t4.x; rr[4 * e + 1] = t4.y; rr[4 * e + 2] = t4.z; rr[4 * e + 3] = t4.w;
+            }
+          }
         };
+#ifdef MST_MLP_PROF
+        tm2 = clock64();
+#endif
         fetch_res(0);
-        if (lane == 0) mbar_wait(smem_u32(&acc1_full[pbuf]), (a1p >> 1) & 1);
+        if (lane == 0) {
+          mbar_wait(smem_u32(&acc1_full[pbuf]), (a1p >> 1) & 1);
+          if (C == 256) {  // X shares its buffer with O: both projection chunks must have finished reading O before X is written
+            const int a1o = a1p ^ 1;  // the other chunk of this tile (lt * CPT is even for C = 256)
+            mbar_wait(smem_u32(&acc1_full[a1o & 1]), (a1o >> 1) & 1);
+          }
+        }
         __syncwarp();
+        PROF_MARK2(tAw)
         tc_fence_after();
         const uint32_t tp = tmem_base + ((uint32_t)(quad * 32) << 16) + pbuf * ML_HC + (n_first & 127);
         const uint32_t tx = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + n_first;  // x1 home: fc2 accumulator
@@ -298,12 +345,13 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
               if (C == 256) mbar_arrive(smem_u32(&acc1_empty[pbuf ^ 1]));  // the other chunk: not read by this warp
             }
           }
+          PROF_MARK2(tAld)
           float x[32];
           const float4* bp4 = reinterpret_cast<const float4*>(p.bpre + n_first + col0);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float4 b4 = __ldg(bp4 + e);
-            const float4 r = rr[e];
+            const float4 r = make_float4(rr[4 * e], rr[4 * e + 1], rr[4 * e + 2], rr[4 * e + 3]);
             float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
             if (mp && row_ok) m = *reinterpret_cast<const float4*>(mp + col0 + 4 * e);
             x[4 * e] = fmaf(r.x, m.x, __uint_as_float(v[4 * e]) + b4.x);
@@ -311,6 +359,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
             x[4 * e + 2] = fmaf(r.z, m.z, __uint_as_float(v[4 * e + 2]) + b4.z);
             x[4 * e + 3] = fmaf(r.w, m.w, __uint_as_float(v[4 * e + 3]) + b4.w);
           }
+          PROF_MARK2(tAres)
           if (col0 + 32 < CPW) fetch_res(col0 + 32);  // next chunk's residual while this one is stored / reduced
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(x[e]);
@@ -323,6 +372,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           }
         }
         tmem_wait_st();
+        PROF_MARK2(tAst)
         if (ln) {
           // LayerNorm over the C columns of the row: this thread owns CPW of them, the three other warps of the TMEM
           // quadrant the rest.  Local mean / centred M2 (x1 re-read from TMEM), one exchange through the quadrant's own rows
@@ -375,6 +425,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&x_full));
+        PROF_MARK(tA)
       }
       for (int j = 0; j < NCH; ++j) {
         const int a1 = lt * CPT + NPRE + j;              // running fc1-chunk count -> acc1 buffer
@@ -382,6 +433,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         const int gc = lt * NCH + j, buf = j & 1, u = gc >> 1;  // Hs buffer
         if (lane == 0) mbar_wait(smem_u32(&acc1_full[abuf]), au & 1);
         __syncwarp();
+        PROF_MARK(tGw)
         tc_fence_after();
         // this warp's 32 hidden units of the chunk: columns part*32 .. of the [128 x 128] Hs tile
         uint32_t v[32];
@@ -401,16 +453,20 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           h[4 * e + 2] = gelu_erf(__uint_as_float(v[4 * e + 2]) + b4.z);
           h[4 * e + 3] = gelu_erf(__uint_as_float(v[4 * e + 3]) + b4.w);
         }
+        PROF_MARK(tG)
         if (lane == 0) mbar_wait(smem_u32(&hs_empty[buf]), (u & 1) ^ 1);  // MMA2(j-2) has finished reading this buffer
         __syncwarp();
+        PROF_MARK(tHw)
         store_tile32(hs_base + buf * Cfg::HS_BYTES, part * 32, h);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hs_full[buf]));
+        PROF_MARK(tG)
       }
       // ---- tile end: fc2 accumulator -> + b2 + residual -> global ----
       if (lane == 0) mbar_wait(smem_u32(&acc2_full), lt & 1);
       __syncwarp();
+      PROF_MARK(tFw)
       tc_fence_after();
       const bool wide_res = resp && ((reinterpret_cast<uintptr_t>(resp) | (uintptr_t)(ld_resp * 4)) & 31) == 0;
       const bool wide_o32 = p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) | (uintptr_t)(p.ld_out32 * 4)) & 31) == 0;
@@ -490,7 +546,15 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           }
         }
       }
+      PROF_MARK(tF)
     }
+#ifdef MST_MLP_PROF
+    if (blockIdx.x == 1 && lane == 0 && (warp == 0 || warp == 9))
+      printf("   A detail: wait %lld tmem_ld %lld bias+res %lld st %lld\n", tAw, tAld, tAres, tAst);
+    if (blockIdx.x == 1 && lane == 0 && (warp == 0 || warp == 9))
+      printf("mlp prof C=%d pre=%d warp %d tiles %d total %lld | A %lld | gelu: wait %lld work %lld hs_wait %lld | final: wait %lld work %lld\n", C, (int)PRE, warp, lt,
+             clock64() - t_all, tA, tGw, tG, tHw, tFw, tF);
+#endif
     tc_fence_before();
   }
   __syncthreads();
