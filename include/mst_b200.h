@@ -194,6 +194,8 @@ int mst_patch_embed_ln(const float* img, const float* w, const float* b, const f
 
 
 /* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
+/* nn.Upsample(scale_factor=2, mode='nearest') on a bf16 NHWC tensor: x [B,H,W,C] -> y [B,2H,2W,C] (decoder.py:27), C % 8 == 0. */
+int mst_upsample2x_nhwc(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream);
 int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -110,6 +110,7 @@ SYMBOLS = {
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
+    "mst_upsample2x_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mst_opt_chunk_elems": (_I, []),
     "mst_adam_step": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),
     "mst_adam_step_dev": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, _P, _I, _P]),

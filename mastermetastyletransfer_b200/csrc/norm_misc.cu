@@ -350,6 +350,27 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(const float* __
   }
 }
 
+// ---------------------------------------------------------------- nearest x2 upsample, bf16 NHWC
+// nn.Upsample(scale_factor=2, mode='nearest') (codes/decoder.py:27) for the one decoder conv whose input has >= 128 channels:
+// the gathered implicit GEMM folds the upsample into its addresses, the TMA-fed one cannot (a tensor copy cannot repeat
+// pixels), and materialising 33 MB is cheaper than the difference (105 -> 66 us).  One thread = 16 bytes of a source pixel.
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long n_chunks, int H, int W, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks) return;
+  const int c = (int)(i % C8);
+  const long long pix = i / C8;
+  const int xs = (int)(pix % W);
+  const long long t = pix / W;
+  const int ys = (int)(t % H);
+  const long long b = t / H;
+  const uint4 v = x[i];
+  uint4* o = y + (((b * 2 * H + 2 * ys) * (2LL * W)) + 2 * xs) * C8 + c;
+  o[0] = v;
+  o[C8] = v;
+  o[2LL * W * C8] = v;
+  o[2LL * W * C8 + C8] = v;
+}
+
 // ---------------------------------------------------------------- packing / casts
 __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -431,6 +452,15 @@ extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float*
   if (e != cudaSuccess) return (int)e;
   if (y16) return mst_layernorm(x, gamma1, beta1, y16, (int)total, 128, stream);
   return 0;
+}
+
+extern "C" int mst_upsample2x_nhwc(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return MST_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return MST_ERR_BAD_ARG;
+  const long long n = (long long)B * H * W * (C / 8);
+  upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), n, H, W,
+                                                                                  C / 8);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream) {

@@ -203,11 +203,14 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     C = w.C
     T = B * H * W
     key32, scale32, shift32 = ws_.f32("st_key32", T, C), ws_.f32("st_scale32", T, C), ws_.f32("st_shift32", T, C)
-    key16, scale16, shift16 = ws_.bf16("st_key16", T, C), ws_.bf16("st_scale16", T, C), ws_.bf16("st_shift16", T, C)
+    key16 = ws_.bf16("st_key16", T, C)
+    ss16 = ws_.bf16("st_scale_shift16", 2 * T, C)  # Scale | Shift back to back: the shared Wv projects both in one GEMM
+    scale16, shift16 = ss16[:T], ss16[T:]
     x32 = out32.view(T, C)
     x16 = out16.view(T, C) if out16 is not None else ws_.bf16("st_x16", T, C)
     qkv = ws_.bf16("st_qkv", T, 3 * C)
-    vs16, vh16 = ws_.bf16("st_vs", T, C), ws_.bf16("st_vh", T, C)
+    vsh16 = ws_.bf16("st_vs_vh", 2 * T, C)
+    vs16, vh16 = vsh16[:T], vsh16[T:]
     o16, o2_16 = ws_.bf16("st_o", T, C), ws_.bf16("st_o2", T, C)
     ln16 = ws_.bf16("st_ln", T, C)
     qhat16, khat16 = ws_.bf16("st_qhat", T, C), ws_.bf16("st_khat", T, C)
@@ -233,8 +236,7 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
             _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
         # Scale / Shift passes: q = k = processed Key (one softmax), v = Scale | Shift, residual from v
         ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
-        ops.gemm(scale16, w.enc_v, T, out_bf16=vs16)
-        ops.gemm(shift16, w.enc_v, T, out_bf16=vh16)
+        ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
         ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
                              v2=vh16, out2=o2_16)
         if FUSE_PROJ_MLP:
@@ -299,6 +301,11 @@ def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace,
     last = len(w.convs) - 1
     for i, (pm, cin, up, relu) in enumerate(w.convs):
         if up:
+            if cin >= 128 and cin % 64 == 0:
+                # wide layer: materialise the nearest-x2 upsample so the conv can be fed by tensor copies (TMA cannot repeat pixels)
+                big = ws_.bf16("cnn_up", B * 4 * h * wd, cin)
+                ops.upsample2x_nhwc(cur, big, B, h, wd, cin)
+                cur, up = big, False
             h, wd = 2 * h, 2 * wd
         M = B * h * wd
         conv = dict(H=h, W=wd, Cin=cin, pad_mode=PAD_REFLECT, upsample=up)

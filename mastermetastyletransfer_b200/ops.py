@@ -56,7 +56,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
-             "mst_cast_bf16": "cast_bf16_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
+             "mst_cast_bf16": "cast_bf16_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
              "mst_loss_finalize": "loss_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
@@ -270,6 +270,12 @@ def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=No
         _ptr(gamma1, torch.float32, "gamma1"), _ptr(beta1, torch.float32, "beta1"), _ptr(y16, torch.bfloat16, "y16"),
         B, S, int(exact), _stream()),
             nbytes=4.0 * B * S * S * 3 + (4.0 + (2.0 if y16 is not None else 0.0)) * B * (S // 4) ** 2 * 128)
+
+
+def upsample2x_nhwc(x, y, B, H, W, C_) -> None:
+    """nearest x2 upsample of a bf16 NHWC tensor [B,H,W,C] -> [B,2H,2W,C]."""
+    _launch("mst_upsample2x_nhwc", lambda: _lib.lib().mst_upsample2x_nhwc(_ptr(x, torch.bfloat16, "x"), _ptr(y, torch.bfloat16, "y"), B, H, W, C_, _stream()),
+            nbytes=2.0 * 5 * B * H * W * C_)
 
 
 def cast_bf16(x, y) -> None:

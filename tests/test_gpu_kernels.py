@@ -239,6 +239,15 @@ def test_patch_embed(S, exact):
     assert torch.equal(out2, out)
 
 
+def test_upsample2x_nhwc():
+    ops = _ops()
+    B, H, W, C = 3, 5, 7, 128
+    x = _rand(B, H, W, C, seed=91).bfloat16().cuda()
+    y = torch.empty(B, 2 * H, 2 * W, C, device="cuda", dtype=torch.bfloat16)
+    ops.upsample2x_nhwc(x, y, B, H, W, C)
+    assert torch.equal(y, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+
+
 def test_bad_arguments_raise():
     ops = _ops()
     A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)

@@ -21,7 +21,7 @@ for r in rows[2:]:
         if k in d:
             print(f"    {k} = {d[k]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
+rows = list(csv.reader(io.StringIO(src))) if nl > 0 else []
 if rows:
     h = rows[0]
     try:
