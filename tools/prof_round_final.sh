@@ -15,7 +15,7 @@ python tools/prof_forward.py > gpurun_out/plain2_${TAG}.log 2>&1 || exit 1
 ncu --metrics $M --clock-control none -k "$K" --csv --log-file gpurun_out/forward_metrics_${TAG}.csv python tools/prof_forward.py > gpurun_out/ncu_${TAG}.log 2>&1
 # hottest SASS of the three heaviest families: one representative launch each (re-captured alone: small reports)
 # label:kernel regex:launches to skip (second forward: 9 mlp_fused, 8 window_attn, 19 gemm_tc, 4 conv_rows launches per forward)
-for spec in "mlp_c128:mlp_fused:9" "attn_ws7:window_attn:8" "gemm_qkv_tma:gemm_tc:19" "gemm_conv128_tma:gemm_tc:35" "conv_rows_32ch:conv_rows:6"; do
+for spec in "mlp_c128:mlp_fused:9" "attn_ws7:window_attn:8" "gemm_qkv_tma:gemm_tc:19" "gemm_conv128to64_tma:gemm_tc:34" "conv_rows_32ch:conv_rows:6"; do
   label=${spec%%:*}; rest=${spec#*:}; name=${rest%%:*}; skip=${rest##*:}
   ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -f -o /tmp/one_$label python tools/prof_forward.py > /dev/null 2>&1
   python tools/ncu_report_summary.py /tmp/one_$label.ncu-rep 0 > gpurun_out/ncu_full_${label}_${TAG}.txt 2>&1
