@@ -227,7 +227,7 @@ MST_DEVINL void pe_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint3
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(const float* __restrict__ img, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) patch_embed_mma_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ out,
                                                                  const float* __restrict__ gamma1, const float* __restrict__ beta1,
@@ -242,15 +242,14 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(const float* __
     prm[3][i] = y16 ? make_float2(gamma1[2 * i], gamma1[2 * i + 1]) : make_float2(0.f, 0.f);
     prm[4][i] = y16 ? make_float2(beta1[2 * i], beta1[2 * i + 1]) : make_float2(0.f, 0.f);
   }
-  uint32_t bw[3][16][2];  // B fragments: B[k][n] = W[n][ci*16 + k]
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      const float* wp = w + (nt * 8 + g) * 48 + ci * 16 + 2 * tg;
-      bw[ci][nt][0] = pe_pack(wp[0], wp[1]);
-      bw[ci][nt][1] = pe_pack(wp[8], wp[9]);
-    }
+  // B fragments (B[k][n] = W[n][ci*16 + k]) in shared memory, one uint2 per (ci, n-tile, lane): conflict-free 64-bit loads.
+  // Keeping them in registers (96 per thread) capped the kernel at 8 warps per SM; it is latency-bound on the image loads.
+  __shared__ uint2 bw_s[3 * 16][32];
+  for (int i = threadIdx.x; i < 3 * 16 * 32; i += blockDim.x) {
+    const int ln = i & 31, nt = (i >> 5) & 15, ci = i >> 9;
+    const float* wp = w + (nt * 8 + (ln >> 2)) * 48 + ci * 16 + 2 * (ln & 3);
+    bw_s[ci * 16 + nt][ln] = make_uint2(pe_pack(wp[0], wp[1]), pe_pack(wp[8], wp[9]));
+  }
   __syncthreads();
   const int P = S >> 2;
   const int gpr = P >> 4;  // 16-token groups per patch row
@@ -302,8 +301,9 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(const float* __
       }
 #pragma unroll
       for (int nt = 0; nt < 16; ++nt) {
-        pe_mma(acc[nt], ah, bw[ci][nt][0], bw[ci][nt][1]);
-        pe_mma(acc[nt], al, bw[ci][nt][0], bw[ci][nt][1]);
+        const uint2 bq = bw_s[ci * 16 + nt][lane];
+        pe_mma(acc[nt], ah, bq.x, bq.y);
+        pe_mma(acc[nt], al, bq.x, bq.y);
       }
     }
     const long long tok0 = (long long)gi * 16 + g;  // rows g and g+8 of the group
@@ -439,7 +439,7 @@ extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float*
     const long long groups = total / 16;
     if (groups > 0x7fffffffLL) return MST_ERR_BAD_ARG;
     const long long want = (groups + 7) / 8;
-    const unsigned grid = (unsigned)(want < sms ? want : sms);
+    const unsigned grid = (unsigned)(want < 2LL * sms ? want : 2LL * sms);
     patch_embed_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, w, b, gamma, beta, x, gamma1, beta1,
                                                                    reinterpret_cast<bf16*>(y16), S, (int)groups);
     return (int)cudaGetLastError();

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
   constexpr int N = WS * WS;   // real tokens per window
   constexpr int NP = 64;       // rows of the staged tiles (N padded to a multiple of 16)
   constexpr int NT = (2 * WS - 1) * (2 * WS - 1);
+  constexpr int NTV = (N + 7) / 8;  // 8-wide key tiles holding real keys (7 of 8 for 7x7 windows): the rest is never computed
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int heads = a.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
         uint32_t b0, b1, b2, b3;
         ldsm_x4(k_base + (krow * AT_LD + kcol) * 2, b0, b1, b2, b3);
         mma_bf16_16816(sc[2 * np], qa[ks], b0, b1);
-        mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
+        if (2 * np + 1 < NTV) mma_bf16_16816(sc[2 * np + 1], qa[ks], b2, b3);
       }
     }
     // ---- scale + relative-position bias + shift mask, row max ----
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
     const int li0 = lab_s[i0], li1 = lab_s[i1];
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NTV; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float s0 = -INFINITY, s1 = -INFINITY;
@@ -235,12 +236,17 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
     uint32_t pa[4][4];  // P as bf16 A fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p00 = exp2f_fast(sc[nt][0] - mx0), p01 = exp2f_fast(sc[nt][1] - mx0);
-      const float p10 = exp2f_fast(sc[nt][2] - mx1), p11 = exp2f_fast(sc[nt][3] - mx1);
-      sum0 += p00 + p01;
-      sum1 += p10 + p11;
-      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p00, p01);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p10, p11);
+      if (nt < NTV) {
+        const float p00 = exp2f_fast(sc[nt][0] - mx0), p01 = exp2f_fast(sc[nt][1] - mx0);
+        const float p10 = exp2f_fast(sc[nt][2] - mx1), p11 = exp2f_fast(sc[nt][3] - mx1);
+        sum0 += p00 + p01;
+        sum1 += p10 + p11;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p00, p01);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p10, p11);
+      } else {  // keys past the window: probability 0
+        pa[nt >> 1][(nt & 1) * 2 + 0] = 0u;
+        pa[nt >> 1][(nt & 1) * 2 + 1] = 0u;
+      }
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
