@@ -228,6 +228,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the ONE JSON line (NCCL prints its banner to stdout)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
