@@ -155,6 +155,8 @@ typedef struct MstWindowAttn {
   const float *pad_q, *pad_k, *pad_v, *pad_v2;
   int B, H, W, heads, ws, shift;
   int ldq, ldk, ldv, ldo;
+  int pad_k_stride; /* 0: pad_k is [C]; C: pad_k is [B, C], one vector per image (the instance-normalised Wk bias of the
+                       sigma/mu attention on a padded map, style_transformer.py:520-530) */
 } MstWindowAttn;
 
 int mst_window_attention(const MstWindowAttn* a, void* stream);
@@ -179,6 +181,11 @@ int mst_layernorm(const float* x, const float* gamma, const float* beta, mst_bf1
 int mst_patch_merge_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int B, int H, int W,
                               int C, void* stream);
 int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream);
+/* Same statistics over a map that additionally holds n_pad tokens whose value is pad_val[c] (the zero-padded positions of a
+ * window-padded map after a Linear: value = its bias; style_transformer.py:520-530 normalises Wk.K over the PADDED map).
+ * pad_norm [B, C] (optional) receives the normalised padding value (pad_val - mean) * rstd. */
+int mst_instnorm_stats_padded(const float* x, float* mean, float* rstd, int B, int T, int C, int n_pad, const float* pad_val,
+                              float* pad_norm, void* stream);
 int mst_instnorm_apply(const float* x, const float* mean, const float* rstd, mst_bf16* y16, float* y32, int B, int T,
                        int C, void* stream);
 

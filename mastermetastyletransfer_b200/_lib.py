@@ -57,7 +57,7 @@ class MstWindowAttn(C.Structure):
         ("out", C.c_void_p), ("out2", C.c_void_p), ("bias_table", C.c_void_p),
         ("pad_q", C.c_void_p), ("pad_k", C.c_void_p), ("pad_v", C.c_void_p), ("pad_v2", C.c_void_p),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("heads", C.c_int), ("ws", C.c_int), ("shift", C.c_int),
-        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
+        ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int), ("pad_k_stride", C.c_int),
     ]
 
 
@@ -106,6 +106,7 @@ SYMBOLS = {
     "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_merge_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_instnorm_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "mst_instnorm_stats_padded": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "mst_instnorm_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

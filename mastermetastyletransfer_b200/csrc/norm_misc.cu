@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // as torch's InstanceNorm2d does (biased variance); the second pass re-reads the slice from L1/L2.
 constexpr int IN_WARPS = 16;
 __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
-                                                                        float* __restrict__ rstd, int T, int C, int twice) {
+                                                                        float* __restrict__ rstd, int T, int C, int twice, int n_pad,
+                                                                        const float* __restrict__ pad_val, float* __restrict__ pad_norm) {
   __shared__ float red[IN_WARPS][33];
   const int groups = C / 32;
   const int b = blockIdx.x / groups;
@@ -84,7 +85,10 @@ __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const flo
   float m = 0.f;
 #pragma unroll
   for (int w = 0; w < IN_WARPS; ++w) m += red[w][lane];
-  m /= (float)T;
+  // n_pad extra tokens of value pad_val[c]: the zero-padded positions of a window-padded map after a Linear (= its bias)
+  const float pv = n_pad > 0 ? pad_val[c] : 0.f;
+  const float n_tot = (float)(T + n_pad);
+  m = (m + (float)n_pad * pv) / n_tot;
   __syncthreads();
   float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
   t = warp;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const flo
     float var = 0.f;
 #pragma unroll
     for (int w = 0; w < IN_WARPS; ++w) var += red[w][lane];
-    var /= (float)T;
+    var = (var + (float)n_pad * (pv - m) * (pv - m)) / n_tot;
     float r = 1.0f / sqrtf(var + 1e-5f);
     if (twice) {
       // IN(IN(x)): the once-normalised tensor has mean 0 and variance var*r^2, so the second pass
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const flo
     }
     mean[(long long)b * C + c] = m;
     rstd[(long long)b * C + c] = r;
+    if (pad_norm) pad_norm[(long long)b * C + c] = (pv - m) * r;
   }
 }
 
@@ -408,7 +413,14 @@ extern "C" int mst_patch_merge_layernorm(const float* x, const float* gamma, con
 
 extern "C" int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream) {
   if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0) return MST_ERR_BAD_ARG;
-  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice);
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice, 0, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_instnorm_stats_padded(const float* x, float* mean, float* rstd, int B, int T, int C, int n_pad, const float* pad_val,
+                                         float* pad_norm, void* stream) {
+  if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0 || n_pad < 0 || (n_pad > 0 && !pad_val)) return MST_ERR_BAD_ARG;
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, 0, n_pad, pad_val, pad_norm);
   return (int)cudaGetLastError();
 }
 

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) window_attn_kernel(const MstWin
           uint32_t* vp = reinterpret_cast<uint32_t*>(&vv); uint32_t* wp = reinterpret_cast<uint32_t*>(&v2v);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (a.pad_k) kp[e] = pack_bf16(a.pad_k[cc + 2 * e], a.pad_k[cc + 2 * e + 1]);
+            if (a.pad_k) kp[e] = pack_bf16(a.pad_k[(long long)b * a.pad_k_stride + cc + 2 * e], a.pad_k[(long long)b * a.pad_k_stride + cc + 2 * e + 1]);
             if (a.pad_v) vp[e] = pack_bf16(a.pad_v[cc + 2 * e], a.pad_v[cc + 2 * e + 1]);
             if (dual && a.pad_v2) wp[e] = pack_bf16(a.pad_v2[cc + 2 * e], a.pad_v2[cc + 2 * e + 1]);
           }
@@ -336,7 +336,7 @@ extern "C" int mst_window_attention(const MstWindowAttn* a, void* stream) {
   if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->heads <= 0 || a->heads > 32) return MST_ERR_BAD_ARG;
   if (a->heads % AT_WARPS != 0) return MST_ERR_UNSUPPORTED;
   if ((a->ldq | a->ldk | a->ldv | a->ldo) % 8 != 0) return MST_ERR_BAD_ARG;
-  if (a->shift < 0 || a->shift >= a->ws) return MST_ERR_BAD_ARG;
+  if (a->shift < 0 || a->shift >= a->ws || a->pad_k_stride < 0) return MST_ERR_BAD_ARG;
   const WinGeom g = make_geom(a->H, a->W, a->ws, a->shift);
   cudaStream_t st = (cudaStream_t)stream;
   if (a->ws == 8) return launch_attn<8>(*a, g, st);

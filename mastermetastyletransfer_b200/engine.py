@@ -181,6 +181,7 @@ class StyleTransformerWeights:
         self.sm_k = ops.pack_linear(g(m + "Wk.weight"), g(m + "Wk.bias"))
         self.sm_vs = ops.pack_linear(g(m + "Wv_scale.weight"), g(m + "Wv_scale.bias"))
         self.sm_vh = ops.pack_linear(g(m + "Wv_shift.weight"), g(m + "Wv_shift.bias"))
+        self.sm_pad = (g(m + "Wk.bias"), g(m + "Wv_scale.bias"), g(m + "Wv_shift.bias"))
         self.sm_proj = ops.pack_linear(g(m + "proj.weight"), g(m + "proj.bias"))
         self.sm_table = g(m + "relative_position_bias_table")
         self.last_mlp = mlp("decoder.last_MLP.")
@@ -198,8 +199,12 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     """Fc, Fs fp32 [B,H,W,C] -> out32 fp32 [B,H,W,C] (+ bf16 copy for the CNN decoder).
     Follows StyleTransformer.forward (:1229-1245) -> StyleEncoder.forward (:855-882) ->
     StyleDecoder.forward (:1045-1059,1123-1128)."""
-    if H % win or W % win:
-        raise ValueError("style transformer feature map must be a multiple of the window (7x7 padded path: see DESIGN.md)")
+    # Feature maps that are not a multiple of the window (the reference CLI's default 7x7 windows on 32^2 / 64^2 maps,
+    # train.py:703-711) are zero-padded at the bottom/right inside the attention (style_transformer.py:77-87): a padded
+    # token's projection is the bias, and the sigma/mu attention normalises Wk.K over the PADDED map (:520-530).
+    padded = bool(H % win or W % win)
+    Hp, Wp = -(-H // win) * win, -(-W // win) * win
+    n_pad = Hp * Wp - H * W
     C = w.C
     T = B * H * W
     key32, scale32, shift32 = ws_.f32("st_key32", T, C), ws_.f32("st_scale32", T, C), ws_.f32("st_shift32", T, C)
@@ -216,6 +221,7 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     qhat16, khat16 = ws_.bf16("st_qhat", T, C), ws_.bf16("st_khat", T, C)
     kk32, sigma32 = ws_.f32("st_kk32", T, C), ws_.f32("st_sigma32", T, C)
     mean, rstd = ws_.f32("st_mean", B, C), ws_.f32("st_rstd", B, C)
+    kpad = ws_.f32("st_kpad", B, C)
 
     x32.copy_(fc32.reshape(T, C))
     key32.copy_(fs32.reshape(T, C))
@@ -228,7 +234,8 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     for _ in range(k):
         # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
         ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
-        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
+        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
+                             pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
         if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
             ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
         else:
@@ -238,7 +245,7 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
         ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
         ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
-                             v2=vh16, out2=o2_16)
+                             v2=vh16, out2=o2_16, pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2], pad_v2=w.enc_pad[2])
         if FUSE_PROJ_MLP:
             ops.mlp_fused(o16, w.pm_scale, T, res=scale32, out_f32=scale32, out_bf16=scale16, pre=True)
             ops.mlp_fused(o2_16, w.pm_shift, T, res=shift32, out_f32=shift32, out_bf16=shift16, pre=True)
@@ -251,7 +258,8 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         # ---------------- StyleDecoder ----------------
         ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
         ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
-        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C)
+        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
+                             pad_q=w.dec_pad[0], pad_k=w.dec_pad[1], pad_v=w.dec_pad[2])
         if FUSE_PROJ_MLP:
             ops.mlp_fused(o16, w.pm_dec, T, res=x32, out_f32=x32, pre=True, ln_g=w.n2[0], ln_b=w.n2[1])  # x32 = Query
         else:
@@ -264,11 +272,16 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         ops.instnorm_stats(key32, mean, rstd, B, H * W, C)
         ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16)
         ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
-        ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
+        if padded:  # statistics over the padded map: its n_pad extra tokens all hold Wk.0 + bk = bk
+            ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad)
+        else:
+            ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
         ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16)
         ops.gemm(scale16, w.sm_vs, T, out_bf16=vs16)
         ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
-        ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16)
+        # padded tokens: q = 0 (no Q projection, :511-514), k = the normalised bias (per image), v = the value biases
+        ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16,
+                             pad_k=kpad if padded else None, pad_v=w.sm_pad[1], pad_v2=w.sm_pad[2], pad_k_per_image=padded)
         ops.gemm(o16, w.sm_proj, T, out_f32=sigma32)
         if FUSE_PROJ_MLP:  # Query = Query*sigma + mu (:1123); Query += last_MLP(Query)
             ops.mlp_fused(o2_16, w.pm_last, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16, pre=True)

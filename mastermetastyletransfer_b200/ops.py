@@ -209,7 +209,7 @@ def _use_band(conv: dict, n_pad: int) -> bool:
 
 
 def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
-                     v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None) -> None:
+                     v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None, pad_k_per_image: bool = False) -> None:
     a = MstWindowAttn()
     a.q, a.k, a.v = _ptr(q, torch.bfloat16, "q"), _ptr(k, torch.bfloat16, "k"), _ptr(v, torch.bfloat16, "v")
     a.v2, a.out, a.out2 = _ptr(v2, torch.bfloat16, "v2"), _ptr(out, torch.bfloat16, "out"), _ptr(out2, torch.bfloat16, "out2")
@@ -218,6 +218,7 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
     a.pad_v, a.pad_v2 = _ptr(pad_v, torch.float32, "pad_v"), _ptr(pad_v2, torch.float32, "pad_v2")
     a.B, a.H, a.W, a.heads, a.ws, a.shift = B, H, W, heads, ws, shift
     a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+    a.pad_k_stride = heads * 32 if pad_k_per_image else 0
     n_tok = ws * ws
     n_win = B * (-(-H // ws)) * (-(-W // ws))
     _launch("mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
@@ -252,6 +253,14 @@ def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False) -> None:
     _launch("mst_instnorm_stats", lambda: _lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
                                         _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), _stream()),
             nbytes=4.0 * B * T * Cdim)
+
+
+def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None) -> None:
+    """InstanceNorm statistics over a map with n_pad extra tokens of value pad_val[c] (window-padded map after a Linear);
+    pad_norm [B,C] receives the normalised padding value."""
+    _launch("mst_instnorm_stats", lambda: _lib.lib().mst_instnorm_stats_padded(
+        _ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"), _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, n_pad,
+        _ptr(pad_val, torch.float32, "pad_val"), _ptr(pad_norm, torch.float32, "pad_norm"), _stream()), nbytes=4.0 * B * T * Cdim)
 
 
 def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None) -> None:

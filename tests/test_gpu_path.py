@@ -89,6 +89,28 @@ def test_full_forward_vs_oracle_and_golden(model, sd, k, golden_dir):
     assert ((mine - g).abs().max() / (g.max() - g.min())).item() <= IMG_TOL
 
 
+@pytest.mark.parametrize("size,k", [(128, 1), (128, 2), (256, 1)])
+def test_full_forward_7x7_windows_vs_oracle_and_golden(size, k, golden_dir):
+    """7x7 style-transformer windows (the reference CLI default, train.py:703-711) on 16^2 / 32^2 feature maps:
+    bottom/right zero padding inside the attention (padded tokens carry the projection biases), and the sigma/mu attention's
+    InstanceNorm of Wk.K taken over the PADDED map (style_transformer.py:520-530)."""
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel, synthetic
+    from oracle import master_oracle as O
+    m = MasterStyleTransferModel(style_encoder_window_size=[7, 7], style_decoder_window_size=[7, 7])
+    synthetic.fill_state_dict_(m, 0)
+    sd7 = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+    m = m.eval().cuda()
+    content, style = synthetic.synthetic_images(2, size, seed=0)
+    with torch.no_grad():
+        out = m(content.cuda(), style.cuda(), k)
+        ref = O.full_forward(sd7, content, style, k, ws=7, sh=4)
+    e = rel_err(out, ref)
+    assert e <= (IMG_TOL if k == 1 else 2 * IMG_TOL), e
+    if size == 128 and k == 1:  # golden minted from the real reference with the same seeded weights (oracle/make_golden.py)
+        g = torch.from_numpy(np.load(os.path.join(golden_dir, "path_128.npz"))["img_ws7"])
+        assert ((out.cpu()[:, :, ::2, ::2] - g).abs().max() / (g.max() - g.min())).item() <= IMG_TOL
+
+
 @pytest.mark.parametrize("k", [1, 3])
 def test_config1_256_vs_golden(model, k, golden_dir):
     """BASELINE configs[0] shape: one 256x256 content + style pair, batch 1 (seeded weights: SURVEY 8c)."""
