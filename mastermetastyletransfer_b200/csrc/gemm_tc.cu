@@ -670,41 +670,40 @@ static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename Tma
   return (int)cudaGetLastError();
 }
 
+// Tensor map for the A operand, or false when the launch is not eligible (then the gathered cp.async producers are used).
+static bool make_a_tensor_map(const MstGemm& g, CUtensorMap* tmap) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc || (reinterpret_cast<uintptr_t>(g.A) & 15) != 0) return false;
+  if (g.a_mode == MST_A_PLAIN) {
+    if ((g.lda * 2) % 16 != 0) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)g.K, (cuuint64_t)g.M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)g.lda * 2};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  // 3x3 conv through TMA: 64-channel k-blocks inside one tap, tiles = whole image rows (or 128-pixel row segments)
+  if (g.a_mode != MST_A_CONV3X3 || g.upsample || g.conv_full || g.Cin % 64 != 0 || g.k_pad != g.K || g.W < 8 || g.M % BM != 0) return false;
+  if (!((g.W <= BM && BM % g.W == 0 && g.H % (BM / g.W) == 0 && (g.pad_mode == 0 || BM / g.W <= 4)) || g.W % BM == 0)) return false;
+  const int B = g.M / (g.H * g.W);
+  const cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B};
+  const cuuint64_t gstride[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
+  const cuuint32_t box[4] = {BK, (cuuint32_t)(g.W < BM ? g.W : BM), 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN>
 static int launch_gemm(const MstGemm& g, cudaStream_t st) {
   const bool ext = g.out_pre16 || g.gate || g.add16 || g.row_scale || g.conv_full;
-  if (ext) return launch_gemm_ext<BN, true, false>(g, st, TmaNone{});
-  if (g.a_mode == MST_A_PLAIN && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (g.lda * 2) % 16 == 0) {
-    if (EncodeTiledFn enc = tma_encoder()) {
-      alignas(64) CUtensorMap tmap;
-      const cuuint64_t gdim[2] = {(cuuint64_t)g.K, (cuuint64_t)g.M};
-      const cuuint64_t gstride[1] = {(cuuint64_t)g.lda * 2};
-      const cuuint32_t box[2] = {BK, BM};
-      const cuuint32_t estr[2] = {1, 1};
-      const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box,
-                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r == CUDA_SUCCESS) return launch_gemm_ext<BN, false, true>(g, st, tmap);
-    }
-  }
-  // 3x3 conv through TMA: 64-channel k-blocks inside one tap, tiles = whole image rows (or 128-pixel row segments)
-  if (g.a_mode == MST_A_CONV3X3 && !g.upsample && g.Cin % 64 == 0 && g.k_pad == g.K && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 &&
-      ((g.W <= BM && BM % g.W == 0 && g.H % (BM / g.W) == 0 && (g.pad_mode == 0 || BM / g.W <= 4)) || g.W % BM == 0) && g.W >= 8 &&
-      g.M % BM == 0) {
-    if (EncodeTiledFn enc = tma_encoder()) {
-      alignas(64) CUtensorMap tmap;
-      const int B = g.M / (g.H * g.W);
-      const cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B};
-      const cuuint64_t gstride[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
-      const cuuint32_t box[4] = {BK, (cuuint32_t)(g.W < BM ? g.W : BM), 1, 1};
-      const cuuint32_t estr[4] = {1, 1, 1, 1};
-      const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box,
-                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r == CUDA_SUCCESS) return launch_gemm_ext<BN, false, true>(g, st, tmap);
-    }
-  }
-  return launch_gemm_ext<BN, false, false>(g, st, TmaNone{});
+  alignas(64) CUtensorMap tmap;
+  const bool tma = make_a_tensor_map(g, &tmap);
+  if (ext) return tma ? launch_gemm_ext<BN, true, true>(g, st, tmap) : launch_gemm_ext<BN, true, false>(g, st, TmaNone{});
+  return tma ? launch_gemm_ext<BN, false, true>(g, st, tmap) : launch_gemm_ext<BN, false, false>(g, st, TmaNone{});
 }
 
 // ---------------------------------------------------------------- weight packing (tile-blocked, pre-swizzled)
