@@ -97,12 +97,15 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const bf16* __restrict_
 // fills the GPU: the taps are [B, 16384..256, 128..512].
 __global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ part, int T, int C,
                                                         int rows_per_cta, int BC) {
-  __shared__ float red[2][32][65];
-  const int c8 = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  // CTA = (T slab, image b), ALL channels: thread = (8-channel chunk c8 of C/8, row lane rl of 256/(C/8)), so a warp reads
+  // 512 contiguous bytes and consecutive passes walk consecutive rows (the earlier 64-channel CTAs read 128 of every
+  // 2C bytes: 61 % of the HBM rate).
+  extern __shared__ float red[];  // [2][RL][C + 1]
+  const int C8 = C >> 3, RL = 256 / C8;
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
   const int b = blockIdx.y;
-  const int col = blockIdx.z * 64 + c8 * 8;
   const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
-  const bf16* xb = x + (long long)b * T * C + col;
+  const bf16* xb = x + (long long)b * T * C + c8 * 8;
   float k[8], s[8], q[8];
   {
     const uint4 f = *reinterpret_cast<const uint4*>(xb);
@@ -112,8 +115,7 @@ __global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-  for (int t = t0 + rl; t < t1; t += 32) {
-    const uint4 v = *reinterpret_cast<const uint4*>(xb + (long long)t * C);
+  auto accumulate = [&](const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -121,16 +123,25 @@ __global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__
       s[2 * e] += a; q[2 * e] = fmaf(a, a, q[2 * e]);
       s[2 * e + 1] += d; q[2 * e + 1] = fmaf(d, d, q[2 * e + 1]);
     }
+  };
+  int t = t0 + rl;
+  for (; t + 3 * RL < t1; t += 4 * RL) {  // four 16-byte loads in flight per thread: the kernel is a pure HBM stream
+    const uint4 v0 = *reinterpret_cast<const uint4*>(xb + (long long)t * C);
+    const uint4 v1 = *reinterpret_cast<const uint4*>(xb + (long long)(t + RL) * C);
+    const uint4 v2 = *reinterpret_cast<const uint4*>(xb + (long long)(t + 2 * RL) * C);
+    const uint4 v3 = *reinterpret_cast<const uint4*>(xb + (long long)(t + 3 * RL) * C);
+    accumulate(v0); accumulate(v1); accumulate(v2); accumulate(v3);
   }
+  for (; t < t1; t += RL) accumulate(*reinterpret_cast<const uint4*>(xb + (long long)t * C));
+  const int pitch = C + 1;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { red[0][rl][c8 * 8 + e] = s[e]; red[1][rl][c8 * 8 + e] = q[e]; }
+  for (int e = 0; e < 8; ++e) { red[rl * pitch + c8 * 8 + e] = s[e]; red[(RL + rl) * pitch + c8 * 8 + e] = q[e]; }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, cc = threadIdx.x & 63;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int which = i / C, cc = i - which * C;
     float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a += red[which][i][cc];
-    part[((long long)blockIdx.x * BC + (long long)b * C + blockIdx.z * 64 + cc) * 2 + which] = a;
+    for (int r = 0; r < RL; ++r) a += red[(which * RL + r) * pitch + cc];
+    part[((long long)blockIdx.x * BC + (long long)b * C + cc) * 2 + which] = a;
   }
 }
 
@@ -154,7 +165,7 @@ __global__ void __launch_bounds__(256) tap_stats_finalize_kernel(const bf16* __r
 
 static int tap_stats_rows(int B, int T, int C) {  // slab size: enough CTAs to cover the GPU a few times over, >= 64 rows each
   int rows = 64;
-  while ((long long)((T + rows - 1) / rows) * B * (C / 64) > 148 * 8 && rows < T) rows *= 2;
+  while ((long long)((T + rows - 1) / rows) * B > 148 * 8 && rows < T) rows *= 2;
   return rows;
 }
 
@@ -163,28 +174,46 @@ static int tap_stats_rows(int B, int T, int C) {  // slab size: enough CTAs to c
 __global__ void __launch_bounds__(256) content_term_kernel(const bf16* __restrict__ fc, const bf16* __restrict__ fo,
                                                            const float* __restrict__ mean_c, const float* __restrict__ var_c,
                                                            const float* __restrict__ mean_o, const float* __restrict__ var_o,
-                                                           long long n8, int TC8, int C8, int squared, float* __restrict__ partials) {
+                                                           int B, int T, int C8, int squared, float* __restrict__ partials) {
+  // CTA = (image b, row slab); a thread keeps ONE 8-channel chunk for all of its rows, so the four statistics of its channels
+  // are loaded (and the two rsqrt taken) once -- the row loop is then a pure 2 x 16-byte-per-thread HBM stream.
   __shared__ float red[8];
+  const int nslab = gridDim.x / B;
+  const int b = blockIdx.x % B, slab = blockIdx.x / B;
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / TC8);
-    const int c = (int)(i % C8) * 8;
-    const uint4 a = reinterpret_cast<const uint4*>(fc)[i];
-    const uint4 o = reinterpret_cast<const uint4*>(fo)[i];
-    const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
-    const uint32_t* op = reinterpret_cast<const uint32_t*>(&o);
-    const long long sb = (long long)b * C8 * 8 + c;
+  if (slab < nslab) {
+    const int rpc = 256 / C8;  // rows covered by one pass of the CTA (C8 = 16 / 32 / 64 chunks per row)
+    const int j = threadIdx.x % C8, r0 = slab * rpc + threadIdx.x / C8;
+    const long long sb = (long long)b * C8 * 8 + j * 8;
+    float mc[8], rc[8], mo[8], ro[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float av = h ? __uint_as_float(ap[j] & 0xFFFF0000u) : __uint_as_float(ap[j] << 16);
-        const float ov = h ? __uint_as_float(op[j] & 0xFFFF0000u) : __uint_as_float(op[j] << 16);
-        const int cc = 2 * j + h;
-        const float d = (av - mean_c[sb + cc]) * rsqrtf(var_c[sb + cc] + 1e-5f) - (ov - mean_o[sb + cc]) * rsqrtf(var_o[sb + cc] + 1e-5f);
-        acc += squared ? d * d : fabsf(d);
-      }
+    for (int e = 0; e < 8; ++e) {
+      mc[e] = mean_c[sb + e]; rc[e] = rsqrtf(var_c[sb + e] + 1e-5f);
+      mo[e] = mean_o[sb + e]; ro[e] = rsqrtf(var_o[sb + e] + 1e-5f);
     }
+    const uint4* pc = reinterpret_cast<const uint4*>(fc) + (long long)b * T * C8 + j;
+    const uint4* po = reinterpret_cast<const uint4*>(fo) + (long long)b * T * C8 + j;
+    const int step = nslab * rpc;
+    auto term = [&](const uint4& a, const uint4& o) {
+      const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+      const uint32_t* op = reinterpret_cast<const uint32_t*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a0 = __uint_as_float(ap[q] << 16), a1 = __uint_as_float(ap[q] & 0xFFFF0000u);
+        const float o0 = __uint_as_float(op[q] << 16), o1 = __uint_as_float(op[q] & 0xFFFF0000u);
+        const float d0 = (a0 - mc[2 * q]) * rc[2 * q] - (o0 - mo[2 * q]) * ro[2 * q];
+        const float d1 = (a1 - mc[2 * q + 1]) * rc[2 * q + 1] - (o1 - mo[2 * q + 1]) * ro[2 * q + 1];
+        acc += squared ? d0 * d0 + d1 * d1 : fabsf(d0) + fabsf(d1);
+      }
+    };
+    int r = r0;
+    for (; r + step < T; r += 2 * step) {  // two rows (four 16-byte loads) in flight per thread
+      const uint4 a0 = pc[(long long)r * C8], o0 = po[(long long)r * C8];
+      const uint4 a1 = pc[(long long)(r + step) * C8], o1 = po[(long long)(r + step) * C8];
+      term(a0, o0);
+      term(a1, o1);
+    }
+    for (; r < T; r += step) term(pc[(long long)r * C8], po[(long long)r * C8]);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -263,13 +292,14 @@ extern "C" size_t mst_tap_stats_scratch_floats(int B, int T, int C) {
 extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, float* scratch, size_t scratch_floats,
                              void* stream) {
   if (!x || !mean || !var || !scratch || B <= 0 || T <= 0 || C <= 0) return MST_ERR_BAD_ARG;
-  if (C % 64) return MST_ERR_UNSUPPORTED;
+  if (C % 64 || 256 % (C / 8) != 0 || C > 2048) return MST_ERR_UNSUPPORTED;  // C/8 chunks per row must tile the 256 threads
   if (scratch_floats < mst_tap_stats_scratch_floats(B, T, C)) return MST_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = tap_stats_rows(B, T, C);
   const int slabs = (T + rows - 1) / rows;
-  dim3 grid((unsigned)slabs, (unsigned)B, (unsigned)(C / 64));
-  tap_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, T, C, rows, B * C);
+  dim3 grid((unsigned)slabs, (unsigned)B, 1);
+  const size_t red_bytes = (size_t)2 * (256 / (C / 8)) * (C + 1) * sizeof(float);
+  tap_stats_kernel<<<grid, 256, red_bytes, st>>>(reinterpret_cast<const bf16*>(x), scratch, T, C, rows, B * C);
   tap_stats_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, mean, var, B, T, C, slabs);
   return (int)cudaGetLastError();
 }
@@ -277,10 +307,10 @@ extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, 
 extern "C" int mst_content_term(const mst_bf16* fc, const mst_bf16* fo, const float* mean_c, const float* var_c, const float* mean_o,
                                 const float* var_o, int B, int T, int C, int squared, float* partials, int n_partials, void* stream) {
   if (!fc || !fo || !mean_c || !var_c || !mean_o || !var_o || !partials || B <= 0 || T <= 0 || C <= 0 || n_partials <= 0) return MST_ERR_BAD_ARG;
-  if (C % 8) return MST_ERR_UNSUPPORTED;
-  const long long n8 = (long long)B * T * C / 8;
+  if (C % 8 || 256 % (C / 8) != 0) return MST_ERR_UNSUPPORTED;  // C in {8, ..., 2048} with C/8 a power of two <= 256
+  if (n_partials < B) return MST_ERR_BAD_ARG;                 // one CTA per (image, row slab): at least one slab per image
   content_term_kernel<<<n_partials, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(fc), reinterpret_cast<const bf16*>(fo), mean_c, var_c,
-                                                                    mean_o, var_o, n8, T * C / 8, C / 8, squared, partials);
+                                                                    mean_o, var_o, B, T, C / 8, squared, partials);
   return (int)cudaGetLastError();
 }
 
