@@ -13,6 +13,7 @@
 // (NS*BN <= 512 columns) while the k-blocks stream once.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -30,6 +31,8 @@ struct BandGeom {
   int n_tiles;    // N / BN
   int wst;        // weight ring stages
   int tmem_cols;  // TMEM columns allocated by the CTA (256 when two CTAs share an SM, else 512)
+  int lead;       // halo pixel index of (row 0, padded column 0): 1, or 8 when the halo is filled by tensor copies (128-byte alignment)
+  int tma;        // 1: halo rows fetched with cp.async.bulk.tensor (one per 8-channel plane and row)
 };
 
 MST_DEVINL void cb_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -52,13 +55,15 @@ MST_DEVINL uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint3
 }
 
 template <int BN>
-__global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore p, const BandGeom g, const int total_units) {
+__global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore p, const BandGeom g, const int total_units,
+                                                                  const __grid_constant__ CUtensorMap tm_halo) {
   constexpr int MAXST = 4;
   constexpr int B_STAGE_BYTES = BN * 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[MAXST];
   __shared__ uint64_t empty_bar[MAXST];
   __shared__ uint64_t accum_bar;
+  __shared__ uint64_t halo_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[CB_MAX_BIAS];
 
@@ -78,6 +83,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&accum_bar), 1);
+    mbar_init(smem_u32(&halo_bar), 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < p.N; i += CB_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
@@ -105,6 +111,28 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
     const int band = unit / g.n_tiles;
     const int b = band / g.bands_per_img;
     const int y0 = (band - b * g.bands_per_img) * g.R;
+    if (g.tma) {
+      // one tensor copy per (halo row, 8-channel plane): box = 8 channels x Wp pixels starting at x = -1; out-of-image
+      // pixels / rows are zero-filled by the hardware (zero padding), reflect rows use the reflected row coordinate and the
+      // two reflect columns are patched from the neighbouring pixels once the copies have landed
+      if (threadIdx.x == 0) {
+        cb_arrive_expect_tx(smem_u32(&halo_bar), (uint32_t)((g.R + 2) * g.Wp * 16 * cpp));
+        for (int hr = 0; hr < g.R + 2; ++hr) {
+          int yy = y0 + hr - 1;
+          if (p.pad_mode == 1) {
+            yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+            yy = min(max(yy, 0), p.H - 1);
+          }
+          const uint32_t rowdst = halo_base + (uint32_t)(hr * g.Wp + g.lead) * 16u;
+          for (int c = 0; c < cpp; ++c)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                             rowdst + (uint32_t)(c * g.npx) * 16u),
+                         "l"(&tm_halo), "r"(c * 8), "r"(-1), "r"(yy), "r"(b), "r"(smem_u32(&halo_bar))
+                         : "memory");
+        }
+      }
+      return;
+    }
     const bf16* img = Abase + (long long)b * Hs * Ws * p.Cin;
     const int row_chunks = g.Wp * cpp;
     for (int hr = 0; hr < g.R + 2; ++hr) {
@@ -118,7 +146,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
       }
       if (p.upsample) yy >>= 1;
       const bf16* rowsrc = img + (long long)yy * Ws * p.Cin;
-      const uint32_t rowdst = halo_base + (uint32_t)(hr * g.Wp + 1) * 16u;
+      const uint32_t rowdst = halo_base + (uint32_t)(hr * g.Wp + g.lead) * 16u;
       for (int idx = threadIdx.x; idx < row_chunks; idx += CB_THREADS) {
         const int col = idx / cpp;
         const int c = idx - col * cpp;
@@ -140,7 +168,22 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
     const int y0 = (band - b * g.bands_per_img) * g.R;
 
     // ---------------- phase 1: the halo of this band was issued ahead (before the previous epilogue); land it ----------------
-    cp_async_wait_all();
+    if (g.tma) {
+      mbar_wait(smem_u32(&halo_bar), ucount & 1);
+      if (p.pad_mode == 1) {  // reflect columns: x = -1 <- x = 1, x = W <- x = W - 2 (16-byte pixels of every row and plane)
+        const int n = (g.R + 2) * cpp * 2;
+        for (int i = threadIdx.x; i < n; i += CB_THREADS) {
+          const int side = i & 1, c = (i >> 1) % cpp, hr = (i >> 1) / cpp;
+          const uint32_t rowb = halo_base + (uint32_t)(c * g.npx + hr * g.Wp + g.lead) * 16u;
+          const uint32_t src = rowb + (uint32_t)(side ? p.W - 1 : 2) * 16u, dst = rowb + (uint32_t)(side ? p.W + 1 : 0) * 16u;
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        }
+      }
+    } else {
+      cp_async_wait_all();
+    }
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
     __syncthreads();
 #ifdef MST_BAND_PROF
@@ -176,7 +219,7 @@ __global__ void __launch_bounds__(CB_THREADS, 2) conv_band_kernel(const GemmCore
             const int chunk0 = (ks - tap * kpt) * 2;  // first of the two 16-byte channel chunks of this K=16 step
             const int ky = tap / 3, kx = tap - ky * 3;
             const uint64_t bd = umma_desc_sw128(b_stage + j * 32);
-            const uint32_t a0 = halo_base + (uint32_t)(chunk0 * g.npx + ky * g.Wp + kx) * 16u;
+            const uint32_t a0 = halo_base + (uint32_t)(chunk0 * g.npx + ky * g.Wp + kx + g.lead - 1) * 16u;
             for (int st = 0; st < g.NS; ++st)
               umma_bf16_pred(tmem_base + st * BN, umma_desc_none(a0 + (uint32_t)st * 2048u, lbo, 128u), bd, idesc, ks != 0);
           }
@@ -290,8 +333,15 @@ static int cb_num_sms() {
 
 // Choose rows per band: the halo must fit beside the weight ring, all strips must fit in TMEM; maximise
 // (useful MMA rows / issued MMA rows) * (halo reuse R/(R+2)).
+static bool band_tma_ok(const MstGemm& g) {  // halo by tensor copies: dense NHWC input (no folded upsample), box width <= 256
+  return !g.upsample && g.Cin % 8 == 0 && g.W + 2 <= 248 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && getenv("MST_BAND_TMA") == nullptr;
+}
+
 static bool plan_band_with(const MstGemm& g, int BN, long long smem_total, int tmem_cols, BandGeom& out, double& best) {
-  const int Wp = g.W + 2;
+  const bool tma = band_tma_ok(g);
+  // tensor copies need 128-byte aligned destinations: row pitch and lead offset in multiples of 8 pixels (16 B each)
+  const int Wp = tma ? (g.W + 2 + 7) / 8 * 8 : g.W + 2;
+  const int lead = tma ? 8 : 1;
   const int wst = BN >= 256 ? 2 : 4;
   const long long budget = smem_total - 1024 /*align*/ - (long long)wst * BN * 128;
   best = 0.0;
@@ -299,7 +349,7 @@ static bool plan_band_with(const MstGemm& g, int BN, long long smem_total, int t
   for (int R = 1; R <= g.H && R <= 32; ++R) {
     const int NS = (R * Wp + 127) / 128;
     if (NS * BN > tmem_cols) break;
-    const int npx = NS * 128 + 2 * Wp + 8;
+    const int npx = (NS * 128 + 2 * Wp + 8 + lead + 7) / 8 * 8;
     const long long halo = (long long)g.Cin * 2 * npx;
     if (halo > budget) break;
     if (npx > 0x3FFF) break;  // LBO field
@@ -311,6 +361,7 @@ static bool plan_band_with(const MstGemm& g, int BN, long long smem_total, int t
       ok = true;
       out.R = R; out.NS = NS; out.npx = npx; out.Wp = Wp; out.bands_per_img = bands; out.n_tiles = g.N / BN; out.wst = wst;
       out.tmem_cols = tmem_cols;
+      out.lead = lead; out.tma = tma ? 1 : 0;
     }
   }
   return ok;
@@ -345,7 +396,28 @@ static int launch_band(const MstGemm& g, cudaStream_t st) {
   const unsigned grid = (unsigned)(units < cb_num_sms() ? units : cb_num_sms());
   GemmCore core;
   memcpy(&core, &g, sizeof(GemmCore));
-  conv_band_kernel<BN><<<grid, CB_THREADS, smem, st>>>(core, geo, (int)units);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (geo.tma) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+      void* fp = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        enc = reinterpret_cast<EncodeTiledFn>(fp);
+    }
+    const cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)B};
+    const cuuint64_t gstride[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.W * g.Cin * 2, (cuuint64_t)g.H * g.W * g.Cin * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)geo.Wp, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(reinterpret_cast<const void*>(g.A)), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MST_ERR_UNSUPPORTED;
+  }
+  conv_band_kernel<BN><<<grid, CB_THREADS, smem, st>>>(core, geo, (int)units, tmap);
   return (int)cudaGetLastError();
 }
 
