@@ -281,20 +281,22 @@ __host__ __device__ inline int rel_pos_index(int i, int j, int ws) {
   return (yi - yj + ws - 1) * (2 * ws - 1) + (xi - xj + ws - 1);
 }
 
-// Exact (erf) GELU.  erf by Abramowitz-Stegun 7.1.26 evaluated with the MUFU reciprocal / exp2: measured max
-// |difference| to 0.5*x*(1+erff(x/sqrt2)) over [-8,8] is 5.9e-7 (tools/micro/gelu_bench.cu), at 1.5x the
-// throughput of erff() -- the GELU epilogue is ALU-bound.
+// Exact (erf) GELU with ONE MUFU op and 9 ALU ops per element:  1 - erf(a/sqrt2) = 2^(-a*R(a)) for a = |x| >= 0, R a
+// degree-4 minimax fit (tools/micro/gelu_fit.py; R is positive and increasing, so large |x| underflow to the right limits
+// without a clamp), and  gelu(x) = max(x, 0) - |x/2| * 2^(-a R(a))  for either sign.  Max |difference| to
+// 0.5*x*(1+erf(x/sqrt2)) over [-8,8]: 5.4e-7, with a relative-accurate negative tail.  It replaces an Abramowitz-Stegun
+// 7.1.26 evaluation (rcp + ex2, 16 ALU ops, 5.9e-7) -- the GELU epilogue of the fused MLP is issue-bound.
+// A one-MUFU tanh form, 0.5x(1+tanh(x*Q(x^2))) with MUFU.TANH, was measured too: 2 ALU ops fewer, but its 2^-11 relative
+// error on tanh pushed the image max-error of one parity case over the 2e-2 gate (tools/debug/path_err.py).
 MST_DEVINL float gelu_erf(float x) {
-  const float z = x * 0.70710678118654752440f, az = fabsf(z);
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-az * az * 1.4426950408889634f));
-  const float er = copysignf(fmaf(-p * t, e, 1.0f), z);
-  return 0.5f * x * (1.0f + er);
+  const float a = fabsf(x);
+  float r = fmaf(0.0004881656787f, a, -0.007198856212f);
+  r = fmaf(r, a, 0.05214627460f);
+  r = fmaf(r, a, 0.4595968127f);
+  r = fmaf(r, a, 1.151000023f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-a * r));
+  return fmaf(-fabsf(0.5f * x), e, fmaxf(x, 0.0f));
 }
 
 // d/dx of the exact GELU: Phi(x) + x*phi(x), same erf approximation (e = exp(-x^2/2) is shared by both terms)
