@@ -328,6 +328,14 @@ int mst_blend_bwd(const float* gy, const float* sigma, const float* query, float
 /* out[i] = a[i] (+ b[i]) -> fp32 and/or bf16 (gradient-stream bookkeeping) */
 int mst_add_cast(const float* a, const float* b, float* out32, mst_bf16* out16, size_t n, void* stream);
 
+/* Token-map pad / crop for window attention on zero-padded feature maps (style_transformer.py:77-87 `F.pad(x, (0,0,0,pad_r,0,pad_b))`
+ * and the final `x[:, :H, :W, :]` crop, :230-232; the sigma/mu attention pads its four inputs at :476-479): src [B,Hs,Ws,token_bytes]
+ * -> dst [B,Hd,Wd,token_bytes]; destination tokens outside the source map are zero-filled, source tokens outside the
+ * destination map are dropped.  accumulate_f32 != 0: tokens are fp32 and dst += src (the adjoint of the pad: gradient streams
+ * on the unpadded map accumulate the cropped data gradient).  token_bytes % 16 == 0, 16-byte aligned buffers. */
+int mst_token_map_copy(const void* src, void* dst, int B, int Hs, int Ws, int Hd, int Wd, int token_bytes, int accumulate_f32,
+                       void* stream);
+
 /* Reflect-pad fold (adjoint of F.pad(mode='reflect') + optional nn.Upsample(2,'nearest'), decoder.py:24-27):
  * dxp bf16 [B,H+2,W+2,C] (the conv_full data gradient on the padded grid) -> dx bf16 [B,H,W,C], or [B,H/2,W/2,C]
  * summing 2x2 blocks when upsample=1; gate (bf16, shape of dx) applies the previous ReLU's mask (gate > 0). */

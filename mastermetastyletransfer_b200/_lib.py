@@ -131,6 +131,7 @@ SYMBOLS = {
     "mst_instnorm_bwd_apply": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
     "mst_blend_bwd": (_I, [_P, _P, _P, _P, _P, _P, _Z, _P]),
     "mst_add_cast": (_I, [_P, _P, _P, _P, _Z, _P]),
+    "mst_token_map_copy": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mst_reflect_fold": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mst_maxpool2x2_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_nchw3_to_nhwc8": (_I, [_P, _P, _I, _I, _I, _P]),

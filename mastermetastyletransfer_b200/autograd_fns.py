@@ -60,8 +60,6 @@ class _StyleTransformerFn(torch.autograd.Function):
         cfg = module._cfg
         w = packed_weights(module, te.StyleTransformerTrainWeights)
         geo = te._Geo(B, H, W, C, cfg["heads"], cfg["window"][0], cfg["shift"][0])
-        if H % geo.win or W % geo.win:
-            raise ValueError("style transformer feature map must be a multiple of the window (7x7 padded path: see DESIGN.md)")
         sd = _draw_stochastic_depth(module, B, k, Fc.device)
         out, tape = te.style_transformer_forward_train(w, Fc.detach().float().contiguous(), Fs.detach().float().contiguous(), k, geo, sd)
         ctx.module, ctx.w, ctx.geo, ctx.tape, ctx.sd = module, w, geo, tape, sd

@@ -215,6 +215,32 @@ __global__ void __launch_bounds__(256) add_cast_kernel(const float4* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- token-map pad / crop (7x7 windows on padded maps, training path)
+// src [B,Hs,Ws,*] -> dst [B,Hd,Wd,*] in 16-byte units (`u` per token): dst tokens outside the source map are zero (pad),
+// source tokens outside the destination map are dropped (crop).  ACC: dst (fp32) += src instead of a copy.
+template <bool ACC>
+__global__ void __launch_bounds__(256) token_map_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int Hs, int Ws, int Hd,
+                                                        int Wd, int u, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % u);
+  long long t = i / u;
+  const int x = (int)(t % Wd);
+  t /= Wd;
+  const int y = (int)(t % Hd);
+  const long long b = t / Hd;
+  const bool inside = y < Hs && x < Ws;
+  if (ACC) {
+    if (!inside) return;
+    const uint4 sv = src[((b * Hs + y) * Ws + x) * u + c];
+    float4 d = *reinterpret_cast<float4*>(dst + i);
+    d.x += __uint_as_float(sv.x); d.y += __uint_as_float(sv.y); d.z += __uint_as_float(sv.z); d.w += __uint_as_float(sv.w);
+    *reinterpret_cast<float4*>(dst + i) = d;
+  } else {
+    dst[i] = inside ? src[((b * Hs + y) * Ws + x) * u + c] : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ---------------------------------------------------------------- reflect-pad fold (+ nearest-x2 upsample adjoint, + ReLU mask)
 // dxp [B,H+2,W+2,C] on the padded grid; padded row 0 mirrors input row 1, padded row H+1 mirrors input row H-2.
 __global__ void __launch_bounds__(256) reflect_fold_kernel(const bf16* __restrict__ dxp, const bf16* __restrict__ gate,
@@ -455,6 +481,21 @@ extern "C" int mst_add_cast(const float* a, const float* b, float* out32, mst_bf
   const long long n4 = (long long)(n / 4);
   add_cast_kernel<<<blocks_for(n4), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                                    reinterpret_cast<float4*>(out32), reinterpret_cast<uint2*>(out16), n4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_token_map_copy(const void* src, void* dst, int B, int Hs, int Ws, int Hd, int Wd, int token_bytes, int accumulate_f32,
+                                  void* stream) {
+  if (!src || !dst || B <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0 || token_bytes <= 0 || token_bytes % 16 != 0) return MST_ERR_BAD_ARG;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0) return MST_ERR_BAD_ARG;
+  const int u = token_bytes / 16;
+  const long long total = (long long)B * Hd * Wd * u;
+  if (accumulate_f32)
+    token_map_kernel<true><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+                                                                               Hs, Ws, Hd, Wd, u, total);
+  else
+    token_map_kernel<false><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
+                                                                                Hs, Ws, Hd, Wd, u, total);
   return (int)cudaGetLastError();
 }
 

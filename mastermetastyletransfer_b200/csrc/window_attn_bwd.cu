@@ -1,5 +1,7 @@
 // Backward of the fused shifted-window attention core (adjoint of window_attn.cu; the reference differentiates
-// codes/style_transformer.py:127-155 / :544-594 with autograd).  8x8 windows on an un-padded map.
+// codes/style_transformer.py:127-155 / :544-594 with autograd).  8x8 or 7x7 windows on a map that is a window multiple (the
+// training path materialises the reference's zero padding, train_engine._pad16); a 7x7 window occupies 49 of the 64 token
+// slots: the other slots load zeros, are masked out of every softmax, carry zero dO and are never stored.
 //
 // One warp per (window, head), four warps per CTA, all matmuls on mma.sync m16n8k16 (bf16 in, fp32 accumulate):
 //   pass 1 (16 query rows at a time):  S = scale*Q K^T + bias + mask,  P = softmax(S),  dP = dO V^T (+ dO2 V2^T),
@@ -99,13 +101,15 @@ MST_DEVINL void ab_store_tile(const float (&o)[4][4], float mul, bf16* stg, bf16
     const int r = rr * 8 + (lane >> 2);
     const int s = src_s[row0 + r];
     const uint4 val = *reinterpret_cast<const uint4*>(stg + r * AB_LD + (lane & 3) * 8);
-    *reinterpret_cast<uint4*>(out + (long long)s * ld + c0 + (lane & 3) * 8) = val;
+    if (s >= 0) *reinterpret_cast<uint4*>(out + (long long)s * ld + c0 + (lane & 3) * 8) = val;
   }
   __syncwarp();
 }
 
+template <int WS>
 __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const MstWindowAttnBwd a, const WinGeom g) {
-  constexpr int WS = 8;
+  constexpr int NTOK = WS * WS;                      // real tokens of a window (<= AB_N slots)
+  constexpr int NT = (2 * WS - 1) * (2 * WS - 1);    // relative-position table entries per head (<= AB_NT)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int heads = a.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,16 +140,21 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
   const int win = win_global - b * g.nW;
   const bool masked = (g.sy + g.sx) > 0;
 
-  for (int i = threadIdx.x; i < AB_NT * heads; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NT * heads; i += blockDim.x) {
     const int idx = i / heads, hh = i - idx * heads;
     table_s[hh * AB_NT + idx] = a.bias_table[i];
   }
   for (int i = threadIdx.x; i < AB_WARPS * AB_NT; i += blockDim.x) dtab_s[i] = 0.f;
   for (int i = threadIdx.x; i < AB_N; i += blockDim.x) {
-    int y, x;
-    win_source(g, win, i, y, x);
-    src_s[i] = (b * g.H + y) * g.W + x;
-    lab_s[i] = win_label(g, win, i);
+    if (i < NTOK) {
+      int y, x;
+      win_source(g, win, i, y, x);
+      src_s[i] = (b * g.H + y) * g.W + x;
+      lab_s[i] = win_label(g, win, i);
+    } else {
+      src_s[i] = -1;
+      lab_s[i] = -1;
+    }
   }
   __syncthreads();
 
@@ -155,16 +164,17 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
     const uint32_t qs = smem_u32(Qs), ks_ = smem_u32(Ks), vs = smem_u32(Vs), dos = smem_u32(dOs), v2s = smem_u32(V2s), do2s = smem_u32(dO2s);
 #pragma unroll
     for (int r = rsub; r < AB_N; r += 8) {
-      const int s = src_s[r];
+      const bool real = src_s[r] >= 0;  // empty slots of a 7x7 window: zero fill
+      const int s = real ? src_s[r] : 0;
       const uint32_t off = (uint32_t)(r * AB_LD + chunk * 8) * 2u;
       const int cc = c0 + chunk * 8;
-      cp_async16(qs + off, reinterpret_cast<const bf16*>(a.q) + (long long)s * a.ldq + cc, true);
-      cp_async16(ks_ + off, reinterpret_cast<const bf16*>(a.k) + (long long)s * a.ldk + cc, true);
-      cp_async16(vs + off, reinterpret_cast<const bf16*>(a.v) + (long long)s * a.ldv + cc, true);
-      cp_async16(dos + off, reinterpret_cast<const bf16*>(a.dout) + (long long)s * a.ldo + cc, true);
+      cp_async16(qs + off, reinterpret_cast<const bf16*>(a.q) + (long long)s * a.ldq + cc, real);
+      cp_async16(ks_ + off, reinterpret_cast<const bf16*>(a.k) + (long long)s * a.ldk + cc, real);
+      cp_async16(vs + off, reinterpret_cast<const bf16*>(a.v) + (long long)s * a.ldv + cc, real);
+      cp_async16(dos + off, reinterpret_cast<const bf16*>(a.dout) + (long long)s * a.ldo + cc, real);
       if (dual) {
-        cp_async16(v2s + off, reinterpret_cast<const bf16*>(a.v2) + (long long)s * a.ldv + cc, true);
-        cp_async16(do2s + off, reinterpret_cast<const bf16*>(a.dout2) + (long long)s * a.ldo + cc, true);
+        cp_async16(v2s + off, reinterpret_cast<const bf16*>(a.v2) + (long long)s * a.ldv + cc, real);
+        cp_async16(do2s + off, reinterpret_cast<const bf16*>(a.dout2) + (long long)s * a.ldo + cc, real);
       }
     }
     cp_async_wait_all();
@@ -178,17 +188,22 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
   const uint32_t q_base = smem_u32(Qs), k_base = smem_u32(Ks), v_base = smem_u32(Vs), do_base = smem_u32(dOs);
   const uint32_t v2_base = smem_u32(V2s), do2_base = smem_u32(dO2s);
   // per-lane column constants: column c = nt*8 + cq + e
+  // (empty slots use token 0's table indices -- in range, and their scores are forced to -inf / their dS is exactly zero)
   int colcp[8][2], colrp[8][2], collab[8][2];
+  uint32_t colreal = 0;  // bit nt*2+e: column is a real token
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int j = nt * 8 + cq + e;
+      const int jslot = nt * 8 + cq + e;
+      const int j = jslot < NTOK ? jslot : 0;
+      if (jslot < NTOK) colreal |= 1u << (nt * 2 + e);
       const int yj = j / WS, xj = j - yj * WS;
       colcp[nt][e] = yj * (2 * WS - 1) + xj;
       colrp[nt][e] = (yj + WS - 1) * (2 * WS - 1) + xj + WS - 1;
       collab[nt][e] = lab_s[j];
     }
+  (void)colreal;
 
   // ------------------------------------------------------------------ pass 1: query tiles
 #pragma unroll 1
@@ -200,9 +215,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
     ab_load_a(q_base, mt * 16, lane, af);
     ab_mm_nt(sc, af, k_base, lane);
     const int i0 = mt * 16 + gq, i1 = i0 + 8;
-    const int rp0 = (i0 / WS + WS - 1) * (2 * WS - 1) + (i0 % WS) + WS - 1;
-    const int rp1 = (i1 / WS + WS - 1) * (2 * WS - 1) + (i1 % WS) + WS - 1;
-    const int li0 = lab_s[i0], li1 = lab_s[i1];
+    const int t0 = i0 < NTOK ? i0 : 0, t1 = i1 < NTOK ? i1 : 0;
+    const int rp0 = (t0 / WS + WS - 1) * (2 * WS - 1) + (t0 % WS) + WS - 1;
+    const int rp1 = (t1 / WS + WS - 1) * (2 * WS - 1) + (t1 % WS) + WS - 1;
+    const int li0 = lab_s[t0], li1 = lab_s[t1];
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -214,6 +230,7 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
           if (collab[nt][e] != li0) s0 += -100.0f;
           if (collab[nt][e] != li1) s1 += -100.0f;
         }
+        if (NTOK < AB_N && !((colreal >> (nt * 2 + e)) & 1u)) s0 = s1 = -INFINITY;  // empty key slot
         sc[nt][e] = s0;
         sc[nt][2 + e] = s1;
         mx0 = fmaxf(mx0, s0);
@@ -287,9 +304,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
     ab_load_a(k_base, jt * 16, lane, af);
     ab_mm_nt(st, af, q_base, lane);  // rows = keys j, columns = queries i
     const int j0 = jt * 16 + gq, j1 = j0 + 8;
-    const int cp0 = (j0 / WS) * (2 * WS - 1) + (j0 % WS);
-    const int cp1 = (j1 / WS) * (2 * WS - 1) + (j1 % WS);
-    const int lj0 = lab_s[j0], lj1 = lab_s[j1];
+    const int u0 = j0 < NTOK ? j0 : 0, u1 = j1 < NTOK ? j1 : 0;
+    const int cp0 = (u0 / WS) * (2 * WS - 1) + (u0 % WS);
+    const int cp1 = (u1 / WS) * (2 * WS - 1) + (u1 % WS);
+    const int lj0 = lab_s[u0], lj1 = lab_s[u1];
     float dpt[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { dpt[nt][0] = dpt[nt][1] = dpt[nt][2] = dpt[nt][3] = 0.f; }
@@ -310,6 +328,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32) window_attn_bwd_kernel(const Ms
         if (masked) {
           if (collab[nt][e] != lj0) s0 += -100.0f;
           if (collab[nt][e] != lj1) s1 += -100.0f;
+        }
+        if (NTOK < AB_N) {  // empty key slots (rows here): P = 0
+          if (j0 >= NTOK) s0 = -INFINITY;
+          if (j1 >= NTOK) s1 = -INFINITY;
         }
         const float p0 = __expf(s0 - mi) * ii, p1 = __expf(s1 - mi) * ii;
         st[nt][e] = p0;
@@ -350,7 +372,7 @@ extern "C" int mst_window_attention_bwd(const MstWindowAttnBwd* a, void* stream)
   const bool dual = a->v2 != nullptr;
   if (dual != (a->dout2 != nullptr) || dual != (a->dv2 != nullptr)) return MST_ERR_BAD_ARG;
   if (a->B <= 0 || a->H <= 0 || a->W <= 0 || a->heads <= 0 || a->heads > 32) return MST_ERR_BAD_ARG;
-  if (a->ws != 8 || a->H % 8 != 0 || a->W % 8 != 0 || a->heads % AB_WARPS != 0) return MST_ERR_UNSUPPORTED;
+  if ((a->ws != 8 && a->ws != 7) || a->H % a->ws != 0 || a->W % a->ws != 0 || a->heads % AB_WARPS != 0) return MST_ERR_UNSUPPORTED;
   if ((a->ldq | a->ldk | a->ldv | a->ldo | a->lddq | a->lddk | a->lddv) % 8 != 0) return MST_ERR_BAD_ARG;
   if (a->shift < 0 || a->shift >= a->ws) return MST_ERR_BAD_ARG;
   const WinGeom g = make_geom(a->H, a->W, a->ws, a->shift);
@@ -358,12 +380,16 @@ extern "C" int mst_window_attention_bwd(const MstWindowAttnBwd* a, void* stream)
   const size_t smem = AB_WARPS * warp_bytes + sizeof(float) * AB_NT * a->heads + sizeof(float) * AB_WARPS * AB_NT + sizeof(int) * 2 * AB_N;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(window_attn_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   if (smem > 160 * 1024) return MST_ERR_UNSUPPORTED;
   const long long tasks = (long long)a->B * g.nW * a->heads;
-  window_attn_bwd_kernel<<<(unsigned)(tasks / AB_WARPS), AB_WARPS * 32, smem, (cudaStream_t)stream>>>(*a, g);
+  if (a->ws == 8)
+    window_attn_bwd_kernel<8><<<(unsigned)(tasks / AB_WARPS), AB_WARPS * 32, smem, (cudaStream_t)stream>>>(*a, g);
+  else
+    window_attn_bwd_kernel<7><<<(unsigned)(tasks / AB_WARPS), AB_WARPS * 32, smem, (cudaStream_t)stream>>>(*a, g);
   return (int)cudaGetLastError();
 }

@@ -62,7 +62,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_loss_finalize": "loss_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
              "mst_window_attention_bwd": "window_attn_bwd_kernel", "mst_layernorm_bwd": "layernorm_bwd_kernel",
              "mst_instnorm_bwd_stats": "instnorm_bwd_stats_kernel", "mst_instnorm_bwd_apply": "instnorm_bwd_apply_kernel",
-             "mst_blend_bwd": "blend_bwd_kernel", "mst_add_cast": "add_cast_kernel", "mst_reflect_fold": "reflect_fold_kernel",
+             "mst_blend_bwd": "blend_bwd_kernel", "mst_add_cast": "add_cast_kernel", "mst_token_map_copy": "token_map_kernel", "mst_reflect_fold": "reflect_fold_kernel",
              "mst_maxpool2x2_bwd": "maxpool2x2_bwd_kernel", "mst_nchw3_to_nhwc8": "nchw3_to_nhwc8_kernel",
              "mst_loss_bwd_stats": "loss_bwd_stats_kernel", "mst_loss_bwd_apply": "loss_bwd_apply_kernel"}
 
@@ -475,6 +475,19 @@ def add_cast(a, b=None, out32=None, out16=None) -> None:
     n = a.numel()
     _launch("mst_add_cast", lambda: _lib.lib().mst_add_cast(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), _ptr(out32, torch.float32, "out32"),
                                                             _ptr(out16, torch.bfloat16, "out16"), n, _stream()), nbytes=8.0 * n)
+
+
+def token_map_copy(src, dst, B, Hs, Ws, Hd, Wd, accumulate=False) -> None:
+    """Pad (zero fill) / crop a [B,Hs,Ws,C] token map into [B,Hd,Wd,C]; accumulate=True: fp32 dst += cropped fp32 src."""
+    if src.dtype != dst.dtype or src.dtype not in (torch.float32, torch.bfloat16) or (accumulate and src.dtype != torch.float32):
+        raise TypeError("token_map_copy: bf16 -> bf16 or fp32 -> fp32 (accumulate: fp32 only)")
+    Cdim = src.numel() // (B * Hs * Ws)
+    if src.numel() != B * Hs * Ws * Cdim or dst.numel() != B * Hd * Wd * Cdim:
+        raise ValueError("token_map_copy: shapes do not match the map sizes")
+    tb = Cdim * src.element_size()
+    _launch("mst_token_map_copy", lambda: _lib.lib().mst_token_map_copy(_ptr(src, src.dtype, "src"), _ptr(dst, dst.dtype, "dst"), B, Hs, Ws, Hd, Wd,
+                                                                        tb, int(accumulate), _stream()),
+            nbytes=float(tb) * B * (min(Hs, Hd) * min(Ws, Wd) * (3 if accumulate else 1) + Hd * Wd))
 
 
 def reflect_fold(dxp, gate, dx, B, H, W, Cdim, upsample=False) -> None:

@@ -119,15 +119,39 @@ class _Geo:
         self.B, self.H, self.W, self.C, self.heads, self.win, self.shift = B, H, W, C, heads, win, shift
         self.T = B * H * W
         self.HW = H * W
+        # maps that are not a multiple of the window (7x7 windows on 32x32 maps, the reference CLI default, train.py:703-711) are
+        # zero-padded at the bottom / right INSIDE every attention (style_transformer.py:77-87, :476-479): the training path
+        # materialises the padded token map (pad -> projections + attention on [B,Hp,Wp] -> crop); T == Tp otherwise.
+        self.Hp, self.Wp = -(-H // win) * win, -(-W // win) * win
+        self.padded = (self.Hp, self.Wp) != (H, W)
+        self.Tp, self.HWp = B * self.Hp * self.Wp, self.Hp * self.Wp
 
 
 def _attn(g: _Geo, q, k, v, out, table, ldq, ldk, ldv, v2=None, out2=None):
-    ops.window_attention(q, k, v, out, table, g.B, g.H, g.W, g.heads, g.win, g.shift, ldq, ldk, ldv, g.C, v2=v2, out2=out2)
+    ops.window_attention(q, k, v, out, table, g.B, g.Hp, g.Wp, g.heads, g.win, g.shift, ldq, ldk, ldv, g.C, v2=v2, out2=out2)
 
 
 def _attn_bwd(g: _Geo, q, k, v, dout, dq, dk, dv, table, dtable, ldq, ldk, ldv, lddq, lddk, lddv, v2=None, dout2=None, dv2=None):
-    ops.window_attention_bwd(q, k, v, dout, dq, dk, dv, table, dtable, g.B, g.H, g.W, g.heads, g.win, g.shift, ldq, ldk, ldv, g.C,
+    ops.window_attention_bwd(q, k, v, dout, dq, dk, dv, table, dtable, g.B, g.Hp, g.Wp, g.heads, g.win, g.shift, ldq, ldk, ldv, g.C,
                              lddq, lddk, lddv, v2=v2, dout2=dout2, dv2=dv2)
+
+
+def _pad16(g: _Geo, x16, ws_: "Workspace" = None, name: str = ""):
+    """bf16 [T,C] -> [Tp,C] with zero tokens at the bottom / right of every map; the tensor itself on window-multiple maps."""
+    if not g.padded:
+        return x16
+    out = ws_.bf16(name, g.Tp, x16.shape[1]) if ws_ is not None else _e16(x16.device, g.Tp, x16.shape[1])
+    ops.token_map_copy(x16, out, g.B, g.H, g.W, g.Hp, g.Wp)
+    return out
+
+
+def _crop16(g: _Geo, xp16, ws_: "Workspace" = None, name: str = ""):
+    """bf16 [Tp,C] -> [T,C]: the reference's `x[:, :H, :W, :]` after the attention (and its adjoint's view of a padded gradient)."""
+    if not g.padded:
+        return xp16
+    out = ws_.bf16(name, g.T, xp16.shape[1]) if ws_ is not None else _e16(xp16.device, g.T, xp16.shape[1])
+    ops.token_map_copy(xp16, out, g.B, g.Hp, g.Wp, g.H, g.W)
+    return out
 
 
 def _mlp_fwd(x16, res32, fc1: _Lin, fc2: _Lin, T, dev, rs, rows, want16=True):
@@ -147,6 +171,18 @@ def _lin_bwd(dy16, x16, M, lin: _Lin, gW, gb, *, ld_dy=None, ld_x=None, res=None
         ops.gemm(dy16, lin.bwd, M, lda=ld_dy, res=res, out_f32=out_f32, out_bf16=out_bf16)
     ops.wgrad(dy16, x16, gW, M, lin.N, lin.K, ld_dy=ld_dy, ld_x=ld_x)
     ops.colsum(dy16, M, lin.N, gb, ld=ld_dy)
+
+
+def _lin_bwd_acc(g: _Geo, dy16p, x16p, lin: _Lin, gW, gb, gstream, ws_: "Workspace", *, ld_dy=None):
+    """_lin_bwd on the (padded) attention map whose data gradient is added to the fp32 stream `gstream` on the unpadded map.
+    The bias gradient sums over the padded tokens too (they hold the bias in the forward), the weight gradient sees their zero
+    input, and their data gradient is dropped by the crop -- exactly the adjoint of F.pad -> Linear."""
+    if not g.padded:
+        _lin_bwd(dy16p, x16p, g.T, lin, gW, gb, ld_dy=ld_dy, res=gstream, out_f32=gstream)
+        return
+    tmp = ws_.f32("bw_dxp32", g.Tp, lin.K)
+    _lin_bwd(dy16p, x16p, g.Tp, lin, gW, gb, ld_dy=ld_dy, out_f32=tmp)
+    ops.token_map_copy(tmp, gstream, g.B, g.Hp, g.Wp, g.H, g.W, accumulate=True)
 
 
 def _mlp_bwd(g16, x16, hpre, hact, fc1: _Lin, fc2: _Lin, T, book: GradBook, pre: str, ws_: Workspace, *, res=None, out_f32=None,
@@ -180,7 +216,7 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
     """Forward of StyleTransformer.forward (:1229-1245) that records a tape.  sd_scales: None or fp32 [k, 9, B] per-sample
     stochastic-depth factors in the reference's draw order (enc MHA Key, MLP_Key, MHA Scale, MLP_Scale, MHA Shift, MLP_Shift,
     dec attn, dec mlp, last MLP).  Returns (out32 [T,C], tape)."""
-    dev, T, C = fc32.device, g.T, g.C
+    dev, T, C, Tp = fc32.device, g.T, g.C, g.Tp
     rows = g.HW
     x32 = fc32.reshape(T, C).contiguous()
     key32 = fs32.reshape(T, C).contiguous()
@@ -188,41 +224,50 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
     key16 = _e16(dev, T, C)
     ops.cast_bf16(key32, key16)
     scale16 = shift16 = key16
+    # attention inputs on the padded map (the tensors themselves when the map is a window multiple); carried across layers
+    key16p = scale16p = shift16p = _pad16(g, key16)
     tape = []
     for l in range(k):
         s = (lambda i: sd_scales[l, i].contiguous()) if sd_scales is not None else (lambda i: None)
         t = {}
         # ---------------- StyleEncoder ----------------
-        t["key16_in"], t["scale16_in"], t["shift16_in"] = key16, scale16, shift16
-        qkv1, o1 = _e16(dev, T, 3 * C), _e16(dev, T, C)
-        ops.gemm(key16, w.enc_qkv.fwd, T, out_bf16=qkv1)
-        _attn(g, qkv1, qkv1[:, C:], qkv1[:, 2 * C:], o1, w.enc_table, 3 * C, 3 * C, 3 * C)
+        t["key16_in"], t["scale16_in"], t["shift16_in"] = key16p, scale16p, shift16p
+        qkv1, o1p = _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
+        ops.gemm(key16p, w.enc_qkv.fwd, Tp, out_bf16=qkv1)
+        _attn(g, qkv1, qkv1[:, C:], qkv1[:, 2 * C:], o1p, w.enc_table, 3 * C, 3 * C, 3 * C)
+        o1 = _crop16(g, o1p)
         key32a, key16a = _e32(dev, T, C), _e16(dev, T, C)
         ops.gemm(o1, w.enc_proj.fwd, T, res=key32, out_f32=key32a, out_bf16=key16a, row_scale=s(0), rows_per_scale=rows)
         fc1, fc2, _ = w.mlp["key"]
         key32, key16, hp, ha = _mlp_fwd(key16a, key32a, fc1, fc2, T, dev, s(1), rows)
-        t.update(qkv1=qkv1, o1=o1, key16a=key16a, hK=(hp, ha), key16b=key16, key32b=key32)
-        qk2, vs, vh = _e16(dev, T, 2 * C), _e16(dev, T, C), _e16(dev, T, C)
-        ops.gemm(key16, w.enc_qk.fwd, T, out_bf16=qk2)
-        ops.gemm(scale16, w.enc_v.fwd, T, out_bf16=vs)
-        ops.gemm(shift16, w.enc_v.fwd, T, out_bf16=vh)
-        os_, oh = _e16(dev, T, C), _e16(dev, T, C)
-        _attn(g, qk2, qk2[:, C:], vs, os_, w.enc_table, 2 * C, 2 * C, C, v2=vh, out2=oh)
+        key16p = _pad16(g, key16)
+        t.update(qkv1=qkv1, o1=o1, key16a=key16a, hK=(hp, ha), key16b=key16p, key32b=key32)
+        qk2, vs, vh = _e16(dev, Tp, 2 * C), _e16(dev, Tp, C), _e16(dev, Tp, C)
+        ops.gemm(key16p, w.enc_qk.fwd, Tp, out_bf16=qk2)
+        ops.gemm(scale16p, w.enc_v.fwd, Tp, out_bf16=vs)
+        ops.gemm(shift16p, w.enc_v.fwd, Tp, out_bf16=vh)
+        osp, ohp = _e16(dev, Tp, C), _e16(dev, Tp, C)
+        _attn(g, qk2, qk2[:, C:], vs, osp, w.enc_table, 2 * C, 2 * C, C, v2=vh, out2=ohp)
+        os_, oh = _crop16(g, osp), _crop16(g, ohp)
         scale32a, scale16a = _e32(dev, T, C), _e16(dev, T, C)
         ops.gemm(os_, w.enc_proj.fwd, T, res=scale32, out_f32=scale32a, out_bf16=scale16a, row_scale=s(2), rows_per_scale=rows)
         fc1, fc2, _ = w.mlp["scale"]
         scale32, scale16, hp, ha = _mlp_fwd(scale16a, scale32a, fc1, fc2, T, dev, s(3), rows)
-        t.update(qk2=qk2, vs=vs, vh=vh, os=os_, oh=oh, scale16a=scale16a, hS=(hp, ha), scale16b=scale16)
+        scale16p = _pad16(g, scale16)
+        t.update(qk2=qk2, vs=vs, vh=vh, os=os_, oh=oh, scale16a=scale16a, hS=(hp, ha), scale16b=scale16p)
         shift32a, shift16a = _e32(dev, T, C), _e16(dev, T, C)
         ops.gemm(oh, w.enc_proj.fwd, T, res=shift32, out_f32=shift32a, out_bf16=shift16a, row_scale=s(4), rows_per_scale=rows)
         fc1, fc2, _ = w.mlp["shift"]
         shift32, shift16, hp, ha = _mlp_fwd(shift16a, shift32a, fc1, fc2, T, dev, s(5), rows)
-        t.update(shift16a=shift16a, hH=(hp, ha), shift16b=shift16)
+        shift16p = _pad16(g, shift16)
+        t.update(shift16a=shift16a, hH=(hp, ha), shift16b=shift16p)
         # ---------------- StyleDecoder ----------------
-        ln1, qkv3, o3 = _e16(dev, T, C), _e16(dev, T, 3 * C), _e16(dev, T, C)
+        ln1, qkv3, o3p = _e16(dev, T, C), _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
         ops.layernorm(x32, w.n1[0], w.n1[1], ln1, T, C)
-        ops.gemm(ln1, w.dec_qkv.fwd, T, out_bf16=qkv3)
-        _attn(g, qkv3, qkv3[:, C:], qkv3[:, 2 * C:], o3, w.dec_table, 3 * C, 3 * C, 3 * C)
+        ln1 = _pad16(g, ln1)
+        ops.gemm(ln1, w.dec_qkv.fwd, Tp, out_bf16=qkv3)
+        _attn(g, qkv3, qkv3[:, C:], qkv3[:, 2 * C:], o3p, w.dec_table, 3 * C, 3 * C, 3 * C)
+        o3 = _crop16(g, o3p)
         x32a = _e32(dev, T, C)
         ops.gemm(o3, w.dec_proj.fwd, T, res=x32, out_f32=x32a, row_scale=s(6), rows_per_scale=rows)
         ln2 = _e16(dev, T, C)
@@ -236,14 +281,17 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
         ops.instnorm_apply(query32, mean, rstd, g.B, g.HW, C, y16=qhat)
         ops.instnorm_stats(key32, mean, rstd, g.B, g.HW, C)
         ops.instnorm_apply(key32, mean, rstd, g.B, g.HW, C, y16=kin)
-        kk32 = _e32(dev, T, C)
-        ops.gemm(kin, w.sm_k.fwd, T, out_f32=kk32)
-        ops.instnorm_stats(kk32, mean, rstd, g.B, g.HW, C)
-        ops.instnorm_apply(kk32, mean, rstd, g.B, g.HW, C, y16=khat)
-        vs2, vh2, osg, omu = _e16(dev, T, C), _e16(dev, T, C), _e16(dev, T, C), _e16(dev, T, C)
-        ops.gemm(scale16, w.sm_vs.fwd, T, out_bf16=vs2)
-        ops.gemm(shift16, w.sm_vh.fwd, T, out_bf16=vh2)
-        _attn(g, qhat, khat, vs2, osg, w.sm_table, C, C, C, v2=vh2, out2=omu)
+        # padded q tokens are zero (no Q projection, :511-514); Wk runs on the padded Key and its InstanceNorm over the PADDED map (:520-530)
+        qhat, kin = _pad16(g, qhat), _pad16(g, kin)
+        kk32, khat = _e32(dev, Tp, C), (khat if not g.padded else _e16(dev, Tp, C))
+        ops.gemm(kin, w.sm_k.fwd, Tp, out_f32=kk32)
+        ops.instnorm_stats(kk32, mean, rstd, g.B, g.HWp, C)
+        ops.instnorm_apply(kk32, mean, rstd, g.B, g.HWp, C, y16=khat)
+        vs2, vh2, osgp, omup = _e16(dev, Tp, C), _e16(dev, Tp, C), _e16(dev, Tp, C), _e16(dev, Tp, C)
+        ops.gemm(scale16p, w.sm_vs.fwd, Tp, out_bf16=vs2)
+        ops.gemm(shift16p, w.sm_vh.fwd, Tp, out_bf16=vh2)
+        _attn(g, qhat, khat, vs2, osgp, w.sm_table, C, C, C, v2=vh2, out2=omup)
+        osg, omu = _crop16(g, osgp), _crop16(g, omup)
         sigma32, y32, y16 = _e32(dev, T, C), _e32(dev, T, C), _e16(dev, T, C)
         ops.gemm(osg, w.sm_proj.fwd, T, out_f32=sigma32)
         ops.gemm(omu, w.sm_proj.fwd, T, res=query32, mul=sigma32, out_f32=y32, out_bf16=y16)
@@ -258,7 +306,7 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
                                book: GradBook, ws_: Workspace):
     """Adjoint of style_transformer_forward_train: accumulates every parameter gradient into `book`; returns nothing for
     Fc / Fs (the Swin encoder is frozen in the reference's default training setup, train.py:216-218)."""
-    dev, T, C = g_out.device, g.T, g.C
+    dev, T, C, Tp = g_out.device, g.T, g.C, g.Tp
     rows = g.HW
     gx = g_out.reshape(T, C).clone()  # grad w.r.t. the layer output (fp32 stream, updated in place)
     gkey = torch.zeros(T, C, dtype=F32, device=dev)
@@ -282,15 +330,17 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
         _lin_bwd(gsig16, t["osg"], T, w.sm_proj, book[SM + "proj.weight"], book[SM + "proj.bias"], out_bf16=dosg)
         _lin_bwd(gmu16, t["omu"], T, w.sm_proj, book[SM + "proj.weight"], book[SM + "proj.bias"], out_bf16=domu)
         # ---- shared-softmax sigma/mu attention
-        dqhat, dkhat, dvs2, dvh2 = (ws_.bf16(n, T, C) for n in ("bw_dqhat", "bw_dkhat", "bw_dvs2", "bw_dvh2"))
+        dqhat, dkhat, dvs2, dvh2 = (ws_.bf16(n, Tp, C) for n in ("bw_dqhat", "bw_dkhat", "bw_dvs2", "bw_dvh2"))
+        dosg, domu = _pad16(g, dosg, ws_, "bw_dosg_p"), _pad16(g, domu, ws_, "bw_domu_p")  # the crop's adjoint: zero gradient at padded tokens
         _attn_bwd(g, t["qhat"], t["khat"], t["vs2"], dosg, dqhat, dkhat, dvs2, w.sm_table, book[SM + "relative_position_bias_table"],
                   C, C, C, C, C, C, v2=t["vh2"], dout2=domu, dv2=dvh2)
-        _lin_bwd(dvs2, t["scale16b"], T, w.sm_vs, book[SM + "Wv_scale.weight"], book[SM + "Wv_scale.bias"], res=gscale, out_f32=gscale)
-        _lin_bwd(dvh2, t["shift16b"], T, w.sm_vh, book[SM + "Wv_shift.weight"], book[SM + "Wv_shift.bias"], res=gshift, out_f32=gshift)
-        # ---- khat = IN(Wk IN(Key)) ; qhat = IN(IN(Query))
-        dkk16, dkin16 = ws_.bf16("bw_dkk", T, C), ws_.bf16("bw_dkin", T, C)
-        ops.instnorm_bwd(t["kk32"], dkhat, coef, g.B, g.HW, C, dx16=dkk16)
-        _lin_bwd(dkk16, t["kin"], T, w.sm_k, book[SM + "Wk.weight"], book[SM + "Wk.bias"], out_bf16=dkin16)
+        _lin_bwd_acc(g, dvs2, t["scale16b"], w.sm_vs, book[SM + "Wv_scale.weight"], book[SM + "Wv_scale.bias"], gscale, ws_)
+        _lin_bwd_acc(g, dvh2, t["shift16b"], w.sm_vh, book[SM + "Wv_shift.weight"], book[SM + "Wv_shift.bias"], gshift, ws_)
+        # ---- khat = IN_padded(Wk pad(IN(Key))) ; qhat = pad(IN(IN(Query)))
+        dkk16, dkin16 = ws_.bf16("bw_dkk", Tp, C), ws_.bf16("bw_dkin", Tp, C)
+        ops.instnorm_bwd(t["kk32"], dkhat, coef, g.B, g.HWp, C, dx16=dkk16)
+        _lin_bwd(dkk16, t["kin"], Tp, w.sm_k, book[SM + "Wk.weight"], book[SM + "Wk.bias"], out_bf16=dkin16)
+        dkin16, dqhat = _crop16(g, dkin16, ws_, "bw_dkin_c"), _crop16(g, dqhat, ws_, "bw_dqhat_c")
         ops.instnorm_bwd(t["key32b"], dkin16, coef, g.B, g.HW, C, dx_accum=gkey)
         ops.instnorm_bwd(t["query32"], dqhat, coef, g.B, g.HW, C, twice=True, dx_accum=gquery)
         # ---- query = x_a + s7 * MLP_D(LN2(x_a))
@@ -303,11 +353,15 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
         g16 = _scaled16(gquery, s(6), rows, ws_)
         do3 = ws_.bf16("bw_do", T, C)
         _lin_bwd(g16, t["o3"], T, w.dec_proj, book[D_ATT + "proj.weight"], book[D_ATT + "proj.bias"], out_bf16=do3)
-        dqkv = ws_.bf16("bw_dqkv", T, 3 * C)
+        dqkv = ws_.bf16("bw_dqkv", Tp, 3 * C)
         q3 = t["qkv3"]
+        do3 = _pad16(g, do3, ws_, "bw_do_p")
         _attn_bwd(g, q3, q3[:, C:], q3[:, 2 * C:], do3, dqkv, dqkv[:, C:], dqkv[:, 2 * C:], w.dec_table,
                   book[D_ATT + "relative_position_bias_table"], 3 * C, 3 * C, 3 * C, 3 * C, 3 * C, 3 * C)
-        _lin_bwd(dqkv, t["ln1"], T, w.dec_qkv, dec_qkv_w, dec_qkv_b, out_bf16=dln)
+        dlnp = ws_.bf16("bw_dln_p", Tp, C) if g.padded else dln
+        _lin_bwd(dqkv, t["ln1"], Tp, w.dec_qkv, dec_qkv_w, dec_qkv_b, out_bf16=dlnp)
+        if g.padded:
+            ops.token_map_copy(dlnp, dln, g.B, g.Hp, g.Wp, g.H, g.W)
         ops.layernorm_bwd(t["x32_in"], w.n1[0], dln, gquery, book[D_BLK + "norm1.weight"], book[D_BLK + "norm1.bias"], T, C)
         gx = gquery  # grad w.r.t. this layer's Fcs input = previous layer's output
 
@@ -321,24 +375,26 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
             _mlp_bwd(g16, t[a16], t[hkey][0], t[hkey][1], fc1, fc2, T, book, pre, ws_, res=gstream, out_f32=gstream)
             g16 = _scaled16(gstream, s(i_att), rows, ws_)
             _lin_bwd(g16, t[o_saved], T, w.enc_proj, pw, pb, out_bf16=d_o)
-        dqk2, dvs, dvh = ws_.bf16("bw_dqk2", T, 2 * C), ws_.bf16("bw_dvs", T, C), ws_.bf16("bw_dvh", T, C)
+        dqk2, dvs, dvh = ws_.bf16("bw_dqk2", Tp, 2 * C), ws_.bf16("bw_dvs", Tp, C), ws_.bf16("bw_dvh", Tp, C)
         qk2 = t["qk2"]
         etab = book[E_ATT + "relative_position_bias_table"]
-        _attn_bwd(g, qk2, qk2[:, C:], t["vs"], dos, dqk2, dqk2[:, C:], dvs, w.enc_table, etab, 2 * C, 2 * C, C, 2 * C, 2 * C, C,
-                  v2=t["vh"], dout2=doh, dv2=dvh)
+        dosp, dohp = _pad16(g, dos, ws_, "bw_dos_p"), _pad16(g, doh, ws_, "bw_doh_p")
+        _attn_bwd(g, qk2, qk2[:, C:], t["vs"], dosp, dqk2, dqk2[:, C:], dvs, w.enc_table, etab, 2 * C, 2 * C, C, 2 * C, 2 * C, C,
+                  v2=t["vh"], dout2=dohp, dv2=dvh)
         wv_w, wv_b = enc_qkv_w[2 * C:], enc_qkv_b[2 * C:]
-        _lin_bwd(dvs, t["scale16_in"], T, w.enc_v, wv_w, wv_b, res=gscale, out_f32=gscale)
-        _lin_bwd(dvh, t["shift16_in"], T, w.enc_v, wv_w, wv_b, res=gshift, out_f32=gshift)
-        _lin_bwd(dqk2, t["key16b"], T, w.enc_qk, enc_qkv_w[:2 * C], enc_qkv_b[:2 * C], res=gkey, out_f32=gkey)
+        _lin_bwd_acc(g, dvs, t["scale16_in"], w.enc_v, wv_w, wv_b, gscale, ws_)
+        _lin_bwd_acc(g, dvh, t["shift16_in"], w.enc_v, wv_w, wv_b, gshift, ws_)
+        _lin_bwd_acc(g, dqk2, t["key16b"], w.enc_qk, enc_qkv_w[:2 * C], enc_qkv_b[:2 * C], gkey, ws_)
         fc1, fc2, pre = w.mlp["key"]
         g16 = _scaled16(gkey, s(1), rows, ws_)
         _mlp_bwd(g16, t["key16a"], t["hK"][0], t["hK"][1], fc1, fc2, T, book, pre, ws_, res=gkey, out_f32=gkey)
         g16 = _scaled16(gkey, s(0), rows, ws_)
         _lin_bwd(g16, t["o1"], T, w.enc_proj, pw, pb, out_bf16=dos)
         q1 = t["qkv1"]
-        _attn_bwd(g, q1, q1[:, C:], q1[:, 2 * C:], dos, dqkv, dqkv[:, C:], dqkv[:, 2 * C:], w.enc_table, etab,
+        dosp = _pad16(g, dos, ws_, "bw_dos_p")
+        _attn_bwd(g, q1, q1[:, C:], q1[:, 2 * C:], dosp, dqkv, dqkv[:, C:], dqkv[:, 2 * C:], w.enc_table, etab,
                   3 * C, 3 * C, 3 * C, 3 * C, 3 * C, 3 * C)
-        _lin_bwd(dqkv, t["key16_in"], T, w.enc_qkv, enc_qkv_w, enc_qkv_b, res=gkey, out_f32=gkey)
+        _lin_bwd_acc(g, dqkv, t["key16_in"], w.enc_qkv, enc_qkv_w, enc_qkv_b, gkey, ws_)
         if l == 0:
             break
         # layer l-1's Key/Scale/Shift outputs feed this layer: the streams carry over as they are

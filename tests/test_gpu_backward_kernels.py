@@ -213,15 +213,17 @@ def _attn_ref(q, k, v, table, B, H, W, heads, ws, shift, v2=None):
     return unwin(p @ vw), unwin(p @ win(v2))
 
 
+@pytest.mark.parametrize("ws", [8, 7])
 @pytest.mark.parametrize("shift", [0, 4])
 @pytest.mark.parametrize("dual", [False, True])
-def test_window_attention_bwd(shift, dual):
+def test_window_attention_bwd(shift, dual, ws):
+    """ws = 7: 49-token windows in 64 slots on a map that is a multiple of 7 (the training path pads the map itself)."""
     ops = _ops()
-    B, H, W, heads, ws, C = 2, 16, 24, 8, 8, 256
+    B, H, W, heads, C = 2, 2 * ws, 3 * ws, 8, 256
     T = B * H * W
     q, k, v, v2 = (_rand(T, C, seed=s).bfloat16() for s in (1, 2, 3, 4))
     do, do2 = _rand(T, C, seed=5).bfloat16(), _rand(T, C, seed=6).bfloat16()
-    table = _rand(225, heads, seed=7, scale=0.5)
+    table = _rand((2 * ws - 1) ** 2, heads, seed=7, scale=0.5)
     qr, kr, vr, v2r = (t.float().clone().requires_grad_(True) for t in (q, k, v, v2))
     tr = table.clone().requires_grad_(True)
     if dual:
@@ -238,7 +240,7 @@ def test_window_attention_bwd(shift, dual):
     _close(of, o.detach(), 2e-2, "fwd")
     dq, dk, dv = (torch.empty(T, C, device="cuda", dtype=torch.bfloat16) for _ in range(3))
     dv2 = torch.empty(T, C, device="cuda", dtype=torch.bfloat16) if dual else None
-    dtab = torch.zeros(225, heads, device="cuda")
+    dtab = torch.zeros((2 * ws - 1) ** 2, heads, device="cuda")
     ops.window_attention_bwd(q.cuda(), k.cuda(), v.cuda(), do.cuda(), dq, dk, dv, table.cuda(), dtab, B, H, W, heads, ws, shift,
                              C, C, C, C, C, C, C, v2=v2.cuda() if dual else None, dout2=do2.cuda() if dual else None, dv2=dv2)
     _close(dq, qr.grad, 3e-2, "dq")

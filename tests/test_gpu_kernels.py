@@ -248,6 +248,30 @@ def test_upsample2x_nhwc():
     assert torch.equal(y, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_token_map_pad_crop(dtype):
+    """mst_token_map_copy: F.pad(x, (0,0,0,pad_r,0,pad_b)) / x[:, :H, :W, :] of style_transformer.py:77-87, :230-232 -- bit-exact."""
+    from mastermetastyletransfer_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Hp, Wp, C = 3, 16, 18, 21, 21, 64
+    x = torch.randn(B, H, W, C, generator=g).to(dtype).cuda()
+    xp = torch.full((B, Hp, Wp, C), 7.0, dtype=dtype, device="cuda")
+    ops.token_map_copy(x, xp, B, H, W, Hp, Wp)
+    assert torch.equal(xp, F.pad(x, (0, 0, 0, Wp - W, 0, Hp - H)))
+    y = torch.randn(B, Hp, Wp, C, generator=g).to(dtype).cuda()
+    yc = torch.empty(B, H, W, C, dtype=dtype, device="cuda")
+    ops.token_map_copy(y, yc, B, Hp, Wp, H, W)
+    assert torch.equal(yc, y[:, :H, :W])
+    if dtype == torch.float32:
+        acc = torch.randn(B, H, W, C, generator=g).cuda()
+        want = acc + y[:, :H, :W]
+        ops.token_map_copy(y, acc, B, Hp, Wp, H, W, accumulate=True)
+        assert torch.equal(acc, want)
+    else:
+        with pytest.raises(TypeError):
+            ops.token_map_copy(y, yc, B, Hp, Wp, H, W, accumulate=True)
+
+
 def test_bad_arguments_raise():
     ops = _ops()
     A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)

@@ -289,6 +289,35 @@ def test_style_transformer_grads(model, sd, k):
     _cmp_all(st, ps)
 
 
+@pytest.mark.parametrize("k,hw", [(1, 16), (2, 16), (1, 32)])
+def test_style_transformer_grads_7x7_windows_padded(k, hw):
+    """SURVEY 8f-1, training side: 7x7 windows (the reference CLI default, train.py:703-711) on maps that are not a window
+    multiple (16 -> 21, 32 -> 35).  Padded tokens carry the projection biases into every attention, the sigma/mu attention's
+    InstanceNorm of Wk.K runs over the padded map, bias gradients sum over the padded tokens too (style_transformer.py:77-87,
+    :476-530).  Forward and every parameter gradient vs autograd through the CPU oracle."""
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel, synthetic
+    from oracle import master_oracle as O
+    m = MasterStyleTransferModel(style_encoder_window_size=[7, 7], style_decoder_window_size=[7, 7])
+    synthetic.fill_state_dict_(m, 0)
+    sd7 = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+    st = m.cuda().eval().style_transformer
+    g = torch.Generator().manual_seed(17)
+    fc, fs = torch.randn(2, hw, hw, 256, generator=g), torch.randn(2, hw, hw, 256, generator=g)
+    G = torch.randn(2, hw, hw, 256, generator=g)
+    ps = _oracle_params(sd7, "style_transformer.")
+    ref = O.style_transformer(ps, fc, fs, k, ws=7, sh=4)
+    (ref * G).sum().backward()
+    st.zero_grad(set_to_none=True)
+    out = st(fc.cuda(), fs.cuda(), k)
+    assert out.requires_grad and out.shape == (2, hw, hw, 256)
+    assert ((out.detach().cpu() - ref.detach()).abs().max() / (ref.max() - ref.min())).item() <= 3e-2
+    with torch.no_grad():  # the taped (materialised padding) and the inference (padding inside the attention kernel) forwards agree
+        inf = st(fc.cuda(), fs.cuda(), k)
+    assert ((out.detach() - inf).abs().max() / (ref.max() - ref.min())).item() <= 3e-2
+    (out * G.cuda()).sum().backward()
+    _cmp_all(st, ps)
+
+
 def test_style_transformer_stochastic_depth(model, sd):
     """Train mode: the per-sample factors are drawn like torchvision's StochasticDepth('row') and applied to all nine
     residual branches per layer, forward and backward."""
@@ -405,3 +434,35 @@ def test_graphed_train_step_matches_eager(model):
     assert le[-1, 0] != le[0, 0]  # the parameters really moved
     worst = max(((a - b).norm() / (a.norm() + 1e-12)).item() for a, b in zip(eager.params, graphed.params))
     assert worst < 2e-3, worst  # (Adam's sign-like first steps amplify the fp32-atomics ordering noise of the gradients)
+
+
+def test_training_steps_with_7x7_windows_reference_cli_default():
+    """The reference CLI's default style-transformer windows ([7,7], train.py:703-711) through the whole inner-loop step
+    (Swin encoder -> padded-window style transformer -> decoder -> VGG loss -> backward -> Adam), eager and as one CUDA graph:
+    the two follow each other and the loss of a repeated batch goes down."""
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel, custom_loss, synthetic
+    from mastermetastyletransfer_b200.training import GraphedTrainStep, InnerLoopTrainer
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.cuda()
+    m = MasterStyleTransferModel(style_encoder_window_size=[7, 7], style_decoder_window_size=[7, 7])
+    synthetic.fill_state_dict_(m, 0)
+    m = m.cuda().eval()
+    for p in m.swin_encoder.parameters():  # train.py:216-218
+        p.requires_grad = False
+    for mod in (m.style_transformer.encoder, m.style_transformer.decoder):
+        mod.stochastic_depth.p = 0.0
+    m.style_transformer.encoder.encoder_stochastic_depth_prob = 0.0
+    content, style = synthetic.synthetic_images(2, 128, seed=9)  # 16x16 feature map -> 21x21 padded
+    content, style = content.cuda(), style.cuda()
+    eager = InnerLoopTrainer(m, loss_fn, inner_lr=1e-4)
+    graphed = InnerLoopTrainer(m, loss_fn, inner_lr=1e-4, capturable=True)
+    g = GraphedTrainStep(graphed, 2, 128, num_layers=1)
+    le, lg = [], []
+    for _ in range(6):
+        le.append(eager.step(content, style, 1).clone())
+        lg.append(g.step(content, style).clone())
+    le, lg = torch.stack(le).cpu(), torch.stack(lg).cpu()
+    assert torch.isfinite(le).all() and torch.isfinite(lg).all()
+    assert torch.allclose(le, lg, rtol=5e-3), (le, lg)
+    assert le[-1, 0] < le[0, 0], le[:, 0]
