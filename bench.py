@@ -144,13 +144,17 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
     style = style[:1].repeat(batch, 1, 1, 1)  # one style image repeated (train_only_inner_loop.py:491-496)
     content, style = content.to(dev), style.to(dev)
     out = {}
-    for name, dp in (("train_step", True), ("train_step_eager", True), ("meta_step", False)):
-        trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1, capturable=(name == "train_step"))
+    for name, dp in (("train_step", True), ("train_step_eager", True), ("meta_step", False), ("meta_step_eager", False)):
+        is_graphed = name in ("train_step", "meta_step")
+        trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1, capturable=is_graphed)
         if name == "train_step":
             graphed = GraphedTrainStep(trainer, batch, size, layers)
             run = lambda: graphed.step(content, style)
         elif name == "train_step_eager":
             run = lambda: trainer.step(content, style, layers)
+        elif name == "meta_step":  # omega <- theta, one graphed inner step, (all-reduced) Reptile update
+            graphed = GraphedTrainStep(trainer, batch, size, layers)
+            run = lambda: meta_iteration(trainer, style, [content], 1e-4, layers, graphed=graphed)
         else:
             run = lambda: meta_iteration(trainer, style, [content], 1e-4, layers)
         for _ in range(warmup):
@@ -169,12 +173,12 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
         ms = ms.item()
         gf = TRAIN_GF_PER_SAMPLE.get(layers)
         out[name] = {"ms_per_step": ms, "samples_per_s": world * batch / (ms / 1e3), "batch_per_gpu": batch, "size": size,
-                     "layers": layers, "n_gpus": world, "launches_per_step": (ops.launch_count - n0) // steps,
+                     "layers": layers, "n_gpus": world, "launches_per_step": (ops.launch_count - n0) // steps + (graphed.launches if is_graphed else 0),
                      "tflops": (gf * 1e9 * batch / (ms * 1e9)) if gf and size == 256 else None,
                      "loss": [round(v, 5) for v in last.tolist()],
                      "collective": ("all-reduce of the 4.30 M fp32 gradient per step" if name.startswith("train_step") else
                                     "all-reduce of the 4.30 M fp32 (omega - theta) delta per outer iteration") if world > 1 else "none (1 rank)",
-                     "timed": ("one CUDA-graph replay per step (training.GraphedTrainStep)" if name == "train_step" else
+                     "timed": ("one CUDA-graph replay per inner step (training.GraphedTrainStep)" if is_graphed else
                                "eager launches through the C ABI (no CUDA graph)") + ", CUDA events, max over ranks"}
     return out
 

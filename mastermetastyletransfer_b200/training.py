@@ -63,15 +63,18 @@ class InnerLoopTrainer:
         self.omega_st = copy.deepcopy(model.style_transformer).train()
         self.omega_dec = copy.deepcopy(model.decoder).train()
         self.params: List[torch.nn.Parameter] = list(self.omega_st.parameters()) + list(self.omega_dec.parameters())
+        self._theta: List[torch.nn.Parameter] = list(model.style_transformer.parameters()) + list(model.decoder.parameters())
         self.opt = FusedAdam(self.params, lr=inner_lr, capturable=capturable)
         self.max_layers, self.data_parallel, self.group = max_layers, data_parallel, group
         self._rng = random.Random(seed)  # shared seed: every rank samples the same layer count
         self._flat = None
 
     def load_from_theta(self) -> None:
-        """omega <- theta (train.py:428-431)."""
-        self.omega_st.load_state_dict(self.model.style_transformer.state_dict())
-        self.omega_dec.load_state_dict(self.model.decoder.state_dict())
+        """omega <- theta (train.py:428-431: load_state_dict of the two trained modules; their buffers -- the relative-position
+        index maps -- are constants).  One multi-tensor copy into the existing omega storage, so a captured training step
+        (GraphedTrainStep) keeps reading the right memory."""
+        with torch.no_grad():
+            torch._foreach_copy_([p.data for p in self.params], [p.data for p in self._theta])
 
     def step(self, content: torch.Tensor, style: torch.Tensor, num_layers: Optional[int] = None):
         """One inner-loop update; returns the device tensor (total, content, style) without synchronising."""
@@ -96,13 +99,16 @@ class InnerLoopTrainer:
 
 
 def meta_iteration(trainer: InnerLoopTrainer, style: torch.Tensor, content_batches: Iterable[torch.Tensor], outer_lr: float,
-                   num_layers: Optional[int] = None):
+                   num_layers: Optional[int] = None, graphed: Optional["GraphedTrainStep"] = None):
     """One outer iteration of train.py:400-534 for this rank's style task: omega <- theta, one inner step per content
-    batch, then the (all-reduced) Reptile update.  Returns the last inner loss tensor."""
+    batch, then the (all-reduced) Reptile update.  Returns the last inner loss tensor.  graphed: a GraphedTrainStep built
+    on `trainer` -- every inner step is then one CUDA-graph replay (its layer count is the graph's)."""
+    if graphed is not None and graphed.trainer is not trainer:
+        raise ValueError("meta_iteration: `graphed` must wrap the same InnerLoopTrainer")
     trainer.load_from_theta()
     last = None
     for content in content_batches:
-        last = trainer.step(content, style, num_layers)
+        last = graphed.step(content, style) if graphed is not None else trainer.step(content, style, num_layers)
     trainer.outer_update(outer_lr)
     return last
 
@@ -133,9 +139,12 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         opt.zero_grad(set_to_none=True)
+        from . import ops
+        n0 = ops.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = trainer.step(self.content, self.style, num_layers)
+        self.launches = ops.launch_count - n0  # kernels of this library inside one replay
         torch.cuda.synchronize(dev)
         with torch.no_grad():
             for p, v in zip(trainer.params, snap[0]):

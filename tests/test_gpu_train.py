@@ -466,3 +466,35 @@ def test_training_steps_with_7x7_windows_reference_cli_default():
     assert torch.isfinite(le).all() and torch.isfinite(lg).all()
     assert torch.allclose(le, lg, rtol=5e-3), (le, lg)
     assert le[-1, 0] < le[0, 0], le[:, 0]
+
+
+def test_graphed_meta_iteration_matches_eager(model):
+    """meta_iteration (omega <- theta, inner steps, Reptile update of theta, train.py:400-534) with the inner steps replayed
+    from one CUDA graph follows the eager one: same losses, same theta after three outer iterations."""
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    from mastermetastyletransfer_b200.training import GraphedTrainStep, InnerLoopTrainer, meta_iteration
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.cuda()
+    content, style = synthetic.synthetic_images(4, 64, seed=12)
+    content, style = content.cuda(), style[:1].repeat(2, 1, 1, 1).cuda()
+    batches = [content[:2], content[2:]]
+    thetas, losses = [], []
+    for use_graph in (False, True):
+        m = copy.deepcopy(model)
+        for mod in (m.style_transformer.encoder, m.style_transformer.decoder):
+            mod.stochastic_depth.p = 0.0
+        m.style_transformer.encoder.encoder_stochastic_depth_prob = 0.0
+        tr = InnerLoopTrainer(m, loss_fn, inner_lr=1e-3, capturable=use_graph)
+        g = GraphedTrainStep(tr, 2, 64, num_layers=1) if use_graph else None
+        ls = [meta_iteration(tr, style, batches, 0.5, 1, graphed=g).clone() for _ in range(3)]
+        losses.append(torch.stack(ls).cpu())
+        thetas.append([p.detach().clone() for p in list(m.style_transformer.parameters()) + list(m.decoder.parameters())])
+        if use_graph:
+            with pytest.raises(ValueError):
+                meta_iteration(InnerLoopTrainer(m, loss_fn), style, batches, 0.5, 1, graphed=g)
+    assert torch.allclose(losses[0], losses[1], rtol=2e-3), losses
+    moved = max(((a - b).norm() / (b.norm() + 1e-12)).item() for a, b in zip(thetas[0], model.style_transformer.parameters()))
+    assert moved > 1e-4, moved  # theta really moved
+    worst = max(((a - b).norm() / (a.norm() + 1e-12)).item() for a, b in zip(*thetas))
+    assert worst < 2e-3, worst
