@@ -165,12 +165,38 @@ def _mlp_fwd(x16, res32, fc1: _Lin, fc2: _Lin, T, dev, rs, rows, want16=True):
     return out32, out16, hpre, hact
 
 
+_branch_streams: Dict[torch.device, list] = {}
+
+
+def _parallel(main_fn, *side_fns):
+    """main_fn on the current stream, every side_fn on a branch stream of its own (forked before, joined after) -- but only
+    while the current stream is being captured into a CUDA graph, where the branches become parallel graph nodes: at batch 8
+    the data-gradient GEMM, the weight-gradient GEMM and the bias column sum of one Linear each fill less than half of the
+    148 SMs (64 row tiles), and all three only read dy.  Eager launches stay on one stream (the host is the limit there).
+    The same side_fn slot always maps to the same branch stream, so accumulations into a shared gradient stay ordered."""
+    if not side_fns or not torch.cuda.is_current_stream_capturing():
+        main_fn()
+        for f in side_fns:
+            f()
+        return
+    cur = torch.cuda.current_stream()
+    pool = _branch_streams.setdefault(cur.device, [])
+    while len(pool) < len(side_fns):
+        pool.append(torch.cuda.Stream(device=cur.device))
+    for st, f in zip(pool, side_fns):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            f()
+    main_fn()
+    for st in pool[:len(side_fns)]:
+        cur.wait_stream(st)
+
+
 def _lin_bwd(dy16, x16, M, lin: _Lin, gW, gb, *, ld_dy=None, ld_x=None, res=None, out_f32=None, out_bf16=None, want_dx=True):
     """Adjoint of y = x W^T + b for bf16 dy [M,N]: dx (= dy W, optional residual add / fp32 / bf16 outputs), dW += dy^T x, db += colsum."""
-    if want_dx:
-        ops.gemm(dy16, lin.bwd, M, lda=ld_dy, res=res, out_f32=out_f32, out_bf16=out_bf16)
-    ops.wgrad(dy16, x16, gW, M, lin.N, lin.K, ld_dy=ld_dy, ld_x=ld_x)
-    ops.colsum(dy16, M, lin.N, gb, ld=ld_dy)
+    _parallel((lambda: ops.gemm(dy16, lin.bwd, M, lda=ld_dy, res=res, out_f32=out_f32, out_bf16=out_bf16)) if want_dx else (lambda: None),
+              lambda: ops.wgrad(dy16, x16, gW, M, lin.N, lin.K, ld_dy=ld_dy, ld_x=ld_x),
+              lambda: ops.colsum(dy16, M, lin.N, gb, ld=ld_dy))
 
 
 def _lin_bwd_acc(g: _Geo, dy16p, x16p, lin: _Lin, gW, gb, gstream, ws_: "Workspace", *, ld_dy=None):
@@ -191,12 +217,12 @@ def _mlp_bwd(g16, x16, hpre, hact, fc1: _Lin, fc2: _Lin, T, book: GradBook, pre:
     The data gradient w.r.t. x goes to out_f32 (= res + dx when res is given) and/or out_bf16."""
     hid = fc1.N
     dh = ws_.bf16("bw_dh", T, hid)
-    ops.gemm(g16, fc2.bwd, T, out_bf16=dh, gate=hpre, gate_mode=GATE_GELU)  # (g W2) * gelu'(hpre)
-    ops.wgrad(g16, hact, book[pre + "3.weight"], T, fc2.N, fc2.K)
-    ops.colsum(g16, T, fc2.N, book[pre + "3.bias"])
-    ops.gemm(dh, fc1.bwd, T, res=res, out_f32=out_f32, out_bf16=out_bf16)
-    ops.wgrad(dh, x16, book[pre + "0.weight"], T, fc1.N, fc1.K)
-    ops.colsum(dh, T, fc1.N, book[pre + "0.bias"])
+    _parallel(lambda: ops.gemm(g16, fc2.bwd, T, out_bf16=dh, gate=hpre, gate_mode=GATE_GELU),  # (g W2) * gelu'(hpre)
+              lambda: ops.wgrad(g16, hact, book[pre + "3.weight"], T, fc2.N, fc2.K),
+              lambda: ops.colsum(g16, T, fc2.N, book[pre + "3.bias"]))
+    _parallel(lambda: ops.gemm(dh, fc1.bwd, T, res=res, out_f32=out_f32, out_bf16=out_bf16),
+              lambda: ops.wgrad(dh, x16, book[pre + "0.weight"], T, fc1.N, fc1.K),
+              lambda: ops.colsum(dh, T, fc1.N, book[pre + "0.bias"]))
 
 
 def _scaled16(g32, rs, rows, ws_: Workspace, name="bw_g16"):
