@@ -292,6 +292,25 @@ def main():
     e1.record()
     barrier()
     ms_single = e0.elapsed_time(e1) / args.steps
+    # the same through the uint8 image boundary of test_model.py (uint8 HWC in -> ToTensor + Normalize -> model -> clip*255 ->
+    # uint8 HWC out): two more kernels per step, a quarter of the host<->device bytes
+    gu = torch.Generator().manual_seed(100 + rank)
+    host8 = [(torch.randint(0, 256, (batch, args.size, args.size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
+              torch.randint(0, 256, (batch, args.size, args.size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
+              torch.empty(batch, args.size, args.size, 3, dtype=torch.uint8).pin_memory()) for _ in range(nbuf)]
+    batches8 = [host8[i % nbuf] for i in range(args.steps)]
+    runner.stylize_many(batches8[:args.warmup], u8=True)
+    barrier()
+    e0.record()
+    runner.stylize_many(batches8, u8=True)
+    e1.record()
+    barrier()
+    ms_u8 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_u8, op=dist.ReduceOp.MAX)
+    e2e_u8 = {"value": world * batch / (ms_u8.item() / args.steps / 1e3), "unit": "images/s", "ms_per_step": ms_u8.item() / args.steps,
+              "h2d_bytes_per_step": 2 * host8[0][0].numel(), "d2h_bytes_per_step": host8[0][2].numel(),
+              "api": "GraphedStylizer.stylize_many(u8=True): uint8 [B,S,S,3] pinned images in / out, pre- and post-processing on the device"}
 
     launches_per_step = runner.launches_per_step
     # ---------------- per-kernel-family timing (eager pass with CUDA events around every launch) ----------------
@@ -353,6 +372,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e.item() / args.steps,
                     "api": "GraphedStylizer.stylize_many (pipelined); single blocking stylize_host call: %.3f ms" % ms_single},
+            "e2e_u8": e2e_u8,
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu, "training": training}))
     if world > 1:

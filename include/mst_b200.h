@@ -200,6 +200,15 @@ int mst_patch_embed_ln(const float* img, const float* w, const float* b, const f
                        const float* gamma1, const float* beta1, mst_bf16* y16, int B, int S, int exact, void* stream);
 
 
+/* uint8 image boundary either side of the path (mean3 / std3 are HOST pointers to three floats, or both NULL).
+ * mst_images_u8_to_nchw: uint8 [B,H,W,3] (a decoded, resized image batch) -> fp32 [B,3,H,W] = ((u8 / 255) - mean_c) / std_c in the
+ *   fp32 operation order of transforms.ToTensor() + transforms.Normalize (test_model.py:39-48, :111-125; get_dataloader.py:37-38)
+ *   -- bit-exact; NULL mean3/std3 stops after the /255 (use_imagenet_normalization_for_swin = False).
+ * mst_images_nchw_to_u8: fp32 [B,3,H,W] -> uint8 [B,H,W,3] = (uint8) clip(x * 255, 0, 255), test_model.py:207's
+ *   `np.clip(img * 255, 0, 255).astype(np.uint8)` (truncation) -- bit-exact.  W % 4 == 0. */
+int mst_images_u8_to_nchw(const uint8_t* src, float* dst, int B, int H, int W, const float* mean3, const float* std3, void* stream);
+int mst_images_nchw_to_u8(const float* src, uint8_t* dst, int B, int H, int W, void* stream);
+
 /* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
 /* nn.Upsample(scale_factor=2, mode='nearest') on a bf16 NHWC tensor: x [B,H,W,C] -> y [B,2H,2W,C] (decoder.py:27), C % 8 == 0. */
 int mst_upsample2x_nhwc(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream);

@@ -111,6 +111,8 @@ SYMBOLS = {
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
+    "mst_images_u8_to_nchw": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "mst_images_nchw_to_u8": (_I, [_P, _P, _I, _I, _I, _P]),
     "mst_upsample2x_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mst_opt_chunk_elems": (_I, []),
     "mst_adam_step": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),

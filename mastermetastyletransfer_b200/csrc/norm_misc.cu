@@ -385,6 +385,54 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, bf16* __restrict__
   reinterpret_cast<uint2*>(y)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
 }
 
+// ---------------------------------------------------------------- uint8 image boundary (test_model.py:39-48,111-125,207)
+// images_u8_to_nchw: uint8 [B,H,W,3] -> fp32 [B,3,H,W] = ((u8 / 255) - mean_c) / std_c, the exact fp32 operation order of
+// torchvision's ToTensor (`.div(255)`) followed by Normalize (`.sub_(mean).div_(std)`); normalize == 0 stops after /255.
+// images_nchw_to_u8: fp32 [B,3,H,W] -> uint8 [B,H,W,3] = trunc(clip(x * 255, 0, 255)) (`np.clip(x*255, 0, 255).astype(np.uint8)`).
+// Four pixels per thread: 12 bytes of interleaved uint8 <-> one float4 per colour plane.  W % 4 == 0.
+__global__ void __launch_bounds__(256) images_u8_to_nchw_kernel(const uint32_t* __restrict__ src, float* __restrict__ dst, long long quads,
+                                                                long long plane, float m0, float m1, float m2, float s0, float s1,
+                                                                float s2, int normalize) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= quads) return;
+  const uint32_t w0 = src[3 * i], w1 = src[3 * i + 1], w2 = src[3 * i + 2];
+  const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
+                           (w1 >> 16) & 255u, w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  const long long pix = 4 * i;              // first pixel of the quad, over [B, H*W]
+  const long long b = pix / plane, r = pix - b * plane;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x = __fdiv_rn((float)by[3 * k + c], 255.0f);
+      if (normalize) x = __fdiv_rn(__fsub_rn(x, mean[c]), sd[c]);
+      v[k] = x;
+    }
+    *reinterpret_cast<float4*>(dst + (b * 3 + c) * plane + r) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) images_nchw_to_u8_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, long long quads,
+                                                                long long plane) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= quads) return;
+  const long long pix = 4 * i;
+  const long long b = pix / plane, r = pix - b * plane;
+  uint32_t by[12];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(src + (b * 3 + c) * plane + r);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) by[3 * k + c] = (uint32_t)fminf(fmaxf(__fmul_rn(x[k], 255.0f), 0.0f), 255.0f);  // NaN -> 0
+  }
+  dst[3 * i] = by[0] | (by[1] << 8) | (by[2] << 16) | (by[3] << 24);
+  dst[3 * i + 1] = by[4] | (by[5] << 8) | (by[6] << 16) | (by[7] << 24);
+  dst[3 * i + 2] = by[8] | (by[9] << 8) | (by[10] << 16) | (by[11] << 24);
+}
+
 }  // namespace mst
 
 using namespace mst;
@@ -479,6 +527,26 @@ extern "C" int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream
   if (!x || !y || n == 0 || n % 4 != 0) return MST_ERR_BAD_ARG;
   const size_t n4 = n / 4;
   cast_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<bf16*>(y), n4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_images_u8_to_nchw(const uint8_t* src, float* dst, int B, int H, int W, const float* mean3, const float* std3,
+                                     void* stream) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || W % 4 != 0 || (mean3 == nullptr) != (std3 == nullptr)) return MST_ERR_BAD_ARG;
+  if (((reinterpret_cast<uintptr_t>(src) & 3) | (reinterpret_cast<uintptr_t>(dst) & 15)) != 0) return MST_ERR_BAD_ARG;
+  const long long plane = (long long)H * W, quads = (long long)B * plane / 4;
+  const float m[3] = {mean3 ? mean3[0] : 0.f, mean3 ? mean3[1] : 0.f, mean3 ? mean3[2] : 0.f};
+  const float sd[3] = {std3 ? std3[0] : 1.f, std3 ? std3[1] : 1.f, std3 ? std3[2] : 1.f};
+  images_u8_to_nchw_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(src), dst, quads, plane, m[0], m[1], m[2], sd[0], sd[1], sd[2], mean3 != nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_images_nchw_to_u8(const float* src, uint8_t* dst, int B, int H, int W, void* stream) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || W % 4 != 0) return MST_ERR_BAD_ARG;
+  if (((reinterpret_cast<uintptr_t>(dst) & 3) | (reinterpret_cast<uintptr_t>(src) & 15)) != 0) return MST_ERR_BAD_ARG;
+  const long long plane = (long long)H * W, quads = (long long)B * plane / 4;
+  images_nchw_to_u8_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<uint32_t*>(dst), quads, plane);
   return (int)cudaGetLastError();
 }
 

@@ -56,7 +56,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
-             "mst_cast_bf16": "cast_bf16_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
+             "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
              "mst_loss_finalize": "loss_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
@@ -290,6 +290,29 @@ def upsample2x_nhwc(x, y, B, H, W, C_) -> None:
 def cast_bf16(x, y) -> None:
     _launch("mst_cast_bf16", lambda: _lib.lib().mst_cast_bf16(_ptr(x, torch.float32, "x"), _ptr(y, torch.bfloat16, "y"), x.numel(), _stream()),
             nbytes=6.0 * x.numel())
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def images_u8_to_nchw(src_u8, dst32, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+    """uint8 [B,H,W,3] -> fp32 [B,3,H,W]: transforms.ToTensor() + transforms.Normalize(mean, std) (test_model.py:39-48); mean=None: /255 only."""
+    B, H, W, ch = src_u8.shape
+    if ch != 3 or tuple(dst32.shape) != (B, 3, H, W):
+        raise ValueError("images_u8_to_nchw: src [B,H,W,3] uint8, dst [B,3,H,W] fp32")
+    m = C.cast((C.c_float * 3)(*mean), C.c_void_p) if mean is not None else None
+    sd = C.cast((C.c_float * 3)(*std), C.c_void_p) if mean is not None else None
+    _launch("mst_images_u8_to_nchw", lambda: _lib.lib().mst_images_u8_to_nchw(_ptr(src_u8, torch.uint8, "src"), _ptr(dst32, torch.float32, "dst"),
+                                                                              B, H, W, m, sd, _stream()), nbytes=15.0 * B * H * W)
+
+
+def images_nchw_to_u8(src32, dst_u8) -> None:
+    """fp32 [B,3,H,W] -> uint8 [B,H,W,3]: np.clip(x * 255, 0, 255).astype(np.uint8) (test_model.py:207)."""
+    B, ch, H, W = src32.shape
+    if ch != 3 or tuple(dst_u8.shape) != (B, H, W, 3):
+        raise ValueError("images_nchw_to_u8: src [B,3,H,W] fp32, dst [B,H,W,3] uint8")
+    _launch("mst_images_nchw_to_u8", lambda: _lib.lib().mst_images_nchw_to_u8(_ptr(src32, torch.float32, "src"), _ptr(dst_u8, torch.uint8, "dst"),
+                                                                              B, H, W, _stream()), nbytes=15.0 * B * H * W)
 
 
 def conv3x3_first(img, w, b, out, B, H, W, relu=True) -> None:

@@ -32,6 +32,35 @@ class GraphedStylizer:
                 self.output = self.model(self.content, self.style, layers)
         torch.cuda.synchronize(self.device)
 
+    def _u8(self, normalize: bool = True):
+        """The uint8 boundary of test_model.py around the same model, as a second graph: uint8 [B,S,S,3] images (decoded and
+        resized, :39-44) -> ToTensor + ImageNet Normalize (:48,:111-125) -> model -> clip(x*255) -> uint8 [B,S,S,3] (:207).
+        A quarter of the host<->device bytes of the fp32 entry points."""
+        if getattr(self, "_u8_norm", None) != normalize:
+            B, S, dev = self.batch, self.size, self.device
+            self.content_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
+            self.style_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
+            self.output_u8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=dev)
+            mean = ops.IMAGENET_MEAN if normalize else None
+
+            def run():
+                ops.images_u8_to_nchw(self.content_u8, self.content, mean)
+                ops.images_u8_to_nchw(self.style_u8, self.style, mean)
+                ops.images_nchw_to_u8(self.model(self.content, self.style, self.layers), self.output_u8)
+
+            with torch.no_grad():
+                self.stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(self.stream):
+                    run()
+                self.stream.synchronize()
+                self.graph_u8 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_u8, stream=self.stream):
+                    run()
+            torch.cuda.synchronize(dev)
+            self._u8_norm = normalize
+            self.__dict__.pop("_stage_u8", None)
+        return (self.content_u8, self.style_u8), self.output_u8, self.graph_u8
+
     def load(self, content: torch.Tensor, style: torch.Tensor) -> None:
         self.content.copy_(content, non_blocking=True)
         self.style.copy_(style, non_blocking=True)
@@ -41,16 +70,24 @@ class GraphedStylizer:
         self.graph.replay()
         return self.output
 
-    def stylize_many(self, batches):
+    def stylize_many(self, batches, u8: bool = False, normalize: bool = True):
         """Pipelined host API: `batches` is a sequence of (content_pinned, style_pinned, out_pinned).  Host->device
         copies of batch i+1 and the device->host copy of batch i-1 run on two copy streams while the graph of
         batch i executes (double-buffered device staging, one small device-to-device copy each way).
-        Returns after every output has landed in its pinned buffer."""
+        Returns after every output has landed in its pinned buffer.
+        u8=True: the buffers are uint8 [B,S,S,3] images (see _u8); otherwise normalised fp32 [B,3,S,S] tensors."""
         dev = self.device
         if not hasattr(self, "_h2d"):
             self._h2d, self._d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-            self._stage_in = [(torch.empty_like(self.content), torch.empty_like(self.style)) for _ in range(2)]
-            self._stage_out = [torch.empty_like(self.output) for _ in range(2)]
+        if u8:
+            (d_content, d_style), d_output, graph = self._u8(normalize)
+            key = "_stage_u8"
+        else:
+            d_content, d_style, d_output, graph, key = self.content, self.style, self.output, self.graph, "_stage_f32"
+        if not hasattr(self, key):
+            setattr(self, key, ([(torch.empty_like(d_content), torch.empty_like(d_style)) for _ in range(2)],
+                                [torch.empty_like(d_output) for _ in range(2)]))
+        stage_in, stage_out = getattr(self, key)
         main = torch.cuda.current_stream(dev)
         in_ready = [torch.cuda.Event() for _ in range(2)]     # staging slot filled by the H2D stream
         in_free = [torch.cuda.Event() for _ in range(2)]      # staging slot consumed by the compute stream
@@ -65,8 +102,8 @@ class GraphedStylizer:
             with torch.cuda.stream(self._h2d):
                 if i >= 2:
                     self._h2d.wait_event(in_free[slot])
-                self._stage_in[slot][0].copy_(batches[i][0], non_blocking=True)
-                self._stage_in[slot][1].copy_(batches[i][1], non_blocking=True)
+                stage_in[slot][0].copy_(batches[i][0], non_blocking=True)
+                stage_in[slot][1].copy_(batches[i][1], non_blocking=True)
                 in_ready[slot].record(self._h2d)
 
         if n:
@@ -76,17 +113,17 @@ class GraphedStylizer:
             if i + 1 < n:
                 issue_h2d(i + 1)
             main.wait_event(in_ready[slot])
-            self.content.copy_(self._stage_in[slot][0], non_blocking=True)
-            self.style.copy_(self._stage_in[slot][1], non_blocking=True)
+            d_content.copy_(stage_in[slot][0], non_blocking=True)
+            d_style.copy_(stage_in[slot][1], non_blocking=True)
             in_free[slot].record(main)
-            self.graph.replay()
+            graph.replay()
             if i >= 2:
                 main.wait_event(out_free[slot])
-            self._stage_out[slot].copy_(self.output, non_blocking=True)
+            stage_out[slot].copy_(d_output, non_blocking=True)
             out_ready[slot].record(main)
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(out_ready[slot])
-                batches[i][2].copy_(self._stage_out[slot], non_blocking=True)
+                batches[i][2].copy_(stage_out[slot], non_blocking=True)
                 out_free[slot].record(self._d2h)
         main.wait_stream(self._d2h)
         main.synchronize()
@@ -98,3 +135,14 @@ class GraphedStylizer:
         out_pinned.copy_(self.output, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return out_pinned
+
+    def stylize_host_u8(self, content_u8_pinned: torch.Tensor, style_u8_pinned: torch.Tensor, out_u8_pinned: torch.Tensor,
+                        normalize: bool = True) -> torch.Tensor:
+        """uint8 [B,S,S,3] pinned host images in, stylised uint8 [B,S,S,3] pinned host images out (one blocking call)."""
+        (d_content, d_style), d_output, graph = self._u8(normalize)
+        d_content.copy_(content_u8_pinned, non_blocking=True)
+        d_style.copy_(style_u8_pinned, non_blocking=True)
+        graph.replay()
+        out_u8_pinned.copy_(d_output, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_u8_pinned

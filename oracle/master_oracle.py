@@ -400,3 +400,29 @@ def overall_loss(vgg_sd: SD, content: Tensor, style: Tensor, output: Tensor, lam
     lc = content_loss(tc, to, squared_content)
     ls = style_loss(ts, to, squared_style)
     return lc + lam * ls, lc, ls
+
+
+# ----------------------------------------------------------------------------------------------
+# uint8 image boundary either side of the path
+# ----------------------------------------------------------------------------------------------
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def images_u8_to_tensor(img_u8: Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> Tensor:
+    """test_model.py:39-48 / get_dataloader.py:37-38 after the resize: transforms.ToTensor() (tv functional.to_tensor:
+    HWC uint8 -> CHW, `.to(float32).div(255)`) then transforms.Normalize (tv functional.normalize: `sub_(mean).div_(std)` with
+    fp32 mean / std tensors).  img_u8 [B,H,W,3] uint8 -> fp32 [B,3,H,W]; mean=None stops after the /255 (:111-125's flag off)."""
+    x = img_u8.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+    if mean is None:
+        return x
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    sd = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return x.sub(m).div(sd)
+
+
+def tensor_to_images_u8(x: Tensor) -> Tensor:
+    """test_model.py:207: np.clip(img.permute(1, 2, 0).numpy() * 255, 0, 255).astype(np.uint8), batched: [B,3,H,W] -> [B,H,W,3]."""
+    import numpy as np
+    a = x.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous().numpy()
+    return torch.from_numpy(np.clip(a * 255, 0, 255).astype(np.uint8))

@@ -272,6 +272,30 @@ def test_token_map_pad_crop(dtype):
             ops.token_map_copy(y, yc, B, Hp, Wp, H, W, accumulate=True)
 
 
+@pytest.mark.parametrize("normalize", [True, False])
+def test_u8_image_boundary_bit_exact(normalize):
+    """mst_images_u8_to_nchw / mst_images_nchw_to_u8 against the oracle's restatement of ToTensor + Normalize and of
+    np.clip(x*255, 0, 255).astype(uint8) (test_model.py:39-48, :207): bit-exact, every uint8 value, out-of-range floats."""
+    from mastermetastyletransfer_b200 import ops
+    from oracle import master_oracle as O
+    g = torch.Generator().manual_seed(1)
+    B, H, W = 3, 20, 256
+    img = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    img[0, 0, :, :] = torch.arange(256, dtype=torch.uint8).view(256, 1)
+    out = torch.empty(B, 3, H, W, device="cuda")
+    ops.images_u8_to_nchw(img.cuda(), out, ops.IMAGENET_MEAN if normalize else None)
+    assert torch.equal(out.cpu(), O.images_u8_to_tensor(img, mean=O.IMAGENET_MEAN if normalize else None))
+    x = torch.randn(B, 3, H, W, generator=g) * 0.6 + 0.5
+    x[0, 0, 0, :256] = torch.arange(256, dtype=torch.float32) / 255
+    x[0, 1, 0, :256] = (torch.arange(256, dtype=torch.float32) + 0.999) / 255
+    x[0, 2, 0, :4] = torch.tensor([-1e9, 1e9, -0.0, 2.0])
+    back = torch.empty(B, H, W, 3, dtype=torch.uint8, device="cuda")
+    ops.images_nchw_to_u8(x.cuda(), back)
+    assert torch.equal(back.cpu(), O.tensor_to_images_u8(x))
+    with pytest.raises(ValueError):
+        ops.images_nchw_to_u8(x.cuda(), torch.empty(B, H, W, 4, dtype=torch.uint8, device="cuda"))
+
+
 def test_bad_arguments_raise():
     ops = _ops()
     A = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)

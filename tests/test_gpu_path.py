@@ -235,3 +235,31 @@ def test_pipelined_host_api_matches_direct_call(model):
     runner.stylize_many(batches)
     for (_, _, out), ref in zip(batches, expect):
         assert torch.equal(out, ref)
+
+
+def test_u8_host_entry_points_match_fp32_path(model, sd):
+    """GraphedStylizer.stylize_host_u8 / stylize_many(u8=True): uint8 HWC images in, uint8 HWC stylised images out -- equal to
+    the fp32 entry point fed ToTensor + Normalize'd inputs and cast like test_model.py:207, and within the image tolerance
+    (in grey levels) of the CPU oracle's stylisation of the same uint8 images."""
+    from mastermetastyletransfer_b200.runtime import GraphedStylizer
+    from oracle import master_oracle as O
+    g = torch.Generator().manual_seed(21)
+    B, S = 2, 128
+    content = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    style = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    runner = GraphedStylizer(model, B, S, 1)
+    c_pin, s_pin = content.pin_memory(), style.pin_memory()
+    o_pin = torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory()
+    runner.stylize_host_u8(c_pin, s_pin, o_pin)
+    cn, sn = O.images_u8_to_tensor(content), O.images_u8_to_tensor(style)
+    f_pin = torch.empty(B, 3, S, S).pin_memory()
+    runner.stylize_host(cn.pin_memory(), sn.pin_memory(), f_pin)
+    assert torch.equal(o_pin, O.tensor_to_images_u8(f_pin))
+    many = [(c_pin, s_pin, torch.empty_like(o_pin).pin_memory()) for _ in range(3)]
+    runner.stylize_many(many, u8=True)
+    assert all(torch.equal(m[2], o_pin) for m in many)
+    with torch.no_grad():
+        ref = O.full_forward(sd, cn, sn, 1)
+    rng = (ref.max() - ref.min()).item()
+    diff = (o_pin.permute(0, 3, 1, 2).float() - (ref * 255).clamp(0, 255)).abs().max().item()
+    assert diff <= IMG_TOL * rng * 255 + 1.0, (diff, rng)

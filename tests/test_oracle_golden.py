@@ -117,3 +117,23 @@ def test_instance_norm_twice_is_not_idempotent():
     x = torch.randn(1, 8, 8, 4, generator=torch.Generator().manual_seed(0)) * 0.01
     once = O.instance_norm_bhwc(x)
     assert (O.instance_norm_bhwc(once) - once).abs().max() > 1e-4
+
+
+def test_u8_boundary_oracle_matches_torchvision_transforms():
+    """The uint8 boundary restatement against the reference's own dependency: transforms.ToTensor() + transforms.Normalize
+    (test_model.py:39-48) and the numpy clip / uint8 cast of test_model.py:207 -- bit for bit."""
+    tvt = pytest.importorskip("torchvision.transforms")
+    from oracle import master_oracle as O
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (2, 24, 20, 3), generator=g, dtype=torch.uint8)
+    img[0, 0, :, 0] = torch.arange(20, dtype=torch.uint8) * 13  # include 0 and 247
+    img[1, 1, :16, 1] = torch.arange(240, 256, dtype=torch.uint8)
+    tf = tvt.Compose([tvt.ToPILImage(), tvt.ToTensor()])
+    norm = tvt.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    plain = torch.stack([tf(i.numpy()) for i in img])
+    assert torch.equal(O.images_u8_to_tensor(img, mean=None), plain)
+    assert torch.equal(O.images_u8_to_tensor(img), torch.stack([norm(p) for p in plain]))
+    x = torch.randn(2, 3, 8, 12, generator=g) * 0.7 + 0.5
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 254.999 / 255, 1.0 / 255])
+    want = np.stack([np.clip(xi.permute(1, 2, 0).numpy() * 255, 0, 255).astype(np.uint8) for xi in x])
+    assert np.array_equal(O.tensor_to_images_u8(x).numpy(), want)
