@@ -195,6 +195,12 @@ def main():
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the secondary training-step measurement (0 = skip)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that nothing a native
+    # library prints (NCCL's version banner goes to stdout whatever NCCL_DEBUG_FILE says on some boxes) can end up in front of it
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    emit = lambda line: (json_out.write(line + "\n"), json_out.flush())
     args.warmup = max(args.warmup, 3)
     batch = args.batch or (32 if args.size == 256 else 16)
     rank = int(os.environ.get("RANK", "0"))
@@ -215,7 +221,7 @@ def main():
         ms = 1e3 * sum(times) / len(times)
         value = cpu_batch / (ms / 1e3)
         sample = f"{steps} steps of batch {cpu_batch} at {args.size}x{args.size} (CPU oracle port of the reference, fp32, {threads} threads)"
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
@@ -365,7 +371,7 @@ def main():
         act_mb = batch * (args.size // 8) ** 2 * 256 * 4 / 1e6
         config["l2"] = f"no explicit flush: a step streams >1 GB of activations (feature map alone {act_mb:.0f} MB fp32 x dozens of tensors) through a 126 MB L2"
         config["timed"] = "one CUDA-graph replay per step"
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
