@@ -133,9 +133,13 @@ class _PerceptualLossFn(torch.autograd.Function):
         w = packed_weights(fe, te.VggTrainWeights)
         wi = packed_weights(fe, engine.VggWeights)
         ws = workspace_of(module, output.device)
+        pre = module.__dict__.pop("_prefetched_taps", None)  # content/style taps computed ahead (prefetch_content_style_taps)
+        if pre is not None and pre[0] != (content.data_ptr(), style.data_ptr(), tuple(content.shape)):
+            pre = None
         out3, saved = te.perceptual_loss_forward_train(
             w, wi, content.detach().float().contiguous(), style.detach().float().contiguous(), output.detach().float().contiguous(),
-            lam, module.distance_content == "euclidian_squared", module.distance_style == "euclidian_squared", ws)
+            lam, module.distance_content == "euclidian_squared", module.distance_style == "euclidian_squared", ws,
+            pre=None if pre is None else pre[1])
         ctx.module, ctx.w, ctx.saved, ctx.lam = module, w, saved, lam
         return out3
 
@@ -147,6 +151,19 @@ class _PerceptualLossFn(torch.autograd.Function):
         dimg = te.perceptual_loss_backward(ctx.w, ctx.saved, coef2, workspace_of(ctx.module, g3.device))
         ctx.saved = None
         return None, None, None, dimg, None
+
+
+def prefetch_content_style_taps(module, content, style) -> None:
+    """Compute the content / style VGG taps + statistics of the NEXT loss call on the current stream (they do not depend on
+    the stylised image) and park them on the loss module; _PerceptualLossFn.forward picks them up if it gets the same tensors."""
+    if not (content.is_cuda and style.is_cuda) or content.dtype != torch.float32 or style.dtype != torch.float32:
+        return
+    if not (content.is_contiguous() and style.is_contiguous()) or content.shape != style.shape:
+        return
+    fe = module.feature_extractor_model
+    with torch.no_grad():
+        data = te.content_style_taps(packed_weights(fe, engine.VggWeights), content, style, workspace_of(module, content.device))
+    module.__dict__["_prefetched_taps"] = ((content.data_ptr(), style.data_ptr(), tuple(content.shape)), data)
 
 
 def perceptual_loss_apply(module, content, style, output, lam: float):

@@ -78,8 +78,6 @@ class custom_loss(nn.Module):
         assert content_image.shape == style_image.shape == output_image.shape, "All images should be in the exact same shape"
         assert content_image.requires_grad == False, "Content image should not require gradient"  # noqa: E712
         assert style_image.requires_grad == False, "Style image should not require gradient"  # noqa: E712
-        if output_similarity_loss:
-            raise NotImplementedError("similarity loss is out of scope (off by default and always 0 in the reference, SURVEY.md 0.2-4)")
         if not output_image.is_cuda:
             raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
         if loss_weight is None:
@@ -87,16 +85,23 @@ class custom_loss(nn.Module):
         if torch.is_grad_enabled() and output_image.requires_grad:
             from .autograd_fns import perceptual_loss_apply
             out3 = perceptual_loss_apply(self, content_image, style_image, output_image, float(loss_weight))
-            if output_content_and_style_loss:
-                return out3[0], out3[1], out3[2]
-            return out3[0]
+            return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss)
         with torch.no_grad():
             w = packed_weights(self.feature_extractor_model, engine.VggWeights)
             ws = workspace_of(self, output_image.device)
             out3 = engine.perceptual_loss_forward(w, content_image.float(), style_image.float(), output_image.float(), float(loss_weight),
                                                   self.distance_content == "euclidian_squared",
                                                   self.distance_style == "euclidian_squared", ws)
-        total, content, style = out3[0], out3[1], out3[2]
-        if output_content_and_style_loss:
-            return total, content, style
-        return total
+        return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss)
+
+    @staticmethod
+    def _pack(total, content, style, want_parts: bool, want_similarity: bool):
+        """Return tuple of get_overall_loss (loss.py:245-262).  The reference's get_similarity_loss compares the CONTENT image's
+        relu3_1 / relu4_1 self-similarity maps with THEMSELVES (loss.py:333-334 passes VGG_features_content_layers twice), so the
+        value it returns is mean(|tril(D) - tril(D)|) + ... = exactly 0 whatever the inputs; the drop-in returns that 0 (an fp32
+        scalar on the device, no graph) without building the two B x N x N cosine maps.  The paper's content-vs-output form is
+        SURVEY.md 8f-3 (not built)."""
+        if want_similarity:
+            similarity = torch.zeros((), dtype=torch.float32, device=total.device)
+            return (total, content, style, similarity) if want_parts else (total, similarity)
+        return (total, content, style) if want_parts else total

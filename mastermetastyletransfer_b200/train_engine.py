@@ -548,26 +548,41 @@ def vgg_forward_saving(w: VggTrainWeights, imgs: torch.Tensor):
     return acts, pooled, taps
 
 
-def perceptual_loss_forward_train(w: VggTrainWeights, infer_w, content, style, output, lam: float, squared_content: bool,
-                                  squared_style: bool, ws_: Workspace):
-    """Loss forward that keeps the stylised image's VGG activations.  content/style taps come from the inference path
-    (ping-pong buffers, nothing saved).  Returns (out3 device tensor, ctx dict for perceptual_loss_backward)."""
+def content_style_taps(infer_w, content, style, ws_: Workspace):
+    """VGG taps and per-channel statistics of the content and style images (nothing saved for a backward: they carry no
+    gradient).  Independent of the stylised image, so a captured training step runs it as a parallel graph branch next to the
+    encoder / style transformer / decoder forward (training.InnerLoopTrainer.step)."""
     from .engine import vgg_taps_forward
     B = int(content.shape[0])
-    dev = output.device
+    dev = content.device
     cs = ws_.f32("lt_imgs", 2 * B, 3, content.shape[2], content.shape[3])
     cs[:B].copy_(content)
     cs[B:].copy_(style)
     taps_cs = vgg_taps_forward(infer_w, cs, ws_, "lt_cs_")
+    stats = []
+    for tcs, h, wd, c in taps_cs:
+        mean_cs, var_cs = _e32(dev, 2 * B, c), _e32(dev, 2 * B, c)
+        ops.tap_stats(tcs, mean_cs, var_cs, 2 * B, h * wd, c)
+        stats.append((mean_cs, var_cs))
+    return taps_cs, stats
+
+
+def perceptual_loss_forward_train(w: VggTrainWeights, infer_w, content, style, output, lam: float, squared_content: bool,
+                                  squared_style: bool, ws_: Workspace, pre=None):
+    """Loss forward that keeps the stylised image's VGG activations.  content/style taps come from the inference path
+    (ping-pong buffers, nothing saved); pre = an earlier content_style_taps(...) result for the same images.
+    Returns (out3 device tensor, ctx dict for perceptual_loss_backward)."""
+    B = int(content.shape[0])
+    dev = output.device
+    taps_cs, stats_cs = pre if pre is not None else content_style_taps(infer_w, content, style, ws_)
     acts, pooled, taps_o = vgg_forward_saving(w, output)
     descs, per_tap = [], []
     for i in range(4):
         tcs, h, wd, c = taps_cs[i]
         to = taps_o[i][0]
         T = h * wd
-        mean_cs, var_cs = _e32(dev, 2 * B, c), _e32(dev, 2 * B, c)
+        mean_cs, var_cs = stats_cs[i]
         mean_o, var_o = _e32(dev, B, c), _e32(dev, B, c)
-        ops.tap_stats(tcs, mean_cs, var_cs, 2 * B, T, c)
         ops.tap_stats(to, mean_o, var_o, B, T, c)
         partials = ws_.f32(f"lt_part{i}", 592)
         fc = tcs.view(2 * B, T * c)[:B]

@@ -81,9 +81,15 @@ class InnerLoopTrainer:
         if num_layers is None:
             num_layers = self._rng.randint(1, self.max_layers)
         with torch.no_grad():
+            branch = self._fork_weight_packing()
+            loss_branch = self._fork_content_style_taps(content, style)
             fc = self.model.swin_encoder(content)
             fs = self.model.swin_encoder(style)
+            if branch is not None:
+                torch.cuda.current_stream(content.device).wait_stream(branch)
         out = self.omega_dec(self.omega_st(fc, fs, num_layers).permute(0, 3, 1, 2))
+        if loss_branch is not None:
+            torch.cuda.current_stream(content.device).wait_stream(loss_branch)
         total, closs, sloss = self.loss_fn(content, style, out, output_content_and_style_loss=True)
         self.opt.zero_grad(set_to_none=True)
         total.backward()
@@ -91,6 +97,39 @@ class InnerLoopTrainer:
             self._flat = allreduce_gradients(self.params, self.group, self._flat)
         self.opt.step()
         return torch.stack([total.detach(), closs.detach(), sloss.detach()])
+
+    def _fork_weight_packing(self):
+        """While a step is being captured into a CUDA graph: re-pack omega's updated weights (58 small launches: bf16 tile images
+        of every Linear / conv, forward and transposed) on a branch stream, i.e. as graph nodes parallel to the frozen encoder's
+        forward, which does not depend on them.  The modules' own forward then finds the packed weights in the cache.
+        Eager steps keep everything on one stream (returns None)."""
+        if not (self.params and self.params[0].is_cuda and torch.cuda.is_current_stream_capturing()):
+            return None
+        from . import train_engine as te
+        from .style_transformer import packed_weights
+        dev = self.params[0].device
+        if getattr(self, "_pack_stream", None) is None:
+            self._pack_stream = torch.cuda.Stream(device=dev)
+        self._pack_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._pack_stream):
+            packed_weights(self.omega_st, te.StyleTransformerTrainWeights)
+            packed_weights(self.omega_dec, te.CnnDecoderTrainWeights)
+        return self._pack_stream
+
+    def _fork_content_style_taps(self, content, style):
+        """While a step is being captured: the VGG passes of the content and style images (no gradient, independent of the
+        model) as a graph branch parallel to the encoder / style transformer / decoder forward, whose batch-8 kernels leave
+        most SMs idle.  Returns the branch stream (joined before the loss) or None (eager: one stream)."""
+        if not (content.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return None
+        from .autograd_fns import prefetch_content_style_taps
+        dev = content.device
+        if getattr(self, "_loss_stream", None) is None:
+            self._loss_stream = torch.cuda.Stream(device=dev)
+        self._loss_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._loss_stream):
+            prefetch_content_style_taps(self.loss_fn, content, style)
+        return self._loss_stream
 
     def outer_update(self, outer_lr: float) -> None:
         """theta += outer_lr * mean_over_ranks(omega - theta) for the style transformer and the decoder (train.py:524-534)."""

@@ -263,3 +263,27 @@ def test_u8_host_entry_points_match_fp32_path(model, sd):
     rng = (ref.max() - ref.min()).item()
     diff = (o_pin.permute(0, 3, 1, 2).float() - (ref * 255).clamp(0, 255)).abs().max().item()
     assert diff <= IMG_TOL * rng * 255 + 1.0, (diff, rng)
+
+
+def test_similarity_loss_flag_matches_reference_fixture(loss_module, golden_dir):
+    """output_similarity_loss=True: same tuple layouts as loss.py:245-254 and the values the REAL reference returned on the same
+    seeded inputs (tests/golden/similarity_loss.json, oracle/make_similarity_fixture.py) -- its similarity term compares the
+    content features with themselves (loss.py:333-334) and is identically 0."""
+    import json
+    from mastermetastyletransfer_b200 import synthetic
+    gold = json.load(open(os.path.join(golden_dir, "similarity_loss.json")))
+    content, style = synthetic.synthetic_images(2, 64, seed=5)
+    out, _ = synthetic.synthetic_images(2, 64, seed=6)
+    with torch.no_grad():
+        four = loss_module(content.cuda(), style.cuda(), out.cuda(), output_content_and_style_loss=True, output_similarity_loss=True)
+        two = loss_module(content.cuda(), style.cuda(), out.cuda(), output_similarity_loss=True)
+    assert len(four) == 4 and len(two) == 2
+    np.testing.assert_allclose([t.item() for t in four[:3]], gold["total_content_style_similarity"][:3], rtol=LOSS_RTOL)
+    np.testing.assert_allclose(two[0].item(), gold["total_similarity"][0], rtol=LOSS_RTOL)
+    for sim in (four[3], two[1]):
+        assert sim.item() == gold["total_content_style_similarity"][3] == 0.0
+        assert str(sim.dtype) == gold["similarity_dtype"] and list(sim.shape) == gold["similarity_shape"] and sim.is_cuda
+    g = out.cuda().requires_grad_(True)  # training mode (autograd path): same layout, the zero term carries no gradient
+    tot, sim = loss_module(content.cuda(), style.cuda(), g, output_similarity_loss=True)
+    (tot + sim).backward()
+    assert sim.item() == 0.0 and g.grad is not None and torch.isfinite(g.grad).all()
