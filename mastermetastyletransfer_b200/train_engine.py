@@ -257,54 +257,70 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
         s = (lambda i: sd_scales[l, i].contiguous()) if sd_scales is not None else (lambda i: None)
         t = {}
         # ---------------- StyleEncoder ----------------
-        t["key16_in"], t["scale16_in"], t["shift16_in"] = key16p, scale16p, shift16p
-        qkv1, o1p = _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
-        ops.gemm(key16p, w.enc_qkv.fwd, Tp, out_bf16=qkv1)
-        _attn(g, qkv1, qkv1[:, C:], qkv1[:, 2 * C:], o1p, w.enc_table, 3 * C, 3 * C, 3 * C)
-        o1 = _crop16(g, o1p)
-        key32a, key16a = _e32(dev, T, C), _e16(dev, T, C)
-        ops.gemm(o1, w.enc_proj.fwd, T, res=key32, out_f32=key32a, out_bf16=key16a, row_scale=s(0), rows_per_scale=rows)
-        fc1, fc2, _ = w.mlp["key"]
-        key32, key16, hp, ha = _mlp_fwd(key16a, key32a, fc1, fc2, T, dev, s(1), rows)
-        key16p = _pad16(g, key16)
-        t.update(qkv1=qkv1, o1=o1, key16a=key16a, hK=(hp, ha), key16b=key16p, key32b=key32)
-        qk2, vs, vh = _e16(dev, Tp, 2 * C), _e16(dev, Tp, C), _e16(dev, Tp, C)
-        ops.gemm(key16p, w.enc_qk.fwd, Tp, out_bf16=qk2)
-        ops.gemm(scale16p, w.enc_v.fwd, Tp, out_bf16=vs)
-        ops.gemm(shift16p, w.enc_v.fwd, Tp, out_bf16=vh)
-        osp, ohp = _e16(dev, Tp, C), _e16(dev, Tp, C)
-        _attn(g, qk2, qk2[:, C:], vs, osp, w.enc_table, 2 * C, 2 * C, C, v2=vh, out2=ohp)
-        os_, oh = _crop16(g, osp), _crop16(g, ohp)
-        scale32a, scale16a = _e32(dev, T, C), _e16(dev, T, C)
-        ops.gemm(os_, w.enc_proj.fwd, T, res=scale32, out_f32=scale32a, out_bf16=scale16a, row_scale=s(2), rows_per_scale=rows)
-        fc1, fc2, _ = w.mlp["scale"]
-        scale32, scale16, hp, ha = _mlp_fwd(scale16a, scale32a, fc1, fc2, T, dev, s(3), rows)
-        scale16p = _pad16(g, scale16)
-        t.update(qk2=qk2, vs=vs, vh=vh, os=os_, oh=oh, scale16a=scale16a, hS=(hp, ha), scale16b=scale16p)
-        shift32a, shift16a = _e32(dev, T, C), _e16(dev, T, C)
-        ops.gemm(oh, w.enc_proj.fwd, T, res=shift32, out_f32=shift32a, out_bf16=shift16a, row_scale=s(4), rows_per_scale=rows)
-        fc1, fc2, _ = w.mlp["shift"]
-        shift32, shift16, hp, ha = _mlp_fwd(shift16a, shift32a, fc1, fc2, T, dev, s(5), rows)
-        shift16p = _pad16(g, shift16)
-        t.update(shift16a=shift16a, hH=(hp, ha), shift16b=shift16p)
-        # ---------------- StyleDecoder ----------------
-        ln1, qkv3, o3p = _e16(dev, T, C), _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
-        ops.layernorm(x32, w.n1[0], w.n1[1], ln1, T, C)
-        ln1 = _pad16(g, ln1)
-        ops.gemm(ln1, w.dec_qkv.fwd, Tp, out_bf16=qkv3)
-        _attn(g, qkv3, qkv3[:, C:], qkv3[:, 2 * C:], o3p, w.dec_table, 3 * C, 3 * C, 3 * C)
-        o3 = _crop16(g, o3p)
-        x32a = _e32(dev, T, C)
-        ops.gemm(o3, w.dec_proj.fwd, T, res=x32, out_f32=x32a, row_scale=s(6), rows_per_scale=rows)
-        ln2 = _e16(dev, T, C)
-        ops.layernorm(x32a, w.n2[0], w.n2[1], ln2, T, C)
-        fc1, fc2, _ = w.mlp["dec"]
-        query32, _, hp, ha = _mlp_fwd(ln2, x32a, fc1, fc2, T, dev, s(7), rows, want16=False)
-        t.update(x32_in=x32, ln1=ln1, qkv3=qkv3, o3=o3, x32a=x32a, ln2=ln2, hD=(hp, ha), query32=query32)
+        st_in = (key32, key16p, scale32, scale16p, shift32, shift16p)
+
+        def enc_chain():
+            key32, key16p, scale32, scale16p, shift32, shift16p = st_in
+            t["key16_in"], t["scale16_in"], t["shift16_in"] = key16p, scale16p, shift16p
+            qkv1, o1p = _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
+            ops.gemm(key16p, w.enc_qkv.fwd, Tp, out_bf16=qkv1)
+            _attn(g, qkv1, qkv1[:, C:], qkv1[:, 2 * C:], o1p, w.enc_table, 3 * C, 3 * C, 3 * C)
+            o1 = _crop16(g, o1p)
+            key32a, key16a = _e32(dev, T, C), _e16(dev, T, C)
+            ops.gemm(o1, w.enc_proj.fwd, T, res=key32, out_f32=key32a, out_bf16=key16a, row_scale=s(0), rows_per_scale=rows)
+            fc1, fc2, _ = w.mlp["key"]
+            key32, key16, hp, ha = _mlp_fwd(key16a, key32a, fc1, fc2, T, dev, s(1), rows)
+            key16p = _pad16(g, key16)
+            t.update(qkv1=qkv1, o1=o1, key16a=key16a, hK=(hp, ha), key16b=key16p, key32b=key32)
+            qk2, vs, vh = _e16(dev, Tp, 2 * C), _e16(dev, Tp, C), _e16(dev, Tp, C)
+            ops.gemm(key16p, w.enc_qk.fwd, Tp, out_bf16=qk2)
+            ops.gemm(scale16p, w.enc_v.fwd, Tp, out_bf16=vs)
+            ops.gemm(shift16p, w.enc_v.fwd, Tp, out_bf16=vh)
+            osp, ohp = _e16(dev, Tp, C), _e16(dev, Tp, C)
+            _attn(g, qk2, qk2[:, C:], vs, osp, w.enc_table, 2 * C, 2 * C, C, v2=vh, out2=ohp)
+            os_, oh = _crop16(g, osp), _crop16(g, ohp)
+            scale32a, scale16a = _e32(dev, T, C), _e16(dev, T, C)
+            ops.gemm(os_, w.enc_proj.fwd, T, res=scale32, out_f32=scale32a, out_bf16=scale16a, row_scale=s(2), rows_per_scale=rows)
+            fc1, fc2, _ = w.mlp["scale"]
+            scale32, scale16, hp, ha = _mlp_fwd(scale16a, scale32a, fc1, fc2, T, dev, s(3), rows)
+            scale16p = _pad16(g, scale16)
+            t.update(qk2=qk2, vs=vs, vh=vh, os=os_, oh=oh, scale16a=scale16a, hS=(hp, ha), scale16b=scale16p)
+            shift32a, shift16a = _e32(dev, T, C), _e16(dev, T, C)
+            ops.gemm(oh, w.enc_proj.fwd, T, res=shift32, out_f32=shift32a, out_bf16=shift16a, row_scale=s(4), rows_per_scale=rows)
+            fc1, fc2, _ = w.mlp["shift"]
+            shift32, shift16, hp, ha = _mlp_fwd(shift16a, shift32a, fc1, fc2, T, dev, s(5), rows)
+            shift16p = _pad16(g, shift16)
+            t.update(shift16a=shift16a, hH=(hp, ha), shift16b=shift16p)
+            t["_enc_out"] = (key32, key16, key16p, scale32, scale16, scale16p, shift32, shift16, shift16p)
+
+        # ---------------- StyleDecoder, self-attention half (independent of the encoder above: a parallel graph branch) ----------------
+        x32_in = x32
+
+        def dec_chain():
+            ln1, qkv3, o3p = _e16(dev, T, C), _e16(dev, Tp, 3 * C), _e16(dev, Tp, C)
+            ops.layernorm(x32_in, w.n1[0], w.n1[1], ln1, T, C)
+            ln1 = _pad16(g, ln1)
+            ops.gemm(ln1, w.dec_qkv.fwd, Tp, out_bf16=qkv3)
+            _attn(g, qkv3, qkv3[:, C:], qkv3[:, 2 * C:], o3p, w.dec_table, 3 * C, 3 * C, 3 * C)
+            o3 = _crop16(g, o3p)
+            x32a = _e32(dev, T, C)
+            ops.gemm(o3, w.dec_proj.fwd, T, res=x32_in, out_f32=x32a, row_scale=s(6), rows_per_scale=rows)
+            ln2 = _e16(dev, T, C)
+            ops.layernorm(x32a, w.n2[0], w.n2[1], ln2, T, C)
+            fc1, fc2, _ = w.mlp["dec"]
+            query32, _, hp, ha = _mlp_fwd(ln2, x32a, fc1, fc2, T, dev, s(7), rows, want16=False)
+            t.update(x32_in=x32_in, ln1=ln1, qkv3=qkv3, o3=o3, x32a=x32a, ln2=ln2, hD=(hp, ha), query32=query32)
+            qmean, qrstd = _e32(dev, g.B, C), _e32(dev, g.B, C)
+            qhat = _e16(dev, T, C)
+            ops.instnorm_stats(query32, qmean, qrstd, g.B, g.HW, C, twice=True)
+            ops.instnorm_apply(query32, qmean, qrstd, g.B, g.HW, C, y16=qhat)
+            t["_qhat"] = qhat
+
+        _parallel(enc_chain, dec_chain)
+        key32, key16, key16p, scale32, scale16, scale16p, shift32, shift16, shift16p = t.pop("_enc_out")
+        query32, qhat = t["query32"], t.pop("_qhat")
         mean, rstd = _e32(dev, g.B, C), _e32(dev, g.B, C)
-        qhat, kin, khat = _e16(dev, T, C), _e16(dev, T, C), _e16(dev, T, C)
-        ops.instnorm_stats(query32, mean, rstd, g.B, g.HW, C, twice=True)
-        ops.instnorm_apply(query32, mean, rstd, g.B, g.HW, C, y16=qhat)
+        kin, khat = _e16(dev, T, C), _e16(dev, T, C)
         ops.instnorm_stats(key32, mean, rstd, g.B, g.HW, C)
         ops.instnorm_apply(key32, mean, rstd, g.B, g.HW, C, y16=kin)
         # padded q tokens are zero (no Q projection, :511-514); Wk runs on the padded Key and its InstanceNorm over the PADDED map (:520-530)
