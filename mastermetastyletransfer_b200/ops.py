@@ -101,6 +101,9 @@ class PackedMatrix:
 def _pad_bias(bias: Optional[torch.Tensor], n_pad: int, device) -> Optional[torch.Tensor]:
     if bias is None:
         return None
+    b = bias.detach().reshape(-1)
+    if b.numel() == n_pad and b.dtype == torch.float32 and b.is_contiguous() and b.device == torch.device(device):
+        return b  # no padding needed: the kernels read the live parameter (re-packing a training step costs no fill + copy per bias)
     out = torch.zeros(n_pad, dtype=torch.float32, device=device)
     out[: bias.numel()].copy_(bias.detach().reshape(-1))
     return out
