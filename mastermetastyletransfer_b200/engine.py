@@ -167,7 +167,9 @@ class StyleTransformerWeights:
         self.pm_shift = mlp("encoder.encoder_MLP_Shift.", e + "proj.")
         d = "decoder.MHA_self_attn."
         self.n1 = (g(d + "norm1.weight"), g(d + "norm1.bias"))
-        self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias"))
+        # decoder_exclude_MLP_after_Fcs_self_MHA=True builds the block without norm2 / mlp (reference :339-343,365)
+        self.has_dec_mlp = (prefix + d + "mlp.0.weight") in sd
+        self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias")) if self.has_dec_mlp else None
         a = d + "attn."
         dbq, dbk, dbv = g(a + "Wq.bias"), g(a + "Wk.bias"), g(a + "Wv.bias")
         self.dec_qkv = ops.pack_linear(torch.cat([g(a + "Wq.weight"), g(a + "Wk.weight"), g(a + "Wv.weight")], 0),
@@ -175,8 +177,8 @@ class StyleTransformerWeights:
         self.dec_pad = (dbq, dbk, dbv)
         self.dec_proj = ops.pack_linear(g(a + "proj.weight"), g(a + "proj.bias"))
         self.dec_table = g(a + "relative_position_bias_table")
-        self.dec_mlp = mlp(d + "mlp.")
-        self.pm_dec = mlp(d + "mlp.", a + "proj.")
+        self.dec_mlp = mlp(d + "mlp.") if self.has_dec_mlp else None
+        self.pm_dec = mlp(d + "mlp.", a + "proj.") if self.has_dec_mlp else None
         m = "decoder.decoder_MHA_for_sigma_and_mu."
         self.sm_k = ops.pack_linear(g(m + "Wk.weight"), g(m + "Wk.bias"))
         self.sm_vs = ops.pack_linear(g(m + "Wv_scale.weight"), g(m + "Wv_scale.bias"))
@@ -195,10 +197,18 @@ def _mlp_residual(x16, x32, fc, T, ws_: Workspace, out16):
 
 def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs32: torch.Tensor, k: int, ws_: Workspace,
                               B: int, H: int, W: int, win: int, shift: int, heads: int,
-                              out32: torch.Tensor, out16: Optional[torch.Tensor] = None):
+                              out32: torch.Tensor, out16: Optional[torch.Tensor] = None, *, processed_key: bool = True,
+                              key_in_after_linear: bool = True, exclude_mlp: bool = False):
     """Fc, Fs fp32 [B,H,W,C] -> out32 fp32 [B,H,W,C] (+ bf16 copy for the CNN decoder).
     Follows StyleTransformer.forward (:1229-1245) -> StyleEncoder.forward (:855-882) ->
-    StyleDecoder.forward (:1045-1059,1123-1128)."""
+    StyleDecoder.forward (:1045-1059,1123-1128).
+    Alternate orderings of the same ops:
+      processed_key=False        Scale / Shift attend with the layer's INPUT Key, the Key pass runs last (:883-909);
+      key_in_after_linear=False  Key is instance-normalised twice BEFORE Wk (:1057 then :470-472, on the unpadded map) and
+                                 Wk.Key is used as it is -- no InstanceNorm over the padded map, padded keys = bk (:520);
+      exclude_mlp=True           the decoder's self-attention block has no norm2 / MLP (:389-392)."""
+    if exclude_mlp == w.has_dec_mlp:
+        raise ValueError("decoder_exclude_MLP_after_Fcs_self_MHA does not match the packed state_dict (decoder.MHA_self_attn.mlp.*)")
     # Feature maps that are not a multiple of the window (the reference CLI's default 7x7 windows on 32^2 / 64^2 maps,
     # train.py:703-711) are zero-padded at the bottom/right inside the attention (style_transformer.py:77-87): a padded
     # token's projection is the bias, and the sigma/mu attention normalises Wk.K over the PADDED map (:520-530).
@@ -233,34 +243,46 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
 
     for _ in range(k):
         # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
-        ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
-        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
-                             pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
-        if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
-            ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
-        else:
-            ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
-            _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
-        # Scale / Shift passes: q = k = processed Key (one softmax), v = Scale | Shift, residual from v
-        ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
-        ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
-        ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
-                             v2=vh16, out2=o2_16, pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2], pad_v2=w.enc_pad[2])
-        if FUSE_PROJ_MLP:
-            ops.mlp_fused(o16, w.pm_scale, T, res=scale32, out_f32=scale32, out_bf16=scale16, pre=True)
-            ops.mlp_fused(o2_16, w.pm_shift, T, res=shift32, out_f32=shift32, out_bf16=shift16, pre=True)
-        else:
-            ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
-            _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
-            ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
-            _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
+        def key_pass():
+            ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
+            ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
+                                 pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
+            if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
+                ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
+            else:
+                ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
+                _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
+
+        def scale_shift_passes():
+            # q = k = Key (one softmax for both), v = Scale | Shift, residual from v
+            ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
+            ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
+            ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
+                                 v2=vh16, out2=o2_16, pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2], pad_v2=w.enc_pad[2])
+            if FUSE_PROJ_MLP:
+                ops.mlp_fused(o16, w.pm_scale, T, res=scale32, out_f32=scale32, out_bf16=scale16, pre=True)
+                ops.mlp_fused(o2_16, w.pm_shift, T, res=shift32, out_f32=shift32, out_bf16=shift16, pre=True)
+            else:
+                ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
+                _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
+                ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
+                _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
+
+        if processed_key:  # default (:857-882): Scale / Shift attend with the processed Key
+            key_pass()
+            scale_shift_passes()
+        else:  # (:883-909): Scale / Shift attend with this layer's input Key, the Key pass runs last
+            scale_shift_passes()
+            key_pass()
 
         # ---------------- StyleDecoder ----------------
         ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
         ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
         ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
                              pad_q=w.dec_pad[0], pad_k=w.dec_pad[1], pad_v=w.dec_pad[2])
-        if FUSE_PROJ_MLP:
+        if exclude_mlp:  # Query = Fcs + proj(attention) only
+            ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
+        elif FUSE_PROJ_MLP:
             ops.mlp_fused(o16, w.pm_dec, T, res=x32, out_f32=x32, pre=True, ln_g=w.n2[0], ln_b=w.n2[1])  # x32 = Query
         else:
             ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
@@ -269,19 +291,23 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         # Query is instance-normalised twice (:1056 then :468); Key once before Wk and once after (:1057, :520-530)
         ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True)
         ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16)
-        ops.instnorm_stats(key32, mean, rstd, B, H * W, C)
+        ops.instnorm_stats(key32, mean, rstd, B, H * W, C, twice=not key_in_after_linear)
         ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16)
-        ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
-        if padded:  # statistics over the padded map: its n_pad extra tokens all hold Wk.0 + bk = bk
-            ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad)
+        if not key_in_after_linear:  # IN(IN(Key)) on the unpadded map, then k = Wk.Key + bk as it is
+            ops.gemm(ln16, w.sm_k, T, out_bf16=khat16)
         else:
-            ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
-        ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16)
+            ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
+            if padded:  # statistics over the padded map: its n_pad extra tokens all hold Wk.0 + bk = bk
+                ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad)
+            else:
+                ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
+            ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16)
         ops.gemm(scale16, w.sm_vs, T, out_bf16=vs16)
         ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
         # padded tokens: q = 0 (no Q projection, :511-514), k = the normalised bias (per image), v = the value biases
         ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16,
-                             pad_k=kpad if padded else None, pad_v=w.sm_pad[1], pad_v2=w.sm_pad[2], pad_k_per_image=padded)
+                             pad_k=(kpad if key_in_after_linear else w.sm_pad[0]) if padded else None,
+                             pad_v=w.sm_pad[1], pad_v2=w.sm_pad[2], pad_k_per_image=padded and key_in_after_linear)
         ops.gemm(o16, w.sm_proj, T, out_f32=sigma32)
         if FUSE_PROJ_MLP:  # Query = Query*sigma + mu (:1123); Query += last_MLP(Query)
             ops.mlp_fused(o2_16, w.pm_last, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16, pre=True)

@@ -6,8 +6,10 @@ unchanged; the arithmetic runs in the sm_100a kernels behind the C ABI (engine.p
 parameters stay ordinary nn.Linear / nn.LayerNorm sub-modules so deepcopy, .apply(init_fn),
 optimizers and load_state_dict behave as in the reference.
 
-Only the reference's default configuration is built in CUDA this round (SURVEY.md section 8f lists the
-alternates); anything else raises NotImplementedError at call time -- never a silent fallback.
+The reference's default configuration is built in CUDA for inference and training; of the alternates SURVEY.md section 8f
+lists, the three that are re-orderings of the same ops (unprocessed Key for Scale/Shift, Key InstanceNorm before Wk, no MLP
+after the decoder's self-attention) run in inference; anything else raises NotImplementedError at call time -- never a
+silent fallback.
 """
 from __future__ import annotations
 
@@ -296,16 +298,26 @@ class StyleTransformer(nn.Module):
                      and encoder_mlp_ratio == decoder_mlp_ratio == 4.0
                      and encoder_norm_layer is None and decoder_norm_layer is nn.LayerNorm
                      and encoder_MLP_activation_layer is nn.GELU and decoder_MLP_activation_layer is nn.GELU
-                     and encoder_if_use_processed_Key_in_Scale_and_Shift_calculation
                      and not decoder_use_instance_norm_with_affine and not decoder_use_regular_MHA_instead_of_Swin_at_the_end
-                     and decoder_use_Key_instance_norm_after_linear_transformation and not decoder_exclude_MLP_after_Fcs_self_MHA
                      and encoder_qkv_bias and decoder_qkv_bias and encoder_proj_bias and decoder_proj_bias
-                     and encoder_dropout == decoder_dropout == encoder_attention_dropout == decoder_attention_dropout == 0.0))
+                     and encoder_dropout == decoder_dropout == encoder_attention_dropout == decoder_attention_dropout == 0.0),
+            # alternates the inference engine sequences from the same kernels (reference :883-909, :470-472, :389-392)
+            flags=dict(processed_key=bool(encoder_if_use_processed_Key_in_Scale_and_Shift_calculation),
+                       key_in_after_linear=bool(decoder_use_Key_instance_norm_after_linear_transformation),
+                       exclude_mlp=bool(decoder_exclude_MLP_after_Fcs_self_MHA)))
 
-    def _check_config(self):
+    def engine_flags(self) -> dict:
+        """Keyword arguments of engine.style_transformer_forward that select the reference's alternate orderings."""
+        return dict(self._cfg["flags"])
+
+    def _check_config(self, training: bool = False):
         c = self._cfg
         if not c["default"]:
-            raise NotImplementedError("only the reference's default StyleTransformer configuration has sm_100a kernels (SURVEY.md 8f-4)")
+            raise NotImplementedError("this StyleTransformer configuration has no sm_100a kernels (affine InstanceNorm, regular MHA at "
+                                      "the end, dropout, non-GELU / non-LayerNorm variants: SURVEY.md 8f-4)")
+        if training and c["flags"] != dict(processed_key=True, key_in_after_linear=True, exclude_mlp=False):
+            raise NotImplementedError("the training step (taped forward + backward kernels) is built for the reference's default "
+                                      "StyleTransformer configuration only; the alternate orderings run in inference (SURVEY.md 8f-4)")
         if c["window"][0] != c["window"][1] or c["shift"][0] != c["shift"][1] or c["dim"] // c["heads"] != 32:
             raise NotImplementedError("square windows and head_dim 32 only")
 
@@ -317,6 +329,7 @@ class StyleTransformer(nn.Module):
         B, H, W, C = Fc.shape
         sd_active = self.training and (self.encoder.encoder_stochastic_depth_prob > 0 or self.decoder.stochastic_depth.p > 0)
         if wants_grad(self, Fc, Fs) or sd_active:
+            self._check_config(training=True)
             from .autograd_fns import style_transformer_apply
             return style_transformer_apply(self, Fc, Fs, int(k))
         with torch.no_grad():
@@ -324,5 +337,6 @@ class StyleTransformer(nn.Module):
             ws = workspace_of(self, Fc.device)
             out = torch.empty(B, H, W, C, dtype=torch.float32, device=Fc.device)
             engine.style_transformer_forward(w, Fc.float().contiguous(), Fs.float().contiguous(), int(k), ws, B, H, W,
-                                             self._cfg["window"][0], self._cfg["shift"][0], self._cfg["heads"], out)
+                                             self._cfg["window"][0], self._cfg["shift"][0], self._cfg["heads"], out,
+                                             **self.engine_flags())
         return out

@@ -187,22 +187,27 @@ def instance_norm_bhwc(x: Tensor, eps: float = 1e-5) -> Tensor:
 
 
 def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk, wvs, bvs, wvh, bvh, wp, bp,
-                       table: Tensor, ws: int, shift: int, heads: int) -> Tuple[Tensor, Tensor]:
+                       table: Tensor, ws: int, shift: int, heads: int, key_in_after_linear: bool = True) -> Tuple[Tensor, Tensor]:
     """codes/style_transformer.py:414-611 (a8), default flags: IN(q) again (:468), no Q projection
     (:511-514), IN over the whole (padded) map of Wk*K (:520-530), one softmax for both values,
-    the same proj for sigma and mu (:575-607)."""
+    the same proj for sigma and mu (:575-607).
+    key_in_after_linear=False (use_Key_instance_norm_after_linear_transformation=False, :470-472): the key input is
+    instance-normalised once more on the UNPADDED map before Wk and Wk*K is used as it is (padded tokens = bk)."""
     B, H, W, C = xq.shape
     Hp, Wp = padded_dims(H, W, ws)
     q = _to_windows(instance_norm_bhwc(xq), ws, shift)
+    if not key_in_after_linear:
+        xk = instance_norm_bhwc(xk)
     k = F.linear(_to_windows(xk, ws, shift), wk, bk)
     vs = F.linear(_to_windows(xvs, ws, shift), wvs, bvs)
     vh = F.linear(_to_windows(xvh, ws, shift), wvh, bvh)
-    # un-window k (still rolled, still padded), normalise per (b,c) over Hp*Wp, re-window
-    gm = window_gather_map(H, W, ws, shift).reshape(-1)
-    kmap = torch.empty(B, Hp * Wp, C)
-    kmap[:, gm] = k.reshape(B, -1, C)
-    kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C)).reshape(B, Hp * Wp, C)
-    k = kmap[:, gm].reshape(k.shape)
+    if key_in_after_linear:
+        # un-window k (still rolled, still padded), normalise per (b,c) over Hp*Wp, re-window
+        gm = window_gather_map(H, W, ws, shift).reshape(-1)
+        kmap = torch.empty(B, Hp * Wp, C)
+        kmap[:, gm] = k.reshape(B, -1, C)
+        kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C)).reshape(B, Hp * Wp, C)
+        k = kmap[:, gm].reshape(k.shape)
     p = _softmax_probs(q, k, heads, _bias_from_table(table, ws), shift_mask(H, W, ws, shift), B)
     sig = F.linear(_apply_probs(p, vs, heads), wp, bp)
     mu = F.linear(_apply_probs(p, vh, heads), wp, bp)
@@ -234,11 +239,22 @@ def _sd(x: Tensor, scales, i: int) -> Tensor:
 
 
 def style_encoder(sd: SD, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
-                  pre: str = "encoder.", sd_scales=None):
+                  pre: str = "encoder.", sd_scales=None, processed_key: bool = True):
     """codes/style_transformer.py:855-882 default branch: one shared MHA (no norm, residual from
     input_q for the Key pass and from input_v for Scale/Shift, :383-386), three private MLPs.
-    sd_scales: optional 9 per-sample stochastic-depth factor vectors in call order (:395,865,873,882)."""
+    sd_scales: optional 9 per-sample stochastic-depth factor vectors in call order (:395,865,873,882).
+    processed_key=False (encoder_if_use_processed_Key_in_Scale_and_Shift_calculation=False, :883-909): Scale and Shift
+    attend with the layer's INPUT Key, the Key pass runs last (eval mode only: sd_scales must be None)."""
     aw = _attn_weights(sd, pre + "shared_MHA_without_MLP.attn.")
+    if not processed_key:
+        assert sd_scales is None
+        scale = scale + window_attention(key, key, scale, *aw, ws, sh, heads)
+        scale = scale + mlp(scale, sd, pre + "encoder_MLP_Scale.")
+        shift_t = shift_t + window_attention(key, key, shift_t, *aw, ws, sh, heads)
+        shift_t = shift_t + mlp(shift_t, sd, pre + "encoder_MLP_Shift.")
+        key = key + window_attention(key, key, key, *aw, ws, sh, heads)
+        key = key + mlp(key, sd, pre + "encoder_MLP_Key.")
+        return key, scale, shift_t
     key = key + _sd(window_attention(key, key, key, *aw, ws, sh, heads), sd_scales, 0)
     key = key + _sd(mlp(key, sd, pre + "encoder_MLP_Key."), sd_scales, 1)
     scale = scale + _sd(window_attention(key, key, scale, *aw, ws, sh, heads), sd_scales, 2)
@@ -249,13 +265,16 @@ def style_encoder(sd: SD, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, 
 
 
 def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
-                  pre: str = "decoder.", sd_scales=None):
-    """codes/style_transformer.py:1045-1059,1123-1128 default branch (stochastic depth at :390,392,1125)."""
+                  pre: str = "decoder.", sd_scales=None, key_in_after_linear: bool = True, exclude_mlp: bool = False):
+    """codes/style_transformer.py:1045-1059,1123-1128 default branch (stochastic depth at :390,392,1125).
+    exclude_mlp=True (decoder_exclude_MLP_after_Fcs_self_MHA, :339-343,365,389-392): the self-attention block has no
+    norm2 / mlp; key_in_after_linear: see sigma_mu_attention."""
     b = pre + "MHA_self_attn."
     C = fcs.shape[-1]
     n1 = F.layer_norm(fcs, (C,), sd[b + "norm1.weight"], sd[b + "norm1.bias"])
     x = fcs + _sd(window_attention(n1, n1, n1, *_attn_weights(sd, b + "attn."), ws, sh, heads), sd_scales, 6)
-    x = x + _sd(mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp."), sd_scales, 7)
+    if not exclude_mlp:
+        x = x + _sd(mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp."), sd_scales, 7)
     query_in = instance_norm_bhwc(x)
     key_in = instance_norm_bhwc(key)
     m = pre + "decoder_MHA_for_sigma_and_mu."
@@ -264,20 +283,25 @@ def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tens
                                    sd[m + "Wv_scale.weight"], sd[m + "Wv_scale.bias"],
                                    sd[m + "Wv_shift.weight"], sd[m + "Wv_shift.bias"],
                                    sd[m + "proj.weight"], sd[m + "proj.bias"],
-                                   sd[m + "relative_position_bias_table"], ws, sh, heads)
+                                   sd[m + "relative_position_bias_table"], ws, sh, heads,
+                                   key_in_after_linear=key_in_after_linear)
     x = x * sigma + mu
     return x + _sd(mlp(x, sd, pre + "last_MLP."), sd_scales, 8)
 
 
 def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8,
-                      sd_scales=None) -> Tensor:
+                      sd_scales=None, processed_key: bool = True, key_in_after_linear: bool = True,
+                      exclude_mlp: bool = False) -> Tensor:
     """codes/style_transformer.py:1229-1245: Scale=Shift=Fs, k times the same weights.
-    sd_scales: optional [k, 9, B] train-mode stochastic-depth factors (None = eval)."""
+    sd_scales: optional [k, 9, B] train-mode stochastic-depth factors (None = eval).
+    processed_key / key_in_after_linear / exclude_mlp: the reference's alternate configurations, see
+    style_encoder / sigma_mu_attention / style_decoder."""
     scale, shift_t = fs, fs
     for l in range(k):
         sc = None if sd_scales is None else sd_scales[l]
-        fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads, sd_scales=sc)
-        fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads, sd_scales=sc)
+        fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads, sd_scales=sc, processed_key=processed_key)
+        fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads, sd_scales=sc,
+                           key_in_after_linear=key_in_after_linear, exclude_mlp=exclude_mlp)
     return fc
 
 

@@ -26,3 +26,37 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(REPO, "tests", "golden")
+
+
+# The reference's alternate StyleTransformer configurations that are built: name -> (constructor flags of
+# codes/style_transformer.py:1185-1189, keyword arguments of the oracle).  Goldens: oracle/make_alternates_golden.py.
+ALTERNATE_CONFIGS = {
+    "unprocessed_key": (dict(encoder_if_use_processed_Key_in_Scale_and_Shift_calculation=False), dict(processed_key=False)),
+    "no_self_mlp": (dict(decoder_exclude_MLP_after_Fcs_self_MHA=True), dict(exclude_mlp=True)),
+    "key_in_before": (dict(decoder_use_Key_instance_norm_after_linear_transformation=False), dict(key_in_after_linear=False)),
+}
+ALTERNATE_CONFIGS["all_three"] = ({k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[0].items()},
+                                  {k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[1].items()})
+
+
+def alternate_style_transformer(name: str, ws: int):
+    """The drop-in StyleTransformer built with one of ALTERNATE_CONFIGS and the seeded (name-keyed) weights."""
+    from mastermetastyletransfer_b200 import StyleTransformer, synthetic
+    m = StyleTransformer(encoder_dim=256, decoder_dim=256, encoder_num_heads=8, decoder_num_heads=8,
+                         encoder_window_size=[ws, ws], decoder_window_size=[ws, ws], encoder_shift_size=[4, 4],
+                         decoder_shift_size=[4, 4], **ALTERNATE_CONFIGS[name][0])
+    synthetic.fill_state_dict_(m, 0)
+    return m.eval()
+
+
+def alternate_inputs():
+    """Fc, Fs [2,16,16,256]: the oracle Swin encoder's features of the seeded 128x128 synthetic images."""
+    import torch
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel, synthetic
+    from oracle import master_oracle as O
+    m = MasterStyleTransferModel()
+    synthetic.fill_state_dict_(m, 0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    content, style = synthetic.synthetic_images(2, 128, seed=0)
+    with torch.no_grad():
+        return O.swin_encoder(sd, content, "swin_encoder."), O.swin_encoder(sd, style, "swin_encoder.")

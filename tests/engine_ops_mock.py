@@ -1,0 +1,152 @@
+"""CPU stand-ins for the C-ABI kernels the inference style transformer launches -- TEST INFRASTRUCTURE ONLY.
+
+`install(monkeypatch)` replaces the wrappers in `mastermetastyletransfer_b200.ops` that `engine.StyleTransformerWeights` and
+`engine.style_transformer_forward` call with torch-CPU restatements of each kernel's documented contract
+(include/mst_b200.h): same arguments, same in-place buffer semantics, bf16 tensors really stored as bf16 (so the rounding
+points of the device path are reproduced: bf16 operands and weights, fp32 accumulation and residual streams).  What this
+checks is the HOST logic -- which kernel runs on which buffer in which order for each configuration -- on a machine
+without a GPU; the kernels themselves are checked on the B200 (`-m gpu`).  Nothing in the product imports this file.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from mastermetastyletransfer_b200 import ops
+from oracle import master_oracle as O
+
+
+class _Mlp:
+    def __init__(self, w1, b1, w2, b2, wpre=None, bpre=None):
+        r = lambda w: None if w is None else w.detach().bfloat16().float()
+        self.w1, self.w2, self.wpre = r(w1), r(w2), r(wpre)
+        self.b1, self.b2 = b1.detach().float(), b2.detach().float()
+        self.bpre = None if bpre is None else bpre.detach().float()
+        self.C = w1.shape[1]
+
+
+def pack_linear(weight, bias=None):
+    N, K = weight.shape
+    return ops.PackedMatrix(weight.detach().bfloat16(), None if bias is None else bias.detach().float(), N, K, N, K)
+
+
+def pack_mlp(w1, b1, w2, b2, wpre=None, bpre=None):
+    return _Mlp(w1, b1, w2, b2, wpre, bpre)
+
+
+def _rows(t, M, N, ld):
+    """[M, N] view with row stride ld of a token-major buffer."""
+    return t.as_strided((M, N), (ld, 1), t.storage_offset())
+
+
+def cast_bf16(x, y):
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16
+    y.copy_(x)
+
+
+def gemm(A, pm, M, *, lda=None, res=None, mul=None, out_f32=None, out_bf16=None, ld_out32=None, ld_out16=None, ld_res=None, **kw):
+    assert not kw, kw
+    assert A.dtype == torch.bfloat16 and (out_f32 is not None or out_bf16 is not None)
+    N, K = pm.N, pm.K
+    x = _rows(A, M, K, K if lda is None else lda).float() @ pm.w.float().t()
+    if pm.bias is not None:
+        x = x + pm.bias
+    if res is not None:
+        r = _rows(res, M, N, N if ld_res is None else ld_res)
+        x = r * _rows(mul, M, N, N if ld_res is None else ld_res) + x if mul is not None else r + x
+    else:
+        assert mul is None
+    if out_f32 is not None:
+        _rows(out_f32, M, N, N if ld_out32 is None else ld_out32).copy_(x)
+    if out_bf16 is not None:
+        _rows(out_bf16, M, N, N if ld_out16 is None else ld_out16).copy_(x)
+
+
+def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=False, mul=None, ln_g=None, ln_b=None):
+    C = pm.C
+    a = _rows(A, M, C, C if lda is None else lda).float()
+    if pre:
+        assert pm.wpre is not None
+        x1 = a @ pm.wpre.t() + pm.bpre
+        x1 = res[:M] * mul[:M] + x1 if mul is not None else res[:M] + x1
+        xin = F.layer_norm(x1, (C,), ln_g, ln_b) if ln_g is not None else x1
+        xin = xin.bfloat16().float()
+    else:
+        assert pm.wpre is None and mul is None and ln_g is None
+        x1 = res[:M] if res is not None else 0.0
+        xin = a
+    h = F.gelu(xin @ pm.w1.t() + pm.b1).bfloat16().float()
+    y = x1 + h @ pm.w2.t() + pm.b2
+    if out_f32 is not None:
+        out_f32[:M].copy_(y)
+    if out_bf16 is not None:
+        out_bf16[:M].copy_(y)
+
+
+def layernorm(x, gamma, beta, y, rows, Cdim):
+    y[:rows].copy_(F.layer_norm(x[:rows], (Cdim,), gamma, beta))
+
+
+def _stats(x, B, T, Cdim, extra=None, n_extra=0):
+    """biased mean / variance per (b, c) over T tokens (+ n_extra tokens of value extra[c])."""
+    xb = x.reshape(B, T, Cdim).double()
+    n = T + n_extra
+    s1, s2 = xb.sum(1), (xb * xb).sum(1)
+    if n_extra:
+        s1, s2 = s1 + n_extra * extra.double(), s2 + n_extra * extra.double() ** 2
+    mean = s1 / n
+    return mean, s2 / n - mean * mean
+
+
+def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False):
+    m, var = _stats(x, B, T, Cdim)
+    r = 1.0 / torch.sqrt(var + 1e-5)
+    if twice:  # IN(IN(x)): the once-normalised map has mean 0 and variance var/(var+eps)
+        r = r / torch.sqrt(var * r * r + 1e-5)
+    mean.copy_(m)
+    rstd.copy_(r)
+
+
+def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None):
+    m, var = _stats(x, B, T, Cdim, pad_val, n_pad)
+    r = 1.0 / torch.sqrt(var + 1e-5)
+    mean.copy_(m)
+    rstd.copy_(r)
+    if pad_norm is not None:
+        pad_norm.copy_((pad_val.double().unsqueeze(0) - m) * r)
+
+
+def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None):
+    y = (x.reshape(B, T, Cdim) - mean.unsqueeze(1)) * rstd.unsqueeze(1)
+    for dst in (y16, y32):
+        if dst is not None:
+            dst.reshape(B, T, Cdim).copy_(y)
+
+
+def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
+                     v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None, pad_k_per_image=False):
+    C = heads * 32
+    T = B * H * W
+    Hp, Wp = O.padded_dims(H, W, ws)
+
+    def padded_map(t, ld, pad, per_image=False):
+        m = torch.zeros(B, Hp, Wp, C)
+        if pad is not None:
+            m += pad.reshape(B, 1, 1, C) if per_image else pad.reshape(1, 1, 1, C)
+        m[:, :H, :W] = _rows(t, T, C, ld).float().reshape(B, H, W, C)
+        return m
+
+    qw = O._to_windows(padded_map(q, ldq, pad_q), ws, shift)
+    kw = O._to_windows(padded_map(k, ldk, pad_k, pad_k_per_image), ws, shift)
+    p = O._softmax_probs(qw, kw, heads, O._bias_from_table(bias_table, ws), O.shift_mask(Hp, Wp, ws, shift), B)
+    for val, pad, dst in ((v, pad_v, out), (v2, pad_v2, out2)):
+        if val is None:
+            continue
+        o = O._apply_probs(p, O._to_windows(padded_map(val, ldv, pad), ws, shift), heads)
+        _rows(dst, T, C, ldo).copy_(O._from_windows(o, B, Hp, Wp, ws, shift)[:, :H, :W].reshape(T, C))
+
+
+def install(monkeypatch):
+    for name in ("pack_linear", "pack_mlp", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
+                 "instnorm_stats_padded", "instnorm_apply", "window_attention"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -81,6 +81,29 @@ def test_error_behaviour(model):
         model.style_transformer.eval()(torch.zeros(1, 8, 8, 256), torch.zeros(1, 8, 8, 256))
 
 
+def test_alternate_configurations_gate():
+    """the three re-ordering flags are accepted for inference and refused (loudly) by the training step; the
+    variants without kernels are refused everywhere."""
+    kw = dict(encoder_dim=256, decoder_dim=256, encoder_num_heads=8, decoder_num_heads=8, encoder_window_size=[8, 8],
+              decoder_window_size=[8, 8], encoder_shift_size=[4, 4], decoder_shift_size=[4, 4])
+    default = mst.StyleTransformer(**kw)
+    default._check_config()
+    default._check_config(training=True)
+    assert default.engine_flags() == dict(processed_key=True, key_in_after_linear=True, exclude_mlp=False)
+    for flag, key, value in (("encoder_if_use_processed_Key_in_Scale_and_Shift_calculation", "processed_key", False),
+                             ("decoder_use_Key_instance_norm_after_linear_transformation", "key_in_after_linear", False),
+                             ("decoder_exclude_MLP_after_Fcs_self_MHA", "exclude_mlp", True)):
+        st = mst.StyleTransformer(**kw, **{flag: value if key == "exclude_mlp" else False})
+        st._check_config()
+        assert st.engine_flags()[key] == value
+        with pytest.raises(NotImplementedError):
+            st._check_config(training=True)
+    assert len(mst.StyleTransformer(**kw, decoder_exclude_MLP_after_Fcs_self_MHA=True).state_dict()) == 48
+    for flag in ("decoder_use_instance_norm_with_affine", "decoder_use_regular_MHA_instead_of_Swin_at_the_end"):
+        with pytest.raises(NotImplementedError):
+            mst.StyleTransformer(**kw, **{flag: True})._check_config()
+
+
 def test_seeded_fill_is_name_keyed_and_deterministic():
     a, b = mst.Decoder(), mst.Decoder()
     synthetic.fill_state_dict_(a, 3)
