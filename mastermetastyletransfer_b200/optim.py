@@ -117,6 +117,63 @@ class FusedAdam:
                 else:
                     p.grad.zero_()
 
+    # ---- checkpoint / resume: torch.optim.Adam's state_dict layout, so a run can move between the two ----
+    def _steps_taken(self) -> int:
+        if self._dev_state is not None:  # graph replays advance the device-side counter only
+            return max(self.step_count, max(int(st[1].item()) for st in self._dev_state))
+        return self.step_count
+
+    def state_dict(self) -> dict:
+        """{'state': {index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} exactly as torch.optim.Adam packs it
+        (parameters numbered in group order, moments cloned)."""
+        step = self._steps_taken()
+        state, groups, i = {}, [], 0
+        for g, st in zip(self.param_groups, self.state):
+            idx = []
+            for m, v in zip(st["exp_avg"], st["exp_avg_sq"]):
+                if step > 0:  # torch creates a parameter's state at its first step
+                    state[i] = {"step": torch.tensor(float(step)), "exp_avg": m.detach().clone(), "exp_avg_sq": v.detach().clone()}
+                idx.append(i)
+                i += 1
+            groups.append({"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": g["weight_decay"],
+                           "amsgrad": False, "maximize": False, "foreach": None, "capturable": self.capturable,
+                           "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": idx})
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        """Accepts FusedAdam.state_dict() and torch.optim.Adam.state_dict() of an optimiser built over the same parameter
+        groups.  The kernel keeps ONE step count for all tensors, so every stored 'step' must be the same."""
+        groups = sd["param_groups"]
+        if len(groups) != len(self.param_groups) or any(len(a["params"]) != len(b["params"]) for a, b in zip(groups, self.param_groups)):
+            raise ValueError("loaded state dict has different parameter groups")
+        for a in groups:
+            if a.get("amsgrad") or a.get("maximize") or a.get("decoupled_weight_decay"):
+                raise ValueError("FusedAdam implements plain Adam only (no amsgrad / maximize / decoupled weight decay)")
+        steps = {int(float(e["step"])) for e in sd["state"].values()}
+        if len(steps) > 1:
+            raise ValueError("FusedAdam keeps one step count for all parameters; the loaded state has several")
+        n = sum(len(g["params"]) for g in self.param_groups)
+        if sd["state"] and len(sd["state"]) != n:
+            raise ValueError("loaded state dict covers only some of the parameters")
+        for g, a, st in zip(self.param_groups, groups, self.state):
+            g["lr"], g["betas"], g["eps"], g["weight_decay"] = a["lr"], tuple(a["betas"]), a["eps"], a["weight_decay"]
+            for j, i in enumerate(a["params"]):
+                e = sd["state"].get(i)
+                if e is None:
+                    st["exp_avg"][j].zero_()
+                    st["exp_avg_sq"][j].zero_()
+                    continue
+                if e["exp_avg"].shape != st["exp_avg"][j].shape:
+                    raise ValueError(f"moment {i} has shape {tuple(e['exp_avg'].shape)}, expected {tuple(st['exp_avg'][j].shape)}")
+                st["exp_avg"][j].copy_(e["exp_avg"])  # in place: the device tables (and captured graphs) keep their pointers
+                st["exp_avg_sq"][j].copy_(e["exp_avg_sq"])
+        self.step_count = steps.pop() if steps else 0
+        if self._dev_state is not None:
+            for g, ds in zip(self.param_groups, self._dev_state):
+                ds.view(torch.float32)[0] = float(g["lr"])
+                ds[1] = self.step_count
+
     @torch.no_grad()
     def step(self):
         self.step_count += 1

@@ -1,0 +1,68 @@
+"""CPU suite: FusedAdam checkpoint / resume.  The state_dict layout is torch.optim.Adam's, so a run can move
+between the two optimisers; the update kernel itself is checked on the B200 (tests/test_gpu_optim.py)."""
+import pytest
+import torch
+
+from mastermetastyletransfer_b200.optim import FusedAdam
+
+
+def _params(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.nn.Parameter(torch.randn(s, generator=g)) for s in ((4, 3), (5,), (2, 2, 3))]
+
+
+def _torch_adam_after(steps, params, **kw):
+    opt = torch.optim.Adam(params, **kw)
+    g = torch.Generator().manual_seed(9)
+    for _ in range(steps):
+        for p in params:
+            p.grad = torch.randn(p.shape, generator=g)
+        opt.step()
+    return opt
+
+
+def test_state_dict_round_trips_through_torch_adam():
+    ref = _torch_adam_after(3, _params(), lr=2e-4, betas=(0.8, 0.99), eps=1e-7, weight_decay=0.01)
+    sd = ref.state_dict()
+    mine = FusedAdam(_params(), lr=1.0)
+    mine.load_state_dict(sd)
+    assert mine.step_count == 3
+    g = mine.param_groups[0]
+    assert (g["lr"], g["betas"], g["eps"], g["weight_decay"]) == (2e-4, (0.8, 0.99), 1e-7, 0.01)
+    for i in range(3):
+        assert torch.equal(mine.state[0]["exp_avg"][i], sd["state"][i]["exp_avg"])
+        assert torch.equal(mine.state[0]["exp_avg_sq"][i], sd["state"][i]["exp_avg_sq"])
+    out = mine.state_dict()
+    assert set(out["param_groups"][0]) == set(sd["param_groups"][0])  # same keys as torch.optim.Adam packs
+    back = torch.optim.Adam(_params(), lr=1.0)
+    back.load_state_dict(out)  # torch accepts it
+    for i, p in enumerate(back.param_groups[0]["params"]):
+        assert float(back.state[p]["step"]) == 3.0
+        assert torch.equal(back.state[p]["exp_avg"], sd["state"][i]["exp_avg"])
+    assert back.param_groups[0]["lr"] == 2e-4
+
+
+def test_moments_are_loaded_in_place_and_groups_are_checked():
+    mine = FusedAdam([{"params": _params()[:2], "lr": 1e-3}, {"params": _params()[2:], "lr": 1e-4}])
+    before = [t.data_ptr() for st in mine.state for t in st["exp_avg"] + st["exp_avg_sq"]]
+    fresh = mine.state_dict()
+    assert fresh["state"] == {} and [g["params"] for g in fresh["param_groups"]] == [[0, 1], [2]]
+    sd = _torch_adam_after(2, _params()).state_dict()
+    with pytest.raises(ValueError):
+        mine.load_state_dict(sd)  # one group vs two
+    p = _params()
+    two = torch.optim.Adam([{"params": p[:2], "lr": 1e-3}, {"params": p[2:], "lr": 5e-5}])
+    for q in p:
+        q.grad = torch.ones_like(q)
+    two.step()
+    mine.load_state_dict(two.state_dict())
+    assert [t.data_ptr() for st in mine.state for t in st["exp_avg"] + st["exp_avg_sq"]] == before
+    assert mine.step_count == 1 and mine.param_groups[1]["lr"] == 5e-5
+    sd = two.state_dict()
+    sd["state"][2]["step"] = torch.tensor(7.0)
+    with pytest.raises(ValueError):
+        mine.load_state_dict(sd)  # the kernel keeps one step count
+    sd = two.state_dict()
+    sd["param_groups"][0]["amsgrad"] = True
+    with pytest.raises(ValueError):
+        mine.load_state_dict(sd)
