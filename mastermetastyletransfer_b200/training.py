@@ -131,6 +131,25 @@ class InnerLoopTrainer:
             prefetch_content_style_taps(self.loss_fn, content, style)
         return self._loss_stream
 
+    # ---- checkpoint / resume (the reference saves only the two trained modules, train.py:288-299) ----
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs: theta (the two trained modules, under the names the reference saves them with),
+        omega, the inner optimiser (torch.optim.Adam layout) and the layer-count sampler."""
+        clone = lambda sd: {k: v.detach().clone() for k, v in sd.items()}
+        return {"style_transformer": clone(self.model.style_transformer.state_dict()), "decoder": clone(self.model.decoder.state_dict()),
+                "omega_style_transformer": clone(self.omega_st.state_dict()), "omega_decoder": clone(self.omega_dec.state_dict()),
+                "optimizer": self.opt.state_dict(), "layer_sampler": self._rng.getstate()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        """In place (parameter storage, optimiser moments and a captured GraphedTrainStep stay valid)."""
+        self.model.style_transformer.load_state_dict(sd["style_transformer"])
+        self.model.decoder.load_state_dict(sd["decoder"])
+        self.omega_st.load_state_dict(sd["omega_style_transformer"])
+        self.omega_dec.load_state_dict(sd["omega_decoder"])
+        self.opt.load_state_dict(sd["optimizer"])
+        state = sd["layer_sampler"]
+        self._rng.setstate((state[0], tuple(state[1]), state[2]))  # a torch.save / json round trip turns the tuple into a list
+
     def outer_update(self, outer_lr: float) -> None:
         """theta += outer_lr * mean_over_ranks(omega - theta) for the style transformer and the decoder (train.py:524-534)."""
         reptile_update(self.model.style_transformer, self.omega_st, outer_lr, self.group)

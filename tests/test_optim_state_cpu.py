@@ -66,3 +66,38 @@ def test_moments_are_loaded_in_place_and_groups_are_checked():
     sd["param_groups"][0]["amsgrad"] = True
     with pytest.raises(ValueError):
         mine.load_state_dict(sd)
+
+
+def test_trainer_checkpoint_round_trip(tmp_path):
+    """InnerLoopTrainer.state_dict(): theta, omega, optimiser and the shared layer-count sampler, through torch.save / load."""
+    import mastermetastyletransfer_b200 as mst
+    from mastermetastyletransfer_b200 import synthetic
+    from mastermetastyletransfer_b200.training import InnerLoopTrainer
+    model = synthetic.fill_state_dict_(mst.MasterStyleTransferModel(), 0)
+    tr = InnerLoopTrainer(model, loss_fn=None, inner_lr=3e-4, seed=5)
+    with torch.no_grad():
+        for p in tr.params:
+            p.add_(0.01)
+        for st in tr.opt.state:
+            for t in st["exp_avg"]:
+                t.fill_(0.5)
+    tr.opt.step_count = 7
+    [tr._rng.randint(1, 4) for _ in range(3)]
+    path = tmp_path / "trainer.pt"
+    torch.save(tr.state_dict(), path)
+    assert set(tr.state_dict()["style_transformer"]) == set(model.style_transformer.state_dict())  # the reference's file layout
+    want_next = [tr._rng.randint(1, 4) for _ in range(5)]
+
+    model2 = synthetic.fill_state_dict_(mst.MasterStyleTransferModel(), 1)
+    tr2 = InnerLoopTrainer(model2, loss_fn=None, seed=0)
+    ptrs = [p.data_ptr() for p in tr2.params]
+    tr2.load_state_dict(torch.load(path, weights_only=False))
+    assert [p.data_ptr() for p in tr2.params] == ptrs
+    for a, b in zip(tr.params, tr2.params):
+        assert torch.equal(a, b)
+    for ma, mb in ((model.style_transformer, model2.style_transformer), (model.decoder, model2.decoder)):
+        for a, b in zip(ma.parameters(), mb.parameters()):  # theta; the frozen Swin encoder is not part of the checkpoint
+            assert torch.equal(a, b)
+    assert tr2.opt.step_count == 7 and tr2.opt.lr == 3e-4
+    assert all(torch.equal(t, torch.full_like(t, 0.5)) for st in tr2.opt.state for t in st["exp_avg"])
+    assert [tr2._rng.randint(1, 4) for _ in range(5)] == want_next
