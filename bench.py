@@ -93,8 +93,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_rate(size: int, layers: int, batch: int, iters: int, threads: int):
-    """images/s of the CPU oracle port (full forward, fp32) on a bounded sample."""
+def cpu_oracle_rate(size: int, layers: int, batch: int, iters: int, threads: int, min_seconds: float = 0.0, max_iters: int = 200):
+    """images/s of the CPU oracle port (full forward, fp32) on a bounded sample: `iters` timed forwards, continued until
+    `min_seconds` of timed work have accumulated (at most `max_iters`)."""
     from mastermetastyletransfer_b200 import synthetic
     from mastermetastyletransfer_b200.full_model import MasterStyleTransferModel
     from oracle import master_oracle as O
@@ -106,7 +107,7 @@ def cpu_oracle_rate(size: int, layers: int, batch: int, iters: int, threads: int
     with torch.no_grad():
         O.full_forward(sd, content, style, layers)  # warm-up
         times = []
-        for _ in range(iters):
+        while len(times) < iters or (sum(times) < min_seconds and len(times) < max_iters):
             t0 = time.perf_counter()
             O.full_forward(sd, content, style, layers)
             times.append(time.perf_counter() - t0)
@@ -356,9 +357,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:
         cpu_batch = 4 if args.size == 256 else 1
-        rate, times = cpu_oracle_rate(args.size, args.layers, cpu_batch, 3, threads)
-        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"best of 3 full forwards of batch {cpu_batch} at {args.size}x{args.size}, fp32 CPU oracle port of the reference"}
+        rate, times = cpu_oracle_rate(args.size, args.layers, cpu_batch, 3, threads, min_seconds=10.0)
+        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "median": cpu_batch / statistics.median(times),
+               "sample": f"best of {len(times)} full forwards of batch {cpu_batch} at {args.size}x{args.size} ({sum(times):.1f} s of CPU work), "
+                         "fp32 CPU oracle port of the reference"}
 
     # ---------------- secondary: training-step workloads (BASELINE configs[2], [3]) ----------------
     training = None
