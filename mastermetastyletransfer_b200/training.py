@@ -56,10 +56,21 @@ class InnerLoopTrainer:
     frozen (train.py:216-218,306-309,436-517).  `model` is a MasterStyleTransferModel, `loss_fn` a custom_loss."""
 
     def __init__(self, model, loss_fn, inner_lr: float = 1e-4, max_layers: int = 4, data_parallel: bool = False, group=None,
-                 seed: int = 0, capturable: bool = False):
+                 seed: int = 0, capturable: bool = False, fast_adaptation: bool = False):
+        """fast_adaptation=True is the reference's few-shot stage (train_only_inner_loop.py:306-318): everything frozen except
+        the style ENCODER of the style transformer; the adjoint kernels still run the whole backward (the encoder's gradients
+        need the chain through the CNN decoder and the style decoder), only the encoder's 2.37 M parameters are updated."""
         self.model, self.loss_fn = model, loss_fn
         for p in model.swin_encoder.parameters():
             p.requires_grad = False
+        self.fast_adaptation = fast_adaptation
+        if fast_adaptation:
+            for p in model.style_transformer.decoder.parameters():
+                p.requires_grad = False
+            for p in model.style_transformer.encoder.parameters():
+                p.requires_grad = True
+            for p in model.decoder.parameters():
+                p.requires_grad = False
         self.omega_st = copy.deepcopy(model.style_transformer).train()
         self.omega_dec = copy.deepcopy(model.decoder).train()
         self.params: List[torch.nn.Parameter] = list(self.omega_st.parameters()) + list(self.omega_dec.parameters())

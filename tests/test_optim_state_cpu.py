@@ -101,3 +101,19 @@ def test_trainer_checkpoint_round_trip(tmp_path):
     assert tr2.opt.step_count == 7 and tr2.opt.lr == 3e-4
     assert all(torch.equal(t, torch.full_like(t, 0.5)) for st in tr2.opt.state for t in st["exp_avg"])
     assert [tr2._rng.randint(1, 4) for _ in range(5)] == want_next
+
+
+def test_fast_adaptation_freezes_everything_but_the_style_encoder():
+    """train_only_inner_loop.py:306-318: the few-shot stage trains the style encoder only."""
+    import mastermetastyletransfer_b200 as mst
+    from mastermetastyletransfer_b200.training import InnerLoopTrainer
+    model = mst.MasterStyleTransferModel()
+    tr = InnerLoopTrainer(model, loss_fn=None, fast_adaptation=True)
+    enc = list(tr.omega_st.encoder.parameters())
+    assert all(p.requires_grad for p in enc)
+    assert not any(p.requires_grad for p in tr.omega_st.decoder.parameters())
+    assert not any(p.requires_grad for p in tr.omega_dec.parameters())
+    assert not any(p.requires_grad for p in model.swin_encoder.parameters())
+    assert [id(p) for p in tr.opt.params] == [id(p) for p in enc]  # Adam updates exactly the style encoder
+    assert sum(p.numel() for p in tr.opt.params) == sum(p.numel() for p in model.style_transformer.encoder.parameters())
+    assert len(tr.params) == len(list(model.style_transformer.parameters())) + len(list(model.decoder.parameters()))  # omega <- theta copies all
