@@ -65,3 +65,55 @@ def test_engine_refuses_a_state_dict_that_does_not_match_the_flag(monkeypatch, f
     with pytest.raises(ValueError):
         engine.style_transformer_forward(w, fc, fs, 1, engine.Workspace(torch.device("cpu")), 2, 16, 16, 8, 4, 8,
                                          torch.empty(2, 16, 16, 256), exclude_mlp=True)
+
+
+@pytest.mark.parametrize("name", ["default", "all_three"])
+def test_full_model_forward_passes_the_configuration_to_the_engine(monkeypatch, name):
+    """MasterStyleTransferModel.forward (inference branch) with the Swin encoder and the CNN decoder replaced by the oracle and
+    the style transformer's kernels by their stand-ins: the module -> engine hand-over (buffers, layer count, window / shift /
+    heads, the alternate-ordering flags) against O.full_forward."""
+    import mastermetastyletransfer_b200 as mst
+    from mastermetastyletransfer_b200 import full_model, synthetic
+    engine_ops_mock.install(monkeypatch)
+    flags = {"style_" + k: v for k, v in CONFIGS[name][0].items()}
+    m = synthetic.fill_state_dict_(mst.MasterStyleTransferModel(**flags), 0).eval()
+    sd = {n: v.detach().clone() for n, v in m.state_dict().items()}
+
+    class Raw:  # weight holders of the two stubbed stages: just the state_dict
+        def __init__(self, sd_):
+            self.sd = sd_
+
+    def swin_encode(w, imgs, ws_, S, out32, out16):
+        out32.copy_(torch.cat([O.swin_encoder(w.sd, i, "") for i in imgs], 0))
+
+    def cnn_decoder_forward(w, x16, ws_, B, H, W, out):
+        out.copy_(O.cnn_decoder(w.sd, x16.float().view(B, H, W, 256).permute(0, 3, 1, 2), "decoder."))
+
+    monkeypatch.setattr(engine, "SwinEncoderWeights", Raw)
+    monkeypatch.setattr(engine, "CnnDecoderWeights", Raw)
+    monkeypatch.setattr(engine, "swin_encode", swin_encode)
+    monkeypatch.setattr(engine, "cnn_decoder_forward", cnn_decoder_forward)
+    monkeypatch.setattr(full_model, "require_cuda", lambda *t: None)
+    content, style = synthetic.synthetic_images(2, 128, seed=0)
+    for k in (1, 2):
+        with torch.no_grad():
+            out = m(content, style, k)
+            fc, fs = O.swin_encoder(sd, content, "swin_encoder."), O.swin_encoder(sd, style, "swin_encoder.")
+            st = {n[len("style_transformer."):]: t for n, t in sd.items() if n.startswith("style_transformer.")}
+            ref = O.cnn_decoder(sd, O.style_transformer(st, fc, fs, k, **CONFIGS[name][1]).permute(0, 3, 1, 2), "decoder.decoder.")
+        assert out.shape == ref.shape == (2, 3, 128, 128)
+        assert ((out - ref).abs().max() / (ref.max() - ref.min())).item() <= 2e-2
+
+
+def test_style_transformer_module_forward_passes_the_configuration_to_the_engine(monkeypatch, feats):
+    from mastermetastyletransfer_b200 import style_transformer as st_mod
+    engine_ops_mock.install(monkeypatch)
+    monkeypatch.setattr(st_mod, "require_cuda", lambda *t: None)
+    fc, fs = feats
+    for name in ("default", "unprocessed_key", "all_three"):
+        m = _build(name, 7)
+        sd = {n: v.detach().clone() for n, v in m.state_dict().items()}
+        with torch.no_grad():
+            out = m(fc, fs, 2)
+            ref = O.style_transformer(sd, fc, fs, 2, ws=7, sh=4, heads=8, **CONFIGS[name][1])
+        assert ((out - ref).abs().max() / (ref.max() - ref.min())).item() <= FEAT_TOL, name
