@@ -1,0 +1,44 @@
+"""CPU suite: include/mst_b200.h is a plain-C header (compiles with gcc -std=c99 -pedantic) and every argument struct has the
+same size and field offsets in the ctypes binding (mastermetastyletransfer_b200/_lib.py) as in C -- a mismatch would make the
+kernels read the wrong pointers without any error."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from mastermetastyletransfer_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STRUCTS = ["MstGemm", "MstWgrad", "MstWindowAttnBwd", "MstWindowAttn", "MstMlp", "MstTensorTable", "MstLossTap", "MstLossTaps"]
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mst_b200.h"', "int main(void) {"]
+    for name in STRUCTS:
+        st = getattr(_lib, name)
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out.splitlines()}
+    for name in STRUCTS:
+        st = getattr(_lib, name)
+        assert got[(name, "size")] == ctypes.sizeof(st), name
+        for field, _ in st._fields_:
+            assert got[(name, field)] == getattr(st, field).offset, (name, field)
+
+
+def test_header_declares_exactly_the_bound_structs():
+    import re
+    text = open(os.path.join(REPO, "include", "mst_b200.h")).read()
+    declared = set(re.findall(r"typedef struct (\w+)", text))
+    assert declared == set(STRUCTS), declared ^ set(STRUCTS)
