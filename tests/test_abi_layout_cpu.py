@@ -42,3 +42,34 @@ def test_header_declares_exactly_the_bound_structs():
     text = open(os.path.join(REPO, "include", "mst_b200.h")).read()
     declared = set(re.findall(r"typedef struct (\w+)", text))
     assert declared == set(STRUCTS), declared ^ set(STRUCTS)
+
+
+def test_bound_prototypes_match_the_header():
+    """Argument count and class (pointer / int / float / size_t) of every SYMBOLS entry against the header's prototypes."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", open(os.path.join(REPO, "include", "mst_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(int|size_t|const char\s*\*)\s+(mst_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert {p[1] for p in protos} == set(_lib.SYMBOLS)
+
+    def klass_c(arg: str) -> str:
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "ptr"
+        for t, k in (("size_t", "size"), ("float", "float"), ("double", "double"), ("int", "int")):
+            if re.search(rf"\b{t}\b", arg):
+                return k
+        raise AssertionError(arg)
+
+    def klass_py(t) -> str:
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None and issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_double: "double", ctypes.c_size_t: "size"}[t]
+
+    for ret, name, args in protos:
+        restype, argtypes = _lib.SYMBOLS[name]
+        args = [a for a in args.split(",") if a.strip() and a.strip() != "void"]
+        assert len(args) == len(argtypes), (name, args, argtypes)
+        for a, t in zip(args, argtypes):
+            assert klass_c(a) == klass_py(t), (name, a, t)
+        want = {"int": ctypes.c_int, "size_t": ctypes.c_size_t}.get(ret, ctypes.c_char_p)
+        assert restype is want, (name, ret, restype)
