@@ -1,7 +1,8 @@
 """CPU stand-ins for the C-ABI kernels the inference style transformer launches -- TEST INFRASTRUCTURE ONLY.
 
-`install(monkeypatch)` replaces the wrappers in `mastermetastyletransfer_b200.ops` that `engine.StyleTransformerWeights` and
-`engine.style_transformer_forward` call with torch-CPU restatements of each kernel's documented contract
+`install(monkeypatch)` replaces the wrappers in `mastermetastyletransfer_b200.ops` that the inference engine (Swin encoder,
+style transformer, CNN decoder: `engine.swin_encode`, `engine.style_transformer_forward`, `engine.cnn_decoder_forward` and
+their weight holders) calls with torch-CPU restatements of each kernel's documented contract
 (include/mst_b200.h): same arguments, same in-place buffer semantics, bf16 tensors really stored as bf16 (so the rounding
 points of the device path are reproduced: bf16 operands and weights, fp32 accumulation and residual streams).  What this
 checks is the HOST logic -- which kernel runs on which buffer in which order for each configuration -- on a machine
@@ -44,8 +45,61 @@ def cast_bf16(x, y):
     y.copy_(x)
 
 
-def gemm(A, pm, M, *, lda=None, res=None, mul=None, out_f32=None, out_bf16=None, ld_out32=None, ld_out16=None, ld_res=None, **kw):
+def pack_conv3x3(weight, bias=None):
+    N, Cin = weight.shape[:2]
+    n_pad = ops.n_pad_of(N)
+    return ops.PackedMatrix(weight.detach().bfloat16(), None if bias is None else bias.detach().float(), N, 9 * Cin, n_pad, 9 * Cin)
+
+
+def _conv3x3(A, pm, M, conv, act, out_f32, out_bf16):
+    """3x3 convolution on a bf16 NHWC tensor: optional nearest x2 upsample folded into the read, reflect or zero padding,
+    bias, ReLU; bf16 NHWC [M, n_pad] or fp32 NCHW [B, n_real, H, W] output (include/mst_b200.h, MstGemm a_mode CONV3X3)."""
+    H, W, Cin, up = conv["H"], conv["W"], conv["Cin"], bool(conv.get("upsample", False))
+    B = M // (H * W)
+    hin, win = (H // 2, W // 2) if up else (H, W)
+    x = A.reshape(-1)[: B * hin * win * Cin].view(B, hin, win, Cin).float().permute(0, 3, 1, 2)
+    if up:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    x = F.pad(x, (1, 1, 1, 1), mode="reflect" if conv.get("pad_mode", ops.PAD_ZERO) == ops.PAD_REFLECT else "constant")
+    y = F.conv2d(x, pm.w.float(), pm.bias)
+    if act == ops.ACT_RELU:
+        y = torch.relu(y)
+    if conv.get("out_nchw"):
+        out_f32.copy_(y[:, : conv.get("n_real", pm.N)])
+    else:
+        out = out_bf16.reshape(-1)[: M * pm.n_pad].view(M, pm.n_pad)
+        out.zero_()
+        out[:, : pm.N].copy_(y.permute(0, 2, 3, 1).reshape(M, pm.N))
+
+
+def upsample2x_nhwc(x, y, B, H, W, C_):
+    src = x.reshape(-1)[: B * H * W * C_].view(B, H, W, C_)
+    y.reshape(-1)[: B * 4 * H * W * C_].view(B, 2 * H, 2 * W, C_).copy_(src.repeat_interleave(2, 1).repeat_interleave(2, 2))
+
+
+def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact=False):
+    """tv swin features[0]: Conv2d(3, 128, 4, stride 4) -> BHWC -> LayerNorm; optional fused norm1 of the first block."""
+    P = S // 4
+    t = F.layer_norm(F.conv2d(img[:B], w, b, stride=4).permute(0, 2, 3, 1), (128,), gamma, beta).reshape(B * P * P, 128)
+    x[: B * P * P].copy_(t)
+    if y16 is not None:
+        y16[: B * P * P].copy_(F.layer_norm(t, (128,), gamma1, beta1))
+
+
+def patch_merge_layernorm(x, gamma, beta, y, B, H, W, Cdim):
+    """tv PatchMerging (swin_transformer.py:35-87) up to the reduction: 2x2 neighbourhood concat [x00, x10, x01, x11] -> LN(4C)."""
+    t = x[: B * H * W].view(B, H, W, Cdim)
+    cat = torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1)
+    y[: B * (H // 2) * (W // 2)].copy_(F.layer_norm(cat, (4 * Cdim,), gamma, beta).reshape(-1, 4 * Cdim))
+
+
+def gemm(A, pm, M, *, lda=None, act=ops.ACT_NONE, res=None, mul=None, out_f32=None, out_bf16=None, ld_out32=None, ld_out16=None,
+         ld_res=None, conv=None, **kw):
     assert not kw, kw
+    if conv is not None:
+        assert res is None and mul is None
+        return _conv3x3(A, pm, M, conv, act, out_f32, out_bf16)
+    assert act == ops.ACT_NONE
     assert A.dtype == torch.bfloat16 and (out_f32 is not None or out_bf16 is not None)
     N, K = pm.N, pm.K
     x = _rows(A, M, K, K if lda is None else lda).float() @ pm.w.float().t()
@@ -147,6 +201,7 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
 
 
 def install(monkeypatch):
-    for name in ("pack_linear", "pack_mlp", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
-                 "instnorm_stats_padded", "instnorm_apply", "window_attention"):
+    for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
+                 "instnorm_stats_padded", "instnorm_apply", "window_attention", "upsample2x_nhwc", "patch_embed",
+                 "patch_merge_layernorm"):
         monkeypatch.setattr(ops, name, globals()[name])

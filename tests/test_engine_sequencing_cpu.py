@@ -117,3 +117,24 @@ def test_style_transformer_module_forward_passes_the_configuration_to_the_engine
             out = m(fc, fs, 2)
             ref = O.style_transformer(sd, fc, fs, 2, ws=7, sh=4, heads=8, **CONFIGS[name][1])
         assert ((out - ref).abs().max() / (ref.max() - ref.min())).item() <= FEAT_TOL, name
+
+
+@pytest.mark.parametrize("ws,size", [(8, 128), (7, 128), (8, 64)])
+def test_whole_inference_forward_sequencing(monkeypatch, ws, size):
+    """The complete inference path of MasterStyleTransferModel.forward -- Swin encoder (7x7 windows on zero-padded maps, patch
+    merging), style transformer, CNN decoder (reflect padding, folded and materialised upsampling, NCHW output) -- as the engine
+    sequences it, with every kernel replaced by its stand-in, against O.full_forward."""
+    import mastermetastyletransfer_b200 as mst
+    from mastermetastyletransfer_b200 import full_model, synthetic
+    engine_ops_mock.install(monkeypatch)
+    monkeypatch.setattr(full_model, "require_cuda", lambda *t: None)
+    m = mst.MasterStyleTransferModel(style_encoder_window_size=[ws, ws], style_decoder_window_size=[ws, ws])
+    synthetic.fill_state_dict_(m, 0).eval()
+    sd = {n: v.detach().clone() for n, v in m.state_dict().items()}
+    content, style = synthetic.synthetic_images(2, size, seed=0)
+    with torch.no_grad():
+        out = m(content, style, 1)
+        ref = O.full_forward(sd, content, style, 1, ws=ws, sh=4)
+    assert out.shape == ref.shape == (2, 3, size, size)
+    err = ((out - ref).abs().max() / (ref.max() - ref.min())).item()
+    assert err <= 2e-2, err
