@@ -1,8 +1,8 @@
 """CPU stand-ins for the C-ABI kernels the inference style transformer launches -- TEST INFRASTRUCTURE ONLY.
 
 `install(monkeypatch)` replaces the wrappers in `mastermetastyletransfer_b200.ops` that the inference engine (Swin encoder,
-style transformer, CNN decoder: `engine.swin_encode`, `engine.style_transformer_forward`, `engine.cnn_decoder_forward` and
-their weight holders) calls with torch-CPU restatements of each kernel's documented contract
+style transformer, CNN decoder, VGG-19 loss: `engine.swin_encode`, `engine.style_transformer_forward`,
+`engine.cnn_decoder_forward`, `engine.perceptual_loss_forward` and their weight holders) calls with torch-CPU restatements of each kernel's documented contract
 (include/mst_b200.h): same arguments, same in-place buffer semantics, bf16 tensors really stored as bf16 (so the rounding
 points of the device path are reproduced: bf16 operands and weights, fp32 accumulation and residual streams).  What this
 checks is the HOST logic -- which kernel runs on which buffer in which order for each configuration -- on a machine
@@ -200,8 +200,44 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
         _rows(dst, T, C, ldo).copy_(O._from_windows(o, B, Hp, Wp, ws, shift)[:, :H, :W].reshape(T, C))
 
 
+def conv3x3_first(img, w, b, out, B, H, W, relu=True):
+    y = F.conv2d(img[:B], w, b, padding=1)
+    if relu:
+        y = torch.relu(y)
+    out.reshape(-1)[: B * H * W * 64].view(B, H, W, 64).copy_(y.permute(0, 2, 3, 1))
+
+
+def maxpool2x2(x, y, B, H, W, Cdim):
+    src = x.reshape(-1)[: B * H * W * Cdim].view(B, H, W, Cdim).float().permute(0, 3, 1, 2)
+    y.reshape(-1)[: B * (H // 2) * (W // 2) * Cdim].view(B, H // 2, W // 2, Cdim).copy_(F.max_pool2d(src, 2).permute(0, 2, 3, 1))
+
+
+def tap_stats(x, mean, var, B, T, Cdim, scratch=None):
+    m, v = _stats(x.reshape(-1)[: B * T * Cdim].float(), B, T, Cdim)
+    mean.copy_(m)
+    var.copy_(v)  # biased
+
+
+def content_term(fc, fo, mean_c, var_c, mean_o, var_o, B, T, Cdim, squared, partials):
+    norm = lambda f, m, v: (f.reshape(B, T, Cdim).float() - m.unsqueeze(1)) / torch.sqrt(v.unsqueeze(1) + 1e-5)
+    d = norm(fc, mean_c, var_c) - norm(fo, mean_o, var_o)
+    partials.zero_()
+    partials[0] = (d * d if squared else d.abs()).double().sum()
+
+
+def loss_finalize(taps, lam, squared_style, out3):
+    content = style = 0.0
+    for t in taps:
+        B, T, Cd = t["B"], t["T"], t["C"]
+        content = content + t["partials"].double().sum() / (B * T * Cd)
+        std = lambda v: torch.sqrt(v.double() * T / (T - 1))  # torch.std is unbiased
+        dm, ds = t["mean_s"].double() - t["mean_o"].double(), std(t["var_s"]) - std(t["var_o"])
+        style = style + ((dm * dm).mean() + (ds * ds).mean() if squared_style else dm.abs().mean() + ds.abs().mean())
+    out3.copy_(torch.stack([content + lam * style, content, style]).float())
+
+
 def install(monkeypatch):
     for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
                  "instnorm_stats_padded", "instnorm_apply", "window_attention", "upsample2x_nhwc", "patch_embed",
-                 "patch_merge_layernorm"):
+                 "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "tap_stats", "content_term", "loss_finalize"):
         monkeypatch.setattr(ops, name, globals()[name])

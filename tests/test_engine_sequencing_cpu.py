@@ -138,3 +138,22 @@ def test_whole_inference_forward_sequencing(monkeypatch, ws, size):
     assert out.shape == ref.shape == (2, 3, size, size)
     err = ((out - ref).abs().max() / (ref.max() - ref.min())).item()
     assert err <= 2e-2, err
+
+
+@pytest.mark.parametrize("squared", [False, True])
+def test_perceptual_loss_sequencing(monkeypatch, squared):
+    """engine.perceptual_loss_forward (VGG-19 taps of content | style | output as one batch, tap statistics, content term,
+    finalize) with the kernels replaced by their stand-ins, against the oracle's get_overall_loss (loss.py:201-262).
+    Tolerance: 1e-2 relative (bf16 taps; BASELINE's 1e-3 is for the device kernels' own accumulation order, checked on the B200)."""
+    from mastermetastyletransfer_b200 import synthetic
+    engine_ops_mock.install(monkeypatch)
+    vgg = synthetic.build_vgg19_to_relu5_1()
+    synthetic.fill_state_dict_(vgg, 0, prefix="vgg.")
+    sd = {k: v.detach().clone() for k, v in vgg.state_dict().items()}
+    content, style = synthetic.synthetic_images(2, 64, seed=3)
+    output, _ = synthetic.synthetic_images(2, 64, seed=4)
+    with torch.no_grad():
+        w = engine.VggWeights(sd, prefix="")
+        out3 = engine.perceptual_loss_forward(w, content, style, output, 10.0, squared, squared, engine.Workspace(torch.device("cpu")))
+        ref = torch.stack(O.overall_loss(sd, content, style, output, 10.0, squared, squared))
+    assert torch.allclose(out3, ref, rtol=1e-2), (out3, ref)
