@@ -28,7 +28,8 @@ class VGG19_custom(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
         if torch.is_grad_enabled() and x.requires_grad:
-            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, scope)")
+            raise NotImplementedError("gradients flow through custom_loss.forward (its autograd node runs the VGG adjoint kernels, "
+                                      "autograd_fns.perceptual_loss_apply); a bare feature_extractor_model(x) call records no tape")
         with torch.no_grad():
             w = packed_weights(self, engine.VggWeights)
             ws = workspace_of(self, x.device)
