@@ -102,11 +102,34 @@ class MasterStyleTransferModel(nn.Module):
         self.decoder = Decoder(channel_dim=style_decoder_dim, initializer=decoder_initializer)
 
         if style_transformer_load_pretrained_weights and not direct_pretrained_style_transformer_path:
-            raise NotImplementedError("Swin-block -> style-transformer weight mapping is out of scope (SURVEY.md section 2 row 8)")
+            self.load_pretained_weights_to_style_transformer(pretrained_weights_path=style_transformer_pretrained_weights_path)
         if direct_pretrained_style_transformer_path != '':
             self.style_transformer.load_state_dict(torch.load(direct_pretrained_style_transformer_path))
         if direct_pretrained_decoder_path != '':
             self.decoder.load_state_dict(torch.load(direct_pretrained_decoder_path))
+
+    def load_pretained_weights_to_style_transformer(self, pretrained_weights_path: str):
+        """Initialise every attention / MLP of the (7x7-window) style transformer from one pretrained Swin block
+        (reference full_model.py:160-212, same method name -- typo included -- and error behaviour)."""
+        from .pretrained_weights import load_block_into_style_transformer
+        if pretrained_weights_path is None:
+            raise ValueError("Please provide the path of the pretrained weights")
+        if self.style_decoder_use_regular_MHA_instead_of_Swin_at_the_end:
+            raise ValueError("The pretrained weights are not compatible with the current model configuration. Please set the "
+                             "style_decoder_use_regular_MHA_instead_of_Swin_at_the_end to False")
+        unchanged = load_block_into_style_transformer(
+            self.style_transformer, pretrained_weights_path,
+            encoder_dim=self.style_encoder_dim, decoder_dim=self.style_decoder_dim,
+            encoder_mlp_ratio=self.style_decoder_mlp_ratio,  # (sic: the reference passes the decoder's ratio twice, :180-181)
+            decoder_mlp_ratio=self.style_decoder_mlp_ratio,
+            encoder_window_size=self.style_encoder_window_size, decoder_window_size=self.style_decoder_window_size,
+            encoder_qkv_bias=self.style_encoder_qkv_bias, decoder_qkv_bias=self.style_decoder_qkv_bias,
+            encoder_proj_bias=self.style_encoder_proj_bias, decoder_proj_bias=self.style_decoder_proj_bias,
+            encoder_norm_layer=self.style_encoder_norm_layer, decoder_norm_layer=self.style_decoder_norm_layer,
+            decoder_exclude_MLP_after_Fcs_self_MHA=self.style_decoder_exclude_MLP_after_Fcs_self_MHA)
+        for key in unchanged:
+            print(f"PRETRAINED WEIGHTS ARE NOT LOADED CORRECTLY FOR KEY: {key}")
+        return unchanged
 
     def forward(self, content_image: Tensor, style_image: Tensor, transformer_layer_count: int = 1) -> Tensor:
         """[B,3,S,S] x2 -> stylised [B,3,S,S] (reference :214-226), one fused pass over shared buffers."""

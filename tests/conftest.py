@@ -60,3 +60,23 @@ def alternate_inputs():
     content, style = synthetic.synthetic_images(2, 128, seed=0)
     with torch.no_grad():
         return O.swin_encoder(sd, content, "swin_encoder."), O.swin_encoder(sd, style, "swin_encoder.")
+
+
+def seeded_swin_block():
+    """A stand-in for the pretrained Swin block of codes/load_pretrained_weights_to_style_transformer.py:17-47: the timm keys,
+    shapes and dtypes of `swin_base_patch4_window7_224` stage 2 (dim 256, 8 heads, window 7), every tensor seeded by its name."""
+    import torch
+    from mastermetastyletransfer_b200 import synthetic
+    shapes = {"0.weight": (256,), "0.bias": (256,), "1.relative_position_bias_table": (169, 8), "1.qkv.weight": (768, 256),
+              "1.qkv.bias": (768,), "1.proj.weight": (256, 256), "1.proj.bias": (256,), "3.weight": (256,), "3.bias": (256,),
+              "4.fc1.weight": (1024, 256), "4.fc1.bias": (1024,), "4.fc2.weight": (256, 1024), "4.fc2.bias": (256,)}
+    block = {k: torch.randn(s, generator=synthetic._gen(7, "block." + k)) for k, s in shapes.items()}
+    ys, xs = torch.meshgrid(torch.arange(7), torch.arange(7), indexing="ij")
+    ys, xs = ys.reshape(-1), xs.reshape(-1)
+    block["1.relative_position_index"] = (ys[:, None] - ys[None, :] + 6) * 13 + (xs[:, None] - xs[None, :] + 6)  # [49,49] int64 (timm)
+    return block
+
+
+def fingerprint(t):
+    t = t.detach().double().reshape(-1)
+    return [float(t.sum()), float(t[0]), float(t[-1]), int(t.numel())]
