@@ -179,15 +179,18 @@ def window_attention(xq: Tensor, xk: Tensor, xv: Tensor, wq, bq, wk, bk, wv, bv,
     return _from_windows(o, B, H, W, ws, shift)
 
 
-def instance_norm_bhwc(x: Tensor, eps: float = 1e-5) -> Tensor:
-    """nn.InstanceNorm2d(C, affine=False) on a BHWC tensor (codes/style_transformer.py:986,1056-1057)."""
+def instance_norm_bhwc(x: Tensor, eps: float = 1e-5, affine: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
+    """nn.InstanceNorm2d(C) on a BHWC tensor (codes/style_transformer.py:986,1056-1057); affine = (weight, bias) of the
+    decoder_use_instance_norm_with_affine variant (:982-984)."""
     mean = x.mean(dim=(1, 2), keepdim=True)
     var = x.var(dim=(1, 2), unbiased=False, keepdim=True)
-    return (x - mean) / torch.sqrt(var + eps)
+    y = (x - mean) / torch.sqrt(var + eps)
+    return y if affine is None else y * affine[0] + affine[1]
 
 
 def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk, wvs, bvs, wvh, bvh, wp, bp,
-                       table: Tensor, ws: int, shift: int, heads: int, key_in_after_linear: bool = True) -> Tuple[Tensor, Tensor]:
+                       table: Tensor, ws: int, shift: int, heads: int, key_in_after_linear: bool = True,
+                       affine_q=None, affine_k=None) -> Tuple[Tensor, Tensor]:
     """codes/style_transformer.py:414-611 (a8), default flags: IN(q) again (:468), no Q projection
     (:511-514), IN over the whole (padded) map of Wk*K (:520-530), one softmax for both values,
     the same proj for sigma and mu (:575-607).
@@ -195,9 +198,9 @@ def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk,
     instance-normalised once more on the UNPADDED map before Wk and Wk*K is used as it is (padded tokens = bk)."""
     B, H, W, C = xq.shape
     Hp, Wp = padded_dims(H, W, ws)
-    q = _to_windows(instance_norm_bhwc(xq), ws, shift)
+    q = _to_windows(instance_norm_bhwc(xq, affine=affine_q), ws, shift)  # affine_q / affine_k: the SAME modules as at :1052-1054
     if not key_in_after_linear:
-        xk = instance_norm_bhwc(xk)
+        xk = instance_norm_bhwc(xk, affine=affine_k)
     k = F.linear(_to_windows(xk, ws, shift), wk, bk)
     vs = F.linear(_to_windows(xvs, ws, shift), wvs, bvs)
     vh = F.linear(_to_windows(xvh, ws, shift), wvh, bvh)
@@ -206,7 +209,7 @@ def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk,
         gm = window_gather_map(H, W, ws, shift).reshape(-1)
         kmap = torch.empty(B, Hp * Wp, C)
         kmap[:, gm] = k.reshape(B, -1, C)
-        kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C)).reshape(B, Hp * Wp, C)
+        kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C), affine=affine_k).reshape(B, Hp * Wp, C)
         k = kmap[:, gm].reshape(k.shape)
     p = _softmax_probs(q, k, heads, _bias_from_table(table, ws), shift_mask(H, W, ws, shift), B)
     sig = F.linear(_apply_probs(p, vs, heads), wp, bp)
@@ -264,8 +267,35 @@ def style_encoder(sd: SD, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, 
     return key, scale, shift_t
 
 
+def _global_sigma_mu(sd: SD, query: Tensor, key: Tensor, scale: Tensor, shift_t: Tensor, pre: str, key_in_after_linear: bool):
+    """decoder_use_regular_MHA_instead_of_Swin_at_the_end (codes/style_transformer.py:1063-1119): ONE head over all T = H*W
+    tokens of an image, q = IN(Query) * C^-0.5 (no Q projection), k / v_scale / v_shift through linear_transformation_*, separate
+    proj_sigma / proj_mu.  The reference feeds [B, C, T] tensors to nn.InstanceNorm2d, which reads a 3-D input as ONE unbatched
+    (C', H', W') image: the statistics are taken over (C, T) JOINTLY per batch element, not per channel -- restated as it is."""
+    B, H, W, C = query.shape
+    lin = lambda x, n: F.linear(x, sd[pre + n + ".weight"], sd[pre + n + ".bias"])
+
+    def joint_norm(x):  # x [B, T, C]
+        mean = x.mean(dim=(1, 2), keepdim=True)
+        var = x.var(dim=(1, 2), unbiased=False, keepdim=True)
+        return (x - mean) / torch.sqrt(var + 1e-5)
+
+    q, k = query.reshape(B, H * W, C), key.reshape(B, H * W, C)
+    vs, vh = scale.reshape(B, H * W, C), shift_t.reshape(B, H * W, C)
+    if key_in_after_linear:
+        k = joint_norm(lin(k, "linear_transformation_Key"))
+    else:
+        k = lin(joint_norm(k), "linear_transformation_Key")
+    q = joint_norm(q) * (C ** -0.5)
+    p = torch.softmax(q @ k.transpose(-2, -1), dim=-1)
+    sigma = lin(p @ lin(vs, "linear_transformation_Scale"), "proj_sigma")
+    mu = lin(p @ lin(vh, "linear_transformation_Shift"), "proj_mu")
+    return sigma.reshape(B, H, W, C), mu.reshape(B, H, W, C)
+
+
 def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tensor, ws: int, sh: int, heads: int,
-                  pre: str = "decoder.", sd_scales=None, key_in_after_linear: bool = True, exclude_mlp: bool = False):
+                  pre: str = "decoder.", sd_scales=None, key_in_after_linear: bool = True, exclude_mlp: bool = False,
+                  affine_in: bool = False, regular_mha: bool = False):
     """codes/style_transformer.py:1045-1059,1123-1128 default branch (stochastic depth at :390,392,1125).
     exclude_mlp=True (decoder_exclude_MLP_after_Fcs_self_MHA, :339-343,365,389-392): the self-attention block has no
     norm2 / mlp; key_in_after_linear: see sigma_mu_attention."""
@@ -275,8 +305,14 @@ def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tens
     x = fcs + _sd(window_attention(n1, n1, n1, *_attn_weights(sd, b + "attn."), ws, sh, heads), sd_scales, 6)
     if not exclude_mlp:
         x = x + _sd(mlp(F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"]), sd, b + "mlp."), sd_scales, 7)
-    query_in = instance_norm_bhwc(x)
-    key_in = instance_norm_bhwc(key)
+    if regular_mha:
+        sigma, mu = _global_sigma_mu(sd, x, key, scale, shift_t, pre, key_in_after_linear)
+        x = x * sigma + mu
+        return x + _sd(mlp(x, sd, pre + "last_MLP."), sd_scales, 8)
+    aq = (sd[pre + "instance_norm_Query.weight"], sd[pre + "instance_norm_Query.bias"]) if affine_in else None
+    ak = (sd[pre + "instance_norm_Key.weight"], sd[pre + "instance_norm_Key.bias"]) if affine_in else None
+    query_in = instance_norm_bhwc(x, affine=aq)
+    key_in = instance_norm_bhwc(key, affine=ak)
     m = pre + "decoder_MHA_for_sigma_and_mu."
     sigma, mu = sigma_mu_attention(query_in, key_in, scale, shift_t,
                                    sd[m + "Wk.weight"], sd[m + "Wk.bias"],
@@ -284,14 +320,14 @@ def style_decoder(sd: SD, fcs: Tensor, key: Tensor, scale: Tensor, shift_t: Tens
                                    sd[m + "Wv_shift.weight"], sd[m + "Wv_shift.bias"],
                                    sd[m + "proj.weight"], sd[m + "proj.bias"],
                                    sd[m + "relative_position_bias_table"], ws, sh, heads,
-                                   key_in_after_linear=key_in_after_linear)
+                                   key_in_after_linear=key_in_after_linear, affine_q=aq, affine_k=ak)
     x = x * sigma + mu
     return x + _sd(mlp(x, sd, pre + "last_MLP."), sd_scales, 8)
 
 
 def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, sh: int = 4, heads: int = 8,
                       sd_scales=None, processed_key: bool = True, key_in_after_linear: bool = True,
-                      exclude_mlp: bool = False) -> Tensor:
+                      exclude_mlp: bool = False, affine_in: bool = False, regular_mha: bool = False) -> Tensor:
     """codes/style_transformer.py:1229-1245: Scale=Shift=Fs, k times the same weights.
     sd_scales: optional [k, 9, B] train-mode stochastic-depth factors (None = eval).
     processed_key / key_in_after_linear / exclude_mlp: the reference's alternate configurations, see
@@ -301,7 +337,8 @@ def style_transformer(sd: SD, fc: Tensor, fs: Tensor, k: int = 1, ws: int = 8, s
         sc = None if sd_scales is None else sd_scales[l]
         fs, scale, shift_t = style_encoder(sd, fs, scale, shift_t, ws, sh, heads, sd_scales=sc, processed_key=processed_key)
         fc = style_decoder(sd, fc, fs, scale, shift_t, ws, sh, heads, sd_scales=sc,
-                           key_in_after_linear=key_in_after_linear, exclude_mlp=exclude_mlp)
+                           key_in_after_linear=key_in_after_linear, exclude_mlp=exclude_mlp, affine_in=affine_in,
+                           regular_mha=regular_mha)
     return fc
 
 

@@ -38,13 +38,25 @@ ALTERNATE_CONFIGS = {
 ALTERNATE_CONFIGS["all_three"] = ({k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[0].items()},
                                   {k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[1].items()})
 
+# Variants without kernels yet (the product builds the modules -- same state_dict layout -- and refuses to run them): the
+# oracle is pinned to the real reference for them too, so the kernels of a later round have a checker.
+ORACLE_ONLY_CONFIGS = {
+    "affine_in": (dict(decoder_use_instance_norm_with_affine=True), dict(affine_in=True)),
+    "affine_in_key_before": (dict(decoder_use_instance_norm_with_affine=True, decoder_use_Key_instance_norm_after_linear_transformation=False),
+                             dict(affine_in=True, key_in_after_linear=False)),
+    "regular_mha": (dict(decoder_use_regular_MHA_instead_of_Swin_at_the_end=True), dict(regular_mha=True)),
+    "regular_mha_key_before": (dict(decoder_use_regular_MHA_instead_of_Swin_at_the_end=True,
+                                    decoder_use_Key_instance_norm_after_linear_transformation=False),
+                               dict(regular_mha=True, key_in_after_linear=False)),
+}
+
 
 def alternate_style_transformer(name: str, ws: int):
     """The drop-in StyleTransformer built with one of ALTERNATE_CONFIGS and the seeded (name-keyed) weights."""
     from mastermetastyletransfer_b200 import StyleTransformer, synthetic
     m = StyleTransformer(encoder_dim=256, decoder_dim=256, encoder_num_heads=8, decoder_num_heads=8,
                          encoder_window_size=[ws, ws], decoder_window_size=[ws, ws], encoder_shift_size=[4, 4],
-                         decoder_shift_size=[4, 4], **ALTERNATE_CONFIGS[name][0])
+                         decoder_shift_size=[4, 4], **{**ALTERNATE_CONFIGS, **ORACLE_ONLY_CONFIGS}[name][0])
     synthetic.fill_state_dict_(m, 0)
     return m.eval()
 
