@@ -428,6 +428,49 @@ def vgg_taps(sd: SD, x: Tensor, pre: str = "") -> List[Tensor]:
     return taps  # type: ignore[return-value]
 
 
+def vgg_bn_layout(last: int = 43):
+    """(kind, index) of vgg19_bn.features[:43] (tv models/vgg.py cfg "E" with batch norm: conv-bn-relu triplets and max-pools;
+    codes/utils.py:34-36 cuts at 43 = relu5_1)."""
+    cfg = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512, 512, 512, 512, "M"]
+    out, i = [], 0
+    for v in cfg:
+        if v == "M":
+            out.append(("pool", i))
+            i += 1
+        else:
+            out += [("conv", i), ("bn", i + 1), ("relu", i + 2)]
+            i += 3
+    return [e for e in out if e[1] < last]
+
+
+VGG_BN_TAPS = {9: 0, 16: 1, 29: 2, 42: 3}  # last ReLU of features[:10], [10:17], [17:30], [30:43] (codes/loss.py:49-63)
+
+
+def vgg_bn_taps(sd: SD, x: Tensor, pre: str = "", training: bool = True, eps: float = 1e-5) -> List[Tensor]:
+    """codes/loss.py:41-63 VGG19_custom_with_batch_norm.  training=True is what the reference's scripts run: custom_loss is never
+    put in eval mode (train.py:249-254), so every BatchNorm2d normalises with the statistics of the batch it is given -- biased
+    variance over (N,H,W), content / style / output images in three separate calls (loss.py:223-225) -- and the running
+    statistics only matter after an explicit .eval()."""
+    taps: List[Optional[Tensor]] = [None] * 4
+    for kind, i in vgg_bn_layout():
+        if kind == "pool":
+            x = F.max_pool2d(x, 2)
+        elif kind == "conv":
+            x = F.conv2d(x, sd[f"{pre}{i}.weight"], sd[f"{pre}{i}.bias"], padding=1)
+        elif kind == "bn":
+            if training:
+                mean, var = x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3), unbiased=False)
+            else:
+                mean, var = sd[f"{pre}{i}.running_mean"], sd[f"{pre}{i}.running_var"]
+            x = (x - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + eps)
+            x = x * sd[f"{pre}{i}.weight"].view(1, -1, 1, 1) + sd[f"{pre}{i}.bias"].view(1, -1, 1, 1)
+        else:
+            x = torch.relu(x)
+            if i in VGG_BN_TAPS:
+                taps[VGG_BN_TAPS[i]] = x
+    return taps  # type: ignore[return-value]
+
+
 def _in_nchw(x: Tensor, eps: float = 1e-5) -> Tensor:
     m = x.mean(dim=(2, 3), keepdim=True)
     v = x.var(dim=(2, 3), unbiased=False, keepdim=True)
@@ -454,10 +497,15 @@ def style_loss(taps_s: List[Tensor], taps_o: List[Tensor], squared: bool = False
 
 
 def overall_loss(vgg_sd: SD, content: Tensor, style: Tensor, output: Tensor, lam: float = 10.0,
-                 squared_content: bool = False, squared_style: bool = False):
-    """codes/loss.py:201-262: total = content + lambda*style; returns (total, content, style)."""
+                 squared_content: bool = False, squared_style: bool = False, batchnorm: Optional[str] = None):
+    """codes/loss.py:201-262: total = content + lambda*style; returns (total, content, style).
+    batchnorm: None = vgg19 (default); "train" / "eval" = the use_vgg19_with_batchnorm variant in that module mode."""
     assert content.shape == style.shape == output.shape, "All images should be in the exact same shape"
-    tc, ts, to = vgg_taps(vgg_sd, content), vgg_taps(vgg_sd, style), vgg_taps(vgg_sd, output)
+    if batchnorm is None:
+        taps = vgg_taps
+    else:
+        taps = lambda sd_, x: vgg_bn_taps(sd_, x, training=batchnorm == "train")  # noqa: E731
+    tc, ts, to = taps(vgg_sd, content), taps(vgg_sd, style), taps(vgg_sd, output)
     lc = content_loss(tc, to, squared_content)
     ls = style_loss(ts, to, squared_style)
     return lc + lam * ls, lc, ls

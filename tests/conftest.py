@@ -92,3 +92,18 @@ def seeded_swin_block():
 def fingerprint(t):
     t = t.detach().double().reshape(-1)
     return [float(t.sum()), float(t[0]), float(t[-1]), int(t.numel())]
+
+
+def seeded_vgg19_bn():
+    """vgg19_bn.features[:43] (what codes/utils.py:34-36 pickles for use_vgg19_with_batchnorm), random architecture with every
+    floating-point state_dict entry seeded by its name; running_var made positive."""
+    import torch
+    from torchvision.models import vgg19_bn
+    from mastermetastyletransfer_b200 import synthetic
+    seq = torch.nn.Sequential(*list(vgg19_bn(weights=None).features)[0:43])
+    synthetic.fill_state_dict_(seq, 0, prefix="vggbn.")
+    with torch.no_grad():
+        for m in seq:
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_var.copy_(m.running_var.abs() + 0.5)
+    return seq

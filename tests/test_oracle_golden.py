@@ -158,3 +158,21 @@ def test_alternate_configurations_against_reference_goldens(golden_dir, name, ws
         with torch.no_grad():
             out = O.style_transformer(sd, fc, fs, k, ws=ws, sh=4, heads=8, **{**ALTERNATE_CONFIGS, **ORACLE_ONLY_CONFIGS}[name][1])
         assert close(out[:, ::2, ::2, ::4], gold[f"{name}_ws{ws}_k{k}"]), (name, ws, k)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_vgg_bn_loss_variant_against_reference_fixture(golden_dir, mode):
+    """use_vgg19_with_batchnorm (codes/loss.py:41-63).  The reference's scripts leave the loss module in train
+    mode, so BatchNorm uses the statistics of each batch it is given; the product has no kernels for it yet and refuses."""
+    from conftest import seeded_vgg19_bn
+    import mastermetastyletransfer_b200 as mst
+    gold = json.load(open(os.path.join(golden_dir, "vgg_bn_loss.json")))
+    sd = {k: v.detach().clone() for k, v in seeded_vgg19_bn().state_dict().items()}
+    assert len(sd) == gold["keys"]
+    content, style = synthetic.synthetic_images(2, 64, seed=3)
+    output, _ = synthetic.synthetic_images(2, 64, seed=4)
+    with torch.no_grad():
+        got = [t.item() for t in O.overall_loss(sd, content, style, output, 10.0, batchnorm=mode)]
+    assert got == pytest.approx(gold[mode], rel=1e-4)
+    with pytest.raises(NotImplementedError):
+        mst.custom_loss("/nonexistent", use_vgg19_with_batchnorm=True)
