@@ -177,7 +177,7 @@ class FusedAdam:
     @torch.no_grad()
     def step(self):
         self.step_count += 1
-        for g, st in zip(self.param_groups, self.state):
+        for gi, (g, st) in enumerate(zip(self.param_groups, self.state)):
             if not g["params"]:
                 continue
             grads = []
@@ -192,7 +192,7 @@ class FusedAdam:
             n = sum(p.numel() for p in g["params"])
             tb = st["table"].tb
             if self.capturable:
-                ds = self._dev_state[self.param_groups.index(g)]
+                ds = self._dev_state[gi]  # (not list.index: comparing group dicts would compare parameter tensors)
                 ops._launch("mst_adam_step", lambda: _lib.lib().mst_adam_step_dev(C.byref(tb), float(g["betas"][0]), float(g["betas"][1]),
                                                                                  float(g["eps"]), float(g["weight_decay"]), ds.data_ptr(), 1,
                                                                                  ops._stream()), nbytes=28.0 * n)
