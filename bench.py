@@ -9,11 +9,18 @@ batch of 32 (images are independent: no data-path collective, weak scaling).
 
 `value`  : whole-job images/s with inputs resident in HBM, one CUDA-graph launch per step, timed with
            CUDA events between barrier+synchronize pairs, max over ranks.
-`e2e`    : same metric through the public host API (GraphedStylizer.stylize_host): pinned host images
-           in -> H2D -> graph -> D2H of the stylised images, every step, host-synchronised per step.
-`roofline`: the dominant kernel (gemm_tc_kernel: every projection / MLP / convolution) -- algorithmic
-           FLOPs of its launches / their summed CUDA-event durations, against the measured bf16 peak.
+`e2e`    : same metric through the public host API at the reference's own image boundary (test_model.py:39-48,207):
+           pinned uint8 HWC images in -> H2D -> ToTensor/Normalize kernel -> graph -> clip*255 kernel -> D2H of the uint8
+           stylised images, every step (GraphedStylizer.stylize_many(u8=True), copies overlapped with the previous / next
+           graph).  `e2e_f32` is the same through fp32 NCHW pinned tensors (4x the bytes).
+`roofline`: the tensor-core kernel family with the largest share of the step (chosen from the measured per-family times) --
+           algorithmic FLOPs of its launches / their summed CUDA-event durations, against the measured sustained bf16 peak.
 `cpu_baseline`: the CPU oracle port of the reference timed on this box's host cores (bounded sample).
+`gpu_eager_baseline`: the reference's ops (the oracle restatement: plain torch, fp32, and with TF32 matmuls) on the same B200,
+           eager -- SURVEY 8d's "beat this" number next to the CPU one.
+`config5`: BASELINE configs[4] (512x512, batch 16/GPU) device-resident and end-to-end images/s in the same line.
+`loss_forward`: the VGG-19 loss forward at batch 32 and 8: HBM GB/s of the reduction kernels against the measured copy rate.
+`summary`: the headline numbers again, LAST in the line (a truncated tail of stdout still shows them).
 `--impl reference`: the reference's CPU implementation of the path (its oracle port: the reference is
            Python and /root/reference does not exist on the GPU box), all host threads, bounded sample.
 """
@@ -144,7 +151,9 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
     content, style = synthetic.synthetic_images(batch, size, seed=rank)
     style = style[:1].repeat(batch, 1, 1, 1)  # one style image repeated (train_only_inner_loop.py:491-496)
     content, style = content.to(dev), style.to(dev)
+    from mastermetastyletransfer_b200.parallel import max_over_ranks
     out = {}
+    identical = True
     for name, dp in (("train_step", True), ("train_step_eager", True), ("meta_step", False), ("meta_step_eager", False)):
         is_graphed = name in ("train_step", "meta_step")
         trainer = InnerLoopTrainer(model, loss_fn, inner_lr=1e-4, data_parallel=dp and world > 1, capturable=is_graphed)
@@ -168,11 +177,19 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
             last = run()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = ms.item()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps, dev)
         gf = TRAIN_GF_PER_SAMPLE.get(layers)
+        if world > 1 and is_graphed:
+            # multi-GPU self-check (tests/test_gpu_multi.py needs >= 2 GPUs and is skipped on a 1-GPU test box): after the timed
+            # steps every rank must hold bit-identical parameters -- omega after data-parallel steps (same averaged gradient, same
+            # Adam), theta after meta iterations (same averaged Reptile delta).  Checksums: per-tensor sum and sum of squares in
+            # fp64, MAX and MIN over ranks must coincide.
+            ps = trainer.params if dp else trainer._theta
+            chk = torch.stack([torch.stack([p.detach().double().sum(), (p.detach().double() ** 2).sum()]) for p in ps]).flatten()
+            hi, lo = chk.clone(), chk.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            identical = identical and bool(torch.equal(hi, lo))
         out[name] = {"ms_per_step": ms, "samples_per_s": world * batch / (ms / 1e3), "batch_per_gpu": batch, "size": size,
                      "layers": layers, "n_gpus": world, "launches_per_step": (ops.launch_count - n0) // steps + (graphed.launches if is_graphed else 0),
                      "tflops": (gf * 1e9 * batch / (ms * 1e9)) if gf and size == 256 else None,
@@ -181,6 +198,80 @@ def bench_training(dev, rank: int, world: int, steps: int, warmup: int, batch: i
                                     "all-reduce of the 4.30 M fp32 (omega - theta) delta per outer iteration") if world > 1 else "none (1 rank)",
                      "timed": ("one CUDA-graph replay per inner step (training.GraphedTrainStep)" if is_graphed else
                                "eager launches through the C ABI (no CUDA graph)") + ", CUDA events, max over ranks"}
+    out["replicas_identical"] = identical if world > 1 else None  # None: one rank, nothing to compare
+    return out
+
+
+def gpu_eager_baseline(model, content, style, layers, dev, iters: int = 5):
+    """The reference's operator sequence (the oracle restatement: plain torch ops, fp32 parameters) run EAGERLY on this GPU:
+    fp32 (cuBLAS/cuDNN fp32 math) and with TF32 tensor-core matmuls/convs allowed -- what a user of the reference gets on a B200
+    without this library.  Not on the product path: bench.py's baseline leg only."""
+    from oracle import master_oracle as O
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    out = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            for _ in range(2):
+                O.full_forward(sd, content, style, layers)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                O.full_forward(sd, content, style, layers)
+            b.record()
+            torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / iters
+        out[name] = {"value": content.shape[0] / (ms / 1e3), "unit": "images/s", "ms_per_step": ms}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["what"] = f"oracle/master_oracle.full_forward (torch eager ops of the reference) on cuda, batch {content.shape[0]}, {iters} timed forwards"
+    return out
+
+
+def bench_loss_forward(dev, hbm_gbs: float, size: int = 256):
+    """VGG-19 content/style loss forward (custom_loss.forward, rows a15-a18) at batch 32 and 8: whole-call milliseconds and the
+    HBM rate of the reduction kernels (tap statistics incl. their finalisation, content term) summed over the four taps, from
+    CUDA events around every launch; algorithmic bytes = each bf16 tap tensor read once per kernel."""
+    from mastermetastyletransfer_b200 import ops, synthetic
+    from mastermetastyletransfer_b200.loss import custom_loss
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.to(dev).eval()
+    out = {}
+    for B in (32, 8):
+        content, style = synthetic.synthetic_images(B, size, seed=3)
+        outimg, _ = synthetic.synthetic_images(B, size, seed=4)
+        c, s, o = content.to(dev), style.to(dev), outimg.to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                loss_fn(c, s, o, output_content_and_style_loss=True)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                loss_fn(c, s, o, output_content_and_style_loss=True)
+            b.record()
+            torch.cuda.synchronize(dev)
+            with ops.timing() as rec:
+                loss_fn(c, s, o, output_content_and_style_loss=True)
+            torch.cuda.synchronize(dev)
+        fam = {}
+        for name, flops, nbytes, e0, e1, _d in rec:
+            f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+            f["launches"] += 1
+            f["ms"] += e0.elapsed_time(e1)
+            f["bytes"] += nbytes
+            f["flops"] += flops
+        red = {k: {"launches": v["launches"], "us": round(1e3 * v["ms"], 1), "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1),
+                   "frac_of_hbm": round(v["bytes"] / (v["ms"] * 1e6) / hbm_gbs, 3)}
+               for k, v in fam.items() if k in ("tap_stats_kernel", "content_term_kernel", "loss_finalize_kernel") and v["bytes"]}
+        conv_ms = sum(v["ms"] for k, v in fam.items() if v["flops"])
+        conv_fl = sum(v["flops"] for k, v in fam.items() if v["flops"])
+        out[f"batch{B}"] = {"ms_per_call": a.elapsed_time(b) / 5, "reductions": red,
+                            "vgg_convs": {"ms": round(conv_ms, 3), "tflops": round(conv_fl / (conv_ms * 1e9), 1) if conv_ms else None},
+                            "roofline_hbm": {"peak_gbs": hbm_gbs, "bytes": "each bf16 tap tensor read once per kernel launch"}}
     return out
 
 
@@ -195,6 +286,7 @@ def main():
     ap.add_argument("--layers", type=int, default=1)
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the secondary training-step measurement (0 = skip)")
+    ap.add_argument("--config5", type=int, default=1, help="also measure BASELINE configs[4] (512x512, batch 16) in the same run")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that nothing a native
     # library prints (NCCL's version banner goes to stdout whatever NCCL_DEBUG_FILE says on some boxes) can end up in front of it
@@ -222,6 +314,8 @@ def main():
         ms = 1e3 * sum(times) / len(times)
         value = cpu_batch / (ms / 1e3)
         sample = f"{steps} steps of batch {cpu_batch} at {args.size}x{args.size} (CPU oracle port of the reference, fp32, {threads} threads)"
+        config["cpu_sample_batch"] = cpu_batch  # the CPU arm times a bounded sample of the workload: batch 4 (1 at 512x512) per step
+        config["workload"] += f" -- CPU arm: bounded sample, batch {cpu_batch} per step"
         emit(json.dumps({
             "impl": "reference", "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -247,79 +341,70 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from mastermetastyletransfer_b200.parallel import max_over_ranks
+
     model = MasterStyleTransferModel()
     synthetic.fill_state_dict_(model, 0)
     model = model.eval().to(dev)
-    content, style = synthetic.synthetic_images(batch, args.size, seed=rank)
-    runner = GraphedStylizer(model, batch, args.size, args.layers, dev)
-    runner.load(content.to(dev), style.to(dev))
-    torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput ----------------
-    for _ in range(args.warmup):
-        runner.replay()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        runner.replay()
-    e1.record()
-    barrier()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if sampler else None
-    ms_step = ms_total.item() / args.steps
-    value = world * batch / (ms_step / 1e3)
+    def timed(fn, steps):
+        """device-side milliseconds for `fn()` (which enqueues `steps` steps), barrier + synchronize on both sides, max over ranks"""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b), dev)
 
-    # ---------------- end to end through the host API ----------------
-    # K distinct pinned host batches in, K pinned host results out, through GraphedStylizer.stylize_many (H2D of the
-    # next batch and D2H of the previous result overlap the running graph).  Also the un-pipelined single call.
-    nbuf = min(args.steps, 4)
-    host = [(content.pin_memory(), style.pin_memory(), torch.empty(batch, 3, args.size, args.size).pin_memory()) for _ in range(nbuf)]
-    batches = [host[i % nbuf] for i in range(args.steps)]
-    runner.stylize_many(batches[:args.warmup])
-    barrier()
-    e0.record()
-    runner.stylize_many(batches)
-    e1.record()
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch / (ms_e2e.item() / args.steps / 1e3)
-    c_pin, s_pin, o_pin = host[0]
-    h2d = c_pin.numel() * 4 + s_pin.numel() * 4
-    d2h = o_pin.numel() * 4
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        runner.stylize_host(c_pin, s_pin, o_pin)
-    e1.record()
-    barrier()
-    ms_single = e0.elapsed_time(e1) / args.steps
-    # the same through the uint8 image boundary of test_model.py (uint8 HWC in -> ToTensor + Normalize -> model -> clip*255 ->
-    # uint8 HWC out): two more kernels per step, a quarter of the host<->device bytes
-    gu = torch.Generator().manual_seed(100 + rank)
-    host8 = [(torch.randint(0, 256, (batch, args.size, args.size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
-              torch.randint(0, 256, (batch, args.size, args.size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
-              torch.empty(batch, args.size, args.size, 3, dtype=torch.uint8).pin_memory()) for _ in range(nbuf)]
-    batches8 = [host8[i % nbuf] for i in range(args.steps)]
-    runner.stylize_many(batches8[:args.warmup], u8=True)
-    barrier()
-    e0.record()
-    runner.stylize_many(batches8, u8=True)
-    e1.record()
-    barrier()
-    ms_u8 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_u8, op=dist.ReduceOp.MAX)
-    e2e_u8 = {"value": world * batch / (ms_u8.item() / args.steps / 1e3), "unit": "images/s", "ms_per_step": ms_u8.item() / args.steps,
-              "h2d_bytes_per_step": 2 * host8[0][0].numel(), "d2h_bytes_per_step": host8[0][2].numel(),
-              "api": "GraphedStylizer.stylize_many(u8=True): uint8 [B,S,S,3] pinned images in / out, pre- and post-processing on the device"}
+    def measure_stylization(size, nbatch, steps, warmup, sample_clocks):
+        """device-resident and end-to-end images/s of one (size, batch) workload; returns (record, runner, clocks)"""
+        content, style = synthetic.synthetic_images(nbatch, size, seed=rank)
+        runner = GraphedStylizer(model, nbatch, size, args.layers, dev)
+        runner.load(content.to(dev), style.to(dev))
+        torch.cuda.synchronize(dev)
+        for _ in range(warmup):
+            runner.replay()
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        ms = timed(lambda: [runner.replay() for _ in range(steps)], steps) / steps
+        clocks = sampler.stop() if sampler else None
+        rec = {"value": world * nbatch / (ms / 1e3), "ms_per_step": ms}
+        # ---- end to end, uint8 image boundary (test_model.py:39-48,207; SURVEY 8f-2): K distinct pinned host batches in, K pinned
+        #      host results out, H2D of the next batch and D2H of the previous result overlap the running graph
+        nbuf = min(steps, 4)
+        gu = torch.Generator().manual_seed(100 + rank)
+        host8 = [(torch.randint(0, 256, (nbatch, size, size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
+                  torch.randint(0, 256, (nbatch, size, size, 3), generator=gu, dtype=torch.uint8).pin_memory(),
+                  torch.empty(nbatch, size, size, 3, dtype=torch.uint8).pin_memory()) for _ in range(nbuf)]
+        batches8 = [host8[i % nbuf] for i in range(steps)]
+        runner.stylize_many(batches8[:warmup], u8=True)
+        ms8 = timed(lambda: runner.stylize_many(batches8, u8=True), steps) / steps
+        h2d8, d2h8 = 2 * host8[0][0].numel(), host8[0][2].numel()
+        rec["e2e"] = {"value": world * nbatch / (ms8 / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d8, "d2h_bytes_per_step": d2h8,
+                      "ms_per_step": ms8, "h2d_gbs_per_rank": h2d8 / (ms8 * 1e6), "d2h_gbs_per_rank": d2h8 / (ms8 * 1e6),
+                      "api": "GraphedStylizer.stylize_many(u8=True): pinned uint8 [B,S,S,3] images in / out (test_model.py's boundary), "
+                             "ToTensor+Normalize and clip*255 on the device, copies overlapped with the neighbouring graphs"}
+        c8, s8, o8 = host8[0]
+        ms8s = timed(lambda: [runner.stylize_host_u8(c8, s8, o8) for _ in range(steps)], steps) / steps
+        rec["e2e"]["single_blocking_call_ms"] = ms8s
+        # ---- the same through fp32 NCHW pinned tensors (4x the bytes)
+        host = [(content.pin_memory(), style.pin_memory(), torch.empty(nbatch, 3, size, size).pin_memory()) for _ in range(nbuf)]
+        batches = [host[i % nbuf] for i in range(steps)]
+        runner.stylize_many(batches[:warmup])
+        ms32 = timed(lambda: runner.stylize_many(batches), steps) / steps
+        c_pin, s_pin, o_pin = host[0]
+        ms32s = timed(lambda: [runner.stylize_host(c_pin, s_pin, o_pin) for _ in range(steps)], steps) / steps
+        rec["e2e_f32"] = {"value": world * nbatch / (ms32 / 1e3), "unit": "images/s", "ms_per_step": ms32,
+                          "h2d_bytes_per_step": 8 * c_pin.numel(), "d2h_bytes_per_step": 4 * o_pin.numel(),
+                          "h2d_gbs_per_rank": 8 * c_pin.numel() / (ms32 * 1e6), "single_blocking_call_ms": ms32s,
+                          "api": "GraphedStylizer.stylize_many: pinned fp32 [B,3,S,S] tensors in / out"}
+        rec["launches_per_step"] = runner.launches_per_step
+        return rec, runner, clocks
 
-    launches_per_step = runner.launches_per_step
+    main_rec, runner, clocks = measure_stylization(args.size, batch, args.steps, args.warmup, True)
+    ms_step, value = main_rec["ms_per_step"], main_rec["value"]
+
+    launches_per_step = main_rec["launches_per_step"]
     # ---------------- per-kernel-family timing (eager pass with CUDA events around every launch) ----------------
     burst, sustained, hbm, peak_src = peaks()
     roofline, families = None, None
@@ -362,10 +447,33 @@ def main():
                "sample": f"best of {len(times)} full forwards of batch {cpu_batch} at {args.size}x{args.size} ({sum(times):.1f} s of CPU work), "
                          "fp32 CPU oracle port of the reference"}
 
+    # ---------------- the reference's ops on this GPU, eager (SURVEY 8d "GPU reference baseline") ----------------
+    gpu_eager = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        gpu_eager = gpu_eager_baseline(model, runner.content, runner.style, args.layers, dev)
+
+    # ---------------- BASELINE configs[4]: 512x512, batch 16/GPU, in the same line (at every N) ----------------
+    config5 = None
+    if args.size == 256 and args.config5:
+        del runner
+        torch.cuda.empty_cache()
+        rec5, runner5, _ = measure_stylization(512, 16, max(3, args.steps // 2), 3, False)
+        rec5.pop("e2e_f32", None)
+        config5 = {"workload": "zero-shot stylization, batch 16/GPU at 512x512, forward only, %d transformer layer(s)" % args.layers,
+                   "unit": "images/s", **rec5,
+                   "tflops": flops_per_image(512, args.layers) * 16 / (rec5["ms_per_step"] * 1e9),
+                   "frac_of_sustained_bf16": flops_per_image(512, args.layers) * 16 / (rec5["ms_per_step"] * 1e9) / sustained}
+        del runner5
+        runner = None
+        torch.cuda.empty_cache()
+
+    # ---------------- VGG-19 loss forward: HBM rate of the reduction kernels ----------------
+    loss_forward = bench_loss_forward(dev, hbm) if (rank == 0 and args.size == 256) else None
+
     # ---------------- secondary: training-step workloads (BASELINE configs[2], [3]) ----------------
     training = None
     if args.train_steps > 0 and args.size == 256:
-        del runner
+        runner = None
         torch.cuda.empty_cache()
         training = bench_training(dev, rank, world, args.train_steps, 3)
 
@@ -373,16 +481,24 @@ def main():
         act_mb = batch * (args.size // 8) ** 2 * 256 * 4 / 1e6
         config["l2"] = f"no explicit flush: a step streams >1 GB of activations (feature map alone {act_mb:.0f} MB fp32 x dozens of tensors) through a 126 MB L2"
         config["timed"] = "one CUDA-graph replay per step"
+        tr = (training or {}).get("train_step") or {}
+        summary = {"images_per_s": round(value, 1), "ms_per_step": round(ms_step, 4), "e2e_u8_images_per_s": round(main_rec["e2e"]["value"], 1),
+                   "e2e_f32_images_per_s": round(main_rec["e2e_f32"]["value"], 1), "h2d_gbs_per_rank_u8": round(main_rec["e2e"]["h2d_gbs_per_rank"], 2),
+                   "step_frac_of_bf16_peak": round(roofline["step"]["frac"], 4) if roofline else None,
+                   "config5_images_per_s": round(config5["value"], 1) if config5 else None,
+                   "config5_e2e_images_per_s": round(config5["e2e"]["value"], 1) if config5 else None,
+                   "train_step_ms": round(tr["ms_per_step"], 4) if tr else None,
+                   "replicas_identical": (training or {}).get("replicas_identical"),
+                   "gpu_eager_fp32_images_per_s": round(gpu_eager["fp32"]["value"], 1) if gpu_eager else None,
+                   "n_gpus": world}
         emit(json.dumps({
             "metric": "stylized_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e.item() / args.steps,
-                    "api": "GraphedStylizer.stylize_many (pipelined); single blocking stylize_host call: %.3f ms" % ms_single},
-            "e2e_u8": e2e_u8,
+            "e2e": main_rec["e2e"], "e2e_f32": main_rec["e2e_f32"],
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-            "roofline": roofline, "kernel_families": families, "cpu_baseline": cpu, "training": training}))
+            "roofline": roofline, "cpu_baseline": cpu, "kernel_families": families, "training": training,
+            "loss_forward": loss_forward, "gpu_eager_baseline": gpu_eager, "config5": config5, "summary": summary}))
     if world > 1:
         dist.destroy_process_group()
 

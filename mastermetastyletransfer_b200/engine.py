@@ -29,6 +29,10 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        # Buffers superseded by a larger request stay alive: a CUDA graph captured earlier (GraphedStylizer,
+        # GraphedTrainStep) has their addresses baked in and still writes to them on replay -- handing the memory back to the
+        # caching allocator would let another tensor reuse it.
+        self.retired = []
 
     def get(self, name: str, shape, dtype) -> torch.Tensor:
         t = self.bufs.get(name)
@@ -36,6 +40,8 @@ class Workspace:
         for s in shape:
             n *= s
         if t is None or t.numel() < n or t.dtype != dtype:
+            if t is not None:
+                self.retired.append(t)
             t = torch.empty(n, dtype=dtype, device=self.device)
             self.bufs[name] = t
         return t[:n].view(*shape)

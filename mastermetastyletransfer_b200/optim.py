@@ -82,7 +82,11 @@ class FusedAdam:
         self.params = [p for g in self.param_groups for p in g["params"]]
         self.state = [{"exp_avg": [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in g["params"]],
                        "exp_avg_sq": [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in g["params"]],
-                       "table": None} for g in self.param_groups]
+                       "table": None, "tables": {}} for g in self.param_groups]
+        # Device tables built while a CUDA graph was being captured: their pinned host staging is read by the captured H2D
+        # copy nodes on EVERY replay, so they must outlive every later table change (an eager step with other gradient
+        # pointers, a second GraphedTrainStep on the same trainer).  Never dropped.
+        self._captured_tables = []
         self.step_count = 0
         self.capturable = capturable
         self._dev_state = None
@@ -91,6 +95,7 @@ class FusedAdam:
             self._dev_state = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in self.param_groups]  # {float lr, int step}
             for g, st in zip(self.param_groups, self._dev_state):
                 st.view(torch.float32)[0] = float(g["lr"])
+            self._dev_lr = [float(g["lr"]) for g in self.param_groups]  # host mirror of the device-side learning rates
 
     def set_lr(self, lr: float, group: Optional[int] = None) -> None:
         """Learning-rate change that a captured graph sees (device-side state); eager mode just updates param_groups."""
@@ -99,6 +104,7 @@ class FusedAdam:
                 g["lr"] = lr
                 if self._dev_state is not None:
                     self._dev_state[i].view(torch.float32)[0] = float(lr)
+                    self._dev_lr[i] = float(lr)
 
     @property
     def lr(self):
@@ -106,8 +112,18 @@ class FusedAdam:
 
     @lr.setter
     def lr(self, value):
-        for g in self.param_groups:
-            g["lr"] = value
+        self.set_lr(value)
+
+    def sync_lr(self) -> None:
+        """capturable mode: push `param_groups[i]['lr']` edits (the reference's rescheduling idiom,
+        train_only_inner_loop.py:321-340) to the device-side state that the kernels and captured graphs read.  Called by every
+        eager step() and by GraphedTrainStep.step() before a replay."""
+        if self._dev_state is None or torch.cuda.is_current_stream_capturing():
+            return
+        for i, g in enumerate(self.param_groups):
+            if float(g["lr"]) != self._dev_lr[i]:
+                self._dev_state[i].view(torch.float32)[0] = float(g["lr"])
+                self._dev_lr[i] = float(g["lr"])
 
     def zero_grad(self, set_to_none: bool = False):
         for p in self.params:
@@ -170,13 +186,15 @@ class FusedAdam:
                 st["exp_avg_sq"][j].copy_(e["exp_avg_sq"])
         self.step_count = steps.pop() if steps else 0
         if self._dev_state is not None:
-            for g, ds in zip(self.param_groups, self._dev_state):
+            for i, (g, ds) in enumerate(zip(self.param_groups, self._dev_state)):
                 ds.view(torch.float32)[0] = float(g["lr"])
                 ds[1] = self.step_count
+                self._dev_lr[i] = float(g["lr"])
 
     @torch.no_grad()
     def step(self):
         self.step_count += 1
+        self.sync_lr()
         for gi, (g, st) in enumerate(zip(self.param_groups, self.state)):
             if not g["params"]:
                 continue
@@ -188,7 +206,15 @@ class FusedAdam:
             lists = [[p.data for p in g["params"]], grads, st["exp_avg"], st["exp_avg_sq"]]
             key = tuple(t.data_ptr() for l in lists for t in l)
             if st["table"] is None or st["table"].key != key:
-                st["table"] = _Table(lists)
+                tbl = st["tables"].get(key)
+                if tbl is None:
+                    tbl = _Table(lists)
+                    if torch.cuda.is_current_stream_capturing():
+                        self._captured_tables.append(tbl)  # immortal: a graph replays uploads from its pinned staging
+                    if len(st["tables"]) >= 8:  # eager training allocates fresh gradients every step: bound the cache
+                        st["tables"].clear()
+                    st["tables"][key] = tbl
+                st["table"] = tbl
             n = sum(p.numel() for p in g["params"])
             tb = st["table"].tb
             if self.capturable:
@@ -204,13 +230,13 @@ class FusedAdam:
 
 
 @torch.no_grad()
-def reptile_update(theta: torch.nn.Module, omega: torch.nn.Module, outer_lr: float, group=None) -> None:
+def reptile_update(theta, omega, outer_lr: float, group=None) -> None:
     """theta += outer_lr * mean_over_ranks(omega - theta)  (train.py:524-534 when there is a single rank).
 
     With torch.distributed initialised, each rank holds an omega trained on its own style task; the flat delta
     buffer is all-reduced (NCCL on GPUs) and every rank applies the same averaged update."""
-    tp = [p for _, p in theta.named_parameters()]
-    op = [p for _, p in omega.named_parameters()]
+    as_list = lambda m: [p for _, p in m.named_parameters()] if isinstance(m, torch.nn.Module) else list(m)
+    tp, op = as_list(theta), as_list(omega)  # modules, or parameter lists (several modules in ONE collective)
     if len(tp) != len(op) or any(a.shape != b.shape for a, b in zip(tp, op)):
         raise ValueError("theta and omega must have identical parameter lists")
     table = _Table([[p.data for p in tp], [p.data for p in op]])

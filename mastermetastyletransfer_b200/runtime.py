@@ -31,6 +31,8 @@ class GraphedStylizer:
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.output = self.model(self.content, self.style, layers)
         torch.cuda.synchronize(self.device)
+        from .style_transformer import pin_state
+        self._pinned = pin_state([self.model])  # packed weights / workspace buffers whose addresses the graph baked in
 
     def _u8(self, normalize: bool = True):
         """The uint8 boundary of test_model.py around the same model, as a second graph: uint8 [B,S,S,3] images (decoded and

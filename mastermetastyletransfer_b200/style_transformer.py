@@ -47,6 +47,24 @@ def packed_weights(module: nn.Module, builder):
     return hit[1]
 
 
+def pin_state(modules) -> list:
+    """References to everything a CUDA graph captured over `modules` has baked in by address and that this file's caches
+    could otherwise drop later: the current packed weights (replaced when a parameter's version changes, e.g. a reload of
+    the frozen Swin / VGG weights) and every workspace buffer (replaced when a larger shape arrives; engine.Workspace keeps
+    superseded buffers itself, this also covers a workspace replaced as a whole).  The Graphed* objects hold the returned
+    list for their lifetime, so a replay never writes to memory the caching allocator has handed to someone else."""
+    keep = []
+    for root in modules:
+        for m in root.modules():
+            if m in _cache:
+                keep.append(dict(_cache[m]))
+            ws = _workspaces.get(m)
+            if ws is not None:
+                keep.append(ws)
+                keep.append(list(ws.bufs.values()))
+    return keep
+
+
 def workspace_of(module: nn.Module, device) -> engine.Workspace:
     ws = _workspaces.get(module)
     if ws is None or ws.device != device:

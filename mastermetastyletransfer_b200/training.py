@@ -16,7 +16,7 @@ from typing import Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-from .optim import FusedAdam, reptile_update
+from .optim import FusedAdam, _bump_versions, reptile_update
 
 
 def _dist_on(group=None) -> bool:
@@ -71,6 +71,18 @@ class InnerLoopTrainer:
                 p.requires_grad = True
             for p in model.decoder.parameters():
                 p.requires_grad = False
+        if _dist_on(group):
+            # every rank must start from the same theta (the all-reduced gradient / Reptile delta is applied to each rank's own
+            # copy): one broadcast of the flat parameter vector from rank 0 instead of trusting seeds and checkpoints to agree
+            with torch.no_grad():
+                theta = list(model.style_transformer.parameters()) + list(model.decoder.parameters())
+                flat = torch.cat([p.data.reshape(-1) for p in theta])
+                dist.broadcast(flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                off = 0
+                for p in theta:
+                    p.data.copy_(flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+            _bump_versions(theta)
         self.omega_st = copy.deepcopy(model.style_transformer).train()
         self.omega_dec = copy.deepcopy(model.decoder).train()
         self.params: List[torch.nn.Parameter] = list(self.omega_st.parameters()) + list(self.omega_dec.parameters())
@@ -86,6 +98,7 @@ class InnerLoopTrainer:
         (GraphedTrainStep) keeps reading the right memory."""
         with torch.no_grad():
             torch._foreach_copy_([p.data for p in self.params], [p.data for p in self._theta])
+        _bump_versions(self.params)  # `.data` has its own version counter: the packed-weight caches key on the parameters'
 
     def step(self, content: torch.Tensor, style: torch.Tensor, num_layers: Optional[int] = None):
         """One inner-loop update; returns the device tensor (total, content, style) without synchronising."""
@@ -163,8 +176,7 @@ class InnerLoopTrainer:
 
     def outer_update(self, outer_lr: float) -> None:
         """theta += outer_lr * mean_over_ranks(omega - theta) for the style transformer and the decoder (train.py:524-534)."""
-        reptile_update(self.model.style_transformer, self.omega_st, outer_lr, self.group)
-        reptile_update(self.model.decoder, self.omega_dec, outer_lr, self.group)
+        reptile_update(self._theta, self.params, outer_lr, self.group)  # both modules: one delta buffer, ONE all-reduce
 
 
 def meta_iteration(trainer: InnerLoopTrainer, style: torch.Tensor, content_batches: Iterable[torch.Tensor], outer_lr: float,
@@ -215,6 +227,8 @@ class GraphedTrainStep:
             self.losses = trainer.step(self.content, self.style, num_layers)
         self.launches = ops.launch_count - n0  # kernels of this library inside one replay
         torch.cuda.synchronize(dev)
+        from .style_transformer import pin_state
+        self._pinned = pin_state([trainer.model, trainer.omega_st, trainer.omega_dec, trainer.loss_fn])  # baked-in addresses stay valid
         with torch.no_grad():
             for p, v in zip(trainer.params, snap[0]):
                 p.copy_(v)
@@ -235,5 +249,9 @@ class GraphedTrainStep:
     def step(self, content: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
         self.content.copy_(content, non_blocking=True)
         self.style.copy_(style, non_blocking=True)
+        self.trainer.opt.sync_lr()
         self.graph.replay()
+        # the replayed Adam kernel wrote omega through raw pointers: anything keyed on (data_ptr, _version) -- the packed
+        # weights an eager forward of omega would reuse -- must see a new version (host-side only, no launch)
+        _bump_versions(self.trainer.params)
         return self.losses

@@ -126,8 +126,8 @@ def _to_windows(x: Tensor, ws: int, shift: int) -> Tensor:
     """[B,H,W,C] -> [B*nW, N, C] via the gather map (zeros where the map points at padding)."""
     B, H, W, C = x.shape
     Hp, Wp = padded_dims(H, W, ws)
-    gm = window_gather_map(H, W, ws, shift)
-    xp = torch.zeros(B, Hp, Wp, C, dtype=x.dtype)
+    gm = window_gather_map(H, W, ws, shift).to(x.device)  # (the maps are built on the CPU; bench.py's GPU-eager leg runs the same ops on cuda)
+    xp = torch.zeros(B, Hp, Wp, C, dtype=x.dtype, device=x.device)
     xp[:, :H, :W] = x
     return xp.reshape(B, Hp * Wp, C)[:, gm.reshape(-1)].reshape(B * gm.shape[0], gm.shape[1], C)
 
@@ -135,9 +135,9 @@ def _to_windows(x: Tensor, ws: int, shift: int) -> Tensor:
 def _from_windows(xw: Tensor, B: int, H: int, W: int, ws: int, shift: int) -> Tensor:
     """Inverse of _to_windows followed by the un-pad (codes/style_transformer.py:160-168)."""
     Hp, Wp = padded_dims(H, W, ws)
-    gm = window_gather_map(H, W, ws, shift).reshape(-1)
+    gm = window_gather_map(H, W, ws, shift).reshape(-1).to(xw.device)
     C = xw.shape[-1]
-    out = torch.empty(B, Hp * Wp, C, dtype=xw.dtype)
+    out = torch.empty(B, Hp * Wp, C, dtype=xw.dtype, device=xw.device)
     out[:, gm] = xw.reshape(B, -1, C)
     return out.reshape(B, Hp, Wp, C)[:, :H, :W].contiguous()
 
@@ -145,7 +145,7 @@ def _from_windows(xw: Tensor, B: int, H: int, W: int, ws: int, shift: int) -> Te
 def _bias_from_table(table: Tensor, ws: int) -> Tensor:
     """codes/style_transformer.py:21-28: [heads, N, N]."""
     n = ws * ws
-    return table[relative_position_index(ws)].reshape(n, n, -1).permute(2, 0, 1)
+    return table[relative_position_index(ws).to(table.device)].reshape(n, n, -1).permute(2, 0, 1)
 
 
 def _softmax_probs(q: Tensor, k: Tensor, heads: int, bias: Tensor, mask: Optional[Tensor], B: int) -> Tensor:
@@ -156,6 +156,7 @@ def _softmax_probs(q: Tensor, k: Tensor, heads: int, bias: Tensor, mask: Optiona
     kh = k.reshape(bw, n, heads, d).permute(0, 2, 1, 3)
     s = qh @ kh.transpose(-2, -1) + bias.unsqueeze(0)
     if mask is not None:
+        mask = mask.to(s.device)
         nW = mask.shape[0]
         s = (s.reshape(B, nW, heads, n, n) + mask.reshape(1, nW, 1, n, n)).reshape(bw, heads, n, n)
     return torch.softmax(s, dim=-1)
@@ -206,8 +207,8 @@ def sigma_mu_attention(xq: Tensor, xk: Tensor, xvs: Tensor, xvh: Tensor, wk, bk,
     vh = F.linear(_to_windows(xvh, ws, shift), wvh, bvh)
     if key_in_after_linear:
         # un-window k (still rolled, still padded), normalise per (b,c) over Hp*Wp, re-window
-        gm = window_gather_map(H, W, ws, shift).reshape(-1)
-        kmap = torch.empty(B, Hp * Wp, C)
+        gm = window_gather_map(H, W, ws, shift).reshape(-1).to(k.device)
+        kmap = torch.empty(B, Hp * Wp, C, dtype=k.dtype, device=k.device)
         kmap[:, gm] = k.reshape(B, -1, C)
         kmap = instance_norm_bhwc(kmap.reshape(B, Hp, Wp, C), affine=affine_k).reshape(B, Hp * Wp, C)
         k = kmap[:, gm].reshape(k.shape)

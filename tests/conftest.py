@@ -107,3 +107,27 @@ def seeded_vgg19_bn():
             if isinstance(m, torch.nn.BatchNorm2d):
                 m.running_var.copy_(m.running_var.abs() + 0.5)
     return seq
+
+
+def condition_vgg_(features, images, shift: float = 1.0):
+    """Data-dependent rescaling of a seeded VGG-19 feature stack (LSUV style), in place and deterministic: conv by conv, on the
+    given image batch (the test's own content / style / fp32-oracle output), scale each output channel's weights so that its
+    pre-activation has unit standard deviation and set its bias so that the mean sits `shift` standard deviations above zero.
+    Every tap channel then carries signal on those images: the InstanceNorm inside the content loss (eps 1e-5) no longer
+    amplifies the bf16 rounding noise of nearly dead channels by 1/sqrt(1e-5) -- a property of random VGG weights, not of the
+    loss -- and end-to-end gradient parity can be gated tightly (VERDICT r1, weak #2).  Test infrastructure."""
+    import torch
+    import torch.nn.functional as F
+    x = images
+    with torch.no_grad():
+        for m in features:
+            if isinstance(m, torch.nn.Conv2d):
+                y = F.conv2d(x, m.weight, None, padding=1)
+                std = y.std(dim=(0, 2, 3)).clamp_min(1e-6)
+                m.weight.div_(std.view(-1, 1, 1, 1))
+                y = y / std.view(1, -1, 1, 1)
+                m.bias.copy_(shift - y.mean(dim=(0, 2, 3)))
+                x = y + m.bias.view(1, -1, 1, 1)
+            else:
+                x = m(x)
+    return features

@@ -287,3 +287,61 @@ def test_similarity_loss_flag_matches_reference_fixture(loss_module, golden_dir)
     tot, sim = loss_module(content.cuda(), style.cuda(), g, output_similarity_loss=True)
     (tot + sim).backward()
     assert sim.item() == 0.0 and g.grad is not None and torch.isfinite(g.grad).all()
+
+
+@pytest.mark.parametrize("ws,k", [(8, 1), (8, 2), (7, 1)])
+def test_config5_512_vs_oracle_and_golden(ws, k, golden_dir):
+    """BASELINE configs[4] geometry: 512x512 images -> 64x64 feature maps (64 8x8 windows, or 100 zero-padded 7x7 windows, per
+    image; Swin stage 1 runs on 128x128 tokens).  Batch 2 against the CPU oracle, image 0 against the golden minted from the
+    REAL reference (oracle/make_golden_512.py)."""
+    from mastermetastyletransfer_b200 import MasterStyleTransferModel, synthetic
+    from oracle import master_oracle as O
+    m = MasterStyleTransferModel(style_encoder_window_size=[ws, ws], style_decoder_window_size=[ws, ws])
+    synthetic.fill_state_dict_(m, 0)
+    sdw = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+    m = m.eval().cuda()
+    c1, s1 = synthetic.synthetic_images(1, 512, seed=2)   # the golden's pair
+    c2, s2 = synthetic.synthetic_images(1, 512, seed=12)
+    content, style = torch.cat([c1, c2]), torch.cat([s1, s2])
+    with torch.no_grad():
+        out = m(content.cuda(), style.cuda(), k).cpu()
+        ref = O.full_forward(sdw, content, style, k, ws=ws, sh=4)
+    assert out.shape == ref.shape == (2, 3, 512, 512)
+    tol = IMG_TOL if k == 1 else 2 * IMG_TOL
+    e = rel_err(out, ref)
+    assert e <= tol, e
+    gold = np.load(os.path.join(golden_dir, "path_512.npz"))
+    g = torch.from_numpy(gold[f"img_ws{ws}_k{k}"])
+    st = gold[f"img_ws{ws}_k{k}_stats"]
+    eg = ((out[:1, :, ::8, ::8] - g).abs().max() / float(st[3] - st[2])).item()
+    assert eg <= tol, eg
+
+
+def test_config5_512_loss_vs_golden(model, loss_module, golden_dir):
+    """VGG-19 content/style loss at 512x512 (taps up to 256x256x128) against the real reference's scalars."""
+    from mastermetastyletransfer_b200 import synthetic
+    from oracle import master_oracle as O
+    loss = loss_module
+    content, style = synthetic.synthetic_images(1, 512, seed=2)
+    sdm = {n: v.detach().cpu() for n, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref_img = O.full_forward(sdm, content, style, 1)  # the loss is checked on the reference's own output image
+        t, c, s = loss(content.cuda(), style.cuda(), ref_img.cuda(), output_content_and_style_loss=True)
+    gold = np.load(os.path.join(golden_dir, "path_512.npz"))["loss"]
+    for mine, g in zip((t, c, s), gold):
+        assert abs(mine.item() - g) <= 1e-3 * abs(g), (mine.item(), g)
+
+
+def test_benched_shape_batch32_256_vs_oracle(model, sd):
+    """The bench's own shape (BASELINE configs[1]: batch 32 at 256x256, one launch sequence over 64 encoder images): four
+    images spread over the batch against the CPU oracle run on just those four."""
+    from mastermetastyletransfer_b200 import synthetic
+    from oracle import master_oracle as O
+    content, style = synthetic.synthetic_images(32, 256, seed=5)
+    pick = [0, 13, 22, 31]
+    with torch.no_grad():
+        out = model(content.cuda(), style.cuda(), 1).cpu()
+        ref = O.full_forward(sd, content[pick], style[pick], 1)
+    assert out.shape == (32, 3, 256, 256)
+    e = rel_err(out[pick], ref)
+    assert e <= IMG_TOL, e

@@ -346,18 +346,65 @@ def test_style_transformer_stochastic_depth(model, sd):
     _cmp_all(st, ps)
 
 
-def test_full_training_step_vs_oracle(model, sd):
-    """One step of the reference's inner loop (train.py:452-517): frozen encoder, omega copies of the style transformer
-    and the decoder, VGG loss, backward, Adam -- gradients vs autograd through the CPU oracle."""
+def _no_stochastic_depth(st):
+    for m in (st.encoder, st.decoder):  # parity runs: stochastic depth off
+        m.stochastic_depth.p = 0.0
+    st.encoder.encoder_stochastic_depth_prob = 0.0
+    st.encoder.shared_MHA_without_MLP.stochastic_depth.p = 0.0
+    st.decoder.MHA_self_attn.stochastic_depth.p = 0.0
+    return st
+
+
+def _seeded_loss(conditioned_on=None):
+    """custom_loss with the seeded VGG-19; `conditioned_on` = image batch for conftest.condition_vgg_ (every tap channel alive)."""
+    from conftest import condition_vgg_
     from mastermetastyletransfer_b200 import custom_loss, synthetic
-    from mastermetastyletransfer_b200.optim import FusedAdam
-    from oracle import master_oracle as O
     loss_fn = custom_loss("/nonexistent")
     synthetic.fill_state_dict_(loss_fn, 1)
-    loss_fn = loss_fn.cuda()
-    vsd = {k[len("feature_extractor_model.features."):]: v.detach().cpu() for k, v in loss_fn.state_dict().items()
+    if conditioned_on is not None:
+        condition_vgg_(loss_fn.feature_extractor_model.features, conditioned_on)
+    vsd = {k[len("feature_extractor_model.features."):]: v.detach().cpu().clone() for k, v in loss_fn.state_dict().items()
            if k.startswith("feature_extractor_model.features.")}
-    content, style = synthetic.synthetic_images(1, 64, seed=4)
+    return loss_fn.cuda(), vsd
+
+
+def _global_cmp(named_mine, ref_params, prefixes):
+    """rel-L2 and cosine of the WHOLE gradient vector (all trainable parameters concatenated) + the worst per-parameter cosine
+    among parameters that carry at least 1 % of the largest gradient norm."""
+    a = torch.cat([g.detach().float().cpu().flatten() for _, g in named_mine])
+    b = torch.cat([ref_params[n].grad.float().flatten() for n, _ in named_mine])
+    rel = ((a - b).norm() / b.norm()).item()
+    cos = (torch.dot(a, b) / (a.norm() * b.norm())).item()
+    scale = max(ref_params[n].grad.norm().item() for n, _ in named_mine)
+    worst, worst_name = 1.0, ""
+    for n, g in named_mine:
+        r = ref_params[n].grad.float().flatten()
+        if r.norm().item() < 1e-2 * scale:
+            continue
+        c = (torch.dot(g.detach().float().cpu().flatten(), r) / (g.norm().item() * r.norm() + 1e-30)).item()
+        if c < worst:
+            worst, worst_name = c, n
+    return rel, cos, worst, worst_name
+
+
+@pytest.mark.parametrize("conditioned", [False, True])
+def test_full_training_step_vs_oracle(model, sd, conditioned):
+    """One step of the reference's inner loop (train.py:452-517): frozen encoder, omega copies of the style transformer
+    and the decoder, VGG loss, backward, Adam -- loss scalars and EVERY trainable parameter's gradient against torch autograd
+    through the fp32 CPU oracle, at 128x128, batch 2 (enough loss terms that the sign flips of the L1 distances under bf16
+    rounding average out: a CPU emulation of the CNN decoder's / VGG's bf16 operand rounding alone moves the gradient vector
+    by 3 % rel-L2, cos 0.9996 -- tools/debug/grad_gate_cpu.py).  Gate: whole gradient vector rel-L2 <= 0.1 and cos >= 0.99,
+    every parameter holding >= 1 % of the largest gradient norm cos >= 0.95.  `conditioned`: the same with a VGG rescaled so
+    that no tap channel is dead on these images (conftest.condition_vgg_)."""
+    from mastermetastyletransfer_b200 import synthetic
+    from mastermetastyletransfer_b200.optim import FusedAdam
+    from oracle import master_oracle as O
+    content, style = synthetic.synthetic_images(2, 128, seed=4)
+    cond_imgs = None
+    if conditioned:
+        with torch.no_grad():
+            cond_imgs = torch.cat([content, style, O.full_forward(sd, content, style, 1)])
+    loss_fn, vsd = _seeded_loss(cond_imgs)
     # oracle side
     ps = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.startswith("swin_encoder.") else v.clone())
           for k, v in sd.items()}
@@ -365,28 +412,67 @@ def test_full_training_step_vs_oracle(model, sd):
     tr, cr, sr = O.overall_loss(vsd, content, style, ref_img, 10.0)
     tr.backward()
     # product side, called the way train.py does
-    omega_st = copy.deepcopy(model.style_transformer).train()
+    omega_st = _no_stochastic_depth(copy.deepcopy(model.style_transformer).train())
     omega_dec = copy.deepcopy(model.decoder).train()
-    for m in (omega_st.encoder, omega_st.decoder):  # parity run: stochastic depth off
-        m.stochastic_depth.p = 0.0
-    omega_st.encoder.encoder_stochastic_depth_prob = 0.0
-    omega_st.encoder.shared_MHA_without_MLP.stochastic_depth.p = 0.0
-    omega_st.decoder.MHA_self_attn.stochastic_depth.p = 0.0
     opt = FusedAdam(list(omega_st.parameters()) + list(omega_dec.parameters()), lr=1e-4)
     c, s = content.cuda(), style.cuda()
     fc, fs = model.swin_encoder(c), model.swin_encoder(s)
     out = omega_dec(omega_st(fc, fs, 1).permute(0, 3, 1, 2))
     t, cl, sl = loss_fn(c, s, out, output_content_and_style_loss=True)
     for a, b in ((t, tr), (cl, cr), (sl, sr)):
-        assert abs(a.item() - b.item()) <= 1e-2 * abs(b.item()), (a.item(), b.item())
+        assert abs(a.item() - b.item()) <= 2e-3 * abs(b.item()), (a.item(), b.item())
     opt.zero_grad()
     t.backward()
-    # fp32 oracle end to end: bounded by ReLU / sign / near-dead-channel flips (see header and test_loss_grads)
-    _cmp_all(omega_st, ps, "style_transformer.", rel=1.0, cos=0.5)
-    _cmp_all(omega_dec, ps, "decoder.", rel=1.0, cos=0.5)
+    named = [("style_transformer." + n, p.grad) for n, p in omega_st.named_parameters()] + \
+            [("decoder." + n, p.grad) for n, p in omega_dec.named_parameters()]
+    rel, cos, worst, worst_name = _global_cmp(named, ps, None)
+    print(f"end-to-end gradient (conditioned={conditioned}): rel-L2 {rel:.4f} cos {cos:.5f}; worst parameter cos {worst:.4f} ({worst_name})")
+    assert rel <= 0.1 and cos >= 0.99, (rel, cos)
+    assert worst >= 0.95, (worst, worst_name)
     before = [p.detach().clone() for p in omega_dec.parameters()]
     opt.step()
     assert any(not torch.equal(a, b) for a, b in zip(before, omega_dec.parameters()))
+
+
+def test_ten_step_loss_trajectory_vs_oracle_adam(model, sd):
+    """Ten inner-loop steps on a fixed batch (train_only_inner_loop.py:523-575): the product's trainer (kernels + fused Adam)
+    against torch autograd through the fp32 CPU oracle + torch.optim.Adam with the same hyper-parameters.  Every step's losses
+    (total, content, style) within 1 % of the oracle's, the loss decrease over the ten steps within 10 %."""
+    from mastermetastyletransfer_b200 import synthetic
+    from mastermetastyletransfer_b200.training import InnerLoopTrainer
+    from oracle import master_oracle as O
+    content, style = synthetic.synthetic_images(2, 64, seed=14)
+    loss_fn, vsd = _seeded_loss()
+    lr, steps = 3e-5, 10  # smooth regime: the oracle's loss halves monotonically (95 -> 48); at 1e-4 and above Adam's sign-like
+    # first steps overshoot on this 2-image batch and the trajectory turns chaotic (any rounding difference is amplified)
+    # oracle trajectory
+    ps = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.startswith("swin_encoder.") else v.clone())
+          for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in ps.values() if v.requires_grad], lr=lr)
+    ref = []
+    for _ in range(steps):
+        opt.zero_grad()
+        t, c_, s_ = O.overall_loss(vsd, content, style, O.full_forward(ps, content, style, 1), 10.0)
+        t.backward()
+        opt.step()
+        ref.append([t.item(), c_.item(), s_.item()])
+    # product trajectory
+    m = copy.deepcopy(model)
+    _no_stochastic_depth(m.style_transformer)
+    tr = InnerLoopTrainer(m, loss_fn, inner_lr=lr)
+    _no_stochastic_depth(tr.omega_st)
+    c, s = content.cuda(), style.cuda()
+    mine = torch.stack([tr.step(c, s, 1).clone() for _ in range(steps)]).cpu()
+    ref = torch.tensor(ref)
+    print("oracle total loss:", [round(v, 4) for v in ref[:, 0].tolist()])
+    print("kernel total loss:", [round(v, 4) for v in mine[:, 0].tolist()])
+    assert ref[-1, 0] < ref[0, 0], "the oracle's loss should go down on a repeated batch"
+    rel = ((mine - ref).abs() / ref.abs()).max().item()
+    rel_final = ((mine[-1] - ref[-1]).abs() / ref[-1].abs()).max().item()
+    print(f"worst step rel {rel:.4f}, final rel {rel_final:.4f}")
+    assert rel <= 1e-2 and rel_final <= 1e-2, (rel, rel_final, mine, ref)
+    drop_ref, drop_mine = (ref[0, 0] - ref[-1, 0]).item(), (mine[0, 0] - mine[-1, 0]).item()
+    assert abs(drop_mine - drop_ref) <= 0.1 * abs(drop_ref), (drop_mine, drop_ref)
 
 
 def test_model_forward_train_mode_matches_modules(model):
@@ -498,3 +584,45 @@ def test_graphed_meta_iteration_matches_eager(model):
     assert moved > 1e-4, moved  # theta really moved
     worst = max(((a - b).norm() / (a.norm() + 1e-12)).item() for a, b in zip(*thetas))
     assert worst < 2e-3, worst
+
+
+def test_two_graphs_and_eager_steps_on_one_trainer(model):
+    """two GraphedTrainStep objects (layer counts 1 and 2 -- the reference samples the layer count per inner
+    step, train.py:448) on ONE trainer, interleaved with eager steps, follow an eager-only trainer.  Each graph's optimiser
+    pointer table (uploaded from pinned staging on every replay) must survive the other graph's and the eager steps' tables;
+    the packed weights must be rebuilt after replays (version bump) so the eager forward sees the updated omega."""
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    from mastermetastyletransfer_b200.training import GraphedTrainStep, InnerLoopTrainer
+    loss_fn = custom_loss("/nonexistent")
+    synthetic.fill_state_dict_(loss_fn, 1)
+    loss_fn = loss_fn.cuda()
+    m = copy.deepcopy(model)
+    _no_stochastic_depth(m.style_transformer)
+    content, style = synthetic.synthetic_images(2, 64, seed=21)
+    content, style = content.cuda(), style.cuda()
+    eager = InnerLoopTrainer(m, loss_fn, inner_lr=1e-3)
+    mixed = InnerLoopTrainer(m, loss_fn, inner_lr=1e-3, capturable=True)
+    g1 = GraphedTrainStep(mixed, 2, 64, num_layers=1)
+    g2 = GraphedTrainStep(mixed, 2, 64, num_layers=2)
+    for a, b in zip(eager.params, mixed.params):
+        assert torch.equal(a, b)
+    plan = [1, 2, "e1", 2, 1, "e2", 1, 2]  # graph(1), graph(2), eager k=1, ...
+    le, lm = [], []
+    for what in plan:
+        k = what if isinstance(what, int) else int(what[1])
+        le.append(eager.step(content, style, k).clone())
+        if isinstance(what, int):
+            lm.append((g1 if what == 1 else g2).step(content, style).clone())
+        else:
+            lm.append(mixed.step(content, style, k).clone())
+    le, lm = torch.stack(le).cpu(), torch.stack(lm).cpu()
+    assert torch.isfinite(lm).all()
+    assert torch.allclose(le, lm, rtol=5e-3), (le, lm)
+    worst = max(((a - b).norm() / (a.norm() + 1e-12)).item() for a, b in zip(eager.params, mixed.params))
+    assert worst < 5e-3, worst
+    # learning-rate rescheduling through param_groups (train_only_inner_loop.py:321-340) reaches the captured graph
+    mixed.opt.param_groups[0]["lr"] = 0.0
+    before = [p.detach().clone() for p in mixed.params]
+    g1.step(content, style)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(before, mixed.params)), "lr = 0 through param_groups must freeze the replayed step"
