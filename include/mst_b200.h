@@ -161,6 +161,35 @@ typedef struct MstWindowAttn {
 
 int mst_window_attention(const MstWindowAttn* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused self-attention half of a window transformer block (csrc/attn_fused.cu): the three projections
+ * q = x Wq^T + bq, k = x Wk^T + bk, v = x Wv^T + bv AND the shifted-window attention core above in one
+ * kernel -- q, k, v never touch HBM.  Replaces F.linear x3 + shifted_window_attention up to (not
+ * including) the output projection, codes/style_transformer.py:77-155 with q_in = k_in = v_in = x, and
+ * the attention of a torchvision Swin block (swin_transformer.py:116-220, fused qkv weight).
+ * x: bf16 token-major [B*H*W, ldx] (already LayerNorm'd where the block has a norm1); out: bf16
+ * [B*H*W, ldo], heads side by side exactly like mst_window_attention's `out`.  Window partition and
+ * cyclic shift are the coordinates of the TMA box that loads a window; zero-padded tokens of maps that
+ * are not a multiple of ws are zero rows of x (their q/k/v = the biases, as pad-then-linear makes
+ * them).  wqkv / bqkv come from mst_pack_attn_qkv.  C in {128, 256}, head_dim 32, ws in {7, 8}.
+ * dbg_qkv (tests only, else NULL): bf16 [B*H*W, 3C] receives the projected q | k | v rows.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MstAttnBlock {
+  const mst_bf16* x;
+  const mst_bf16* wqkv;     /* mst_attn_qkv_packed_bytes(C, heads) bytes */
+  const float* bqkv;        /* [3C] fp32, packed order */
+  const float* bias_table;  /* [(2ws-1)^2, heads] fp32 */
+  mst_bf16* out;
+  mst_bf16* dbg_qkv;
+  int B, H, W, C, heads, ws, shift;
+  int ldx, ldo;
+} MstAttnBlock;
+size_t mst_attn_qkv_packed_bytes(int C, int heads);
+/* wq, wk, wv: fp32 [C, C] row-major (nn.Linear weights; slices of a fused [3C, C] qkv weight work); bq, bk, bv: [C] or NULL */
+int mst_pack_attn_qkv(const float* wq, const float* wk, const float* wv, const float* bq, const float* bk, const float* bv,
+                      mst_bf16* dst_w, float* dst_b, int C, int heads, void* stream);
+int mst_attn_block(const MstAttnBlock* a, void* stream);
+
 /* integer maps the attention kernel uses, exported for the bit-exact parity tests
  * (gather: [nW, ws*ws] int32 = y*W+x or -1 for padding; labels: [nW, ws*ws] int32;
  *  relidx: [ws^4] int32).  Device pointers. */

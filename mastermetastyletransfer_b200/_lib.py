@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmst_b200.so")
+LIB_PATH = os.environ.get("MST_LIB_PATH") or os.path.join(_HERE, "libmst_b200.so")  # MST_LIB_PATH: an instrumented build (tools/build_prof.sh)
 
 c_bf16_p = C.c_void_p
 c_f32_p = C.c_void_p
@@ -61,6 +61,13 @@ class MstWindowAttn(C.Structure):
     ]
 
 
+class MstAttnBlock(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("wqkv", C.c_void_p), ("bqkv", C.c_void_p), ("bias_table", C.c_void_p), ("out", C.c_void_p),
+                ("dbg_qkv", C.c_void_p),
+                ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("heads", C.c_int), ("ws", C.c_int), ("shift", C.c_int),
+                ("ldx", C.c_int), ("ldo", C.c_int)]
+
+
 class MstMlp(C.Structure):
     _fields_ = [("A", C.c_void_p), ("Wstream", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("res", C.c_void_p),
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
@@ -103,6 +110,9 @@ SYMBOLS = {
     "mst_mlp_fused": (_I, [C.POINTER(MstMlp), _P]),
     "mst_window_attention": (_I, [C.POINTER(MstWindowAttn), _P]),
     "mst_window_maps": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "mst_attn_qkv_packed_bytes": (_Z, [_I, _I]),
+    "mst_pack_attn_qkv": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mst_attn_block": (_I, [C.POINTER(MstAttnBlock), _P]),
     "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_merge_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_instnorm_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

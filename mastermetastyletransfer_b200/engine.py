@@ -61,6 +61,13 @@ class Workspace:
 
 # MST_FUSE_PROJ_MLP=0 falls back to the separate projection GEMM / LayerNorm / MLP kernels (A/B measurements)
 FUSE_PROJ_MLP = os.environ.get("MST_FUSE_PROJ_MLP", "1") != "0"
+# MST_FUSE_ATTN=0 falls back to the stand-alone QKV GEMM + window-attention kernel for the self-attentions (A/B measurements);
+# default: LN1(x) -> ONE kernel (three projections + shifted-window attention, q/k/v stay on chip, csrc/attn_fused.cu)
+FUSE_ATTN = os.environ.get("MST_FUSE_ATTN", "1") != "0"
+
+
+def _can_fuse_attn(C: int, heads: int, ws: int) -> bool:
+    return FUSE_ATTN and C in (128, 256) and heads * 32 == C and ws in (7, 8)
 
 
 class SwinEncoderWeights:
@@ -77,6 +84,8 @@ class SwinEncoderWeights:
                 heads=heads, C=C,
                 n1w=g(p + "norm1.weight"), n1b=g(p + "norm1.bias"), n2w=g(p + "norm2.weight"), n2b=g(p + "norm2.bias"),
                 qkv=ops.pack_linear(g(p + "attn.qkv.weight"), qkv_b),
+                attn=(lambda w_, b_, C_=C, h_=heads: ops.pack_attn_qkv(w_[:C_], w_[C_:2 * C_], w_[2 * C_:], b_[:C_], b_[C_:2 * C_], b_[2 * C_:], h_))(
+                    g(p + "attn.qkv.weight"), qkv_b) if _can_fuse_attn(C, heads, 7) else None,
                 pad_q=qkv_b[:C].contiguous(), pad_k=qkv_b[C:2 * C].contiguous(), pad_v=qkv_b[2 * C:].contiguous(),
                 proj=ops.pack_linear(g(p + "attn.proj.weight"), g(p + "attn.proj.bias")),
                 table=g(p + "attn.relative_position_bias_table"),
@@ -100,9 +109,12 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
     o = ws_.bf16(tag + "o", T, C)
     if not ln1_done:
         ops.layernorm(x32, bw["n1w"], bw["n1b"], ln, T, C)
-    ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
-    ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
-                         3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
+    if bw["attn"] is not None:  # q | k | v projections + window attention in one kernel
+        ops.attn_block(ln, bw["attn"], bw["table"], o, Bt, H, W, 7, shift)
+    else:
+        ops.gemm(ln, bw["qkv"], T, out_bf16=qkv)
+        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
+                             3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
     if FUSE_PROJ_MLP:  # x1 = x + proj(o); x = x1 + mlp(LN2(x1)): one kernel, LN2(x1) and the hidden activation stay on chip
         ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"])
         return
@@ -159,6 +171,8 @@ class StyleTransformerWeights:
         bq, bk, bv = g(e + "Wq.bias"), g(e + "Wk.bias"), g(e + "Wv.bias")
         self.C = wq.shape[0]
         self.enc_qkv = ops.pack_linear(torch.cat([wq, wk, wv], 0), torch.cat([bq, bk, bv], 0))
+        self.heads = int(g(e + "relative_position_bias_table").shape[1])
+        self.enc_attn = ops.pack_attn_qkv(wq, wk, wv, bq, bk, bv, self.heads) if _can_fuse_attn(self.C, self.heads, 8) else None
         self.enc_qk = ops.pack_linear(torch.cat([wq, wk], 0), torch.cat([bq, bk], 0))
         self.enc_v = ops.pack_linear(wv, bv)
         self.enc_pad = (bq, bk, bv)
@@ -181,6 +195,8 @@ class StyleTransformerWeights:
         self.dec_qkv = ops.pack_linear(torch.cat([g(a + "Wq.weight"), g(a + "Wk.weight"), g(a + "Wv.weight")], 0),
                                        torch.cat([dbq, dbk, dbv], 0))
         self.dec_pad = (dbq, dbk, dbv)
+        self.dec_attn = (ops.pack_attn_qkv(g(a + "Wq.weight"), g(a + "Wk.weight"), g(a + "Wv.weight"), dbq, dbk, dbv, self.heads)
+                         if _can_fuse_attn(self.C, self.heads, 8) else None)
         self.dec_proj = ops.pack_linear(g(a + "proj.weight"), g(a + "proj.bias"))
         self.dec_table = g(a + "relative_position_bias_table")
         self.dec_mlp = mlp(d + "mlp.") if self.has_dec_mlp else None
@@ -239,6 +255,7 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     mean, rstd = ws_.f32("st_mean", B, C), ws_.f32("st_rstd", B, C)
     kpad = ws_.f32("st_kpad", B, C)
 
+    fuse_attn = w.enc_attn is not None and w.dec_attn is not None and win in (7, 8) and heads == w.heads
     x32.copy_(fc32.reshape(T, C))
     key32.copy_(fs32.reshape(T, C))
     scale32.copy_(key32)
@@ -250,9 +267,12 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     for _ in range(k):
         # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
         def key_pass():
-            ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
-            ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
-                                 pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
+            if fuse_attn:
+                ops.attn_block(key16, w.enc_attn, w.enc_table, o16, B, H, W, win, shift)
+            else:
+                ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
+                ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
+                                     pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
             if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
                 ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
             else:
@@ -283,9 +303,12 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
 
         # ---------------- StyleDecoder ----------------
         ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
-        ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
-        ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
-                             pad_q=w.dec_pad[0], pad_k=w.dec_pad[1], pad_v=w.dec_pad[2])
+        if fuse_attn:
+            ops.attn_block(ln16, w.dec_attn, w.dec_table, o16, B, H, W, win, shift)
+        else:
+            ops.gemm(ln16, w.dec_qkv, T, out_bf16=qkv)
+            ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
+                                 pad_q=w.dec_pad[0], pad_k=w.dec_pad[1], pad_v=w.dec_pad[2])
         if exclude_mlp:  # Query = Fcs + proj(attention) only
             ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
         elif FUSE_PROJ_MLP:

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MstGemm, MstLossTap, MstLossTaps, MstMlp, MstWgrad, MstWindowAttn, MstWindowAttnBwd, check
+from ._lib import MstAttnBlock, MstGemm, MstLossTap, MstLossTaps, MstMlp, MstWgrad, MstWindowAttn, MstWindowAttnBwd, check
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 GATE_NONE, GATE_RELU, GATE_GELU = 0, 1, 2
@@ -53,7 +53,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 
 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
-             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_layernorm": "layernorm_kernel",
+             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -227,6 +227,47 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
     _launch("mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
             flops=2.0 * n_win * heads * n_tok * n_tok * 32 * (3 if v2 is not None else 2),
             desc=f"B={B} H={H} heads={heads} ws={ws} shift={shift} dual={v2 is not None}")
+
+
+class PackedAttnQkv:
+    """Wq | Wk | Wv of a self-attention, packed per head pair for the fused attention-block kernel (csrc/attn_fused.cu)."""
+
+    __slots__ = ("w", "b", "C", "heads")
+
+    def __init__(self, w, b, C_, heads):
+        self.w, self.b, self.C, self.heads = w, b, C_, heads
+
+
+def pack_attn_qkv(wq, wk, wv, bq, bk, bv, heads: int) -> PackedAttnQkv:
+    """Three nn.Linear weights [C,C] (slices of a fused [3C,C] qkv weight work) + biases [C] -> PackedAttnQkv."""
+    wq, wk, wv = (t.detach().contiguous() for t in (wq, wk, wv))
+    bq, bk, bv = (None if t is None else t.detach().contiguous() for t in (bq, bk, bv))
+    Cdim = int(wq.shape[0])
+    nbytes = _lib.lib().mst_attn_qkv_packed_bytes(Cdim, heads)
+    if nbytes == 0 or wq.shape != (Cdim, Cdim) or wk.shape != wq.shape or wv.shape != wq.shape:
+        raise ValueError("pack_attn_qkv: needs square [C,C] weights with C in {128, 256} and head_dim 32")
+    dst_w = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=wq.device)
+    dst_b = torch.empty(3 * Cdim, dtype=torch.float32, device=wq.device)
+    _launch("mst_pack_attn_qkv", lambda: _lib.lib().mst_pack_attn_qkv(
+        _ptr(wq, torch.float32, "wq"), _ptr(wk, torch.float32, "wk"), _ptr(wv, torch.float32, "wv"), _ptr(bq, torch.float32, "bq"),
+        _ptr(bk, torch.float32, "bk"), _ptr(bv, torch.float32, "bv"), dst_w.data_ptr(), dst_b.data_ptr(), Cdim, heads, _stream()))
+    return PackedAttnQkv(dst_w, dst_b, Cdim, heads)
+
+
+def attn_block(x16, pk: PackedAttnQkv, bias_table, out, B, H, W, ws, shift, ldx=None, ldo=None, dbg_qkv=None) -> None:
+    """out = window_attention(x Wq^T + bq, x Wk^T + bk, x Wv^T + bv) before the output projection: the three projections and
+    the shifted-window attention core in ONE kernel (q, k, v stay on chip)."""
+    a = MstAttnBlock()
+    a.x, a.wqkv, a.bqkv = _ptr(x16, torch.bfloat16, "x"), _ptr(pk.w, torch.bfloat16, "wqkv"), _ptr(pk.b, torch.float32, "bqkv")
+    a.bias_table, a.out = _ptr(bias_table, torch.float32, "bias_table"), _ptr(out, torch.bfloat16, "out")
+    a.dbg_qkv = _ptr(dbg_qkv, torch.bfloat16, "dbg_qkv")
+    a.B, a.H, a.W, a.C, a.heads, a.ws, a.shift = B, H, W, pk.C, pk.heads, ws, shift
+    a.ldx, a.ldo = ldx or pk.C, ldo or pk.C
+    T = B * H * W
+    # reference-algorithm FLOPs: three linears on the real tokens + QK^T and PV over ws*ws keys per token
+    _launch("mst_attn_block", lambda: _lib.lib().mst_attn_block(C.byref(a), _stream()),
+            flops=6.0 * T * pk.C * pk.C + 4.0 * T * ws * ws * pk.C, nbytes=4.0 * T * pk.C,
+            desc=f"B={B} H={H} C={pk.C} ws={ws} shift={shift}")
 
 
 def window_maps(H: int, W: int, ws: int, shift: int, device="cuda"):

@@ -200,6 +200,30 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
         _rows(dst, T, C, ldo).copy_(O._from_windows(o, B, Hp, Wp, ws, shift)[:, :H, :W].reshape(T, C))
 
 
+class _AttnQkv:
+    def __init__(self, ws_, bs_, C_, heads):
+        self.w3, self.b3, self.C, self.heads = ws_, bs_, C_, heads
+
+
+def pack_attn_qkv(wq, wk, wv, bq, bk, bv, heads):
+    """bf16-rounded weights, fp32 biases (what mst_pack_attn_qkv stores)."""
+    return _AttnQkv([t.detach().bfloat16().float() for t in (wq, wk, wv)], [t.detach().float() for t in (bq, bk, bv)], int(wq.shape[0]), heads)
+
+
+def attn_block(x16, pk, bias_table, out, B, H, W, ws, shift, ldx=None, ldo=None, dbg_qkv=None):
+    """Contract of mst_attn_block: q, k, v = bf16(x W^T + b) on the zero-padded token map (a padded token's projection is the
+    bias), then the attention core of window_attention()."""
+    C, T = pk.C, B * H * W
+    Hp, Wp = O.padded_dims(H, W, ws)
+    xm = torch.zeros(B, Hp, Wp, C)
+    xm[:, :H, :W] = _rows(x16, T, C, ldx or C).float().reshape(B, H, W, C)
+    xw = O._to_windows(xm, ws, shift)
+    q, k, v = (F.linear(xw, w_, b_).bfloat16().float() for w_, b_ in zip(pk.w3, pk.b3))
+    p = O._softmax_probs(q, k, pk.heads, O._bias_from_table(bias_table, ws), O.shift_mask(Hp, Wp, ws, shift), B)
+    o = O._apply_probs(p, v, pk.heads)
+    _rows(out, T, C, ldo or C).copy_(O._from_windows(o, B, Hp, Wp, ws, shift)[:, :H, :W].reshape(T, C))
+
+
 def conv3x3_first(img, w, b, out, B, H, W, relu=True):
     y = F.conv2d(img[:B], w, b, padding=1)
     if relu:
@@ -238,6 +262,6 @@ def loss_finalize(taps, lam, squared_style, out3):
 
 def install(monkeypatch):
     for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
-                 "instnorm_stats_padded", "instnorm_apply", "window_attention", "upsample2x_nhwc", "patch_embed",
+                 "instnorm_stats_padded", "instnorm_apply", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
                  "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "tap_stats", "content_term", "loss_finalize"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -11,7 +11,7 @@ import pytest
 from mastermetastyletransfer_b200 import _lib
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STRUCTS = ["MstGemm", "MstWgrad", "MstWindowAttnBwd", "MstWindowAttn", "MstMlp", "MstTensorTable", "MstLossTap", "MstLossTaps"]
+STRUCTS = ["MstGemm", "MstWgrad", "MstWindowAttnBwd", "MstWindowAttn", "MstAttnBlock", "MstMlp", "MstTensorTable", "MstLossTap", "MstLossTaps"]
 
 
 @pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")

@@ -359,3 +359,58 @@ def test_proj_mlp_fused(M, C, ln, mul):
     err = (x.cpu() - ref).abs().max()
     assert torch.allclose(x.cpu(), ref, atol=6e-3, rtol=6e-3), err
     assert torch.allclose(out16.float().cpu(), ref, atol=4e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,C,ws,shift", [(1, 8, 256, 8, 0), (2, 32, 256, 8, 4), (1, 24, 256, 8, 4), (2, 32, 256, 7, 4), (1, 16, 256, 7, 3),
+                                            (2, 32, 128, 7, 0), (1, 64, 128, 7, 3), (1, 16, 128, 8, 4), (3, 64, 256, 7, 4)])
+def test_attn_block_fused_vs_oracle(B, H, C, ws, shift):
+    """csrc/attn_fused.cu: the three projections + shifted-window attention in one kernel (q, k, v stay on chip) against the fp32
+    oracle restatement of codes/style_transformer.py:77-155 on the bf16-rounded operands, and its projected q | k | v (test hook)
+    against a plain matmul.  Geometries: unshifted / shifted (wrap-around windows take the cp.async path, the others one TMA box
+    per k-block), 8x8 and zero-padded 7x7 windows, an odd number of windows (24x24 map: nine), both channel counts."""
+    from oracle import master_oracle as O
+    ops = _ops()
+    heads = C // 32
+    g = torch.Generator().manual_seed(100 * H + ws + shift)
+    x = torch.randn(B, H, H, C, generator=g)
+    wq, wk, wv = (torch.randn(C, C, generator=g) * (0.7 / C ** 0.5) for _ in range(3))
+    bq, bk, bv = (torch.randn(C, generator=g) * 0.2 for _ in range(3))
+    table = torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5
+    T = B * H * H
+    x16 = x.cuda().bfloat16().view(T, C).contiguous()
+    pk = ops.pack_attn_qkv(wq.cuda(), wk.cuda(), wv.cuda(), bq.cuda(), bk.cuda(), bv.cuda(), heads)
+    out = torch.zeros(T, C, dtype=torch.bfloat16, device="cuda")
+    dbg = torch.zeros(T, 3 * C, dtype=torch.bfloat16, device="cuda")
+    ops.attn_block(x16, pk, table.cuda(), out, B, H, H, ws, shift, dbg_qkv=dbg)
+    torch.cuda.synchronize()
+    xr = x16.float().cpu()
+    r = lambda t: t.bfloat16().float()
+    qkv_ref = torch.cat([xr @ r(wq).t() + bq, xr @ r(wk).t() + bk, xr @ r(wv).t() + bv], 1)
+    assert (dbg.float().cpu() - qkv_ref).abs().max().item() <= 0.03  # bf16 rounding of O(1) values
+    xw = O._to_windows(xr.view(B, H, H, C), ws, shift)
+    q, k, v = (r(torch.nn.functional.linear(xw, r(w_), b_)) for w_, b_ in ((wq, bq), (wk, bk), (wv, bv)))
+    p = O._softmax_probs(q, k, heads, O._bias_from_table(table, ws), O.shift_mask(H, H, ws, shift), B)
+    ref = O._from_windows(O._apply_probs(p, v, heads), B, H, H, ws, shift).reshape(T, C)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 1.5e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_attn_block_equals_unfused_kernels():
+    """The fused kernel and the kernels it replaces (QKV GEMM + window_attn_kernel) agree to bf16 rounding on a benched shape."""
+    ops = _ops()
+    B, H, C, ws, shift, heads = 4, 32, 256, 8, 4, 8
+    g = torch.Generator().manual_seed(3)
+    T = B * H * H
+    x16 = torch.randn(T, C, generator=g).cuda().bfloat16()
+    w3 = [(torch.randn(C, C, generator=g) * (0.7 / 16)).cuda() for _ in range(3)]
+    b3 = [(torch.randn(C, generator=g) * 0.2).cuda() for _ in range(3)]
+    table = (torch.randn(225, heads, generator=g) * 0.5).cuda()
+    pm = ops.pack_linear(torch.cat(w3, 0), torch.cat(b3, 0))
+    qkv = torch.empty(T, 3 * C, dtype=torch.bfloat16, device="cuda")
+    o_ref = torch.zeros(T, C, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(x16, pm, T, out_bf16=qkv)
+    ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o_ref, table, B, H, H, heads, ws, shift, 3 * C, 3 * C, 3 * C, C)
+    o = torch.zeros(T, C, dtype=torch.bfloat16, device="cuda")
+    ops.attn_block(x16, ops.pack_attn_qkv(*w3, *b3, heads), table, o, B, H, H, ws, shift)
+    torch.cuda.synchronize()
+    assert (o.float() - o_ref.float()).abs().max().item() <= 1e-2
