@@ -210,6 +210,25 @@ int mst_layernorm(const float* x, const float* gamma, const float* beta, mst_bf1
 int mst_patch_merge_layernorm(const float* x, const float* gamma, const float* beta, mst_bf16* y, int B, int H, int W,
                               int C, void* stream);
 int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream);
+/* Affine InstanceNorm2d (decoder_use_instance_norm_with_affine, style_transformer.py:982-984): gamma [C] (or NULL = 1) is folded
+ * into rstd -- once: r*gamma; twice=1 (the same affine module applied to its own output): gamma^2*r/sqrt(gamma^2*var*r^2+eps) --
+ * and mst_instnorm_apply_affine adds beta [C] (or NULL): y = (x-mean)*rstd + beta.  n_pad / pad_val / pad_norm as below
+ * (pad_norm then includes beta); twice and n_pad > 0 together are not supported. */
+int mst_instnorm_stats_affine(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, int n_pad,
+                              const float* pad_val, float* pad_norm, const float* gamma, const float* beta, void* stream);
+int mst_instnorm_apply_affine(const float* x, const float* mean, const float* rstd, const float* beta, mst_bf16* y16, float* y32,
+                              int B, int T, int C, void* stream);
+/* Statistics over (T, C) JOINTLY per image -- what nn.InstanceNorm2d computes when the regular-MHA decoder variant feeds it
+ * [B, C, T] tensors, read as one unbatched image (style_transformer.py:1063-1119).  mean / rstd [B, C] receive the per-image
+ * scalars replicated over C, so mst_instnorm_apply applies them. */
+int mst_jointnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, void* stream);
+/* P[r, :] = softmax(scale * S[r, :]): fp32 scores [rows, n] -> bf16 probabilities (the single-head global attention of the
+ * regular-MHA decoder variant, style_transformer.py:1100-1106); n % 4 == 0, scale > 0. */
+int mst_softmax_rows(const float* S, mst_bf16* P, int rows, int n, float scale, void* stream);
+/* Tile-blocked, pre-swizzled B-operand image (the format of mst_pack_linear_weight) of a bf16 matrix already on the device:
+ * trans = 0: W[n][k] = src[n*ld + k]; trans = 1: W[n][k] = src[k*ld + n].  Used where an ACTIVATION is the second operand of a
+ * GEMM (keys and values of the regular-MHA variant's global attention). */
+int mst_pack_bf16_matrix(const mst_bf16* src, int N, int K, int ld, int trans, mst_bf16* dst, int n_pad, int k_pad, void* stream);
 /* Same statistics over a map that additionally holds n_pad tokens whose value is pad_val[c] (the zero-padded positions of a
  * window-padded map after a Linear: value = its bias; style_transformer.py:520-530 normalises Wk.K over the PADDED map).
  * pad_norm [B, C] (optional) receives the normalised padding value (pad_val - mean) * rstd. */

@@ -109,7 +109,7 @@ struct AttnCfg {
 
 template <int C, int WS>
 __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCore p, const WinGeom g, const __grid_constant__ CUtensorMap tm,
-                                                                   const int use_tma, const int n_tiles, const int total_windows) {
+                                                                   const int use_tma, const int n_tiles, const int total_windows, const int stagger) {
   using Cfg = AttnCfg<C>;
   constexpr int KB = Cfg::KB, XB = Cfg::XB;
   constexpr int N = WS * WS;
@@ -235,57 +235,57 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);  // B (the V tile) is MN-major
     mbar_wait(smem_u32(&w_full), 0);
     tc_fence_after();
-    auto issue_qkv = [&](int lt) {
-      const int buf = lt % XB, u = lt / XB;
-      mbar_wait(smem_u32(&x_full[buf]), u & 1);
-      tc_fence_after();
-      const uint32_t xb = x_base + buf * Cfg::X_BYTES;
+    // The two heads are independent chains  QKV_p(t) -> [drain] -> S_p(t) -> [softmax] -> PV_p(t) -> [output]  that share only the
+    // x tile.  This warp is their event loop: it polls the hand-off barriers of both chains and issues whatever has become
+    // ready, so the chains may drift apart -- and they are STARTED apart (head 1's first QKV is held back until head 0 has
+    // reached its softmax): from then on one head's warps compute while the other head's warps, on the same schedulers, wait
+    // for a tensor-core hand-off or a TMEM load.
+    auto ready = [&](uint64_t* bar, int parity) { return __shfl_sync(0xffffffffu, (int)mbar_test_wait(smem_u32(bar), (uint32_t)parity), 0) != 0; };
+    int t_q[2] = {0, 0}, t_s[2] = {0, 0}, t_pv[2] = {0, 0};  // next tile whose QKV_p / S_p / PV_p is to be issued
+    while (t_pv[0] < n_my || t_pv[1] < n_my) {
 #pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {  // head pp: weight rows 96 pp .. 96 pp + 95 of every k-block
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_pred(tmem_base + pp * AF_COL_ACC, umma_desc_sw128(xb + kb * AF_XKB_BYTES + k * 32),
-                           umma_desc_sw128(w_base + kb * AF_WKB_BYTES + pp * 12288 + k * 32), idesc_qkv, (kb | k) != 0);
-        if (pp == 1) umma_commit_pred(smem_u32(&x_empty[buf]));
-        umma_commit_pred(smem_u32(&acc_full[pp]));
-      }
-    };
-    if (n_my > 0) issue_qkv(0);
-    for (int lt = 0; lt < n_my; ++lt) {
-#pragma unroll 1
       for (int pp = 0; pp < 2; ++pp) {
-        mbar_wait(smem_u32(&qkv_ready[pp]), lt & 1);  // q | k tile and V columns of head pp written, its QKV accumulator drained
-        tc_fence_after();
-        const uint32_t qk = qk_base + pp * 16384;
+        // ---- QKV_p(t): x tile landed, and this head's accumulator drained (its S of the previous tile has been issued)
+        if (t_q[pp] < n_my && t_s[pp] >= t_q[pp]) {
+          const int t = t_q[pp];
+          const bool held = pp == 1 && t == 0 && stagger > 0 && n_my >= 3 && (stagger == 1 ? t_s[0] < 1 : t_pv[0] < 1);
+          const int buf = t % XB, u = t / XB;
+          if (!held && ready(&x_full[buf], u & 1)) {
+            tc_fence_after();
+            const uint32_t xb = x_base + buf * Cfg::X_BYTES;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_bf16_pred(tmem_base + AF_COL_S + pp * 128, umma_desc_sw128(qk + k * 32), umma_desc_sw128(qk + 64 + k * 32), idesc_s, k != 0);
-        umma_commit_pred(smem_u32(&s_full[pp]));
-      }
-      // QKV of the next tile runs on the tensor core while the epilogue warps do this tile's softmax -- if its x tile has
-      // landed; otherwise it is issued after PV (a blocking wait here would hold back PV and with it the output phase)
-      bool next_issued = lt + 1 >= n_my;
-      if (!next_issued && __shfl_sync(0xffffffffu, (int)mbar_try_wait(smem_u32(&x_full[(lt + 1) % XB]), ((lt + 1) / XB) & 1), 0)) {
-        issue_qkv(lt + 1);
-        next_issued = true;
-      }
-#pragma unroll 1
-      for (int pp = 0; pp < 2; ++pp) {
-        mbar_wait(smem_u32(&p_ready[pp]), lt & 1);
-        tc_fence_after();
-        const uint32_t pb = qk_base + pp * 16384;
+            for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+              for (int k = 0; k < 4; ++k)  // head pp: weight rows 96 pp .. 96 pp + 95 of every k-block
+                umma_bf16_pred(tmem_base + pp * AF_COL_ACC, umma_desc_sw128(xb + kb * AF_XKB_BYTES + k * 32),
+                               umma_desc_sw128(w_base + kb * AF_WKB_BYTES + pp * 12288 + k * 32), idesc_qkv, (kb | k) != 0);
+            if (t_q[pp ^ 1] > t) umma_commit_pred(smem_u32(&x_empty[buf]));  // both heads have read this x tile
+            umma_commit_pred(smem_u32(&acc_full[pp]));
+            t_q[pp] = t + 1;
+          }
+        }
+        // ---- S_p(t): q | k tile and V columns written, QKV accumulator drained
+        if (t_s[pp] < t_q[pp] && ready(&qkv_ready[pp], t_s[pp] & 1)) {
+          tc_fence_after();
+          const uint32_t qk = qk_base + pp * 16384;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 16 keys per step: 32 B along K in the P tile, two 8-key groups (2 KB) in the V tile
-            umma_bf16_pred(tmem_base + AF_COL_S + pp * 128 + w * 32, umma_desc_sw128(pb + k * 32),
-                           af_desc_mn_sw128(v_base + w * 8192 + pp * 64 + k * 2048), idesc_pv, k != 0);
-        umma_commit_pred(smem_u32(&o_full[pp]));
-        if (!next_issued && (pp == 1 || __shfl_sync(0xffffffffu, (int)mbar_try_wait(smem_u32(&x_full[(lt + 1) % XB]), ((lt + 1) / XB) & 1), 0))) {
-          issue_qkv(lt + 1);
-          next_issued = true;
+          for (int k = 0; k < 2; ++k)
+            umma_bf16_pred(tmem_base + AF_COL_S + pp * 128, umma_desc_sw128(qk + k * 32), umma_desc_sw128(qk + 64 + k * 32), idesc_s, k != 0);
+          umma_commit_pred(smem_u32(&s_full[pp]));
+          t_s[pp] += 1;
+        }
+        // ---- PV_p(t): P tile written (over q | k), S_p read
+        if (t_pv[pp] < t_s[pp] && ready(&p_ready[pp], t_pv[pp] & 1)) {
+          tc_fence_after();
+          const uint32_t pb = qk_base + pp * 16384;
+#pragma unroll
+          for (int w = 0; w < 2; ++w)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 16 keys per step: 32 B along K in the P tile, two 8-key groups (2 KB) in the V tile
+              umma_bf16_pred(tmem_base + AF_COL_S + pp * 128 + w * 32, umma_desc_sw128(pb + k * 32),
+                             af_desc_mn_sw128(v_base + w * 8192 + pp * 64 + k * 2048), idesc_pv, k != 0);
+          umma_commit_pred(smem_u32(&o_full[pp]));
+          t_pv[pp] += 1;
         }
       }
     }
@@ -617,7 +617,12 @@ static int launch_attn_fused(const MstAttnBlock& a, cudaStream_t st) {
   core.out = reinterpret_cast<bf16*>(a.out);
   core.dbg_qkv = reinterpret_cast<bf16*>(a.dbg_qkv);
   core.B = a.B; core.H = a.H; core.W = a.W; core.heads = a.heads; core.ldx = a.ldx; core.ldo = a.ldo;
-  attn_fused_kernel<C, WS><<<(unsigned)grid, AF_THREADS, Cfg::SMEM_BYTES, st>>>(core, g, tmap, use_tma, n_tiles, (int)total);
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char* e = getenv("MST_ATTN_STAGGER");  // 0: heads start together; 1 (default): head 1 starts when head 0's S is issued; 2: when its PV is
+    stagger = e ? atoi(e) : 1;
+  }
+  attn_fused_kernel<C, WS><<<(unsigned)grid, AF_THREADS, Cfg::SMEM_BYTES, st>>>(core, g, tmap, use_tma, n_tiles, (int)total, stagger);
   return (int)cudaGetLastError();
 }
 

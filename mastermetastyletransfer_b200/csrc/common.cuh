@@ -35,6 +35,21 @@ MST_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (try_wait may park the thread for a system-dependent time; an event loop that polls several
+// barriers must not be held by one of them).
+MST_DEVINL bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // try_wait with a suspend-time hint: the hardware may park the thread (it is woken when the phase completes) for up to `ns`
 // nanoseconds before returning false, instead of returning at once.
 MST_DEVINL bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {

@@ -734,6 +734,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, in
   dst[off] = __float2bfloat16(v);
 }
 
+// The same tile-blocked image from a bf16 matrix that already lives on the device (an ACTIVATION used as the B operand: the keys
+// and the values of the regular-MHA decoder variant's global attention).  trans = 0: W[n][k] = src[n * ld + k];
+// trans = 1: W[n][k] = src[k * ld + n] (the [T, 2C] value tensor read as the [2C, T] operand of P.V).
+__global__ void pack_bf16_kernel(const bf16* __restrict__ src, int N, int K, int ld, int trans, bf16* __restrict__ dst, int n_pad,
+                                 int k_pad, int bn) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pad * k_pad) return;
+  // trans: consecutive threads walk n (the contiguous direction of src), otherwise k
+  const int n = trans ? (int)(i % n_pad) : (int)(i / k_pad);
+  const int k = trans ? (int)(i / n_pad) : (int)(i % k_pad);
+  bf16 v = __float2bfloat16(0.f);
+  if (n < N && k < K) v = trans ? src[(long long)k * ld + n] : src[(long long)n * ld + k];
+  const int nkb = k_pad / 64;
+  const int n_tile = n / bn, r = n - n_tile * bn;
+  const int kb = k / 64, kk = k - kb * 64;
+  const int c = kk >> 3, e = kk & 7;
+  const long long block = ((long long)n_tile * nkb + kb) * bn * 64;
+  dst[block + ((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) / 2 + e] = v;
+}
+
 static int tile_n_for(int n_pad) {
   if (n_pad % 256 == 0) return 256;
   if (n_pad % 128 == 0) return 128;
@@ -753,6 +773,14 @@ extern "C" int mst_pack_linear_weight(const float* w, int N, int K, mst_bf16* ds
   const long long n = (long long)n_pad * k_pad;
   pack_weight_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, N, K, 0, reinterpret_cast<bf16*>(dst),
                                                                                          n_pad, k_pad, tile_n_for(n_pad));
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_pack_bf16_matrix(const mst_bf16* src, int N, int K, int ld, int trans, mst_bf16* dst, int n_pad, int k_pad, void* stream) {
+  if (!src || !dst || N <= 0 || K <= 0 || n_pad < N || k_pad < K || n_pad % 16 || k_pad % 64 || ld < (trans ? N : K)) return MST_ERR_BAD_ARG;
+  const long long n = (long long)n_pad * k_pad;
+  pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(src), N, K, ld, trans,
+                                                                                  reinterpret_cast<bf16*>(dst), n_pad, k_pad, tile_n_for(n_pad));
   return (int)cudaGetLastError();
 }
 

@@ -58,71 +58,81 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- InstanceNorm statistics
-// x [B,T,C] fp32.  CTA = (b, 32-channel group); 16 warps stride over T, lane = channel (128 B rows), four rows in flight
-// per warp (the kernel is latency-bound: a CTA's slice is only T*128 B).  Two passes (mean, then centred second moment)
-// as torch's InstanceNorm2d does (biased variance); the second pass re-reads the slice from L1/L2.
+// x [B,T,C] fp32.  CTA = (b, 32-channel group); 16 warps stride over T, lane = channel (128 B rows), EIGHT rows in flight per
+// warp (a CTA's slice is only T*128 B: the kernel is latency-bound, bytes in flight are what counts -- 16 KB per CTA).  ONE pass
+// over HBM: shifted sums  sum(x - K), sum((x - K)^2)  with K = the channel's first row, so the cancellation of the textbook
+// one-pass formula does not arise (|mean - K| is of the order of the standard deviation), fp32 accumulation over <= 8 partial
+// sums per thread and a 16-way tree; biased variance as nn.InstanceNorm2d.
+// Affine variant (decoder_use_instance_norm_with_affine, codes/style_transformer.py:982-984): gamma [C] folds into the scale the
+// apply kernel multiplies with -- once: r*gamma; twice (the same affine module applied to its own output, :1056 then :468):
+// gamma^2 * r / sqrt(gamma^2 * var * r^2 + eps) -- and beta [C] is added by the apply kernel (and to pad_norm).
 constexpr int IN_WARPS = 16;
+constexpr int IN_UNROLL = 8;
 __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean,
                                                                         float* __restrict__ rstd, int T, int C, int twice, int n_pad,
-                                                                        const float* __restrict__ pad_val, float* __restrict__ pad_norm) {
-  __shared__ float red[IN_WARPS][33];
+                                                                        const float* __restrict__ pad_val, float* __restrict__ pad_norm,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta) {
+  __shared__ float red[2][IN_WARPS][33];
   const int groups = C / 32;
   const int b = blockIdx.x / groups;
   const int c = (blockIdx.x - b * groups) * 32 + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* xb = x + (long long)b * T * C + c;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int t = warp;
-  for (; t + 3 * IN_WARPS < T; t += 4 * IN_WARPS) {
-    s0 += xb[(long long)t * C];
-    s1 += xb[(long long)(t + IN_WARPS) * C];
-    s2 += xb[(long long)(t + 2 * IN_WARPS) * C];
-    s3 += xb[(long long)(t + 3 * IN_WARPS) * C];
-  }
-  for (; t < T; t += IN_WARPS) s0 += xb[(long long)t * C];
-  red[warp][lane] = (s0 + s1) + (s2 + s3);
-  __syncthreads();
-  float m = 0.f;
+  const float K = xb[0];
+  float s[IN_UNROLL], q[IN_UNROLL];
 #pragma unroll
-  for (int w = 0; w < IN_WARPS; ++w) m += red[w][lane];
-  // n_pad extra tokens of value pad_val[c]: the zero-padded positions of a window-padded map after a Linear (= its bias)
-  const float pv = n_pad > 0 ? pad_val[c] : 0.f;
-  const float n_tot = (float)(T + n_pad);
-  m = (m + (float)n_pad * pv) / n_tot;
-  __syncthreads();
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-  t = warp;
-  for (; t + 3 * IN_WARPS < T; t += 4 * IN_WARPS) {
-    const float d0 = xb[(long long)t * C] - m, d1 = xb[(long long)(t + IN_WARPS) * C] - m;
-    const float d2 = xb[(long long)(t + 2 * IN_WARPS) * C] - m, d3 = xb[(long long)(t + 3 * IN_WARPS) * C] - m;
-    q0 += d0 * d0; q1 += d1 * d1; q2 += d2 * d2; q3 += d3 * d3;
+  for (int u = 0; u < IN_UNROLL; ++u) s[u] = q[u] = 0.f;
+  int t = warp;
+  for (; t + (IN_UNROLL - 1) * IN_WARPS < T; t += IN_UNROLL * IN_WARPS) {
+    float v[IN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u) v[u] = xb[(long long)(t + u * IN_WARPS) * C];
+#pragma unroll
+    for (int u = 0; u < IN_UNROLL; ++u) {
+      const float d = v[u] - K;
+      s[u] += d;
+      q[u] = fmaf(d, d, q[u]);
+    }
   }
   for (; t < T; t += IN_WARPS) {
-    const float d = xb[(long long)t * C] - m;
-    q0 += d * d;
+    const float d = xb[(long long)t * C] - K;
+    s[0] += d;
+    q[0] = fmaf(d, d, q[0]);
   }
-  red[warp][lane] = (q0 + q1) + (q2 + q3);
+  red[0][warp][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  red[1][warp][lane] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
   __syncthreads();
   if (warp == 0) {
-    float var = 0.f;
+    float S = 0.f, Q = 0.f;
 #pragma unroll
-    for (int w = 0; w < IN_WARPS; ++w) var += red[w][lane];
-    var = (var + (float)n_pad * (pv - m) * (pv - m)) / n_tot;
+    for (int w = 0; w < IN_WARPS; ++w) { S += red[0][w][lane]; Q += red[1][w][lane]; }
+    // n_pad extra tokens of value pad_val[c]: the zero-padded positions of a window-padded map after a Linear (= its bias)
+    const float pv = n_pad > 0 ? pad_val[c] : 0.f;
+    const float n_tot = (float)(T + n_pad);
+    const float dp = pv - K;
+    S += (float)n_pad * dp;
+    Q += (float)n_pad * dp * dp;
+    const float ms = S / n_tot;                       // mean - K
+    const float var = fmaxf(Q / n_tot - ms * ms, 0.f);
+    const float m = K + ms;
     float r = 1.0f / sqrtf(var + 1e-5f);
+    const float g = gamma ? gamma[c] : 1.0f;
     if (twice) {
-      // IN(IN(x)): the once-normalised tensor has mean 0 and variance var*r^2, so the second pass
-      // multiplies by 1/sqrt(var*r^2 + eps) (codes/style_transformer.py:1056 then :468)
-      r *= 1.0f / sqrtf(var * r * r + 1e-5f);
+      // IN(IN(x)): the once-normalised tensor has mean beta and variance g^2*var*r^2, so the second pass multiplies by
+      // g / sqrt(g^2*var*r^2 + eps) (codes/style_transformer.py:1056 then :468)
+      r *= g * g / sqrtf(g * g * var * r * r + 1e-5f);
+    } else {
+      r *= g;
     }
     mean[(long long)b * C + c] = m;
     rstd[(long long)b * C + c] = r;
-    if (pad_norm) pad_norm[(long long)b * C + c] = (pv - m) * r;
+    if (pad_norm) pad_norm[(long long)b * C + c] = (pv - m) * r + (beta ? beta[c] : 0.f);
   }
 }
 
 __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, bf16* __restrict__ y16,
-                                                             float* __restrict__ y32, long long n4, int TC4, int C4) {
+                                                             const float* __restrict__ rstd, const float* __restrict__ beta,
+                                                             bf16* __restrict__ y16, float* __restrict__ y32, long long n4, int TC4, int C4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const int b = (int)(i / TC4);
@@ -130,11 +140,81 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float* __rest
   const float4 v = reinterpret_cast<const float4*>(x)[i];
   const float4 m = reinterpret_cast<const float4*>(mean)[(long long)b * C4 + c4];
   const float4 r = reinterpret_cast<const float4*>(rstd)[(long long)b * C4 + c4];
-  const float4 o = make_float4((v.x - m.x) * r.x, (v.y - m.y) * r.y, (v.z - m.z) * r.z, (v.w - m.w) * r.w);
+  const float4 be = beta ? reinterpret_cast<const float4*>(beta)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 o = make_float4(fmaf(v.x - m.x, r.x, be.x), fmaf(v.y - m.y, r.y, be.y), fmaf(v.z - m.z, r.z, be.z), fmaf(v.w - m.w, r.w, be.w));
   if (y32) reinterpret_cast<float4*>(y32)[i] = o;
   if (y16) {
     __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
     reinterpret_cast<uint2*>(y16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+// Statistics of an image taken over (T, C) JOINTLY: the regular-MHA decoder variant hands [B, C, T] tensors to nn.InstanceNorm2d,
+// which reads a 3-D input as ONE unbatched image and normalises over all of its elements (codes/style_transformer.py:1063-1119).
+// One CTA per image; the scalar mean / rstd are written replicated to mean[b, :] / rstd[b, :] so that instnorm_apply applies them.
+__global__ void __launch_bounds__(1024) jointnorm_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
+                                                               long long n, int C) {
+  __shared__ double red[2][32];
+  const float* xb = x + (long long)blockIdx.x * n;
+  const float K = xb[0];
+  float s = 0.f, q = 0.f;
+  double S = 0.0, Q = 0.0;
+  int cnt = 0;
+  for (long long i = (long long)threadIdx.x * 4; i < n; i += 4096) {  // n % 4 == 0 (C % 4 == 0)
+    const float4 v = *reinterpret_cast<const float4*>(xb + i);
+    const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
+    s += (d0 + d1) + (d2 + d3);
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    if (++cnt == 64) { S += s; Q += q; s = q = 0.f; cnt = 0; }  // fp32 runs of 256 elements, fp64 across runs
+  }
+  S += s; Q += q;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = S; red[1][threadIdx.x >> 5] = Q; }
+  __syncthreads();
+  __shared__ float out2[2];
+  if (threadIdx.x == 0) {
+    double St = 0.0, Qt = 0.0;
+    for (int w = 0; w < 32; ++w) { St += red[0][w]; Qt += red[1][w]; }
+    const double ms = St / (double)n, var = Qt / (double)n - ms * ms;
+    out2[0] = (float)((double)K + ms);
+    out2[1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    mean[(long long)blockIdx.x * C + c] = out2[0];
+    rstd[(long long)blockIdx.x * C + c] = out2[1];
+  }
+}
+
+// ---------------------------------------------------------------- row softmax (regular-MHA decoder variant)
+// P[r, :] = softmax(scale * S[r, :]) for fp32 scores S [rows, n] -> bf16 probabilities (codes/style_transformer.py:1100-1106: one
+// head over all T tokens of an image).  One warp per row, the row is read twice (max, then exp + sum) and the probabilities are
+// written normalised; n % 4 == 0.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int rows, int n, float scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* s4 = reinterpret_cast<const float4*>(S + (long long)row * n);
+  const int n4 = n >> 2;
+  const float sc = scale * 1.4426950408889634f;
+  float mx = -INFINITY;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = s4[i];
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx) * sc;
+  float sum = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = s4[i];
+    sum += (exp2f(fmaf(v.x, sc, -mx)) + exp2f(fmaf(v.y, sc, -mx))) + (exp2f(fmaf(v.z, sc, -mx)) + exp2f(fmaf(v.w, sc, -mx)));
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  uint2* p2 = reinterpret_cast<uint2*>(P + (long long)row * n);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 v = s4[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(exp2f(fmaf(v.x, sc, -mx)) * inv, exp2f(fmaf(v.y, sc, -mx)) * inv);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(exp2f(fmaf(v.z, sc, -mx)) * inv, exp2f(fmaf(v.w, sc, -mx)) * inv);
+    p2[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
   }
 }
 
@@ -461,14 +541,35 @@ extern "C" int mst_patch_merge_layernorm(const float* x, const float* gamma, con
 
 extern "C" int mst_instnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, void* stream) {
   if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0) return MST_ERR_BAD_ARG;
-  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice, 0, nullptr, nullptr);
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice, 0, nullptr, nullptr, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_instnorm_stats_affine(const float* x, float* mean, float* rstd, int B, int T, int C, int twice, int n_pad,
+                                         const float* pad_val, float* pad_norm, const float* gamma, const float* beta, void* stream) {
+  if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0 || n_pad < 0 || (n_pad > 0 && !pad_val)) return MST_ERR_BAD_ARG;
+  if (twice && n_pad > 0) return MST_ERR_UNSUPPORTED;
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, twice, n_pad, pad_val, pad_norm, gamma, beta);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_softmax_rows(const float* S, mst_bf16* P, int rows, int n, float scale, void* stream) {
+  if (!S || !P || rows <= 0 || n <= 0 || n % 4 != 0 || (reinterpret_cast<uintptr_t>(S) & 15) || (reinterpret_cast<uintptr_t>(P) & 7)) return MST_ERR_BAD_ARG;
+  if (scale <= 0.f) return MST_ERR_BAD_ARG;  // (the row maximum is scaled with the scores: a positive scale keeps it the maximum)
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(S, reinterpret_cast<bf16*>(P), rows, n, scale);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_jointnorm_stats(const float* x, float* mean, float* rstd, int B, int T, int C, void* stream) {
+  if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return MST_ERR_BAD_ARG;
+  jointnorm_stats_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(x, mean, rstd, (long long)T * C, C);
   return (int)cudaGetLastError();
 }
 
 extern "C" int mst_instnorm_stats_padded(const float* x, float* mean, float* rstd, int B, int T, int C, int n_pad, const float* pad_val,
                                          float* pad_norm, void* stream) {
   if (!x || !mean || !rstd || B <= 0 || T <= 0 || C <= 0 || C % 32 != 0 || n_pad < 0 || (n_pad > 0 && !pad_val)) return MST_ERR_BAD_ARG;
-  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, 0, n_pad, pad_val, pad_norm);
+  instnorm_stats_kernel<<<B * (C / 32), IN_WARPS * 32, 0, (cudaStream_t)stream>>>(x, mean, rstd, T, C, 0, n_pad, pad_val, pad_norm, nullptr, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -477,7 +578,17 @@ extern "C" int mst_instnorm_apply(const float* x, const float* mean, const float
   if (!x || !mean || !rstd || (!y16 && !y32) || B <= 0 || T <= 0 || C <= 0 || C % 4 != 0) return MST_ERR_BAD_ARG;
   const long long n4 = (long long)B * T * C / 4;
   instnorm_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, mean, rstd, reinterpret_cast<bf16*>(y16), y32, n4, T * C / 4, C / 4);
+      x, mean, rstd, nullptr, reinterpret_cast<bf16*>(y16), y32, n4, T * C / 4, C / 4);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_instnorm_apply_affine(const float* x, const float* mean, const float* rstd, const float* beta, mst_bf16* y16, float* y32,
+                                         int B, int T, int C, void* stream) {
+  if (!x || !mean || !rstd || (!y16 && !y32) || B <= 0 || T <= 0 || C <= 0 || C % 4 != 0) return MST_ERR_BAD_ARG;
+  if (beta && (reinterpret_cast<uintptr_t>(beta) & 15)) return MST_ERR_BAD_ARG;
+  const long long n4 = (long long)B * T * C / 4;
+  instnorm_apply_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, mean, rstd, beta, reinterpret_cast<bf16*>(y16), y32, n4, T * C / 4, C / 4);
   return (int)cudaGetLastError();
 }
 

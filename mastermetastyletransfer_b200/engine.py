@@ -201,6 +201,19 @@ class StyleTransformerWeights:
         self.dec_table = g(a + "relative_position_bias_table")
         self.dec_mlp = mlp(d + "mlp.") if self.has_dec_mlp else None
         self.pm_dec = mlp(d + "mlp.", a + "proj.") if self.has_dec_mlp else None
+        # decoder_use_instance_norm_with_affine (:982-984): separate affine InstanceNorm2d modules for Query and Key
+        has = lambda k: (prefix + k) in sd
+        self.affine_q = (g("decoder.instance_norm_Query.weight"), g("decoder.instance_norm_Query.bias")) if has("decoder.instance_norm_Query.weight") else None
+        self.affine_k = (g("decoder.instance_norm_Key.weight"), g("decoder.instance_norm_Key.bias")) if has("decoder.instance_norm_Key.weight") else None
+        # decoder_use_regular_MHA_instead_of_Swin_at_the_end (:1063-1119): five plain Linears instead of the windowed sigma/mu attention
+        self.regular_mha = has("decoder.linear_transformation_Key.weight")
+        self.last_mlp = mlp("decoder.last_MLP.")
+        if self.regular_mha:
+            lin = lambda n: ops.pack_linear(g(f"decoder.{n}.weight"), g(f"decoder.{n}.bias"))
+            self.rg_k, self.rg_vs, self.rg_vh = lin("linear_transformation_Key"), lin("linear_transformation_Scale"), lin("linear_transformation_Shift")
+            self.rg_proj_sigma, self.rg_proj_mu = lin("proj_sigma"), lin("proj_mu")
+            self.pm_last = mlp("decoder.last_MLP.", "decoder.proj_mu.")
+            return
         m = "decoder.decoder_MHA_for_sigma_and_mu."
         self.sm_k = ops.pack_linear(g(m + "Wk.weight"), g(m + "Wk.bias"))
         self.sm_vs = ops.pack_linear(g(m + "Wv_scale.weight"), g(m + "Wv_scale.bias"))
@@ -208,7 +221,6 @@ class StyleTransformerWeights:
         self.sm_pad = (g(m + "Wk.bias"), g(m + "Wv_scale.bias"), g(m + "Wv_shift.bias"))
         self.sm_proj = ops.pack_linear(g(m + "proj.weight"), g(m + "proj.bias"))
         self.sm_table = g(m + "relative_position_bias_table")
-        self.last_mlp = mlp("decoder.last_MLP.")
         self.pm_last = mlp("decoder.last_MLP.", m + "proj.")
 
 
@@ -317,23 +329,30 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
             ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
             ops.layernorm(x32, w.n2[0], w.n2[1], ln16, T, C)
             _mlp_residual(ln16, x32, w.dec_mlp, T, ws_, None)  # x32 = Query
-        # Query is instance-normalised twice (:1056 then :468); Key once before Wk and once after (:1057, :520-530)
-        ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True)
-        ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16)
-        ops.instnorm_stats(key32, mean, rstd, B, H * W, C, twice=not key_in_after_linear)
-        ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16)
+        if w.regular_mha:
+            _regular_mha_tail(w, x32, key32, key16, scale16, shift16, x16, ws_, B, H * W, C, key_in_after_linear)
+            continue
+        # Query is instance-normalised twice (:1056 then :468); Key once before Wk and once after (:1057, :520-530).  With
+        # decoder_use_instance_norm_with_affine both normalisations of a tensor go through the SAME affine module (:982-984,1052-1054)
+        gq, bq_ = w.affine_q if w.affine_q is not None else (None, None)
+        gk, bk_ = w.affine_k if w.affine_k is not None else (None, None)
+        ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True, gamma=gq)
+        ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16, beta=bq_)
+        ops.instnorm_stats(key32, mean, rstd, B, H * W, C, twice=not key_in_after_linear, gamma=gk)
+        ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16, beta=bk_)
         if not key_in_after_linear:  # IN(IN(Key)) on the unpadded map, then k = Wk.Key + bk as it is
             ops.gemm(ln16, w.sm_k, T, out_bf16=khat16)
         else:
             ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
             if padded:  # statistics over the padded map: its n_pad extra tokens all hold Wk.0 + bk = bk
-                ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad)
+                ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad, gamma=gk, beta=bk_)
             else:
-                ops.instnorm_stats(kk32, mean, rstd, B, H * W, C)
-            ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16)
+                ops.instnorm_stats(kk32, mean, rstd, B, H * W, C, gamma=gk)
+            ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16, beta=bk_)
         ops.gemm(scale16, w.sm_vs, T, out_bf16=vs16)
         ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
-        # padded tokens: q = 0 (no Q projection, :511-514), k = the normalised bias (per image), v = the value biases
+        # padded tokens: q = IN(0) (no Q projection, :511-514: zero without the affine bias), k = the normalised bias (per image),
+        # v = the value biases
         ops.window_attention(qhat16, khat16, vs16, o16, w.sm_table, B, H, W, heads, win, shift, C, C, C, C, v2=vh16, out2=o2_16,
                              pad_k=(kpad if key_in_after_linear else w.sm_pad[0]) if padded else None,
                              pad_v=w.sm_pad[1], pad_v2=w.sm_pad[2], pad_k_per_image=padded and key_in_after_linear)
@@ -343,6 +362,56 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         else:
             ops.gemm(o2_16, w.sm_proj, T, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16)  # Query*sigma + mu (:1123)
             _mlp_residual(x16, x32, w.last_mlp, T, ws_, x16)
+
+
+def _regular_mha_tail(w: StyleTransformerWeights, x32, key32, key16, scale16, shift16, x16, ws_: Workspace, B: int, Ti: int, C: int,
+                      key_in_after_linear: bool):
+    """decoder_use_regular_MHA_instead_of_Swin_at_the_end (codes/style_transformer.py:1063-1119): ONE head over all Ti = H*W tokens
+    of an image.  q = IN(Query) * C^-0.5 with no projection, k / v_scale / v_shift through linear_transformation_*, separate
+    proj_sigma / proj_mu; the reference's InstanceNorm2d reads the [B, C, T] tensors as one unbatched image, i.e. normalises over
+    (C, T) jointly (mst_jointnorm_stats).  Sequenced from the tensor-core GEMM with the image's keys / values packed as the B
+    operand: S = Q K^T (fp32, [Ti, Ti] per image), row softmax, O = P [V_scale | V_shift]; then sigma = proj_sigma(O_s) and
+    Query*sigma + proj_mu(O_h) + last_MLP through the fused projection + MLP kernel.  x32 holds Query on entry, the layer
+    output on exit."""
+    T = B * Ti
+    mean, rstd = ws_.f32("st_mean", B, C), ws_.f32("st_rstd", B, C)
+    qhat16, khat16 = ws_.bf16("st_qhat", T, C), ws_.bf16("st_khat", T, C)
+    ln16 = ws_.bf16("st_ln", T, C)
+    kk32, sigma32 = ws_.f32("st_kk32", T, C), ws_.f32("st_sigma32", T, C)
+    vcat = ws_.bf16("rg_vcat", T, 2 * C)   # [v_scale | v_shift] per token
+    ocat = ws_.bf16("rg_ocat", T, 2 * C)   # [P v_scale | P v_shift]
+    S = ws_.f32("rg_scores", Ti, Ti)
+    P = ws_.bf16("rg_probs", Ti, Ti)
+    NC = min(Ti, 1024)  # keys per score GEMM (mst_gemm takes N <= 1024)
+    kpack = ws_.bf16("rg_kpack", NC, ops.round_up(C, 64))
+    vpack = ws_.bf16("rg_vpack", ops.n_pad_of(2 * C), ops.round_up(Ti, 64))
+    ops.jointnorm_stats(x32, mean, rstd, B, Ti, C)
+    ops.instnorm_apply(x32, mean, rstd, B, Ti, C, y16=qhat16)
+    if key_in_after_linear:
+        ops.gemm(key16, w.rg_k, T, out_f32=kk32)
+        ops.jointnorm_stats(kk32, mean, rstd, B, Ti, C)
+        ops.instnorm_apply(kk32, mean, rstd, B, Ti, C, y16=khat16)
+    else:
+        ops.jointnorm_stats(key32, mean, rstd, B, Ti, C)
+        ops.instnorm_apply(key32, mean, rstd, B, Ti, C, y16=ln16)
+        ops.gemm(ln16, w.rg_k, T, out_bf16=khat16)
+    ops.gemm(scale16, w.rg_vs, T, out_bf16=vcat, ld_out16=2 * C)
+    ops.gemm(shift16, w.rg_vh, T, out_bf16=vcat[:, C:], ld_out16=2 * C)
+    for b in range(B):
+        rows = slice(b * Ti, (b + 1) * Ti)
+        for j0 in range(0, Ti, NC):
+            nc = min(NC, Ti - j0)
+            pk = ops.pack_bf16_matrix(khat16[b * Ti + j0: b * Ti + j0 + nc], nc, C, C, dst=kpack)
+            ops.gemm(qhat16[rows], pk, Ti, out_f32=S[:, j0:], ld_out32=Ti)
+        ops.softmax_rows(S, P, Ti, Ti, float(C) ** -0.5)
+        pv = ops.pack_bf16_matrix(vcat[rows], 2 * C, Ti, 2 * C, trans=True, dst=vpack)
+        ops.gemm(P, pv, Ti, out_bf16=ocat[rows])
+    ops.gemm(ocat, w.rg_proj_sigma, T, lda=2 * C, out_f32=sigma32)
+    if FUSE_PROJ_MLP:
+        ops.mlp_fused(ocat[:, C:], w.pm_last, T, lda=2 * C, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16, pre=True)
+    else:
+        ops.gemm(ocat[:, C:], w.rg_proj_mu, T, lda=2 * C, res=x32, mul=sigma32, out_f32=x32, out_bf16=x16)
+        _mlp_residual(x16, x32, w.last_mlp, T, ws_, x16)
 
 
 # --------------------------------------------------------------------------------------------

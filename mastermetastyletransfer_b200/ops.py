@@ -55,7 +55,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
              "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
-             "mst_instnorm_apply": "instnorm_apply_kernel", "mst_patch_embed": "patch_embed_kernel",
+             "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
@@ -117,6 +117,21 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> Pa
     dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=w.device)
     _launch("mst_pack_linear_weight", lambda: _lib.lib().mst_pack_linear_weight(_ptr(w, torch.float32, "weight"), N, K, dst.data_ptr(), n_pad, k_pad, _stream()))
     return PackedMatrix(dst, _pad_bias(bias, n_pad, w.device), N, K, n_pad, k_pad)
+
+
+def pack_bf16_matrix(src: torch.Tensor, N: int, K: int, ld: int, trans: bool = False, dst: Optional[torch.Tensor] = None) -> PackedMatrix:
+    """A bf16 device matrix (an activation) as the packed B operand of gemm(): W[n][k] = src[n*ld+k], or src[k*ld+n] if trans."""
+    n_pad, k_pad = n_pad_of(N), round_up(K, 64)
+    if dst is None:
+        dst = torch.empty(n_pad, k_pad, dtype=torch.bfloat16, device=src.device)
+    _launch("mst_pack_bf16_matrix", lambda: _lib.lib().mst_pack_bf16_matrix(_ptr(src, torch.bfloat16, "src"), N, K, ld, int(trans),
+                                                                           _ptr(dst, torch.bfloat16, "dst"), n_pad, k_pad, _stream()))
+    return PackedMatrix(dst, None, N, K, n_pad, k_pad)
+
+
+def softmax_rows(S: torch.Tensor, P: torch.Tensor, rows: int, n: int, scale: float) -> None:
+    _launch("mst_softmax_rows", lambda: _lib.lib().mst_softmax_rows(_ptr(S, torch.float32, "S"), _ptr(P, torch.bfloat16, "P"), rows, n,
+                                                                   float(scale), _stream()), nbytes=10.0 * rows * n)
 
 
 def pack_conv3x3(weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedMatrix:
@@ -293,24 +308,51 @@ def patch_merge_layernorm(x, gamma, beta, y, B, H, W, Cdim) -> None:
                                                _stream()), nbytes=6.0 * B * H * W * Cdim)
 
 
-def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False) -> None:
-    _launch("mst_instnorm_stats", lambda: _lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
-                                        _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), _stream()),
+def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False, gamma=None) -> None:
+    """gamma [C]: the affine InstanceNorm's weight, folded into rstd (see mst_instnorm_stats_affine); pass the bias to
+    instnorm_apply(beta=...)."""
+    if gamma is None:
+        fn = lambda: _lib.lib().mst_instnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                                   _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), _stream())
+    else:
+        fn = lambda: _lib.lib().mst_instnorm_stats_affine(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                                          _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, int(twice), 0, None, None,
+                                                          _ptr(gamma, torch.float32, "gamma"), None, _stream())
+    _launch("mst_instnorm_stats", fn, nbytes=4.0 * B * T * Cdim)
+
+
+def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None, gamma=None, beta=None) -> None:
+    """InstanceNorm statistics over a map with n_pad extra tokens of value pad_val[c] (window-padded map after a Linear);
+    pad_norm [B,C] receives the normalised padding value (affine: gamma folded into rstd, beta added to pad_norm)."""
+    if gamma is None and beta is None:
+        fn = lambda: _lib.lib().mst_instnorm_stats_padded(
+            _ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"), _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, n_pad,
+            _ptr(pad_val, torch.float32, "pad_val"), _ptr(pad_norm, torch.float32, "pad_norm"), _stream())
+    else:
+        fn = lambda: _lib.lib().mst_instnorm_stats_affine(
+            _ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"), _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, 0, n_pad,
+            _ptr(pad_val, torch.float32, "pad_val"), _ptr(pad_norm, torch.float32, "pad_norm"), _ptr(gamma, torch.float32, "gamma"),
+            _ptr(beta, torch.float32, "beta"), _stream())
+    _launch("mst_instnorm_stats", fn, nbytes=4.0 * B * T * Cdim)
+
+
+def jointnorm_stats(x, mean, rstd, B, T, Cdim) -> None:
+    """mean / rstd of every image over (T, C) jointly, replicated into [B, C] (the regular-MHA variant's InstanceNorm quirk)."""
+    _launch("mst_jointnorm_stats", lambda: _lib.lib().mst_jointnorm_stats(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                                                         _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, _stream()),
             nbytes=4.0 * B * T * Cdim)
 
 
-def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None) -> None:
-    """InstanceNorm statistics over a map with n_pad extra tokens of value pad_val[c] (window-padded map after a Linear);
-    pad_norm [B,C] receives the normalised padding value."""
-    _launch("mst_instnorm_stats", lambda: _lib.lib().mst_instnorm_stats_padded(
-        _ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"), _ptr(rstd, torch.float32, "rstd"), B, T, Cdim, n_pad,
-        _ptr(pad_val, torch.float32, "pad_val"), _ptr(pad_norm, torch.float32, "pad_norm"), _stream()), nbytes=4.0 * B * T * Cdim)
-
-
-def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None) -> None:
-    _launch("mst_instnorm_apply", lambda: _lib.lib().mst_instnorm_apply(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
-                                        _ptr(rstd, torch.float32, "rstd"), _ptr(y16, torch.bfloat16, "y16"),
-                                        _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream()),
+def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None, beta=None) -> None:
+    if beta is None:
+        fn = lambda: _lib.lib().mst_instnorm_apply(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                                   _ptr(rstd, torch.float32, "rstd"), _ptr(y16, torch.bfloat16, "y16"),
+                                                   _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream())
+    else:
+        fn = lambda: _lib.lib().mst_instnorm_apply_affine(_ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"),
+                                                          _ptr(rstd, torch.float32, "rstd"), _ptr(beta, torch.float32, "beta"),
+                                                          _ptr(y16, torch.bfloat16, "y16"), _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream())
+    _launch("mst_instnorm_apply", fn,
             nbytes=B * T * Cdim * (4.0 + (2.0 if y16 is not None else 0.0) + (4.0 if y32 is not None else 0.0)))
 
 

@@ -316,13 +316,14 @@ class StyleTransformer(nn.Module):
                      and encoder_mlp_ratio == decoder_mlp_ratio == 4.0
                      and encoder_norm_layer is None and decoder_norm_layer is nn.LayerNorm
                      and encoder_MLP_activation_layer is nn.GELU and decoder_MLP_activation_layer is nn.GELU
-                     and not decoder_use_instance_norm_with_affine and not decoder_use_regular_MHA_instead_of_Swin_at_the_end
                      and encoder_qkv_bias and decoder_qkv_bias and encoder_proj_bias and decoder_proj_bias
                      and encoder_dropout == decoder_dropout == encoder_attention_dropout == decoder_attention_dropout == 0.0),
             # alternates the inference engine sequences from the same kernels (reference :883-909, :470-472, :389-392)
             flags=dict(processed_key=bool(encoder_if_use_processed_Key_in_Scale_and_Shift_calculation),
                        key_in_after_linear=bool(decoder_use_Key_instance_norm_after_linear_transformation),
-                       exclude_mlp=bool(decoder_exclude_MLP_after_Fcs_self_MHA)))
+                       exclude_mlp=bool(decoder_exclude_MLP_after_Fcs_self_MHA)),
+            # variants with kernels of their own in the inference engine (packed from the state_dict: engine.StyleTransformerWeights)
+            affine_in=bool(decoder_use_instance_norm_with_affine), regular_mha=bool(decoder_use_regular_MHA_instead_of_Swin_at_the_end))
 
     def engine_flags(self) -> dict:
         """Keyword arguments of engine.style_transformer_forward that select the reference's alternate orderings."""
@@ -331,9 +332,9 @@ class StyleTransformer(nn.Module):
     def _check_config(self, training: bool = False):
         c = self._cfg
         if not c["default"]:
-            raise NotImplementedError("this StyleTransformer configuration has no sm_100a kernels (affine InstanceNorm, regular MHA at "
-                                      "the end, dropout, non-GELU / non-LayerNorm variants: SURVEY.md 8f-4)")
-        if training and c["flags"] != dict(processed_key=True, key_in_after_linear=True, exclude_mlp=False):
+            raise NotImplementedError("this StyleTransformer configuration has no sm_100a kernels (dropout, non-GELU / non-LayerNorm "
+                                      "variants, different encoder / decoder geometry: SURVEY.md 8f-4)")
+        if training and (c["flags"] != dict(processed_key=True, key_in_after_linear=True, exclude_mlp=False) or c["affine_in"] or c["regular_mha"]):
             raise NotImplementedError("the training step (taped forward + backward kernels) is built for the reference's default "
                                       "StyleTransformer configuration only; the alternate orderings run in inference (SURVEY.md 8f-4)")
         if c["window"][0] != c["window"][1] or c["shift"][0] != c["shift"][1] or c["dim"] // c["heads"] != 32:

@@ -38,9 +38,11 @@ ALTERNATE_CONFIGS = {
 ALTERNATE_CONFIGS["all_three"] = ({k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[0].items()},
                                   {k: v for c in list(ALTERNATE_CONFIGS.values()) for k, v in c[1].items()})
 
-# Variants without kernels yet (the product builds the modules -- same state_dict layout -- and refuses to run them): the
-# oracle is pinned to the real reference for them too, so the kernels of a later round have a checker.
-ORACLE_ONLY_CONFIGS = {
+# Variants with kernels of their own (round 2): affine InstanceNorm (gamma folded into the statistics kernel's scale, beta added
+# by the apply kernel) and the regular-MHA decoder tail (joint (C,T) normalisation + one-head global attention sequenced from
+# the tensor-core GEMM with packed keys / values + a row-softmax kernel).  Inference only.  Goldens from the real reference:
+# oracle/make_alternates_golden.py (which knows them under the name ORACLE_ONLY).
+VARIANT_CONFIGS = ORACLE_ONLY_CONFIGS = {
     "affine_in": (dict(decoder_use_instance_norm_with_affine=True), dict(affine_in=True)),
     "affine_in_key_before": (dict(decoder_use_instance_norm_with_affine=True, decoder_use_Key_instance_norm_after_linear_transformation=False),
                              dict(affine_in=True, key_in_after_linear=False)),

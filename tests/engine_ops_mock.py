@@ -31,6 +31,15 @@ def pack_linear(weight, bias=None):
     return ops.PackedMatrix(weight.detach().bfloat16(), None if bias is None else bias.detach().float(), N, K, N, K)
 
 
+def pack_bf16_matrix(src, N, K, ld, trans=False, dst=None):
+    m = _rows(src, K, N, ld).t() if trans else _rows(src, N, K, ld)
+    return ops.PackedMatrix(m.clone(), None, N, K, ops.n_pad_of(N), ops.round_up(K, 64))
+
+
+def softmax_rows(S, P, rows, n, scale):
+    _rows(P, rows, n, n).copy_(torch.softmax(_rows(S, rows, n, n) * scale, dim=-1))
+
+
 def pack_mlp(w1, b1, w2, b2, wpre=None, bpre=None):
     return _Mlp(w1, b1, w2, b2, wpre, bpre)
 
@@ -152,26 +161,41 @@ def _stats(x, B, T, Cdim, extra=None, n_extra=0):
     return mean, s2 / n - mean * mean
 
 
-def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False):
+def instnorm_stats(x, mean, rstd, B, T, Cdim, twice=False, gamma=None):
     m, var = _stats(x, B, T, Cdim)
     r = 1.0 / torch.sqrt(var + 1e-5)
-    if twice:  # IN(IN(x)): the once-normalised map has mean 0 and variance var/(var+eps)
-        r = r / torch.sqrt(var * r * r + 1e-5)
+    g = 1.0 if gamma is None else gamma.double().unsqueeze(0)
+    if twice:  # IN(IN(x)) with the same (affine) module: the once-normalised map has variance g^2 var/(var+eps)
+        r = r * g * g / torch.sqrt(g * g * var * r * r + 1e-5)
+    else:
+        r = r * g
     mean.copy_(m)
     rstd.copy_(r)
 
 
-def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None):
+def instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=None, gamma=None, beta=None):
     m, var = _stats(x, B, T, Cdim, pad_val, n_pad)
     r = 1.0 / torch.sqrt(var + 1e-5)
+    if gamma is not None:
+        r = r * gamma.double().unsqueeze(0)
     mean.copy_(m)
     rstd.copy_(r)
     if pad_norm is not None:
-        pad_norm.copy_((pad_val.double().unsqueeze(0) - m) * r)
+        pad_norm.copy_((pad_val.double().unsqueeze(0) - m) * r + (0.0 if beta is None else beta.double().unsqueeze(0)))
 
 
-def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None):
+def jointnorm_stats(x, mean, rstd, B, T, Cdim):
+    xd = x.reshape(B, T * Cdim).double()
+    m = xd.mean(1, keepdim=True)
+    var = xd.var(1, unbiased=False, keepdim=True)
+    mean.copy_(m.expand(B, Cdim))
+    rstd.copy_((1.0 / torch.sqrt(var + 1e-5)).expand(B, Cdim))
+
+
+def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None, beta=None):
     y = (x.reshape(B, T, Cdim) - mean.unsqueeze(1)) * rstd.unsqueeze(1)
+    if beta is not None:
+        y = y + beta.reshape(1, 1, Cdim)
     for dst in (y16, y32):
         if dst is not None:
             dst.reshape(B, T, Cdim).copy_(y)
@@ -262,6 +286,6 @@ def loss_finalize(taps, lam, squared_style, out3):
 
 def install(monkeypatch):
     for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
-                 "instnorm_stats_padded", "instnorm_apply", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
+                 "instnorm_stats_padded", "jointnorm_stats", "pack_bf16_matrix", "softmax_rows", "instnorm_apply", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
                  "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "tap_stats", "content_term", "loss_finalize"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -82,8 +82,8 @@ def test_error_behaviour(model):
 
 
 def test_alternate_configurations_gate():
-    """the three re-ordering flags are accepted for inference and refused (loudly) by the training step; the
-    variants without kernels are refused everywhere."""
+    """the three re-ordering flags, affine InstanceNorm and the regular-MHA tail are accepted for inference and
+    refused (loudly) by the training step; dropout (active even in eval in the reference) has no kernels and is refused everywhere."""
     kw = dict(encoder_dim=256, decoder_dim=256, encoder_num_heads=8, decoder_num_heads=8, encoder_window_size=[8, 8],
               decoder_window_size=[8, 8], encoder_shift_size=[4, 4], decoder_shift_size=[4, 4])
     default = mst.StyleTransformer(**kw)
@@ -100,8 +100,12 @@ def test_alternate_configurations_gate():
             st._check_config(training=True)
     assert len(mst.StyleTransformer(**kw, decoder_exclude_MLP_after_Fcs_self_MHA=True).state_dict()) == 48
     for flag in ("decoder_use_instance_norm_with_affine", "decoder_use_regular_MHA_instead_of_Swin_at_the_end"):
+        st = mst.StyleTransformer(**kw, **{flag: True})
+        st._check_config()
         with pytest.raises(NotImplementedError):
-            mst.StyleTransformer(**kw, **{flag: True})._check_config()
+            st._check_config(training=True)
+    with pytest.raises(NotImplementedError):
+        mst.StyleTransformer(**kw, decoder_dropout=0.1)._check_config()
 
 
 def test_seeded_fill_is_name_keyed_and_deterministic():

@@ -14,7 +14,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ALTERNATE_CONFIGS, alternate_inputs, alternate_style_transformer
+from conftest import ALTERNATE_CONFIGS, VARIANT_CONFIGS, alternate_inputs, alternate_style_transformer
+
+ALL_CONFIGS = {**ALTERNATE_CONFIGS, **VARIANT_CONFIGS}
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +28,7 @@ def feats():
     return alternate_inputs()
 
 
-@pytest.mark.parametrize("name", list(ALTERNATE_CONFIGS))
+@pytest.mark.parametrize("name", list(ALL_CONFIGS))
 @pytest.mark.parametrize("ws", [8, 7])
 @pytest.mark.parametrize("k", [1, 2])
 def test_alternate_configuration_vs_oracle_and_golden(feats, golden_dir, name, ws, k):
@@ -35,7 +37,7 @@ def test_alternate_configuration_vs_oracle_and_golden(feats, golden_dir, name, w
     fc, fs = feats
     m = alternate_style_transformer(name, ws)
     sd = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
-    okw = ALTERNATE_CONFIGS[name][1]
+    okw = ALL_CONFIGS[name][1]
     m = m.cuda()
     n0 = ops.launch_count
     with torch.no_grad():
@@ -47,10 +49,23 @@ def test_alternate_configuration_vs_oracle_and_golden(feats, golden_dir, name, w
     assert err <= FEAT_TOL, err
     gold = torch.from_numpy(np.load(os.path.join(golden_dir, "alternates.npz"))[f"{name}_ws{ws}_k{k}"])
     assert ((out[:, ::2, ::2, ::4] - gold).abs().max() / rng).item() <= FEAT_TOL
-    if not okw.get("exclude_mlp"):  # the default ordering is computable from the same state_dict: must be the farther one
+    if not okw.get("exclude_mlp") and name not in VARIANT_CONFIGS:  # the default ordering is computable from the same state_dict: must be the farther one
         with torch.no_grad():
             other = O.style_transformer(sd, fc, fs, k, ws=ws, sh=4, heads=8)
         assert (out - ref).norm().item() < (out - other).norm().item()
+
+
+def test_regular_mha_variant_at_64x64_feature_maps():
+    """The regular-MHA tail on a 64x64 map (T = 4096 keys per image: the score GEMM runs in 1024-key chunks)."""
+    from oracle import master_oracle as O
+    m = alternate_style_transformer("regular_mha", 8)
+    sd = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    fc, fs = torch.randn(1, 64, 64, 256, generator=g), torch.randn(1, 64, 64, 256, generator=g)
+    with torch.no_grad():
+        out = m.cuda()(fc.cuda(), fs.cuda(), 1).cpu()
+        ref = O.style_transformer(sd, fc, fs, 1, ws=8, sh=4, heads=8, regular_mha=True)
+    assert ((out - ref).abs().max() / (ref.max() - ref.min())).item() <= FEAT_TOL
 
 
 def test_alternate_configurations_have_no_training_step(feats):
