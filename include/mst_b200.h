@@ -196,6 +196,23 @@ int mst_attn_block(const MstAttnBlock* a, void* stream);
 int mst_window_maps(int H, int W, int ws, int shift, int32_t* gather, int32_t* labels, int32_t* relidx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Similarity loss of the paper (codes/utils.py:105-133, codes/loss.py:137-146,321-336) without materialising the B x N x N
+ * cosine self-similarity maps (csrc/similarity.cu).  For a tap tensor feat [B, N, C] bf16 token-major:
+ *   mst_sim_prepare : ahat = feat / max(|feat row|, 1e-8) (bf16, [B, N, C]), svec [B, C] = per-image sum of the ahat rows,
+ *                     inv_cs [B, N] = 1 / (column sum of the cosine map + 1e-6)   (the map is symmetric: column sum j = ahat_j . svec)
+ *   mst_sim_tiles   : per 128x128 tile of the strict lower triangle, both maps by tcgen05.mma and
+ *                     sum |D_c[i][j]*inv_c[j] - D_o[i][j]*inv_o[j]| (or squares) -> partials[mst_sim_num_tiles(B, N)]
+ *   mst_sim_finalize: out[0] = sum(partials0)/count0 + sum(partials1)/count1 (two taps; count = B*N*N, the mean runs over the
+ *                     whole map as torch.mean over the tril'ed tensors does)
+ * N % 128 == 0, C % 256 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int mst_sim_num_tiles(int B, int N);
+int mst_sim_prepare(const mst_bf16* feat, int B, int N, int C, mst_bf16* ahat, float* svec, float* inv_cs, void* stream);
+int mst_sim_tiles(const mst_bf16* ahat_c, const float* inv_cs_c, const mst_bf16* ahat_o, const float* inv_cs_o, int B, int N, int C,
+                  int squared, float* partials, int n_partials, void* stream);
+int mst_sim_finalize(const float* partials0, int n0, double count0, const float* partials1, int n1, double count1, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Normalisations.
  * mst_layernorm: nn.LayerNorm(C) eps 1e-5 over the last dim, fp32 in -> bf16 out
  *   (style_transformer.py:340-343,390-392; tv swin blocks).  C in {128,256,512}.

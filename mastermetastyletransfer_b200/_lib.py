@@ -113,6 +113,10 @@ SYMBOLS = {
     "mst_attn_qkv_packed_bytes": (_Z, [_I, _I]),
     "mst_pack_attn_qkv": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_attn_block": (_I, [C.POINTER(MstAttnBlock), _P]),
+    "mst_sim_num_tiles": (_I, [_I, _I]),
+    "mst_sim_prepare": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "mst_sim_tiles": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "mst_sim_finalize": (_I, [_P, _I, C.c_double, _P, _I, C.c_double, _P, _P]),
     "mst_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_merge_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_instnorm_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -500,9 +500,34 @@ def vgg_taps_forward(w: VggWeights, imgs: torch.Tensor, ws_: Workspace, tag: str
     return taps
 
 
+def similarity_loss_forward(taps, B: int, squared: bool, ws_: Workspace) -> torch.Tensor:
+    """The paper's similarity loss between the CONTENT and the OUTPUT image's relu3_1 / relu4_1 taps (codes/loss.py:137-146,
+    321-336 with the arguments the paper means; codes/utils.py:105-133): column-normalised cosine self-similarity maps, strict
+    lower triangle, mean |difference| (or squared) over the whole B x N x N map, summed over the two taps.  taps: the list
+    vgg_taps_forward returns for the stacked (content | style | output) batch.  Returns a device fp32 scalar tensor."""
+    parts = []
+    for i in (1, 2):
+        t, h, wd, c = taps[i]
+        N = h * wd
+        tiles = ops.sim_num_tiles(B, N)
+        rows = t.view(3 * B * N, c)
+        ah_c, ah_o = ws_.bf16(f"sim_ahat_c{i}", B * N, c), ws_.bf16(f"sim_ahat_o{i}", B * N, c)
+        sv = ws_.f32(f"sim_svec{i}", 2, B, c)
+        inv = ws_.f32(f"sim_inv{i}", 2, B, N)
+        part = ws_.f32(f"sim_part{i}", tiles)
+        ops.sim_prepare(rows[:B * N], B, N, c, ah_c, sv[0], inv[0])
+        ops.sim_prepare(rows[2 * B * N:], B, N, c, ah_o, sv[1], inv[1])
+        ops.sim_tiles(ah_c, inv[0], ah_o, inv[1], B, N, c, squared, part)
+        parts.append((part, float(B) * N * N))
+    out = torch.empty(1, dtype=torch.float32, device=taps[1][0].device)
+    ops.sim_finalize(parts[0][0], parts[0][1], parts[1][0], parts[1][1], out)
+    return out[0]
+
+
 def perceptual_loss_forward(w: VggWeights, content: torch.Tensor, style: torch.Tensor, output: torch.Tensor, lam: float,
-                            squared_content: bool, squared_style: bool, ws_: Workspace) -> torch.Tensor:
-    """Returns a device fp32 tensor [3] = (total, content, style) following get_overall_loss (loss.py:201-262)."""
+                            squared_content: bool, squared_style: bool, ws_: Workspace, similarity: bool = False):
+    """Returns a device fp32 tensor [3] = (total, content, style) following get_overall_loss (loss.py:201-262); with
+    similarity=True a pair (that tensor, the content-vs-output similarity loss scalar)."""
     B = int(content.shape[0])
     imgs = ws_.f32("loss_imgs", 3 * B, 3, content.shape[2], content.shape[3])
     imgs[:B].copy_(content)
@@ -520,4 +545,6 @@ def perceptual_loss_forward(w: VggWeights, content: torch.Tensor, style: torch.T
         descs.append(dict(partials=partials, mean_s=mean[B:2 * B], var_s=var[B:2 * B], mean_o=mean[2 * B:], var_o=var[2 * B:], B=B, T=T, C=c))
     out3 = torch.empty(3, dtype=torch.float32, device=content.device)
     ops.loss_finalize(descs, lam, squared_style, out3)
+    if similarity:
+        return out3, similarity_loss_forward(taps, B, squared_style, ws_)
     return out3

@@ -52,6 +52,10 @@ class custom_loss(nn.Module):
             feature_extractor_model_relative_path = os.path.join("weights", "vgg_19_last_layer_is_relu_5_1_output.pt")
         self.lambda_value = default_lambda_value
         self.distance_content, self.distance_style = distance_content, distance_style
+        # False (default): output_similarity_loss=True returns what the reference computes -- its get_similarity_loss hands the
+        # CONTENT features to both arguments of every term (loss.py:333-334), i.e. exactly 0.  True: the paper's form, content vs
+        # OUTPUT features, on the tensor cores (csrc/similarity.cu); forward only.
+        self.similarity_content_vs_output = False
         # parameter-free, kept for attribute compatibility with the reference (loss.py:102-105)
         self.IN_0, self.IN_1 = nn.InstanceNorm2d(128), nn.InstanceNorm2d(256)
         self.IN_2, self.IN_3 = nn.InstanceNorm2d(512), nn.InstanceNorm2d(512)
@@ -83,7 +87,10 @@ class custom_loss(nn.Module):
             raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
         if loss_weight is None:
             loss_weight = self.lambda_value
+        want_sim = bool(output_similarity_loss and self.similarity_content_vs_output)
         if torch.is_grad_enabled() and output_image.requires_grad:
+            if want_sim:
+                raise NotImplementedError("the content-vs-output similarity loss has a forward kernel only (SURVEY.md 8f-3)")
             from .autograd_fns import perceptual_loss_apply
             out3 = perceptual_loss_apply(self, content_image, style_image, output_image, float(loss_weight))
             return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss)
@@ -92,17 +99,21 @@ class custom_loss(nn.Module):
             ws = workspace_of(self, output_image.device)
             out3 = engine.perceptual_loss_forward(w, content_image.float(), style_image.float(), output_image.float(), float(loss_weight),
                                                   self.distance_content == "euclidian_squared",
-                                                  self.distance_style == "euclidian_squared", ws)
-        return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss)
+                                                  self.distance_style == "euclidian_squared", ws, similarity=want_sim)
+        sim = None
+        if want_sim:
+            out3, sim = out3
+        return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss, sim)
 
     @staticmethod
-    def _pack(total, content, style, want_parts: bool, want_similarity: bool):
+    def _pack(total, content, style, want_parts: bool, want_similarity: bool, similarity=None):
         """Return tuple of get_overall_loss (loss.py:245-262).  The reference's get_similarity_loss compares the CONTENT image's
         relu3_1 / relu4_1 self-similarity maps with THEMSELVES (loss.py:333-334 passes VGG_features_content_layers twice), so the
         value it returns is mean(|tril(D) - tril(D)|) + ... = exactly 0 whatever the inputs; the drop-in returns that 0 (an fp32
-        scalar on the device, no graph) without building the two B x N x N cosine maps.  The paper's content-vs-output form is
-        SURVEY.md 8f-3 (not built)."""
+        scalar on the device, no graph) without building the two B x N x N cosine maps.  The paper's content-vs-output form
+         is computed when `similarity_content_vs_output` is set (`similarity` then holds it)."""
         if want_similarity:
-            similarity = torch.zeros((), dtype=torch.float32, device=total.device)
+            if similarity is None:
+                similarity = torch.zeros((), dtype=torch.float32, device=total.device)
             return (total, content, style, similarity) if want_parts else (total, similarity)
         return (total, content, style) if want_parts else total

@@ -59,7 +59,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
-             "mst_loss_finalize": "loss_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
+             "mst_loss_finalize": "loss_finalize_kernel", "mst_sim_prepare": "sim_prepare_kernels", "mst_sim_tiles": "sim_tile_kernel", "mst_sim_finalize": "sim_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
              "mst_window_attention_bwd": "window_attn_bwd_kernel", "mst_layernorm_bwd": "layernorm_bwd_kernel",
              "mst_instnorm_bwd_stats": "instnorm_bwd_stats_kernel", "mst_instnorm_bwd_apply": "instnorm_bwd_apply_kernel",
              "mst_blend_bwd": "blend_bwd_kernel", "mst_add_cast": "add_cast_kernel", "mst_token_map_copy": "token_map_kernel", "mst_reflect_fold": "reflect_fold_kernel",
@@ -436,6 +436,34 @@ def content_term(fc, fo, mean_c, var_c, mean_o, var_o, B, T, Cdim, squared, part
         _ptr(var_c, torch.float32, "var_c"), _ptr(mean_o, torch.float32, "mean_o"), _ptr(var_o, torch.float32, "var_o"),
         B, T, Cdim, int(squared), _ptr(partials, torch.float32, "partials"), partials.numel(), _stream()),
         nbytes=4.0 * B * T * Cdim)
+
+
+def sim_prepare(feat, B, N, Cdim, ahat, svec, inv_cs) -> None:
+    """Row-normalised features (bf16), per-image sum vector and the reciprocal column sums of the cosine self-similarity map."""
+    _launch("mst_sim_prepare", lambda: _lib.lib().mst_sim_prepare(_ptr(feat, torch.bfloat16, "feat"), B, N, Cdim, _ptr(ahat, torch.bfloat16, "ahat"),
+                                                                 _ptr(svec, torch.float32, "svec"), _ptr(inv_cs, torch.float32, "inv_cs"), _stream()),
+            nbytes=6.0 * B * N * Cdim)
+
+
+def sim_num_tiles(B: int, N: int) -> int:
+    n = _lib.lib().mst_sim_num_tiles(B, N)
+    if n <= 0:
+        raise ValueError("similarity loss: the number of tokens per image must be a multiple of 128")
+    return n
+
+
+def sim_tiles(ahat_c, inv_c, ahat_o, inv_o, B, N, Cdim, squared, partials) -> None:
+    """partials[tile] = sum over the tile's strict-lower-triangle entries of |S_c - S_o| (or squares), both maps on the tensor cores."""
+    _launch("mst_sim_tiles", lambda: _lib.lib().mst_sim_tiles(
+        _ptr(ahat_c, torch.bfloat16, "ahat_c"), _ptr(inv_c, torch.float32, "inv_c"), _ptr(ahat_o, torch.bfloat16, "ahat_o"),
+        _ptr(inv_o, torch.float32, "inv_o"), B, N, Cdim, int(squared), _ptr(partials, torch.float32, "partials"), partials.numel(), _stream()),
+        flops=2.0 * 2.0 * B * N * N * Cdim)  # reference-algorithm FLOPs: two full N x N x C cosine maps
+
+
+def sim_finalize(p0, count0, p1, count1, out) -> None:
+    _launch("mst_sim_finalize", lambda: _lib.lib().mst_sim_finalize(_ptr(p0, torch.float32, "p0"), p0.numel(), float(count0),
+                                                                   _ptr(p1, torch.float32, "p1"), 0 if p1 is None else p1.numel(),
+                                                                   float(count1 or 1.0), _ptr(out, torch.float32, "out"), _stream()))
 
 
 def loss_finalize(taps, lam: float, squared_style: bool, out3) -> None:

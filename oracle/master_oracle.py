@@ -497,6 +497,27 @@ def style_loss(taps_s: List[Tensor], taps_o: List[Tensor], squared: bool = False
     return tot
 
 
+def scaled_self_cosine_lower_triangle(a: Tensor, eps: float = 1e-6) -> Tensor:
+    """codes/utils.py:105-133: a [B,C,H,W] -> [B,N,N]: cosine similarity of every pair of spatial positions
+    (torch.cosine_similarity: each vector divided by max(its norm, 1e-8)), every COLUMN divided by its sum + eps, strict lower
+    triangle kept.  (Restated with a matmul: the reference broadcasts a [B,N,N,C] tensor.)"""
+    B, C = a.shape[:2]
+    f = a.reshape(B, C, -1).permute(0, 2, 1)
+    fh = f / f.norm(dim=2, keepdim=True).clamp_min(1e-8)
+    d = fh @ fh.transpose(1, 2)
+    return (d / (d.sum(dim=1) + eps).unsqueeze(1)).tril(diagonal=-1)
+
+
+def similarity_loss(taps_a: List[Tensor], taps_b: List[Tensor], squared: bool = False) -> Tensor:
+    """codes/loss.py:137-146,321-336: relu3_1 and relu4_1 terms, mean of |.| (or squares) over the WHOLE [B,N,N] maps.  The
+    reference calls it with the content taps for BOTH arguments (:333-334) -> 0; the paper's form is (content, output)."""
+    tot = torch.zeros(())
+    for i in (1, 2):
+        d = scaled_self_cosine_lower_triangle(taps_a[i]) - scaled_self_cosine_lower_triangle(taps_b[i])
+        tot = tot + ((d * d).mean() if squared else d.abs().mean())
+    return tot
+
+
 def overall_loss(vgg_sd: SD, content: Tensor, style: Tensor, output: Tensor, lam: float = 10.0,
                  squared_content: bool = False, squared_style: bool = False, batchnorm: Optional[str] = None):
     """codes/loss.py:201-262: total = content + lambda*style; returns (total, content, style).

@@ -345,3 +345,57 @@ def test_benched_shape_batch32_256_vs_oracle(model, sd):
     assert out.shape == (32, 3, 256, 256)
     e = rel_err(out[pick], ref)
     assert e <= IMG_TOL, e
+
+
+@pytest.mark.parametrize("squared", [False, True])
+def test_similarity_loss_content_vs_output(loss_module, squared, golden_dir):
+    """the paper's similarity loss (codes/utils.py:105-133, codes/loss.py:137-146,321-336 with content vs OUTPUT
+    features) on the tensor cores (csrc/similarity.cu: the B x N x N cosine maps are never materialised).  (1) the kernels
+    against the oracle restatement on the product's OWN VGG taps (bf16 operand rounding only); (2) the module end to end against
+    the value the REAL reference's functions give on its fp32 taps (tests/golden/similarity_loss.json) -- the loss is a mean
+    |difference| of two nearly equal maps, so the taps' bf16 rounding shows: 5e-2; (3) the default (reference-as-written) value
+    stays exactly 0."""
+    import json
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    from oracle import master_oracle as O
+    gold = json.load(open(os.path.join(golden_dir, "similarity_loss.json")))["content_vs_output"]
+    c128, _ = synthetic.synthetic_images(1, 128, seed=7)
+    o128, _ = synthetic.synthetic_images(1, 128, seed=8)
+    o128 = 0.6 * c128 + 0.4 * o128
+    dist = "euclidian_squared" if squared else "euclidian"
+    mod = custom_loss(project_absolute_path="/nonexistent", distance_content=dist, distance_style=dist)
+    mod.feature_extractor_model.load_state_dict(loss_module.feature_extractor_model.state_dict())
+    mod = mod.eval().cuda()
+    c, o = c128.cuda(), o128.cuda()
+    with torch.no_grad():
+        assert mod(c, c, o, output_similarity_loss=True)[1].item() == 0.0          # the reference as written (loss.py:333-334)
+        mod.similarity_content_vs_output = True
+        total, sim = mod(c, c, o, output_similarity_loss=True)
+        four = mod(c, c, o, output_content_and_style_loss=True, output_similarity_loss=True)
+        taps_c = [t.cpu() for t in mod.feature_extractor_model(c)]
+        taps_o = [t.cpu() for t in mod.feature_extractor_model(o)]
+        ref_same_taps = O.similarity_loss(taps_c, taps_o, squared).item()
+    assert len(four) == 4 and four[3].item() == sim.item() and sim.dim() == 0
+    got = sim.item()
+    print(f"similarity ({dist}): kernels {got:.6e}, oracle on the same taps {ref_same_taps:.6e}, reference on fp32 taps {gold[dist]:.6e}")
+    assert abs(got - ref_same_taps) <= 2e-2 * abs(ref_same_taps), (got, ref_same_taps)
+    assert abs(got - gold[dist]) <= (1e-1 if squared else 5e-2) * abs(gold[dist]), (got, gold[dist])
+
+
+def test_similarity_loss_at_bench_shape_is_finite_and_symmetric(loss_module):
+    """256x256, batch 2 (relu3_1: 4096 tokens -> 528 tiles per image): identical images give (numerically) 0, swapping the two
+    images gives the same value (|a - b| = |b - a|), values are finite."""
+    from mastermetastyletransfer_b200 import synthetic
+    content, style = synthetic.synthetic_images(2, 256, seed=9)
+    c, s = content.cuda(), style.cuda()
+    loss_module.similarity_content_vs_output = True
+    try:
+        with torch.no_grad():
+            same = loss_module(c, s, c, output_similarity_loss=True)[1].item()
+            ab = loss_module(c, s, s, output_similarity_loss=True)[1].item()
+            ba = loss_module(s, c, c, output_similarity_loss=True)[1].item()
+    finally:
+        loss_module.similarity_content_vs_output = False
+    # (the per-image sum vector is accumulated with fp32 atomics: two passes over the same image agree to ~1e-7 relative, not bit for bit)
+    assert ab > 0 and np.isfinite(ab) and abs(ab - ba) <= 1e-5 * ab, (ab, ba)
+    assert 0.0 <= same <= 1e-4 * ab, (same, ab)
