@@ -1,7 +1,7 @@
 // Fused transformer MLP for sm_100a:  out = res + fc2(GELU(fc1(A) + b1)) + b2   (torchvision MLP, the five
 // 256->1024->256 MLPs of a style-transformer layer and the four Swin-encoder MLPs).  The [tokens x 4C] hidden
 // activation never touches HBM: per 128-token tile it is produced 128 hidden units at a time into TMEM (fc1),
-// pulled through bias + GELU by the epilogue warps into a 128B-swizzled bf16 shared-memory tile, and consumed
+// pulled through bias + GELU by the epilogue warps (packed-fp16 GELU) into a 128B-swizzled fp16 shared-memory tile, and consumed
 // from there as the A operand of the second tcgen05 GEMM, which accumulates the [128 x C] output in TMEM
 // across all hidden chunks.
 //
@@ -18,6 +18,7 @@
 // TMEM: fc1 accumulator double buffered (2 x 128 columns) + fc2 accumulator (C columns) <= 512 columns.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace mst {
 
@@ -46,7 +47,7 @@ struct MlpCfg {
   static constexpr int NSTG = 3;                     // ring depth (C == 256 streams 1 MB of weights per tile: two stages starved the MMA)
   static constexpr int ABUF = C == 256 ? 1 : 2;      // A tiles resident (C == 128: the next tile's A is prefetched during this tile)
   static constexpr int A_BYTES = KB1 * 128 * 128;    // resident A tile
-  static constexpr int HS_BYTES = 2 * 128 * 128;     // one Hs buffer: [128 x 128] bf16 as two k-blocks
+  static constexpr int HS_BYTES = 2 * 128 * 128;     // one Hs buffer: [128 x 128] fp16 as two k-blocks
   static constexpr int SMEM_BYTES = 1024 + ABUF * A_BYTES + 2 * HS_BYTES + NSTG * ML_STAGE_BYTES;
   static constexpr int ACC2_COL = 256;
 };
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
     // whole warp, convergent, warp-uniform values; one lane elected inside umma_bf16_pred / umma_commit_pred so that
     // ptxas keeps the descriptors in uniform registers (see gemm_tc.cu)
     constexpr uint32_t idesc1 = umma_idesc_bf16(128, ML_HC);
-    constexpr uint32_t idesc2 = umma_idesc_bf16(128, C);
+    // fc2: the hidden activation tile (written by the GELU epilogue) and the packed W2 are both fp16 (format 0 in the a / b fields)
+    constexpr uint32_t idesc2 = umma_idesc_bf16(128, C) & ~((7u << 7) | (7u << 10));
     int ws = 0, lt = 0;
     auto wait_stage = [&](int& slot) {
       slot = ws % NSTG;
@@ -269,6 +271,16 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         }
         const uint32_t addr = kbase + ((uint32_t)((c0 + q) ^ (row_in_tile & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      }
+    };
+    // the same for 32 values that are already packed two to a register (fp16 pairs out of gelu_erf_h2)
+    auto store_tile32_packed = [&](uint32_t base, int n0, const uint32_t* pk) {
+      const uint32_t kbase = base + (n0 >> 6) * 16384 + xrow;
+      const int c0 = (n0 & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t addr = kbase + ((uint32_t)((c0 + q) ^ (row_in_tile & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
       }
     };
     int lt = 0;
@@ -444,20 +456,18 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         if (lane == 0) mbar_arrive(smem_u32(&acc1_empty[abuf]));
         // fc1 bias straight from global (warp-uniform address, L1-resident): shared memory is fully committed to tiles
         const float4* bb = reinterpret_cast<const float4*>(p.b1 + j * ML_HC + part * 32);
-        float h[32];
+        uint32_t h[16];  // GELU in packed fp16, two hidden units per instruction (common.cuh: gelu_erf_h2): the phase is issue-bound
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float4 b4 = __ldg(bb + e);
-          h[4 * e] = gelu_erf(__uint_as_float(v[4 * e]) + b4.x);
-          h[4 * e + 1] = gelu_erf(__uint_as_float(v[4 * e + 1]) + b4.y);
-          h[4 * e + 2] = gelu_erf(__uint_as_float(v[4 * e + 2]) + b4.z);
-          h[4 * e + 3] = gelu_erf(__uint_as_float(v[4 * e + 3]) + b4.w);
+          h[2 * e] = gelu_erf_h2(__uint_as_float(v[4 * e]) + b4.x, __uint_as_float(v[4 * e + 1]) + b4.y);
+          h[2 * e + 1] = gelu_erf_h2(__uint_as_float(v[4 * e + 2]) + b4.z, __uint_as_float(v[4 * e + 3]) + b4.w);
         }
         PROF_MARK(tG)
         if (lane == 0) mbar_wait(smem_u32(&hs_empty[buf]), (u & 1) ^ 1);  // MMA2(j-2) has finished reading this buffer
         __syncwarp();
         PROF_MARK(tHw)
-        store_tile32(hs_base + buf * Cfg::HS_BYTES, part * 32, h);
+        store_tile32_packed(hs_base + buf * Cfg::HS_BYTES, part * 32, h);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hs_full[buf]));
@@ -595,7 +605,7 @@ __global__ void pack_mlp_kernel(const float* __restrict__ wpre, const float* __r
     long long stage = pre_stages + mlp_stage_of_w2(j, NCH, S1, S2);
     long long inner = ((n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4)) / 2 + e;
     if (C == 256) stage += kb; else inner += kb * 8192;
-    dst[stage * (ML_STAGE_BYTES / 2) + inner] = __float2bfloat16(w2[q]);
+    reinterpret_cast<__half*>(dst)[stage * (ML_STAGE_BYTES / 2) + inner] = __float2half_rn(w2[q]);  // fc2 runs in fp16 (see idesc2)
   } else if (wpre && i < 2 * n1 + (long long)C * C) {  // Wpre[n][k]: chunk pc = n / 128, same stage format as a W1 chunk
     const long long q = i - 2 * n1;
     const int n = (int)(q / C), k = (int)(q % C);

@@ -20,7 +20,7 @@ from oracle import master_oracle as O
 class _Mlp:
     def __init__(self, w1, b1, w2, b2, wpre=None, bpre=None):
         r = lambda w: None if w is None else w.detach().bfloat16().float()
-        self.w1, self.w2, self.wpre = r(w1), r(w2), r(wpre)
+        self.w1, self.w2, self.wpre = r(w1), w2.detach().half().float(), r(wpre)  # fc2 runs in fp16 (hidden activation and W2)
         self.b1, self.b2 = b1.detach().float(), b2.detach().float()
         self.bpre = None if bpre is None else bpre.detach().float()
         self.C = w1.shape[1]
@@ -138,7 +138,7 @@ def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=
         assert pm.wpre is None and mul is None and ln_g is None
         x1 = res[:M] if res is not None else 0.0
         xin = a
-    h = F.gelu(xin @ pm.w1.t() + pm.b1).bfloat16().float()
+    h = F.gelu(xin @ pm.w1.t() + pm.b1).half().float()
     y = x1 + h @ pm.w2.t() + pm.b2
     if out_f32 is not None:
         out_f32[:M].copy_(y)
