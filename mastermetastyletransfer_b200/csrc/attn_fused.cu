@@ -175,6 +175,16 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
       for (int kb = 0; kb < KB; ++kb) af_bulk_g2s(w_base + kb * AF_WKB_BYTES, wsrc + (size_t)kb * AF_WKB_BYTES, AF_WKB_BYTES, smem_u32(&w_full));
     }
     const int c = pt & 7, r0 = pt >> 3;
+    // this thread's eight slot rows of a gathered window (r0 + 8 i): in-window position, or -1 for slots past a 7x7 window
+    int siy[8], six[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int slot = r0 + 8 * i;
+      siy[i] = slot < N ? slot / WS : -1;
+      six[i] = slot < N ? slot - (slot / WS) * WS : 0;
+    }
+    const unsigned long long magic_nwx_p = (1ull << 32) / (unsigned)g.nwx + 1ull;  // win / nwx without a run-time division
+    const unsigned long long magic_nw_p = (1ull << 32) / (unsigned)g.nW + 1ull;    // wg / nW likewise (wg < 2^16 * nW is far away)
     for (int lt = 0; lt < n_my; ++lt) {
       const int tile = first + lt * stride;
       const int buf = lt % XB, u = lt / XB;
@@ -182,17 +192,19 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
       const uint32_t xb = x_base + buf * Cfg::X_BYTES;
       const uint32_t bar = smem_u32(&x_full[buf]);
       // pass 1: which windows go through TMA (thread 0 announces the bytes before issuing anything)
-      int bw[2], win[2];
+      int bw[2], wyv[2], wxv[2];
       bool tma_w[2], ok_w[2];
       uint32_t tx = 0;
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         const int wg = tile * 2 + w;
         ok_w[w] = wg < total_windows;
-        bw[w] = ok_w[w] ? wg / g.nW : 0;
-        win[w] = ok_w[w] ? wg - bw[w] * g.nW : 0;
-        const int wy = win[w] / g.nwx, wx = win[w] - wy * g.nwx;
-        const bool wrapped = (g.sy > 0 && wy == nWy - 1) || (g.sx > 0 && wx == g.nwx - 1);
+        bw[w] = ok_w[w] ? (g.nW == 1 ? wg : (int)(((unsigned long long)(unsigned)wg * magic_nw_p) >> 32)) : 0;
+        if (ok_w[w] && (bw[w] + 1) * g.nW <= wg) ++bw[w];  // (the magic quotient can be one short for very large wg)
+        const int win = ok_w[w] ? wg - bw[w] * g.nW : 0;
+        wyv[w] = (int)(((unsigned long long)(unsigned)win * magic_nwx_p) >> 32);
+        wxv[w] = win - wyv[w] * g.nwx;
+        const bool wrapped = (g.sy > 0 && wyv[w] == nWy - 1) || (g.sx > 0 && wxv[w] == g.nwx - 1);
         tma_w[w] = ok_w[w] && use_tma && !wrapped;
         if (tma_w[w]) tx += (uint32_t)(KB * N * 128);
       }
@@ -204,19 +216,23 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
         if (!ok_w[w]) continue;  // (odd window count: the tile's second half keeps whatever finite rows it holds)
         if (tma_w[w]) {
           if (pt == 0) {
-            const int wy = win[w] / g.nwx, wx = win[w] - wy * g.nwx;
             for (int kb = 0; kb < KB; ++kb)
-              af_tma_load_4d(xb + kb * AF_XKB_BYTES + w * 8192, &tm, kb * 64, wx * WS + g.sx, wy * WS + g.sy, bw[w], bar);
+              af_tma_load_4d(xb + kb * AF_XKB_BYTES + w * 8192, &tm, kb * 64, wxv[w] * WS + g.sx, wyv[w] * WS + g.sy, bw[w], bar);
           }
         } else {
+          // wrap-around window (or no TMA): gathered row by row, 16 bytes per cp.async; win_source() of common.cuh with the
+          // window side as a compile-time constant
+          const int y0 = wyv[w] * WS + g.sy, x0 = wxv[w] * WS + g.sx;
+          const long long img = (long long)bw[w] * g.H;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int slot = r0 + 8 * i;
             long long src = -1;
-            if (slot < N) {
-              int y, x;
-              win_source(g, win[w], slot, y, x);
-              if (y < g.H && x < g.W) src = ((long long)bw[w] * g.H + y) * g.W + x;
+            if (siy[i] >= 0) {
+              int y = y0 + siy[i], x = x0 + six[i];
+              if (y >= g.Hp) y -= g.Hp;
+              if (x >= g.Wp) x -= g.Wp;
+              if (y < g.H && x < g.W) src = (img + y) * g.W + x;
             }
             const bf16* sp = src >= 0 ? p.x + src * p.ldx + c * 8 : p.x;
 #pragma unroll
@@ -231,62 +247,28 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
   } else if (warp == AF_MMA_WARP) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc_qkv = umma_idesc_bf16(128, 96);
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);  // B (the V tile) is MN-major
     mbar_wait(smem_u32(&w_full), 0);
     tc_fence_after();
-    // The two heads are independent chains  QKV_p(t) -> [drain] -> S_p(t) -> [softmax] -> PV_p(t) -> [output]  that share only the
-    // x tile.  This warp is their event loop: it polls the hand-off barriers of both chains and issues whatever has become
-    // ready, so the chains may drift apart -- and they are STARTED apart (head 1's first QKV is held back until head 0 has
-    // reached its softmax): from then on one head's warps compute while the other head's warps, on the same schedulers, wait
-    // for a tensor-core hand-off or a TMEM load.
-    auto ready = [&](uint64_t* bar, int parity) { return __shfl_sync(0xffffffffu, (int)mbar_test_wait(smem_u32(bar), (uint32_t)parity), 0) != 0; };
-    int t_q[2] = {0, 0}, t_s[2] = {0, 0}, t_pv[2] = {0, 0};  // next tile whose QKV_p / S_p / PV_p is to be issued
-    while (t_pv[0] < n_my || t_pv[1] < n_my) {
-#pragma unroll
+    // This warp issues only the projections: QKV_p(t) as soon as the x tile has landed and head p's accumulator has been
+    // drained (qkv_ready[p] of tile t-1).  S_p and PV_p are issued by the head's OWN epilogue warps (its leader warp, right after
+    // a named barrier of the head's four warps): a hand-off through this warp costs an mbarrier round trip and a poll, twice per
+    // tile and head, on a chain that is latency-bound.
+    for (int t = 0; t < n_my; ++t) {
+      const int buf = t % XB, u = t / XB;
+      mbar_wait(smem_u32(&x_full[buf]), u & 1);
+#pragma unroll 1
       for (int pp = 0; pp < 2; ++pp) {
-        // ---- QKV_p(t): x tile landed, and this head's accumulator drained (its S of the previous tile has been issued)
-        if (t_q[pp] < n_my && t_s[pp] >= t_q[pp]) {
-          const int t = t_q[pp];
-          const bool held = pp == 1 && t == 0 && stagger > 0 && n_my >= 3 && (stagger == 1 ? t_s[0] < 1 : t_pv[0] < 1);
-          const int buf = t % XB, u = t / XB;
-          if (!held && ready(&x_full[buf], u & 1)) {
-            tc_fence_after();
-            const uint32_t xb = x_base + buf * Cfg::X_BYTES;
+        if (t > 0) mbar_wait(smem_u32(&qkv_ready[pp]), (t - 1) & 1);
+        tc_fence_after();
+        const uint32_t xb = x_base + buf * Cfg::X_BYTES;
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
+        for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)  // head pp: weight rows 96 pp .. 96 pp + 95 of every k-block
-                umma_bf16_pred(tmem_base + pp * AF_COL_ACC, umma_desc_sw128(xb + kb * AF_XKB_BYTES + k * 32),
-                               umma_desc_sw128(w_base + kb * AF_WKB_BYTES + pp * 12288 + k * 32), idesc_qkv, (kb | k) != 0);
-            if (t_q[pp ^ 1] > t) umma_commit_pred(smem_u32(&x_empty[buf]));  // both heads have read this x tile
-            umma_commit_pred(smem_u32(&acc_full[pp]));
-            t_q[pp] = t + 1;
-          }
-        }
-        // ---- S_p(t): q | k tile and V columns written, QKV accumulator drained
-        if (t_s[pp] < t_q[pp] && ready(&qkv_ready[pp], t_s[pp] & 1)) {
-          tc_fence_after();
-          const uint32_t qk = qk_base + pp * 16384;
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16_pred(tmem_base + AF_COL_S + pp * 128, umma_desc_sw128(qk + k * 32), umma_desc_sw128(qk + 64 + k * 32), idesc_s, k != 0);
-          umma_commit_pred(smem_u32(&s_full[pp]));
-          t_s[pp] += 1;
-        }
-        // ---- PV_p(t): P tile written (over q | k), S_p read
-        if (t_pv[pp] < t_s[pp] && ready(&p_ready[pp], t_pv[pp] & 1)) {
-          tc_fence_after();
-          const uint32_t pb = qk_base + pp * 16384;
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)  // 16 keys per step: 32 B along K in the P tile, two 8-key groups (2 KB) in the V tile
-              umma_bf16_pred(tmem_base + AF_COL_S + pp * 128 + w * 32, umma_desc_sw128(pb + k * 32),
-                             af_desc_mn_sw128(v_base + w * 8192 + pp * 64 + k * 2048), idesc_pv, k != 0);
-          umma_commit_pred(smem_u32(&o_full[pp]));
-          t_pv[pp] += 1;
-        }
+          for (int k = 0; k < 4; ++k)  // head pp: weight rows 96 pp .. 96 pp + 95 of every k-block
+            umma_bf16_pred(tmem_base + pp * AF_COL_ACC, umma_desc_sw128(xb + kb * AF_XKB_BYTES + k * 32),
+                           umma_desc_sw128(w_base + kb * AF_WKB_BYTES + pp * 12288 + k * 32), idesc_qkv, (kb | k) != 0);
+        if (pp == 1) umma_commit_pred(smem_u32(&x_empty[buf]));  // both heads have read this x tile
+        umma_commit_pred(smem_u32(&acc_full[pp]));
       }
     }
     tc_fence_before();
@@ -308,6 +290,9 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
     const uint32_t qk_tile = qk_base + part * 16384;   // this head's q | k tile, later its P tile
     const uint32_t acc_addr = lane_addr + part * AF_COL_ACC;
     const uint32_t s_addr = lane_addr + AF_COL_S + part * 128;
+    const uint32_t s_addr_mma = tmem_base + AF_COL_S + part * 128;  // the accumulator address the head's leader warp issues to (lane 0)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 32) | (1u << 16);  // B (the V tile) is MN-major
     // window index of this warp's half-tile, advanced incrementally (no per-tile divisions by run-time values)
     const int step_w = 2 * stride;
     const int db = step_w / g.nW, dwin = step_w - db * g.nW;
@@ -421,7 +406,16 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&qkv_ready[part]));
+      if (lane == 0) mbar_arrive(smem_u32(&qkv_ready[part]));  // (tells the projection issuer that this head's accumulator is free)
+      // the head's four warps meet; its leader issues S_p = Q_p K_p^T (two windows stacked) itself
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+      if (quad == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          umma_bf16_pred(s_addr_mma, umma_desc_sw128(qk_tile + k * 32), umma_desc_sw128(qk_tile + 64 + k * 32), idesc_s, k != 0);
+        umma_commit_pred(smem_u32(&s_full[part]));
+      }
       AF_MARK(tD)
 
       // ---- (2) softmax of this thread's query row ----
@@ -480,8 +474,17 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
       }
       fence_proxy_async_smem();
       tc_fence_before();  // S_p has been read: PV_p may overwrite its columns
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&p_ready[part]));
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
+      if (quad == 0) {  // O_p[:, 32w..] = P_p . V_{p,w}: 16 keys per step = 32 B along K in the P tile, two 8-key groups (2 KB) in the V tile
+        tc_fence_after();
+#pragma unroll
+        for (int ww = 0; ww < 2; ++ww)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_pred(s_addr_mma + ww * 32, umma_desc_sw128(qk_tile + k * 32), af_desc_mn_sw128(v_base + ww * 8192 + part * 64 + k * 2048),
+                           idesc_pv, k != 0);
+        umma_commit_pred(smem_u32(&o_full[part]));
+      }
       AF_MARK(tS)
 
       // ---- (3) O = P V -> * 1/rowsum -> bf16 -> global (window reverse + roll back = the row's source token) ----
