@@ -297,6 +297,13 @@ int mst_cast_bf16(const float* x, mst_bf16* y, size_t n, void* stream);
  * ------------------------------------------------------------------------------------------ */
 int mst_conv3x3_first(const float* img, const float* w, const float* b, mst_bf16* out, int B, int H, int W, int relu,
                       void* stream);
+/* BatchNorm2d (+ ReLU) of the VGG-19-BN loss variant (codes/loss.py:41-63) on a token-major [M, C] activation:
+ * y = max(0, (x - mean[c]) * gamma[c] * inv_std[c] + beta[c]) -> bf16.  x = x32 (the convolution's fp32 output; the normalisation
+ * must see it before any rounding to bf16) or, with x32 == NULL, y itself in place.  var_is_rstd = 1: `var` already holds
+ * 1/sqrt(var + eps) (mst_instnorm_stats with B = 1, T = M: the batch statistics of train mode, which is what the reference's
+ * scripts run); 0: `var` is a variance (running_var in eval mode, or mst_tap_stats output).  C % 8 == 0, C / 8 divides 256. */
+int mst_bn_relu(const float* x32, mst_bf16* y, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                size_t M, int C, int relu, int var_is_rstd, void* stream);
 int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream);
 size_t mst_tap_stats_scratch_floats(int B, int T, int C);
 int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, float* scratch, size_t scratch_floats,

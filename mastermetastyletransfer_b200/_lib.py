@@ -140,6 +140,7 @@ SYMBOLS = {
     "mst_reptile_apply": (_I, [C.POINTER(MstTensorTable), _P, C.c_float, _P]),
     "mst_conv3x3_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mst_maxpool2x2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mst_bn_relu": (_I, [_P, _P, _P, _P, _P, _P, C.c_float, _Z, _I, _I, _I, _P]),
     "mst_tap_stats_scratch_floats": (_Z, [_I, _I, _I]),
     "mst_tap_stats": (_I, [_P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "mst_content_term": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),

@@ -262,6 +262,50 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const MstLossTaps ta
   }
 }
 
+// ---------------------------------------------------------------- BatchNorm2d + ReLU of the VGG-19-BN loss variant
+// y = max(0, (x - mean[c]) * gamma[c] * inv_std[c] + beta[c])  (codes/loss.py:41-63) for a token-major [M, C] activation; y is bf16.
+// x is the convolution's fp32 output (x32 != NULL) -- a channel whose mean is large against its standard deviation would lose its
+// signal if it were rounded to bf16 BEFORE the normalisation -- or, for the first layer, the bf16 tensor y itself (in place).
+// Train mode (what the reference's scripts run): mean / inv_std are the statistics of the batch (mst_instnorm_stats with B = 1,
+// or mst_tap_stats for bf16 input: then var_is_rstd = 0 and the kernel takes 1/sqrt(var + eps)); eval mode: the running statistics.
+// Thread = eight channels of a row; the per-channel scale / shift live in registers.
+__global__ void __launch_bounds__(256) bn_relu_kernel(const float* __restrict__ x32, bf16* __restrict__ y, const float* __restrict__ mean,
+                                                      const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float eps, long long M, int C, int relu, int var_is_rstd) {
+  const int C8 = C >> 3;
+  const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8, RL = 256 / C8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c8 * 8 + e;
+    sc[e] = gamma[c] * (var_is_rstd ? var[c] : 1.0f / sqrtf(var[c] + eps));
+    sh[e] = beta[c] - mean[c] * sc[e];
+  }
+  for (long long r = (long long)blockIdx.x * RL + rl; r < M; r += (long long)gridDim.x * RL) {
+    float f[8];
+    uint4* py = reinterpret_cast<uint4*>(y + r * C + c8 * 8);
+    if (x32) {
+      const float4 a = *reinterpret_cast<const float4*>(x32 + r * C + c8 * 8), b = *reinterpret_cast<const float4*>(x32 + r * C + c8 * 8 + 4);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+      const uint4 v = *py;
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(w[e] << 16); f[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u); }
+    }
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = fmaf(f[2 * e], sc[2 * e], sh[2 * e]), d = fmaf(f[2 * e + 1], sc[2 * e + 1], sh[2 * e + 1]);
+      if (relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, d);
+      ow[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *py = o;
+  }
+}
+
 }  // namespace mst
 
 using namespace mst;
@@ -280,6 +324,18 @@ extern "C" int mst_maxpool2x2(const mst_bf16* x, mst_bf16* y, int B, int H, int 
   const long long n8 = (long long)B * (H / 2) * (W / 2) * (C / 8);
   maxpool2x2_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y),
                                                                                  n8, H / 2, W / 2, C / 8);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mst_bn_relu(const float* x32, mst_bf16* y, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                           size_t M, int C, int relu, int var_is_rstd, void* stream) {
+  if (!y || !mean || !var || !gamma || !beta || M == 0 || C <= 0 || C % 8 != 0 || 256 % (C / 8) != 0) return MST_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x32)) & 15) return MST_ERR_BAD_ARG;
+  const int RL = 256 / (C / 8);
+  long long blocks = ((long long)M + RL - 1) / RL;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x32, reinterpret_cast<bf16*>(y), mean, var, gamma, beta, eps, (long long)M, C, relu,
+                                                                     var_is_rstd);
   return (int)cudaGetLastError();
 }
 

@@ -500,6 +500,102 @@ def vgg_taps_forward(w: VggWeights, imgs: torch.Tensor, ws_: Workspace, tag: str
     return taps
 
 
+# ---- VGG-19-BN variant (use_vgg19_with_batchnorm, codes/loss.py:41-63; torchvision vgg19_bn.features[:43]) ----
+VGG_BN_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512]  # up to relu5_1 (index 42)
+VGG_BN_TAP_AFTER = {9: 0, 16: 1, 29: 2, 42: 3}  # the ReLU that closes features[:10], [10:17], [17:30], [30:43]
+
+
+class VggBnWeights:
+    """features.{i}.weight/bias of the convolutions, features.{i+1}.{weight,bias,running_mean,running_var} of their BatchNorm2d."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = "features."):
+        self.layers = []  # ("pool",) | ("conv", packed / first-conv weights, cin, bn tensors, index of the ReLU)
+        i = 0
+        for v in VGG_BN_CFG:
+            if v == "M":
+                self.layers.append(("pool",))
+                i += 1
+                continue
+            wt, bias = _f32(sd[f"{prefix}{i}.weight"]), _f32(sd[f"{prefix}{i}.bias"])
+            bn = tuple(_f32(sd[f"{prefix}{i + 1}.{k}"]) for k in ("weight", "bias", "running_mean", "running_var"))
+            conv = (wt, bias) if i == 0 else ops.pack_conv3x3(wt, bias)
+            self.layers.append(("conv", conv, int(wt.shape[1]), bn, i + 2))
+            i += 3
+
+
+def vgg_bn_taps_forward(w: VggBnWeights, imgs: torch.Tensor, ws_: Workspace, tag: str, training: bool, tap_out=None, tap_row0: int = 0,
+                        eps: float = 1e-5):
+    """imgs fp32 [N,3,H,W] -> the four bf16 NHWC taps.  Every convolution is followed by BatchNorm2d -- in train mode with the
+    statistics of THIS batch over (N,H,W) (biased variance; mst_tap_stats with B = 1), in eval mode with the running ones -- and
+    ReLU, applied in place by one elementwise kernel.  tap_out: optional list of four [rows, C] buffers; the taps are written
+    there starting at row tap_row0 * (tap tokens per image) (the loss stacks content | style | output taps)."""
+    N, _, H, W = imgs.shape
+    h, wd, c = H, W, 3
+    cur = None
+    taps = [None] * 4
+    mean, var = ws_.f32(tag + "bn_mean", 512), ws_.f32(tag + "bn_var", 512)
+    flip = 0
+    for layer in w.layers:
+        if layer[0] == "pool":
+            pooled = ws_.bf16(tag + f"p{flip}", N * (h // 2) * (wd // 2), c)
+            ops.maxpool2x2(cur, pooled, N, h, wd, c)
+            cur, h, wd = pooled, h // 2, wd // 2
+            continue
+        _, conv, cin, (g, b, rm, rv), relu_idx = layer
+        M = N * h * wd
+        slot = VGG_BN_TAP_AFTER.get(relu_idx)
+        pre = None
+        if isinstance(conv, tuple):  # first convolution: fp32 NCHW image in, 64 channels out (bf16; normalised in place)
+            cout = 64
+            out = ws_.bf16(tag + "a0", M, cout)
+            ops.conv3x3_first(imgs, conv[0], conv[1], out, N, h, wd, relu=False)
+        else:
+            cout = conv.n_pad
+            if slot is not None and tap_out is not None:
+                out = tap_out[slot][tap_row0 * h * wd: tap_row0 * h * wd + M]
+            else:
+                out = ws_.bf16(tag + (f"tap{slot}" if slot is not None else f"a{1 + flip}"), M, cout)
+            # the convolution's output stays fp32 until it is normalised: a channel with |mean| >> std must not meet bf16 first
+            pre = ws_.f32(tag + "pre", M, cout)
+            ops.gemm(cur, conv, M, act=ACT_NONE, out_f32=pre, conv=dict(H=h, W=wd, Cin=cin, pad_mode=0, upsample=False))
+        if not training:
+            ops.bn_relu(out, rm, rv, g, b, eps, M, cout, x32=pre)
+        elif pre is None:
+            ops.tap_stats(out, mean[:cout].view(1, cout), var[:cout].view(1, cout), 1, M, cout)
+            ops.bn_relu(out, mean[:cout], var[:cout], g, b, eps, M, cout)
+        else:  # batch statistics over (N, H, W): the InstanceNorm statistics kernel on the batch read as ONE image (eps = 1e-5 = BN's)
+            ops.instnorm_stats(pre, mean[:cout].view(1, cout), var[:cout].view(1, cout), 1, M, cout)
+            ops.bn_relu(out, mean[:cout], var[:cout], g, b, eps, M, cout, x32=pre, var_is_rstd=True)
+        cur, c = out, cout
+        flip ^= 1
+        if slot is not None:
+            taps[slot] = (out, h, wd, cout)
+    return taps
+
+
+def perceptual_loss_forward_bn(w: VggBnWeights, content, style, output, lam: float, squared_content: bool, squared_style: bool,
+                               ws_: Workspace, training: bool) -> torch.Tensor:
+    """get_overall_loss (loss.py:201-262) with the VGG-19-BN extractor: the content, style and output batches go through the
+    network in three separate passes (loss.py:223-225), each normalised with its own batch statistics in train mode."""
+    B, _, H, W = content.shape
+    shapes = [(H // 2, W // 2, 128), (H // 4, W // 4, 256), (H // 8, W // 8, 512), (H // 16, W // 16, 512)]
+    stacked = [ws_.bf16(f"vggbn_tap{i}", 3 * B * h * wd, c) for i, (h, wd, c) in enumerate(shapes)]
+    for k, img in enumerate((content, style, output)):
+        vgg_bn_taps_forward(w, img.float().contiguous(), ws_, "vggbn_", training, tap_out=stacked, tap_row0=k * B)
+    descs = []
+    for i, (h, wd, c) in enumerate(shapes):
+        T = h * wd
+        mean, var = ws_.f32(f"loss_mean{i}", 3 * B, c), ws_.f32(f"loss_var{i}", 3 * B, c)
+        ops.tap_stats(stacked[i], mean, var, 3 * B, T, c)
+        partials = ws_.f32(f"loss_part{i}", 592)
+        tv = stacked[i].view(3 * B, T * c)
+        ops.content_term(tv[:B], tv[2 * B:], mean[:B], var[:B], mean[2 * B:], var[2 * B:], B, T, c, squared_content, partials)
+        descs.append(dict(partials=partials, mean_s=mean[B:2 * B], var_s=var[B:2 * B], mean_o=mean[2 * B:], var_o=var[2 * B:], B=B, T=T, C=c))
+    out3 = torch.empty(3, dtype=torch.float32, device=content.device)
+    ops.loss_finalize(descs, lam, squared_style, out3)
+    return out3
+
+
 def similarity_loss_forward(taps, B: int, squared: bool, ws_: Workspace) -> torch.Tensor:
     """The paper's similarity loss between the CONTENT and the OUTPUT image's relu3_1 / relu4_1 taps (codes/loss.py:137-146,
     321-336 with the arguments the paper means; codes/utils.py:105-133): column-normalised cosine self-similarity maps, strict

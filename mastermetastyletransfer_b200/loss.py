@@ -38,6 +38,28 @@ class VGG19_custom(nn.Module):
             return [t.view(N, h, wd, c).permute(0, 3, 1, 2).float() for (t, h, wd, c) in taps]
 
 
+class VGG19_custom_with_batch_norm(nn.Module):
+    """Mirror of loss.py:41-63: holds vgg19_bn.features[:43]; forward returns [relu2_1, relu3_1, relu4_1, relu5_1] NCHW fp32.
+    Like the reference, BatchNorm follows the module's mode: batch statistics in train mode (the reference's scripts never put
+    the loss in eval mode), running statistics after .eval().  (The train-mode forward does not move the running statistics:
+    they play no role in anything the reference computes from this module.)"""
+
+    def __init__(self, features: nn.Module):
+        super().__init__()
+        self.features = features
+
+    def forward(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("mastermetastyletransfer_b200 runs on sm_100a only: inputs must be CUDA tensors (no CPU fallback)")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the VGG-19-BN loss variant has forward kernels only (SURVEY.md 8f-4)")
+        with torch.no_grad():
+            w = packed_weights(self, engine.VggBnWeights)
+            taps = engine.vgg_bn_taps_forward(w, x.float().contiguous(), workspace_of(self, x.device), "vggbnmod_", self.training)
+            N = x.shape[0]
+            return [t.view(N, h, wd, c).permute(0, 3, 1, 2).float() for (t, h, wd, c) in taps]
+
+
 class custom_loss(nn.Module):
     """Mirror of loss.py:71-336.  total = content + lambda * style (:243)."""
 
@@ -46,10 +68,10 @@ class custom_loss(nn.Module):
         super().__init__()
         assert distance_content in ["euclidian", "euclidian_squared"], "distance should be either 'euclidian' or 'euclidian_squared'"
         assert distance_style in ["euclidian", "euclidian_squared"], "distance should be either 'euclidian' or 'euclidian_squared'"
-        if use_vgg19_with_batchnorm:
-            raise NotImplementedError("the VGG-19-BN variant has no sm_100a kernels (SURVEY.md 8f-4)")
+        self.use_vgg19_with_batchnorm = bool(use_vgg19_with_batchnorm)
         if feature_extractor_model_relative_path is None:
-            feature_extractor_model_relative_path = os.path.join("weights", "vgg_19_last_layer_is_relu_5_1_output.pt")
+            feature_extractor_model_relative_path = os.path.join("weights", "vgg_19_last_layer_is_relu_5_1_output_bn.pt" if use_vgg19_with_batchnorm
+                                                                 else "vgg_19_last_layer_is_relu_5_1_output.pt")
         self.lambda_value = default_lambda_value
         self.distance_content, self.distance_style = distance_content, distance_style
         # False (default): output_similarity_loss=True returns what the reference computes -- its get_similarity_loss hands the
@@ -62,10 +84,13 @@ class custom_loss(nn.Module):
         path = os.path.join(project_absolute_path, feature_extractor_model_relative_path)
         if os.path.exists(path):
             features = torch.load(path, weights_only=False)
-        else:  # offline: same architecture, random init (the reference would download IMAGENET1K_V1 here)
+        elif use_vgg19_with_batchnorm:  # offline: same architecture, random init (the reference would download IMAGENET1K_V1 here)
+            from torchvision.models import vgg19_bn
+            features = nn.Sequential(*list(vgg19_bn(weights=None).features)[0:43])
+        else:
             from .synthetic import build_vgg19_to_relu5_1
             features = build_vgg19_to_relu5_1()
-        self.feature_extractor_model = VGG19_custom(features)
+        self.feature_extractor_model = (VGG19_custom_with_batch_norm if use_vgg19_with_batchnorm else VGG19_custom)(features)
         for p in self.feature_extractor_model.parameters():
             p.requires_grad = False
 
@@ -88,6 +113,15 @@ class custom_loss(nn.Module):
         if loss_weight is None:
             loss_weight = self.lambda_value
         want_sim = bool(output_similarity_loss and self.similarity_content_vs_output)
+        if self.use_vgg19_with_batchnorm:
+            if (torch.is_grad_enabled() and output_image.requires_grad) or want_sim:
+                raise NotImplementedError("the VGG-19-BN loss variant has forward kernels for the content / style loss only (SURVEY.md 8f-4)")
+            with torch.no_grad():
+                w = packed_weights(self.feature_extractor_model, engine.VggBnWeights)
+                out3 = engine.perceptual_loss_forward_bn(w, content_image, style_image, output_image, float(loss_weight),
+                                                         self.distance_content == "euclidian_squared", self.distance_style == "euclidian_squared",
+                                                         workspace_of(self, output_image.device), self.feature_extractor_model.training)
+            return self._pack(out3[0], out3[1], out3[2], output_content_and_style_loss, output_similarity_loss)
         if torch.is_grad_enabled() and output_image.requires_grad:
             if want_sim:
                 raise NotImplementedError("the content-vs-output similarity loss has a forward kernel only (SURVEY.md 8f-3)")

@@ -58,7 +58,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
-             "mst_maxpool2x2": "maxpool2x2_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
+             "mst_maxpool2x2": "maxpool2x2_kernel", "mst_bn_relu": "bn_relu_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
              "mst_loss_finalize": "loss_finalize_kernel", "mst_sim_prepare": "sim_prepare_kernels", "mst_sim_tiles": "sim_tile_kernel", "mst_sim_finalize": "sim_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
              "mst_window_attention_bwd": "window_attn_bwd_kernel", "mst_layernorm_bwd": "layernorm_bwd_kernel",
              "mst_instnorm_bwd_stats": "instnorm_bwd_stats_kernel", "mst_instnorm_bwd_apply": "instnorm_bwd_apply_kernel",
@@ -414,6 +414,15 @@ def maxpool2x2(x, y, B, H, W, Cdim) -> None:
 
 
 _tap_scratch = {}
+
+
+def bn_relu(y, mean, var, gamma, beta, eps: float, M: int, Cdim: int, relu: bool = True, x32=None, var_is_rstd: bool = False) -> None:
+    """BatchNorm2d (+ ReLU) -> bf16 y [M, C]; input = x32 (fp32 conv output) or y itself in place; mean / var [C] are the batch
+    (train) or running (eval) statistics (var_is_rstd: `var` holds 1/sqrt(var + eps) already)."""
+    _launch("mst_bn_relu", lambda: _lib.lib().mst_bn_relu(_ptr(x32, torch.float32, "x32"), _ptr(y, torch.bfloat16, "y"), _ptr(mean, torch.float32, "mean"),
+                                                         _ptr(var, torch.float32, "var"), _ptr(gamma, torch.float32, "gamma"),
+                                                         _ptr(beta, torch.float32, "beta"), float(eps), M, Cdim, int(relu), int(var_is_rstd), _stream()),
+            nbytes=(6.0 if x32 is not None else 4.0) * M * Cdim)
 
 
 def tap_stats(x, mean, var, B, T, Cdim, scratch=None) -> None:

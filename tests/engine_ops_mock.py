@@ -76,9 +76,12 @@ def _conv3x3(A, pm, M, conv, act, out_f32, out_bf16):
     if conv.get("out_nchw"):
         out_f32.copy_(y[:, : conv.get("n_real", pm.N)])
     else:
-        out = out_bf16.reshape(-1)[: M * pm.n_pad].view(M, pm.n_pad)
-        out.zero_()
-        out[:, : pm.N].copy_(y.permute(0, 2, 3, 1).reshape(M, pm.N))
+        for dst in (out_bf16, out_f32):
+            if dst is None:
+                continue
+            out = dst.reshape(-1)[: M * pm.n_pad].view(M, pm.n_pad)
+            out.zero_()
+            out[:, : pm.N].copy_(y.permute(0, 2, 3, 1).reshape(M, pm.N))
 
 
 def upsample2x_nhwc(x, y, B, H, W, C_):
@@ -260,6 +263,14 @@ def maxpool2x2(x, y, B, H, W, Cdim):
     y.reshape(-1)[: B * (H // 2) * (W // 2) * Cdim].view(B, H // 2, W // 2, Cdim).copy_(F.max_pool2d(src, 2).permute(0, 2, 3, 1))
 
 
+def bn_relu(y, mean, var, gamma, beta, eps, M, Cdim, relu=True, x32=None, var_is_rstd=False):
+    v = y.reshape(-1)[: M * Cdim].view(M, Cdim)
+    src = v.float() if x32 is None else x32.reshape(-1)[: M * Cdim].view(M, Cdim)
+    inv = var if var_is_rstd else 1.0 / torch.sqrt(var + eps)
+    out = (src - mean) * (gamma * inv) + beta
+    v.copy_(torch.relu(out) if relu else out)
+
+
 def tap_stats(x, mean, var, B, T, Cdim, scratch=None):
     m, v = _stats(x.reshape(-1)[: B * T * Cdim].float(), B, T, Cdim)
     mean.copy_(m)
@@ -287,5 +298,5 @@ def loss_finalize(taps, lam, squared_style, out3):
 def install(monkeypatch):
     for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
                  "instnorm_stats_padded", "jointnorm_stats", "pack_bf16_matrix", "softmax_rows", "instnorm_apply", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
-                 "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "tap_stats", "content_term", "loss_finalize"):
+                 "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "bn_relu", "tap_stats", "content_term", "loss_finalize"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -157,3 +157,21 @@ def test_perceptual_loss_sequencing(monkeypatch, squared):
         out3 = engine.perceptual_loss_forward(w, content, style, output, 10.0, squared, squared, engine.Workspace(torch.device("cpu")))
         ref = torch.stack(O.overall_loss(sd, content, style, output, 10.0, squared, squared))
     assert torch.allclose(out3, ref, rtol=1e-2), (out3, ref)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_perceptual_loss_vgg_bn_sequencing(monkeypatch, mode):
+    """engine.perceptual_loss_forward_bn (VGG-19-BN extractor, three separate passes, batch statistics in train mode /
+    running statistics in eval mode, BatchNorm + ReLU in place) with the kernels replaced by their stand-ins, against the oracle."""
+    from conftest import seeded_vgg19_bn
+    from mastermetastyletransfer_b200 import synthetic
+    engine_ops_mock.install(monkeypatch)
+    sd = {k: v.detach().clone() for k, v in seeded_vgg19_bn().state_dict().items()}
+    content, style = synthetic.synthetic_images(2, 64, seed=3)
+    output, _ = synthetic.synthetic_images(2, 64, seed=4)
+    with torch.no_grad():
+        w = engine.VggBnWeights(sd, prefix="")
+        out3 = engine.perceptual_loss_forward_bn(w, content, style, output, 10.0, False, False, engine.Workspace(torch.device("cpu")),
+                                                 training=mode == "train")
+        ref = torch.stack(O.overall_loss(sd, content, style, output, 10.0, batchnorm=mode))
+    assert torch.allclose(out3, ref, rtol=2e-2), (out3, ref)

@@ -399,3 +399,43 @@ def test_similarity_loss_at_bench_shape_is_finite_and_symmetric(loss_module):
     # (the per-image sum vector is accumulated with fp32 atomics: two passes over the same image agree to ~1e-7 relative, not bit for bit)
     assert ab > 0 and np.isfinite(ab) and abs(ab - ba) <= 1e-5 * ab, (ab, ba)
     assert 0.0 <= same <= 1e-4 * ab, (same, ab)
+
+
+@pytest.mark.parametrize("mode,size", [("train", 64), ("eval", 64), ("train", 128)])
+def test_vgg_bn_loss_variant_vs_oracle_and_reference_fixture(mode, size, golden_dir):
+    """custom_loss(use_vgg19_with_batchnorm=True) (codes/loss.py:41-63).  Train mode (what the reference's scripts
+    run): every BatchNorm2d uses the statistics of the batch it is given, content / style / output in three separate passes;
+    eval mode: the running statistics.  Against the oracle and, at 64x64, the values minted from the REAL reference
+    (oracle/make_vgg_bn_fixture.py): loss scalars within 1e-2 (measured: 1e-4 .. 6e-3), taps within 3 % relative L2 and 3 % of the range
+    max-abs in eval mode; in train mode every layer re-standardises its input with batch statistics, a seeded random 16-layer
+    network amplifies the bf16 operand rounding from layer to layer (measured 1 / 1.5 / 3.5 / 6 % relative L2 at the four taps):
+    10 % there -- the loss scalars, which are what the path returns, still agree to 1e-3."""
+    import json
+    from conftest import seeded_vgg19_bn
+    from mastermetastyletransfer_b200 import custom_loss, synthetic
+    from oracle import master_oracle as O
+    gold = json.load(open(os.path.join(golden_dir, "vgg_bn_loss.json")))
+    seq = seeded_vgg19_bn()
+    sdv = {k: v.detach().clone() for k, v in seq.state_dict().items()}
+    m = custom_loss("/nonexistent", use_vgg19_with_batchnorm=True)
+    m.feature_extractor_model.features.load_state_dict(seq.state_dict())
+    m = m.cuda().train(mode == "train")
+    content, style = synthetic.synthetic_images(2, size, seed=3)
+    output, _ = synthetic.synthetic_images(2, size, seed=4)
+    with torch.no_grad():
+        got = [t.item() for t in m(content.cuda(), style.cuda(), output.cuda(), output_content_and_style_loss=True)]
+        ref = [t.item() for t in O.overall_loss(sdv, content, style, output, 10.0, batchnorm=mode)]
+        taps = m.feature_extractor_model(content.cuda())
+        taps_ref = O.vgg_bn_taps(sdv, content, training=mode == "train")
+    errs = [rel_err(t, r) for t, r in zip(taps, taps_ref)]
+    l2 = [((t.float().cpu() - r).norm() / r.norm()).item() for t, r in zip(taps, taps_ref)]
+    print("vgg-bn tap errors: max-abs / range", [round(e, 4) for e in errs], "relative L2", [round(e, 4) for e in l2])
+    for t, r, e, e2 in zip(taps, taps_ref, errs, l2):
+        assert t.shape == r.shape and e2 <= (3e-2 if mode == "eval" else 1e-1), e2
+        if mode == "eval":  # (train mode: a nearly dead channel of the seeded random network is re-scaled to unit variance by its
+            assert e <= FEAT_TOL, e  # batch statistics, rounding noise included -- outliers that the loss does not see)
+    tight = True
+    print(f"vgg-bn loss ({mode}, {size}): kernels {got}, oracle {ref}" + (f", reference {gold[mode]}" if size == 64 else ""))
+    np.testing.assert_allclose(got, ref, rtol=1e-2 if tight else 2e-2)
+    if size == 64:
+        np.testing.assert_allclose(got, gold[mode], rtol=1e-2 if tight else 2e-2)

@@ -163,7 +163,7 @@ def test_alternate_configurations_against_reference_goldens(golden_dir, name, ws
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_vgg_bn_loss_variant_against_reference_fixture(golden_dir, mode):
     """use_vgg19_with_batchnorm (codes/loss.py:41-63).  The reference's scripts leave the loss module in train
-    mode, so BatchNorm uses the statistics of each batch it is given; the product has no kernels for it yet and refuses."""
+    mode, so BatchNorm uses the statistics of each batch it is given."""
     from conftest import seeded_vgg19_bn
     import mastermetastyletransfer_b200 as mst
     gold = json.load(open(os.path.join(golden_dir, "vgg_bn_loss.json")))
@@ -174,5 +174,5 @@ def test_vgg_bn_loss_variant_against_reference_fixture(golden_dir, mode):
     with torch.no_grad():
         got = [t.item() for t in O.overall_loss(sd, content, style, output, 10.0, batchnorm=mode)]
     assert got == pytest.approx(gold[mode], rel=1e-4)
-    with pytest.raises(NotImplementedError):
-        mst.custom_loss("/nonexistent", use_vgg19_with_batchnorm=True)
+    m = mst.custom_loss("/nonexistent", use_vgg19_with_batchnorm=True)  # builds the reference's module tree (kernels: tests/test_gpu_path.py)
+    assert sorted(m.feature_extractor_model.features.state_dict().keys()) == sorted(sd.keys())
