@@ -273,6 +273,14 @@ int mst_patch_embed_ln(const float* img, const float* w, const float* b, const f
  *   `np.clip(img * 255, 0, 255).astype(np.uint8)` (truncation) -- bit-exact.  W % 4 == 0. */
 int mst_images_u8_to_nchw(const uint8_t* src, float* dst, int B, int H, int W, const float* mean3, const float* std3, void* stream);
 int mst_images_nchw_to_u8(const float* src, uint8_t* dst, int B, int H, int W, void* stream);
+/* The reference's training-image transform (codes/get_dataloader.py:30-36: ToPILImage -> Resize((512,512)) -> RandomCrop((256,256))
+ * -> ToTensor -> Normalize) on a decoded uint8 [H, W, 3] image, one kernel: out fp32 [3, ch, cw] = the (top, left) crop of Pillow's
+ * antialiased bilinear resize, /255, normalised (mean3 / std3 host pointers, NULL = ToTensor only).  xmin / xcnt [out_w], xk
+ * [out_w, ksx] (and the y arrays, [out_h]) are Pillow's resampling windows and 22-bit fixed-point coefficients for (W -> out_w) and
+ * (H -> out_h), device pointers (mastermetastyletransfer_b200.data.pil_resize_coeffs).  Bit-exact against the torchvision pipeline. */
+int mst_resize_crop_normalize(const uint8_t* img, int H, int W, const int32_t* xmin, const int32_t* xcnt, const int32_t* xk, int ksx,
+                              const int32_t* ymin, const int32_t* ycnt, const int32_t* yk, int ksy, int top, int left, int ch, int cw,
+                              const float* mean3, const float* std3, float* out, void* stream);
 
 /* fp32 [rows, C] -> bf16 copy (A operands of the first projections) */
 /* nn.Upsample(scale_factor=2, mode='nearest') on a bf16 NHWC tensor: x [B,H,W,C] -> y [B,2H,2W,C] (decoder.py:27), C % 8 == 0. */

@@ -132,6 +132,7 @@ SYMBOLS = {
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
     "mst_images_u8_to_nchw": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "mst_images_nchw_to_u8": (_I, [_P, _P, _I, _I, _I, _P]),
+    "mst_resize_crop_normalize": (_I, [_P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "mst_upsample2x_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "mst_opt_chunk_elems": (_I, []),
     "mst_adam_step": (_I, [C.POINTER(MstTensorTable), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _I, _P]),

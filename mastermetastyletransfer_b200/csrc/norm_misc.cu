@@ -661,6 +661,64 @@ extern "C" int mst_images_nchw_to_u8(const float* src, uint8_t* dst, int B, int 
   return (int)cudaGetLastError();
 }
 
+namespace mst {
+// ---------------------------------------------------------------- training-image transform (codes/get_dataloader.py:30-36)
+// ToPILImage -> Resize((512, 512)) -> RandomCrop((256, 256)) -> ToTensor -> Normalize as ONE kernel on a decoded uint8 HWC image:
+// only the cropped window of the resized image is ever computed.  The resize is Pillow's antialiased bilinear resample
+// (libImaging/Resample.c, 8 bits per channel), restated exactly: a horizontal pass into an 8-bit intermediate, then a vertical
+// pass, each  clip8((2^21 + sum_t pixel_t * k_t) >> 22)  with the fixed-point coefficients k = (int)(0.5 + w * 2^22) that the host
+// precomputes the way precompute_coeffs / normalize_coeffs_8bpc do (data.pil_resize_coeffs); then ((v / 255) - mean) / std in the
+// fp32 operation order of torchvision (bit-exact against the reference's transform pipeline, tests/test_gpu_kernels.py).
+// Thread = one output pixel (three channels); the intermediate values a thread needs are recomputed, not stored.
+__global__ void __launch_bounds__(256) resize_crop_normalize_kernel(const uint8_t* __restrict__ img, int H, int W, const int32_t* __restrict__ xmin,
+                                                                    const int32_t* __restrict__ xcnt, const int32_t* __restrict__ xk, int ksx,
+                                                                    const int32_t* __restrict__ ymin, const int32_t* __restrict__ ycnt,
+                                                                    const int32_t* __restrict__ yk, int ksy, int top, int left, int ch, int cw,
+                                                                    float m0, float m1, float m2, float s0, float s1, float s2, int normalize,
+                                                                    float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= cw || y >= ch) return;
+  const int X = left + x, Y = top + y;           // position in the resized image
+  const int x0 = xmin[X], nx = xcnt[X], y0 = ymin[Y], ny = ycnt[Y];
+  const int32_t* kx = xk + (long long)X * ksx;
+  const int32_t* ky = yk + (long long)Y * ksy;
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int v = 0; v < ny; ++v) {
+    const uint8_t* row = img + ((long long)(y0 + v) * W + x0) * 3;
+    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int u = 0; u < nx; ++u) {
+      const int k = kx[u];
+      h[0] += (int)row[3 * u] * k;
+      h[1] += (int)row[3 * u + 1] * k;
+      h[2] += (int)row[3 * u + 2] * k;
+    }
+    const int kv = ky[v];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += min(max(h[c] >> 22, 0), 255) * kv;  // the 8-bit intermediate image of the horizontal pass
+  }
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float f = __fdiv_rn((float)min(max(acc[c] >> 22, 0), 255), 255.0f);
+    if (normalize) f = __fdiv_rn(__fsub_rn(f, mean[c]), sd[c]);
+    out[((long long)c * ch + y) * cw + x] = f;
+  }
+}
+}  // namespace mst
+
+extern "C" int mst_resize_crop_normalize(const uint8_t* img, int H, int W, const int32_t* xmin, const int32_t* xcnt, const int32_t* xk, int ksx,
+                                         const int32_t* ymin, const int32_t* ycnt, const int32_t* yk, int ksy, int top, int left, int ch, int cw,
+                                         const float* mean3, const float* std3, float* out, void* stream) {
+  if (!img || !xmin || !xcnt || !xk || !ymin || !ycnt || !yk || !out || H <= 0 || W <= 0 || ksx <= 0 || ksy <= 0) return MST_ERR_BAD_ARG;
+  if (top < 0 || left < 0 || ch <= 0 || cw <= 0 || (mean3 == nullptr) != (std3 == nullptr)) return MST_ERR_BAD_ARG;
+  const float m[3] = {mean3 ? mean3[0] : 0.f, mean3 ? mean3[1] : 0.f, mean3 ? mean3[2] : 0.f};
+  const float sd[3] = {std3 ? std3[0] : 1.f, std3 ? std3[1] : 1.f, std3 ? std3[2] : 1.f};
+  dim3 grid((cw + 255) / 256, ch);
+  mst::resize_crop_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, H, W, xmin, xcnt, xk, ksx, ymin, ycnt, yk, ksy, top, left, ch, cw, m[0],
+                                                                            m[1], m[2], sd[0], sd[1], sd[2], mean3 != nullptr, out);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mst_version(void) { return 100; }
 extern "C" int mst_sm_arch(void) { return 100; }
 extern "C" const char* mst_error_string(int code) {

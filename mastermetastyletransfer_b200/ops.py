@@ -56,7 +56,7 @@ KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kerne
              "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
-             "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
+             "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_resize_crop_normalize": "resize_crop_normalize_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_bn_relu": "bn_relu_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
              "mst_loss_finalize": "loss_finalize_kernel", "mst_sim_prepare": "sim_prepare_kernels", "mst_sim_tiles": "sim_tile_kernel", "mst_sim_finalize": "sim_finalize_kernel", "mst_wgrad": "wgrad_tc_kernel", "mst_colsum": "colsum_kernel",
@@ -390,6 +390,25 @@ def images_u8_to_nchw(src_u8, dst32, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> No
     sd = C.cast((C.c_float * 3)(*std), C.c_void_p) if mean is not None else None
     _launch("mst_images_u8_to_nchw", lambda: _lib.lib().mst_images_u8_to_nchw(_ptr(src_u8, torch.uint8, "src"), _ptr(dst32, torch.float32, "dst"),
                                                                               B, H, W, m, sd, _stream()), nbytes=15.0 * B * H * W)
+
+
+def resize_crop_normalize(img_u8, coeffs_x, coeffs_y, top: int, left: int, out32, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> None:
+    """Decoded uint8 [H,W,3] image -> fp32 [3,ch,cw]: the (top, left) crop of Pillow's bilinear resize, ToTensor, Normalize
+    (codes/get_dataloader.py:30-36).  coeffs_* = (xmin int32 [out], count int32 [out], k int32 [out, ksize]) device tensors from
+    data.pil_resize_coeffs for the image's width / height."""
+    H, W, ch3 = img_u8.shape
+    if ch3 != 3 or out32.dim() != 3 or out32.shape[0] != 3 or not out32.is_contiguous() or not img_u8.is_contiguous():
+        raise ValueError("resize_crop_normalize: img [H,W,3] uint8 contiguous, out [3,ch,cw] fp32 contiguous")
+    (xm, xc, xk), (ym, yc, yk) = coeffs_x, coeffs_y
+    chh, cw = int(out32.shape[1]), int(out32.shape[2])
+    if top + chh > ym.numel() or left + cw > xm.numel():
+        raise ValueError("resize_crop_normalize: the crop window leaves the resized image")
+    m = C.cast((C.c_float * 3)(*mean), C.c_void_p) if mean is not None else None
+    sd = C.cast((C.c_float * 3)(*std), C.c_void_p) if mean is not None else None
+    _launch("mst_resize_crop_normalize", lambda: _lib.lib().mst_resize_crop_normalize(
+        _ptr(img_u8, torch.uint8, "img"), H, W, _ptr(xm, torch.int32, "xmin"), _ptr(xc, torch.int32, "xcnt"), _ptr(xk, torch.int32, "xk"),
+        int(xk.shape[1]), _ptr(ym, torch.int32, "ymin"), _ptr(yc, torch.int32, "ycnt"), _ptr(yk, torch.int32, "yk"), int(yk.shape[1]),
+        int(top), int(left), chh, cw, m, sd, _ptr(out32, torch.float32, "out"), _stream()), nbytes=3.0 * H * W + 12.0 * chh * cw)
 
 
 def images_nchw_to_u8(src32, dst_u8) -> None:

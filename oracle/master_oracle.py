@@ -557,3 +557,20 @@ def tensor_to_images_u8(x: Tensor) -> Tensor:
     import numpy as np
     a = x.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous().numpy()
     return torch.from_numpy(np.clip(a * 255, 0, 255).astype(np.uint8))
+
+
+# ----------------------------------------------------------------------------------------------
+# training-image transform (codes/get_dataloader.py:30-36)
+# ----------------------------------------------------------------------------------------------
+
+
+def train_transform(img_u8_hwc, top: int, left: int, size=(512, 512), crop=(256, 256), mean=IMAGENET_MEAN, std=IMAGENET_STD) -> Tensor:
+    """ToPILImage -> Resize(size) -> crop at (top, left) -> ToTensor -> Normalize, with the libraries the reference's transform
+    itself is made of (torchvision.transforms.functional on a PIL image): the checker of the fused GPU transform.  RandomCrop's
+    only random part is the choice of (top, left) (RandomCrop.get_params), passed in here."""
+    import torchvision.transforms.functional as TF
+    pil = TF.to_pil_image(img_u8_hwc if not isinstance(img_u8_hwc, Tensor) else img_u8_hwc.numpy())
+    pil = TF.resize(pil, list(size))
+    pil = TF.crop(pil, top, left, crop[0], crop[1])
+    return TF.normalize(TF.to_tensor(pil), list(mean), list(std))
+

@@ -414,3 +414,32 @@ def test_attn_block_equals_unfused_kernels():
     ops.attn_block(x16, ops.pack_attn_qkv(*w3, *b3, heads), table, o, B, H, H, ws, shift)
     torch.cuda.synchronize()
     assert (o.float() - o_ref.float()).abs().max().item() <= 1e-2
+
+
+@pytest.mark.parametrize("H,W", [(480, 640), (333, 500), (700, 1024), (100, 120), (512, 512)])
+def test_gpu_train_transform_bit_exact_vs_reference_pipeline(H, W):
+    """the reference's training-image transform (codes/get_dataloader.py:30-36: ToPILImage -> Resize((512,512)) ->
+    RandomCrop((256,256)) -> ToTensor -> Normalize) as ONE kernel on the decoded uint8 image, against the torchvision / Pillow
+    pipeline itself (oracle.train_transform) with the same crop window: BIT-EXACT (integer resample arithmetic restated from
+    Pillow, IEEE fp32 division / subtraction in torchvision's order).  Shrinking (antialiased), enlarging, identity sizes; crop
+    windows at the borders and drawn like RandomCrop does."""
+    from mastermetastyletransfer_b200.data import GpuTrainTransform
+    from oracle import master_oracle as O
+    rng = np.random.default_rng(H * 7 + W)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    tf = GpuTrainTransform("cuda")
+    torch.manual_seed(H + W)
+    windows = [(0, 0), (256, 256), (0, 256), tf.crop_params(), tf.crop_params()]
+    for top, left in windows:
+        out = tf(img, top_left=(top, left)).cpu()
+        ref = O.train_transform(img, top, left)
+        assert out.shape == ref.shape == (3, 256, 256)
+        assert torch.equal(out, ref), (H, W, top, left, (out - ref).abs().max().item())
+    # the random path consumes the generator exactly like the reference's Compose
+    from torchvision import transforms
+    compose = transforms.Compose([transforms.ToPILImage(), transforms.Resize((512, 512)), transforms.RandomCrop((256, 256)),
+                                  transforms.ToTensor(), transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    torch.manual_seed(5)
+    ref = compose(img)
+    torch.manual_seed(5)
+    assert torch.equal(tf(img).cpu(), ref)

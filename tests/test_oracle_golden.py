@@ -176,3 +176,47 @@ def test_vgg_bn_loss_variant_against_reference_fixture(golden_dir, mode):
     assert got == pytest.approx(gold[mode], rel=1e-4)
     m = mst.custom_loss("/nonexistent", use_vgg19_with_batchnorm=True)  # builds the reference's module tree (kernels: tests/test_gpu_path.py)
     assert sorted(m.feature_extractor_model.features.state_dict().keys()) == sorted(sd.keys())
+
+
+def test_pil_resize_coefficients_reproduce_pillow_bit_for_bit():
+    """the fixed-point resampling coefficients the GPU transform uploads (data.pil_resize_coeffs, a restatement of
+    Pillow's precompute_coeffs / normalize_coeffs_8bpc) drive a plain integer two-pass resample that equals PIL.Image.resize
+    (BILINEAR) exactly -- shrinking (antialiased, many taps), enlarging and mixed cases."""
+    from PIL import Image
+    from mastermetastyletransfer_b200.data import PRECISION_BITS, pil_resize_coeffs
+    rng = np.random.default_rng(0)
+    for (H, W, oh, ow) in [(480, 640, 512, 512), (333, 500, 512, 512), (700, 1024, 512, 512), (100, 120, 512, 512), (37, 1200, 64, 48)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        xm, xc, xk = pil_resize_coeffs(W, ow)
+        ym, yc, yk = pil_resize_coeffs(H, oh)
+        src = img.astype(np.int64)
+        tmp = np.zeros((H, ow, 3), np.int64)
+        for x in range(ow):
+            acc = np.full((H, 3), 1 << (PRECISION_BITS - 1), np.int64)
+            for t in range(xc[x]):
+                acc += src[:, xm[x] + t, :] * int(xk[x, t])
+            tmp[:, x, :] = np.clip(acc >> PRECISION_BITS, 0, 255)
+        out = np.zeros((oh, ow, 3), np.uint8)
+        for y in range(oh):
+            acc = np.full((ow, 3), 1 << (PRECISION_BITS - 1), np.int64)
+            for t in range(yc[y]):
+                acc += tmp[ym[y] + t] * int(yk[y, t])
+            out[y] = np.clip(acc >> PRECISION_BITS, 0, 255)
+        assert np.array_equal(out, ref), (H, W, oh, ow)
+
+
+def test_oracle_train_transform_is_the_reference_compose():
+    """oracle.train_transform == the reference's transforms.Compose (codes/get_dataloader.py:30-36) when RandomCrop draws the same
+    window: the Compose is run under a fixed seed, the drawn (top, left) recovered with RandomCrop.get_params under the same seed."""
+    from torchvision import transforms
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (300, 420, 3), dtype=np.uint8)
+    compose = transforms.Compose([transforms.ToPILImage(), transforms.Resize((512, 512)), transforms.RandomCrop((256, 256)),
+                                  transforms.ToTensor(), transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    torch.manual_seed(123)
+    ref = compose(img)
+    torch.manual_seed(123)
+    from mastermetastyletransfer_b200.data import GpuTrainTransform
+    top, left = GpuTrainTransform("cpu").crop_params()
+    assert torch.equal(O.train_transform(img, top, left), ref)
