@@ -230,6 +230,53 @@ def gpu_eager_baseline(model, content, style, layers, dev, iters: int = 5):
     return out
 
 
+def loss_reduction_rates(dev, B: int, size: int, hbm_gbs: float):
+    """Device-side HBM rate of the loss reductions on the four tap shapes of a batch-B loss call (3B images in the statistics
+    pass, content + output images in the content term): ten back-to-back launches of one op are captured in a CUDA graph and the
+    replay is timed, so the number is the kernels' own time -- an eager launch through ctypes costs ~10 us of host time per call,
+    more than the smaller taps take.  Taps that fit the 126 MB L2 are marked: their rate is not an HBM rate."""
+    from mastermetastyletransfer_b200 import ops
+    rec, tot_b, tot_t = {}, {"tap_stats": 0.0, "content_term": 0.0}, {"tap_stats": 0.0, "content_term": 0.0}
+    for i, (hw, c) in enumerate(((size // 2, 128), (size // 4, 256), (size // 8, 512), (size // 16, 512))):
+        T = hw * hw
+        x = torch.randn(3 * B, T, c, device=dev).bfloat16()
+        mean, var = torch.empty(3 * B, c, device=dev), torch.empty(3 * B, c, device=dev)
+        part = torch.empty(592, device=dev)
+        xv = x.view(3 * B, T * c)
+        fns = {"tap_stats": (lambda: ops.tap_stats(x, mean, var, 3 * B, T, c), 2.0 * 3 * B * T * c),
+               "content_term": (lambda: ops.content_term(xv[:B], xv[2 * B:], mean[:B], var[:B], mean[2 * B:], var[2 * B:], B, T, c, False, part),
+                                2.0 * 2 * B * T * c)}
+        for name, (fn, nbytes) in fns.items():
+            fn()
+            torch.cuda.synchronize(dev)
+            st = torch.cuda.Stream(device=dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(st):
+                fn()
+                st.synchronize()
+                with torch.cuda.graph(graph, stream=st):
+                    for _ in range(10):
+                        fn()
+            torch.cuda.synchronize(dev)
+            graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / 30
+            rec[f"{name}_tap{i}"] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1), "frac_of_hbm": round(nbytes / us / 1e3 / hbm_gbs, 3),
+                                     "mbytes": round(nbytes / 1e6, 1), "fits_l2": nbytes < 100e6}
+            tot_b[name] += nbytes
+            tot_t[name] += us
+        del x
+    for name in tot_b:
+        rec[name + "_all_taps"] = {"us": round(tot_t[name], 1), "gbs": round(tot_b[name] / tot_t[name] / 1e3, 1),
+                                   "frac_of_hbm": round(tot_b[name] / tot_t[name] / 1e3 / hbm_gbs, 3)}
+    return rec
+
+
 def bench_loss_forward(dev, hbm_gbs: float, size: int = 256):
     """VGG-19 content/style loss forward (custom_loss.forward, rows a15-a18) at batch 32 and 8: whole-call milliseconds and the
     HBM rate of the reduction kernels (tap statistics incl. their finalisation, content term) summed over the four taps, from
@@ -269,7 +316,8 @@ def bench_loss_forward(dev, hbm_gbs: float, size: int = 256):
                for k, v in fam.items() if k in ("tap_stats_kernel", "content_term_kernel", "loss_finalize_kernel") and v["bytes"]}
         conv_ms = sum(v["ms"] for k, v in fam.items() if v["flops"])
         conv_fl = sum(v["flops"] for k, v in fam.items() if v["flops"])
-        out[f"batch{B}"] = {"ms_per_call": a.elapsed_time(b) / 5, "reductions": red,
+        out[f"batch{B}"] = {"ms_per_call": a.elapsed_time(b) / 5, "reductions_eager_events": red,
+                            "reductions": loss_reduction_rates(dev, B, size, hbm_gbs),
                             "vgg_convs": {"ms": round(conv_ms, 3), "tflops": round(conv_fl / (conv_ms * 1e9), 1) if conv_ms else None},
                             "roofline_hbm": {"peak_gbs": hbm_gbs, "bytes": "each bf16 tap tensor read once per kernel launch"}}
     return out

@@ -16,6 +16,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 IMG_TOL = 2e-2
+# k >= 2 shared-weight layers compound the bf16 operand rounding: measured max error / range over the tested shapes 1.3e-2 .. 2.3e-2
+# (tools/debug/path_err.py; mean 2e-3, p99.9 1e-2) -- held to 2.5e-2 (it was 4e-2 before the fused MLP moved to fp16 hidden activations)
+K_GE2_TOL = 2.5e-2
 FEAT_TOL = 3e-2
 
 
@@ -105,7 +108,7 @@ def test_full_forward_7x7_windows_vs_oracle_and_golden(size, k, golden_dir):
         out = m(content.cuda(), style.cuda(), k)
         ref = O.full_forward(sd7, content, style, k, ws=7, sh=4)
     e = rel_err(out, ref)
-    assert e <= (IMG_TOL if k == 1 else 2 * IMG_TOL), e
+    assert e <= (IMG_TOL if k == 1 else K_GE2_TOL), e
     if size == 128 and k == 1:  # golden minted from the real reference with the same seeded weights (oracle/make_golden.py)
         g = torch.from_numpy(np.load(os.path.join(golden_dir, "path_128.npz"))["img_ws7"])
         assert ((out.cpu()[:, :, ::2, ::2] - g).abs().max() / (g.max() - g.min())).item() <= IMG_TOL
@@ -122,7 +125,7 @@ def test_config1_256_vs_golden(model, k, golden_dir):
     g = torch.from_numpy(gold[f"img_k{k}"])
     rng = float(gold[f"img_k{k}_stats"][3] - gold[f"img_k{k}_stats"][2])
     e = ((out[:, :, ::4, ::4] - g).abs().max() / rng).item()
-    assert e <= (IMG_TOL if k == 1 else 2 * IMG_TOL), e  # three shared-weight layers compound the bf16 rounding
+    assert e <= (IMG_TOL if k == 1 else K_GE2_TOL), e  # three shared-weight layers compound the bf16 rounding
 
 
 def test_batch_independence_and_determinism(model):
@@ -307,7 +310,7 @@ def test_config5_512_vs_oracle_and_golden(ws, k, golden_dir):
         out = m(content.cuda(), style.cuda(), k).cpu()
         ref = O.full_forward(sdw, content, style, k, ws=ws, sh=4)
     assert out.shape == ref.shape == (2, 3, 512, 512)
-    tol = IMG_TOL if k == 1 else 2 * IMG_TOL
+    tol = IMG_TOL if k == 1 else K_GE2_TOL
     e = rel_err(out, ref)
     assert e <= tol, e
     gold = np.load(os.path.join(golden_dir, "path_512.npz"))

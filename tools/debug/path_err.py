@@ -14,7 +14,7 @@ for ws in (8, 7):
     synthetic.fill_state_dict_(m, 0)
     sd = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
     m = m.eval().cuda()
-    for size, k, seed in ((128, 1, 0), (128, 2, 0), (256, 1, 0), (128, 1, 3), (128, 1, 4)):
+    for size, k, seed in ((128, 1, 0), (128, 2, 0), (128, 3, 0), (256, 1, 0), (256, 2, 1), (256, 3, 1), (512, 1, 2), (512, 2, 2), (128, 1, 3), (128, 1, 4)):
         content, style = synthetic.synthetic_images(2, size, seed=seed)
         with torch.no_grad():
             out = m(content.cuda(), style.cuda(), k)
