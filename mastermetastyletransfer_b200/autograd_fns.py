@@ -61,8 +61,9 @@ class _StyleTransformerFn(torch.autograd.Function):
         w = packed_weights(module, te.StyleTransformerTrainWeights)
         geo = te._Geo(B, H, W, C, cfg["heads"], cfg["window"][0], cfg["shift"][0])
         sd = _draw_stochastic_depth(module, B, k, Fc.device)
-        out, tape = te.style_transformer_forward_train(w, Fc.detach().float().contiguous(), Fs.detach().float().contiguous(), k, geo, sd)
-        ctx.module, ctx.w, ctx.geo, ctx.tape, ctx.sd = module, w, geo, tape, sd
+        flags = module.engine_flags()  # the reference's alternate orderings: same kernels, re-sequenced forward and adjoint
+        out, tape = te.style_transformer_forward_train(w, Fc.detach().float().contiguous(), Fs.detach().float().contiguous(), k, geo, sd, **flags)
+        ctx.module, ctx.w, ctx.geo, ctx.tape, ctx.sd, ctx.flags = module, w, geo, tape, sd, flags
         return out.view(B, H, W, C)
 
     @staticmethod
@@ -71,7 +72,8 @@ class _StyleTransformerFn(torch.autograd.Function):
         names, params = _param_lists(module)
         book = te.st_grad_book({n: p.shape for n, p in zip(names, params)}, g.device)
         if ctx.tape:
-            te.style_transformer_backward(ctx.w, ctx.tape, g.float().contiguous(), ctx.geo, ctx.sd, book, workspace_of(module, g.device))
+            te.style_transformer_backward(ctx.w, ctx.tape, g.float().contiguous(), ctx.geo, ctx.sd, book, workspace_of(module, g.device),
+                                          **ctx.flags)
         ctx.tape = None  # free the saved activations
         return (None, None, None, None) + _grads_out(names, params, book)
 

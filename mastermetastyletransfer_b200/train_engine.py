@@ -83,12 +83,16 @@ class StyleTransformerTrainWeights:
         self.enc_proj = lin(e + "proj")
         self.enc_table = g(e + "relative_position_bias_table")
         self.mlp = {}
-        for tag, p in (("key", "encoder.encoder_MLP_Key."), ("scale", "encoder.encoder_MLP_Scale."), ("shift", "encoder.encoder_MLP_Shift."),
-                       ("dec", "decoder.MHA_self_attn.mlp."), ("last", "decoder.last_MLP.")):
-            self.mlp[tag] = (lin(p + "0"), lin(p + "3"), p)
         d = "decoder.MHA_self_attn."
+        # decoder_exclude_MLP_after_Fcs_self_MHA=True builds the block without norm2 / mlp (reference :339-343,365)
+        self.has_dec_mlp = (prefix + d + "mlp.0.weight") in sd
+        for tag, p in (("key", "encoder.encoder_MLP_Key."), ("scale", "encoder.encoder_MLP_Scale."), ("shift", "encoder.encoder_MLP_Shift."),
+                       ("dec", d + "mlp."), ("last", "decoder.last_MLP.")):
+            if tag == "dec" and not self.has_dec_mlp:
+                continue
+            self.mlp[tag] = (lin(p + "0"), lin(p + "3"), p)
         self.n1 = (g(d + "norm1.weight"), g(d + "norm1.bias"))
-        self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias"))
+        self.n2 = (g(d + "norm2.weight"), g(d + "norm2.bias")) if self.has_dec_mlp else None
         a = d + "attn."
         self.dec_qkv = _Lin(torch.cat([g(a + "Wq.weight"), g(a + "Wk.weight"), g(a + "Wv.weight")], 0),
                             torch.cat([g(a + "Wq.bias"), g(a + "Wk.bias"), g(a + "Wv.bias")], 0))
@@ -238,10 +242,16 @@ def _scaled16(g32, rs, rows, ws_: Workspace, name="bw_g16"):
 
 
 def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch.Tensor, fs32: torch.Tensor, k: int, g: _Geo,
-                                    sd_scales: Optional[torch.Tensor]):
+                                    sd_scales: Optional[torch.Tensor], *, processed_key: bool = True, key_in_after_linear: bool = True,
+                                    exclude_mlp: bool = False):
     """Forward of StyleTransformer.forward (:1229-1245) that records a tape.  sd_scales: None or fp32 [k, 9, B] per-sample
     stochastic-depth factors in the reference's draw order (enc MHA Key, MLP_Key, MHA Scale, MLP_Scale, MHA Shift, MLP_Shift,
-    dec attn, dec mlp, last MLP).  Returns (out32 [T,C], tape)."""
+    dec attn, dec mlp, last MLP).  Returns (out32 [T,C], tape).
+    processed_key / key_in_after_linear / exclude_mlp: the reference's alternate orderings (engine.style_transformer_forward
+    documents them): the Scale / Shift passes attend with the layer's INPUT Key; Key is instance-normalised twice BEFORE Wk and Wk.Key
+    is used as it is; the decoder's self-attention block has no norm2 / MLP."""
+    if exclude_mlp == w.has_dec_mlp:
+        raise ValueError("decoder_exclude_MLP_after_Fcs_self_MHA does not match the packed state_dict (decoder.MHA_self_attn.mlp.*)")
     dev, T, C, Tp = fc32.device, g.T, g.C, g.Tp
     rows = g.HW
     x32 = fc32.reshape(T, C).contiguous()
@@ -273,7 +283,10 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
             key16p = _pad16(g, key16)
             t.update(qkv1=qkv1, o1=o1, key16a=key16a, hK=(hp, ha), key16b=key16p, key32b=key32)
             qk2, vs, vh = _e16(dev, Tp, 2 * C), _e16(dev, Tp, C), _e16(dev, Tp, C)
-            ops.gemm(key16p, w.enc_qk.fwd, Tp, out_bf16=qk2)
+            # q, k of the Scale / Shift passes: the processed Key (default, :857-882) or this layer's input Key (:883-909); the
+            # passes are independent of the Key pass in the second case, only their gradient lands on a different tensor
+            t["qk2_in"] = key16p if processed_key else t["key16_in"]
+            ops.gemm(t["qk2_in"], w.enc_qk.fwd, Tp, out_bf16=qk2)
             ops.gemm(scale16p, w.enc_v.fwd, Tp, out_bf16=vs)
             ops.gemm(shift16p, w.enc_v.fwd, Tp, out_bf16=vh)
             osp, ohp = _e16(dev, Tp, C), _e16(dev, Tp, C)
@@ -305,11 +318,15 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
             o3 = _crop16(g, o3p)
             x32a = _e32(dev, T, C)
             ops.gemm(o3, w.dec_proj.fwd, T, res=x32_in, out_f32=x32a, row_scale=s(6), rows_per_scale=rows)
-            ln2 = _e16(dev, T, C)
-            ops.layernorm(x32a, w.n2[0], w.n2[1], ln2, T, C)
-            fc1, fc2, _ = w.mlp["dec"]
-            query32, _, hp, ha = _mlp_fwd(ln2, x32a, fc1, fc2, T, dev, s(7), rows, want16=False)
-            t.update(x32_in=x32_in, ln1=ln1, qkv3=qkv3, o3=o3, x32a=x32a, ln2=ln2, hD=(hp, ha), query32=query32)
+            if exclude_mlp:  # Query = Fcs + proj(attention) only (:389-392)
+                query32 = x32a
+                t.update(x32_in=x32_in, ln1=ln1, qkv3=qkv3, o3=o3, x32a=x32a, query32=query32)
+            else:
+                ln2 = _e16(dev, T, C)
+                ops.layernorm(x32a, w.n2[0], w.n2[1], ln2, T, C)
+                fc1, fc2, _ = w.mlp["dec"]
+                query32, _, hp, ha = _mlp_fwd(ln2, x32a, fc1, fc2, T, dev, s(7), rows, want16=False)
+                t.update(x32_in=x32_in, ln1=ln1, qkv3=qkv3, o3=o3, x32a=x32a, ln2=ln2, hD=(hp, ha), query32=query32)
             qmean, qrstd = _e32(dev, g.B, C), _e32(dev, g.B, C)
             qhat = _e16(dev, T, C)
             ops.instnorm_stats(query32, qmean, qrstd, g.B, g.HW, C, twice=True)
@@ -321,14 +338,19 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
         query32, qhat = t["query32"], t.pop("_qhat")
         mean, rstd = _e32(dev, g.B, C), _e32(dev, g.B, C)
         kin, khat = _e16(dev, T, C), _e16(dev, T, C)
-        ops.instnorm_stats(key32, mean, rstd, g.B, g.HW, C)
+        ops.instnorm_stats(key32, mean, rstd, g.B, g.HW, C, twice=not key_in_after_linear)
         ops.instnorm_apply(key32, mean, rstd, g.B, g.HW, C, y16=kin)
         # padded q tokens are zero (no Q projection, :511-514); Wk runs on the padded Key and its InstanceNorm over the PADDED map (:520-530)
         qhat, kin = _pad16(g, qhat), _pad16(g, kin)
-        kk32, khat = _e32(dev, Tp, C), (khat if not g.padded else _e16(dev, Tp, C))
-        ops.gemm(kin, w.sm_k.fwd, Tp, out_f32=kk32)
-        ops.instnorm_stats(kk32, mean, rstd, g.B, g.HWp, C)
-        ops.instnorm_apply(kk32, mean, rstd, g.B, g.HWp, C, y16=khat)
+        khat = khat if not g.padded else _e16(dev, Tp, C)
+        if key_in_after_linear:
+            kk32 = _e32(dev, Tp, C)
+            ops.gemm(kin, w.sm_k.fwd, Tp, out_f32=kk32)
+            ops.instnorm_stats(kk32, mean, rstd, g.B, g.HWp, C)
+            ops.instnorm_apply(kk32, mean, rstd, g.B, g.HWp, C, y16=khat)
+        else:  # IN(IN(Key)) on the unpadded map (:1057 then :470-472), k = Wk.Key + bk as it is (padded tokens: bk, :520)
+            kk32 = None
+            ops.gemm(kin, w.sm_k.fwd, Tp, out_bf16=khat)
         vs2, vh2, osgp, omup = _e16(dev, Tp, C), _e16(dev, Tp, C), _e16(dev, Tp, C), _e16(dev, Tp, C)
         ops.gemm(scale16p, w.sm_vs.fwd, Tp, out_bf16=vs2)
         ops.gemm(shift16p, w.sm_vh.fwd, Tp, out_bf16=vh2)
@@ -345,7 +367,8 @@ def style_transformer_forward_train(w: StyleTransformerTrainWeights, fc32: torch
 
 
 def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: torch.Tensor, g: _Geo, sd_scales: Optional[torch.Tensor],
-                               book: GradBook, ws_: Workspace):
+                               book: GradBook, ws_: Workspace, *, processed_key: bool = True, key_in_after_linear: bool = True,
+                               exclude_mlp: bool = False):
     """Adjoint of style_transformer_forward_train: accumulates every parameter gradient into `book`; returns nothing for
     Fc / Fs (the Swin encoder is frozen in the reference's default training setup, train.py:216-218)."""
     dev, T, C, Tp = g_out.device, g.T, g.C, g.Tp
@@ -380,17 +403,21 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
         _lin_bwd_acc(g, dvh2, t["shift16b"], w.sm_vh, book[SM + "Wv_shift.weight"], book[SM + "Wv_shift.bias"], gshift, ws_)
         # ---- khat = IN_padded(Wk pad(IN(Key))) ; qhat = pad(IN(IN(Query)))
         dkk16, dkin16 = ws_.bf16("bw_dkk", Tp, C), ws_.bf16("bw_dkin", Tp, C)
-        ops.instnorm_bwd(t["kk32"], dkhat, coef, g.B, g.HWp, C, dx16=dkk16)
+        if key_in_after_linear:
+            ops.instnorm_bwd(t["kk32"], dkhat, coef, g.B, g.HWp, C, dx16=dkk16)
+        else:  # khat = Wk pad(IN(IN(Key))) + bk: no normalisation after the projection
+            dkk16 = dkhat
         _lin_bwd(dkk16, t["kin"], Tp, w.sm_k, book[SM + "Wk.weight"], book[SM + "Wk.bias"], out_bf16=dkin16)
         dkin16, dqhat = _crop16(g, dkin16, ws_, "bw_dkin_c"), _crop16(g, dqhat, ws_, "bw_dqhat_c")
-        ops.instnorm_bwd(t["key32b"], dkin16, coef, g.B, g.HW, C, dx_accum=gkey)
+        ops.instnorm_bwd(t["key32b"], dkin16, coef, g.B, g.HW, C, twice=not key_in_after_linear, dx_accum=gkey)
         ops.instnorm_bwd(t["query32"], dqhat, coef, g.B, g.HW, C, twice=True, dx_accum=gquery)
-        # ---- query = x_a + s7 * MLP_D(LN2(x_a))
-        fc1, fc2, pre = w.mlp["dec"]
-        g16 = _scaled16(gquery, s(7), rows, ws_)
+        # ---- query = x_a + s7 * MLP_D(LN2(x_a))   (query = x_a with decoder_exclude_MLP_after_Fcs_self_MHA)
         dln = ws_.bf16("bw_dln", T, C)
-        _mlp_bwd(g16, t["ln2"], t["hD"][0], t["hD"][1], fc1, fc2, T, book, pre, ws_, out_bf16=dln)
-        ops.layernorm_bwd(t["x32a"], w.n2[0], dln, gquery, book[D_BLK + "norm2.weight"], book[D_BLK + "norm2.bias"], T, C)  # gquery = g(x_a)
+        if not exclude_mlp:
+            fc1, fc2, pre = w.mlp["dec"]
+            g16 = _scaled16(gquery, s(7), rows, ws_)
+            _mlp_bwd(g16, t["ln2"], t["hD"][0], t["hD"][1], fc1, fc2, T, book, pre, ws_, out_bf16=dln)
+            ops.layernorm_bwd(t["x32a"], w.n2[0], dln, gquery, book[D_BLK + "norm2.weight"], book[D_BLK + "norm2.bias"], T, C)  # gquery = g(x_a)
         # ---- x_a = x + s6 * proj(attn(qkv(LN1(x))))
         g16 = _scaled16(gquery, s(6), rows, ws_)
         do3 = ws_.bf16("bw_do", T, C)
@@ -426,7 +453,8 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
         wv_w, wv_b = enc_qkv_w[2 * C:], enc_qkv_b[2 * C:]
         _lin_bwd_acc(g, dvs, t["scale16_in"], w.enc_v, wv_w, wv_b, gscale, ws_)
         _lin_bwd_acc(g, dvh, t["shift16_in"], w.enc_v, wv_w, wv_b, gshift, ws_)
-        _lin_bwd_acc(g, dqk2, t["key16b"], w.enc_qk, enc_qkv_w[:2 * C], enc_qkv_b[:2 * C], gkey, ws_)
+        if processed_key:  # q, k of the Scale / Shift passes came from the PROCESSED Key: their gradient joins gkey before the Key pass' adjoint
+            _lin_bwd_acc(g, dqk2, t["qk2_in"], w.enc_qk, enc_qkv_w[:2 * C], enc_qkv_b[:2 * C], gkey, ws_)
         fc1, fc2, pre = w.mlp["key"]
         g16 = _scaled16(gkey, s(1), rows, ws_)
         _mlp_bwd(g16, t["key16a"], t["hK"][0], t["hK"][1], fc1, fc2, T, book, pre, ws_, res=gkey, out_f32=gkey)
@@ -437,6 +465,8 @@ def style_transformer_backward(w: StyleTransformerTrainWeights, tape, g_out: tor
         _attn_bwd(g, q1, q1[:, C:], q1[:, 2 * C:], dosp, dqkv, dqkv[:, C:], dqkv[:, 2 * C:], w.enc_table, etab,
                   3 * C, 3 * C, 3 * C, 3 * C, 3 * C, 3 * C)
         _lin_bwd_acc(g, dqkv, t["key16_in"], w.enc_qkv, enc_qkv_w, enc_qkv_b, gkey, ws_)
+        if not processed_key:  # ... from the layer's INPUT Key: it joins gkey after the Key pass' adjoint has mapped gkey back to the input
+            _lin_bwd_acc(g, dqk2, t["qk2_in"], w.enc_qk, enc_qkv_w[:2 * C], enc_qkv_b[:2 * C], gkey, ws_)
         if l == 0:
             break
         # layer l-1's Key/Scale/Shift outputs feed this layer: the streams carry over as they are

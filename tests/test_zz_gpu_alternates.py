@@ -68,8 +68,36 @@ def test_regular_mha_variant_at_64x64_feature_maps():
     assert ((out - ref).abs().max() / (ref.max() - ref.min())).item() <= FEAT_TOL
 
 
-def test_alternate_configurations_have_no_training_step(feats):
+def test_variants_without_adjoint_kernels_refuse_the_training_step(feats):
     fc, fs = feats
-    m = alternate_style_transformer("unprocessed_key", 8).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m(fc.cuda(), fs.cuda(), 1)
+    for name in ("affine_in", "regular_mha"):
+        m = alternate_style_transformer(name, 8).cuda().train()
+        with pytest.raises(NotImplementedError):
+            m(fc.cuda(), fs.cuda(), 1)
+
+
+@pytest.mark.parametrize("name,ws,k", [("unprocessed_key", 8, 1), ("unprocessed_key", 8, 2), ("no_self_mlp", 8, 1), ("key_in_before", 8, 2),
+                                       ("key_in_before", 7, 1), ("all_three", 8, 2), ("all_three", 7, 1)])
+def test_alternate_orderings_in_the_training_step(feats, name, ws, k):
+    """The three re-ordering flags inside the training step (taped forward + adjoint kernels re-sequenced like the inference
+    engine): forward and EVERY parameter gradient against torch autograd through the CPU oracle built with the same flags --
+    same gate as the default configuration's test (tests/test_gpu_train.py::test_style_transformer_grads): rel-L2 <= 5e-2,
+    cos >= 0.998 per parameter."""
+    from oracle import master_oracle as O
+    from test_gpu_train import _cmp_all, _oracle_params
+    fc, fs = feats
+    m = alternate_style_transformer(name, ws)
+    sd = {n: v.detach().cpu().clone() for n, v in m.state_dict().items()}
+    okw = ALTERNATE_CONFIGS[name][1]
+    g = torch.Generator().manual_seed(41)
+    G = torch.randn(fc.shape, generator=g)
+    ps = _oracle_params(sd, "")
+    ref = O.style_transformer(ps, fc, fs, k, ws=ws, sh=4, heads=8, **okw)
+    (ref * G).sum().backward()
+    st = m.cuda().eval()  # eval: no stochastic depth; parameters require grad, so the call goes through the training engine
+    st.zero_grad(set_to_none=True)
+    out = st(fc.cuda(), fs.cuda(), k)
+    assert out.requires_grad
+    assert ((out.detach().cpu() - ref.detach()).abs().max() / (ref.max() - ref.min())).item() <= FEAT_TOL
+    (out * G.cuda()).sum().backward()
+    _cmp_all(st, ps)
