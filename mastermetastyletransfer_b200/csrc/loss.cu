@@ -90,21 +90,26 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const bf16* __restrict_
 }
 
 // ---------------------------------------------------------------- per-(image, channel) mean / biased variance of a bf16 tap
-// x [B,T,C] bf16.  CTA = (T slab, b, 64-channel group); thread = (8-channel chunk, row lane): 16-byte loads, 128-byte rows.
-// Sums are taken relative to a per-channel shift (the channel's first element) so the sum of squares stays well
-// conditioned; every slab writes its partial (sum, sum of squares) to the caller's scratch [slabs][B*C][2] and
-// tap_stats_finalize adds the slabs in a fixed order (deterministic) into mean and biased variance.  The T split is what
-// fills the GPU: the taps are [B, 16384..256, 128..512].
-__global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ part, int T, int C,
-                                                        int rows_per_cta, int BC) {
-  // CTA = (T slab, image b), ALL channels: thread = (8-channel chunk c8 of C/8, row lane rl of 256/(C/8)), so a warp reads
-  // 512 contiguous bytes and consecutive passes walk consecutive rows (the earlier 64-channel CTAs read 128 of every
-  // 2C bytes: 61 % of the HBM rate).
+// x [B,T,C] bf16.  CTA = (T slab, image b), ALL channels: thread = (8-channel chunk c8 of C/8, row lane rl of 256/(C/8)), so a
+// warp reads 512 contiguous bytes and consecutive passes walk consecutive rows.  Sums are taken relative to a per-channel shift
+// (the channel's first element) so the sum of squares stays well conditioned; every slab writes its partial (sum, sum of
+// squares) to the caller's scratch [slabs][B*C][2] and tap_stats_finalize adds the slabs in a fixed order (deterministic) into
+// mean and biased variance.  The slab count is chosen by the host so that the whole grid is ONE resident wave of equal slabs
+// (tap_stats_slabs): a grid of 2.3 waves ran the relu1_1 tap at 65 % of the HBM rate, the missing third being the tail wave.
+// Arithmetic: sm_100's mixed-precision scalar ops (FHADD.BF16 takes a bf16 half of a 32-bit register straight into an fp32
+// subtract), 3 instructions per element instead of 4.5 with an unpack.
+__device__ __forceinline__ void bf16x2_minus_f32(uint32_t w, float klo, float khi, float& alo, float& ahi) {
+  asm("{.reg .b16 lo, hi;\n mov.b32 {lo, hi}, %2;\n sub.rn.f32.bf16 %0, lo, %3;\n sub.rn.f32.bf16 %1, hi, %4;}"
+      : "=f"(alo), "=f"(ahi) : "r"(w), "f"(klo), "f"(khi));
+}
+
+__global__ void __launch_bounds__(256, 5) tap_stats_kernel(const bf16* __restrict__ x, float* __restrict__ part, int T, int C,
+                                                        int slabs, int BC) {
   extern __shared__ float red[];  // [2][RL][C + 1]
   const int C8 = C >> 3, RL = 256 / C8;
   const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * rows_per_cta, t1 = min(T, t0 + rows_per_cta);
+  const int t0 = (int)((long long)blockIdx.x * T / slabs), t1 = (int)((long long)(blockIdx.x + 1) * T / slabs);
   const bf16* xb = x + (long long)b * T * C + c8 * 8;
   float k[8], s[8], q[8];
   {
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float a = __uint_as_float(w[e] << 16) - k[2 * e], d = __uint_as_float(w[e] & 0xFFFF0000u) - k[2 * e + 1];
+      float a, d;
+      bf16x2_minus_f32(w[e], k[2 * e], k[2 * e + 1], a, d);
       s[2 * e] += a; q[2 * e] = fmaf(a, a, q[2 * e]);
       s[2 * e + 1] += d; q[2 * e + 1] = fmaf(d, d, q[2 * e + 1]);
     }
@@ -145,28 +151,52 @@ __global__ void __launch_bounds__(256) tap_stats_kernel(const bf16* __restrict__
   }
 }
 
+// CTA = 32 consecutive (image, channel) entries x 8 slab lanes: lane l adds slabs l, l+8, ... (coalesced 256-byte loads, the
+// loads of one lane independent), then the eight lane sums are added in lane order: a fixed order, so the result is
+// deterministic, and a chain of slabs/8 loads instead of slabs.
 __global__ void __launch_bounds__(256) tap_stats_finalize_kernel(const bf16* __restrict__ x, const float* __restrict__ part,
                                                                  float* __restrict__ mean, float* __restrict__ var, int B, int T,
                                                                  int C, int slabs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
+  __shared__ float2 acc[8][32];
+  const int il = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
   float s = 0.f, q = 0.f;
-  for (int sl = 0; sl < slabs; ++sl) {
-    const float2 v = reinterpret_cast<const float2*>(part)[(long long)sl * B * C + i];
-    s += v.x;
-    q += v.y;
-  }
+  if (i < B * C)
+    for (int sl = lane; sl < slabs; sl += 8) {
+      const float2 v = reinterpret_cast<const float2*>(part)[(long long)sl * B * C + i];
+      s += v.x;
+      q += v.y;
+    }
+  acc[lane][il] = make_float2(s, q);
+  __syncthreads();
+  if (lane != 0 || i >= B * C) return;
+#pragma unroll
+  for (int l = 1; l < 8; ++l) { s += acc[l][il].x; q += acc[l][il].y; }
+  const int b = i / C, c = i - b * C;
   const float k = __bfloat162float(x[(long long)b * T * C + c]);
   const float m = s / (float)T;
   mean[i] = m + k;
   var[i] = fmaxf(q / (float)T - m * m, 0.f);
 }
 
-static int tap_stats_rows(int B, int T, int C) {  // slab size: enough CTAs to cover the GPU a few times over, >= 64 rows each
-  int rows = 64;
-  while ((long long)((T + rows - 1) / rows) * B > 148 * 8 && rows < T) rows *= 2;
-  return rows;
+static size_t tap_stats_smem(int C) { return (size_t)2 * (256 / (C / 8)) * (C + 1) * sizeof(float); }
+
+// Slabs per image: the grid (slabs x B) is one resident wave -- as many CTAs as the device holds at once (occupancy of
+// tap_stats_kernel x SM count; 5 x 148 assumed when no device answers, as on a build host), rounded down to a multiple of B --
+// of equal slabs, none shorter than 16 rows.
+static int tap_stats_slabs(int B, int T, int C) {
+  int per_sm = 0, sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tap_stats_kernel, 256, tap_stats_smem(C)) != cudaSuccess ||
+      per_sm < 1 || sms < 1) {
+    (void)cudaGetLastError();
+    per_sm = 5;
+    sms = 148;
+  }
+  long long slabs = (long long)per_sm * sms / B;
+  if (slabs > T / 16) slabs = T / 16;
+  return (int)(slabs < 1 ? 1 : slabs);
 }
 
 // ---------------------------------------------------------------- content term: sum |IN(Fc) - IN(Fcs)| (or squared)
@@ -341,8 +371,7 @@ extern "C" int mst_bn_relu(const float* x32, mst_bf16* y, const float* mean, con
 
 extern "C" size_t mst_tap_stats_scratch_floats(int B, int T, int C) {
   if (B <= 0 || T <= 0 || C <= 0) return 0;
-  const int rows = tap_stats_rows(B, T, C);
-  return (size_t)((T + rows - 1) / rows) * B * C * 2;
+  return (size_t)tap_stats_slabs(B, T, C) * B * C * 2;
 }
 
 extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, int T, int C, float* scratch, size_t scratch_floats,
@@ -351,12 +380,10 @@ extern "C" int mst_tap_stats(const mst_bf16* x, float* mean, float* var, int B, 
   if (C % 64 || 256 % (C / 8) != 0 || C > 2048) return MST_ERR_UNSUPPORTED;  // C/8 chunks per row must tile the 256 threads
   if (scratch_floats < mst_tap_stats_scratch_floats(B, T, C)) return MST_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rows = tap_stats_rows(B, T, C);
-  const int slabs = (T + rows - 1) / rows;
+  const int slabs = tap_stats_slabs(B, T, C);
   dim3 grid((unsigned)slabs, (unsigned)B, 1);
-  const size_t red_bytes = (size_t)2 * (256 / (C / 8)) * (C + 1) * sizeof(float);
-  tap_stats_kernel<<<grid, 256, red_bytes, st>>>(reinterpret_cast<const bf16*>(x), scratch, T, C, rows, B * C);
-  tap_stats_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, mean, var, B, T, C, slabs);
+  tap_stats_kernel<<<grid, 256, tap_stats_smem(C), st>>>(reinterpret_cast<const bf16*>(x), scratch, T, C, slabs, B * C);
+  tap_stats_finalize_kernel<<<(B * C + 31) / 32, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), scratch, mean, var, B, T, C, slabs);
   return (int)cudaGetLastError();
 }
 
