@@ -434,14 +434,19 @@ static int launch_band(const MstGemm& g, cudaStream_t st) {
 //   warps 8-14  producers  : one padded input row per ring slot with cp.async (reflect / zero padding and the
 //                            nearest-x2 upsample folded into the source address), asynchronous mbarrier arrival
 //   warp  15    MMA issuer : output row y = 9 taps x Cin/16 k-steps x W/128 strips of tcgen05.mma reading ring
-//                            rows y-1, y, y+1 through shifted SWIZZLE_NONE descriptors; accumulators rotate
+//                            rows y-1, y, y+1 through ROW-SHIFTED swizzled descriptors; accumulators rotate
 //                            through NACC TMEM buffers
 //
 // The whole [N x 9 Cin] weight matrix stays resident in shared memory (fetched once per CTA).  Each CTA owns a
 // contiguous run of output rows (over all images), so every input row is fetched from L2/HBM once per CTA that
 // needs it (3 extra rows per run) and each strip is exactly one 128-pixel half/whole row: no padded-raster waste.
-// Ring layout: plane c (16-byte channel chunk) x [slot][padded pixel] x 16 B -- for one chunk, 8 consecutive
-// pixels are one 128-byte core matrix (SBO = 128 B), the next chunk is LBO = plane bytes further.
+// Ring layout: a slot is one padded row, pixel-major, one pixel = one K-major operand row of Cin * 2 bytes (64 B ->
+// SWIZZLE_64B, 128 B -> SWIZZLE_128B), the 16-byte chunks swizzled by the address bits above them; slot pitch = a whole
+// number of 8-row swizzle atoms.  Tap (ky, kx) of a strip is the SAME bytes read through a descriptor whose start is
+// moved by kx rows: the swizzle is a function of the absolute shared-memory address (tools/micro/umma_rowshift.cu
+// checks every shift 0..9 on the device), so a start that is not atom-aligned is fine, base-offset field 0.  The
+// earlier SWIZZLE_NONE layout (planes of 16-byte chunks, pixel shift = 16 B) made two of three taps read core
+// matrices that straddle 128-byte lines: ~58 clk per MMA whatever N.
 constexpr int RS_EPI_WARPS = 8;
 constexpr int RS_PROD_WARPS = 7;
 constexpr int RS_MMA_WARPS = 1;
@@ -455,7 +460,7 @@ struct RowsGeom {
   int tmem_cols;    // allocated TMEM columns (power of two >= nacc * spr * BN)
   int rows_total;   // B * H output rows
   int rows_per_cta;
-  int plane_bytes;  // ring * (W + 2) * 16
+  int row_pitch;    // bytes per ring slot: (W + 2) pixels rounded up to whole 8-pixel swizzle atoms
   int mode;         // experiment switch (MST_ROWS_MODE)
 };
 
@@ -537,7 +542,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
       else valid = valid && (unsigned)xx < (unsigned)p.W;
       if (p.upsample) xx >>= 1;
       src_off[k] = valid ? xx * CIN + c * 8 : -1;
-      dst_off[k] = (uint32_t)c * (uint32_t)g.plane_bytes + (uint32_t)col * 16u;
+      // pixel-major, chunk index XOR the address bits 7.. of the pixel row (CIN 64: col & 7; CIN 32: (col >> 1) & 3)
+      const int sw = CIN == 64 ? (col & 7) : ((col >> 1) & 3);
+      dst_off[k] = (uint32_t)col * (uint32_t)(CIN * 2) + (uint32_t)((c ^ sw) << 4);
     }
     const int nk = (row_chunks - t + NPROD - 1) / NPROD;  // copies this thread makes per row
     int slot = 0;
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
         long long tp0 = prof ? clock64() : 0;
         mbar_wait(smem_u32(&free_bar[slot]), fphase);
         if (prof) t_wait += clock64() - tp0;
-        const uint32_t rowdst = ring_base + (uint32_t)(slot * Wp) * 16u;
+        const uint32_t rowdst = ring_base + (uint32_t)slot * (uint32_t)g.row_pitch;
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
           if (k < nk) {
@@ -581,13 +588,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     // `if (lane == 0)` branch instead costs ~15 instructions (register -> uniform-register broadcasts in an elect
     // loop) per MMA, more than these small (N <= 64) MMAs take to execute.
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-    const uint32_t lbo16 = (uint32_t)g.plane_bytes >> 4;
-    constexpr uint32_t a_hi = (128u >> 4) | (1u << 14);                // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
+    constexpr uint32_t PIX16 = CIN * 2 / 16;                           // one pixel (operand row) in address-field units
+    constexpr uint32_t a_hi = ((8u * CIN * 2u) >> 4) | (1u << 14) | ((CIN == 64 ? 2u : 4u) << 29);  // SBO = 8 pixels, version 1, SWIZZLE_128B / _64B
     constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
     const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t row16 = (uint32_t)Wp;                               // one ring row in address-field units (16 B)
-    const uint32_t a_lo_base = ((ring_base & 0x3FFFFu) >> 4) | (lbo16 << 16);
+    const uint32_t row16 = (uint32_t)g.row_pitch >> 4;                 // one ring slot in address-field units (16 B)
+    const uint32_t a_lo_base = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
     mbar_wait(smem_u32(&w_bar), 0);
+    const bool prof = (g.mode & 8) != 0;
+    long long t_full = 0, t_acc = 0, t_all = prof ? clock64() : 0;
     int rcount = 0;                 // output rows issued
     int y = r_begin % p.H;
     int s_new = 0;                  // ring slot of the next padded row to arrive
@@ -597,12 +606,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     uint32_t acc_phase = 1;         // a fresh acc_empty passes a wait on parity 1
     for (int r = r_begin; r < r_end; ++r, ++rcount) {
       const int nload = (r == r_begin || y == 0) ? 3 : 1;
+      long long tm0 = prof ? clock64() : 0;
       for (int j = 0; j < nload; ++j) {
         mbar_wait(smem_u32(&full_bar[s_new]), full_phase);
         s0 = s1; s1 = s2; s2 = s_new;
         if (++s_new == g.ring) { s_new = 0; full_phase ^= 1; }
       }
+      long long tm1 = prof ? clock64() : 0;
       mbar_wait(smem_u32(&acc_empty[buf]), acc_phase);
+      if (prof) { t_full += tm1 - tm0; t_acc += clock64() - tm1; }
       fence_proxy_async_smem();
       tc_fence_after();
       if (++y == p.H) y = 0;
@@ -615,8 +627,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
         for (int ks = 0; ks < TOTAL_KS; ++ks) {
           const int tap = ks / KPT, kk = ks - tap * KPT;
           const int ky = tap / 3, kx = tap - ky * 3;
-          // +1 in the address field = 16 bytes = one pixel; a K=16 step further = two channel-chunk planes
-          const uint32_t a_lo = (ky == 0 ? a_row0 : (ky == 1 ? a_row1 : a_row2)) + (uint32_t)(st * 128 + kx) + (uint32_t)(kk * 2) * lbo16;
+          // a pixel further = one operand row (PIX16 address units); a K=16 step = 32 bytes inside the swizzled row
+          const uint32_t a_lo = (ky == 0 ? a_row0 : (ky == 1 ? a_row1 : a_row2)) + (uint32_t)(st * 128 + kx) * PIX16 + (uint32_t)(kk * 2);
           const uint32_t b_lo = b_lo0 + (uint32_t)(((ks >> 2) * B_STAGE_BYTES + (ks & 3) * 32) >> 4);
           umma_bf16_pred(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, ks != 0);
         }
@@ -629,6 +641,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
       }
       if (++buf == g.nacc) { buf = 0; acc_phase ^= 1; }
     }
+    if (prof && blockIdx.x == 1 && lane == 0) printf("rows prof mma: total %lld wait_full %lld wait_acc_empty %lld\n", clock64() - t_all, t_full, t_acc);
     tc_fence_before();
   } else {
     // =========================== epilogue (warps 0-7) ===========================
@@ -734,7 +747,7 @@ static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
   const int nkb = (9 * g.Cin + 63) / 64;
   if (g.k_pad != nkb * 64) return false;
   const long long budget = 220LL * 1024 - 1024 - (long long)nkb * BN * 128;
-  const long long row_bytes = (long long)(g.W + 2) * g.Cin * 2;
+  const long long row_bytes = (long long)((g.W + 2 + 7) / 8 * 8) * g.Cin * 2;
   long long ring = budget / row_bytes;
   if (ring > 12) ring = 12;
   if (ring < 4) return false;
@@ -749,9 +762,8 @@ static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
   int cols = 32;
   while (cols < nacc * acc_cols) cols <<= 1;
   out.tmem_cols = cols;
-  out.plane_bytes = out.ring * (g.W + 2) * 16;
+  out.row_pitch = (int)row_bytes;
   { const char* e = getenv("MST_ROWS_MODE"); out.mode = e ? atoi(e) : 0; }
-  if (out.plane_bytes >= (1 << 18)) return false;
   const int B = g.M / (g.H * g.W);
   out.rows_total = B * g.H;
   const int sms = cb_num_sms();
@@ -763,7 +775,7 @@ static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
 
 template <int BN, int CIN>
 static int launch_rows(const MstGemm& g, const RowsGeom& geo, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)((9 * CIN + 63) / 64) * BN * 128 + (size_t)geo.ring * (g.W + 2) * CIN * 2;
+  const size_t smem = 1024 + (size_t)((9 * CIN + 63) / 64) * BN * 128 + (size_t)geo.ring * geo.row_pitch;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mastermetastyletransfer_b200 import ops
-for (B, H, Cin, Cout, up) in [(32, 256, 32, 32, True), (32, 128, 64, 64, True), (96, 256, 64, 64, False)]:
+for (B, H, Cin, Cout, up) in [(32, 256, 32, 32, True), (32, 256, 32, 16, False), (32, 128, 64, 64, False), (32, 128, 64, 32, False)]:
     hs = H // 2 if up else H
     x = torch.randn(B, hs, hs, Cin, device="cuda").bfloat16()
     pm = ops.pack_conv3x3(torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5, torch.randn(Cout, device="cuda"))
