@@ -18,7 +18,10 @@
 // TMEM: fc1 accumulator double buffered (2 x 128 columns) + fc2 accumulator (C columns) <= 512 columns.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace mst {
 
@@ -35,6 +38,12 @@ MST_DEVINL void ml_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint3
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// [32 fp32 columns x 32 rows] box of the output matrix, shared memory -> global (bulk async-group completion)
+MST_DEVINL void ml_tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+MST_DEVINL void ml_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+MST_DEVINL void ml_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 MST_DEVINL void ml_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -62,8 +71,17 @@ struct MlpCfg {
 // producer warps: C = 128 has a buffer of its own; C = 256 time-shares the X tile -- O(next tile) is loaded as soon as this
 // tile's last fc1 MMA has retired (so it arrives during the GELU / fc2 / output tail), and the projection epilogue overwrites it
 // with X only after BOTH projection chunks have finished reading it.
+//
+// Output (PRE, fp32): a lane owns a row, so direct stores touch 32 different 128-byte lines per instruction (a quarter of the
+// LSU's width; the 2048 / 4096 wavefronts per tile were the bulk of the tile-end phase and delayed the next tile's residual
+// loads behind them).  With tma_out each warp writes its [32 rows x 32 columns] block into a private 4 KB slab of the Hs
+// buffers (idle between the tile's last fc2 MMA and the next tile's first GELU), 128B-swizzled, and one lane hands it to the
+// TMA engine as a tensor store; rows past M are clipped by the tensor map.  The slab is reused only after
+// cp.async.bulk.wait_group.read, and every warp waits for its own stores before it arrives on x_full, which orders all of
+// them before the first GELU write of the next tile (x_full -> fc1 MMA -> acc1_full).
 template <int C, bool PRE>
-__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles) {
+__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles,
+                                                                  const __grid_constant__ CUtensorMap tm_out, const int tma_out) {
   using Cfg = MlpCfg<C>;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int ABUF = PRE ? 1 : Cfg::ABUF;
@@ -436,7 +454,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&x_full));
+        if (lane == 0) {
+          if (tma_out) ml_bulk_wait_read();  // the previous tile's output slab has been read: the Hs buffers may be written again
+          mbar_arrive(smem_u32(&x_full));
+        }
         PROF_MARK(tA)
       }
       for (int j = 0; j < NCH; ++j) {
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&acc2_empty));
         }
-        if (!row_ok) continue;
+        if (!row_ok && !(PRE && tma_out)) continue;  // (tensor store: whole warp takes part, rows past M are clipped by the map)
         const int n = part * CPW + col0;
         float x[32];
 #pragma unroll
@@ -517,7 +538,24 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
             }
           }
         }
-        if (p.out_f32) {
+        if (PRE && tma_out) {
+          const uint32_t slab = hs_base + (uint32_t)warp * 4096u;
+          if (col0 > 0) {  // the slab still holds the previous 32 columns until the TMA engine has read them
+            if (lane == 0) ml_bulk_wait_read();
+            __syncwarp();
+          }
+          const uint32_t srow = slab + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((uint32_t)(q ^ (lane & 7)) << 4)), "f"(x[4 * q]),
+                         "f"(x[4 * q + 1]), "f"(x[4 * q + 2]), "f"(x[4 * q + 3]) : "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ml_tma_store_2d(&tm_out, slab, n, tile * 128 + quad * 32);
+            ml_bulk_commit();
+          }
+        } else if (p.out_f32) {
           float* op = p.out_f32 + (long long)row * p.ld_out32 + n;
           if (wide_o32) {
 #pragma unroll
@@ -528,7 +566,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
             for (int e = 0; e < 8; ++e) o4[e] = make_float4(x[4 * e], x[4 * e + 1], x[4 * e + 2], x[4 * e + 3]);
           }
         }
-        if (p.out_bf16) {
+        if (p.out_bf16 && row_ok) {
           bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n;
           if (wide_o16) {
 #pragma unroll
@@ -558,6 +596,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       }
       PROF_MARK(tF)
     }
+    if (PRE && tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
 #ifdef MST_MLP_PROF
     if (blockIdx.x == 1 && lane == 0 && (warp == 0 || warp == 9))
       printf("   A detail: wait %lld tmem_ld %lld bias+res %lld st %lld\n", tAw, tAld, tAres, tAst);
@@ -628,6 +667,23 @@ static int ml_num_sms() {
   return sms;
 }
 
+typedef CUresult (*MlEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static MlEncodeTiledFn ml_tma_encoder() {
+  static MlEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("MST_MLP_TMA_OUT");  // 0: direct row-per-lane stores (experiments)
+    if (e && e[0] == '0') return nullptr;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<MlEncodeTiledFn>(q);
+  }
+  return fn;
+}
+
 template <int C, bool PRE>
 static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   using Cfg = MlpCfg<C>;
@@ -639,7 +695,20 @@ static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   }
   const int tiles = (p.M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < ml_num_sms() ? tiles : ml_num_sms());
-  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int tma_out = 0;
+  if (PRE && p.out_f32) {  // fp32 output as a [C, M] tensor, box = 32 columns (128 B) x 32 rows, 128B swizzle
+    if (MlEncodeTiledFn enc = ml_tma_encoder()) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)p.M};
+      const cuuint64_t gstride[1] = {(cuuint64_t)p.ld_out32 * 4};
+      const cuuint32_t box[2] = {32, 32};
+      const cuuint32_t estr[2] = {1, 1};
+      tma_out = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.out_f32, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
+  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles, tmap, tma_out);
   return (int)cudaGetLastError();
 }
 
