@@ -103,6 +103,8 @@ SYMBOLS = {
     "mst_conv3x3_band_supported": (_I, [_I, _I, _I, _I]),
     "mst_conv3x3_rows": (_I, [C.POINTER(MstGemm), _P]),
     "mst_conv3x3_rows_supported": (_I, [_I, _I, _I, _I]),
+    "mst_conv3x3_cm": (_I, [C.POINTER(MstGemm), _P]),
+    "mst_conv3x3_cm_supported": (_I, [_I, _I, _I, _I]),
     "mst_mlp_stream_bytes": (_Z, [_I]),
     "mst_pack_mlp_weights": (_I, [_P, _P, _P, _I, _P]),
     "mst_mlp_stream_bytes_pre": (_Z, [_I]),

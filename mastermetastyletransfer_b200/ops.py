@@ -53,7 +53,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 
 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
-             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
+             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_conv3x3_cm": "conv_cm_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_resize_crop_normalize": "resize_crop_normalize_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -185,7 +185,10 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
         training_ext = training_ext or bool(g.conv_full)
     desc = f"M={M} N={N} K={pm.K} conv={conv is not None} act={act} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None}"
     flops = 2.0 * M * min(N, pm.N) * pm.K
-    if conv is not None and not training_ext and _use_rows(conv, N):
+    plain16 = out_f32 is None and res is None and mul is None and out_bf16 is not None
+    if conv is not None and not training_ext and plain16 and _use_cm(conv, N, act):
+        _launch("mst_conv3x3_cm", lambda: _lib.lib().mst_conv3x3_cm(C.byref(g), _stream()), flops=flops, desc=desc + " cm")
+    elif conv is not None and not training_ext and _use_rows(conv, N):
         _launch("mst_conv3x3_rows", lambda: _lib.lib().mst_conv3x3_rows(C.byref(g), _stream()), flops=flops, desc=desc + " rows")
     elif conv is not None and not training_ext and _use_band(conv, N):
         _launch("mst_conv3x3_band", lambda: _lib.lib().mst_conv3x3_band(C.byref(g), _stream()), flops=flops, desc=desc + " band")
@@ -202,6 +205,22 @@ def band_supported(n: int, cin: int, H: int, W: int) -> bool:
 
 def rows_supported(n: int, cin: int, H: int, W: int) -> bool:
     return bool(_lib.lib().mst_conv3x3_rows_supported(n_pad_of(n), cin, H, W))
+
+
+def cm_supported(n: int, cin: int, H: int, W: int) -> bool:
+    return bool(_lib.lib().mst_conv3x3_cm_supported(n_pad_of(n), cin, H, W))
+
+
+def _use_cm(conv: dict, n_pad: int, act: int) -> bool:
+    """The channel-major kernel for the wide layers (conv_cm.cu): 'auto' takes it whenever the shape fits."""
+    impl = conv.get("impl", "auto")
+    if impl not in ("auto", "cm"):
+        return False
+    ok = (not conv.get("upsample", False) and not conv.get("out_nchw", False) and act in (ACT_NONE, ACT_RELU)
+          and bool(_lib.lib().mst_conv3x3_cm_supported(n_pad, conv["Cin"], conv["H"], conv["W"])))
+    if impl == "cm" and not ok:
+        raise ValueError("conv3x3 channel-major kernel does not support this shape")
+    return ok
 
 
 def _use_rows(conv: dict, n_pad: int) -> bool:

@@ -103,6 +103,40 @@ def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
     assert torch.allclose(out.cpu(), ref, atol=3e-3, rtol=3e-3), (out.cpu() - ref).abs().max()
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,pad,relu", [
+    (2, 64, 64, 128, 128, "reflect", True),    # decoder.py:29-35 at 64x64
+    (3, 32, 32, 256, 128, "reflect", True),    # decoder.py:25: two channel slices, 8 rows per unit
+    (1, 128, 128, 64, 128, "zeros", True),     # VGG conv2_1: one 64-channel plane, 2 rows per unit
+    (2, 128, 128, 128, 128, "zeros", False),   # VGG conv2_2 shape, no activation: 64-channel slices because W > 64
+    (2, 64, 64, 256, 256, "zeros", True),      # VGG conv3_x: two output-channel tiles out of a 256-wide packed weight
+    (5, 64, 64, 512, 512, "zeros", True),      # four slices, four channel tiles, units not a multiple of the SM count
+    (1, 8, 64, 64, 128, "reflect", False), (7, 16, 64, 128, 384, "zeros", True)])
+def test_conv3x3_channel_major(B, H, W, Cin, Cout, pad, relu):
+    """conv_cm.cu (output channels = MMA M, one image row = MMA N, row-shifted taps) vs F.conv2d on the bf16-rounded operands;
+    'auto' must pick it for these shapes, and its result must equal the gathered implicit GEMM's to bf16 rounding."""
+    ops = _ops()
+    assert ops.cm_supported(Cout, Cin, H, W)
+    x = _rand(B, H, W, Cin, seed=20).bfloat16()
+    wt = _rand(Cout, Cin, 3, 3, seed=21, scale=(9 * Cin) ** -0.5)
+    bias = _rand(Cout, seed=22)
+    pm = ops.pack_conv3x3(wt.cuda(), bias.cuda())
+    conv = dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT if pad == "reflect" else ops.PAD_ZERO)
+    act = ops.ACT_RELU if relu else ops.ACT_NONE
+    outs = {}
+    for impl in ("cm", "auto", "gather"):
+        out = torch.full((B * H * W, pm.n_pad), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(x.cuda(), pm, B * H * W, act=act, out_bf16=out, conv=dict(conv, impl=impl))
+        outs[impl] = out.float().cpu()[:, :Cout]
+    xi = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect" if pad == "reflect" else "constant")
+    ref = F.conv2d(xi, wt.bfloat16().float(), bias)
+    if relu:
+        ref = torch.relu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    assert torch.equal(outs["cm"], outs["auto"])
+    assert torch.allclose(outs["cm"], ref, atol=1e-2, rtol=1e-2), (outs["cm"] - ref).abs().max()
+    assert torch.allclose(outs["cm"], outs["gather"], atol=1e-2, rtol=1e-2)
+
+
 @pytest.mark.parametrize("impl", ["gather", "band", "rows"])
 def test_conv3x3_nchw_out(impl):
     ops = _ops()
