@@ -464,13 +464,23 @@ struct RowsGeom {
   int mode;         // experiment switch (MST_ROWS_MODE)
 };
 
-template <int BN, int CIN>
+// G > 1: BANDED weights.  One MMA group produces G consecutive output rows of a strip: N = G * BN accumulator columns
+// (column dy * BN + co = output row y + dy, channel co), K runs over the G + 2 input rows the group touches
+// (k = ((j * 3 + kx) * CIN + c), j = input row y - 1 + j), and the B operand is the weight matrix laid out as a band:
+// B[dy * BN + co][j, kx, c] = W[co][ky = j - dy][kx][c] for 0 <= j - dy <= 2, zero elsewhere.  Two thirds (G = 2) or half
+// (G = 4) of the MACs multiply zeros -- but the thin layers are bound by the shared-memory read of the PIXEL operand (4 KB per
+// MMA whatever N), and a banded MMA reads each staged pixel row once for all G output rows: (G + 2) * 3 * CIN / 16 MMAs per G
+// rows instead of 9 * CIN / 16 per row.  The band is built once per CTA in shared memory from the ordinary packed weights.
+template <int BN, int CIN, int G>
 __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore p, const RowsGeom g) {
   constexpr int CPP = CIN / 8;    // 16-byte chunks per pixel
   constexpr int KPT = CIN / 16;   // K=16 steps per tap
-  constexpr int TOTAL_KS = 9 * KPT;
-  constexpr int NKB = (9 * CIN + 63) / 64;
-  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int NB = G * BN;      // MMA N: G output rows x BN channels
+  constexpr int JR = G + 2;       // input rows per group
+  constexpr int TOTAL_KS = JR * 3 * KPT;
+  constexpr int NKB = (JR * 3 * CIN + 63) / 64;
+  constexpr int NKB_SRC = (9 * CIN + 63) / 64;  // k-blocks of the packed (un-banded) weights
+  constexpr int B_STAGE_BYTES = NB * 128;
   constexpr int CH = BN >= 32 ? 32 : 16;  // columns per tcgen05.ld
   constexpr int NCC = BN / CH;
   extern __shared__ uint8_t smem_raw[];
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
       mbar_init(smem_u32(&acc_full[b]), RS_MMA_WARPS);
       mbar_init(smem_u32(&acc_empty[b]), RS_EPI_WARPS);
     }
-    mbar_init(smem_u32(&w_bar), 1);
+    mbar_init(smem_u32(&w_bar), G == 1 ? 1 : RS_PROD_WARPS * 32);
     mbar_fence_init();
   }
   if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
@@ -510,16 +520,39 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const int acc_cols = g.spr * BN;
+  const int acc_cols = g.spr * NB;
 
   if (warp >= RS_EPI_WARPS && warp < RS_EPI_WARPS + RS_PROD_WARPS) {
     // =========================== producers ===========================
     const int t = threadIdx.x - RS_EPI_WARPS * 32;
-    if (t == 0) {  // resident weights, once
-      cb_arrive_expect_tx(smem_u32(&w_bar), NKB * B_STAGE_BYTES);
+    if constexpr (G == 1) {
+      if (t == 0) {  // resident weights, once
+        cb_arrive_expect_tx(smem_u32(&w_bar), NKB * B_STAGE_BYTES);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wt);
+        for (int kb = 0; kb < NKB; ++kb)
+          cb_bulk_g2s(w_base + kb * B_STAGE_BYTES, wsrc + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&w_bar));
+      }
+    } else {
+      // the band, 16 bytes (8 input channels) at a time: destination row n = dy * BN + co, K chunk (j, kx, c8)
+      uint8_t* gen = smem_raw + (w_base - smem_u32(smem_raw));
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.Wt);
-      for (int kb = 0; kb < NKB; ++kb)
-        cb_bulk_g2s(w_base + kb * B_STAGE_BYTES, wsrc + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, smem_u32(&w_bar));
+      constexpr int KCH = NKB * 8;  // 16-byte K chunks per destination row (incl. the zero tail of the last k-block)
+      for (int i = t; i < NB * KCH; i += RS_PROD_WARPS * 32) {
+        const int n = i / KCH, kc = i - n * KCH;
+        const int dy = n / BN, co = n - dy * BN;
+        const int kel = kc * 8;                      // first K element of the chunk
+        const int jk = kel / CIN, c = kel - jk * CIN;  // jk = j * 3 + kx
+        const int j = jk / 3, kx = jk - j * 3;
+        const int ky = j - dy;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (jk < JR * 3 && ky >= 0 && ky <= 2) {
+          const int ksrc = (ky * 3 + kx) * CIN + c;
+          v = *reinterpret_cast<const uint4*>(wsrc + (size_t)(ksrc >> 6) * (BN * 128) + sw128_offset(co, (ksrc & 63) >> 3));
+        }
+        *reinterpret_cast<uint4*>(gen + (size_t)(kc >> 3) * B_STAGE_BYTES + sw128_offset(n, kc & 7)) = v;
+      }
+      fence_proxy_async_smem();  // generic-proxy stores, read by the tensor core through the async proxy
+      mbar_arrive(smem_u32(&w_bar));
     }
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const int Hs = p.upsample ? (p.H >> 1) : p.H;
@@ -553,9 +586,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     uint32_t fphase = 1;  // a fresh free_bar passes a wait on parity 1
     int b = r_begin / p.H;
     int y = r_begin - b * p.H;
-    for (int r = r_begin; r < r_end; ++r) {
-      const int nload = (r == r_begin || y == 0) ? 3 : 1;
-      for (int j = 3 - nload; j < 3; ++j) {
+    for (int r = r_begin; r < r_end; r += G) {
+      const int nload = (r == r_begin || y == 0) ? JR : G;
+      for (int j = JR - nload; j < JR; ++j) {
         int yy = y + j - 1;  // padded row -1 .. H
         bool vrow = true;
         if (p.pad_mode == 1) yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
@@ -576,7 +609,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
         cp_async_mbar_arrive_noinc(smem_u32(&full_bar[slot]));
         if (++slot == g.ring) { slot = 0; fphase ^= 1; }
       }
-      if (++y == p.H) { y = 0; ++b; }
+      y += G;
+      if (y == p.H) { y = 0; ++b; }
     }
     cp_async_wait_all();
     if (prof && blockIdx.x == 1 && t == 0) printf("rows prof producer: total %lld wait_free %lld rows %d\n", clock64() - t_all, t_wait, r_end - r_begin);
@@ -587,7 +621,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     // registers and emits back-to-back UTCHMMA with one uniform add in between -- issuing from inside an
     // `if (lane == 0)` branch instead costs ~15 instructions (register -> uniform-register broadcasts in an elect
     // loop) per MMA, more than these small (N <= 64) MMAs take to execute.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NB);
     constexpr uint32_t PIX16 = CIN * 2 / 16;                           // one pixel (operand row) in address-field units
     constexpr uint32_t a_hi = ((8u * CIN * 2u) >> 4) | (1u << 14) | ((CIN == 64 ? 2u : 4u) << 29);  // SBO = 8 pixels, version 1, SWIZZLE_128B / _64B
     constexpr uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
@@ -597,19 +631,23 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     mbar_wait(smem_u32(&w_bar), 0);
     const bool prof = (g.mode & 8) != 0;
     long long t_full = 0, t_acc = 0, t_all = prof ? clock64() : 0;
-    int rcount = 0;                 // output rows issued
+    int rcount = 0;                 // row groups issued
     int y = r_begin % p.H;
     int s_new = 0;                  // ring slot of the next padded row to arrive
     uint32_t full_phase = 0;
-    int s0 = 0, s1 = 0, s2 = 0;     // ring slots of padded rows y-1, y, y+1
+    int sl[JR];                     // ring slots of padded rows y-1 .. y+G
+#pragma unroll
+    for (int j = 0; j < JR; ++j) sl[j] = 0;
     int buf = 0;
     uint32_t acc_phase = 1;         // a fresh acc_empty passes a wait on parity 1
-    for (int r = r_begin; r < r_end; ++r, ++rcount) {
-      const int nload = (r == r_begin || y == 0) ? 3 : 1;
+    for (int r = r_begin; r < r_end; r += G, ++rcount) {
+      const int nload = (r == r_begin || y == 0) ? JR : G;
       long long tm0 = prof ? clock64() : 0;
       for (int j = 0; j < nload; ++j) {
         mbar_wait(smem_u32(&full_bar[s_new]), full_phase);
-        s0 = s1; s1 = s2; s2 = s_new;
+#pragma unroll
+        for (int q = 0; q + 1 < JR; ++q) sl[q] = sl[q + 1];
+        sl[JR - 1] = s_new;
         if (++s_new == g.ring) { s_new = 0; full_phase ^= 1; }
       }
       long long tm1 = prof ? clock64() : 0;
@@ -617,27 +655,31 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
       if (prof) { t_full += tm1 - tm0; t_acc += clock64() - tm1; }
       fence_proxy_async_smem();
       tc_fence_after();
-      if (++y == p.H) y = 0;
-      const bool last_of_run = (r + 1 == r_end || y == 0);
-      const uint32_t a_row0 = a_lo_base + (uint32_t)s0 * row16, a_row1 = a_lo_base + (uint32_t)s1 * row16,
-                     a_row2 = a_lo_base + (uint32_t)s2 * row16;
+      y += G;
+      if (y == p.H) y = 0;
+      const bool last_of_run = (r + G >= r_end || y == 0);
+      uint32_t a_row[JR];
+#pragma unroll
+      for (int j = 0; j < JR; ++j) a_row[j] = a_lo_base + (uint32_t)sl[j] * row16;
       for (int st = 0; st < g.spr; ++st) {
-        const uint32_t d_tmem = tmem_base + buf * acc_cols + st * BN;
+        const uint32_t d_tmem = tmem_base + buf * acc_cols + st * NB;
 #pragma unroll
         for (int ks = 0; ks < TOTAL_KS; ++ks) {
           const int tap = ks / KPT, kk = ks - tap * KPT;
-          const int ky = tap / 3, kx = tap - ky * 3;
+          const int j = tap / 3, kx = tap - j * 3;
           // a pixel further = one operand row (PIX16 address units); a K=16 step = 32 bytes inside the swizzled row
-          const uint32_t a_lo = (ky == 0 ? a_row0 : (ky == 1 ? a_row1 : a_row2)) + (uint32_t)(st * 128 + kx) * PIX16 + (uint32_t)(kk * 2);
+          const uint32_t a_lo = a_row[j] + (uint32_t)(st * 128 + kx) * PIX16 + (uint32_t)(kk * 2);
           const uint32_t b_lo = b_lo0 + (uint32_t)(((ks >> 2) * B_STAGE_BYTES + (ks & 3) * 32) >> 4);
           umma_bf16_pred(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc, ks != 0);
         }
       }
       umma_commit_pred(smem_u32(&acc_full[buf]));
-      umma_commit_pred(smem_u32(&free_bar[s0]));  // padded row y-1 is not needed again
-      if (last_of_run) {                           // last row of an image / of this CTA's run: rows y and y+1 die too
-        umma_commit_pred(smem_u32(&free_bar[s1]));
-        umma_commit_pred(smem_u32(&free_bar[s2]));
+      // padded rows y-1 .. y+G-2 are not needed again; at the end of an image / of this CTA's run the last two die as well
+#pragma unroll
+      for (int j = 0; j < G; ++j) umma_commit_pred(smem_u32(&free_bar[sl[j]]));
+      if (last_of_run) {
+        umma_commit_pred(smem_u32(&free_bar[sl[G]]));
+        umma_commit_pred(smem_u32(&free_bar[sl[G + 1]]));
       }
       if (++buf == g.nacc) { buf = 0; acc_phase ^= 1; }
     }
@@ -648,11 +690,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
     const int quad = warp & 3, half = warp >> 2;
     const bool prof = (g.mode & 8) != 0;
     long long t_wait = 0, t_all = prof ? clock64() : 0;
-    const int items = g.spr * NCC;
+    const int items = g.spr * G * NCC;  // (strip, output row of the group, column chunk)
+    float bias_r[NCC == 1 ? CH : 1];    // one column chunk per row (BN <= 32): the bias lives in registers, not 32 LDS per item
+    if constexpr (NCC == 1) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) bias_r[j] = bias_s[j];
+    }
     const long long hw = (long long)p.H * p.W;
     const bool wide16 = p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
     int rcount = 0;
-    for (int r = r_begin; r < r_end; ++r, ++rcount) {
+    for (int r0 = r_begin; r0 < r_end; r0 += G, ++rcount) {
       const int buf = rcount % g.nacc;
       long long te0 = prof ? clock64() : 0;
       if (lane == 0) mbar_wait(smem_u32(&acc_full[buf]), ((uint32_t)(rcount / g.nacc)) & 1u);
@@ -668,9 +715,11 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
       }
 #pragma unroll 1
       for (int item = half; item < items; item += 2) {
-        const int st = item / NCC, cc = item - st * NCC;
+        const int st = item / (G * NCC), rem = item - st * (G * NCC);
+        const int dy = rem / NCC, cc = rem - dy * NCC;
+        const int r = r0 + dy;  // output row of this item
         uint32_t v[CH];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * acc_cols + st * BN + cc * CH;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * acc_cols + st * NB + dy * BN + cc * CH;
         if constexpr (CH == 32) tmem_ld32(taddr, v);
         else tmem_ld16(taddr, v);
         tmem_wait_ld();
@@ -684,7 +733,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
         float xv[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          xv[j] = __uint_as_float(v[j]) + bias_s[n + j];
+          xv[j] = __uint_as_float(v[j]) + (NCC == 1 ? bias_r[j] : bias_s[n + j]);
           if (p.act == MST_ACT_RELU) xv[j] = fmaxf(xv[j], 0.0f);
           else if (p.act == MST_ACT_GELU) xv[j] = gelu_erf(xv[j]);
         }
@@ -741,19 +790,35 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
   }
 }
 
+// Output rows per MMA group: as many as keep N = G * BN at 64 (the pixel operand's shared-memory read then serves G rows),
+// if the image height divides and the band + a ring of G + 3 rows fit.  MST_ROWS_BAND=0 turns banding off (experiments).
+static int rows_band(const MstGemm& g, int BN) {
+  static int allow = -1;
+  if (allow < 0) { const char* e = getenv("MST_ROWS_BAND"); allow = e ? atoi(e) : 1; }
+  if (!allow) return 1;
+  // measured (tools/rows_prof.py, bench detail): 32 -> 3(16) @256^2: G = 4 starves the ring (a 74 KB band leaves 8 slots for
+  // 6 live rows), G = 2 does not; 32 -> 32: G = 2 a little faster (76 -> 70 us); 64 -> 32 @128^2: slower (98 KB band, ring of 7)
+  int G = 1;
+  if (g.Cin == 32 && (BN == 32 || BN == 16)) G = 2;
+  if (G > 1 && g.H % G != 0) G = 1;
+  return G;
+}
+
 static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
   if (g.W % 128 != 0 || g.W > 512 || g.N != BN || BN > 64) return false;
   if (g.Cin != 32 && g.Cin != 64) return false;
-  const int nkb = (9 * g.Cin + 63) / 64;
-  if (g.k_pad != nkb * 64) return false;
-  const long long budget = 220LL * 1024 - 1024 - (long long)nkb * BN * 128;
+  const int nkb_src = (9 * g.Cin + 63) / 64;
+  if (g.k_pad != nkb_src * 64) return false;
+  const int G = rows_band(g, BN);
+  const int nkb = ((G + 2) * 3 * g.Cin + 63) / 64;
+  const long long budget = 220LL * 1024 - 1024 - (long long)nkb * G * BN * 128;
   const long long row_bytes = (long long)((g.W + 2 + 7) / 8 * 8) * g.Cin * 2;
   long long ring = budget / row_bytes;
   if (ring > 12) ring = 12;
-  if (ring < 4) return false;
+  if (ring < G + 3) return false;
   out.ring = (int)ring;
   out.spr = g.W / 128;
-  const int acc_cols = out.spr * BN;
+  const int acc_cols = out.spr * G * BN;
   if (acc_cols > 256) return false;
   int nacc = 256 / acc_cols;
   if (nacc > 4) nacc = 4;
@@ -770,22 +835,23 @@ static bool plan_rows(const MstGemm& g, int BN, RowsGeom& out) {
   out.rows_per_cta = (out.rows_total + sms - 1) / sms;
   const int min_rows = out.rows_total < 4 ? out.rows_total : 4;  // a run re-fetches 2 extra input rows: keep runs >= 4 rows
   if (out.rows_per_cta < min_rows) out.rows_per_cta = min_rows;
+  out.rows_per_cta = (out.rows_per_cta + G - 1) / G * G;  // runs are whole row groups (H % G == 0, so a group never straddles two images)
   return true;
 }
 
-template <int BN, int CIN>
+template <int BN, int CIN, int G>
 static int launch_rows(const MstGemm& g, const RowsGeom& geo, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)((9 * CIN + 63) / 64) * BN * 128 + (size_t)geo.ring * geo.row_pitch;
+  const size_t smem = 1024 + (size_t)(((G + 2) * 3 * CIN + 63) / 64) * G * BN * 128 + (size_t)geo.ring * geo.row_pitch;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<BN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<BN, CIN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)((geo.rows_total + geo.rows_per_cta - 1) / geo.rows_per_cta);
   GemmCore core;
   memcpy(&core, &g, sizeof(GemmCore));
-  conv_rows_kernel<BN, CIN><<<grid, RS_THREADS, smem, st>>>(core, geo);
+  conv_rows_kernel<BN, CIN, G><<<grid, RS_THREADS, smem, st>>>(core, geo);
   return (int)cudaGetLastError();
 }
 
@@ -795,10 +861,11 @@ static int try_launch_rows(const MstGemm& g, cudaStream_t st, bool& handled) {
   handled = true;
   const int bn = mst_gemm_tile_n(g.N);
   if (!plan_rows(g, bn, geo)) { handled = false; return 0; }
-  if (bn == 64 && g.Cin == 64) return launch_rows<64, 64>(g, geo, st);
-  if (bn == 32 && g.Cin == 64) return launch_rows<32, 64>(g, geo, st);
-  if (bn == 32 && g.Cin == 32) return launch_rows<32, 32>(g, geo, st);
-  if (bn == 16 && g.Cin == 32) return launch_rows<16, 32>(g, geo, st);
+  const int G = rows_band(g, bn);
+  if (bn == 64 && g.Cin == 64) return launch_rows<64, 64, 1>(g, geo, st);
+  if (bn == 32 && g.Cin == 64) return launch_rows<32, 64, 1>(g, geo, st);
+  if (bn == 32 && g.Cin == 32) return G == 2 ? launch_rows<32, 32, 2>(g, geo, st) : launch_rows<32, 32, 1>(g, geo, st);
+  if (bn == 16 && g.Cin == 32) return G == 2 ? launch_rows<16, 32, 2>(g, geo, st) : launch_rows<16, 32, 1>(g, geo, st);
   handled = false;
   return 0;
 }
