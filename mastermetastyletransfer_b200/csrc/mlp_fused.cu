@@ -213,32 +213,38 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
       }
       umma_commit_pred(smem_u32(&acc1_full[buf]));
     };
-    auto mma2 = [&](int j) {  // acc2 += Hs(j) . W2_j^T
+    auto mma2 = [&](int j) {  // acc2 += Hs(j) . W2_j^T, Hs(j) read from TENSOR MEMORY: it sits in the fc1 accumulator it came from
       const int gc = lt * NCH + j, buf = j & 1, u = gc >> 1;
+      const int abuf = (lt * CPT + NPRE + j) & 1;  // fc1 accumulator of chunk j
       mbar_wait(smem_u32(&hs_full[buf]), u & 1);
       if (j == 0) mbar_wait(smem_u32(&acc2_empty), (lt & 1) ^ 1);
       tc_fence_after();
-      const uint32_t hs = hs_base + buf * Cfg::HS_BYTES;
+      // K step k = hidden units 16k .. 16k+15 of the chunk = the eight packed columns (k & 1) * 8 of the 32-column block k >> 1
+      // (each GELU warp overwrites the first 16 of the 32 fp32 columns it has just read with its 32 fp16 results)
+      const uint32_t hs_t = tmem_base + abuf * ML_HC;
       for (int s = 0; s < Cfg::S2; ++s, ++ws) {
         int slot;
         wait_stage(slot);
         const uint32_t wb = ring_base + slot * ML_STAGE_BYTES;
         if constexpr (C == 256) {  // stage = k-block s of the chunk: [256 x 64]
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + s * 16384 + k * 32), umma_desc_sw128(wb + k * 32), idesc2,
-                           PRE || (j | s | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const int kk = s * 4 + k;
+            umma_ts_pred(tmem_base + Cfg::ACC2_COL, hs_t + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_sw128(wb + k * 32), idesc2,
+                         PRE || (j | s | k) != 0);
+          }
         } else {  // stage = both k-blocks: 2 x [128 x 64]
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_pred(tmem_base + Cfg::ACC2_COL, umma_desc_sw128(hs + kb * 16384 + k * 32), umma_desc_sw128(wb + kb * 16384 + k * 32),
-                             idesc2, PRE || (j | kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const int kk = kb * 4 + k;
+              umma_ts_pred(tmem_base + Cfg::ACC2_COL, hs_t + (kk >> 1) * 32 + (kk & 1) * 8, umma_desc_sw128(wb + kb * 16384 + k * 32),
+                           idesc2, PRE || (j | kb | k) != 0);
+            }
         }
         umma_commit_pred(smem_u32(&w_empty[slot]));
       }
-      umma_commit_pred(smem_u32(&hs_empty[buf]));
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt % ABUF, au = lt / ABUF;
@@ -472,9 +478,6 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + abuf * ML_HC + part * 32, v);
         tmem_wait_ld();
-        tc_fence_before();  // the fc1 accumulator can be overwritten by MMA1(j+2) once all sixteen warps have read it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&acc1_empty[abuf]));
         // fc1 bias straight from global (warp-uniform address, L1-resident): shared memory is fully committed to tiles
         const float4* bb = reinterpret_cast<const float4*>(p.b1 + j * ML_HC + part * 32);
         uint32_t h[16];  // GELU in packed fp16, two hidden units per instruction (common.cuh: gelu_erf_h2): the phase is issue-bound
@@ -485,13 +488,16 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           h[2 * e + 1] = gelu_erf_h2(__uint_as_float(v[4 * e + 2]) + b4.z, __uint_as_float(v[4 * e + 3]) + b4.w);
         }
         PROF_MARK(tG)
-        if (lane == 0) mbar_wait(smem_u32(&hs_empty[buf]), (u & 1) ^ 1);  // MMA2(j-2) has finished reading this buffer
+        // the fp16 hidden activation goes back into TENSOR MEMORY, over the first 16 of the 32 accumulator columns this warp has
+        // just read: it is the A operand of the second GEMM from there (no shared-memory store, no shared-memory operand read)
+        tmem_st16(tmem_base + ((uint32_t)(quad * 32) << 16) + abuf * ML_HC + part * 32, h);
+        tmem_wait_st();
+        tc_fence_before();
         __syncwarp();
-        PROF_MARK(tHw)
-        store_tile32_packed(hs_base + buf * Cfg::HS_BYTES, part * 32, h);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&hs_full[buf]));
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&acc1_empty[abuf]));  // (fc1 of chunk j+2 is issued after fc2 of chunk j: it cannot overtake the read of Hs)
+          mbar_arrive(smem_u32(&hs_full[buf]));
+        }
         PROF_MARK(tG)
       }
       // ---- tile end: fc2 accumulator -> + b2 + residual -> global ----
