@@ -156,6 +156,18 @@ MST_DEVINL void umma_ts_pred(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, 
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One [128 rows x 32 bytes] K step of a swizzled K-major shared-memory tile (same descriptor as the MMA's) -> 8 TMEM columns.
+// Copies and MMAs issued by one thread execute in issue order.
+MST_DEVINL void tmem_cp_128x256b_pred(uint32_t taddr, uint64_t s_desc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.cp.cta_group::1.128x256b [%0], %1;\n"
+      "}\n" ::"r"(taddr),
+      "l"(s_desc)
+      : "memory");
+}
 MST_DEVINL void umma_commit_pred(uint32_t bar) {
   asm volatile(
       "{\n"

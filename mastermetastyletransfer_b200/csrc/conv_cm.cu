@@ -13,17 +13,27 @@
 //   * tap (ky, kx) is the staged row y + ky - 1 read through a descriptor whose start is moved by kx pixels (the swizzle is a
 //     function of the absolute shared-memory address: tools/micro/umma_rowshift.cu) -- no im2col, every input row of a unit is
 //     fetched once and used by three output rows x three taps;
-//   * a unit = R = 256 / W output rows x 128 output channels = 256 accumulator columns in TMEM, double buffered; one weight
-//     k-block (16 KB) streamed from L2 feeds 4 R MMAs, so the weights are fetched once per 256 pixels instead of once per 128.
-// L2 -> SM traffic per 256 pixels of a 128 -> 128 layer: 288 KB of weights + 110 KB of rows instead of 1152 KB.
+//   * a unit = R = 256 / W output rows x 128 output channels = 256 accumulator columns in TMEM; one weight k-block (16 KB)
+//     streamed from L2 feeds 4 R MMAs, so the weights are fetched once per 256 pixels instead of once per 128;
+//   * the weight k-block is the MMA's A operand and is reused by R instructions per K step.  Read from shared memory it costs
+//     4 KB of shared-memory bandwidth per instruction (6 KB per N = 64 MMA = 48 clk for 32 clk of math: measured 54).  So each
+//     k-block is copied ONCE into tensor memory (tcgen05.cp 128x256b, 32 columns per k-block, eight k-blocks in flight) and
+//     the MMAs take A from TMEM; the shared-memory stage returns to the streamer as soon as the copy has read it;
+//   * with A out of the way a single issuing warp is the limit (~7 uniform-datapath instructions per MMA at ~7 clk each for
+//     a lone warp): TWO warps issue, one the even and one the odd rows of the unit -- disjoint accumulator columns, so the
+//     order in which the tensor pipe takes their instructions does not matter.  Warp 0 also issues the copies (one k-block
+//     ahead of its MMAs) and publishes each through an mbarrier (tcgen05.commit) that warp 1 waits on.
+// TMEM: accumulator columns 0..255 (single buffer: the epilogue's drain is not overlapped with the next unit's MMAs), weight
+// k-blocks in columns 256..511.  L2 -> SM traffic per 256 pixels of a 128 -> 128 layer: 288 KB of weights + 110 KB of rows
+// instead of 1152 KB.
 //
 //   warps 0-7   epilogue  : TMEM (lane = output channel, column = pixel) -> + bias -> ReLU -> bf16 -> global; a warp's store
 //                           instruction writes 32 consecutive channels of one pixel (64 contiguous bytes)
-//   warps 8-13  producers : padded input rows, 128 (or 64) channels at a time, into the row ring with cp.async (reflect / zero
+//   warps 8-12  producers : padded input rows, 128 (or 64) channels at a time, into the row ring with cp.async (reflect / zero
 //                           padding in the source address; per-thread offsets computed once)
-//   warp  14    MMA issuer: per unit and channel slice: 9 taps x CS/64 weight stages x R rows x 4 k-steps; rows are released to
-//                           the producers as soon as their last tap row has been issued
-//   warp  15    weight streamer: one cp.async.bulk per 16 KB stage out of the packed weight image (mst_pack_conv3x3_weight)
+//   warp  13    weight streamer: one cp.async.bulk per 16 KB stage out of the packed weight image (mst_pack_conv3x3_weight)
+//   warps 14,15 MMA issuers: per unit and channel slice: 9 taps x CS/64 weight k-blocks x R/2 rows each x 4 k-steps; rows are
+//                           released to the producers when both have issued their last tap row
 #include "../../include/mst_b200.h"
 #include "common.cuh"
 #include <stdio.h>
@@ -33,14 +43,15 @@
 namespace mst {
 
 constexpr int CM_EPI_WARPS = 8;
-constexpr int CM_PROD_WARPS = 6;
-constexpr int CM_MMA_WARP = CM_EPI_WARPS + CM_PROD_WARPS;  // 14
-constexpr int CM_WSTREAM_WARP = CM_MMA_WARP + 1;           // 15
+constexpr int CM_PROD_WARPS = 5;
+constexpr int CM_WSTREAM_WARP = CM_EPI_WARPS + CM_PROD_WARPS;  // 13
+constexpr int CM_MMA_WARP = CM_WSTREAM_WARP + 1;               // 14 and 15
 constexpr int CM_THREADS = 16 * 32;
 constexpr int CM_MAX_RING = 12;
 constexpr int CM_WSTAGES = 4;
 constexpr int CM_WSTAGE_BYTES = 128 * 128;  // [128 output channels x 64 k] bf16, SWIZZLE_128B image
 constexpr int CM_ACC_COLS = 256;            // accumulator columns per unit (R rows x W pixels)
+constexpr int CM_TSTAGES = 8;               // weight k-blocks resident in TMEM (32 columns each, columns 256..511)
 
 struct CmGeom {
   int R;              // output rows per unit
@@ -73,7 +84,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t row_full[CM_MAX_RING], row_free[CM_MAX_RING];
   __shared__ uint64_t w_full[CM_WSTAGES], w_empty[CM_WSTAGES];
-  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_ready[CM_TSTAGES], a_free[CM_TSTAGES];
+  __shared__ uint64_t acc_full, acc_empty;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
@@ -87,16 +99,18 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.ring; ++s) {
       mbar_init(smem_u32(&row_full[s]), CM_PROD_WARPS * 32);
-      mbar_init(smem_u32(&row_free[s]), 1);
+      mbar_init(smem_u32(&row_free[s]), 2);
     }
     for (int s = 0; s < CM_WSTAGES; ++s) {
       mbar_init(smem_u32(&w_full[s]), 1);
       mbar_init(smem_u32(&w_empty[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&acc_full[b]), 1);
-      mbar_init(smem_u32(&acc_empty[b]), CM_EPI_WARPS);
+    for (int s = 0; s < CM_TSTAGES; ++s) {
+      mbar_init(smem_u32(&a_ready[s]), 1);
+      mbar_init(smem_u32(&a_free[s]), 2);
     }
+    mbar_init(smem_u32(&acc_full), 2);
+    mbar_init(smem_u32(&acc_empty), CM_EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == CM_MMA_WARP) {
@@ -108,7 +122,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp >= CM_EPI_WARPS && warp < CM_MMA_WARP) {
+  if (warp >= CM_EPI_WARPS && warp < CM_WSTREAM_WARP) {
     // =========================== row producers ===========================
     const int t = threadIdx.x - CM_EPI_WARPS * 32;
     constexpr int NPROD = CM_PROD_WARPS * 32;
@@ -183,16 +197,31 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
         }
       }
     }
-  } else if (warp == CM_MMA_WARP) {
-    // =========================== MMA issuer ===========================
-    // whole warp, convergent, warp-uniform values; one lane is elected inside umma_bf16_pred / umma_commit_pred
+  } else if (warp >= CM_MMA_WARP) {
+    // =========================== MMA issuers (two warps) ===========================
+    // each warp whole, convergent, on warp-uniform values; one lane is elected inside the *_pred helpers
+    const int mw = warp - CM_MMA_WARP;  // 0: even rows + the weight copies; 1: odd rows
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 B, version 1, SWIZZLE_128B
     const uint32_t plane16 = (uint32_t)g.plane_bytes >> 4, slot16 = (uint32_t)g.slot_bytes >> 4;
     const uint32_t ring_lo = ((ring_base & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t w_lo = ((w_base & 0x3FFFFu) >> 4) | (1u << 16);
-    int ws = 0;
-    uint32_t wphase = 0;
+    const int stages_total = (u_end - u_begin) * g.nslices * 9 * PLANES;
+    // the weight k-blocks are ONE linear sequence of stages: stage q sits in shared-memory slot q % CM_WSTAGES and goes to
+    // TMEM slot q % CM_TSTAGES
+    int q_cp = 0;                        // (warp 0) next stage to copy
+    auto copy_stage = [&]() {            // shared memory -> tensor memory, then hand the shared-memory stage back
+      const int ws = q_cp % CM_WSTAGES, ts = q_cp % CM_TSTAGES;
+      mbar_wait(smem_u32(&w_full[ws]), (uint32_t)((q_cp / CM_WSTAGES) & 1));
+      mbar_wait(smem_u32(&a_free[ts]), (uint32_t)(((q_cp / CM_TSTAGES) & 1) ^ 1));  // both warps' MMAs of the slot's previous k-block are done
+      tc_fence_after();
+      const uint32_t a_lo = w_lo + (uint32_t)((ws * CM_WSTAGE_BYTES) >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tmem_cp_128x256b_pred(tmem_base + CM_ACC_COLS + ts * 32 + k * 8, ((uint64_t)desc_hi << 32) | (a_lo + k * 2));
+      umma_commit_pred(smem_u32(&w_empty[ws]));
+      umma_commit_pred(smem_u32(&a_ready[ts]));
+      ++q_cp;
+    };
     // ring position of row 0 of the current item and the parity of that slot's current use; row j of the item sits j slots
     // further (one wrap at most: an item has fewer rows than the ring) -- no division in the issue loop
     int base_slot = 0;
@@ -204,15 +233,15 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       phase = base_phase ^ (wrapped ? 1u : 0u);
       return sidx;
     };
+    int q = 0;  // current stage
     int ucount = 0;
     long long t_rows = 0, t_w = 0, t_acc = 0, t_all = g.prof ? clock64() : 0, t0 = 0;
+    if (mw == 0 && stages_total > 0) copy_stage();
     for (int u = u_begin; u < u_end; ++u, ++ucount) {
-      const int buf = ucount & 1;
       if (g.prof) t0 = clock64();
-      mbar_wait(smem_u32(&acc_empty[buf]), (uint32_t)(((ucount >> 1) & 1) ^ 1));
+      mbar_wait(smem_u32(&acc_empty), (uint32_t)((ucount & 1) ^ 1));
       if (g.prof) t_acc += clock64() - t0;
       tc_fence_after();
-      const uint32_t d_base = tmem_base + buf * CM_ACC_COLS;
       for (int sl = 0; sl < g.nslices; ++sl) {
         int rows_waited = 0;
         for (int ky = 0; ky < 3; ++ky) {
@@ -227,26 +256,29 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
           tc_fence_after();
           for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-            for (int pl = 0; pl < PLANES; ++pl) {
-              if (g.prof) t0 = clock64();
-              mbar_wait(smem_u32(&w_full[ws]), wphase);
-              if (g.prof) t_w += clock64() - t0;
-              tc_fence_after();
-              const uint32_t a_lo = w_lo + (uint32_t)((ws * CM_WSTAGE_BYTES) >> 4);
+            for (int pl = 0; pl < PLANES; ++pl, ++q) {
+              const int ts = q % CM_TSTAGES;
+              if (mw == 0) {
+                if (q_cp <= q + 1 && q_cp < stages_total) copy_stage();  // one k-block ahead of the MMAs
+              } else {
+                if (g.prof) t0 = clock64();
+                mbar_wait(smem_u32(&a_ready[ts]), (uint32_t)((q / CM_TSTAGES) & 1));
+                if (g.prof) t_w += clock64() - t0;
+                tc_fence_after();
+              }
+              const uint32_t a_tmem = tmem_base + CM_ACC_COLS + ts * 32;
               const bool first_stage = sl == 0 && ky == 0 && kx == 0 && pl == 0;
 #pragma unroll 1
-              for (int r = 0; r < g.R; ++r) {
+              for (int r = mw; r < g.R; r += 2) {
                 uint32_t ph_unused;
                 const int slot = slot_of(r + ky, ph_unused);
                 // + kx pixels = kx operand rows of 128 B (8 address units); k-step = 32 B inside the swizzled row
                 const uint32_t b_lo = ring_lo + (uint32_t)slot * slot16 + (uint32_t)pl * plane16 + (uint32_t)kx * 8u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16_pred(d_base + r * p.W, ((uint64_t)desc_hi << 32) | (a_lo + k * 2), ((uint64_t)desc_hi << 32) | (b_lo + k * 2), idesc,
-                                 !(first_stage && k == 0));
+                  umma_ts_pred(tmem_base + r * p.W, a_tmem + k * 8, ((uint64_t)desc_hi << 32) | (b_lo + k * 2), idesc, !(first_stage && k == 0));
               }
-              umma_commit_pred(smem_u32(&w_empty[ws]));
-              if (++ws == CM_WSTAGES) { ws = 0; wphase ^= 1; }
+              umma_commit_pred(smem_u32(&a_free[ts]));
             }
           }
           // rows whose last tap row this was go back to the producers: row ky for ky < 2, rows 2 .. R+1 after ky = 2
@@ -260,10 +292,10 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
         base_slot += rows_per_item;
         if (base_slot >= g.ring) { base_slot -= g.ring; base_phase ^= 1u; }
       }
-      umma_commit_pred(smem_u32(&acc_full[buf]));
+      umma_commit_pred(smem_u32(&acc_full));
     }
     if (g.prof && blockIdx.x == 1 && lane == 0)
-      printf("cm prof mma: units %d total %lld wait rows %lld weights %lld acc_empty %lld\n", ucount, clock64() - t_all, t_rows, t_w, t_acc);
+      printf("cm prof mma %d: units %d total %lld wait rows %lld a_ready %lld acc_empty %lld\n", mw, ucount, clock64() - t_all, t_rows, t_w, t_acc);
     tc_fence_before();
   } else {
     // =========================== epilogue (warps 0-7) ===========================
@@ -271,24 +303,23 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
     bf16* out = reinterpret_cast<bf16*>(p.out_bf16);
     int ucount = 0;
     for (int u = u_begin; u < u_end; ++u, ++ucount) {
-      const int buf = ucount & 1;
       const int ct = u % g.ctiles, rest = u / g.ctiles;
       const int b = rest / g.yblocks, y0 = (rest - b * g.yblocks) * g.R;
       const int ch = ct * 128 + quad * 32 + lane;
       const float bias = p.bias ? p.bias[ch] : 0.f;
-      if (lane == 0) mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)((ucount >> 1) & 1));
+      if (lane == 0) mbar_wait(smem_u32(&acc_full), (uint32_t)(ucount & 1));
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = half * 128 + cc * 32;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * CM_ACC_COLS + col0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + col0, v);
         tmem_wait_ld();
         if (cc == 3) {  // accumulator drained by this warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
         }
         const int r = col0 / p.W, x0 = col0 - r * p.W;  // 32 consecutive pixels of one output row (W >= 32)
         bf16* op = out + ((long long)(b * p.H + y0 + r) * p.W + x0) * p.ld_out16 + ch;
