@@ -77,10 +77,18 @@ MST_DEVINL void cm_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 
 // CS = channels per slice: 128 (two 64-channel planes per staged row; W <= 64) or 64 (one plane; W <= 128)
-template <int CS>
+// RR = rows per unit (256 / W), a template parameter so that the issue loops unroll completely: measured, a lone warp pays ~7 clk
+// per uniform-datapath instruction, and an N = 64 MMA with its A operand in TMEM takes 32 clk (tools/micro/umma_rate.cu), so
+// the instruction stream between two MMAs has to be a handful of adds.
+template <int CS, int RR>
 __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p, const CmGeom g) {
   constexpr int PLANES = CS / 64;
   constexpr int CPP = CS / 8;  // 16-byte chunks per pixel of a slice
+  // Weight k-block through TMEM only when it is reused often enough: the copy runs at 64 B/clk in the same pipe as the MMAs
+  // (256 clk per 16 KB k-block), a shared-memory A operand costs 32 clk per MMA (tools/micro/umma_rate.cu).  Per k-block:
+  // RR = 8 (N = 32): 32 x 16 + 256 = 768 clk against 32 x 40 = 1280; RR = 4 (N = 64): 768 against 768; RR = 2 (N = 128): 8 x 64
+  // + 256 = 768 against 8 x 64 = 512 (the N = 128 MMA is at its math floor with both operands in shared memory).
+  constexpr bool TS = RR >= 4;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t row_full[CM_MAX_RING], row_free[CM_MAX_RING];
   __shared__ uint64_t w_full[CM_WSTAGES], w_empty[CM_WSTAGES];
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
     }
     for (int s = 0; s < CM_WSTAGES; ++s) {
       mbar_init(smem_u32(&w_full[s]), 1);
-      mbar_init(smem_u32(&w_empty[s]), 1);
+      mbar_init(smem_u32(&w_empty[s]), TS ? 1 : 2);
     }
     for (int s = 0; s < CM_TSTAGES; ++s) {
       mbar_init(smem_u32(&a_ready[s]), 1);
@@ -233,10 +241,13 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       phase = base_phase ^ (wrapped ? 1u : 0u);
       return sidx;
     };
+    uint32_t d_row[RR / 2];  // accumulator columns of this warp's rows
+#pragma unroll
+    for (int i = 0; i < RR / 2; ++i) d_row[i] = tmem_base + (uint32_t)((2 * i + mw) * p.W);
     int q = 0;  // current stage
     int ucount = 0;
     long long t_rows = 0, t_w = 0, t_acc = 0, t_all = g.prof ? clock64() : 0, t0 = 0;
-    if (mw == 0 && stages_total > 0) copy_stage();
+    if (TS && mw == 0 && stages_total > 0) copy_stage();
     for (int u = u_begin; u < u_end; ++u, ++ucount) {
       if (g.prof) t0 = clock64();
       mbar_wait(smem_u32(&acc_empty), (uint32_t)((ucount & 1) ^ 1));
@@ -254,31 +265,58 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
           if (g.prof) t_rows += clock64() - t0;
           fence_proxy_async_smem();  // the rows were written by cp.async (generic proxy)
           tc_fence_after();
+          // descriptor low words of this warp's rows for this tap row (ring slot of item row r + ky), once per ky
+          uint32_t rb[RR / 2];
+#pragma unroll
+          for (int i = 0; i < RR / 2; ++i) {
+            uint32_t ph_unused;
+            rb[i] = ring_lo + (uint32_t)slot_of(2 * i + mw + ky, ph_unused) * slot16;
+          }
+#pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
             for (int pl = 0; pl < PLANES; ++pl, ++q) {
-              const int ts = q % CM_TSTAGES;
-              if (mw == 0) {
-                if (q_cp <= q + 1 && q_cp < stages_total) copy_stage();  // one k-block ahead of the MMAs
+              const uint32_t acc = (sl | ky | kx | pl) != 0;  // 0: the unit's first k-block overwrites the accumulator
+              if constexpr (TS) {
+                const int ts = q % CM_TSTAGES;
+                if (mw == 0) {
+                  if (q_cp <= q + 1 && q_cp < stages_total) copy_stage();  // one k-block ahead of the MMAs
+                } else {
+                  if (g.prof) t0 = clock64();
+                  mbar_wait(smem_u32(&a_ready[ts]), (uint32_t)((q / CM_TSTAGES) & 1));
+                  if (g.prof) t_w += clock64() - t0;
+                  tc_fence_after();
+                }
+                const uint32_t a_tmem = tmem_base + CM_ACC_COLS + ts * 32;
+#pragma unroll
+                for (int i = 0; i < RR / 2; ++i) {
+                  // + kx pixels = kx operand rows of 128 B (8 address units); k-step = 32 B inside the swizzled row
+                  const uint32_t b_lo = rb[i] + (uint32_t)pl * plane16 + (uint32_t)(kx * 8);
+                  const uint32_t d = d_row[i];
+                  umma_ts_pred(d, a_tmem, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+                  umma_ts_pred(d, a_tmem + 8, ((uint64_t)desc_hi << 32) | (b_lo + 2), idesc, 1);
+                  umma_ts_pred(d, a_tmem + 16, ((uint64_t)desc_hi << 32) | (b_lo + 4), idesc, 1);
+                  umma_ts_pred(d, a_tmem + 24, ((uint64_t)desc_hi << 32) | (b_lo + 6), idesc, 1);
+                }
+                umma_commit_pred(smem_u32(&a_free[ts]));
               } else {
+                const int ws = q % CM_WSTAGES;
                 if (g.prof) t0 = clock64();
-                mbar_wait(smem_u32(&a_ready[ts]), (uint32_t)((q / CM_TSTAGES) & 1));
+                mbar_wait(smem_u32(&w_full[ws]), (uint32_t)((q / CM_WSTAGES) & 1));
                 if (g.prof) t_w += clock64() - t0;
                 tc_fence_after();
-              }
-              const uint32_t a_tmem = tmem_base + CM_ACC_COLS + ts * 32;
-              const bool first_stage = sl == 0 && ky == 0 && kx == 0 && pl == 0;
-#pragma unroll 1
-              for (int r = mw; r < g.R; r += 2) {
-                uint32_t ph_unused;
-                const int slot = slot_of(r + ky, ph_unused);
-                // + kx pixels = kx operand rows of 128 B (8 address units); k-step = 32 B inside the swizzled row
-                const uint32_t b_lo = ring_lo + (uint32_t)slot * slot16 + (uint32_t)pl * plane16 + (uint32_t)kx * 8u;
+                const uint32_t a_lo = w_lo + (uint32_t)((ws * CM_WSTAGE_BYTES) >> 4);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_ts_pred(tmem_base + r * p.W, a_tmem + k * 8, ((uint64_t)desc_hi << 32) | (b_lo + k * 2), idesc, !(first_stage && k == 0));
+                for (int i = 0; i < RR / 2; ++i) {
+                  const uint32_t b_lo = rb[i] + (uint32_t)pl * plane16 + (uint32_t)(kx * 8);
+                  const uint32_t d = d_row[i];
+                  umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
+                  umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | (a_lo + 2), ((uint64_t)desc_hi << 32) | (b_lo + 2), idesc, 1);
+                  umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | (a_lo + 4), ((uint64_t)desc_hi << 32) | (b_lo + 4), idesc, 1);
+                  umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | (a_lo + 6), ((uint64_t)desc_hi << 32) | (b_lo + 6), idesc, 1);
+                }
+                umma_commit_pred(smem_u32(&w_empty[ws]));  // both issuing warps arrive: the stage is free when both are done
               }
-              umma_commit_pred(smem_u32(&a_free[ts]));
             }
           }
           // rows whose last tap row this was go back to the producers: row ky for ky < 2, rows 2 .. R+1 after ky = 2
@@ -388,19 +426,19 @@ static bool plan_cm(const MstGemm& g, CmGeom& out) {
   return out.bn >= 128;
 }
 
-template <int CS>
+template <int CS, int RR>
 static int launch_cm(const MstGemm& g, const CmGeom& geo, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)CM_WSTAGES * CM_WSTAGE_BYTES + (size_t)geo.ring * geo.slot_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_cm_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_cm_kernel<CS, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)((geo.units + geo.units_per_cta - 1) / geo.units_per_cta);
   GemmCore core;
   memcpy(&core, &g, sizeof(GemmCore));
-  conv_cm_kernel<CS><<<grid, CM_THREADS, smem, st>>>(core, geo);
+  conv_cm_kernel<CS, RR><<<grid, CM_THREADS, smem, st>>>(core, geo);
   return (int)cudaGetLastError();
 }
 
@@ -422,5 +460,8 @@ extern "C" int mst_conv3x3_cm(const MstGemm* g, void* stream) {
   CmGeom geo;
   if (!plan_cm(*g, geo)) return MST_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  return cm_slice(g->Cin, g->W) == 128 ? launch_cm<128>(*g, geo, st) : launch_cm<64>(*g, geo, st);
+  const int cs = cm_slice(g->Cin, g->W);
+  if (g->W == 32) return cs == 128 ? launch_cm<128, 8>(*g, geo, st) : launch_cm<64, 8>(*g, geo, st);
+  if (g->W == 64) return cs == 128 ? launch_cm<128, 4>(*g, geo, st) : launch_cm<64, 4>(*g, geo, st);
+  return launch_cm<64, 2>(*g, geo, st);  // W == 128
 }
