@@ -456,24 +456,28 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
         }
         const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
         float suma[4] = {0.f, 0.f, 0.f, 0.f};
+        // P goes back into TENSOR MEMORY, bf16 pairs in columns 0..31 of the head's S region, and is the TMEM A operand of PV
+        // (an N = 32 MMA takes 16 clk with A in TMEM against 40 from shared memory, tools/micro/umma_rate.cu; no shared-memory
+        // stores, no proxy fence).  Columns 0..31 are free in every lane: rows of window 0 have just read them (their own S),
+        // rows of window 1 hold window-1-query x window-0-key products there that nobody reads.
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          uint32_t pk[4];
+        for (int h16 = 0; h16 < 2; ++h16) {
+          uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j0 = c8 * 8 + e * 2;
+          for (int e = 0; e < 16; ++e) {
+            const int j0 = h16 * 32 + e * 2;
             const float p0 = j0 < N ? af_ex2(s[j0 < N ? j0 : 0] - mx) : 0.f;          // keys past a 7x7 window: probability 0
             const float p1 = j0 + 1 < N ? af_ex2(s[j0 + 1 < N ? j0 + 1 : 0] - mx) : 0.f;
-            suma[e] += p0 + p1;
+            suma[e & 3] += p0 + p1;
             pk[e] = af_pack(p0, p1);
           }
-          af_sts128(qk_tile + xrow + ((uint32_t)(c8 ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          tmem_st16(s_addr + h16 * 16, pk);
         }
         const float sum = (suma[0] + suma[1]) + (suma[2] + suma[3]);
         inv = 1.0f / sum;
       }
-      fence_proxy_async_smem();
-      tc_fence_before();  // S_p has been read: PV_p may overwrite its columns
+      tmem_wait_st();
+      tc_fence_before();  // S_p has been read and P_p written: PV_p may run (it writes O into columns 64..127 of the region)
       asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
       if (quad == 0) {  // O_p[:, 32w..] = P_p . V_{p,w}: 16 keys per step = 32 B along K in the P tile, two 8-key groups (2 KB) in the V tile
         tc_fence_after();
@@ -481,8 +485,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
         for (int ww = 0; ww < 2; ++ww)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_pred(s_addr_mma + ww * 32, umma_desc_sw128(qk_tile + k * 32), af_desc_mn_sw128(v_base + ww * 8192 + part * 64 + k * 2048),
-                           idesc_pv, k != 0);
+            umma_ts_pred(s_addr_mma + 64 + ww * 32, s_addr_mma + k * 8, af_desc_mn_sw128(v_base + ww * 8192 + part * 64 + k * 2048), idesc_pv, k != 0);
         umma_commit_pred(smem_u32(&o_full[part]));
       }
       AF_MARK(tS)
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(AF_THREADS, 1) attn_fused_kernel(const AttnCor
       tc_fence_after();
       {
         uint32_t ov[32];
-        tmem_ld32(s_addr + w * 32, ov);
+        tmem_ld32(s_addr + 64 + w * 32, ov);
         tmem_wait_ld();
         tc_fence_before();
         if (src >= 0) {
