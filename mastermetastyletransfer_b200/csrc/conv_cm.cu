@@ -1,6 +1,7 @@
 // 3x3 convolution for the WIDE layers (Cout a multiple of 128, Cin a multiple of 64, W in {32, 64, 128}) on sm_100a:
 // the CNN decoder's 256->128 @32^2 and 128->128 @64^2 layers (codes/decoder.py:25-37) and VGG-19 conv2_x .. conv4_x
-// (codes/loss.py:23-37).  bf16 NHWC in, bf16 NHWC out, fp32 accumulation, zero or reflect padding, optional ReLU.
+// (codes/loss.py:23-37).  bf16 NHWC in, bf16 NHWC out, fp32 accumulation, zero or reflect padding, optional ReLU, optional nearest-x2
+// upsample of the input folded into the row fetch (decoder.py:27).
 //
 // Why another conv kernel: the gathered implicit GEMM (gemm_tc.cu) fetches every input pixel nine times (once per tap) and the
 // whole [Cout x 9 Cin] weight matrix once per 128-pixel tile.  For 128 -> 128 channels that is 576 KB of L2 -> shared-memory
@@ -149,12 +150,14 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       bool valid = idx < row_chunks;
       if (p.pad_mode == 1) xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
       else valid = valid && (unsigned)xx < (unsigned)p.W;
+      if (p.upsample) xx >>= 1;  // nearest x2 (decoder.py:27): the stored input is [B, H/2, W/2, Cin]
       src_off[k] = valid ? xx * p.Cin + c * 8 : -1;
       // plane (64 channels) -> pixel row of 128 B -> chunk XOR the pixel's low three bits (planes are 1024-byte aligned)
       dst_off[k] = (uint32_t)(c >> 3) * (uint32_t)g.plane_bytes + (uint32_t)col * 128u + (uint32_t)(((c & 7) ^ (col & 7)) << 4);
     }
     const int nk = (row_chunks - t + NPROD - 1) / NPROD;
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
+    const int Hs = p.upsample ? (p.H >> 1) : p.H, Ws = p.upsample ? (p.W >> 1) : p.W;  // stored input size
     int slot = 0;
     uint32_t fphase = 1;  // a fresh row_free passes a wait on parity 1
     for (int u = u_begin; u < u_end; ++u) {
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
           bool vrow = true;
           if (p.pad_mode == 1) yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
           else vrow = (unsigned)yy < (unsigned)p.H;
-          const bf16* rowsrc = Abase + ((long long)b * p.H + (vrow ? yy : 0)) * p.W * p.Cin + sl * CS;
+          if (p.upsample) yy >>= 1;
+          const bf16* rowsrc = Abase + ((long long)b * Hs + (vrow ? yy : 0)) * Ws * p.Cin + sl * CS;
           mbar_wait(smem_u32(&row_free[slot]), fphase);
           const uint32_t rowdst = ring_base + (uint32_t)slot * (uint32_t)g.slot_bytes;
 #pragma unroll
@@ -451,8 +455,8 @@ extern "C" int mst_conv3x3_cm_supported(int N, int Cin, int H, int W) { return c
 extern "C" int mst_conv3x3_cm(const MstGemm* g, void* stream) {
   if (!g || !g->A || !g->Wt || !g->out_bf16) return MST_ERR_BAD_ARG;
   if (g->a_mode != MST_A_CONV3X3 || g->M <= 0 || g->H <= 0 || g->W <= 0) return MST_ERR_BAD_ARG;
-  // what this kernel does not do: fp32 / NCHW outputs, residuals, the folded upsample, the training-step extensions
-  if (g->out_f32 || g->res || g->mul || g->out_nchw || g->upsample || g->gate || g->add16 || g->out_pre16 || g->row_scale || g->conv_full)
+  // what this kernel does not do: fp32 / NCHW outputs, residuals, the training-step extensions
+  if (g->out_f32 || g->res || g->mul || g->out_nchw || g->gate || g->add16 || g->out_pre16 || g->row_scale || g->conv_full)
     return MST_ERR_UNSUPPORTED;
   if (g->act != MST_ACT_NONE && g->act != MST_ACT_RELU) return MST_ERR_UNSUPPORTED;
   if (g->pad_mode != 0 && g->pad_mode != 1) return MST_ERR_BAD_ARG;

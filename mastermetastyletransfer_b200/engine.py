@@ -438,8 +438,9 @@ def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace,
     last = len(w.convs) - 1
     for i, (pm, cin, up, relu) in enumerate(w.convs):
         if up:
-            if cin >= 128 and cin % 64 == 0:
-                # wide layer: materialise the nearest-x2 upsample so the conv can be fed by tensor copies (TMA cannot repeat pixels)
+            if cin >= 128 and cin % 64 == 0 and not ops.cm_supported(pm.N, cin, 2 * h, 2 * wd):
+                # wide layer on the gathered GEMM: materialise the nearest-x2 upsample so the conv can be fed by tensor copies (TMA
+                # cannot repeat pixels); the channel-major kernel folds it into its row fetch
                 big = ws_.bf16("cnn_up", B * 4 * h * wd, cin)
                 ops.upsample2x_nhwc(cur, big, B, h, wd, cin)
                 cur, up = big, False

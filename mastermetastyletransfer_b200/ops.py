@@ -216,7 +216,7 @@ def _use_cm(conv: dict, n_pad: int, act: int) -> bool:
     impl = conv.get("impl", "auto")
     if impl not in ("auto", "cm"):
         return False
-    ok = (not conv.get("upsample", False) and not conv.get("out_nchw", False) and act in (ACT_NONE, ACT_RELU)
+    ok = (not conv.get("out_nchw", False) and act in (ACT_NONE, ACT_RELU)
           and bool(_lib.lib().mst_conv3x3_cm_supported(n_pad, conv["Cin"], conv["H"], conv["W"])))
     if impl == "cm" and not ok:
         raise ValueError("conv3x3 channel-major kernel does not support this shape")

@@ -137,6 +137,22 @@ def test_conv3x3_channel_major(B, H, W, Cin, Cout, pad, relu):
     assert torch.allclose(outs["cm"], outs["gather"], atol=1e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 128, 128), (3, 128, 128, 128, 128), (1, 32, 32, 256, 128)])
+def test_conv3x3_channel_major_folded_upsample(B, H, W, Cin, Cout):
+    """decoder.py:27-29: nearest-x2 upsample + reflect-padded conv; conv_cm.cu folds the upsample into its row fetch (the stored
+    input is [B, H/2, W/2, Cin]).  Same result as the gathered GEMM on the materialised upsample, to bf16 rounding, and as F.conv2d."""
+    ops = _ops()
+    x = _rand(B, H // 2, W // 2, Cin, seed=23).bfloat16()
+    wt = _rand(Cout, Cin, 3, 3, seed=24, scale=(9 * Cin) ** -0.5)
+    bias = _rand(Cout, seed=25)
+    pm = ops.pack_conv3x3(wt.cuda(), bias.cuda())
+    out = torch.full((B * H * W, pm.n_pad), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x.cuda(), pm, B * H * W, act=ops.ACT_RELU, out_bf16=out, conv=dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT, upsample=True, impl="cm"))
+    xi = x.float().permute(0, 3, 1, 2).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    ref = torch.relu(F.conv2d(F.pad(xi, (1, 1, 1, 1), mode="reflect"), wt.bfloat16().float(), bias)).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    assert torch.allclose(out.float().cpu()[:, :Cout], ref, atol=1e-2, rtol=1e-2), (out.float().cpu()[:, :Cout] - ref).abs().max()
+
+
 @pytest.mark.parametrize("impl", ["gather", "band", "rows"])
 def test_conv3x3_nchw_out(impl):
     ops = _ops()
