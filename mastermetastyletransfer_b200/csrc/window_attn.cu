@@ -329,6 +329,8 @@ static int launch_attn(const MstWindowAttn& a, const WinGeom& g, cudaStream_t st
 
 }  // namespace mst
 
+namespace mst { int attn_core_try(const MstWindowAttn& a, cudaStream_t st, bool& handled); }  // attn_core.cu
+
 extern "C" int mst_window_attention(const MstWindowAttn* a, void* stream) {
   using namespace mst;
   if (!a || !a->q || !a->k || !a->v || !a->out || !a->bias_table) return MST_ERR_BAD_ARG;
@@ -339,6 +341,11 @@ extern "C" int mst_window_attention(const MstWindowAttn* a, void* stream) {
   if (a->shift < 0 || a->shift >= a->ws || a->pad_k_stride < 0) return MST_ERR_BAD_ARG;
   const WinGeom g = make_geom(a->H, a->W, a->ws, a->shift);
   cudaStream_t st = (cudaStream_t)stream;
+  {  // the dual (two value tensors, one softmax) passes on maps the windows tile: the tcgen05 kernel of attn_core.cu
+    bool handled = false;
+    const int rc = attn_core_try(*a, st, handled);
+    if (handled) return rc;
+  }
   if (a->ws == 8) return launch_attn<8>(*a, g, st);
   if (a->ws == 7) return launch_attn<7>(*a, g, st);
   return MST_ERR_UNSUPPORTED;

@@ -222,6 +222,29 @@ def test_window_attention_core(ws, s, H, heads, dual):
         assert torch.allclose(out2.float().cpu(), ref2, atol=2e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("ws,s,B,H,W,heads", [(8, 4, 2, 32, 32, 8), (8, 0, 1, 16, 32, 8), (7, 3, 2, 28, 28, 8), (8, 4, 1, 24, 24, 4),
+                                              (7, 3, 3, 14, 21, 4), (8, 4, 3, 64, 64, 8)])
+def test_window_attention_dual_tcgen05(ws, s, B, H, W, heads):
+    """The dual (one softmax, two value tensors) passes on maps the windows tile run on attn_core.cu (TMA window loads, S / PV on
+    tcgen05, P as a TMEM operand); against the oracle's attention with identity projections.  Odd window counts, rectangular maps,
+    unshifted and shifted windows, strided (fused-buffer) operands."""
+    from oracle import master_oracle as O
+    ops = _ops()
+    C = heads * 32
+    T = B * H * W
+    big = _rand(T, 4 * C, seed=60).bfloat16()  # q | k | v | v2 side by side: leading dimension 4C
+    table = _rand((2 * ws - 1) ** 2, heads, seed=61, scale=0.5)
+    bigc = big.cuda()
+    out = torch.full((T, 2 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.window_attention(bigc[:, :C], bigc[:, C:2 * C], bigc[:, 2 * C:3 * C], out[:, :C], table.cuda(), B, H, W, heads, ws, s, 4 * C, 4 * C, 4 * C, 2 * C,
+                         v2=bigc[:, 3 * C:], out2=out[:, C:])
+    eye, zero = torch.eye(C), torch.zeros(C)
+    q, k, v, v2 = (big[:, i * C:(i + 1) * C].float().reshape(B, H, W, C) for i in range(4))
+    for vv, o in ((v, out[:, :C]), (v2, out[:, C:])):
+        ref = O.window_attention(q, k, vv, eye, zero, eye, zero, eye, zero, eye, zero, table, ws, s, heads).reshape(T, C)
+        assert torch.allclose(o.float().cpu(), ref, atol=2e-2, rtol=2e-2), (o.float().cpu() - ref).abs().max()
+
+
 @pytest.mark.parametrize("C", [128, 256, 512])
 def test_layernorm(C):
     ops = _ops()
