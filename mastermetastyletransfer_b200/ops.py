@@ -53,7 +53,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 
 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
-             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_conv3x3_cm": "conv_cm_kernel", "mst_window_attention": "window_attn_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
+             "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_conv3x3_cm": "conv_cm_kernel", "mst_window_attention": "window_attn_kernel", "mst_window_attention:core": "attn_core_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
              "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_resize_crop_normalize": "resize_crop_normalize_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
@@ -258,7 +258,10 @@ def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, l
     a.pad_k_stride = heads * 32 if pad_k_per_image else 0
     n_tok = ws * ws
     n_win = B * (-(-H // ws)) * (-(-W // ws))
-    _launch("mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
+    # which kernel the library picks (csrc/attn_core.cu: attn_core_try): the dual passes on maps the windows tile run on tcgen05
+    core = (v2 is not None and ws in (7, 8) and H % ws == 0 and W % ws == 0 and heads % 2 == 0 and (ldq | ldk | ldv | ldo) % 16 == 0
+            and all(t.data_ptr() % 32 == 0 for t in (q, k, v, v2, out, out2)) and os.environ.get("MST_ATTN_CORE", "1") != "0")
+    _launch("mst_window_attention:core" if core else "mst_window_attention", lambda: _lib.lib().mst_window_attention(C.byref(a), _stream()),
             flops=2.0 * n_win * heads * n_tok * n_tok * 32 * (3 if v2 is not None else 2),
             desc=f"B={B} H={H} heads={heads} ws={ws} shift={shift} dual={v2 is not None}")
 

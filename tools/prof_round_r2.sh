@@ -4,7 +4,7 @@
 #   2. per-launch metrics of one eager forward            -> gpurun_out/r2_forward_metrics_b32_256.csv  (-> profiles/ncu_traffic.json)
 #   3. `--set full` captures of one representative launch of each heavy family, summarised ON THE BOX (headline metrics, stall
 #      reasons, hottest SASS); the reports themselves are deleted (large with imported source).
-K='regex:gemm_tc|mlp_fused|attn_fused|window_attn|conv_rows|conv_cm|conv_band|layernorm|instnorm|patch_embed|cast_bf16|upsample'
+K='regex:gemm_tc|mlp_fused|attn_fused|attn_core|window_attn|conv_rows|conv_cm|conv_band|layernorm|instnorm|patch_embed|cast_bf16|upsample'
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size
 BENCH="python bench.py --steps 2 --warmup 3 --train-steps 0 --cpu-baseline 0 --config5 0"
 $BENCH > gpurun_out/r2_plain_bench.log 2>&1 || exit 1
