@@ -592,6 +592,11 @@ extern "C" int mst_instnorm_apply_affine(const float* x, const float* mean, cons
   return (int)cudaGetLastError();
 }
 
+namespace mst {
+int patch_embed_tc_try(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x, const float* gamma1,
+                       const float* beta1, bf16* y16, int B, int S, cudaStream_t st, bool& handled);  // patch_embed_tc.cu
+}
+
 extern "C" int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta,
                                float* x, int B, int S, void* stream) {
   return mst_patch_embed_ln(img, w, b, gamma, beta, x, nullptr, nullptr, nullptr, B, S, 0, stream);
@@ -603,6 +608,11 @@ extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float*
   if (!img || !w || !b || !gamma || !beta || !x || B <= 0 || S <= 0 || S % 4 != 0) return MST_ERR_BAD_ARG;
   if (y16 && (!gamma1 || !beta1)) return MST_ERR_BAD_ARG;
   const long long total = (long long)B * (S / 4) * (S / 4);
+  if (!exact) {  // tcgen05 kernel (patch_embed_tc.cu): 128-token tiles, both LayerNorms thread-local
+    bool handled = false;
+    const int rc = mst::patch_embed_tc_try(img, w, b, gamma, beta, x, gamma1, beta1, reinterpret_cast<bf16*>(y16), B, S, (cudaStream_t)stream, handled);
+    if (handled) return rc;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
