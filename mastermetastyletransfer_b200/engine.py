@@ -268,43 +268,54 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     kpad = ws_.f32("st_kpad", B, C)
 
     fuse_attn = w.enc_attn is not None and w.dec_attn is not None and win in (7, 8) and heads == w.heads
-    x32.copy_(fc32.reshape(T, C))
-    key32.copy_(fs32.reshape(T, C))
-    scale32.copy_(key32)
-    shift32.copy_(key32)
-    ops.cast_bf16(key32, key16)
-    scale16.copy_(key16)
-    shift16.copy_(key16)
+    # Scale = Shift = Key = Fs and Query = Fc at the first layer (:1233-1236).  No copies: the first layer reads the INPUT tensors
+    # (as residual sources and operands) and writes the work buffers; later layers read what the previous one wrote.  (Four fp32
+    # and two bf16 copies of a [T, C] map used to open every call: ~70 us of a 2.3 ms step at batch 32.)
+    fc_in, fs_in = fc32.reshape(T, C), fs32.reshape(T, C)
+    fs16 = ws_.bf16("st_fs16", T, C)
+    ops.cast_bf16(fs_in, fs16)
+    x_src, key_src, scale_src, shift_src = fc_in, fs_in, fs_in, fs_in   # fp32 residual sources of the next update of each stream
+    key16_cur = fs16                                                    # bf16 Key as the attentions read it
+    first = True                                                        # Scale16 = Shift16 = fs16 until the first Scale / Shift pass
 
     for _ in range(k):
         # ---------------- StyleEncoder: shared MHA, three private MLPs ----------------
         def key_pass():
+            nonlocal key_src, key16_cur
             if fuse_attn:
-                ops.attn_block(key16, w.enc_attn, w.enc_table, o16, B, H, W, win, shift)
+                ops.attn_block(key16_cur, w.enc_attn, w.enc_table, o16, B, H, W, win, shift)
             else:
-                ops.gemm(key16, w.enc_qkv, T, out_bf16=qkv)
+                ops.gemm(key16_cur, w.enc_qkv, T, out_bf16=qkv)
                 ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
                                      pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2])
             if FUSE_PROJ_MLP:  # Key' = Key + proj(o); Key' += MLP_K(Key')
-                ops.mlp_fused(o16, w.pm_key, T, res=key32, out_f32=key32, out_bf16=key16, pre=True)
+                ops.mlp_fused(o16, w.pm_key, T, res=key_src, out_f32=key32, out_bf16=key16, pre=True)
             else:
-                ops.gemm(o16, w.enc_proj, T, res=key32, out_f32=key32, out_bf16=key16)
+                ops.gemm(o16, w.enc_proj, T, res=key_src, out_f32=key32, out_bf16=key16)
                 _mlp_residual(key16, key32, w.mlp_key, T, ws_, key16)
+            key_src, key16_cur = key32, key16
 
         def scale_shift_passes():
             # q = k = Key (one softmax for both), v = Scale | Shift, residual from v
-            ops.gemm(key16, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
-            ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
-            ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
-                                 v2=vh16, out2=o2_16, pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2], pad_v2=w.enc_pad[2])
-            if FUSE_PROJ_MLP:
-                ops.mlp_fused(o16, w.pm_scale, T, res=scale32, out_f32=scale32, out_bf16=scale16, pre=True)
-                ops.mlp_fused(o2_16, w.pm_shift, T, res=shift32, out_f32=shift32, out_bf16=shift16, pre=True)
+            nonlocal scale_src, shift_src, first
+            ops.gemm(key16_cur, w.enc_qk, T, out_bf16=qkv, ld_out16=3 * C)
+            if first:  # Scale = Shift = Fs: one projection Wv.Fs serves both value tensors (fs16 is the bf16 copy of Fs)
+                ops.gemm(fs16, w.enc_v, T, out_bf16=vs16)
+                v2_16 = vs16
             else:
-                ops.gemm(o16, w.enc_proj, T, res=scale32, out_f32=scale32, out_bf16=scale16)
+                ops.gemm(ss16, w.enc_v, 2 * T, out_bf16=vsh16)  # v_scale = Wv.Scale, v_shift = Wv.Shift (same weight: one launch)
+                v2_16 = vh16
+            ops.window_attention(qkv, qkv[:, C:], vs16, o16, w.enc_table, B, H, W, heads, win, shift, 3 * C, 3 * C, C, C,
+                                 v2=v2_16, out2=o2_16, pad_q=w.enc_pad[0], pad_k=w.enc_pad[1], pad_v=w.enc_pad[2], pad_v2=w.enc_pad[2])
+            if FUSE_PROJ_MLP:
+                ops.mlp_fused(o16, w.pm_scale, T, res=scale_src, out_f32=scale32, out_bf16=scale16, pre=True)
+                ops.mlp_fused(o2_16, w.pm_shift, T, res=shift_src, out_f32=shift32, out_bf16=shift16, pre=True)
+            else:
+                ops.gemm(o16, w.enc_proj, T, res=scale_src, out_f32=scale32, out_bf16=scale16)
                 _mlp_residual(scale16, scale32, w.mlp_scale, T, ws_, scale16)
-                ops.gemm(o2_16, w.enc_proj, T, res=shift32, out_f32=shift32, out_bf16=shift16)
+                ops.gemm(o2_16, w.enc_proj, T, res=shift_src, out_f32=shift32, out_bf16=shift16)
                 _mlp_residual(shift16, shift32, w.mlp_shift, T, ws_, shift16)
+            scale_src, shift_src, first = scale32, shift32, False
 
         if processed_key:  # default (:857-882): Scale / Shift attend with the processed Key
             key_pass()
@@ -314,7 +325,7 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
             key_pass()
 
         # ---------------- StyleDecoder ----------------
-        ops.layernorm(x32, w.n1[0], w.n1[1], ln16, T, C)
+        ops.layernorm(x_src, w.n1[0], w.n1[1], ln16, T, C)
         if fuse_attn:
             ops.attn_block(ln16, w.dec_attn, w.dec_table, o16, B, H, W, win, shift)
         else:
@@ -322,13 +333,14 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
             ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o16, w.dec_table, B, H, W, heads, win, shift, 3 * C, 3 * C, 3 * C, C,
                                  pad_q=w.dec_pad[0], pad_k=w.dec_pad[1], pad_v=w.dec_pad[2])
         if exclude_mlp:  # Query = Fcs + proj(attention) only
-            ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
+            ops.gemm(o16, w.dec_proj, T, res=x_src, out_f32=x32)
         elif FUSE_PROJ_MLP:
-            ops.mlp_fused(o16, w.pm_dec, T, res=x32, out_f32=x32, pre=True, ln_g=w.n2[0], ln_b=w.n2[1])  # x32 = Query
+            ops.mlp_fused(o16, w.pm_dec, T, res=x_src, out_f32=x32, pre=True, ln_g=w.n2[0], ln_b=w.n2[1])  # x32 = Query
         else:
-            ops.gemm(o16, w.dec_proj, T, res=x32, out_f32=x32)
+            ops.gemm(o16, w.dec_proj, T, res=x_src, out_f32=x32)
             ops.layernorm(x32, w.n2[0], w.n2[1], ln16, T, C)
             _mlp_residual(ln16, x32, w.dec_mlp, T, ws_, None)  # x32 = Query
+        x_src = x32
         if w.regular_mha:
             _regular_mha_tail(w, x32, key32, key16, scale16, shift16, x16, ws_, B, H * W, C, key_in_after_linear)
             continue
