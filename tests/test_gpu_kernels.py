@@ -432,6 +432,12 @@ def test_proj_mlp_fused(M, C, ln, mul):
     err = (x.cpu() - ref).abs().max()
     assert torch.allclose(x.cpu(), ref, atol=6e-3, rtol=6e-3), err
     assert torch.allclose(out16.float().cpu(), ref, atol=4e-2, rtol=1e-2)
+    # out of place (the style transformer's first layer reads the encoder's feature map as the residual and writes its own buffer):
+    # same bits as in place, and the residual source is left untouched
+    res_dev, y = res.cuda(), torch.full((M, C), float("nan"), device="cuda")
+    ops.mlp_fused(A.cuda(), pm, M, res=res_dev, out_f32=y, pre=True, mul=m.cuda() if mul else None,
+                  ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None)
+    assert torch.equal(y, x) and torch.equal(res_dev.cpu(), res)
 
 
 @pytest.mark.parametrize("B,H,C,ws,shift", [(1, 8, 256, 8, 0), (2, 32, 256, 8, 4), (1, 24, 256, 8, 4), (2, 32, 256, 7, 4), (1, 16, 256, 7, 3),
