@@ -78,7 +78,7 @@ MST_DEVINL void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint
 template <int BN, bool EXT, bool TMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore p, const typename ExtSel<EXT>::type x_,
                                                                   const __grid_constant__ typename TmaSel<TMA>::type tm_, const int num_tiles,
-                                                                  const int res_stages) {
+                                                                  const int res_stages, const int wsplit) {
   using Cfg = GemmCfg<BN>;
   const bool resident = res_stages > 0;
   const int STAGES = resident ? res_stages : Cfg::STAGES;
@@ -162,12 +162,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
     }
     const bf16* Abase = reinterpret_cast<const bf16*>(p.A);
     const uint8_t* Wbase = reinterpret_cast<const uint8_t*>(p.Wt);
+    // wsplit = 1: the weights were packed in 2 BN-wide tiles (mst_gemm_tile_n) and this launch runs them as two BN-wide halves
+    // (small M: twice the CTAs): half h of packed block (n_tile >> 1, kb) starts B_STAGE_BYTES * h into the block
+    const size_t w_kb_stride = (size_t)Cfg::B_STAGE_BYTES << wsplit;
+    auto wtile_of = [&](int nt) { return Wbase + (size_t)(nt >> wsplit) * nkb * w_kb_stride + (size_t)(nt & wsplit) * Cfg::B_STAGE_BYTES; };
     const bool conv = p.a_mode != MST_A_PLAIN;
     if (resident && t == 0) {  // the CTA's whole weight slab, once
       mbar_arrive_expect_tx(smem_u32(&b_full_bar), nkb * Cfg::B_STAGE_BYTES);
-      const uint8_t* wslab = Wbase + (size_t)res_nt * nkb * Cfg::B_STAGE_BYTES;
+      const uint8_t* wslab = wtile_of(res_nt);
       for (int kb = 0; kb < nkb; ++kb)
-        bulk_g2s(smem_base + kb * Cfg::B_STAGE_BYTES, wslab + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&b_full_bar));
+        bulk_g2s(smem_base + kb * Cfg::B_STAGE_BYTES, wslab + (size_t)kb * w_kb_stride, Cfg::B_STAGE_BYTES, smem_u32(&b_full_bar));
     }
     int stage = 0;
     uint32_t pphase = 1;  // producer's view of empty_bar: a fresh barrier passes a wait on parity 1
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
           const int b = m0 / hw;
           const int rem = m0 - b * hw;
           const int y0 = rem / p.W, x0 = rem - y0 * p.W;
-          const uint8_t* wtile = Wbase + (size_t)tt.n_tile * nkb * Cfg::B_STAGE_BYTES;
+          const uint8_t* wtile = wtile_of(tt.n_tile);
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = (int)(it % STAGES);
             // a ring stage is owned by ONE warp, which therefore sees its uses in order: a parity wait cannot tell "phase
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
                 if (p.pad_mode == 1) yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
                 tma_load_4d(a_stage + r * row_bytes, &tm_, c0c, x0 + kx - 1, yy, b, smem_u32(&tma_bar[s]));
               }
-              if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&tma_bar[s]));
+              if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * w_kb_stride, Cfg::B_STAGE_BYTES, smem_u32(&tma_bar[s]));
             }
             mbar_wait(smem_u32(&tma_bar[s]), ph);
             if (patch) {
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
       } else if (t == 0) {  // one thread feeds the whole ring: a tensor copy for A (+ a bulk copy for the weight tile) per stage
         for (TileIter tt = tile_begin(); tt.m_tile < m_tiles; tile_next(tt)) {
           const int m0 = tt.m_tile * BM;
-          const uint8_t* wtile = Wbase + (size_t)tt.n_tile * nkb * Cfg::B_STAGE_BYTES;
+          const uint8_t* wtile = wtile_of(tt.n_tile);
           for (int kb = 0; kb < nkb; ++kb) {
             const int s = stage;
             mbar_wait(smem_u32(&empty_bar[s]), pphase);
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
             const uint32_t a_stage = ring_base + s * stage_bytes;
             mbar_arrive_expect_tx(smem_u32(&full_bar[s]), A_STAGE_BYTES + (resident ? 0 : Cfg::B_STAGE_BYTES));
             tma_load_2d(a_stage, &tm_, kb * BK, m0, smem_u32(&full_bar[s]));
-            if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
+            if (!resident) bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * w_kb_stride, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
           }
         }
       }
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
           }
         }
       }
-      const uint8_t* wtile = Wbase + (size_t)n_tile * nkb * Cfg::B_STAGE_BYTES;
+      const uint8_t* wtile = wtile_of(n_tile);
       int tap = 0, ch = c * 8;  // conv: this thread's (tap, channel) for k0 = kb*64 + c*8, advanced without divisions
       while (conv && ch >= p.Cin) { ch -= p.Cin; ++tap; }
       for (int kb = 0; kb < nkb; ++kb) {
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
         const uint32_t a_stage = ring_base + s * stage_bytes;
         if (!resident && t == 0) {  // weight tile: one bulk copy of the pre-swizzled [BN x 64] block
           mbar_arrive_expect_tx(smem_u32(&full_bar[s]), Cfg::B_STAGE_BYTES);
-          bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * Cfg::B_STAGE_BYTES, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
+          bulk_g2s(a_stage + A_STAGE_BYTES, wtile + (size_t)kb * w_kb_stride, Cfg::B_STAGE_BYTES, smem_u32(&full_bar[s]));
         }
         if (!conv) {
           const int k0 = kb * BK + c * 8;
@@ -621,7 +625,7 @@ static EncodeTiledFn tma_encoder() {
 }
 
 template <int BN, bool EXT, bool TMA>
-static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename TmaSel<TMA>::type& tmap) {
+static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename TmaSel<TMA>::type& tmap, int wsplit) {
   using Cfg = GemmCfg<BN>;
   constexpr int MAX_SMEM = 222 * 1024;  // + ~4.3 KB static (bias, barriers) <= 227 KB
   static bool attr_set = false;
@@ -666,7 +670,7 @@ static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename Tma
     ext.gate = g.gate; ext.add16 = g.add16; ext.out_pre16 = g.out_pre16; ext.row_scale = g.row_scale;
     ext.gate_mode = g.gate_mode; ext.ld_gate = g.ld_gate; ext.rows_per_scale = g.rows_per_scale; ext.conv_full = g.conv_full;
   }
-  gemm_tc_kernel<BN, EXT, TMA><<<grid, GEMM_THREADS, smem, st>>>(core, ext, tmap, (int)tiles, res_stages);
+  gemm_tc_kernel<BN, EXT, TMA><<<grid, GEMM_THREADS, smem, st>>>(core, ext, tmap, (int)tiles, res_stages, wsplit);
   return (int)cudaGetLastError();
 }
 
@@ -698,12 +702,12 @@ static bool make_a_tensor_map(const MstGemm& g, CUtensorMap* tmap) {
 }
 
 template <int BN>
-static int launch_gemm(const MstGemm& g, cudaStream_t st) {
+static int launch_gemm(const MstGemm& g, cudaStream_t st, int wsplit = 0) {
   const bool ext = g.out_pre16 || g.gate || g.add16 || g.row_scale || g.conv_full;
   alignas(64) CUtensorMap tmap;
   const bool tma = make_a_tensor_map(g, &tmap);
-  if (ext) return tma ? launch_gemm_ext<BN, true, true>(g, st, tmap) : launch_gemm_ext<BN, true, false>(g, st, TmaNone{});
-  return tma ? launch_gemm_ext<BN, false, true>(g, st, tmap) : launch_gemm_ext<BN, false, false>(g, st, TmaNone{});
+  if (ext) return tma ? launch_gemm_ext<BN, true, true>(g, st, tmap, wsplit) : launch_gemm_ext<BN, true, false>(g, st, TmaNone{}, wsplit);
+  return tma ? launch_gemm_ext<BN, false, true>(g, st, tmap, wsplit) : launch_gemm_ext<BN, false, false>(g, st, TmaNone{}, wsplit);
 }
 
 // ---------------------------------------------------------------- weight packing (tile-blocked, pre-swizzled)
@@ -823,7 +827,21 @@ extern "C" int mst_gemm(const MstGemm* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // the tile width is a property of the packed weight (N here must be the n_pad it was packed with)
   switch (tile_n_for(g->N)) {
-    case 256: return launch_gemm<256>(*g, st);
+    case 256: {
+      // Small M (the training step's batch-8 GEMMs: 64 row tiles): 256-wide tiles would occupy fewer than half of the SMs.  Run
+      // the same packed weights as 128-wide halves (twice the CTAs, half the work each): the kernel addresses half h of a packed
+      // 256-row block directly, no re-packing.
+      static int sms = 0;
+      if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+      }
+      const long long tiles256 = (long long)((g->M + BM - 1) / BM) * (g->N / 256);
+      if (tiles256 * 2 <= sms) return launch_gemm<128>(*g, st, 1);
+      return launch_gemm<256>(*g, st);
+    }
     case 128: return launch_gemm<128>(*g, st);
     case 64: return launch_gemm<64>(*g, st);
     case 32: return launch_gemm<32>(*g, st);

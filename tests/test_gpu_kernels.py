@@ -19,7 +19,7 @@ def _rand(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 16, 64), (256, 32, 128), (300, 64, 256), (1024, 384, 128),
-                                   (4096, 256, 256), (2048, 1024, 256), (2048, 256, 1024), (777, 768, 256), (128, 512, 512)])
+                                   (4096, 256, 256), (2048, 1024, 256), (2048, 256, 1024), (777, 768, 256), (128, 512, 512), (8192, 256, 256), (20000, 512, 128)])
 def test_gemm_plain(M, N, K):
     ops = _ops()
     A = _rand(M, K, seed=1).bfloat16().cuda()
