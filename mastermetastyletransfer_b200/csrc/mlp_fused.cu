@@ -42,6 +42,12 @@ MST_DEVINL void ml_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint3
 MST_DEVINL void ml_tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// [32 fp32 columns x 32 rows] box of a matrix, global -> shared memory (mbarrier completion)
+MST_DEVINL void ml_tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap),
+               "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
 MST_DEVINL void ml_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 MST_DEVINL void ml_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 MST_DEVINL void ml_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -81,7 +87,7 @@ struct MlpCfg {
 // them before the first GELU write of the next tile (x_full -> fc1 MMA -> acc1_full).
 template <int C, bool PRE>
 __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles,
-                                                                  const __grid_constant__ CUtensorMap tm_out, const int tma_out) {
+                                                                  const __grid_constant__ CUtensorMap tm_out, const int tma_out, const int res_tma) {
   using Cfg = MlpCfg<C>;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int ABUF = PRE ? 1 : Cfg::ABUF;
@@ -90,6 +96,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
   __shared__ uint64_t a_full[2], a_empty[2], acc2_full, acc2_empty, x_full;
   __shared__ uint64_t w_full[NSTG], w_empty[NSTG];
   __shared__ uint64_t acc1_full[2], acc1_empty[2], hs_full[2], hs_empty[2];
+  __shared__ uint64_t res_bar[ML_EPI_WARPS];  // res_tma: the warp's residual block has landed in its slab
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float b2_s[256];
 
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&a_full[b]), ML_PROD_WARPS * 32); mbar_init(smem_u32(&a_empty[b]), 1); }
+    for (int w = 0; w < ML_EPI_WARPS; ++w) mbar_init(smem_u32(&res_bar[w]), 1);
     mbar_init(smem_u32(&acc2_full), 1);
     mbar_init(smem_u32(&acc2_empty), ML_EPI_WARPS);
     mbar_init(smem_u32(&x_full), ML_EPI_WARPS);
@@ -307,6 +315,17 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
       }
     };
+    // res_tma (C = 128, in-place residual stream): the warp's [32 rows x 32 columns] residual block comes through the TMA engine
+    // into the warp's output slab (free between its tensor store of tile t and its staging of tile t+1) instead of four
+    // row-per-lane 256-bit loads per thread (32 lines per instruction: a quarter of the LSU's width); the load of tile t+1 is
+    // issued as soon as the store of tile t has read the slab.
+    const uint32_t res_slab = hs_base + (uint32_t)warp * 4096u;
+    if constexpr (PRE && C == 128) {
+      if (res_tma && lane == 0 && (int)blockIdx.x < num_tiles) {
+        ml_arrive_expect_tx(smem_u32(&res_bar[warp]), 4096u);
+        ml_tma_load_2d(res_slab, &tm_out, part * CPW, (int)blockIdx.x * 128 + quad * 32, smem_u32(&res_bar[warp]));
+      }
+    }
     int lt = 0;
 #ifdef MST_MLP_PROF
     long long tA = 0, tGw = 0, tG = 0, tHw = 0, tFw = 0, tF = 0, t_all = clock64(), tm = 0, tAw = 0, tAld = 0, tAres = 0, tAst = 0, tm2 = 0;
@@ -354,7 +373,21 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
 #ifdef MST_MLP_PROF
         tm2 = clock64();
 #endif
-        fetch_res(0);
+        bool res_from_slab = false;
+        if constexpr (C == 128) res_from_slab = res_tma != 0;
+        if (res_from_slab) {
+          if (lane == 0) mbar_wait(smem_u32(&res_bar[warp]), lt & 1);
+          __syncwarp();
+          const uint32_t srow = res_slab + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(rr[4 * q]), "=f"(rr[4 * q + 1]), "=f"(rr[4 * q + 2]), "=f"(rr[4 * q + 3])
+                         : "r"(srow + ((uint32_t)(q ^ (lane & 7)) << 4))
+                         : "memory");
+        } else {
+          fetch_res(0);
+        }
         if (lane == 0) {
           mbar_wait(smem_u32(&acc1_full[pbuf]), (a1p >> 1) & 1);
           if (C == 256) {  // X shares its buffer with O: both projection chunks must have finished reading O before X is written
@@ -560,6 +593,13 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           if (lane == 0) {
             ml_tma_store_2d(&tm_out, slab, n, tile * 128 + quad * 32);
             ml_bulk_commit();
+            if constexpr (C == 128) {
+              if (res_tma && tile + (int)gridDim.x < num_tiles) {  // next tile's residual block into the same slab, once the store has read it
+                ml_bulk_wait_read();
+                ml_arrive_expect_tx(smem_u32(&res_bar[warp]), 4096u);
+                ml_tma_load_2d(slab, &tm_out, n, (tile + (int)gridDim.x) * 128 + quad * 32, smem_u32(&res_bar[warp]));
+              }
+            }
           }
         } else if (p.out_f32) {
           float* op = p.out_f32 + (long long)row * p.ld_out32 + n;
@@ -714,7 +754,11 @@ static int launch_mlp(const MstMlp& p, cudaStream_t st) {
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
   }
-  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles, tmap, tma_out);
+  // residual through TMA as well when it is the in-place stream the tensor map already describes (C = 128: one block per warp)
+  static int res_allow = -1;
+  if (res_allow < 0) { const char* e = getenv("MST_MLP_TMA_RES"); res_allow = e ? atoi(e) : 1; }
+  const int res_tma = (PRE && C == 128 && tma_out && res_allow && p.res == p.out_f32 && p.ld_res == p.ld_out32 && !p.mul) ? 1 : 0;
+  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles, tmap, tma_out, res_tma);
   return (int)cudaGetLastError();
 }
 
