@@ -89,12 +89,16 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
   // (256 clk per 16 KB k-block), a shared-memory A operand costs 32 clk per MMA (tools/micro/umma_rate.cu).  Per k-block:
   // RR = 8 (N = 32): 32 x 16 + 256 = 768 clk against 32 x 40 = 1280; RR = 4 (N = 64): 768 against 768; RR = 2 (N = 128): 8 x 64
   // + 256 = 768 against 8 x 64 = 512 (the N = 128 MMA is at its math floor with both operands in shared memory).
-  constexpr bool TS = RR >= 4;
+  constexpr bool TS = RR >= 8;
+  // accumulators: the TMEM k-block slots take columns 256..511, so the TMEM path has ONE accumulator buffer (the epilogue's drain is
+  // not overlapped); with the weights read from shared memory both halves of TMEM are accumulators and unit u+1 is issued while
+  // the epilogue drains unit u.  At N = 64 the two forms cost the same per k-block (768 clk, see above): the double buffer decides.
+  constexpr int NACC = TS ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t row_full[CM_MAX_RING], row_free[CM_MAX_RING];
   __shared__ uint64_t w_full[CM_WSTAGES], w_empty[CM_WSTAGES];
   __shared__ uint64_t a_ready[CM_TSTAGES], a_free[CM_TSTAGES];
-  __shared__ uint64_t acc_full, acc_empty;
+  __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform for ptxas
@@ -118,8 +122,10 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       mbar_init(smem_u32(&a_ready[s]), 1);
       mbar_init(smem_u32(&a_free[s]), 2);
     }
-    mbar_init(smem_u32(&acc_full), 2);
-    mbar_init(smem_u32(&acc_empty), CM_EPI_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 2);
+      mbar_init(smem_u32(&acc_empty[b]), CM_EPI_WARPS);
+    }
     mbar_fence_init();
   }
   if (warp == CM_MMA_WARP) {
@@ -254,7 +260,9 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
     if (TS && mw == 0 && stages_total > 0) copy_stage();
     for (int u = u_begin; u < u_end; ++u, ++ucount) {
       if (g.prof) t0 = clock64();
-      mbar_wait(smem_u32(&acc_empty), (uint32_t)((ucount & 1) ^ 1));
+      const int buf = ucount % NACC, use = ucount / NACC;
+      const uint32_t dbuf = (uint32_t)(buf * CM_ACC_COLS);
+      mbar_wait(smem_u32(&acc_empty[buf]), (uint32_t)((use & 1) ^ 1));
       if (g.prof) t_acc += clock64() - t0;
       tc_fence_after();
       for (int sl = 0; sl < g.nslices; ++sl) {
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
                 for (int i = 0; i < RR / 2; ++i) {
                   // + kx pixels = kx operand rows of 128 B (8 address units); k-step = 32 B inside the swizzled row
                   const uint32_t b_lo = rb[i] + (uint32_t)pl * plane16 + (uint32_t)(kx * 8);
-                  const uint32_t d = d_row[i];
+                  const uint32_t d = d_row[i] + dbuf;
                   umma_ts_pred(d, a_tmem, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
                   umma_ts_pred(d, a_tmem + 8, ((uint64_t)desc_hi << 32) | (b_lo + 2), idesc, 1);
                   umma_ts_pred(d, a_tmem + 16, ((uint64_t)desc_hi << 32) | (b_lo + 4), idesc, 1);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
 #pragma unroll
                 for (int i = 0; i < RR / 2; ++i) {
                   const uint32_t b_lo = rb[i] + (uint32_t)pl * plane16 + (uint32_t)(kx * 8);
-                  const uint32_t d = d_row[i];
+                  const uint32_t d = d_row[i] + dbuf;
                   umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, acc);
                   umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | (a_lo + 2), ((uint64_t)desc_hi << 32) | (b_lo + 2), idesc, 1);
                   umma_bf16_pred(d, ((uint64_t)desc_hi << 32) | (a_lo + 4), ((uint64_t)desc_hi << 32) | (b_lo + 4), idesc, 1);
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
         base_slot += rows_per_item;
         if (base_slot >= g.ring) { base_slot -= g.ring; base_phase ^= 1u; }
       }
-      umma_commit_pred(smem_u32(&acc_full));
+      umma_commit_pred(smem_u32(&acc_full[buf]));
     }
     if (g.prof && blockIdx.x == 1 && lane == 0)
       printf("cm prof mma %d: units %d total %lld wait rows %lld a_ready %lld acc_empty %lld\n", mw, ucount, clock64() - t_all, t_rows, t_w, t_acc);
@@ -349,19 +357,20 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       const int b = rest / g.yblocks, y0 = (rest - b * g.yblocks) * g.R;
       const int ch = ct * 128 + quad * 32 + lane;
       const float bias = p.bias ? p.bias[ch] : 0.f;
-      if (lane == 0) mbar_wait(smem_u32(&acc_full), (uint32_t)(ucount & 1));
+      const int buf = ucount % NACC, use = ucount / NACC;
+      if (lane == 0) mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)(use & 1));
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = half * 128 + cc * 32;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + col0, v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * CM_ACC_COLS + col0, v);
         tmem_wait_ld();
         if (cc == 3) {  // accumulator drained by this warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
         }
         const int r = col0 / p.W, x0 = col0 - r * p.W;  // 32 consecutive pixels of one output row (W >= 32)
         bf16* op = out + ((long long)(b * p.H + y0 + r) * p.W + x0) * p.ld_out16 + ch;
