@@ -24,9 +24,11 @@
 //     a lone warp): TWO warps issue, one the even and one the odd rows of the unit -- disjoint accumulator columns, so the
 //     order in which the tensor pipe takes their instructions does not matter.  Warp 0 also issues the copies (one k-block
 //     ahead of its MMAs) and publishes each through an mbarrier (tcgen05.commit) that warp 1 waits on.
-// TMEM: accumulator columns 0..255 (single buffer: the epilogue's drain is not overlapped with the next unit's MMAs), weight
-// k-blocks in columns 256..511.  L2 -> SM traffic per 256 pixels of a 128 -> 128 layer: 288 KB of weights + 110 KB of rows
-// instead of 1152 KB.
+// TMEM: 32-pixel rows (N = 32 MMAs: 16 clk with A in TMEM against 40 from shared memory): accumulator columns 0..255, weight
+// k-blocks in columns 256..511 (one accumulator buffer: the epilogue's drain is not overlapped).  64- and 128-pixel rows: the copy
+// would cost what it saves (768 clk per k-block either way at N = 64), so the weights stay in shared memory, TWO accumulators of
+// 256 columns alternate and unit u+1 is issued while the epilogue drains unit u.  L2 -> SM traffic per 256 pixels of a
+// 128 -> 128 layer: 288 KB of weights + 110 KB of rows instead of 1152 KB.
 //
 //   warps 0-7   epilogue  : TMEM (lane = output channel, column = pixel) -> + bias -> ReLU -> bf16 -> global; a warp's store
 //                           instruction writes 32 consecutive channels of one pixel (64 contiguous bytes)
