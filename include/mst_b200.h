@@ -104,7 +104,7 @@ int mst_conv3x3_band_supported(int N, int Cin, int H, int W);
 int mst_conv3x3_rows(const MstGemm* g, void* stream);
 int mst_conv3x3_rows_supported(int N, int Cin, int H, int W);
 
-/* Channel-major variant for the wide layers (N % 128 == 0, Cin % 64 == 0, W in {32, 64, 128}, H % (256 / W) == 0; decoder.py:25-37
+/* Channel-major variant for the wide layers (N % 128 == 0 or N == 64, Cin % 64 == 0, W in {32, 64, 128}, H % (256 / W) == 0; decoder.py:25-37
  * and VGG conv2_x .. conv4_x, loss.py:23-37): output channels are the MMA's M dimension, the pixels of ONE image row its N
  * dimension, each padded input row is staged once and all nine taps read it through row-shifted descriptors, one streamed
  * weight k-block feeds 256 pixels (conv_cm.cu).  bf16 output only (the folded nearest-x2 upsample is supported); no residual /

@@ -1,4 +1,4 @@
-// 3x3 convolution for the WIDE layers (Cout a multiple of 128, Cin a multiple of 64, W in {32, 64, 128}) on sm_100a:
+// 3x3 convolution for the WIDE layers (Cout a multiple of 128 -- or 64: half-filled operand --, Cin a multiple of 64, W in {32, 64, 128}) on sm_100a:
 // the CNN decoder's 256->128 @32^2 and 128->128 @64^2 layers (codes/decoder.py:25-37) and VGG-19 conv2_x .. conv4_x
 // (codes/loss.py:23-37).  bf16 NHWC in, bf16 NHWC out, fp32 accumulation, zero or reflect padding, optional ReLU, optional nearest-x2
 // upsample of the input folded into the row fetch (decoder.py:27).
@@ -130,6 +130,11 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
     }
     mbar_fence_init();
   }
+  if (p.N < 128) {  // 64 output channels: operand rows 64..127 of every weight stage are zeros
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(CM_WSTAGES * CM_WSTAGE_BYTES) / 16u; i += CM_THREADS)
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(w_base + i * 16u), "r"(0u) : "memory");
+    fence_proxy_async_smem();
+  }
   if (warp == CM_MMA_WARP) {
     tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
@@ -198,6 +203,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
     // =========================== weight streamer ===========================
     if (lane == 0) {
       const bf16* wt = reinterpret_cast<const bf16*>(p.Wt);
+      // a 64-channel layer (decoder.py:37) fills the lower half of every [128 x 64] stage; the upper half stays zero (zeroed once)
+      const uint32_t w_bytes = p.N >= 128 ? (uint32_t)CM_WSTAGE_BYTES : (uint32_t)(p.N * 128);
       int ws = 0;
       uint32_t wphase = 1;
       for (int u = u_begin; u < u_end; ++u) {
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
             for (int pl = 0; pl < PLANES; ++pl) {
               const int kb = (tap * p.Cin + sl * CS + pl * 64) >> 6;
               mbar_wait(smem_u32(&w_empty[ws]), wphase);
-              cm_arrive_expect_tx(smem_u32(&w_full[ws]), CM_WSTAGE_BYTES);
-              cm_bulk_g2s(w_base + ws * CM_WSTAGE_BYTES, wtile + (long long)kb * g.bn * 64, CM_WSTAGE_BYTES, smem_u32(&w_full[ws]));
+              cm_arrive_expect_tx(smem_u32(&w_full[ws]), w_bytes);
+              cm_bulk_g2s(w_base + ws * CM_WSTAGE_BYTES, wtile + (long long)kb * g.bn * 64, w_bytes, smem_u32(&w_full[ws]));
               if (++ws == CM_WSTAGES) { ws = 0; wphase ^= 1; }
             }
           }
@@ -358,7 +365,8 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
       const int ct = u % g.ctiles, rest = u / g.ctiles;
       const int b = rest / g.yblocks, y0 = (rest - b * g.yblocks) * g.R;
       const int ch = ct * 128 + quad * 32 + lane;
-      const float bias = p.bias ? p.bias[ch] : 0.f;
+      const bool ch_ok = ch < p.N;
+      const float bias = (p.bias && ch_ok) ? p.bias[ch] : 0.f;
       const int buf = ucount % NACC, use = ucount / NACC;
       if (lane == 0) mbar_wait(smem_u32(&acc_full[buf]), (uint32_t)(use & 1));
       __syncwarp();
@@ -374,6 +382,7 @@ __global__ void __launch_bounds__(CM_THREADS, 1) conv_cm_kernel(const GemmCore p
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
         }
+        if (!ch_ok) continue;  // (warp-uniform: a quadrant is 32 channels)
         const int r = col0 / p.W, x0 = col0 - r * p.W;  // 32 consecutive pixels of one output row (W >= 32)
         bf16* op = out + ((long long)(b * p.H + y0 + r) * p.W + x0) * p.ld_out16 + ch;
 #pragma unroll
@@ -407,7 +416,8 @@ static int cm_num_sms() {
 static int cm_slice(int Cin, int W) { return (Cin % 128 == 0 && W <= 64) ? 128 : 64; }
 
 static bool cm_shape_ok(int N, int Cin, int H, int W) {
-  if (N <= 0 || N % 128 != 0 || Cin <= 0 || Cin % 64 != 0) return false;
+  if (N <= 0 || (N % 128 != 0 && N != 64) || Cin <= 0 || Cin % 64 != 0) return false;
+  if (N == 64 && Cin % 128 != 0) return false;  // 64 -> 64 / 64 -> 32 layers: the row-streaming kernel (conv_band.cu) is faster (49 vs 62 us)
   if (W != 32 && W != 64 && W != 128) return false;
   // 32-pixel rows make N = 32 MMAs, which are bound by the shared-memory read of their 4 KB weight operand (40 clk for 16 clk of
   // math): measured slower than the gathered GEMM's 256-wide tiles except for a single 128-channel tile (decoder.py:25)
@@ -430,7 +440,7 @@ static bool plan_cm(const MstGemm& g, CmGeom& out) {
   out.ring = (int)ring;
   out.nslices = g.Cin / CS;
   out.yblocks = g.H / out.R;
-  out.ctiles = g.N / 128;
+  out.ctiles = (g.N + 127) / 128;
   const int B = g.M / (g.H * g.W);
   out.units = B * out.yblocks * out.ctiles;
   const int sms = cm_num_sms();
@@ -438,7 +448,7 @@ static bool plan_cm(const MstGemm& g, CmGeom& out) {
   out.bn = mst_gemm_tile_n(g.N);
   out.nkb = g.k_pad / 64;
   { const char* e = getenv("MST_CM_PROF"); out.prof = e ? atoi(e) : 0; }
-  return out.bn >= 128;
+  return out.bn >= 128 || (g.N == 64 && out.bn == 64);
 }
 
 template <int CS, int RR>

@@ -110,7 +110,8 @@ def test_conv3x3(B, H, W, Cin, Cout, pad, up, relu, impl):
     (2, 128, 128, 128, 128, "zeros", False),   # VGG conv2_2 shape, no activation: 64-channel slices because W > 64
     (2, 64, 64, 256, 256, "zeros", True),      # VGG conv3_x: two output-channel tiles out of a 256-wide packed weight
     (5, 64, 64, 512, 512, "zeros", True),      # four slices, four channel tiles, units not a multiple of the SM count
-    (1, 8, 64, 64, 128, "reflect", False), (7, 16, 64, 128, 384, "zeros", True)])
+    (1, 8, 64, 64, 128, "reflect", False), (7, 16, 64, 128, 384, "zeros", True),
+    (3, 64, 64, 128, 64, "reflect", True), (2, 64, 64, 256, 64, "zeros", False)])   # 64 output channels: half-filled weight stages (decoder.py:37)
 def test_conv3x3_channel_major(B, H, W, Cin, Cout, pad, relu):
     """conv_cm.cu (output channels = MMA M, one image row = MMA N, row-shifted taps) vs F.conv2d on the bf16-rounded operands;
     'auto' must pick it for these shapes, and its result must equal the gathered implicit GEMM's to bf16 rounding."""
