@@ -99,7 +99,7 @@ class SwinEncoderWeights:
 
 
 def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W: int, shift: int, tag: str,
-                ln1_done: bool = False):
+                ln1_done: bool = False, out16: Optional[torch.Tensor] = None):
     """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place).
     ln1_done: the producer of x32 already wrote LN1(x) into the block's `ln` buffer (patch embedding)."""
     C, heads = bw["C"], bw["heads"]
@@ -116,11 +116,11 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
         ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
                              3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
     if FUSE_PROJ_MLP:  # x1 = x + proj(o); x = x1 + mlp(LN2(x1)): one kernel, LN2(x1) and the hidden activation stay on chip
-        ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"])
+        ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, out_bf16=out16, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"])
         return
     ops.gemm(o, bw["proj"], T, res=x32, out_f32=x32)
     ops.layernorm(x32, bw["n2w"], bw["n2b"], ln, T, C)
-    ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32)  # fc1 + GELU + fc2 + residual, hidden kept on chip
+    ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32, out_bf16=out16)  # fc1 + GELU + fc2 + residual, hidden kept on chip
 
 
 def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor]):
@@ -146,9 +146,8 @@ def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torc
     x2 = out32.view(T2, 256)
     ops.gemm(pm, w.pm_red, T2, out_f32=x2)
     _swin_block(w.blocks["3.0"], x2, ws_, Bt, P2, P2, 0, "sw2_")
-    _swin_block(w.blocks["3.1"], x2, ws_, Bt, P2, P2, 3, "sw2_")
-    if out16 is not None:
-        ops.cast_bf16(x2, out16.view(T2, 256))
+    # the bf16 copy of the features (the style transformer's first operands) comes out of the last block's MLP epilogue
+    _swin_block(w.blocks["3.1"], x2, ws_, Bt, P2, P2, 3, "sw2_", out16=out16.view(T2, 256) if out16 is not None else None)
 
 
 # --------------------------------------------------------------------------------------------
@@ -232,7 +231,7 @@ def _mlp_residual(x16, x32, fc, T, ws_: Workspace, out16):
 def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs32: torch.Tensor, k: int, ws_: Workspace,
                               B: int, H: int, W: int, win: int, shift: int, heads: int,
                               out32: torch.Tensor, out16: Optional[torch.Tensor] = None, *, processed_key: bool = True,
-                              key_in_after_linear: bool = True, exclude_mlp: bool = False):
+                              key_in_after_linear: bool = True, exclude_mlp: bool = False, fs16_in: Optional[torch.Tensor] = None):
     """Fc, Fs fp32 [B,H,W,C] -> out32 fp32 [B,H,W,C] (+ bf16 copy for the CNN decoder).
     Follows StyleTransformer.forward (:1229-1245) -> StyleEncoder.forward (:855-882) ->
     StyleDecoder.forward (:1045-1059,1123-1128).
@@ -272,8 +271,11 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
     # (as residual sources and operands) and writes the work buffers; later layers read what the previous one wrote.  (Four fp32
     # and two bf16 copies of a [T, C] map used to open every call: ~70 us of a 2.3 ms step at batch 32.)
     fc_in, fs_in = fc32.reshape(T, C), fs32.reshape(T, C)
-    fs16 = ws_.bf16("st_fs16", T, C)
-    ops.cast_bf16(fs_in, fs16)
+    if fs16_in is not None:  # the caller already holds bf16(Fs) (the Swin encoder writes it from its last MLP epilogue)
+        fs16 = fs16_in.reshape(T, C)
+    else:
+        fs16 = ws_.bf16("st_fs16", T, C)
+        ops.cast_bf16(fs_in, fs16)
     x_src, key_src, scale_src, shift_src = fc_in, fs_in, fs_in, fs_in   # fp32 residual sources of the next update of each stream
     key16_cur = fs16                                                    # bf16 Key as the attentions read it
     first = True                                                        # Scale16 = Shift16 = fs16 until the first Scale / Shift pass

@@ -157,12 +157,13 @@ class MasterStyleTransferModel(nn.Module):
             ws = workspace_of(self, dev)
             Hf = S // 8
             feats = ws.f32("feats", 2 * B, Hf, Hf, 256)
-            engine.swin_encode(ew, [content_image.float().contiguous(), style_image.float().contiguous()], ws, S, feats, None)
+            feats16 = ws.bf16("feats16", 2 * B, Hf, Hf, 256)
+            engine.swin_encode(ew, [content_image.float().contiguous(), style_image.float().contiguous()], ws, S, feats, feats16)
             fcs32 = ws.f32("fcs32", B, Hf, Hf, 256)
             fcs16 = ws.bf16("fcs16", B, Hf, Hf, 256)
             engine.style_transformer_forward(sw, feats[:B], feats[B:], int(transformer_layer_count), ws, B, Hf, Hf,
                                              st._cfg["window"][0], st._cfg["shift"][0], st._cfg["heads"], fcs32, fcs16,
-                                             **st.engine_flags())
+                                             fs16_in=feats16[B:], **st.engine_flags())
             if int(transformer_layer_count) == 0:
                 from . import ops
                 ops.cast_bf16(fcs32.view(-1, 256), fcs16.view(-1, 256))

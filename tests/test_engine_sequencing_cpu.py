@@ -85,6 +85,8 @@ def test_full_model_forward_passes_the_configuration_to_the_engine(monkeypatch, 
 
     def swin_encode(w, imgs, ws_, S, out32, out16):
         out32.copy_(torch.cat([O.swin_encoder(w.sd, i, "") for i in imgs], 0))
+        if out16 is not None:  # the encoder also hands the style transformer the bf16 copy of the features
+            out16.copy_(out32)
 
     def cnn_decoder_forward(w, x16, ws_, B, H, W, out):
         out.copy_(O.cnn_decoder(w.sd, x16.float().view(B, H, W, 256).permute(0, 3, 1, 2), "decoder."))
