@@ -11,8 +11,8 @@ $BENCH > gpurun_out/r2_plain_bench.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches_bench_b32_256.csv $BENCH > gpurun_out/r2_ncu_bench.log 2>&1
 python tools/prof_forward.py > gpurun_out/r2_plain_forward.log 2>&1 || exit 1
 ncu --metrics $M --clock-control none -k "$K" --csv --log-file gpurun_out/r2_forward_metrics_b32_256.csv python tools/prof_forward.py > gpurun_out/r2_ncu_forward.log 2>&1
-# one representative launch per family from the THIRD forward (per forward: 9 mlp_fused, 6 attn_fused, 8 gemm_tc, 4 conv_cm, 4 conv_rows)
-for spec in "mlp_c128_pre:mlp_fused:18" "mlp_c256_pre:mlp_fused:22" "attn_fused_c256_ws8:attn_fused:16" "gemm_conv128to64_tma:gemm_tc:23" "conv_cm_128to128:conv_cm:9" "attn_core_ws8:attn_core:4" "conv_rows_32ch:conv_rows:10"; do
+# one representative launch per family from the THIRD forward (per forward: 9 mlp_fused, 6 attn_fused, 8 gemm_tc, 5 conv_cm, 4 conv_rows)
+for spec in "mlp_c128_pre:mlp_fused:18" "mlp_c256_pre:mlp_fused:22" "attn_fused_c256_ws8:attn_fused:16" "conv_cm_128to128:conv_cm:11" "conv_cm_128to64:conv_cm:14" "attn_core_ws8:attn_core:4" "conv_rows_32ch:conv_rows:10"; do
   label=${spec%%:*}; rest=${spec#*:}; name=${rest%%:*}; skip=${rest##*:}
   ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -f -o /tmp/one_$label python tools/prof_forward.py > /dev/null 2>&1
   python tools/ncu_report_summary.py /tmp/one_$label.ncu-rep 0 > gpurun_out/r2_ncu_full_${label}.txt 2>&1
