@@ -281,6 +281,13 @@ int mst_patch_embed_ln(const float* img, const float* w, const float* b, const f
  *   `np.clip(img * 255, 0, 255).astype(np.uint8)` (truncation) -- bit-exact.  W % 4 == 0. */
 int mst_images_u8_to_nchw(const uint8_t* src, float* dst, int B, int H, int W, const float* mean3, const float* std3, void* stream);
 int mst_images_nchw_to_u8(const float* src, uint8_t* dst, int B, int H, int W, void* stream);
+/* mst_patch_embed_ln with mst_images_u8_to_nchw folded into its image loads: img_u8 uint8 [B,S,S,3]; mean3 / std3 as above.  The
+ * results equal mst_images_u8_to_nchw followed by mst_patch_embed_ln(exact = 0) bit for bit (same tcgen05 kernel, same fp32 image
+ * values), without the fp32 NCHW image in HBM.  S % 16 == 0 (mst_patch_embed_ln_u8_supported), else MST_ERR_UNSUPPORTED. */
+int mst_patch_embed_ln_u8(const uint8_t* img_u8, const float* mean3, const float* std3, const float* w, const float* b,
+                          const float* gamma, const float* beta, float* x, const float* gamma1, const float* beta1, mst_bf16* y16,
+                          int B, int S, void* stream);
+int mst_patch_embed_ln_u8_supported(int S);
 /* The reference's training-image transform (codes/get_dataloader.py:30-36: ToPILImage -> Resize((512,512)) -> RandomCrop((256,256))
  * -> ToTensor -> Normalize) on a decoded uint8 [H, W, 3] image, one kernel: out fp32 [3, ch, cw] = the (top, left) crop of Pillow's
  * antialiased bilinear resize, /255, normalised (mean3 / std3 host pointers, NULL = ToTensor only).  xmin / xcnt [out_w], xk

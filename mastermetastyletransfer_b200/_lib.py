@@ -131,6 +131,8 @@ SYMBOLS = {
     "mst_pack_bf16_matrix": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "mst_patch_embed": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mst_patch_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mst_patch_embed_ln_u8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mst_patch_embed_ln_u8_supported": (_I, [_I]),
     "mst_cast_bf16": (_I, [_P, _P, _Z, _P]),
     "mst_images_u8_to_nchw": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "mst_images_nchw_to_u8": (_I, [_P, _P, _I, _I, _I, _P]),

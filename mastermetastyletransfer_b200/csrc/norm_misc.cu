@@ -594,7 +594,8 @@ extern "C" int mst_instnorm_apply_affine(const float* x, const float* mean, cons
 
 namespace mst {
 int patch_embed_tc_try(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x, const float* gamma1,
-                       const float* beta1, bf16* y16, int B, int S, cudaStream_t st, bool& handled);  // patch_embed_tc.cu
+                       const float* beta1, bf16* y16, int B, int S, cudaStream_t st, bool& handled, const uint8_t* img8, const float* mean3,
+                       const float* std3);  // patch_embed_tc.cu
 }
 
 extern "C" int mst_patch_embed(const float* img, const float* w, const float* b, const float* gamma, const float* beta,
@@ -610,7 +611,8 @@ extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float*
   const long long total = (long long)B * (S / 4) * (S / 4);
   if (!exact) {  // tcgen05 kernel (patch_embed_tc.cu): 128-token tiles, both LayerNorms thread-local
     bool handled = false;
-    const int rc = mst::patch_embed_tc_try(img, w, b, gamma, beta, x, gamma1, beta1, reinterpret_cast<bf16*>(y16), B, S, (cudaStream_t)stream, handled);
+    const int rc = mst::patch_embed_tc_try(img, w, b, gamma, beta, x, gamma1, beta1, reinterpret_cast<bf16*>(y16), B, S, (cudaStream_t)stream, handled,
+                                           nullptr, nullptr, nullptr);
     if (handled) return rc;
   }
   int dev = 0, sms = 148;
@@ -633,6 +635,21 @@ extern "C" int mst_patch_embed_ln(const float* img, const float* w, const float*
   if (e != cudaSuccess) return (int)e;
   if (y16) return mst_layernorm(x, gamma1, beta1, y16, (int)total, 128, stream);
   return 0;
+}
+
+extern "C" int mst_patch_embed_ln_u8_supported(int S) { return S > 0 && S % 16 == 0; }
+
+extern "C" int mst_patch_embed_ln_u8(const uint8_t* img_u8, const float* mean3, const float* std3, const float* w, const float* b,
+                                     const float* gamma, const float* beta, float* x, const float* gamma1, const float* beta1,
+                                     mst_bf16* y16, int B, int S, void* stream) {
+  if (!img_u8 || !w || !b || !gamma || !beta || !x || B <= 0 || S <= 0) return MST_ERR_BAD_ARG;
+  if ((mean3 == nullptr) != (std3 == nullptr)) return MST_ERR_BAD_ARG;
+  if (y16 && (!gamma1 || !beta1)) return MST_ERR_BAD_ARG;
+  if (!mst_patch_embed_ln_u8_supported(S)) return MST_ERR_UNSUPPORTED;
+  bool handled = false;
+  const int rc = mst::patch_embed_tc_try(nullptr, w, b, gamma, beta, x, gamma1, beta1, reinterpret_cast<bf16*>(y16), B, S, (cudaStream_t)stream, handled,
+                                         img_u8, mean3, std3);
+  return handled ? rc : MST_ERR_BAD_ARG;  // not handled: misaligned pointers
 }
 
 extern "C" int mst_upsample2x_nhwc(const mst_bf16* x, mst_bf16* y, int B, int H, int W, int C, void* stream) {

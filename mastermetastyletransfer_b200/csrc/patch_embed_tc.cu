@@ -32,12 +32,22 @@ constexpr int PT_KB_BYTES = 128 * 128;                      // one [128 rows x 6
 constexpr int PT_A_BYTES = 2 * PT_KB_BYTES;                 // hi | lo
 constexpr int PT_SMEM_BYTES = 1024 + PT_NBUF * PT_A_BYTES + PT_A_BYTES;  // the A buffers + the weight tile (W | W)
 
+// uint8 [B,S,S,3] image input (img8 != nullptr): the producers read the interleaved bytes and apply ToTensor + Normalize themselves
+// (the values images_u8_to_nchw_kernel would have written, norm_misc.cu), so the fp32 NCHW image never exists in HBM.
+struct PeU8 {
+  const uint32_t* img8;
+  float mean[3], sd[3];
+  int normalize;
+};
+
 __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                                       const float* __restrict__ bias, const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta, float* __restrict__ out,
                                                                       const float* __restrict__ gamma1, const float* __restrict__ beta1,
-                                                                      bf16* __restrict__ y16, int S, int n_tiles, long long total) {
+                                                                      bf16* __restrict__ y16, int S, int n_tiles, long long total,
+                                                                      PeU8 u8) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float lut[3][256];  // u8 images: ((v / 255) - mean_c) / std_c for every byte value, in images_u8_to_nchw's operation order
   __shared__ uint64_t a_full[PT_NBUF], a_empty[PT_NBUF], acc_full[PT_NBUF], acc_empty[PT_NBUF];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float prm[5][128];  // bias, gamma, beta, gamma1, beta1
@@ -60,6 +70,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
     prm[0][i] = bias[i]; prm[1][i] = gamma[i]; prm[2][i] = beta[i];
     prm[3][i] = y16 ? gamma1[i] : 0.f; prm[4][i] = y16 ? beta1[i] : 0.f;
   }
+  if (u8.img8)
+    for (int i = threadIdx.x; i < 3 * 256; i += PT_THREADS) {
+      const int c = i >> 8;
+      float v = __fdiv_rn((float)(i & 255), 255.0f);
+      const float mc = c == 0 ? u8.mean[0] : c == 1 ? u8.mean[1] : u8.mean[2], sc = c == 0 ? u8.sd[0] : c == 1 ? u8.sd[1] : u8.sd[2];
+      if (u8.normalize) v = __fdiv_rn(__fsub_rn(v, mc), sc);
+      lut[c][i & 255] = v;
+    }
   // weight tile: row n (output channel), k-block 0 = W[n][0..47] then zeros, k-block 1 the same again (multiplies the lo parts)
   for (int i = threadIdx.x; i < 128 * 16; i += PT_THREADS) {
     const int n = i >> 4, c = i & 15;  // 16-byte chunk c of the row's 2 x 64 k
@@ -108,12 +126,33 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
         const int px = (int)(tok - rowi * P);
         const long long b = rowi / P;
         const int py = (int)(rowi - b * P);
-        const float* p0 = img + (b * 3 * S + (long long)py * 4) * S + px * 4;
         float4 v[12];
+        if (u8.img8) {  // 4 rows x 12 bytes (4 pixels x RGB) -> the same 12 float4 (channel, row)
+          const uint32_t* q0 = u8.img8 + ((b * S + (long long)py * 4) * S * 3) / 4 + px * 3;
+          uint32_t wv[12];
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+          for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-          for (int ky = 0; ky < 4; ++ky) v[ci * 4 + ky] = *reinterpret_cast<const float4*>(p0 + ci * plane + (long long)ky * S);
+            for (int e = 0; e < 3; ++e) wv[ky * 3 + e] = __ldg(q0 + (long long)ky * (S * 3 / 4) + e);
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              float f[4];
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) {
+                const int byte = 3 * kx + ci;
+                f[kx] = lut[ci][(wv[ky * 3 + (byte >> 2)] >> ((byte & 3) * 8)) & 255u];
+              }
+              v[ci * 4 + ky] = make_float4(f[0], f[1], f[2], f[3]);
+            }
+        } else {
+          const float* p0 = img + (b * 3 * S + (long long)py * 4) * S + px * 4;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) v[ci * 4 + ky] = *reinterpret_cast<const float4*>(p0 + ci * plane + (long long)ky * S);
+        }
 #pragma unroll
         for (int j = 0; j < 12; ++j) {  // k = 4 j .. 4 j + 3: half of 16-byte chunk j >> 1
           const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
@@ -266,14 +305,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
 }
 
 // Called first by mst_patch_embed_ln (norm_misc.cu); handled = false leaves the call to the other kernels.
+// img8 != nullptr: uint8 [B,S,S,3] images with mean3 / std3 (host floats; mean3 == nullptr stops after / 255) instead of img.
 int patch_embed_tc_try(const float* img, const float* w, const float* b, const float* gamma, const float* beta, float* x,
-                       const float* gamma1, const float* beta1, bf16* y16, int B, int S, cudaStream_t st, bool& handled) {
+                       const float* gamma1, const float* beta1, bf16* y16, int B, int S, cudaStream_t st, bool& handled,
+                       const uint8_t* img8, const float* mean3, const float* std3) {
   handled = false;
   static int allow = -1;
   if (allow < 0) { const char* e = getenv("MST_PATCH_EMBED_TC"); allow = e ? atoi(e) : 1; }  // 0: the mma.sync kernel (experiments)
-  if (!allow || S % 16 != 0) return 0;  // 16-byte image loads: px * 4 floats at 16-byte alignment needs S % 4; rows of S floats: S % 4
-  if ((reinterpret_cast<uintptr_t>(img) & 15) || (reinterpret_cast<uintptr_t>(x) & 31) || (reinterpret_cast<uintptr_t>(y16) & 31)) return 0;
+  if ((!allow && !img8) || S % 16 != 0) return 0;  // 16-byte image loads: px * 4 floats at 16-byte alignment needs S % 4; rows of S floats: S % 4
+  if ((img8 ? (reinterpret_cast<uintptr_t>(img8) & 3) : (reinterpret_cast<uintptr_t>(img) & 15)) || (reinterpret_cast<uintptr_t>(x) & 31) ||
+      (reinterpret_cast<uintptr_t>(y16) & 31))
+    return 0;
   handled = true;
+  PeU8 u8{};
+  u8.img8 = reinterpret_cast<const uint32_t*>(img8);
+  if (img8 && mean3 && std3) {
+    u8.normalize = 1;
+    for (int c = 0; c < 3; ++c) { u8.mean[c] = mean3[c]; u8.sd[c] = std3[c]; }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(patch_embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
@@ -287,7 +336,7 @@ int patch_embed_tc_try(const float* img, const float* w, const float* b, const f
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  patch_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM_BYTES, st>>>(img, w, b, gamma, beta, x, gamma1, beta1, y16, S, (int)tiles, total);
+  patch_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM_BYTES, st>>>(img, w, b, gamma, beta, x, gamma1, beta1, y16, S, (int)tiles, total, u8);
   return (int)cudaGetLastError();
 }
 

@@ -123,9 +123,12 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
     ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32, out_bf16=out16)  # fc1 + GELU + fc2 + residual, hidden kept on chip
 
 
-def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor]):
-    """imgs: list of [B,3,S,S] fp32 NCHW tensors (content, style) encoded as one batch.
+def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor],
+                u8_norm=None):
+    """imgs: list of [B,3,S,S] fp32 NCHW tensors (content, style) encoded as one batch -- or of uint8 [B,S,S,3] images, converted
+    inside the patch-embedding kernel (u8_norm = (mean, std) of transforms.Normalize, None: ToTensor only).
     out32: fp32 [sum(B), S/8, S/8, 256]; out16: optional bf16 copy."""
+    u8_mean, u8_std = u8_norm if u8_norm is not None else (None, None)
     Bt = sum(int(i.shape[0]) for i in imgs)
     P = S // 4
     x1 = ws_.f32("sw_x1", Bt * P * P, 128)
@@ -135,7 +138,7 @@ def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torc
     for img in imgs:
         b = int(img.shape[0])
         ops.patch_embed(img, w.pe_w, w.pe_b, w.pe_g, w.pe_beta, x1[off * P * P:], b, S,
-                        gamma1=b10["n1w"], beta1=b10["n1b"], y16=ln1[off * P * P:])
+                        gamma1=b10["n1w"], beta1=b10["n1b"], y16=ln1[off * P * P:], u8_mean=u8_mean, u8_std=u8_std)
         off += b
     _swin_block(b10, x1, ws_, Bt, P, P, 0, "sw1_", ln1_done=True)
     _swin_block(w.blocks["1.1"], x1, ws_, Bt, P, P, 3, "sw1_")

@@ -147,9 +147,28 @@ class MasterStyleTransferModel(nn.Module):
         B, _, S, S2 = content_image.shape
         if S != S2 or S % 8:
             raise ValueError("square inputs with S a multiple of 8 only")
+        return self._stylize([content_image.float().contiguous(), style_image.float().contiguous()], B, S, transformer_layer_count, None)
+
+    def forward_u8(self, content_u8: Tensor, style_u8: Tensor, transformer_layer_count: int = 1, normalize=None) -> Tensor:
+        """forward() on decoded uint8 [B,S,S,3] images (test_model.py:39-48's boundary): transforms.ToTensor() and, with
+        normalize = (mean, std), transforms.Normalize are applied inside the patch-embedding kernel's image loads -- the result is
+        bit-identical to forward(images_u8_to_nchw(content), images_u8_to_nchw(style)).  Inference only; S % 16 == 0."""
+        require_cuda(content_u8, style_u8)
+        if (content_u8.dtype != torch.uint8 or style_u8.dtype != torch.uint8 or content_u8.shape != style_u8.shape or content_u8.dim() != 4
+                or content_u8.shape[3] != 3 or content_u8.shape[1] != content_u8.shape[2]):
+            raise ValueError("content and style must both be uint8 [B,S,S,3]")
+        if self.training:
+            raise RuntimeError("forward_u8 is an inference entry point: call model.eval() first")
+        B, S = int(content_u8.shape[0]), int(content_u8.shape[1])
+        from . import ops
+        if not ops.patch_embed_u8_supported(S):
+            raise ValueError("forward_u8: S must be a multiple of 16")
+        return self._stylize([content_u8.contiguous(), style_u8.contiguous()], B, S, transformer_layer_count, normalize)
+
+    def _stylize(self, images, B: int, S: int, transformer_layer_count: int, u8_norm) -> Tensor:
         st = self.style_transformer
         st._check_config()
-        dev = content_image.device
+        dev = images[0].device
         with torch.no_grad():
             ew = packed_weights(self.swin_encoder, engine.SwinEncoderWeights)
             sw = packed_weights(st, engine.StyleTransformerWeights)
@@ -158,7 +177,7 @@ class MasterStyleTransferModel(nn.Module):
             Hf = S // 8
             feats = ws.f32("feats", 2 * B, Hf, Hf, 256)
             feats16 = ws.bf16("feats16", 2 * B, Hf, Hf, 256)
-            engine.swin_encode(ew, [content_image.float().contiguous(), style_image.float().contiguous()], ws, S, feats, feats16)
+            engine.swin_encode(ew, images, ws, S, feats, feats16, u8_norm=u8_norm)
             fcs32 = ws.f32("fcs32", B, Hf, Hf, 256)
             fcs16 = ws.bf16("fcs16", B, Hf, Hf, 256)
             engine.style_transformer_forward(sw, feats[:B], feats[B:], int(transformer_layer_count), ws, B, Hf, Hf,

@@ -378,9 +378,27 @@ def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None, beta=None) -> 
             nbytes=B * T * Cdim * (4.0 + (2.0 if y16 is not None else 0.0) + (4.0 if y32 is not None else 0.0)))
 
 
-def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact: bool = False) -> None:
+def patch_embed_u8_supported(S: int) -> bool:
+    return bool(_lib.lib().mst_patch_embed_ln_u8_supported(int(S)))
+
+
+def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact: bool = False, u8_mean=None, u8_std=None) -> None:
     """tv swin features[0] (conv 4x4/s4 + LayerNorm).  With y16 the first block's norm1 (gamma1/beta1) is fused and its bf16
-    output written to y16.  exact=True forces the fp32 SIMT kernel (the default tensor-core path rounds the weights to bf16)."""
+    output written to y16.  exact=True forces the fp32 SIMT kernel (the default tensor-core path rounds the weights to bf16).
+    A uint8 [B,S,S,3] img is read directly, ToTensor + Normalize(u8_mean, u8_std) applied in the image loads (None: / 255 only)
+    -- the same values images_u8_to_nchw would have written, the same kernel after that."""
+    if img.dtype == torch.uint8:
+        if tuple(img.shape) != (B, S, S, 3) or exact:
+            raise ValueError("patch_embed: uint8 images are [B,S,S,3] and run on the tensor-core kernel only")
+        m = C.cast((C.c_float * 3)(*u8_mean), C.c_void_p) if u8_mean is not None else None
+        sd = C.cast((C.c_float * 3)(*u8_std), C.c_void_p) if u8_mean is not None else None
+        _launch("mst_patch_embed", lambda: _lib.lib().mst_patch_embed_ln_u8(
+            _ptr(img, torch.uint8, "img"), m, sd, _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
+            _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"), _ptr(x, torch.float32, "x"),
+            _ptr(gamma1, torch.float32, "gamma1"), _ptr(beta1, torch.float32, "beta1"), _ptr(y16, torch.bfloat16, "y16"),
+            B, S, _stream()),
+                nbytes=1.0 * B * S * S * 3 + (4.0 + (2.0 if y16 is not None else 0.0)) * B * (S // 4) ** 2 * 128)
+        return
     _launch("mst_patch_embed", lambda: _lib.lib().mst_patch_embed_ln(
         _ptr(img, torch.float32, "img"), _ptr(w, torch.float32, "w"), _ptr(b, torch.float32, "b"),
         _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"), _ptr(x, torch.float32, "x"),

@@ -34,6 +34,18 @@ class GraphedStylizer:
         from .style_transformer import pin_state
         self._pinned = pin_state([self.model])  # packed weights / workspace buffers whose addresses the graph baked in
 
+    def _run_u8(self, c8, s8, o8, normalize: bool) -> None:
+        """uint8 images -> model -> uint8 images.  ToTensor + Normalize run inside the patch-embedding kernel's loads when the
+        model offers forward_u8 for this size (bit-identical to converting first), else as their own two launches."""
+        if hasattr(self.model, "forward_u8") and not self.model.training and ops.patch_embed_u8_supported(self.size):
+            out = self.model.forward_u8(c8, s8, self.layers, normalize=(ops.IMAGENET_MEAN, ops.IMAGENET_STD) if normalize else None)
+        else:
+            mean = ops.IMAGENET_MEAN if normalize else None
+            ops.images_u8_to_nchw(c8, self.content, mean)
+            ops.images_u8_to_nchw(s8, self.style, mean)
+            out = self.model(self.content, self.style, self.layers)
+        ops.images_nchw_to_u8(out, o8)
+
     def _u8(self, normalize: bool = True):
         """The uint8 boundary of test_model.py around the same model, as a second graph: uint8 [B,S,S,3] images (decoded and
         resized, :39-44) -> ToTensor + ImageNet Normalize (:48,:111-125) -> model -> clip(x*255) -> uint8 [B,S,S,3] (:207).
@@ -43,12 +55,9 @@ class GraphedStylizer:
             self.content_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
             self.style_u8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
             self.output_u8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=dev)
-            mean = ops.IMAGENET_MEAN if normalize else None
 
             def run():
-                ops.images_u8_to_nchw(self.content_u8, self.content, mean)
-                ops.images_u8_to_nchw(self.style_u8, self.style, mean)
-                ops.images_nchw_to_u8(self.model(self.content, self.style, self.layers), self.output_u8)
+                self._run_u8(self.content_u8, self.style_u8, self.output_u8, normalize)
 
             with torch.no_grad():
                 self.stream.wait_stream(torch.cuda.current_stream(dev))
@@ -60,8 +69,36 @@ class GraphedStylizer:
                     run()
             torch.cuda.synchronize(dev)
             self._u8_norm = normalize
-            self.__dict__.pop("_stage_u8", None)
         return (self.content_u8, self.style_u8), self.output_u8, self.graph_u8
+
+    def _u8_slots(self, normalize: bool = True):
+        """Two copies of the uint8 graph, each with its own input / output buffers: the pipelined entry point copies host images
+        straight into slot i & 1 and reads the result straight out of it -- no device-to-device staging copies between the
+        copy streams and the graph (three per step with a single graph)."""
+        if getattr(self, "_u8_slots_norm", None) != normalize:
+            B, S, dev = self.batch, self.size, self.device
+            slots = []
+            with torch.no_grad():
+                for _ in range(2):
+                    c8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
+                    s8 = torch.zeros(B, S, S, 3, dtype=torch.uint8, device=dev)
+                    o8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=dev)
+
+                    def run(c8=c8, s8=s8, o8=o8):
+                        self._run_u8(c8, s8, o8, normalize)
+
+                    self.stream.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(self.stream):
+                        run()
+                    self.stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        run()
+                    slots.append((c8, s8, o8, g))
+            torch.cuda.synchronize(dev)
+            self._u8_slot_graphs = slots
+            self._u8_slots_norm = normalize
+        return self._u8_slot_graphs
 
     def load(self, content: torch.Tensor, style: torch.Tensor) -> None:
         self.content.copy_(content, non_blocking=True)
@@ -75,17 +112,15 @@ class GraphedStylizer:
     def stylize_many(self, batches, u8: bool = False, normalize: bool = True):
         """Pipelined host API: `batches` is a sequence of (content_pinned, style_pinned, out_pinned).  Host->device
         copies of batch i+1 and the device->host copy of batch i-1 run on two copy streams while the graph of
-        batch i executes (double-buffered device staging, one small device-to-device copy each way).
-        Returns after every output has landed in its pinned buffer.
+        batch i executes (fp32: double-buffered device staging, one small device-to-device copy each way; uint8: two graphs with
+        their own buffers, no staging copies -- _stylize_many_u8).  Returns after every output has landed in its pinned buffer.
         u8=True: the buffers are uint8 [B,S,S,3] images (see _u8); otherwise normalised fp32 [B,3,S,S] tensors."""
         dev = self.device
         if not hasattr(self, "_h2d"):
             self._h2d, self._d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         if u8:
-            (d_content, d_style), d_output, graph = self._u8(normalize)
-            key = "_stage_u8"
-        else:
-            d_content, d_style, d_output, graph, key = self.content, self.style, self.output, self.graph, "_stage_f32"
+            return self._stylize_many_u8(batches, normalize)
+        d_content, d_style, d_output, graph, key = self.content, self.style, self.output, self.graph, "_stage_f32"
         if not hasattr(self, key):
             setattr(self, key, ([(torch.empty_like(d_content), torch.empty_like(d_style)) for _ in range(2)],
                                 [torch.empty_like(d_output) for _ in range(2)]))
@@ -126,6 +161,47 @@ class GraphedStylizer:
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(out_ready[slot])
                 batches[i][2].copy_(stage_out[slot], non_blocking=True)
+                out_free[slot].record(self._d2h)
+        main.wait_stream(self._d2h)
+        main.synchronize()
+
+    def _stylize_many_u8(self, batches, normalize: bool) -> None:
+        """stylize_many for uint8 images: slot-specific graphs (see _u8_slots), host <-> device copies on the two copy streams."""
+        dev = self.device
+        slots = self._u8_slots(normalize)
+        main = torch.cuda.current_stream(dev)
+        in_ready = [torch.cuda.Event() for _ in range(2)]   # slot inputs filled by the H2D stream
+        in_free = [torch.cuda.Event() for _ in range(2)]    # slot inputs consumed by the graph
+        out_ready = [torch.cuda.Event() for _ in range(2)]  # slot output written by the graph
+        out_free = [torch.cuda.Event() for _ in range(2)]   # slot output drained by the D2H stream
+        self._h2d.wait_stream(main)
+        self._d2h.wait_stream(main)
+        n = len(batches)
+
+        def issue_h2d(i):
+            slot = i & 1
+            with torch.cuda.stream(self._h2d):
+                if i >= 2:
+                    self._h2d.wait_event(in_free[slot])
+                slots[slot][0].copy_(batches[i][0], non_blocking=True)
+                slots[slot][1].copy_(batches[i][1], non_blocking=True)
+                in_ready[slot].record(self._h2d)
+
+        if n:
+            issue_h2d(0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            main.wait_event(in_ready[slot])
+            if i >= 2:
+                main.wait_event(out_free[slot])
+            slots[slot][3].replay()
+            in_free[slot].record(main)
+            out_ready[slot].record(main)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(out_ready[slot])
+                batches[i][2].copy_(slots[slot][2], non_blocking=True)
                 out_free[slot].record(self._d2h)
         main.wait_stream(self._d2h)
         main.synchronize()

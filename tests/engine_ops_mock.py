@@ -89,9 +89,14 @@ def upsample2x_nhwc(x, y, B, H, W, C_):
     y.reshape(-1)[: B * 4 * H * W * C_].view(B, 2 * H, 2 * W, C_).copy_(src.repeat_interleave(2, 1).repeat_interleave(2, 2))
 
 
-def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact=False):
-    """tv swin features[0]: Conv2d(3, 128, 4, stride 4) -> BHWC -> LayerNorm; optional fused norm1 of the first block."""
+def patch_embed(img, w, b, gamma, beta, x, B, S, gamma1=None, beta1=None, y16=None, exact=False, u8_mean=None, u8_std=None):
+    """tv swin features[0]: Conv2d(3, 128, 4, stride 4) -> BHWC -> LayerNorm; optional fused norm1 of the first block.
+    uint8 [B,S,S,3] images: transforms.ToTensor() (+ Normalize(u8_mean, u8_std)) first."""
     P = S // 4
+    if img.dtype == torch.uint8:
+        img = img.permute(0, 3, 1, 2).float().div(255)
+        if u8_mean is not None:
+            img = (img - torch.tensor(u8_mean).view(1, 3, 1, 1)) / torch.tensor(u8_std).view(1, 3, 1, 1)
     t = F.layer_norm(F.conv2d(img[:B], w, b, stride=4).permute(0, 2, 3, 1), (128,), gamma, beta).reshape(B * P * P, 128)
     x[: B * P * P].copy_(t)
     if y16 is not None:

@@ -83,7 +83,8 @@ def test_full_model_forward_passes_the_configuration_to_the_engine(monkeypatch, 
         def __init__(self, sd_):
             self.sd = sd_
 
-    def swin_encode(w, imgs, ws_, S, out32, out16):
+    def swin_encode(w, imgs, ws_, S, out32, out16, u8_norm=None):
+        assert u8_norm is None  # fp32 tensors in: no uint8 conversion asked of the encoder
         out32.copy_(torch.cat([O.swin_encoder(w.sd, i, "") for i in imgs], 0))
         if out16 is not None:  # the encoder also hands the style transformer the bf16 copy of the features
             out16.copy_(out32)

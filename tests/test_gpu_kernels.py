@@ -313,6 +313,34 @@ def test_patch_embed(S, exact):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("S,normalize", [(64, True), (48, True), (128, False)])
+def test_patch_embed_u8_images(S, normalize):
+    """mst_patch_embed_ln_u8: uint8 [B,S,S,3] images with ToTensor + Normalize folded into the image loads == mst_images_u8_to_nchw
+    followed by mst_patch_embed_ln, bit for bit (same kernel, same fp32 image values); S % 16 != 0 is refused."""
+    ops = _ops()
+    B = 3
+    gen = torch.Generator().manual_seed(71)
+    img8 = torch.randint(0, 256, (B, S, S, 3), generator=gen, dtype=torch.uint8).cuda()
+    mean = ops.IMAGENET_MEAN if normalize else None
+    img32 = torch.empty(B, 3, S, S, device="cuda")
+    ops.images_u8_to_nchw(img8, img32, mean)
+    w, b = _rand(128, 3, 4, 4, seed=58, scale=48 ** -0.5).cuda(), (0.05 * _rand(128, seed=59)).cuda()
+    g, beta = (1 + 0.1 * _rand(128, seed=60)).cuda(), (0.1 * _rand(128, seed=61)).cuda()
+    g1, beta1 = (1 + 0.1 * _rand(128, seed=62)).cuda(), (0.1 * _rand(128, seed=63)).cuda()
+    outs = []
+    for img in (img32, img8):
+        out = torch.empty(B, S // 4, S // 4, 128, device="cuda")
+        y16 = torch.empty(B, S // 4, S // 4, 128, device="cuda", dtype=torch.bfloat16)
+        ops.patch_embed(img, w, b, g, beta, out, B, S, gamma1=g1, beta1=beta1, y16=y16,
+                        u8_mean=mean, u8_std=ops.IMAGENET_STD if normalize else None)
+        outs.append((out, y16))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[1][0].abs().max() > 0.1
+    assert not ops.patch_embed_u8_supported(40)
+    with pytest.raises(Exception):
+        ops.patch_embed(torch.zeros(1, 40, 40, 3, dtype=torch.uint8, device="cuda"), w, b, g, beta, torch.empty(1, 10, 10, 128, device="cuda"), 1, 40)
+
+
 def test_upsample2x_nhwc():
     ops = _ops()
     B, H, W, C = 3, 5, 7, 128

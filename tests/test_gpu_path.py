@@ -258,14 +258,51 @@ def test_u8_host_entry_points_match_fp32_path(model, sd):
     f_pin = torch.empty(B, 3, S, S).pin_memory()
     runner.stylize_host(cn.pin_memory(), sn.pin_memory(), f_pin)
     assert torch.equal(o_pin, O.tensor_to_images_u8(f_pin))
-    many = [(c_pin, s_pin, torch.empty_like(o_pin).pin_memory()) for _ in range(3)]
+    # five DIFFERENT batches through the pipelined entry point (two graph slots reused in turn): each equals the blocking call
+    many, want = [], []
+    for i in range(5):
+        ci = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory() if i else c_pin
+        si = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).pin_memory() if i else s_pin
+        many.append((ci, si, torch.empty_like(o_pin).pin_memory()))
+        want.append(runner.stylize_host_u8(ci, si, torch.empty_like(o_pin).pin_memory()).clone())
+    assert torch.equal(want[0], o_pin) and not torch.equal(want[1], want[2])
     runner.stylize_many(many, u8=True)
-    assert all(torch.equal(m[2], o_pin) for m in many)
+    assert all(torch.equal(m[2], w) for m, w in zip(many, want))
+    runner.stylize_many(many[::-1], u8=True)   # second call: slots and events start over
+    assert all(torch.equal(m[2], w) for m, w in zip(many, want))
     with torch.no_grad():
         ref = O.full_forward(sd, cn, sn, 1)
     rng = (ref.max() - ref.min()).item()
     diff = (o_pin.permute(0, 3, 1, 2).float() - (ref * 255).clamp(0, 255)).abs().max().item()
     assert diff <= IMG_TOL * rng * 255 + 1.0, (diff, rng)
+
+
+def test_forward_u8_equals_forward_on_converted_images(model):
+    """model.forward_u8 (ToTensor + Normalize inside the patch-embedding kernel) == model(images_u8_to_nchw(...)) bit for bit, with
+    and without the ImageNet normalisation; wrong dtypes / shapes / training mode are refused."""
+    from mastermetastyletransfer_b200 import ops
+    g = torch.Generator().manual_seed(33)
+    B, S = 2, 64
+    c8 = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).cuda()
+    s8 = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8).cuda()
+    for norm in ((ops.IMAGENET_MEAN, ops.IMAGENET_STD), None):
+        c32, s32 = torch.empty(B, 3, S, S, device="cuda"), torch.empty(B, 3, S, S, device="cuda")
+        ops.images_u8_to_nchw(c8, c32, norm[0] if norm else None)
+        ops.images_u8_to_nchw(s8, s32, norm[0] if norm else None)
+        with torch.no_grad():
+            want = model(c32, s32, 2).clone()
+            got = model.forward_u8(c8, s8, 2, normalize=norm)
+        assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        model.forward_u8(c8.float(), s8.float(), 1)
+    with pytest.raises(ValueError):
+        model.forward_u8(c8[:, :40, :40].contiguous(), s8[:, :40, :40].contiguous(), 1)
+    model.train()
+    try:
+        with pytest.raises(RuntimeError):
+            model.forward_u8(c8, s8, 1)
+    finally:
+        model.eval()
 
 
 def test_similarity_loss_flag_matches_reference_fixture(loss_module, golden_dir):
