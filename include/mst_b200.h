@@ -60,6 +60,7 @@ int mst_pack_conv3x3_weight(const float* w, int N, int Cin, mst_bf16* dst, int n
 enum { MST_A_PLAIN = 0, MST_A_CONV3X3 = 1 };
 enum { MST_ACT_NONE = 0, MST_ACT_RELU = 1, MST_ACT_GELU = 2 };
 enum { MST_GATE_NONE = 0, MST_GATE_RELU = 1, MST_GATE_GELU = 2 };
+enum { MST_OUT_TOKENS = 0, MST_OUT_NCHW_F32 = 1, MST_OUT_IMAGE_U8 = 2 }; /* MstGemm.out_nchw */
 
 typedef struct MstGemm {
   const mst_bf16* A; /* bf16 activations */
@@ -74,7 +75,10 @@ typedef struct MstGemm {
   int lda, ld_res, ld_out32, ld_out16;
   int a_mode, act;
   int H, W, Cin, pad_mode, upsample; /* MST_A_CONV3X3 geometry (H,W = output = padded-input size) */
-  int out_nchw;       /* 1: out_f32 is [B, n_real, H, W] (final decoder conv, decoder.py:54) */
+  int out_nchw;       /* MST_OUT_NCHW_F32: out_f32 is [B, n_real, H, W] (final decoder conv, decoder.py:54).
+                       * MST_OUT_IMAGE_U8 (mst_conv3x3_rows only, others: MST_ERR_UNSUPPORTED): out_f32 points at a uint8_t
+                       * [B, H, W, n_real] image and the epilogue stores (uint8) clip(x * 255, 0, 255) -- test_model.py:207's
+                       * `np.clip(img * 255, 0, 255).astype(np.uint8)` on the NHWC result, without the fp32 image in HBM. */
   int n_real;         /* channels actually stored when out_nchw (<= N) */
   /* ---- training-step extensions (all optional; zero = the inference behaviour above) ----
    * epilogue order:  x = acc + bias;  out_pre16 <- x;  x = act(x);  gate;  x += add16;  x *= row_scale[m / rows_per_scale];

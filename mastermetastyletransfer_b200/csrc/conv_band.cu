@@ -738,7 +738,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rows_kernel(const GemmCore
           else if (p.act == MST_ACT_GELU) xv[j] = gelu_erf(xv[j]);
         }
         const long long pix = (long long)r * p.W + x;
-        if (p.out_nchw) {
+        if (p.out_nchw == MST_OUT_IMAGE_U8) {  // uint8 [B,H,W,n_real] image: np.clip(x * 255, 0, 255).astype(np.uint8) (NaN -> 0)
+          uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out_f32) + pix * p.n_real;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.n_real) o8[n + j] = (uint8_t)(uint32_t)fminf(fmaxf(__fmul_rn(xv[j], 255.0f), 0.0f), 255.0f);
+        } else if (p.out_nchw) {
           const int b = r / p.H;
           const long long base = (long long)b * p.n_real * hw + (pix - (long long)b * hw);
 #pragma unroll
@@ -889,7 +894,7 @@ extern "C" int mst_conv3x3_band(const MstGemm* g, void* stream) {
   if (g->N % 16 || g->N > CB_MAX_BIAS || g->Cin % 16) return MST_ERR_UNSUPPORTED;
   if (g->H < 2 || g->W < 2 || g->M % (g->H * g->W) != 0) return MST_ERR_BAD_ARG;
   if (g->upsample && ((g->H | g->W) & 1)) return MST_ERR_BAD_ARG;
-  if (g->res || g->mul) return MST_ERR_UNSUPPORTED;
+  if (g->res || g->mul || g->out_nchw == MST_OUT_IMAGE_U8) return MST_ERR_UNSUPPORTED;
   if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
   if (g->out_nchw) {
     if (!g->out_f32 || g->n_real <= 0 || g->n_real > g->N) return MST_ERR_BAD_ARG;
@@ -929,7 +934,8 @@ extern "C" int mst_conv3x3_rows(const MstGemm* g, void* stream) {
   if (g->res || g->mul || g->gate || g->add16 || g->out_pre16 || g->row_scale || g->conv_full) return MST_ERR_UNSUPPORTED;
   if (!g->out_f32 && !g->out_bf16) return MST_ERR_BAD_ARG;
   if (g->out_nchw) {
-    if (!g->out_f32 || g->n_real <= 0 || g->n_real > g->N) return MST_ERR_BAD_ARG;
+    if (g->out_nchw < 0 || g->out_nchw > MST_OUT_IMAGE_U8 || !g->out_f32 || g->n_real <= 0 || g->n_real > g->N) return MST_ERR_BAD_ARG;
+    if (g->out_nchw == MST_OUT_IMAGE_U8 && g->out_bf16) return MST_ERR_BAD_ARG;
   } else {
     if (g->out_f32 && g->ld_out32 % 4) return MST_ERR_BAD_ARG;
     if (g->out_bf16 && g->ld_out16 % 8) return MST_ERR_BAD_ARG;

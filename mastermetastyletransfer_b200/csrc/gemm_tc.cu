@@ -817,8 +817,9 @@ extern "C" int mst_gemm(const MstGemm* g, void* stream) {
   } else {
     return MST_ERR_BAD_ARG;
   }
+  if (g->out_nchw == MST_OUT_IMAGE_U8) return MST_ERR_UNSUPPORTED;  // the row-streaming kernel's epilogue only (mst_conv3x3_rows)
   if (g->out_nchw) {
-    if (!g->out_f32 || g->a_mode != MST_A_CONV3X3 || g->n_real <= 0 || g->n_real > g->N || g->res) return MST_ERR_BAD_ARG;
+    if (g->out_nchw != MST_OUT_NCHW_F32 || !g->out_f32 || g->a_mode != MST_A_CONV3X3 || g->n_real <= 0 || g->n_real > g->N || g->res) return MST_ERR_BAD_ARG;
   } else {
     if (g->out_f32 && g->ld_out32 % 4 != 0) return MST_ERR_BAD_ARG;
     if (g->out_bf16 && g->ld_out16 % 8 != 0) return MST_ERR_BAD_ARG;

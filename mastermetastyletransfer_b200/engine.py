@@ -448,8 +448,15 @@ class CnnDecoderWeights:
             self.convs.append((ops.pack_conv3x3(wt, _f32(sd[f"{prefix}{idx}.bias"])), int(wt.shape[1]), up, relu))
 
 
+def decoder_u8_supported(w: "CnnDecoderWeights", H: int, W: int) -> bool:
+    """Whether cnn_decoder_forward can write the uint8 image itself (the last conv runs on the row-streaming kernel)."""
+    pm, cin, _, _ = w.convs[-1]
+    return ops.rows_supported(pm.N, cin, 8 * H, 8 * W)
+
+
 def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace, B: int, H: int, W: int, out: torch.Tensor):
-    """x16 bf16 [B,H,W,256] token-major -> out fp32 [B,3,8H,8W] NCHW."""
+    """x16 bf16 [B,H,W,256] token-major -> out fp32 [B,3,8H,8W] NCHW, or -- out uint8 [B,8H,8W,3], see decoder_u8_supported --
+    the image test_model.py:207 saves, np.clip(out * 255, 0, 255).astype(np.uint8), straight from the last conv's epilogue."""
     cur = x16
     h, wd = H, W
     last = len(w.convs) - 1
@@ -464,7 +471,10 @@ def cnn_decoder_forward(w: CnnDecoderWeights, x16: torch.Tensor, ws_: Workspace,
             h, wd = 2 * h, 2 * wd
         M = B * h * wd
         conv = dict(H=h, W=wd, Cin=cin, pad_mode=PAD_REFLECT, upsample=up)
-        if i == last:
+        if i == last and out.dtype == torch.uint8:
+            conv.update(n_real=pm.N)
+            ops.gemm(cur, pm, M, act=ACT_NONE, out_u8=out, conv=conv)
+        elif i == last:
             conv.update(out_nchw=True, n_real=pm.N)
             ops.gemm(cur, pm, M, act=ACT_NONE, out_f32=out, conv=conv)
         else:

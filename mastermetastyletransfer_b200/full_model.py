@@ -149,10 +149,13 @@ class MasterStyleTransferModel(nn.Module):
             raise ValueError("square inputs with S a multiple of 8 only")
         return self._stylize([content_image.float().contiguous(), style_image.float().contiguous()], B, S, transformer_layer_count, None)
 
-    def forward_u8(self, content_u8: Tensor, style_u8: Tensor, transformer_layer_count: int = 1, normalize=None) -> Tensor:
+    def forward_u8(self, content_u8: Tensor, style_u8: Tensor, transformer_layer_count: int = 1, normalize=None,
+                   out_u8: Optional[Tensor] = None) -> Tensor:
         """forward() on decoded uint8 [B,S,S,3] images (test_model.py:39-48's boundary): transforms.ToTensor() and, with
         normalize = (mean, std), transforms.Normalize are applied inside the patch-embedding kernel's image loads -- the result is
-        bit-identical to forward(images_u8_to_nchw(content), images_u8_to_nchw(style)).  Inference only; S % 16 == 0."""
+        bit-identical to forward(images_u8_to_nchw(content), images_u8_to_nchw(style)).  Inference only; S % 16 == 0.
+        out_u8 (uint8 [B,S,S,3]): receives the image test_model.py:207 saves, np.clip(out * 255, 0, 255).astype(np.uint8), and
+        is returned instead of the fp32 tensor (written by the last convolution's epilogue when its kernel can, else converted)."""
         require_cuda(content_u8, style_u8)
         if (content_u8.dtype != torch.uint8 or style_u8.dtype != torch.uint8 or content_u8.shape != style_u8.shape or content_u8.dim() != 4
                 or content_u8.shape[3] != 3 or content_u8.shape[1] != content_u8.shape[2]):
@@ -163,9 +166,12 @@ class MasterStyleTransferModel(nn.Module):
         from . import ops
         if not ops.patch_embed_u8_supported(S):
             raise ValueError("forward_u8: S must be a multiple of 16")
-        return self._stylize([content_u8.contiguous(), style_u8.contiguous()], B, S, transformer_layer_count, normalize)
+        if out_u8 is not None and (out_u8.dtype != torch.uint8 or tuple(out_u8.shape) != (B, S, S, 3) or not out_u8.is_contiguous()
+                                   or out_u8.device != content_u8.device):
+            raise ValueError("out_u8 must be a contiguous uint8 [B,S,S,3] tensor on the inputs' device")
+        return self._stylize([content_u8.contiguous(), style_u8.contiguous()], B, S, transformer_layer_count, normalize, out_u8)
 
-    def _stylize(self, images, B: int, S: int, transformer_layer_count: int, u8_norm) -> Tensor:
+    def _stylize(self, images, B: int, S: int, transformer_layer_count: int, u8_norm, out_u8: Optional[Tensor] = None) -> Tensor:
         st = self.style_transformer
         st._check_config()
         dev = images[0].device
@@ -186,6 +192,13 @@ class MasterStyleTransferModel(nn.Module):
             if int(transformer_layer_count) == 0:
                 from . import ops
                 ops.cast_bf16(fcs32.view(-1, 256), fcs16.view(-1, 256))
+            if out_u8 is not None and engine.decoder_u8_supported(dw, Hf, Hf):
+                engine.cnn_decoder_forward(dw, fcs16.view(B * Hf * Hf, 256), ws, B, Hf, Hf, out_u8)
+                return out_u8
             out = torch.empty(B, 3, S, S, dtype=torch.float32, device=dev)
             engine.cnn_decoder_forward(dw, fcs16.view(B * Hf * Hf, 256), ws, B, Hf, Hf, out)
+            if out_u8 is not None:
+                from . import ops
+                ops.images_nchw_to_u8(out, out_u8)
+                return out_u8
         return out

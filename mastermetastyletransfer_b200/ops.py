@@ -152,15 +152,24 @@ def gemm(A: torch.Tensor, pm: PackedMatrix, M: int, *, lda: Optional[int] = None
          ld_out32: Optional[int] = None, ld_out16: Optional[int] = None, ld_res: Optional[int] = None,
          conv: Optional[dict] = None, gate: Optional[torch.Tensor] = None, gate_mode: int = GATE_NONE,
          add16: Optional[torch.Tensor] = None, ld_gate: Optional[int] = None, out_pre16: Optional[torch.Tensor] = None,
-         row_scale: Optional[torch.Tensor] = None, rows_per_scale: int = 0) -> None:
-    """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h)."""
+         row_scale: Optional[torch.Tensor] = None, rows_per_scale: int = 0, out_u8: Optional[torch.Tensor] = None) -> None:
+    """acc = A . Wt^T ; x = act(acc + bias) ; x = res*mul + x | res + x ; store (see include/mst_b200.h).
+    out_u8 (3x3 convolutions the row-streaming kernel takes -- rows_supported): a uint8 [B,H,W,n_real] image receiving
+    (uint8) clip(x * 255, 0, 255) instead of an fp32 / bf16 result (MST_OUT_IMAGE_U8)."""
+    if out_u8 is not None:
+        if conv is None or out_f32 is not None or out_bf16 is not None or res is not None or not _use_rows(dict(conv, impl="rows"), pm.n_pad):
+            raise ValueError("gemm: out_u8 is the only output of a 3x3 convolution on the row-streaming kernel")
+        n_real = conv.get("n_real", pm.N)
+        if out_u8.dtype != torch.uint8 or out_u8.numel() != M * n_real or not out_u8.is_contiguous():
+            raise ValueError("gemm: out_u8 must be a contiguous uint8 [B,H,W,n_real] image")
+        conv = dict(conv, out_nchw=2, impl="rows")
     g = MstGemm()
     g.A = _ptr(A, torch.bfloat16, "A")
     g.Wt = pm.w.data_ptr()
     g.bias = _ptr(pm.bias, torch.float32, "bias")
     g.res = _ptr(res, torch.float32, "res")
     g.mul = _ptr(mul, torch.float32, "mul")
-    g.out_f32 = _ptr(out_f32, torch.float32, "out_f32")
+    g.out_f32 = _ptr(out_f32, torch.float32, "out_f32") if out_u8 is None else _ptr(out_u8, torch.uint8, "out_u8")
     g.out_bf16 = _ptr(out_bf16, torch.bfloat16, "out_bf16")
     N = pm.n_pad
     g.M, g.N, g.K, g.k_pad = M, N, pm.K, pm.k_pad

@@ -35,10 +35,12 @@ class GraphedStylizer:
         self._pinned = pin_state([self.model])  # packed weights / workspace buffers whose addresses the graph baked in
 
     def _run_u8(self, c8, s8, o8, normalize: bool) -> None:
-        """uint8 images -> model -> uint8 images.  ToTensor + Normalize run inside the patch-embedding kernel's loads when the
-        model offers forward_u8 for this size (bit-identical to converting first), else as their own two launches."""
+        """uint8 images -> model -> uint8 images.  ToTensor + Normalize run inside the patch-embedding kernel's loads and clip * 255
+        in the last convolution's epilogue when the model offers forward_u8 for this size (bit-identical to converting first /
+        afterwards), else as their own launches."""
         if hasattr(self.model, "forward_u8") and not self.model.training and ops.patch_embed_u8_supported(self.size):
-            out = self.model.forward_u8(c8, s8, self.layers, normalize=(ops.IMAGENET_MEAN, ops.IMAGENET_STD) if normalize else None)
+            self.model.forward_u8(c8, s8, self.layers, normalize=(ops.IMAGENET_MEAN, ops.IMAGENET_STD) if normalize else None, out_u8=o8)
+            return
         else:
             mean = ops.IMAGENET_MEAN if normalize else None
             ops.images_u8_to_nchw(c8, self.content, mean)

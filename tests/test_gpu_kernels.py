@@ -169,6 +169,40 @@ def test_conv3x3_nchw_out(impl):
     assert torch.allclose(out.cpu(), ref, atol=3e-3, rtol=3e-3)
 
 
+@pytest.mark.parametrize("up", [False, True])
+def test_conv3x3_u8_image_out(up):
+    """MST_OUT_IMAGE_U8: the row-streaming conv storing (uint8) clip(x * 255, 0, 255) as an [B,H,W,3] image == the same conv's fp32
+    NCHW output through mst_images_nchw_to_u8, bit for bit (values spread over < 0, [0, 1] and > 1); the other conv kernels refuse."""
+    ops = _ops()
+    B, H, W, Cin = 3, 20, 256, 32
+    hs, wsz = (H // 2, W // 2) if up else (H, W)
+    x = _rand(B, hs, wsz, Cin, seed=13).bfloat16().cuda()
+    wt = _rand(3, Cin, 3, 3, seed=14, scale=(9 * Cin) ** -0.5)
+    bias = torch.tensor([0.5, -0.2, 1.0])
+    pm = ops.pack_conv3x3(wt.cuda(), bias.cuda())
+    conv = dict(H=H, W=W, Cin=Cin, pad_mode=ops.PAD_REFLECT, upsample=up, n_real=3)
+    out32 = torch.empty(B, 3, H, W, device="cuda")
+    ops.gemm(x, pm, B * H * W, out_f32=out32, conv=dict(conv, out_nchw=True, impl="rows"))
+    want = torch.empty(B, H, W, 3, dtype=torch.uint8, device="cuda")
+    ops.images_nchw_to_u8(out32, want)
+    got = torch.zeros(B, H, W, 3, dtype=torch.uint8, device="cuda")
+    ops.gemm(x, pm, B * H * W, out_u8=got, conv=conv)
+    assert torch.equal(got, want)
+    frac0, frac255 = (want == 0).float().mean().item(), (want == 255).float().mean().item()
+    assert 0.02 < frac0 < 0.9 and 0.02 < frac255 < 0.9  # both clip branches exercised
+    with pytest.raises(ValueError):
+        ops.gemm(x, pm, B * H * W, out_u8=got, out_f32=out32, conv=conv)
+    from mastermetastyletransfer_b200 import _lib
+    import ctypes as C
+    g = _lib.MstGemm()
+    g.A, g.Wt, g.bias, g.out_f32 = x.data_ptr(), pm.w.data_ptr(), pm.bias.data_ptr(), got.data_ptr()
+    g.M, g.N, g.K, g.k_pad, g.lda = B * H * W, pm.n_pad, pm.K, pm.k_pad, pm.K
+    g.ld_out32 = g.ld_out16 = g.ld_res = pm.n_pad
+    g.a_mode, g.H, g.W, g.Cin, g.pad_mode, g.upsample, g.out_nchw, g.n_real = 1, H, W, Cin, 1, int(up), 2, 3
+    st = torch.cuda.current_stream().cuda_stream
+    assert _lib.lib().mst_gemm(C.byref(g), st) == -2 and _lib.lib().mst_conv3x3_band(C.byref(g), st) == -2  # MST_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("H,ws,s", [(32, 8, 4), (64, 8, 4), (16, 8, 4), (8, 8, 4), (32, 7, 4), (64, 7, 4), (32, 7, 3), (64, 7, 3), (16, 7, 3), (32, 7, 0)])
 def test_window_maps_bit_exact(H, ws, s, golden_dir):
     """Partition / shift / mask indexing of the CUDA kernels == oracle == reference-derived goldens, bit for bit."""

@@ -293,6 +293,14 @@ def test_forward_u8_equals_forward_on_converted_images(model):
             want = model(c32, s32, 2).clone()
             got = model.forward_u8(c8, s8, 2, normalize=norm)
         assert torch.equal(got, want)
+        want8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device="cuda")
+        ops.images_nchw_to_u8(want, want8)
+        got8 = torch.zeros_like(want8)
+        with torch.no_grad():
+            assert model.forward_u8(c8, s8, 2, normalize=norm, out_u8=got8) is got8   # clip * 255 in the last conv's epilogue
+        assert torch.equal(got8, want8) and 0 < got8.float().mean().item() < 255
+    with pytest.raises(ValueError):
+        model.forward_u8(c8, s8, 1, out_u8=torch.empty(B, 3, S, S, dtype=torch.uint8, device="cuda"))
     with pytest.raises(ValueError):
         model.forward_u8(c8.float(), s8.float(), 1)
     with pytest.raises(ValueError):
