@@ -143,6 +143,11 @@ typedef struct MstMlp {
   const float* ln_g;       /* [C] or NULL */
   const float* ln_b;       /* [C] or NULL */
   int pre;
+  /* ---- optional LayerNorm of the result for the NEXT block (pre != 0 and C == 128, else MST_ERR_UNSUPPORTED) ----
+   *   out_bf16 = LayerNorm(out; lnn_g, lnn_b) eps 1e-5 instead of the plain bf16 copy of out (out_f32 is unchanged): the following
+   *   swin block's norm1 (tv swin_transformer.py SwinTransformerBlock.forward) without a launch of its own.  Both or neither. */
+  const float* lnn_g;      /* [C] or NULL */
+  const float* lnn_b;      /* [C] or NULL */
 } MstMlp;
 size_t mst_mlp_stream_bytes(int C);
 size_t mst_mlp_stream_bytes_pre(int C);

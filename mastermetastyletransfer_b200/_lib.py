@@ -72,7 +72,8 @@ class MstMlp(C.Structure):
     _fields_ = [("A", C.c_void_p), ("Wstream", C.c_void_p), ("b1", C.c_void_p), ("b2", C.c_void_p), ("res", C.c_void_p),
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
                 ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int),
-                ("bpre", C.c_void_p), ("mul", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("pre", C.c_int)]
+                ("bpre", C.c_void_p), ("mul", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("pre", C.c_int),
+                ("lnn_g", C.c_void_p), ("lnn_b", C.c_void_p)]
 
 
 class MstTensorTable(C.Structure):

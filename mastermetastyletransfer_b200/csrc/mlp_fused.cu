@@ -85,9 +85,21 @@ struct MlpCfg {
 // TMA engine as a tensor store; rows past M are clipped by the tensor map.  The slab is reused only after
 // cp.async.bulk.wait_group.read, and every warp waits for its own stores before it arrives on x_full, which orders all of
 // them before the first GELU write of the next tile (x_full -> fc1 MMA -> acc1_full).
+// Kernel-side view of MstMlp: its leading fields, by value (layout-identical prefix).  The next-block LayerNorm pointers travel as
+// separate arguments: growing the by-value struct itself made ptxas spill in every instantiation (see GemmCore, common.cuh).
+struct MlpCore {
+  const void* A; const void* Wstream; const float* b1; const float* b2; const float* res; float* out_f32; void* out_bf16;
+  int M, C, lda, ld_res, ld_out32, ld_out16;
+  const float* bpre; const float* mul; const float* ln_g; const float* ln_b;
+  int pre;
+};
+static_assert(offsetof(MlpCore, pre) == offsetof(MstMlp, pre) && offsetof(MlpCore, bpre) == offsetof(MstMlp, bpre) &&
+              offsetof(MlpCore, M) == offsetof(MstMlp, M) && sizeof(MlpCore) <= sizeof(MstMlp), "MlpCore must be a prefix of MstMlp");
+
 template <int C, bool PRE>
-__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p, const int num_tiles,
-                                                                  const __grid_constant__ CUtensorMap tm_out, const int tma_out, const int res_tma) {
+__global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore p, const int num_tiles,
+                                                                  const __grid_constant__ CUtensorMap tm_out, const int tma_out, const int res_tma,
+                                                                  const float* __restrict__ lnn_g, const float* __restrict__ lnn_b) {
   using Cfg = MlpCfg<C>;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int ABUF = PRE ? 1 : Cfg::ABUF;
@@ -552,6 +564,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&acc2_empty));
         }
+        // lnn: out_bf16 = LayerNorm(out; lnn_g, lnn_b) -- the NEXT block's norm1 -- instead of a plain cast (C = 128: the warp's 32
+        // columns of the row stay in registers between the statistics and the store)
+        bool lnn = false;
+        if constexpr (PRE && C == 128) lnn = lnn_g != nullptr;  // (the host passes lnn_g only together with tma_out: no early exit above)
         if (!row_ok && !(PRE && tma_out)) continue;  // (tensor store: whole warp takes part, rows past M are clipped by the map)
         const int n = part * CPW + col0;
         float x[32];
@@ -575,6 +591,33 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
               const float4 r = r4[e];
               x[4 * e] += r.x; x[4 * e + 1] += r.y; x[4 * e + 2] += r.z; x[4 * e + 3] += r.w;
             }
+          }
+        }
+        float ln_mean = 0.f, ln_rstd = 0.f;
+        if constexpr (PRE && C == 128) {
+          if (lnn) {
+            // as the LN2 stage above: local mean / centred M2 over this warp's 32 columns, one exchange with the three other warps of
+            // the TMEM quadrant through the quadrant's own rows of the X tile (idle: this tile's fc1 has finished, the next tile's
+            // projection epilogue -- these same four warps -- writes it after the second barrier), pairwise merge
+            float sum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sum += x[e];
+            const float ml = sum * (1.0f / 32.0f);
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) q = fmaf(x[e] - ml, x[e] - ml, q);
+            const uint32_t ex = x_base + quad * 4096 + (uint32_t)lane * 32u;
+            asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(ex + part * 8), "f"(ml), "f"(q) : "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+            float mi[4], qi[4];
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(mi[0]), "=f"(qi[0]), "=f"(mi[1]), "=f"(qi[1]) : "r"(ex) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(mi[2]), "=f"(qi[2]), "=f"(mi[3]), "=f"(qi[3]) : "r"(ex + 16) : "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+            ln_mean = 0.25f * ((mi[0] + mi[1]) + (mi[2] + mi[3]));
+            float m2 = (qi[0] + qi[1]) + (qi[2] + qi[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m2 = fmaf((mi[i] - ln_mean) * (mi[i] - ln_mean), 32.0f, m2);
+            ln_rstd = rsqrtf(m2 * (1.0f / C) + 1e-5f);
           }
         }
         if (PRE && tma_out) {
@@ -614,6 +657,20 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MstMlp p
         }
         if (p.out_bf16 && row_ok) {
           bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n;
+          if constexpr (PRE && C == 128) {
+            if (lnn) {
+              const float4* g4 = reinterpret_cast<const float4*>(lnn_g + n);
+              const float4* be4 = reinterpret_cast<const float4*>(lnn_b + n);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 g = __ldg(g4 + e), be = __ldg(be4 + e);
+                x[4 * e] = (x[4 * e] - ln_mean) * ln_rstd * g.x + be.x;
+                x[4 * e + 1] = (x[4 * e + 1] - ln_mean) * ln_rstd * g.y + be.y;
+                x[4 * e + 2] = (x[4 * e + 2] - ln_mean) * ln_rstd * g.z + be.z;
+                x[4 * e + 3] = (x[4 * e + 3] - ln_mean) * ln_rstd * g.w + be.w;
+              }
+            }
+          }
           if (wide_o16) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -758,8 +815,20 @@ static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   static int res_allow = -1;
   if (res_allow < 0) { const char* e = getenv("MST_MLP_TMA_RES"); res_allow = e ? atoi(e) : 1; }
   const int res_tma = (PRE && C == 128 && tma_out && res_allow && p.res == p.out_f32 && p.ld_res == p.ld_out32 && !p.mul) ? 1 : 0;
-  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(p, tiles, tmap, tma_out, res_tma);
-  return (int)cudaGetLastError();
+  MlpCore core;
+  memcpy(&core, &p, sizeof(core));
+  // next-block LayerNorm: in the tile-end epilogue when the tensor-store path runs (its statistics exchange needs whole warps),
+  // else as a launch of its own after the kernel
+  const bool lnn_fused = p.lnn_g && PRE && C == 128 && tma_out;
+  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(core, tiles, tmap, tma_out, res_tma, lnn_fused ? p.lnn_g : nullptr,
+                                                                       lnn_fused ? p.lnn_b : nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (p.lnn_g && !lnn_fused) {
+    if (!p.out_f32) return MST_ERR_UNSUPPORTED;
+    return mst_layernorm(p.out_f32, p.lnn_g, p.lnn_b, p.out_bf16, p.M, C, (void*)st);
+  }
+  return 0;
 }
 
 }  // namespace mst
@@ -790,6 +859,11 @@ extern "C" int mst_mlp_fused(const MstMlp* p, void* stream) {
   if (!p->out_f32 && !p->out_bf16) return MST_ERR_BAD_ARG;
   if ((p->out_f32 && p->ld_out32 % 4) || (p->out_bf16 && p->ld_out16 % 8) || (p->res && p->ld_res % 4)) return MST_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if ((p->lnn_g == nullptr) != (p->lnn_b == nullptr)) return MST_ERR_BAD_ARG;
+  if (p->lnn_g) {  // LayerNorm of the output for the next block: the pre-stage kernel at C = 128 only
+    if (!p->out_bf16 || ((reinterpret_cast<uintptr_t>(p->lnn_g) | reinterpret_cast<uintptr_t>(p->lnn_b)) & 15)) return MST_ERR_BAD_ARG;
+    if (!p->pre || p->C != 128) return MST_ERR_UNSUPPORTED;
+  }
   if (p->pre) {
     // attention-output stage in front: needs the residual / blend operand, the x1 destination and 16-byte aligned vectors
     if (!p->bpre || !p->res || (p->ln_g == nullptr) != (p->ln_b == nullptr)) return MST_ERR_BAD_ARG;

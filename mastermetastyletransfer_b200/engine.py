@@ -99,9 +99,11 @@ class SwinEncoderWeights:
 
 
 def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W: int, shift: int, tag: str,
-                ln1_done: bool = False, out16: Optional[torch.Tensor] = None):
+                ln1_done: bool = False, out16: Optional[torch.Tensor] = None, next_ln=None) -> bool:
     """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place).
-    ln1_done: the producer of x32 already wrote LN1(x) into the block's `ln` buffer (patch embedding)."""
+    ln1_done: the producer of x32 already wrote LN1(x) into the block's `ln` buffer (patch embedding, or the previous block).
+    next_ln: (gamma, beta) of the FOLLOWING block's norm1 (same tag, so the same `ln` buffer): when the MLP kernel can apply it in
+    its output epilogue it does, and the block returns True -- call the next block with ln1_done=True."""
     C, heads = bw["C"], bw["heads"]
     T = Bt * H * W
     ln = ws_.bf16(tag + "ln", T, C)
@@ -116,11 +118,14 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
         ops.window_attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, bw["table"], Bt, H, W, heads, 7, shift,
                              3 * C, 3 * C, 3 * C, C, pad_q=bw["pad_q"], pad_k=bw["pad_k"], pad_v=bw["pad_v"])
     if FUSE_PROJ_MLP:  # x1 = x + proj(o); x = x1 + mlp(LN2(x1)): one kernel, LN2(x1) and the hidden activation stay on chip
-        ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, out_bf16=out16, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"])
-        return
+        fuse_next = next_ln is not None and out16 is None and ops.mlp_next_ln_supported(C)
+        ops.mlp_fused(o, bw["proj_mlp"], T, res=x32, out_f32=x32, out_bf16=ln if fuse_next else out16, pre=True, ln_g=bw["n2w"], ln_b=bw["n2b"],
+                      next_ln=next_ln if fuse_next else None)
+        return fuse_next
     ops.gemm(o, bw["proj"], T, res=x32, out_f32=x32)
     ops.layernorm(x32, bw["n2w"], bw["n2b"], ln, T, C)
     ops.mlp_fused(ln, bw["mlp"], T, res=x32, out_f32=x32, out_bf16=out16)  # fc1 + GELU + fc2 + residual, hidden kept on chip
+    return False
 
 
 def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torch.Tensor, out16: Optional[torch.Tensor],
@@ -140,8 +145,9 @@ def swin_encode(w: SwinEncoderWeights, imgs, ws_: Workspace, S: int, out32: torc
         ops.patch_embed(img, w.pe_w, w.pe_b, w.pe_g, w.pe_beta, x1[off * P * P:], b, S,
                         gamma1=b10["n1w"], beta1=b10["n1b"], y16=ln1[off * P * P:], u8_mean=u8_mean, u8_std=u8_std)
         off += b
-    _swin_block(b10, x1, ws_, Bt, P, P, 0, "sw1_", ln1_done=True)
-    _swin_block(w.blocks["1.1"], x1, ws_, Bt, P, P, 3, "sw1_")
+    b11 = w.blocks["1.1"]
+    done = _swin_block(b10, x1, ws_, Bt, P, P, 0, "sw1_", ln1_done=True, next_ln=(b11["n1w"], b11["n1b"]))
+    _swin_block(b11, x1, ws_, Bt, P, P, 3, "sw1_", ln1_done=done)
     P2 = P // 2
     T2 = Bt * P2 * P2
     pm = ws_.bf16("sw_pm", T2, 512)

@@ -592,11 +592,16 @@ def pack_mlp(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Ten
                      bpre.detach().float().contiguous())
 
 
+def mlp_next_ln_supported(C_: int) -> bool:
+    return C_ == 128
+
+
 def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out_bf16=None,
-              pre: bool = False, mul=None, ln_g=None, ln_b=None) -> None:
+              pre: bool = False, mul=None, ln_g=None, ln_b=None, next_ln=None) -> None:
     """out = res + fc2(gelu(fc1(A) + b1)) + b2, hidden activation kept on chip.
     pre=True (pm packed with wpre): x1 = res (*mul) + A.Wpre^T + bpre; out = x1 + mlp([LayerNorm](x1)) -- the whole
-    attention-output half of a transformer block in one kernel (see include/mst_b200.h)."""
+    attention-output half of a transformer block in one kernel (see include/mst_b200.h).
+    next_ln = (gamma, beta) (pre=True, C = 128 -- mlp_next_ln_supported): out_bf16 = LayerNorm(out), the next block's norm1."""
     g = MstMlp()
     g.A, g.Wstream = _ptr(A, torch.bfloat16, "A"), pm.stream.data_ptr()
     g.b1, g.b2 = _ptr(pm.b1, torch.float32, "b1"), _ptr(pm.b2, torch.float32, "b2")
@@ -614,8 +619,12 @@ def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out
         flops += 2.0 * M * pm.C * pm.C
     elif pm.bpre is not None or mul is not None or ln_g is not None:
         raise ValueError("mlp_fused: mul / ln / a pre-packed stream need pre=True")
+    if next_ln is not None:
+        if not (pre and mlp_next_ln_supported(pm.C)) or out_bf16 is None:
+            raise ValueError("mlp_fused: next_ln needs pre=True, C = 128 and out_bf16")
+        g.lnn_g, g.lnn_b = _ptr(next_ln[0], torch.float32, "next_ln gamma"), _ptr(next_ln[1], torch.float32, "next_ln beta")
     _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=flops,
-            desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None} pre={int(pre)} ln={ln_g is not None} mul={mul is not None}")
+            desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None} pre={int(pre)} ln={ln_g is not None} mul={mul is not None} next_ln={next_ln is not None}")
 
 
 # --------------------------------------------------------------------------------------------

@@ -133,8 +133,13 @@ def gemm(A, pm, M, *, lda=None, act=ops.ACT_NONE, res=None, mul=None, out_f32=No
         _rows(out_bf16, M, N, N if ld_out16 is None else ld_out16).copy_(x)
 
 
-def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=False, mul=None, ln_g=None, ln_b=None):
+def mlp_next_ln_supported(C_):
+    return C_ == 128
+
+
+def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=False, mul=None, ln_g=None, ln_b=None, next_ln=None):
     C = pm.C
+    assert next_ln is None or (pre and C == 128 and out_bf16 is not None)
     a = _rows(A, M, C, C if lda is None else lda).float()
     if pre:
         assert pm.wpre is not None
@@ -151,7 +156,7 @@ def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=
     if out_f32 is not None:
         out_f32[:M].copy_(y)
     if out_bf16 is not None:
-        out_bf16[:M].copy_(y)
+        out_bf16[:M].copy_(y if next_ln is None else F.layer_norm(y, (C,), next_ln[0], next_ln[1]))
 
 
 def layernorm(x, gamma, beta, y, rows, Cdim):

@@ -501,6 +501,23 @@ def test_proj_mlp_fused(M, C, ln, mul):
     ops.mlp_fused(A.cuda(), pm, M, res=res_dev, out_f32=y, pre=True, mul=m.cuda() if mul else None,
                   ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None)
     assert torch.equal(y, x) and torch.equal(res_dev.cpu(), res)
+    # MstMlp::lnn_g / lnn_b: out_bf16 = LayerNorm(out) for the next block (C = 128), from the tile-end epilogue.  out_f32 keeps its
+    # bits; the bf16 tensor matches a separate LayerNorm of it (different summation order: one bf16 ulp of slack).
+    if C == 128:
+        g2, be2 = (1 + 0.1 * _rand(C, seed=91)).cuda(), (0.1 * _rand(C, seed=92)).cuda()
+        for inplace in (True, False):
+            src = res.cuda()
+            y2 = src if inplace else torch.empty(M, C, device="cuda")
+            ln16 = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            ops.mlp_fused(A.cuda(), pm, M, res=src, out_f32=y2, out_bf16=ln16, pre=True, mul=m.cuda() if mul else None,
+                          ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None, next_ln=(g2, be2))
+            assert torch.equal(y2, x)
+            want = F.layer_norm(x, (C,), g2, be2)
+            assert torch.allclose(ln16.float(), want, atol=2e-2, rtol=1e-2), (ln16.float() - want).abs().max()
+    else:
+        assert not ops.mlp_next_ln_supported(C)
+        with pytest.raises(ValueError):
+            ops.mlp_fused(A.cuda(), pm, M, res=x, out_f32=x, out_bf16=out16, pre=True, next_ln=(x[0], x[1]))
 
 
 @pytest.mark.parametrize("B,H,C,ws,shift", [(1, 8, 256, 8, 0), (2, 32, 256, 8, 4), (1, 24, 256, 8, 4), (2, 32, 256, 7, 4), (1, 16, 256, 7, 3),
