@@ -252,6 +252,14 @@ int mst_instnorm_stats_affine(const float* x, float* mean, float* rstd, int B, i
                               const float* pad_val, float* pad_norm, const float* gamma, const float* beta, void* stream);
 int mst_instnorm_apply_affine(const float* x, const float* mean, const float* rstd, const float* beta, mst_bf16* y16, float* y32,
                               int B, int T, int C, void* stream);
+/* mst_instnorm_stats_affine + mst_instnorm_apply_affine(y16) as ONE call: mean / rstd [B,C] (and pad_norm) as the former, y16 bf16
+ * [B,T,C] = (x - mean) * rstd + beta as the latter, bit-identical to the sequence.  When a (image, 32-channel) slice of x fits in
+ * shared memory (mst_instnorm_fused_supported: T <= 1600, T a multiple of a box height in 8..256) it runs as one kernel that
+ * fetches the slice once with TMA tensor copies (instnorm_fused.cu); other shapes run the two kernels.  gamma / beta / pad_val /
+ * pad_norm may be NULL (n_pad == 0 without pad_val). */
+int mst_instnorm(const float* x, float* mean, float* rstd, mst_bf16* y16, int B, int T, int C, int twice, int n_pad,
+                 const float* pad_val, float* pad_norm, const float* gamma, const float* beta, void* stream);
+int mst_instnorm_fused_supported(int T, int C);
 /* Statistics over (T, C) JOINTLY per image -- what nn.InstanceNorm2d computes when the regular-MHA decoder variant feeds it
  * [B, C, T] tensors, read as one unbatched image (style_transformer.py:1063-1119).  mean / rstd [B, C] receive the per-image
  * scalars replicated over C, so mst_instnorm_apply applies them. */

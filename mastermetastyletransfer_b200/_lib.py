@@ -127,6 +127,8 @@ SYMBOLS = {
     "mst_instnorm_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mst_instnorm_stats_affine": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mst_instnorm_apply_affine": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mst_instnorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mst_instnorm_fused_supported": (_I, [_I, _I]),
     "mst_jointnorm_stats": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mst_softmax_rows": (_I, [_P, _P, _I, _I, C.c_float, _P]),
     "mst_pack_bf16_matrix": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),

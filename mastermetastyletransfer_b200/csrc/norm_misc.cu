@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(IN_WARPS * 32) instnorm_stats_kernel(const flo
     }
     mean[(long long)b * C + c] = m;
     rstd[(long long)b * C + c] = r;
-    if (pad_norm) pad_norm[(long long)b * C + c] = (pv - m) * r + (beta ? beta[c] : 0.f);
+    if (pad_norm) pad_norm[(long long)b * C + c] = fmaf(pv - m, r, beta ? beta[c] : 0.f);  // (explicit: instnorm_fused_kernel must match)
   }
 }
 

@@ -359,19 +359,16 @@ def style_transformer_forward(w: StyleTransformerWeights, fc32: torch.Tensor, fs
         # decoder_use_instance_norm_with_affine both normalisations of a tensor go through the SAME affine module (:982-984,1052-1054)
         gq, bq_ = w.affine_q if w.affine_q is not None else (None, None)
         gk, bk_ = w.affine_k if w.affine_k is not None else (None, None)
-        ops.instnorm_stats(x32, mean, rstd, B, H * W, C, twice=True, gamma=gq)
-        ops.instnorm_apply(x32, mean, rstd, B, H * W, C, y16=qhat16, beta=bq_)
-        ops.instnorm_stats(key32, mean, rstd, B, H * W, C, twice=not key_in_after_linear, gamma=gk)
-        ops.instnorm_apply(key32, mean, rstd, B, H * W, C, y16=ln16, beta=bk_)
+        ops.instnorm(x32, mean, rstd, qhat16, B, H * W, C, twice=True, gamma=gq, beta=bq_)
+        ops.instnorm(key32, mean, rstd, ln16, B, H * W, C, twice=not key_in_after_linear, gamma=gk, beta=bk_)
         if not key_in_after_linear:  # IN(IN(Key)) on the unpadded map, then k = Wk.Key + bk as it is
             ops.gemm(ln16, w.sm_k, T, out_bf16=khat16)
         else:
             ops.gemm(ln16, w.sm_k, T, out_f32=kk32)
             if padded:  # statistics over the padded map: its n_pad extra tokens all hold Wk.0 + bk = bk
-                ops.instnorm_stats_padded(kk32, mean, rstd, B, H * W, C, n_pad, w.sm_pad[0], pad_norm=kpad, gamma=gk, beta=bk_)
+                ops.instnorm(kk32, mean, rstd, khat16, B, H * W, C, gamma=gk, beta=bk_, n_pad=n_pad, pad_val=w.sm_pad[0], pad_norm=kpad)
             else:
-                ops.instnorm_stats(kk32, mean, rstd, B, H * W, C, gamma=gk)
-            ops.instnorm_apply(kk32, mean, rstd, B, H * W, C, y16=khat16, beta=bk_)
+                ops.instnorm(kk32, mean, rstd, khat16, B, H * W, C, gamma=gk, beta=bk_)
         ops.gemm(scale16, w.sm_vs, T, out_bf16=vs16)
         ops.gemm(shift16, w.sm_vh, T, out_bf16=vh16)
         # padded tokens: q = IN(0) (no Q projection, :511-514: zero without the affine bias), k = the normalised bias (per image),

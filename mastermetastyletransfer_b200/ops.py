@@ -55,7 +55,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, desc: str = 
 KERNEL_OF = {"mst_adam_step": "adam_kernel", "mst_reptile_delta": "reptile_kernel", "mst_reptile_apply": "reptile_kernel",
              "mst_gemm": "gemm_tc_kernel", "mst_mlp_fused": "mlp_fused_kernel", "mst_pack_mlp_weights": "pack_kernel", "mst_conv3x3_band": "conv_band_kernel", "mst_conv3x3_rows": "conv_rows_kernel", "mst_conv3x3_cm": "conv_cm_kernel", "mst_window_attention": "window_attn_kernel", "mst_window_attention:core": "attn_core_kernel", "mst_attn_block": "attn_fused_kernel", "mst_pack_attn_qkv": "pack_kernel", "mst_layernorm": "layernorm_kernel",
              "mst_patch_merge_layernorm": "layernorm_kernel", "mst_instnorm_stats": "instnorm_stats_kernel",
-             "mst_instnorm_apply": "instnorm_apply_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
+             "mst_instnorm_apply": "instnorm_apply_kernel", "mst_instnorm": "instnorm_fused_kernel", "mst_jointnorm_stats": "jointnorm_stats_kernel", "mst_softmax_rows": "softmax_rows_kernel", "mst_pack_bf16_matrix": "pack_kernel", "mst_patch_embed": "patch_embed_kernel",
              "mst_cast_bf16": "cast_bf16_kernel", "mst_images_u8_to_nchw": "images_u8_to_nchw_kernel", "mst_images_nchw_to_u8": "images_nchw_to_u8_kernel", "mst_resize_crop_normalize": "resize_crop_normalize_kernel", "mst_upsample2x_nhwc": "upsample2x_kernel", "mst_pack_linear_weight": "pack_kernel", "mst_pack_conv3x3_weight": "pack_kernel",
              "mst_window_maps": "window_maps_kernel", "mst_conv3x3_first": "conv3x3_first_kernel",
              "mst_maxpool2x2": "maxpool2x2_kernel", "mst_bn_relu": "bn_relu_kernel", "mst_tap_stats": "tap_stats_kernel", "mst_content_term": "content_term_kernel",
@@ -385,6 +385,22 @@ def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None, beta=None) -> 
                                                           _ptr(y16, torch.bfloat16, "y16"), _ptr(y32, torch.float32, "y32"), B, T, Cdim, _stream())
     _launch("mst_instnorm_apply", fn,
             nbytes=B * T * Cdim * (4.0 + (2.0 if y16 is not None else 0.0) + (4.0 if y32 is not None else 0.0)))
+
+
+def instnorm(x, mean, rstd, y16, B, T, Cdim, twice=False, gamma=None, beta=None, n_pad=0, pad_val=None, pad_norm=None) -> None:
+    """InstanceNorm statistics (instnorm_stats / instnorm_stats_padded) + application to bf16 (instnorm_apply) of one tensor: one kernel
+    that reads x once when an (image, 32-channel) slice fits in shared memory (csrc/instnorm_fused.cu; bit-identical), else the two."""
+    if not _lib.lib().mst_instnorm_fused_supported(T, Cdim) or os.environ.get("MST_INSTNORM_FUSED", "1") == "0":
+        if n_pad > 0 or pad_norm is not None:
+            instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=pad_norm, gamma=gamma, beta=beta)
+        else:
+            instnorm_stats(x, mean, rstd, B, T, Cdim, twice=twice, gamma=gamma)
+        instnorm_apply(x, mean, rstd, B, T, Cdim, y16=y16, beta=beta)
+        return
+    _launch("mst_instnorm", lambda: _lib.lib().mst_instnorm(
+        _ptr(x, torch.float32, "x"), _ptr(mean, torch.float32, "mean"), _ptr(rstd, torch.float32, "rstd"), _ptr(y16, torch.bfloat16, "y16"),
+        B, T, Cdim, int(twice), int(n_pad), _ptr(pad_val, torch.float32, "pad_val"), _ptr(pad_norm, torch.float32, "pad_norm"),
+        _ptr(gamma, torch.float32, "gamma"), _ptr(beta, torch.float32, "beta"), _stream()), nbytes=6.0 * B * T * Cdim)
 
 
 def patch_embed_u8_supported(S: int) -> bool:

@@ -214,6 +214,16 @@ def instnorm_apply(x, mean, rstd, B, T, Cdim, y16=None, y32=None, beta=None):
             dst.reshape(B, T, Cdim).copy_(y)
 
 
+def instnorm(x, mean, rstd, y16, B, T, Cdim, twice=False, gamma=None, beta=None, n_pad=0, pad_val=None, pad_norm=None):
+    """statistics + application in one call (ops.instnorm)"""
+    if n_pad > 0 or pad_norm is not None:
+        assert not twice
+        instnorm_stats_padded(x, mean, rstd, B, T, Cdim, n_pad, pad_val, pad_norm=pad_norm, gamma=gamma, beta=beta)
+    else:
+        instnorm_stats(x, mean, rstd, B, T, Cdim, twice=twice, gamma=gamma)
+    instnorm_apply(x, mean, rstd, B, T, Cdim, y16=y16, beta=beta)
+
+
 def window_attention(q, k, v, out, bias_table, B, H, W, heads, ws, shift, ldq, ldk, ldv, ldo,
                      v2=None, out2=None, pad_q=None, pad_k=None, pad_v=None, pad_v2=None, pad_k_per_image=False):
     C = heads * 32
@@ -307,6 +317,6 @@ def loss_finalize(taps, lam, squared_style, out3):
 
 def install(monkeypatch):
     for name in ("pack_linear", "pack_mlp", "pack_conv3x3", "cast_bf16", "gemm", "mlp_fused", "layernorm", "instnorm_stats",
-                 "instnorm_stats_padded", "jointnorm_stats", "pack_bf16_matrix", "softmax_rows", "instnorm_apply", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
+                 "instnorm_stats_padded", "jointnorm_stats", "pack_bf16_matrix", "softmax_rows", "instnorm_apply", "instnorm", "window_attention", "pack_attn_qkv", "attn_block", "upsample2x_nhwc", "patch_embed",
                  "patch_merge_layernorm", "conv3x3_first", "maxpool2x2", "bn_relu", "tap_stats", "content_term", "loss_finalize"):
         monkeypatch.setattr(ops, name, globals()[name])

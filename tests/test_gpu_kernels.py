@@ -321,6 +321,51 @@ def test_instance_norm(twice):
     assert torch.allclose(y16.float().cpu(), ref, atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("B,T,C,twice,affine,n_pad", [(3, 1024, 256, True, False, 0), (2, 1024, 256, False, True, 0), (2, 256, 128, True, True, 0),
+                                                      (3, 576, 256, False, False, 49), (2, 1024, 256, False, True, 64), (1, 1600, 64, False, False, 0),
+                                                      (2, 49, 256, True, False, 0), (1, 4096, 256, False, False, 0)])
+def test_instnorm_one_call(B, T, C, twice, affine, n_pad):
+    """mst_instnorm (statistics + application; csrc/instnorm_fused.cu: the slice through TMA into shared memory, read once) == the
+    two-kernel sequence mst_instnorm_stats_affine -> mst_instnorm_apply_affine bit for bit: mean, rstd, the normalised padding value
+    and the bf16 result; and against nn.InstanceNorm semantics in fp32.  Includes box heights other than 256 (576 = 3 x 192,
+    1600 = 8 x 200), shapes the fused kernel does not take (T = 49: no box height; T = 4096: too large), affine and padded variants."""
+    ops = _ops()
+    from mastermetastyletransfer_b200 import _lib
+    x = (_rand(B, T, C, seed=156, scale=1.7) + 0.3).cuda()
+    g = (1 + 0.2 * _rand(C, seed=157)).cuda() if affine else None
+    be = (0.3 * _rand(C, seed=158)).cuda() if affine else None
+    pad_val = (0.5 * _rand(C, seed=159)).cuda() if n_pad else None
+    outs = []
+    for fused in (False, True):
+        mean, rstd = torch.full((B, C), float("nan"), device="cuda"), torch.full((B, C), float("nan"), device="cuda")
+        pad_norm = torch.full((B, C), float("nan"), device="cuda") if n_pad else None
+        y16 = torch.full((B, T, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        if fused:
+            ops.instnorm(x, mean, rstd, y16, B, T, C, twice=twice, gamma=g, beta=be, n_pad=n_pad, pad_val=pad_val, pad_norm=pad_norm)
+        else:
+            if n_pad:
+                ops.instnorm_stats_padded(x, mean, rstd, B, T, C, n_pad, pad_val, pad_norm=pad_norm, gamma=g, beta=be)
+            else:
+                ops.instnorm_stats(x, mean, rstd, B, T, C, twice=twice, gamma=g)
+            ops.instnorm_apply(x, mean, rstd, B, T, C, y16=y16, beta=be)
+        outs.append((mean, rstd, y16, pad_norm))
+    for name, a, b_ in zip(("mean", "rstd", "y16", "pad_norm"), outs[0], outs[1]):
+        assert (a is None and b_ is None) or torch.equal(a, b_), name
+    assert bool(_lib.lib().mst_instnorm_fused_supported(T, C)) == (T not in (49, 4096))
+    # semantics (fp32): biased variance over the T tokens plus n_pad tokens of value pad_val
+    xd = x.double()
+    if n_pad:
+        xd = torch.cat([xd, pad_val.double().view(1, 1, C).expand(B, n_pad, C)], 1)
+    m, var = xd.mean(1, keepdim=True), xd.var(1, unbiased=False, keepdim=True)
+    gd = g.double() if affine else 1.0
+    bd = be.double() if affine else 0.0
+    y = (xd - m) / torch.sqrt(var + 1e-5) * gd + bd
+    if twice:
+        m2, v2 = y.mean(1, keepdim=True), y.var(1, unbiased=False, keepdim=True)
+        y = (y - m2) / torch.sqrt(v2 + 1e-5) * gd + bd
+    assert torch.allclose(outs[1][2].double(), y[:, :T], atol=3e-2, rtol=1e-2)
+
+
 @pytest.mark.parametrize("S,exact", [(64, False), (128, False), (64, True), (40, False)])
 def test_patch_embed(S, exact):
     """tv swin features[0] + (fused) norm1 of the first block.  The tensor-core path (S % 64 == 0) rounds the conv weights to
