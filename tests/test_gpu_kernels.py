@@ -323,12 +323,13 @@ def test_instance_norm(twice):
 
 @pytest.mark.parametrize("B,T,C,twice,affine,n_pad", [(3, 1024, 256, True, False, 0), (2, 1024, 256, False, True, 0), (2, 256, 128, True, True, 0),
                                                       (3, 576, 256, False, False, 49), (2, 1024, 256, False, True, 64), (1, 1600, 64, False, False, 0),
-                                                      (2, 49, 256, True, False, 0), (1, 4096, 256, False, False, 0)])
+                                                      (2, 49, 256, True, False, 0), (1, 1021, 64, False, True, 0), (1, 4096, 256, False, False, 0)])
 def test_instnorm_one_call(B, T, C, twice, affine, n_pad):
     """mst_instnorm (statistics + application; csrc/instnorm_fused.cu: the slice through TMA into shared memory, read once) == the
     two-kernel sequence mst_instnorm_stats_affine -> mst_instnorm_apply_affine bit for bit: mean, rstd, the normalised padding value
     and the bf16 result; and against nn.InstanceNorm semantics in fp32.  Includes box heights other than 256 (576 = 3 x 192,
-    1600 = 8 x 200), shapes the fused kernel does not take (T = 49: no box height; T = 4096: too large), affine and padded variants."""
+    1600 = 8 x 200, 49 = one box), shapes the fused kernel does not take (T = 1021, a prime: no box height; T = 4096: too large), affine
+    and padded variants."""
     ops = _ops()
     from mastermetastyletransfer_b200 import _lib
     x = (_rand(B, T, C, seed=156, scale=1.7) + 0.3).cuda()
@@ -351,7 +352,7 @@ def test_instnorm_one_call(B, T, C, twice, affine, n_pad):
         outs.append((mean, rstd, y16, pad_norm))
     for name, a, b_ in zip(("mean", "rstd", "y16", "pad_norm"), outs[0], outs[1]):
         assert (a is None and b_ is None) or torch.equal(a, b_), name
-    assert bool(_lib.lib().mst_instnorm_fused_supported(T, C)) == (T not in (49, 4096))
+    assert bool(_lib.lib().mst_instnorm_fused_supported(T, C)) == (T not in (1021, 4096))
     # semantics (fp32): biased variance over the T tokens plus n_pad tokens of value pad_val
     xd = x.double()
     if n_pad:
