@@ -10,8 +10,9 @@ batch of 32 (images are independent: no data-path collective, weak scaling).
 `value`  : whole-job images/s with inputs resident in HBM, one CUDA-graph launch per step, timed with
            CUDA events between barrier+synchronize pairs, max over ranks.
 `e2e`    : same metric through the public host API at the reference's own image boundary (test_model.py:39-48,207):
-           pinned uint8 HWC images in -> H2D -> ToTensor/Normalize kernel -> graph -> clip*255 kernel -> D2H of the uint8
-           stylised images, every step (GraphedStylizer.stylize_many(u8=True), copies overlapped with the previous / next
+           pinned uint8 HWC images in -> H2D into the graph's input buffers -> graph (ToTensor/Normalize inside the patch-embedding
+           kernel's loads, clip*255 in the last convolution's epilogue) -> D2H of the uint8 stylised images, every step
+           (GraphedStylizer.stylize_many(u8=True): two graphs, one per staging slot, copies overlapped with the previous / next
            graph).  `e2e_f32` is the same through fp32 NCHW pinned tensors (4x the bytes).
 `roofline`: the tensor-core kernel family with the largest share of the step (chosen from the measured per-family times) --
            algorithmic FLOPs of its launches / their summed CUDA-event durations, against the measured sustained bf16 peak.
