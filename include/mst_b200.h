@@ -143,11 +143,14 @@ typedef struct MstMlp {
   const float* ln_g;       /* [C] or NULL */
   const float* ln_b;       /* [C] or NULL */
   int pre;
-  /* ---- optional LayerNorm of the result for the NEXT block (pre != 0 and C == 128, else MST_ERR_UNSUPPORTED) ----
-   *   out_bf16 = LayerNorm(out; lnn_g, lnn_b) eps 1e-5 instead of the plain bf16 copy of out (out_f32 is unchanged): the following
-   *   swin block's norm1 (tv swin_transformer.py SwinTransformerBlock.forward) without a launch of its own.  Both or neither. */
+  /* ---- optional LayerNorm of the result for the NEXT block (pre != 0, else MST_ERR_UNSUPPORTED) ----
+   *   out_bf16 rows < lnn_rows = LayerNorm(out; lnn_g, lnn_b) eps 1e-5 instead of the plain bf16 copy of out (rows >= lnn_rows keep
+   *   the copy; out_f32 is unchanged): the following block's norm1 (tv swin_transformer.py SwinTransformerBlock.forward;
+   *   style_transformer.py StyleDecoder norm1 on the content half of the encoded batch) without a launch of its own.
+   *   lnn_g / lnn_b: both or neither; lnn_rows == 0 means all M rows. */
   const float* lnn_g;      /* [C] or NULL */
   const float* lnn_b;      /* [C] or NULL */
+  int lnn_rows;
 } MstMlp;
 size_t mst_mlp_stream_bytes(int C);
 size_t mst_mlp_stream_bytes_pre(int C);

@@ -73,7 +73,7 @@ class MstMlp(C.Structure):
                 ("out_f32", C.c_void_p), ("out_bf16", C.c_void_p),
                 ("M", C.c_int), ("C", C.c_int), ("lda", C.c_int), ("ld_res", C.c_int), ("ld_out32", C.c_int), ("ld_out16", C.c_int),
                 ("bpre", C.c_void_p), ("mul", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("pre", C.c_int),
-                ("lnn_g", C.c_void_p), ("lnn_b", C.c_void_p)]
+                ("lnn_g", C.c_void_p), ("lnn_b", C.c_void_p), ("lnn_rows", C.c_int)]
 
 
 class MstTensorTable(C.Structure):

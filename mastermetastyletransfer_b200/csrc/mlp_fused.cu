@@ -96,10 +96,14 @@ struct MlpCore {
 static_assert(offsetof(MlpCore, pre) == offsetof(MstMlp, pre) && offsetof(MlpCore, bpre) == offsetof(MstMlp, bpre) &&
               offsetof(MlpCore, M) == offsetof(MstMlp, M) && sizeof(MlpCore) <= sizeof(MstMlp), "MlpCore must be a prefix of MstMlp");
 
-template <int C, bool PRE>
+// LNN (PRE only; its own instantiations so that the hot ones keep their register allocation): out_bf16 rows < lnn_rows receive
+// LayerNorm(out; lnn_g, lnn_b) -- the next block's norm1 -- instead of the plain bf16 copy (rows >= lnn_rows still get the copy).
+template <int C, bool PRE, bool LNN = false>
 __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore p, const int num_tiles,
                                                                   const __grid_constant__ CUtensorMap tm_out, const int tma_out, const int res_tma,
-                                                                  const float* __restrict__ lnn_g, const float* __restrict__ lnn_b) {
+                                                                  const float* __restrict__ lnn_g, const float* __restrict__ lnn_b,
+                                                                  const int lnn_rows) {
+  static_assert(!LNN || PRE, "the next-block LayerNorm rides on the pre-stage kernel");
   using Cfg = MlpCfg<C>;
   constexpr int NSTG = Cfg::NSTG;
   constexpr int ABUF = PRE ? 1 : Cfg::ABUF;
@@ -554,6 +558,33 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore 
       const bool wide_o32 = p.out_f32 && ((reinterpret_cast<uintptr_t>(p.out_f32) | (uintptr_t)(p.ld_out32 * 4)) & 31) == 0;
       const bool wide_o16 = p.out_bf16 && ((reinterpret_cast<uintptr_t>(p.out_bf16) | (uintptr_t)(p.ld_out16 * 2)) & 31) == 0;
       const uint32_t t2 = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL + part * CPW;
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      const bool ln_tile = LNN && tile * 128 < lnn_rows;  // (warp-uniform) any row of this tile is normalised
+      if constexpr (LNN && C == 256) {
+        // C = 256 has no idle shared memory or TMEM for an exchange between the four warps that share a row (the X tile is receiving the
+        // next tile's O, all 512 TMEM columns are live): every warp reads the WHOLE row's accumulator instead -- 8 TMEM loads, 1 % of
+        // a tile's time -- and computes the same shifted one-pass statistics
+        if (ln_tile) {
+          const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::ACC2_COL;
+          float K0 = 0.f, sm = 0.f, sq = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < C; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + cb, v);
+            tmem_wait_ld();
+            if (cb == 0) K0 = __uint_as_float(v[0]) + b2_s[0];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float d = (__uint_as_float(v[e]) + b2_s[cb + e]) - K0;
+              sm += d;
+              sq = fmaf(d, d, sq);
+            }
+          }
+          const float ms = sm * (1.0f / C);
+          ln_mean = K0 + ms;
+          ln_rstd = rsqrtf(fmaxf(sq * (1.0f / C) - ms * ms, 0.f) + 1e-5f);
+        }
+      }
 #pragma unroll 1
       for (int col0 = 0; col0 < CPW; col0 += 32) {
         uint32_t v[32];
@@ -566,8 +597,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore 
         }
         // lnn: out_bf16 = LayerNorm(out; lnn_g, lnn_b) -- the NEXT block's norm1 -- instead of a plain cast (C = 128: the warp's 32
         // columns of the row stay in registers between the statistics and the store)
-        bool lnn = false;
-        if constexpr (PRE && C == 128) lnn = lnn_g != nullptr;  // (the host passes lnn_g only together with tma_out: no early exit above)
+        // (the host instantiates LNN only together with tma_out: no early exit below)
         if (!row_ok && !(PRE && tma_out)) continue;  // (tensor store: whole warp takes part, rows past M are clipped by the map)
         const int n = part * CPW + col0;
         float x[32];
@@ -593,9 +623,8 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore 
             }
           }
         }
-        float ln_mean = 0.f, ln_rstd = 0.f;
-        if constexpr (PRE && C == 128) {
-          if (lnn) {
+        if constexpr (LNN && C == 128) {
+          if (ln_tile) {
             // as the LN2 stage above: local mean / centred M2 over this warp's 32 columns, one exchange with the three other warps of
             // the TMEM quadrant through the quadrant's own rows of the X tile (idle: this tile's fc1 has finished, the next tile's
             // projection epilogue -- these same four warps -- writes it after the second barrier), pairwise merge
@@ -657,8 +686,8 @@ __global__ void __launch_bounds__(ML_THREADS, 1) mlp_fused_kernel(const MlpCore 
         }
         if (p.out_bf16 && row_ok) {
           bf16* op = reinterpret_cast<bf16*>(p.out_bf16) + (long long)row * p.ld_out16 + n;
-          if constexpr (PRE && C == 128) {
-            if (lnn) {
+          if constexpr (LNN) {
+            if (row < lnn_rows) {
               const float4* g4 = reinterpret_cast<const float4*>(lnn_g + n);
               const float4* be4 = reinterpret_cast<const float4*>(lnn_b + n);
 #pragma unroll
@@ -787,15 +816,22 @@ static MlEncodeTiledFn ml_tma_encoder() {
   return fn;
 }
 
-template <int C, bool PRE>
-static int launch_mlp(const MstMlp& p, cudaStream_t st) {
+template <int C, bool PRE, bool LNN>
+static int launch_kernel(const MlpCore& core, unsigned grid, cudaStream_t st, int tiles, const CUtensorMap& tmap, int tma_out, int res_tma,
+                         const float* lnn_g, const float* lnn_b, int lnn_rows) {
   using Cfg = MlpCfg<C>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel<C, PRE, LNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  mlp_fused_kernel<C, PRE, LNN><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(core, tiles, tmap, tma_out, res_tma, lnn_g, lnn_b, lnn_rows);
+  return (int)cudaGetLastError();
+}
+
+template <int C, bool PRE>
+static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   const int tiles = (p.M + 127) / 128;
   const unsigned grid = (unsigned)(tiles < ml_num_sms() ? tiles : ml_num_sms());
   alignas(64) CUtensorMap tmap;
@@ -819,14 +855,19 @@ static int launch_mlp(const MstMlp& p, cudaStream_t st) {
   memcpy(&core, &p, sizeof(core));
   // next-block LayerNorm: in the tile-end epilogue when the tensor-store path runs (its statistics exchange needs whole warps),
   // else as a launch of its own after the kernel
-  const bool lnn_fused = p.lnn_g && PRE && C == 128 && tma_out;
-  mlp_fused_kernel<C, PRE><<<grid, ML_THREADS, Cfg::SMEM_BYTES, st>>>(core, tiles, tmap, tma_out, res_tma, lnn_fused ? p.lnn_g : nullptr,
-                                                                       lnn_fused ? p.lnn_b : nullptr);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  if (p.lnn_g && !lnn_fused) {
+  const int lnn_rows = p.lnn_g ? (p.lnn_rows > 0 && p.lnn_rows < p.M ? p.lnn_rows : p.M) : 0;
+  const bool lnn_fused = p.lnn_g && PRE && tma_out;
+  int rc;
+  if constexpr (PRE) {
+    rc = lnn_fused ? launch_kernel<C, true, true>(core, grid, st, tiles, tmap, tma_out, res_tma, p.lnn_g, p.lnn_b, lnn_rows)
+                   : launch_kernel<C, true, false>(core, grid, st, tiles, tmap, tma_out, res_tma, nullptr, nullptr, 0);
+  } else {
+    rc = launch_kernel<C, false, false>(core, grid, st, tiles, tmap, tma_out, res_tma, nullptr, nullptr, 0);
+  }
+  if (rc != 0) return rc;
+  if (p.lnn_g && !lnn_fused) {  // no tensor-store path (driver entry point missing / switched off): a LayerNorm launch over the rows
     if (!p.out_f32) return MST_ERR_UNSUPPORTED;
-    return mst_layernorm(p.out_f32, p.lnn_g, p.lnn_b, p.out_bf16, p.M, C, (void*)st);
+    return mst_layernorm(p.out_f32, p.lnn_g, p.lnn_b, p.out_bf16, lnn_rows, C, (void*)st);
   }
   return 0;
 }
@@ -860,9 +901,9 @@ extern "C" int mst_mlp_fused(const MstMlp* p, void* stream) {
   if ((p->out_f32 && p->ld_out32 % 4) || (p->out_bf16 && p->ld_out16 % 8) || (p->res && p->ld_res % 4)) return MST_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if ((p->lnn_g == nullptr) != (p->lnn_b == nullptr)) return MST_ERR_BAD_ARG;
-  if (p->lnn_g) {  // LayerNorm of the output for the next block: the pre-stage kernel at C = 128 only
-    if (!p->out_bf16 || ((reinterpret_cast<uintptr_t>(p->lnn_g) | reinterpret_cast<uintptr_t>(p->lnn_b)) & 15)) return MST_ERR_BAD_ARG;
-    if (!p->pre || p->C != 128) return MST_ERR_UNSUPPORTED;
+  if (p->lnn_g) {  // LayerNorm of the output for the next block: the pre-stage kernel only
+    if (!p->out_bf16 || p->lnn_rows < 0 || ((reinterpret_cast<uintptr_t>(p->lnn_g) | reinterpret_cast<uintptr_t>(p->lnn_b)) & 15)) return MST_ERR_BAD_ARG;
+    if (!p->pre) return MST_ERR_UNSUPPORTED;
   }
   if (p->pre) {
     // attention-output stage in front: needs the residual / blend operand, the x1 destination and 16-byte aligned vectors

@@ -103,7 +103,9 @@ def _swin_block(bw: dict, x32: torch.Tensor, ws_: Workspace, Bt: int, H: int, W:
     """x += attn(LN1(x)); x += mlp(LN2(x)) on the fp32 residual stream x32 [T, C] (in place).
     ln1_done: the producer of x32 already wrote LN1(x) into the block's `ln` buffer (patch embedding, or the previous block).
     next_ln: (gamma, beta) of the FOLLOWING block's norm1 (same tag, so the same `ln` buffer): when the MLP kernel can apply it in
-    its output epilogue it does, and the block returns True -- call the next block with ln1_done=True."""
+    its output epilogue it does, and the block returns True -- call the next block with ln1_done=True.  (Asked for at C = 128 only:
+    the C = 256 instantiation has no idle on-chip memory for the row-statistics exchange, every warp re-reads the whole row from TMEM,
+    and that cost more (+19 us per launch) than the LayerNorm launch it saves (14-17 us) -- DESIGN.md section 8.)"""
     C, heads = bw["C"], bw["heads"]
     T = Bt * H * W
     ln = ws_.bf16(tag + "ln", T, C)

@@ -609,7 +609,7 @@ def pack_mlp(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Ten
 
 
 def mlp_next_ln_supported(C_: int) -> bool:
-    return C_ == 128
+    return C_ in (128, 256)
 
 
 def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out_bf16=None,
@@ -617,7 +617,8 @@ def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out
     """out = res + fc2(gelu(fc1(A) + b1)) + b2, hidden activation kept on chip.
     pre=True (pm packed with wpre): x1 = res (*mul) + A.Wpre^T + bpre; out = x1 + mlp([LayerNorm](x1)) -- the whole
     attention-output half of a transformer block in one kernel (see include/mst_b200.h).
-    next_ln = (gamma, beta) (pre=True, C = 128 -- mlp_next_ln_supported): out_bf16 = LayerNorm(out), the next block's norm1."""
+    next_ln = (gamma, beta[, rows]) (pre=True): out_bf16 = LayerNorm(out), the next block's norm1, on the first `rows` rows (default
+    all); the other rows keep the plain bf16 copy."""
     g = MstMlp()
     g.A, g.Wstream = _ptr(A, torch.bfloat16, "A"), pm.stream.data_ptr()
     g.b1, g.b2 = _ptr(pm.b1, torch.float32, "b1"), _ptr(pm.b2, torch.float32, "b2")
@@ -637,8 +638,9 @@ def mlp_fused(A, pm: PackedMlp, M: int, *, lda=None, res=None, out_f32=None, out
         raise ValueError("mlp_fused: mul / ln / a pre-packed stream need pre=True")
     if next_ln is not None:
         if not (pre and mlp_next_ln_supported(pm.C)) or out_bf16 is None:
-            raise ValueError("mlp_fused: next_ln needs pre=True, C = 128 and out_bf16")
+            raise ValueError("mlp_fused: next_ln needs pre=True and out_bf16")
         g.lnn_g, g.lnn_b = _ptr(next_ln[0], torch.float32, "next_ln gamma"), _ptr(next_ln[1], torch.float32, "next_ln beta")
+        g.lnn_rows = int(next_ln[2]) if len(next_ln) > 2 else 0
     _launch("mst_mlp_fused", lambda: _lib.lib().mst_mlp_fused(C.byref(g), _stream()), flops=flops,
             desc=f"M={M} C={pm.C} res={res is not None} o32={out_f32 is not None} o16={out_bf16 is not None} pre={int(pre)} ln={ln_g is not None} mul={mul is not None} next_ln={next_ln is not None}")
 

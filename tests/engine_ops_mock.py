@@ -134,12 +134,12 @@ def gemm(A, pm, M, *, lda=None, act=ops.ACT_NONE, res=None, mul=None, out_f32=No
 
 
 def mlp_next_ln_supported(C_):
-    return C_ == 128
+    return C_ in (128, 256)
 
 
 def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=False, mul=None, ln_g=None, ln_b=None, next_ln=None):
     C = pm.C
-    assert next_ln is None or (pre and C == 128 and out_bf16 is not None)
+    assert next_ln is None or (pre and out_bf16 is not None)
     a = _rows(A, M, C, C if lda is None else lda).float()
     if pre:
         assert pm.wpre is not None
@@ -156,7 +156,10 @@ def mlp_fused(A, pm, M, *, lda=None, res=None, out_f32=None, out_bf16=None, pre=
     if out_f32 is not None:
         out_f32[:M].copy_(y)
     if out_bf16 is not None:
-        out_bf16[:M].copy_(y if next_ln is None else F.layer_norm(y, (C,), next_ln[0], next_ln[1]))
+        out_bf16[:M].copy_(y)
+        if next_ln is not None:
+            rows = next_ln[2] if len(next_ln) > 2 and next_ln[2] else M
+            out_bf16[:rows].copy_(F.layer_norm(y[:rows], (C,), next_ln[0], next_ln[1]))
 
 
 def layernorm(x, gamma, beta, y, rows, Cdim):

@@ -547,23 +547,24 @@ def test_proj_mlp_fused(M, C, ln, mul):
     ops.mlp_fused(A.cuda(), pm, M, res=res_dev, out_f32=y, pre=True, mul=m.cuda() if mul else None,
                   ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None)
     assert torch.equal(y, x) and torch.equal(res_dev.cpu(), res)
-    # MstMlp::lnn_g / lnn_b: out_bf16 = LayerNorm(out) for the next block (C = 128), from the tile-end epilogue.  out_f32 keeps its
-    # bits; the bf16 tensor matches a separate LayerNorm of it (different summation order: one bf16 ulp of slack).
-    if C == 128:
-        g2, be2 = (1 + 0.1 * _rand(C, seed=91)).cuda(), (0.1 * _rand(C, seed=92)).cuda()
-        for inplace in (True, False):
-            src = res.cuda()
-            y2 = src if inplace else torch.empty(M, C, device="cuda")
-            ln16 = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
-            ops.mlp_fused(A.cuda(), pm, M, res=src, out_f32=y2, out_bf16=ln16, pre=True, mul=m.cuda() if mul else None,
-                          ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None, next_ln=(g2, be2))
-            assert torch.equal(y2, x)
-            want = F.layer_norm(x, (C,), g2, be2)
-            assert torch.allclose(ln16.float(), want, atol=2e-2, rtol=1e-2), (ln16.float() - want).abs().max()
-    else:
-        assert not ops.mlp_next_ln_supported(C)
-        with pytest.raises(ValueError):
-            ops.mlp_fused(A.cuda(), pm, M, res=x, out_f32=x, out_bf16=out16, pre=True, next_ln=(x[0], x[1]))
+    # MstMlp::lnn_g / lnn_b / lnn_rows: out_bf16 = LayerNorm(out) for the next block on the first lnn_rows rows (the others keep the
+    # bf16 copy), from the tile-end epilogue.  out_f32 keeps its bits; the bf16 tensor matches a separate LayerNorm of it (different
+    # summation order: one bf16 ulp of slack).
+    assert ops.mlp_next_ln_supported(C)
+    g2, be2 = (1 + 0.1 * _rand(C, seed=91)).cuda(), (0.1 * _rand(C, seed=92)).cuda()
+    for inplace, rows in ((True, None), (False, M // 3), (True, 128 * (M // 256))):
+        src = res.cuda()
+        y2 = src if inplace else torch.empty(M, C, device="cuda")
+        ln16 = torch.full((M, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.mlp_fused(A.cuda(), pm, M, res=src, out_f32=y2, out_bf16=ln16, pre=True, mul=m.cuda() if mul else None,
+                      ln_g=g.cuda() if ln else None, ln_b=be.cuda() if ln else None, next_ln=(g2, be2) if rows is None else (g2, be2, rows))
+        assert torch.equal(y2, x)
+        n_ln = M if rows is None or rows == 0 else rows
+        want = F.layer_norm(x[:n_ln], (C,), g2, be2)
+        assert torch.allclose(ln16[:n_ln].float(), want, atol=2e-2, rtol=1e-2), (ln16[:n_ln].float() - want).abs().max()
+        assert torch.equal(ln16[n_ln:], out16[n_ln:])   # plain bf16 copy of out beyond lnn_rows
+    with pytest.raises(ValueError):
+        ops.mlp_fused(A.cuda(), pm, M, res=x, out_f32=x, pre=True, next_ln=(g2, be2))   # needs out_bf16
 
 
 @pytest.mark.parametrize("B,H,C,ws,shift", [(1, 8, 256, 8, 0), (2, 32, 256, 8, 4), (1, 24, 256, 8, 4), (2, 32, 256, 7, 4), (1, 16, 256, 7, 3),
