@@ -1,9 +1,8 @@
 // Patch embedding of the torchvision Swin encoder (features[0]: Conv2d(3, 128, 4, 4) + LayerNorm(128)) with the first block's
-// norm1 fused behind it, on tcgen05 (round 2).  Measured: 44-45 us per launch at batch 32 / 256^2, the SAME as the mma.sync
-// kernel of norm_misc.cu it replaces (43-44 us), with 8 or with 16 epilogue warps: the kernel writes 100 MB (fp32 x + bf16
-// LN1(x)) for 25 MB read, and a write-dominated stream tops out near half of the copy rate the roofline is quoted against
-// (a copy moves 3.3 TB/s in each direction) -- it is write-bound at ~2.3 TB/s of stores, not issue-bound as the ncu stall
-// list of the old kernel (`mio_throttle`) suggested.  Kept because it takes the last mma.sync kernel off the inference path.
+// norm1 fused behind it, on tcgen05 (round 2).  The kernel writes 100 MB (fp32 x + bf16 LN1(x)) for 25 MB read.  With each lane
+// storing its own token row (32-byte sectors of 32 different rows per instruction) it took 44-49 us per launch at batch 32 / 256^2,
+// the SAME as the mma.sync kernel of norm_misc.cu it replaces, with 8 or with 16 epilogue warps -- which read as "write-bound at
+// 2.3 TB/s"; it was the store PATTERN: through TMA tensor stores (below) the same kernel takes 37 us (2.7 TB/s of stores).
 //
 // The 4x4 / stride-4 conv is a [tokens x 48] . [48 x 128] GEMM, k = ci*16 + ky*4 + kx.  Per 128-token tile:
 //   warps 16-19 producers: thread = token; twelve 16-byte loads straight from the NCHW image (one per input channel and patch
@@ -15,10 +14,18 @@
 //               and pass, is what the kernel costs, so it gets the warps): thread = token, the whole 128-channel row is in the
 //               thread's TMEM lane, so both LayerNorms are thread-local (no shuffles, no exchange): shifted one-pass statistics,
 //               then  x = LN0(acc + bias) -> fp32 [T,128]  and  y = LN1(x) -> bf16 [T,128]  with the parameters read as
-//               warp-uniform shared-memory broadcasts; rows leave as 32-byte sectors per lane
+//               warp-uniform shared-memory broadcasts; rows leave through TMA tensor stores (32-byte sectors per lane without them)
+//
+// Output through TMA tensor stores (end of round 2): a lane owns a token row, so direct stores touch 32 different rows per
+// instruction.  Each epilogue warp stages its [32 tokens x 32 channels] block in a private 4 KB slab (fp32: 128-byte rows, 128B
+// swizzle; bf16: 64-byte rows, 64B swizzle -- both conflict-free for row-per-lane 16-byte writes) and one lane hands it to the TMA
+// engine; rows past the last token are clipped by the tensor map.  The weight tile is stored once (both k-blocks read the same 16 KB),
+// which pays for the slabs.
 #include "../../include/mst_b200.h"
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mst {
 
@@ -30,7 +37,14 @@ constexpr int PT_MMA_WARP = PT_PROD_WARP0 + PT_PROD_WARPS;  // 12
 constexpr int PT_THREADS = (PT_MMA_WARP + 1) * 32;          // 672
 constexpr int PT_KB_BYTES = 128 * 128;                      // one [128 rows x 64 k] bf16 k-block
 constexpr int PT_A_BYTES = 2 * PT_KB_BYTES;                 // hi | lo
-constexpr int PT_SMEM_BYTES = 1024 + PT_NBUF * PT_A_BYTES + PT_A_BYTES;  // the A buffers + the weight tile (W | W)
+constexpr int PT_SLAB_BYTES = 4096;                         // one staging slab per epilogue warp
+constexpr int PT_SMEM_BYTES = 1024 + PT_NBUF * PT_A_BYTES + PT_KB_BYTES + PT_EPI_WARPS * PT_SLAB_BYTES;  // A buffers + weight tile + slabs
+
+MST_DEVINL void pt_tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+MST_DEVINL void pt_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+MST_DEVINL void pt_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // uint8 [B,S,S,3] image input (img8 != nullptr): the producers read the interleaved bytes and apply ToTensor + Normalize themselves
 // (the values images_u8_to_nchw_kernel would have written, norm_misc.cu), so the fp32 NCHW image never exists in HBM.
@@ -45,7 +59,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
                                                                       const float* __restrict__ beta, float* __restrict__ out,
                                                                       const float* __restrict__ gamma1, const float* __restrict__ beta1,
                                                                       bf16* __restrict__ y16, int S, int n_tiles, long long total,
-                                                                      PeU8 u8) {
+                                                                      PeU8 u8, const __grid_constant__ CUtensorMap tm_x,
+                                                                      const __grid_constant__ CUtensorMap tm_y, int tma) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float lut[3][256];  // u8 images: ((v / 255) - mean_c) / std_c for every byte value, in images_u8_to_nchw's operation order
   __shared__ uint64_t a_full[PT_NBUF], a_empty[PT_NBUF], acc_full[PT_NBUF], acc_empty[PT_NBUF];
@@ -78,10 +93,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
       if (u8.normalize) v = __fdiv_rn(__fsub_rn(v, mc), sc);
       lut[c][i & 255] = v;
     }
-  // weight tile: row n (output channel), k-block 0 = W[n][0..47] then zeros, k-block 1 the same again (multiplies the lo parts)
-  for (int i = threadIdx.x; i < 128 * 16; i += PT_THREADS) {
-    const int n = i >> 4, c = i & 15;  // 16-byte chunk c of the row's 2 x 64 k
-    const int kb = c >> 3, ch = c & 7;
+  // weight tile: row n (output channel) = W[n][0..47] then zeros; both k-blocks of A (hi parts, lo parts) multiply this one tile
+  for (int i = threadIdx.x; i < 128 * 8; i += PT_THREADS) {
+    const int n = i >> 3, ch = i & 7;  // 16-byte chunk ch of the row's 64 k
+    const int kb = 0;
     uint32_t pk[4] = {0u, 0u, 0u, 0u};
     if (ch < 6) {
 #pragma unroll
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
       for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_pred(tmem_base + buf * 128, umma_desc_sw128(ab + kb * PT_KB_BYTES + k * 32), umma_desc_sw128(b_base + kb * PT_KB_BYTES + k * 32),
+          umma_bf16_pred(tmem_base + buf * 128, umma_desc_sw128(ab + kb * PT_KB_BYTES + k * 32), umma_desc_sw128(b_base + k * 32),
                          idesc, (kb | k) != 0);
       umma_commit_pred(smem_u32(&a_empty[buf]));
       umma_commit_pred(smem_u32(&acc_full[buf]));
@@ -204,6 +219,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
     const int quad = warp & 3, grp = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t slab = b_base + PT_KB_BYTES + (uint32_t)warp * PT_SLAB_BYTES;
     for (int lt = grp; lt < n_my; lt += PT_NBUF) {
       const long long tile = blockIdx.x + (long long)lt * gridDim.x;
       const int buf = lt % PT_NBUF, u = lt / PT_NBUF;  // buf == grp
@@ -248,7 +264,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
           t1 += d;
           t2 = fmaf(d, d, t2);
         }
-        if (tok < total) {
+        if (tma) {  // [32 tokens x 32 channels] fp32 through the slab: 128-byte rows, 128B swizzle
+          if (lane == 0) pt_bulk_wait_read();  // the slab's previous store has been read
+          __syncwarp();
+          const uint32_t srow = slab + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((uint32_t)(q ^ (lane & 7)) << 4)), "f"(x[4 * q]),
+                         "f"(x[4 * q + 1]), "f"(x[4 * q + 2]), "f"(x[4 * q + 3]) : "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            pt_tma_store_2d(&tm_x, slab, c0, (int)(tile * 128 + quad * 32));
+            pt_bulk_commit();
+          }
+        } else if (tok < total) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) st_global_256f(op + c0 + 8 * e, x + 8 * e);
         }
@@ -281,7 +311,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
             __nv_bfloat162 hh = __floats2bfloat162_rn(z[0], z[1]);
             pk[e] = *reinterpret_cast<uint32_t*>(&hh);
           }
-          if (tok < total) {
+          if (tma) {  // [32 tokens x 32 channels] bf16: 64-byte rows, 64B swizzle (16-byte chunk ^= (row >> 1) & 3)
+            if (lane == 0) pt_bulk_wait_read();
+            __syncwarp();
+            const uint32_t srow = slab + (uint32_t)lane * 64u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((uint32_t)(q ^ ((lane >> 1) & 3)) << 4)), "r"(pk[4 * q]),
+                           "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              pt_tma_store_2d(&tm_y, slab, c0, (int)(tile * 128 + quad * 32));
+              pt_bulk_commit();
+            }
+          } else if (tok < total) {
             uint32_t a8[8], b8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { a8[e] = pk[e]; b8[e] = pk[8 + e]; }
@@ -295,6 +339,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
         if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
       }
     }
+    if (tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
     tc_fence_before();
   }
   __syncthreads();
@@ -302,6 +347,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) patch_embed_tc_kernel(const flo
     tc_fence_after();
     tmem_dealloc(tmem_base, 128 * PT_NBUF);
   }
+}
+
+typedef CUresult (*PtEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PtEncodeTiledFn pt_tma_encoder() {
+  static PtEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PtEncodeTiledFn>(q);
+  }
+  return fn;
 }
 
 // Called first by mst_patch_embed_ln (norm_misc.cu); handled = false leaves the call to the other kernels.
@@ -336,7 +396,28 @@ int patch_embed_tc_try(const float* img, const float* w, const float* b, const f
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  patch_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM_BYTES, st>>>(img, w, b, gamma, beta, x, gamma1, beta1, y16, S, (int)tiles, total, u8);
+  // tensor maps of the two outputs ([128 channels, tokens], box 32 x 32); without the driver entry point the lanes store directly
+  alignas(64) CUtensorMap tm_x, tm_y;
+  memset(&tm_x, 0, sizeof(tm_x));
+  memset(&tm_y, 0, sizeof(tm_y));
+  int tma = 0;
+  static int tma_allow = -1;
+  if (tma_allow < 0) { const char* e = getenv("MST_PATCH_EMBED_TMA"); tma_allow = e ? atoi(e) : 1; }
+  if (tma_allow && total * 128 <= 0x7fffffffLL * 64) {
+    if (PtEncodeTiledFn enc = pt_tma_encoder()) {
+      const cuuint64_t gdim[2] = {128, (cuuint64_t)total};
+      const cuuint32_t box[2] = {32, 32};
+      const cuuint32_t estr[2] = {1, 1};
+      const cuuint64_t gs32[1] = {128 * 4}, gs16[1] = {128 * 2};
+      tma = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, gdim, gs32, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      if (tma && y16)
+        tma = enc(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y16, gdim, gs16, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
+  patch_embed_tc_kernel<<<grid, PT_THREADS, PT_SMEM_BYTES, st>>>(img, w, b, gamma, beta, x, gamma1, beta1, y16, S, (int)tiles, total, u8, tm_x, tm_y,
+                                                                 tma);
   return (int)cudaGetLastError();
 }
 
