@@ -75,11 +75,23 @@ MST_DEVINL void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint
                : "memory");
 }
 
-template <int BN, bool EXT, bool TMA>
+MST_DEVINL void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+constexpr int TMO_SLAB_BYTES = 4096;  // one output staging slab per epilogue warp
+
+// TMO = true (its own instantiation: plain epilogues with exactly one output, no residual): the output leaves through TMA tensor
+// stores.  A lane owns a row, so direct stores touch 32 different rows per instruction (the pattern that bounded the patch embedding
+// and the fused MLP before their stores went through TMA); here each epilogue warp stages its [32 rows x 32 columns] block in a 4 KB
+// slab at slab_off (fp32: 128-byte rows, 128B swizzle; bf16: 64-byte rows, 64B swizzle) and one lane issues the store.  Rows past M
+// are clipped by the tensor map tmo_ ([N columns, M rows] of the output, row stride ld_out).
+template <int BN, bool EXT, bool TMA, bool TMO = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore p, const typename ExtSel<EXT>::type x_,
                                                                   const __grid_constant__ typename TmaSel<TMA>::type tm_, const int num_tiles,
-                                                                  const int res_stages, const int wsplit) {
+                                                                  const int res_stages, const int wsplit,
+                                                                  const __grid_constant__ typename TmaSel<TMO>::type tmo_, const int slab_off) {
   using Cfg = GemmCfg<BN>;
+  static_assert(!TMO || (!EXT && Cfg::COLS_PER_WARP >= 32), "TMA output stores: inference epilogue, 32-column chunks");
   const bool resident = res_stages > 0;
   const int STAGES = resident ? res_stages : Cfg::STAGES;
 
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
           }
-          if (!row_ok) continue;
+          if (!TMO && !row_ok) continue;  // (TMO: the whole warp takes part in the tensor store; rows past M are clipped by the map)
           const int n = nbase + col0;
           float x[CH];
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + n);  // n % 16 == 0: LDS.128 broadcasts (4x fewer LSU wavefronts)
@@ -548,7 +560,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
               }
             }
           }
-          if (p.out_nchw) {
+          if constexpr (TMO) {
+            const uint32_t slab = smem_base + (uint32_t)slab_off + (uint32_t)warp * TMO_SLAB_BYTES;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slab's previous store has been read
+            __syncwarp();
+            if (p.out_f32) {
+              const uint32_t srow = slab + (uint32_t)lane * 128u;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((uint32_t)(q ^ (lane & 7)) << 4)), "f"(x[4 * q]),
+                             "f"(x[4 * q + 1]), "f"(x[4 * q + 2]), "f"(x[4 * q + 3]) : "memory");
+            } else {
+              const uint32_t srow = slab + (uint32_t)lane * 64u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(x[8 * q + 2 * e], x[8 * q + 2 * e + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((uint32_t)(q ^ ((lane >> 1) & 3)) << 4)), "r"(pk[0]),
+                             "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmo_, slab, n, m0 + quad * 32);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (p.out_nchw) {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (n + j < p.n_real) p.out_f32[nchw_base + (long long)(n + j) * hw] = x[j];
@@ -595,6 +637,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmCore
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
     }
+    if (TMO && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA exits
     tc_fence_before();
   }
   __syncthreads();
@@ -665,12 +708,57 @@ static int launch_gemm_ext(const MstGemm& g, cudaStream_t st, const typename Tma
   GemmCore core;
   static_assert(sizeof(GemmCore) <= sizeof(MstGemm), "GemmCore must be a prefix of MstGemm");
   memcpy(&core, &g, sizeof(GemmCore));
+  if constexpr (BN == 256 && !EXT && TMA) {
+    // output through TMA tensor stores (see the kernel): plain linear layers with exactly one output and no residual
+    static int tmo_allow = -1;
+    if (tmo_allow < 0) { const char* e = getenv("MST_GEMM_TMA_OUT"); tmo_allow = e ? atoi(e) : 1; }
+    const bool one_out = (g.out_f32 != nullptr) != (g.out_bf16 != nullptr);
+    const int slabs = NUM_EPI_WARPS * TMO_SLAB_BYTES;
+    int rs = res_stages;
+    size_t smem_o = 0;
+    if (res_stages > 0) {
+      const int fit = (int)((MAX_SMEM - 1024 - slab - slabs) / A_STAGE_BYTES);
+      if (rs > fit) rs = fit;
+      smem_o = 1024 + (size_t)slab + (size_t)rs * A_STAGE_BYTES + slabs;
+    } else {
+      smem_o = (size_t)Cfg::SMEM_BYTES + slabs;
+    }
+    if (tmo_allow && wsplit == 0 && g.a_mode == MST_A_PLAIN && one_out && !g.out_nchw && !g.res && !g.mul && (res_stages == 0 || rs >= 3) &&
+        smem_o <= (size_t)MAX_SMEM) {
+      if (EncodeTiledFn enc = tma_encoder()) {
+        alignas(64) CUtensorMap tmo;
+        memset(&tmo, 0, sizeof(tmo));
+        const bool f32 = g.out_f32 != nullptr;
+        void* optr = f32 ? (void*)g.out_f32 : (void*)g.out_bf16;
+        const int ld = f32 ? g.ld_out32 : g.ld_out16;
+        const cuuint64_t gdim[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+        const cuuint64_t gstride[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+        const cuuint32_t box[2] = {32, 32};
+        const cuuint32_t estr[2] = {1, 1};
+        if ((reinterpret_cast<uintptr_t>(optr) & 15) == 0 && gstride[0] % 16 == 0 &&
+            enc(&tmo, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, optr, gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+          static bool attr_o = false;
+          if (!attr_o) {
+            cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            attr_o = true;
+          }
+          GemmNoExt none;
+          gemm_tc_kernel<BN, false, true, true><<<grid, GEMM_THREADS, smem_o, st>>>(core, none, tmap, (int)tiles, rs, wsplit, tmo,
+                                                                                     (int)(smem_o - 1024 - slabs));
+          return (int)cudaGetLastError();
+        }
+      }
+    }
+  }
   typename ExtSel<EXT>::type ext;
   if constexpr (EXT) {
     ext.gate = g.gate; ext.add16 = g.add16; ext.out_pre16 = g.out_pre16; ext.row_scale = g.row_scale;
     ext.gate_mode = g.gate_mode; ext.ld_gate = g.ld_gate; ext.rows_per_scale = g.rows_per_scale; ext.conv_full = g.conv_full;
   }
-  gemm_tc_kernel<BN, EXT, TMA><<<grid, GEMM_THREADS, smem, st>>>(core, ext, tmap, (int)tiles, res_stages, wsplit);
+  gemm_tc_kernel<BN, EXT, TMA><<<grid, GEMM_THREADS, smem, st>>>(core, ext, tmap, (int)tiles, res_stages, wsplit, TmaNone{}, 0);
   return (int)cudaGetLastError();
 }
 
